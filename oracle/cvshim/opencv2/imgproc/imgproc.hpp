@@ -1,0 +1,2 @@
+// oracle-build stand-in (see cvshim_core.hpp)
+#include "../cvshim_core.hpp"

@@ -1,0 +1,424 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into the product library.
+//
+// C entry points around the UNMODIFIED reference translation units (compiled where they lie under
+// /root/reference by oracle/Makefile into oracle/_ref/libopref_{f32,f64}.so).  Used by tests/ and by
+// bench.py's cpu_baseline / --impl reference legs to (1) pin the C restatement in oracle/opb_oracle.c,
+// (2) generate tests/golden/*.npz and (3) time the reference's own CPU path.
+//
+// Reference entry points exercised:
+//   integration::CubeHandler::{IntegrateImage,PrepareCubes,ComputeBounding,ExtractTriangleMesh,GetCubeMap}
+//       src/Integration/CubeHandler.cpp:9-44,116-214, CubeHandler.h:36,141,339,349-356
+//   registration::{PointToPlane,PointToPoint,EstimateRigidTransformationPointToPlane,CountInliers}
+//       src/Registration/ICP.cpp:9-224
+//   geometry::{TransformPoints,EstimateRigidTransformation,Se3ToSE3}  src/Geometry/Geometry.cpp:9-27,107-151
+//   geometry::PointCloud::{LoadFromDepth,EstimateNormals}             src/Geometry/PointCloud.cpp:72-144
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "Camera/Camera.h"
+#include "Geometry/Geometry.h"
+#include "Geometry/KDTree.h"
+#include "Geometry/PointCloud.h"
+#include "Geometry/TriangleMesh.h"
+#include "Integration/CubeHandler.h"
+#include "Integration/Frustum.h"
+#include "Integration/MarchingCube.h"
+#include "Registration/ICP.h"
+
+using namespace one_piece;
+typedef geometry::scalar scalar;
+
+namespace one_piece
+{
+namespace registration
+{
+// external linkage in ICP.cpp:9 but not declared in ICP.h
+double CountInliers(const geometry::Point3List &source, const geometry::Point3List target,
+                    const std::vector<int> &correspondence_index, const geometry::TransformationMatrix &T,
+                    double threshold, geometry::FMatchSet &inliers);
+} // namespace registration
+} // namespace one_piece
+
+namespace
+{
+struct RefVolume
+{
+    integration::CubeHandler handler;
+    camera::PinholeCamera cam;
+    geometry::TriangleMesh mesh;
+    // CubeHandler keeps camera/c_para protected; expose what the harness needs
+};
+// access to protected members for read-only inspection (bounding box, cube list)
+struct HandlerPeek : public integration::CubeHandler
+{
+    const integration::CubeMap &map() const { return cube_map; }
+};
+
+geometry::TransformationMatrix PoseFromColMajor(const float *p)
+{
+    geometry::TransformationMatrix T;
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 4; ++r) T(r, c) = (scalar)p[c * 4 + r];
+    return T;
+}
+void PoseToColMajor(const geometry::TransformationMatrix &T, double *p)
+{
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 4; ++r) p[c * 4 + r] = (double)T(r, c);
+}
+cv::Mat WrapDepth(const void *depth, int is_u16, int w, int h)
+{
+    return cv::Mat(h, w, is_u16 ? CV_16UC1 : CV_32FC1, const_cast<void *>(depth));
+}
+cv::Mat WrapBgr(const uint8_t *bgr, int w, int h) { return cv::Mat(h, w, CV_8UC3, const_cast<uint8_t *>(bgr)); }
+void ToList(const float *xyz, size_t n, geometry::Point3List &out)
+{
+    out.resize(n);
+    for (size_t i = 0; i < n; ++i) out[i] = geometry::Point3((scalar)xyz[3 * i], (scalar)xyz[3 * i + 1], (scalar)xyz[3 * i + 2]);
+}
+double Now()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+} // namespace
+
+extern "C"
+{
+int ref_scalar_bytes() { return (int)sizeof(scalar); }
+// the reference prints a line per call (DEBUG_MODE 1); keep test logs readable
+void ref_set_quiet(int quiet)
+{
+    if (quiet) std::cout.setstate(std::ios_base::failbit);
+    else std::cout.clear();
+}
+
+void *ref_volume_create(float fx, float fy, float cx, float cy, int w, int h, float depth_scale, float voxel_res,
+                        float truncation, float near_plane, float far_plane)
+{
+    RefVolume *v = new RefVolume();
+    v->cam = camera::PinholeCamera(fx, fy, cx, cy, w, h, depth_scale);
+    v->handler.SetCamera(v->cam);
+    v->handler.SetVoxelResolution(voxel_res);
+    v->handler.SetTruncation(truncation);
+    v->handler.SetNearPlane(near_plane);
+    v->handler.SetFarPlane(far_plane);
+    return v;
+}
+void ref_volume_destroy(void *h) { delete (RefVolume *)h; }
+void ref_volume_clear(void *h) { ((RefVolume *)h)->handler.Clear(); }
+
+// CubeHandler::IntegrateImage (CubeHandler.cpp:197-210). Returns seconds spent inside the call.
+double ref_volume_integrate(void *h, const void *depth, int is_u16, const uint8_t *bgr, const float *pose_cm)
+{
+    RefVolume *v = (RefVolume *)h;
+    int w = v->cam.GetWidth(), hh = v->cam.GetHeight();
+    cv::Mat d = WrapDepth(depth, is_u16, w, hh), c = WrapBgr(bgr, w, hh);
+    geometry::TransformationMatrix pose = PoseFromColMajor(pose_cm);
+    double t0 = Now();
+    v->handler.IntegrateImage(d, c, pose);
+    return Now() - t0;
+}
+// CubeHandler::ComputeBounding (CubeHandler.cpp:116-145)
+void ref_volume_bounding(void *h, const void *depth, int is_u16, const float *pose_cm, double *max_pos, double *min_pos)
+{
+    RefVolume *v = (RefVolume *)h;
+    int w = v->cam.GetWidth(), hh = v->cam.GetHeight();
+    cv::Mat d = WrapDepth(depth, is_u16, w, hh);
+    geometry::Point3 mx, mn;
+    v->handler.ComputeBounding(d, PoseFromColMajor(pose_cm), mx, mn);
+    for (int i = 0; i < 3; ++i) { max_pos[i] = mx(i); min_pos[i] = mn(i); }
+}
+// CubeHandler::PrepareCubes (CubeHandler.cpp:147-196): allocates absent cubes and returns the frame's list
+long ref_volume_prepare_cubes(void *h, const void *depth, int is_u16, const float *pose_cm, int32_t *ids, long cap)
+{
+    RefVolume *v = (RefVolume *)h;
+    int w = v->cam.GetWidth(), hh = v->cam.GetHeight();
+    cv::Mat d = WrapDepth(depth, is_u16, w, hh);
+    std::vector<integration::CubeID> list;
+    v->handler.PrepareCubes(d, PoseFromColMajor(pose_cm), list);
+    long n = (long)list.size();
+    for (long i = 0; i < n && i < cap; ++i)
+        for (int k = 0; k < 3; ++k) ids[3 * i + k] = list[i](k);
+    return n;
+}
+long ref_volume_num_cubes(void *h)
+{
+    return (long)static_cast<HandlerPeek *>(&((RefVolume *)h)->handler)->map().size();
+}
+// ids: n*3 int32; voxels: n*512*5 float (sdf, weight, c0, c1, c2) in the reference's voxel order x+8y+64z
+void ref_volume_download(void *h, int32_t *ids, float *voxels)
+{
+    const integration::CubeMap &m = static_cast<HandlerPeek *>(&((RefVolume *)h)->handler)->map();
+    size_t i = 0;
+    for (auto it = m.begin(); it != m.end(); ++it, ++i)
+    {
+        for (int k = 0; k < 3; ++k) ids[3 * i + k] = it->first(k);
+        float *dst = voxels + i * 512 * 5;
+        for (int j = 0; j < 512; ++j)
+        {
+            const integration::TSDFVoxel &vx = it->second.voxels[j];
+            dst[5 * j + 0] = (float)vx.sdf;
+            dst[5 * j + 1] = (float)vx.weight;
+            dst[5 * j + 2] = (float)vx.color(0);
+            dst[5 * j + 3] = (float)vx.color(1);
+            dst[5 * j + 4] = (float)vx.color(2);
+        }
+    }
+}
+// replaces the whole map (CubeHandler::SetCubeMap, CubeHandler.h:344)
+void ref_volume_upload(void *h, const int32_t *ids, const float *voxels, long n)
+{
+    integration::CubeMap m;
+    for (long i = 0; i < n; ++i)
+    {
+        integration::CubeID id(ids[3 * i], ids[3 * i + 1], ids[3 * i + 2]);
+        integration::VoxelCube c(id);
+        const float *src = voxels + (size_t)i * 512 * 5;
+        for (int j = 0; j < 512; ++j)
+        {
+            c.voxels[j].sdf = src[5 * j];
+            c.voxels[j].weight = src[5 * j + 1];
+            c.voxels[j].color = geometry::Point3(src[5 * j + 2], src[5 * j + 3], src[5 * j + 4]);
+        }
+        m[id] = c;
+    }
+    bool was_quiet = std::cout.fail();
+    std::cout.setstate(std::ios_base::failbit);
+    ((RefVolume *)h)->handler.SetCubeMap(m);
+    if (!was_quiet) std::cout.clear();
+}
+// CubeHandler::ExtractTriangleMesh (CubeHandler.cpp:9-44). Returns seconds; sizes through out params.
+double ref_volume_extract_mesh(void *h, long *n_points, long *n_triangles)
+{
+    RefVolume *v = (RefVolume *)h;
+    v->mesh.Reset();
+    double t0 = Now();
+    v->handler.ExtractTriangleMesh(v->mesh);
+    double dt = Now() - t0;
+    *n_points = (long)v->mesh.points.size();
+    *n_triangles = (long)v->mesh.triangles.size();
+    return dt;
+}
+void ref_volume_mesh_copy(void *h, float *points, float *colors, uint32_t *triangles)
+{
+    RefVolume *v = (RefVolume *)h;
+    for (size_t i = 0; i < v->mesh.points.size(); ++i)
+        for (int k = 0; k < 3; ++k)
+        {
+            points[3 * i + k] = (float)v->mesh.points[i](k);
+            colors[3 * i + k] = (float)v->mesh.colors[i](k);
+        }
+    for (size_t i = 0; i < v->mesh.triangles.size(); ++i)
+        for (int k = 0; k < 3; ++k) triangles[3 * i + k] = v->mesh.triangles[i](k);
+}
+bool ref_volume_write(void *h, const char *path) { return ((RefVolume *)h)->handler.WriteToFile(path); }
+bool ref_volume_read(void *h, const char *path) { return ((RefVolume *)h)->handler.ReadFromFile(path); }
+
+
+// integration::MarchingCube on one cell (MarchingCube.cpp:31-74): corners 8x3, sdf 8, colors 8x3.
+// Writes up to 15 vertices (xyz, rgb); returns the vertex count (3 per triangle).
+int ref_marching_cube_cell(const float *corners, const float *sdf, const float *colors, float *out_xyz, float *out_rgb)
+{
+    geometry::Point3List c(8);
+    std::vector<integration::TSDFVoxel> v(8);
+    for (int i = 0; i < 8; ++i)
+    {
+        c[i] = geometry::Point3(corners[3 * i], corners[3 * i + 1], corners[3 * i + 2]);
+        v[i] = integration::TSDFVoxel(sdf[i], 1.0f, geometry::Point3(colors[3 * i], colors[3 * i + 1], colors[3 * i + 2]));
+    }
+    geometry::TriangleMesh m;
+    integration::MarchingCube(c, v, m);
+    for (size_t i = 0; i < m.points.size(); ++i)
+        for (int k = 0; k < 3; ++k)
+        {
+            out_xyz[3 * i + k] = (float)m.points[i](k);
+            out_rgb[3 * i + k] = (float)m.colors[i](k);
+        }
+    return (int)m.points.size();
+}
+// integration::Frustum::{ComputeFromCamera,ContainPoint} (Frustum.cpp:7-25, Frustum.h:74-103).
+// planes: 6x4 in the order top,left,right,bottom,near,far; mask[i] = ContainPoint(points[i]).
+void ref_frustum(float fx, float fy, float cx, float cy, int w, int h, const float *pose_cm, float far_d, float near_d,
+                 double *planes, const float *points, long n, uint8_t *mask)
+{
+    camera::PinholeCamera cam(fx, fy, cx, cy, w, h, 1000.0f);
+    integration::Frustum f;
+    f.ComputeFromCamera(cam, PoseFromColMajor(pose_cm), far_d, near_d);
+    const geometry::Plane *pl[6] = {&f.top_plane, &f.left_plane, &f.right_plane, &f.bottom_plane, &f.near_plane, &f.far_plane};
+    for (int i = 0; i < 6; ++i)
+        for (int k = 0; k < 4; ++k) planes[4 * i + k] = (*pl[i])(k);
+    for (long i = 0; i < n; ++i)
+        mask[i] = f.ContainPoint(geometry::Point3(points[3 * i], points[3 * i + 1], points[3 * i + 2])) ? 1 : 0;
+}
+// Eigen's Matrix4 inverse as used at Integrator.cpp:18,48
+void ref_pose_inverse(const float *pose_cm, double *inv_cm)
+{
+    geometry::TransformationMatrix inv = PoseFromColMajor(pose_cm).inverse();
+    PoseToColMajor(inv, inv_cm);
+}
+// Integrator::GetSDF (Integrator.cpp:8-35) at explicit points
+void ref_get_sdf(void *h, const void *depth, int is_u16, const float *pose_cm, const float *points, long n, float *sdf)
+{
+    RefVolume *v = (RefVolume *)h;
+    int w = v->cam.GetWidth(), hh = v->cam.GetHeight();
+    cv::Mat d = WrapDepth(depth, is_u16, w, hh);
+    integration::Integrator integ;
+    geometry::TransformationMatrix pose = PoseFromColMajor(pose_cm);
+    for (long i = 0; i < n; ++i)
+        sdf[i] = integ.GetSDF(geometry::Point3(points[3 * i], points[3 * i + 1], points[3 * i + 2]), v->cam, pose, d);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Registration
+// ---------------------------------------------------------------------------------------------
+// registration::PointToPlane / PointToPoint called exactly as example/ICPTest.cpp:33 does.
+// tgt_nrm == NULL -> PointToPoint.  out_T column-major double[16]; pairs: 2*n int32 (source, target).
+// Returns seconds spent in the call; *n_pairs = -1 if the reference returned its default (error) result.
+double ref_icp(const float *src, long ns, const float *tgt, const float *tgt_nrm, long nt, const float *init_T_cm,
+               int max_iter, double threshold, double *out_T_cm, int32_t *pairs, long pairs_cap, long *n_pairs,
+               double *rmse)
+{
+    geometry::PointCloud s, t;
+    ToList(src, ns, s.points);
+    ToList(tgt, nt, t.points);
+    if (tgt_nrm) ToList(tgt_nrm, nt, t.normals);
+    registration::ICPParameter para;
+    para.max_iteration = max_iter;
+    para.threshold = threshold;
+    geometry::TransformationMatrix T0 = PoseFromColMajor(init_T_cm);
+    double t0 = Now();
+    std::shared_ptr<registration::RegistrationResult> r =
+        tgt_nrm ? registration::PointToPlane(s, t, T0, para) : registration::PointToPoint(s, t, T0, para);
+    double dt = Now() - t0;
+    PoseToColMajor(r->T, out_T_cm);
+    *rmse = r->rmse;
+    long n = (long)r->correspondence_set_index.size();
+    *n_pairs = n;
+    for (long i = 0; i < n && i < pairs_cap; ++i)
+    {
+        pairs[2 * i] = r->correspondence_set_index[i].first;
+        pairs[2 * i + 1] = r->correspondence_set_index[i].second;
+    }
+    return dt;
+}
+
+// One loop body of PointToPlane (ICP.cpp:175-205) for teacher-forced comparison: given T_in, return the
+// nearest-neighbour indices, the inlier count, the 6x6 system the reference accumulates (recomputed with the
+// same statement order as ICP.cpp:121-136) and T_out = Se3ToSE3(x) * T_in.
+struct RefIcpState
+{
+    geometry::PointCloud source, target;
+    geometry::KDTree<> kdtree;
+};
+void *ref_icp_state_create(const float *src, long ns, const float *tgt, const float *tgt_nrm, long nt)
+{
+    RefIcpState *st = new RefIcpState();
+    ToList(src, ns, st->source.points);
+    ToList(tgt, nt, st->target.points);
+    if (tgt_nrm) ToList(tgt_nrm, nt, st->target.normals);
+    st->kdtree.BuildTree(st->target.points);
+    return st;
+}
+void ref_icp_state_destroy(void *p) { delete (RefIcpState *)p; }
+long ref_icp_iteration(void *p, const double *T_in_cm, double threshold, int32_t *nn_index, double *JTJ36,
+                       double *JTr6, double *x6, double *T_out_cm, double *rmse)
+{
+    RefIcpState *st = (RefIcpState *)p;
+    geometry::TransformationMatrix T;
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 4; ++r) T(r, c) = (scalar)T_in_cm[c * 4 + r];
+    std::vector<int> corr(st->source.points.size(), -1);
+    geometry::Point3List transformed = st->source.points;
+    geometry::TransformPoints(T, transformed);
+#pragma omp parallel for
+    for (size_t i = 0; i < transformed.size(); ++i)
+    {
+        std::vector<int> indices(1);
+        std::vector<float> dists(1);
+        st->kdtree.KnnSearch(transformed[i], indices, dists, 1, geometry::SearchParameter(128));
+        if (indices.size() > 0) corr[i] = indices[0];
+    }
+    geometry::FMatchSet inliers;
+    *rmse = registration::CountInliers(st->source.points, st->target.points, corr, T, threshold, inliers);
+    for (size_t i = 0; i < corr.size(); ++i) nn_index[i] = corr[i];
+    if (st->target.HasNormals())
+    {
+        geometry::Matrix6 JTJ = geometry::Matrix6::Zero();
+        geometry::Se3 JTr = geometry::Se3::Zero();
+        for (size_t i = 0; i != inliers.size(); ++i)
+        {
+            int sid = inliers[i].first, tid = inliers[i].second;
+            geometry::Se3 row;
+            double r = (st->target.normals[tid].transpose() * transformed[sid] -
+                        st->target.normals[tid].transpose() * st->target.points[tid])(0);
+            row.block<3, 1>(0, 0) = st->target.normals[tid];
+            row.block<3, 1>(3, 0) = transformed[sid].cross(st->target.normals[tid]);
+            JTJ.noalias() += row * row.transpose();
+            JTr.noalias() += r * row;
+        }
+        Eigen::JacobiSVD<geometry::MatrixX> svd(JTJ, Eigen::ComputeThinU | Eigen::ComputeThinV);
+        geometry::Se3 x = svd.solve(-JTr);
+        for (int i = 0; i < 36; ++i) JTJ36[i] = JTJ(i / 6, i % 6);
+        for (int i = 0; i < 6; ++i) { JTr6[i] = JTr(i); x6[i] = x(i); }
+        geometry::TransformationMatrix dT = registration::EstimateRigidTransformationPointToPlane(
+            transformed, st->target.points, st->target.normals, inliers);
+        PoseToColMajor(dT * T, T_out_cm);
+    }
+    else
+    {
+        geometry::PointCorrespondenceSet cs;
+        for (size_t i = 0; i != inliers.size(); ++i)
+            cs.push_back(std::make_pair(transformed[inliers[i].first], st->target.points[inliers[i].second]));
+        geometry::TransformationMatrix dT = geometry::EstimateRigidTransformation(cs);
+        PoseToColMajor(dT * T, T_out_cm);
+    }
+    return (long)inliers.size();
+}
+
+// geometry::Se3ToSE3 (Geometry.cpp:9-13)
+void ref_se3_exp(const double *x6, double *T_cm)
+{
+    geometry::Se3 x;
+    for (int i = 0; i < 6; ++i) x(i) = (scalar)x6[i];
+    PoseToColMajor(geometry::Se3ToSE3(x), T_cm);
+}
+// geometry::EstimateRigidTransformation (Geometry.cpp:107-151) on explicit pairs
+void ref_kabsch(const float *a, const float *b, long n, double *T_cm)
+{
+    geometry::PointCorrespondenceSet cs(n);
+    for (long i = 0; i < n; ++i)
+    {
+        cs[i].first = geometry::Point3((scalar)a[3 * i], (scalar)a[3 * i + 1], (scalar)a[3 * i + 2]);
+        cs[i].second = geometry::Point3((scalar)b[3 * i], (scalar)b[3 * i + 1], (scalar)b[3 * i + 2]);
+    }
+    PoseToColMajor(geometry::EstimateRigidTransformation(cs), T_cm);
+}
+#ifndef USING_FLOAT64
+// PointCloud::LoadFromDepth (PointCloud.cpp:72-100); returns the number of points written
+long ref_load_from_depth(const void *depth, int is_u16, int w, int h, float fx, float fy, float cx, float cy,
+                         float depth_scale, float *xyz)
+{
+    camera::PinholeCamera cam(fx, fy, cx, cy, w, h, depth_scale);
+    geometry::PointCloud pcd;
+    pcd.LoadFromDepth(WrapDepth(depth, is_u16, w, h), cam);
+    for (size_t i = 0; i < pcd.points.size(); ++i)
+        for (int k = 0; k < 3; ++k) xyz[3 * i + k] = pcd.points[i](k);
+    return (long)pcd.points.size();
+}
+// PointCloud::EstimateNormals (PointCloud.cpp:102-144)
+double ref_estimate_normals(const float *xyz, long n, float radius, int knn, float *normals)
+{
+    geometry::PointCloud pcd;
+    ToList(xyz, n, pcd.points);
+    double t0 = Now();
+    pcd.EstimateNormals(radius, knn);
+    double dt = Now() - t0;
+    for (long i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) normals[3 * i + k] = pcd.normals[i](k);
+    return dt;
+}
+#endif
+} // extern "C"
