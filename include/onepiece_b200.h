@@ -1,0 +1,146 @@
+/*
+ * onepiece_b200 -- C-ABI of the B200-native (sm_100a) dense-reconstruction hot path.
+ *
+ * The reference (wlsdzyzl/OnePiece) has no FFI: its hot path sits behind C++ symbols of libone_piece.so.
+ * This header is the one device boundary the rebuild introduces, directly underneath those symbols
+ * (SURVEY.md §8b).  Every entry point names the reference interface it replaces (file:line relative to the
+ * reference tree).  Plain pointers and sizes only; no C++/torch types.  The reference-side C++ classes that
+ * call these functions (drop-in for CubeHandler / PointToPlane / Odometry::DenseTracking) live in
+ * onepiece_b200/cpp/ and are described in INTEGRATION.md.
+ *
+ * Conventions
+ *   - all functions return OPB_OK (0) or a negative opb_status; opb_last_error() gives the message of the
+ *     last failure on the calling thread.  Nothing ever falls back to a CPU path: without a CUDA device the
+ *     create calls fail with OPB_ERR_CUDA.
+ *   - poses are camera-to-world 4x4 float, COLUMN-major (Eigen's default, geometry::TransformationMatrix).
+ *   - depth is either float32 metres (OPB_DEPTH_F32 == CV_32FC1) or uint16 raw units divided by
+ *     depth_scale (OPB_DEPTH_U16 == CV_16UC1), row-major W x H; colour is uint8 x 3 in file order (BGR).
+ *   - an object may be driven from one host thread at a time (same as the reference's classes).
+ */
+#ifndef ONEPIECE_B200_H
+#define ONEPIECE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum
+{
+    OPB_OK = 0,
+    OPB_ERR_INVALID = -1,  /* bad argument */
+    OPB_ERR_CUDA = -2,     /* CUDA runtime failure or no device */
+    OPB_ERR_CAPACITY = -3, /* block pool / output buffer too small */
+    OPB_ERR_UNSUPPORTED = -4
+} opb_status;
+
+enum { OPB_DEPTH_F32 = 5 /* CV_32FC1 */, OPB_DEPTH_U16 = 2 /* CV_16UC1 */ };
+enum
+{
+    OPB_STORAGE_F32 = 0,     /* 20 B/voxel: f32 sdf, weight, 3 x colour -- bit-exact with TSDFVoxel.h:8-82 */
+    OPB_STORAGE_PACKED16 = 1 /* 8 B/voxel: f16 sdf, f16 weight, rgb8 (throughput mode, error reported) */
+};
+
+const char *opb_last_error(void);
+int opb_device_count(void);
+/* pinned host staging buffers for the *_async entry points */
+int opb_host_alloc(void **ptr, size_t bytes);
+void opb_host_free(void *ptr);
+/* frees memory returned through out-parameters of this library (opb_volume_extract_mesh) */
+void opb_free(void *ptr);
+
+/* ------------------------------------------------------------------------------------------------------
+ * TSDF volume  (replaces one_piece::integration::CubeHandler, src/Integration/CubeHandler.h:24-366)
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct opb_volume opb_volume;
+
+typedef struct
+{
+    /* camera::PinholeCamera (src/Camera/Camera.h:13-130) */
+    float fx, fy, cx, cy;
+    int32_t width, height;
+    float depth_scale;
+    /* CubeHandler::SetVoxelResolution (CubeHandler.h:36), SetTruncation (:141), SetNearPlane/SetFarPlane (:349-356) */
+    float voxel_resolution; /* reference default 0.01 */
+    float truncation;       /* reference default 0.1  */
+    float near_plane;       /* reference default 0.5  */
+    float far_plane;        /* reference default 5.0  */
+    /* device-side block pool: the unordered_map<CubeID,VoxelCube> (CubeHandler.h:22) becomes a bounded pool of
+     * 8^3-voxel cubes plus an open-addressing hash table cube-id -> slot */
+    int32_t max_cubes;
+    int32_t storage; /* OPB_STORAGE_* */
+    int32_t device;  /* CUDA ordinal */
+    /* sub-volume ownership for multi-GPU fusion: this volume allocates/integrates cube (i,j,k)
+     * only if floor_mod(floor_div(id[shard_axis], shard_slab_cubes), shard_world) == shard_rank.
+     * shard_world <= 1 disables sharding. */
+    int32_t shard_rank, shard_world, shard_axis, shard_slab_cubes;
+    /* optional cudaStream_t to run on (NULL: the volume creates its own non-blocking stream) */
+    void *stream;
+} opb_volume_desc;
+
+/* per-frame counters of the last integrate call (device counters, read back on request) */
+typedef struct
+{
+    int32_t candidate_cubes; /* cubes tested in [min-1,max+1]^3   (CubeHandler.cpp:165-171) */
+    int32_t frame_cubes;     /* cubes listed for this frame        (:181-191)               */
+    int32_t total_cubes;     /* cubes allocated in the volume                                */
+    int32_t overflow;        /* !=0 if the pool or table was full and cubes were dropped     */
+    int64_t updated_voxels;  /* voxels whose |sdf| < truncation this frame (Integrator.cpp:74) */
+    float bbox_min[3], bbox_max[3]; /* CubeHandler::ComputeBounding result (CubeHandler.cpp:116-145) */
+    float select_ms;         /* device time of cube selection, when profiling is on */
+    float integrate_ms;      /* device time of the voxel-update kernel, when profiling is on */
+} opb_frame_stats;
+
+void opb_volume_desc_default(opb_volume_desc *desc);
+int opb_volume_create(const opb_volume_desc *desc, opb_volume **out);
+void opb_volume_destroy(opb_volume *v);
+/* CubeHandler::Clear (CubeHandler.h:133-136) */
+int opb_volume_clear(opb_volume *v);
+/* setters of CubeHandler callable at any time (SetCamera :137, SetVoxelResolution :36, SetTruncation :141,
+ * SetFarPlane/SetNearPlane :349-356); pool/storage/device/shard fields of desc are ignored */
+int opb_volume_set_params(opb_volume *v, const opb_volume_desc *desc);
+/* record CUDA events around the selection and update kernels of every frame (for bench.py) */
+int opb_volume_set_profiling(opb_volume *v, int on);
+/* accumulated device milliseconds of cube selection (K1) and voxel update (K2) over *frames profiled frames */
+int opb_volume_profile_read(opb_volume *v, double *select_ms, double *integrate_ms, int64_t *frames, int reset);
+
+/* CubeHandler::IntegrateImage(depth, rgb, pose) (CubeHandler.cpp:197-210; Integrator.cpp:36-94):
+ * host buffers, synchronous -- returns after the volume has been updated. */
+int opb_volume_integrate(opb_volume *v, const void *depth, int depth_type, const uint8_t *bgr,
+                         const float pose_colmajor[16]);
+/* same, but only enqueues (host buffers should be pinned: opb_host_alloc); up to two frames in flight, the
+ * call blocks only while the staging buffer it needs is still busy.  opb_volume_synchronize() drains. */
+int opb_volume_integrate_async(opb_volume *v, const void *depth, int depth_type, const uint8_t *bgr,
+                               const float pose_colmajor[16]);
+/* same with inputs already resident in device memory (enqueue only) */
+int opb_volume_integrate_device(opb_volume *v, const void *d_depth, int depth_type, const uint8_t *d_bgr,
+                                const float pose_colmajor[16]);
+int opb_volume_synchronize(opb_volume *v);
+int opb_volume_frame_stats(opb_volume *v, opb_frame_stats *out); /* synchronizes */
+
+/* CubeHandler::PrepareCubes alone (CubeHandler.cpp:147-196): selects + allocates, returns the frame's cube
+ * list (ids: 3 x int32 per cube, unordered).  *n_cubes in: capacity, out: count. */
+int opb_volume_prepare_cubes(opb_volume *v, const void *depth, int depth_type, const float pose_colmajor[16],
+                             int32_t *cube_ids, size_t *n_cubes);
+
+int opb_volume_num_cubes(opb_volume *v, size_t *n);
+/* CubeHandler::GetCubeMap (CubeHandler.h:339): cube_ids 3 x int32 per cube; voxels 512 x 5 float per cube in
+ * the reference's AoS order (sdf, weight, c0, c1, c2), voxel index x + 8y + 64z (VoxelCube.h:56).
+ * *n_cubes in: capacity of both arrays (in cubes), out: cubes written.  Either array may be NULL. */
+int opb_volume_download(opb_volume *v, int32_t *cube_ids, float *voxels_aos, size_t *n_cubes);
+/* CubeHandler::SetCubeMap (CubeHandler.h:344) / ReadFromFile (:40-69): replaces the volume content */
+int opb_volume_upload(opb_volume *v, const int32_t *cube_ids, const float *voxels_aos, size_t n_cubes);
+
+/* CubeHandler::ExtractTriangleMesh (CubeHandler.cpp:9-44,70-114; MarchingCube.cpp:9-74):
+ * 3 fresh vertices per triangle, xyz/rgb float[3*nv], tri uint32[3*nt] (tri[i] = 3i,3i+1,3i+2 like
+ * TriangleMesh::LoadFromMeshes produces).  Buffers are malloc'ed by the library: release with opb_free. */
+int opb_volume_extract_mesh(opb_volume *v, float **xyz, float **rgb, uint32_t **tri, size_t *nv, size_t *nt);
+/* counts only (no download) */
+int opb_volume_count_mesh(opb_volume *v, size_t *nv, size_t *nt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ONEPIECE_B200_H */

@@ -1,0 +1,100 @@
+"""ctypes binding of include/onepiece_b200.h (the C-ABI of libonepiece_b200.so).
+
+This is the Python-side stub a host application would write; tests and bench.py drive the CUDA path through
+it.  There is no fallback: if the shared library is missing the import of this module raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libonepiece_b200.so")
+
+OPB_OK = 0
+OPB_ERR_INVALID = -1
+OPB_ERR_CUDA = -2
+OPB_ERR_CAPACITY = -3
+OPB_ERR_UNSUPPORTED = -4
+OPB_DEPTH_F32 = 5
+OPB_DEPTH_U16 = 2
+OPB_STORAGE_F32 = 0
+OPB_STORAGE_PACKED16 = 1
+
+
+class OpbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"onepiece_b200 error {code}: {msg}")
+        self.code = code
+
+
+class VolumeDesc(C.Structure):
+    _fields_ = [
+        ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+        ("width", C.c_int32), ("height", C.c_int32), ("depth_scale", C.c_float),
+        ("voxel_resolution", C.c_float), ("truncation", C.c_float),
+        ("near_plane", C.c_float), ("far_plane", C.c_float),
+        ("max_cubes", C.c_int32), ("storage", C.c_int32), ("device", C.c_int32),
+        ("shard_rank", C.c_int32), ("shard_world", C.c_int32), ("shard_axis", C.c_int32),
+        ("shard_slab_cubes", C.c_int32),
+        ("stream", C.c_void_p),
+    ]
+
+
+class FrameStats(C.Structure):
+    _fields_ = [
+        ("candidate_cubes", C.c_int32), ("frame_cubes", C.c_int32), ("total_cubes", C.c_int32),
+        ("overflow", C.c_int32), ("updated_voxels", C.c_int64),
+        ("bbox_min", C.c_float * 3), ("bbox_max", C.c_float * 3),
+        ("select_ms", C.c_float), ("integrate_ms", C.c_float),
+    ]
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -m onepiece_b200.build` (onepiece_b200 has no CPU path)")
+
+lib = C.CDLL(LIB_PATH)
+_p = C.c_void_p
+_sz = C.c_size_t
+
+# name -> (restype, argtypes); every function include/onepiece_b200.h declares
+SIGNATURES = {
+    "opb_last_error": (C.c_char_p, []),
+    "opb_device_count": (C.c_int, []),
+    "opb_host_alloc": (C.c_int, [C.POINTER(_p), _sz]),
+    "opb_host_free": (None, [_p]),
+    "opb_free": (None, [_p]),
+    "opb_volume_desc_default": (None, [C.POINTER(VolumeDesc)]),
+    "opb_volume_create": (C.c_int, [C.POINTER(VolumeDesc), C.POINTER(_p)]),
+    "opb_volume_destroy": (None, [_p]),
+    "opb_volume_clear": (C.c_int, [_p]),
+    "opb_volume_set_params": (C.c_int, [_p, C.POINTER(VolumeDesc)]),
+    "opb_volume_set_profiling": (C.c_int, [_p, C.c_int]),
+    "opb_volume_profile_read": (C.c_int, [_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
+    "opb_volume_integrate": (C.c_int, [_p, _p, C.c_int, _p, _p]),
+    "opb_volume_integrate_async": (C.c_int, [_p, _p, C.c_int, _p, _p]),
+    "opb_volume_integrate_device": (C.c_int, [_p, _p, C.c_int, _p, _p]),
+    "opb_volume_synchronize": (C.c_int, [_p]),
+    "opb_volume_frame_stats": (C.c_int, [_p, C.POINTER(FrameStats)]),
+    "opb_volume_prepare_cubes": (C.c_int, [_p, _p, C.c_int, _p, _p, C.POINTER(_sz)]),
+    "opb_volume_num_cubes": (C.c_int, [_p, C.POINTER(_sz)]),
+    "opb_volume_download": (C.c_int, [_p, _p, _p, C.POINTER(_sz)]),
+    "opb_volume_upload": (C.c_int, [_p, _p, _p, _sz]),
+}
+
+
+def _bind():
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name, None)
+        if fn is None:
+            continue  # tests/test_abi.py reports missing symbols explicitly
+        fn.restype = res
+        fn.argtypes = args
+
+
+_bind()
+
+
+def check(rc: int):
+    if rc != OPB_OK:
+        raise OpbError(rc, lib.opb_last_error().decode(errors="replace"))

@@ -1,0 +1,93 @@
+// Shared helpers of the sm_100a kernels: error plumbing and the "reference arithmetic" primitives.
+//
+// The reference is compiled with -O3 -msse4.2 (CMakeLists.txt:149-150): scalar SSE float math, no FMA
+// contraction, IEEE division.  Discrete decisions on the path (pixel selection by truncation, |sdf| < trunc,
+// sdf > 0 in Marching Cubes) flip on 1-ulp differences, so every float operation that feeds one is written
+// with the non-contracting intrinsics below, in the reference's operation order (SURVEY.md §7 hard part 1).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+namespace opb
+{
+void set_error(const char *fmt, ...);
+
+#define OPB_CUDA(expr)                                                                          \
+    do                                                                                          \
+    {                                                                                           \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+        {                                                                                       \
+            opb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return OPB_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+// ---- float ops that ptxas must not fuse ----
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// x86 cvttsd2si semantics: C truncation toward zero, INT_MIN ("integer indefinite") for NaN and for values
+// that do not fit -- CUDA's own conversion saturates and maps NaN to 0, which would select pixel 0.
+__device__ __forceinline__ int cvtt_x86(double d)
+{
+    if (!(d > -2147483649.0 && d < 2147483648.0)) return INT32_MIN;
+    return __double2int_rz(d);
+}
+// float -> int as g++ emits it (cvttss2si)
+__device__ __forceinline__ int cvtt_x86(float f)
+{
+    if (!(f >= -2147483648.0f && f < 2147483648.0f)) return INT32_MIN;
+    return __float2int_rz(f);
+}
+
+// int u = a + 0.5 + c with a, c float:  the 0.5 literal is double, so both adds are done in double
+// (Integrator.cpp:19-20,61-62)
+__device__ __forceinline__ int pixel_index(float a, float c)
+{
+    return cvtt_x86(__dadd_rn(__dadd_rn((double)a, 0.5), (double)c));
+}
+
+// Eigen 3.3.7 Matrix4f * Vector4f(x, y, z, 1) row, SSE gemv order: ((m0*x + m1*y) + m2*z) + m3*1
+__device__ __forceinline__ float row_xyz1(float m0, float m1, float m2, float m3, float x, float y, float z)
+{
+    return fadd(fadd(fadd(fmul(m0, x), fmul(m1, y)), fmul(m2, z)), m3);
+}
+// Eigen 3.3.7 fixed-size-3 redux order: a0*b0 + (a1*b1 + a2*b2)
+__device__ __forceinline__ float dot3(float a0, float a1, float a2, float b0, float b1, float b2)
+{
+    return fadd(fmul(a0, b0), fadd(fmul(a1, b1), fmul(a2, b2)));
+}
+
+// monotone float <-> uint mapping for atomicMin/atomicMax on floats
+__device__ __forceinline__ unsigned int float_to_ordered(float f)
+{
+    unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ordered_to_float(unsigned int u)
+{
+    unsigned int b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+
+// floor division / modulo of ints by a positive int
+__host__ __device__ __forceinline__ int floor_div(int a, int b)
+{
+    int q = a / b;
+    return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+__host__ __device__ __forceinline__ int floor_mod(int a, int b) { return a - floor_div(a, b) * b; }
+
+} // namespace opb

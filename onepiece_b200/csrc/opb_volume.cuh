@@ -1,0 +1,105 @@
+// Device-side layout of the TSDF volume (replaces the reference's
+// std::unordered_map<CubeID, VoxelCube> of 20-byte AoS voxels, CubeHandler.h:22, VoxelCube.h:95-197).
+//
+//   block pool   max_cubes slots; a slot holds one 8^3 cube as five float planes of 512 values
+//                [sdf | weight | c0 | c1 | c2]  (10,240 B, the same 20 B/voxel as the reference, but
+//                plane-major so that a warp touching 32 consecutive voxels moves whole 128 B lines)
+//   slot_ids     3 x int32 per slot: the CubeID stored in it
+//   hash table   open addressing, 64-bit packed CubeID -> slot, capacity = pow2 >= 2*max_cubes
+//   frame list   slots selected for the frame being integrated (CubeHandler::PrepareCubes' cube_id_list)
+//   counters     allocation bump pointer, frame counters, bounding box (ordered-uint encoding)
+#pragma once
+#include "opb_common.cuh"
+
+namespace opb
+{
+constexpr int kCube = 8;                 // CUBE_SIZE (VoxelCube.h:4)
+constexpr int kCubeVoxels = 512;         // 8^3
+constexpr int kPlanes = 5;               // sdf, weight, c0, c1, c2
+constexpr int kSlotFloats = kCubeVoxels * kPlanes;
+constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr int kIdBias = 1 << 20;         // cube ids are packed 21 bits per axis
+
+struct FrameCounters
+{
+    unsigned int bbox_min[3]; // ordered-uint floats
+    unsigned int bbox_max[3];
+    int candidate_cubes;
+    int frame_cubes;
+    int overflow;
+    int pad;
+    unsigned long long updated_voxels;
+};
+
+struct VolumeDev
+{
+    float *pool;              // max_cubes * kSlotFloats
+    int *slot_ids;            // max_cubes * 3
+    unsigned long long *keys; // table_cap
+    int *vals;                // table_cap
+    int *frame_list;          // max_cubes
+    int *n_alloc;             // cubes allocated so far
+    FrameCounters *fc;        // counters of the frame in flight
+    int max_cubes;
+    unsigned int table_mask;
+};
+
+// per-frame constants, passed to the kernels by value
+struct FrameParams
+{
+    float fx, fy, cx, cy;
+    int width, height;
+    float depth_scale;
+    int depth_u16;
+    float res;       // VoxelResolution
+    float cube_res;  // VoxelResolution * CUBE_SIZE
+    float half_res;  // VoxelResolution / 2
+    float trunc;
+    float pose[16];  // camera-to-world, column-major
+    float pinv[16];  // Eigen-order inverse of pose, column-major
+    float planes[24];
+    int shard_rank, shard_world, shard_axis, shard_slab;
+};
+
+__host__ __device__ __forceinline__ bool pack_id(int i, int j, int k, unsigned long long &key)
+{
+    const unsigned int a = (unsigned int)(i + kIdBias), b = (unsigned int)(j + kIdBias), c = (unsigned int)(k + kIdBias);
+    if ((a | b | c) >> 21) return false;
+    key = ((unsigned long long)a << 42) | ((unsigned long long)b << 21) | (unsigned long long)c;
+    return true;
+}
+__host__ __device__ __forceinline__ unsigned int hash_key(unsigned long long k)
+{
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return (unsigned int)k;
+}
+// slot of a cube or -1
+__device__ __forceinline__ int table_find(const VolumeDev &v, int i, int j, int k)
+{
+    unsigned long long key;
+    if (!pack_id(i, j, k, key)) return -1;
+    unsigned int h = hash_key(key) & v.table_mask;
+    for (;;)
+    {
+        const unsigned long long cur = v.keys[h];
+        if (cur == key) return v.vals[h];
+        if (cur == kEmptyKey) return -1;
+        h = (h + 1) & v.table_mask;
+    }
+}
+
+// VoxelCentroidOffSet component (VoxelCube.h:48-61): x*VoxelResolution + half_resolution
+__device__ __forceinline__ float centroid_offset(int x, float res, float half_res)
+{
+    return fadd(fmul((float)x, res), half_res);
+}
+// cube origin component: CubeID * CUBE_SIZE * VoxelResolution == CubeID * (VoxelResolution*CUBE_SIZE)
+// (GetGlobalPoint VoxelCube.h:75-80, GetOrigin :143-147, PrepareCubes CubeHandler.cpp:163,175 -- the factor 8 is
+// a power of two, so both association orders round identically)
+__device__ __forceinline__ float cube_origin(int id, float cube_res) { return fmul((float)id, cube_res); }
+
+} // namespace opb

@@ -1,0 +1,153 @@
+"""Python mirror of one_piece::integration::CubeHandler (reference src/Integration/CubeHandler.h:24-366) over the
+C-ABI.  Method names and argument meaning follow the reference class so that tests read like its examples
+(example/ImageSequenceIntegration.cpp:20-53).  All computation happens in libonepiece_b200.so on the GPU."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .scenes import Camera
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))
+
+
+def pose_colmajor(pose) -> np.ndarray:
+    """4x4 camera-to-world (numpy, row-major indexing) -> Eigen column-major float32[16]."""
+    return np.ascontiguousarray(np.asarray(pose, dtype=np.float32).reshape(4, 4).T).reshape(16)
+
+
+def depth_type_of(depth) -> int:
+    if depth.dtype == np.float32:
+        return capi.OPB_DEPTH_F32
+    if depth.dtype == np.uint16:
+        return capi.OPB_DEPTH_U16
+    return -1  # rejected by the library like the reference's "Unknown depth image type"
+
+
+class CubeHandler:
+    def __init__(self, camera: Camera = Camera(), voxel_resolution: float = 0.01, truncation: float = 0.1,
+                 near: float = 0.5, far: float = 5.0, max_cubes: int = 1 << 17, device: int = 0,
+                 storage: int = capi.OPB_STORAGE_F32, shard=None, stream=None):
+        d = capi.VolumeDesc()
+        capi.lib.opb_volume_desc_default(C.byref(d))
+        d.fx, d.fy, d.cx, d.cy = camera.fx, camera.fy, camera.cx, camera.cy
+        d.width, d.height, d.depth_scale = camera.width, camera.height, camera.depth_scale
+        d.voxel_resolution, d.truncation, d.near_plane, d.far_plane = voxel_resolution, truncation, near, far
+        d.max_cubes, d.device, d.storage = max_cubes, device, storage
+        if shard is not None:
+            d.shard_rank, d.shard_world, d.shard_axis, d.shard_slab_cubes = shard
+        d.stream = stream
+        self.desc = d
+        self.camera = camera
+        self._h = C.c_void_p()
+        capi.check(capi.lib.opb_volume_create(C.byref(d), C.byref(self._h)))
+
+    # -- lifetime ---------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            capi.lib.opb_volume_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- setters (CubeHandler.h:36,137,141,349-356) ---------------------------------------------------
+    def _push_params(self):
+        capi.check(capi.lib.opb_volume_set_params(self._h, C.byref(self.desc)))
+
+    def SetVoxelResolution(self, r):
+        self.desc.voxel_resolution = r
+        self._push_params()
+
+    def SetTruncation(self, t):
+        self.desc.truncation = t
+        self._push_params()
+
+    def SetFarPlane(self, f):
+        self.desc.far_plane = f
+        self._push_params()
+
+    def SetNearPlane(self, n):
+        self.desc.near_plane = n
+        self._push_params()
+
+    def SetCamera(self, cam: Camera):
+        d = self.desc
+        d.fx, d.fy, d.cx, d.cy = cam.fx, cam.fy, cam.cx, cam.cy
+        d.width, d.height, d.depth_scale = cam.width, cam.height, cam.depth_scale
+        self.camera = cam
+        self._push_params()
+
+    def Clear(self):
+        capi.check(capi.lib.opb_volume_clear(self._h))
+
+    # -- integration ------------------------------------------------------------------------------------
+    def IntegrateImage(self, depth, rgb, pose):
+        """CubeHandler::IntegrateImage(depth, rgb, pose) with host arrays (synchronous)."""
+        depth = np.ascontiguousarray(depth)
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        p = pose_colmajor(pose)
+        capi.check(capi.lib.opb_volume_integrate(self._h, _ptr(depth), depth_type_of(depth), _ptr(rgb), _ptr(p)))
+
+    def IntegrateImageAsync(self, depth_ptr, depth_type, bgr_ptr, pose_cm):
+        capi.check(capi.lib.opb_volume_integrate_async(self._h, _ptr(depth_ptr), depth_type, _ptr(bgr_ptr), _ptr(pose_cm)))
+
+    def IntegrateImageDevice(self, d_depth_ptr, depth_type, d_bgr_ptr, pose_cm):
+        capi.check(capi.lib.opb_volume_integrate_device(self._h, _ptr(d_depth_ptr), depth_type, _ptr(d_bgr_ptr), _ptr(pose_cm)))
+
+    def Synchronize(self):
+        capi.check(capi.lib.opb_volume_synchronize(self._h))
+
+    def PrepareCubes(self, depth, pose):
+        depth = np.ascontiguousarray(depth)
+        p = pose_colmajor(pose)
+        cap = int(self.desc.max_cubes)
+        ids = np.zeros((cap, 3), np.int32)
+        n = C.c_size_t(cap)
+        capi.check(capi.lib.opb_volume_prepare_cubes(self._h, _ptr(depth), depth_type_of(depth), _ptr(p), _ptr(ids), C.byref(n)))
+        return ids[: n.value].copy()
+
+    def FrameStats(self) -> capi.FrameStats:
+        s = capi.FrameStats()
+        capi.check(capi.lib.opb_volume_frame_stats(self._h, C.byref(s)))
+        return s
+
+    def SetProfiling(self, on: bool):
+        capi.check(capi.lib.opb_volume_set_profiling(self._h, int(on)))
+
+    def ProfileRead(self, reset=True):
+        a, b, n = C.c_double(0), C.c_double(0), C.c_int64(0)
+        capi.check(capi.lib.opb_volume_profile_read(self._h, C.byref(a), C.byref(b), C.byref(n), int(reset)))
+        return a.value, b.value, n.value
+
+    # -- content ----------------------------------------------------------------------------------------
+    def NumCubes(self) -> int:
+        n = C.c_size_t(0)
+        capi.check(capi.lib.opb_volume_num_cubes(self._h, C.byref(n)))
+        return n.value
+
+    def GetCubeMap(self):
+        """-> (ids [n,3] int32, voxels [n,512,5] float32 = sdf, weight, c0, c1, c2) sorted by cube id."""
+        n = self.NumCubes()
+        ids = np.zeros((n, 3), np.int32)
+        vox = np.zeros((n, 512, 5), np.float32)
+        cnt = C.c_size_t(n)
+        capi.check(capi.lib.opb_volume_download(self._h, _ptr(ids), _ptr(vox), C.byref(cnt)))
+        order = np.lexsort((ids[:, 2], ids[:, 1], ids[:, 0]))
+        return ids[order], vox[order]
+
+    def SetCubeMap(self, ids, vox):
+        ids = np.ascontiguousarray(ids, np.int32)
+        vox = np.ascontiguousarray(vox, np.float32)
+        capi.check(capi.lib.opb_volume_upload(self._h, _ptr(ids), _ptr(vox), len(ids)))
