@@ -51,6 +51,15 @@ void opb_host_free(void *ptr);
 /* frees memory returned through out-parameters of this library (opb_volume_extract_mesh) */
 void opb_free(void *ptr);
 
+/* Host-side helpers, exported because the per-frame constants they produce feed discrete decisions on the
+ * device and must match the reference bit for bit (no GPU needed to call them):
+ *   opb_pose_inverse   = Eigen::Matrix4f::inverse() as used at Integrator.cpp:18,48 (column-major in/out)
+ *   opb_frustum_planes = Frustum::ComputeFromCamera (Frustum.cpp:7-52); 6 planes x 4 floats in the order
+ *                        Frustum::ContainPoint tests them: top, left, right, bottom, near, far */
+void opb_pose_inverse(const float pose_colmajor[16], float inverse_colmajor[16]);
+void opb_frustum_planes(float fx, float fy, float cy, int width, int height, float near_plane, float far_plane,
+                        const float pose_colmajor[16], float planes[24]);
+
 /* ------------------------------------------------------------------------------------------------------
  * TSDF volume  (replaces one_piece::integration::CubeHandler, src/Integration/CubeHandler.h:24-366)
  * ---------------------------------------------------------------------------------------------------- */

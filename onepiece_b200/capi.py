@@ -64,6 +64,8 @@ SIGNATURES = {
     "opb_host_alloc": (C.c_int, [C.POINTER(_p), _sz]),
     "opb_host_free": (None, [_p]),
     "opb_free": (None, [_p]),
+    "opb_pose_inverse": (None, [_p, _p]),
+    "opb_frustum_planes": (None, [C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_float, C.c_float, _p, _p]),
     "opb_volume_desc_default": (None, [C.POINTER(VolumeDesc)]),
     "opb_volume_create": (C.c_int, [C.POINTER(VolumeDesc), C.POINTER(_p)]),
     "opb_volume_destroy": (None, [_p]),
@@ -80,6 +82,8 @@ SIGNATURES = {
     "opb_volume_num_cubes": (C.c_int, [_p, C.POINTER(_sz)]),
     "opb_volume_download": (C.c_int, [_p, _p, _p, C.POINTER(_sz)]),
     "opb_volume_upload": (C.c_int, [_p, _p, _p, _sz]),
+    "opb_volume_extract_mesh": (C.c_int, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_sz), C.POINTER(_sz)]),
+    "opb_volume_count_mesh": (C.c_int, [_p, C.POINTER(_sz), C.POINTER(_sz)]),
 }
 
 

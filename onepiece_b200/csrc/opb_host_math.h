@@ -121,8 +121,10 @@ static inline void frustum_planes(const float *pose_cm, float fx, float fy, floa
     V3 fwd{pose_cm[8], pose_cm[9], pose_cm[10]};
     V3 pos{pose_cm[12], pose_cm[13], pose_cm[14]};
     float aspect = (fy * width) / (fx * height);
-    float fov = atan2(cy, fy) + atan2(height - cy, fy);
-    float angle_tangent = tan(fov / 2);
+    // Frustum.cpp:23,29 call unqualified atan2()/tan() on floats from a plain C++ translation unit: they bind to
+    // the C library's double versions, and the result is rounded once on assignment
+    float fov = (float)(std::atan2((double)cy, (double)fy) + std::atan2((double)(height - cy), (double)fy));
+    float angle_tangent = (float)std::tan((double)(fov / 2));
     float height_far = angle_tangent * far_dist;
     float width_far = height_far * aspect;
     float height_near = angle_tangent * near_dist;

@@ -151,3 +151,24 @@ class CubeHandler:
         ids = np.ascontiguousarray(ids, np.int32)
         vox = np.ascontiguousarray(vox, np.float32)
         capi.check(capi.lib.opb_volume_upload(self._h, _ptr(ids), _ptr(vox), len(ids)))
+
+    # -- Marching Cubes ---------------------------------------------------------------------------------
+    def ExtractTriangleMesh(self):
+        """CubeHandler::ExtractTriangleMesh -> (points [nv,3] f32, colors [nv,3] f32, triangles [nt,3] u32)."""
+        xyz, rgb, tri = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nv, nt = C.c_size_t(0), C.c_size_t(0)
+        capi.check(capi.lib.opb_volume_extract_mesh(self._h, C.byref(xyz), C.byref(rgb), C.byref(tri), C.byref(nv), C.byref(nt)))
+        n = nv.value
+        if n == 0:
+            return np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32)
+        pts = np.ctypeslib.as_array(C.cast(xyz, C.POINTER(C.c_float)), shape=(n * 3,)).reshape(n, 3).copy()
+        col = np.ctypeslib.as_array(C.cast(rgb, C.POINTER(C.c_float)), shape=(n * 3,)).reshape(n, 3).copy()
+        t = np.ctypeslib.as_array(C.cast(tri, C.POINTER(C.c_uint32)), shape=(nt.value * 3,)).reshape(nt.value, 3).copy()
+        for p in (xyz, rgb, tri):
+            capi.lib.opb_free(p)
+        return pts, col, t
+
+    def CountMesh(self):
+        nv, nt = C.c_size_t(0), C.c_size_t(0)
+        capi.check(capi.lib.opb_volume_count_mesh(self._h, C.byref(nv), C.byref(nt)))
+        return nv.value, nt.value

@@ -1,0 +1,499 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- see opb_oracle.h.  CPU restatement of the reference algorithm, written as
+ * straight-line C that mirrors the reference's statement order so the float32 results are bit-identical to
+ * the reference built with its own flags (-O3 -msse4.2, no FMA).  Build: `make -C oracle oracle`
+ * (gcc -O2 -msse4.2 -ffp-contract=off).
+ *
+ * Parity status: PINNED against oracle/_ref (the reference's translation units compiled unmodified) by
+ * tests/test_oracle_vs_ref.py and against tests/golden/ fixtures by tests/test_oracle_golden.py.
+ */
+#include "opb_oracle.h"
+
+#include <float.h>
+#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../onepiece_b200/csrc/opb_mc_table.h" /* generated data: Marching Cubes case table */
+
+#define CUBE 8 /* CUBE_SIZE, src/Integration/VoxelCube.h:4 */
+#define NVOX 512
+
+/* TSDFVoxel, src/Integration/TSDFVoxel.h:8-82 (20 bytes) */
+typedef struct
+{
+    float sdf, weight, c[3];
+} voxel_t;
+typedef struct
+{
+    int id[3];
+    voxel_t vox[NVOX];
+} cube_t;
+
+struct orc_volume
+{
+    float fx, fy, cx, cy, depth_scale;
+    int width, height;
+    float res, trunc, near_plane, far_plane;
+    float centroid[NVOX][3]; /* CubePara::VoxelCentroidOffSet, VoxelCube.h:48-61 */
+    cube_t **cubes;          /* insertion order */
+    long n_cubes, cap_cubes;
+    long *table;             /* open addressing: index into cubes or -1 */
+    long table_cap;
+};
+
+/* x86 float/double -> int conversion as g++ emits it (cvttss2si / cvttsd2si): out-of-range and NaN give INT_MIN */
+static int cvtt_d(double d) { return (d > -2147483649.0 && d < 2147483648.0) ? (int)d : INT_MIN; }
+static int cvtt_f(float f) { return (f >= -2147483648.0f && f < 2147483648.0f) ? (int)f : INT_MIN; }
+
+/* ------------------------------------------------------------------------------------------------------- */
+/* cube container (std::unordered_map<CubeID, VoxelCube>, CubeHandler.h:22)                               */
+/* ------------------------------------------------------------------------------------------------------- */
+static unsigned long hash_id(const int *id)
+{
+    /* VoxelGridHasher, src/Geometry/Geometry.h:101-112 (the oracle's container order is its own) */
+    return ((unsigned long)(long)id[0] * 73856093ul) ^ ((unsigned long)(long)id[1] * 19349663ul) ^
+           ((unsigned long)(long)id[2] * 83492791ul);
+}
+static void table_rebuild(orc_volume *v, long cap)
+{
+    free(v->table);
+    v->table_cap = cap;
+    v->table = (long *)malloc(sizeof(long) * cap);
+    for (long i = 0; i < cap; ++i) v->table[i] = -1;
+    for (long c = 0; c < v->n_cubes; ++c)
+    {
+        unsigned long h = hash_id(v->cubes[c]->id) & (cap - 1);
+        while (v->table[h] >= 0) h = (h + 1) & (cap - 1);
+        v->table[h] = c;
+    }
+}
+static cube_t *find_cube(const orc_volume *v, int i, int j, int k)
+{
+    const int id[3] = {i, j, k};
+    unsigned long h = hash_id(id) & (v->table_cap - 1);
+    while (v->table[h] >= 0)
+    {
+        cube_t *c = v->cubes[v->table[h]];
+        if (c->id[0] == i && c->id[1] == j && c->id[2] == k) return c;
+        h = (h + 1) & (v->table_cap - 1);
+    }
+    return NULL;
+}
+/* VoxelCube(const CubeID&), VoxelCube.h:102-106 with TSDFVoxel defaults TSDFVoxel.h:79-81 */
+static cube_t *add_cube(orc_volume *v, int i, int j, int k)
+{
+    if (v->n_cubes == v->cap_cubes)
+    {
+        v->cap_cubes = v->cap_cubes ? v->cap_cubes * 2 : 1024;
+        v->cubes = (cube_t **)realloc(v->cubes, sizeof(cube_t *) * v->cap_cubes);
+    }
+    cube_t *c = (cube_t *)malloc(sizeof(cube_t));
+    c->id[0] = i; c->id[1] = j; c->id[2] = k;
+    for (int n = 0; n < NVOX; ++n)
+    {
+        c->vox[n].sdf = 999; c->vox[n].weight = 0;
+        c->vox[n].c[0] = c->vox[n].c[1] = c->vox[n].c[2] = -1;
+    }
+    v->cubes[v->n_cubes++] = c;
+    if (v->n_cubes * 2 > v->table_cap) table_rebuild(v, v->table_cap * 2);
+    else
+    {
+        unsigned long h = hash_id(c->id) & (v->table_cap - 1);
+        while (v->table[h] >= 0) h = (h + 1) & (v->table_cap - 1);
+        v->table[h] = v->n_cubes - 1;
+    }
+    return c;
+}
+
+orc_volume *orc_volume_create(float fx, float fy, float cx, float cy, int width, int height, float depth_scale,
+                              float res, float trunc, float near_plane, float far_plane)
+{
+    orc_volume *v = (orc_volume *)calloc(1, sizeof(orc_volume));
+    v->fx = fx; v->fy = fy; v->cx = cx; v->cy = cy; v->width = width; v->height = height; v->depth_scale = depth_scale;
+    v->res = res; v->trunc = trunc; v->near_plane = near_plane; v->far_plane = far_plane;
+    /* CubePara::InitializeVoxelCube, VoxelCube.h:48-61 */
+    float half = res / 2;
+    for (int x = 0; x < CUBE; ++x)
+        for (int y = 0; y < CUBE; ++y)
+            for (int z = 0; z < CUBE; ++z)
+            {
+                float *o = v->centroid[x + y * CUBE + z * CUBE * CUBE];
+                o[0] = x * res + half; o[1] = y * res + half; o[2] = z * res + half;
+            }
+    table_rebuild(v, 4096);
+    return v;
+}
+void orc_volume_clear(orc_volume *v)
+{
+    for (long c = 0; c < v->n_cubes; ++c) free(v->cubes[c]);
+    v->n_cubes = 0;
+    table_rebuild(v, 4096);
+}
+void orc_volume_destroy(orc_volume *v)
+{
+    if (!v) return;
+    orc_volume_clear(v);
+    free(v->cubes); free(v->table); free(v);
+}
+void orc_free(void *p) { free(p); }
+long orc_volume_num_cubes(const orc_volume *v) { return v->n_cubes; }
+
+/* ------------------------------------------------------------------------------------------------------- */
+/* small Eigen computations                                                                                */
+/* ------------------------------------------------------------------------------------------------------- */
+/* Eigen 3.3.7 Matrix4f::inverse() on SSE targets (3rdparty/Eigen/Eigen/src/LU/arch/Inverse_SSE.h): 2x2-block
+ * cofactor scheme; called at Integrator.cpp:18,48.  Lanes written out explicitly.                          */
+void orc_pose_inverse(const float *m, float *out)
+{
+    const float A[4] = {m[0], m[1], m[4], m[5]}, B[4] = {m[2], m[3], m[6], m[7]};
+    const float C[4] = {m[8], m[9], m[12], m[13]}, D[4] = {m[10], m[11], m[14], m[15]};
+    float AB[4], DC[4], iA[4], iB[4], iC[4], iD[4];
+    /* AB = adj(A)*B, DC = adj(D)*C */
+    AB[0] = A[3] * B[0] - A[1] * B[2]; AB[1] = A[3] * B[1] - A[1] * B[3];
+    AB[2] = A[0] * B[2] - A[2] * B[0]; AB[3] = A[0] * B[3] - A[2] * B[1];
+    DC[0] = D[3] * C[0] - D[1] * C[2]; DC[1] = D[3] * C[1] - D[1] * C[3];
+    DC[2] = D[0] * C[2] - D[2] * C[0]; DC[3] = D[0] * C[3] - D[2] * C[1];
+    const float dA = A[3] * A[0] - A[1] * A[2], dB = B[3] * B[0] - B[1] * B[2];
+    const float dC = C[3] * C[0] - C[1] * C[2], dD = D[3] * D[0] - D[1] * D[2];
+    const float t0 = DC[0] * AB[0], t1 = DC[2] * AB[1], t2 = DC[1] * AB[2], t3 = DC[3] * AB[3];
+    const float tr = (t0 + t2) + (t1 + t3);
+    iD[0] = C[0] * AB[0] + C[1] * AB[2]; iD[1] = C[0] * AB[1] + C[1] * AB[3];
+    iD[2] = C[2] * AB[0] + C[3] * AB[2]; iD[3] = C[2] * AB[1] + C[3] * AB[3];
+    iA[0] = B[0] * DC[0] + B[1] * DC[2]; iA[1] = B[0] * DC[1] + B[1] * DC[3];
+    iA[2] = B[2] * DC[0] + B[3] * DC[2]; iA[3] = B[2] * DC[1] + B[3] * DC[3];
+    for (int i = 0; i < 4; ++i) { iD[i] = D[i] * dA - iD[i]; iA[i] = A[i] * dD - iA[i]; }
+    const float det = (dA * dD + dB * dC) - tr;
+    const float rd = 1.0f / det;
+    iB[0] = D[0] * AB[3] - D[1] * AB[2]; iB[1] = D[1] * AB[0] - D[0] * AB[1];
+    iB[2] = D[2] * AB[3] - D[3] * AB[2]; iB[3] = D[3] * AB[0] - D[2] * AB[1];
+    iC[0] = A[0] * DC[3] - A[1] * DC[2]; iC[1] = A[1] * DC[0] - A[0] * DC[1];
+    iC[2] = A[2] * DC[3] - A[3] * DC[2]; iC[3] = A[3] * DC[0] - A[2] * DC[1];
+    for (int i = 0; i < 4; ++i) { iB[i] = C[i] * dB - iB[i]; iC[i] = B[i] * dC - iC[i]; }
+    const float s[4] = {rd, -rd, -rd, rd};
+    for (int i = 0; i < 4; ++i) { iA[i] = s[i] * iA[i]; iB[i] = s[i] * iB[i]; iC[i] = s[i] * iC[i]; iD[i] = s[i] * iD[i]; }
+    out[0] = iA[3]; out[1] = iA[1]; out[2] = iB[3]; out[3] = iB[1];
+    out[4] = iA[2]; out[5] = iA[0]; out[6] = iB[2]; out[7] = iB[0];
+    out[8] = iC[3]; out[9] = iC[1]; out[10] = iD[3]; out[11] = iD[1];
+    out[12] = iC[2]; out[13] = iC[0]; out[14] = iD[2]; out[15] = iD[0];
+}
+
+/* Eigen fixed-size-3 reduction order: a0*b0 + (a1*b1 + a2*b2) */
+static float dot3(const float *a, const float *b) { return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]); }
+
+/* geometry::GetPlane, src/Geometry/Geometry.cpp:170-176 */
+static void get_plane(const float *p1, const float *p2, const float *p3, float *pl)
+{
+    float a[3], b[3], n[3];
+    for (int i = 0; i < 3; ++i) { a[i] = p2[i] - p1[i]; b[i] = p3[i] - p1[i]; }
+    n[0] = a[1] * b[2] - a[2] * b[1]; n[1] = a[2] * b[0] - a[0] * b[2]; n[2] = a[0] * b[1] - a[1] * b[0];
+    float z = dot3(n, n);
+    if (z > 0) { float len = sqrtf(z); n[0] = n[0] / len; n[1] = n[1] / len; n[2] = n[2] / len; }
+    double d = -dot3(p1, n);
+    pl[0] = n[0]; pl[1] = n[1]; pl[2] = n[2]; pl[3] = (float)d;
+}
+/* Frustum::ComputeFromCamera / ComputeFromVectors, src/Integration/Frustum.cpp:7-52; plane order = the order
+ * ContainPoint tests them (Frustum.h:74-103): top, left, right, bottom, near, far */
+void orc_frustum_planes(const orc_volume *v, const float *T, float *planes)
+{
+    const float right[3] = {T[0], T[1], T[2]}, up[3] = {-T[4], -T[5], -T[6]}, fwd[3] = {T[8], T[9], T[10]};
+    const float pos[3] = {T[12], T[13], T[14]};
+    const float width = (float)v->width, height = (float)v->height;
+    float aspect = (v->fy * width) / (v->fx * height);
+    /* unqualified atan2()/tan() on floats in a plain C++ translation unit bind to the C library's double
+     * versions (Frustum.cpp:23,29): evaluate in double, round once on assignment */
+    float fov = (float)(atan2((double)v->cy, (double)v->fy) + atan2((double)(height - v->cy), (double)v->fy));
+    float tang = (float)tan((double)(fov / 2));
+    float hf = tang * v->far_plane, wf = hf * aspect, hn = tang * v->near_plane, wn = hn * aspect;
+    float ftl[3], ftr[3], fbl[3], fbr[3], ntl[3], ntr[3], nbl[3], nbr[3];
+    for (int i = 0; i < 3; ++i)
+    {
+        float fc = pos[i] + fwd[i] * v->far_plane, nc = pos[i] + fwd[i] * v->near_plane;
+        ftl[i] = fc + (up[i] * hf) - (right[i] * wf); ftr[i] = fc + (up[i] * hf) + (right[i] * wf);
+        fbl[i] = fc - (up[i] * hf) - (right[i] * wf); fbr[i] = fc - (up[i] * hf) + (right[i] * wf);
+        ntl[i] = nc + (up[i] * hn) - (right[i] * wn); ntr[i] = nc + (up[i] * hn) + (right[i] * wn);
+        nbl[i] = nc - (up[i] * hn) - (right[i] * wn); nbr[i] = nc - (up[i] * hn) + (right[i] * wn);
+    }
+    get_plane(ntl, ftl, ntr, planes + 0);
+    get_plane(ftl, ntl, fbl, planes + 4);
+    get_plane(ntr, ftr, nbr, planes + 8);
+    get_plane(nbr, fbl, nbl, planes + 12);
+    get_plane(nbl, ntl, nbr, planes + 16);
+    get_plane(ftr, ftl, fbr, planes + 20);
+}
+/* Frustum::ContainPoint, src/Integration/Frustum.h:74-103 */
+int orc_frustum_contains(const float *pl, float x, float y, float z)
+{
+    const float p[3] = {x, y, z};
+    for (int i = 0; i < 6; ++i)
+    {
+        float d = dot3(pl + 4 * i, p) + pl[4 * i + 3];
+        if (d < 0) return 0;
+        if (d == 0) return 1;
+    }
+    return 1;
+}
+/* Eigen Matrix4f * Vector4f(x,y,z,1) row r (vectorised gemv): ((m0*x + m1*y) + m2*z) + m3*1 */
+static float row_xyz1(const float *m, int r, float x, float y, float z)
+{
+    return ((m[r] * x + m[4 + r] * y) + m[8 + r] * z) + m[12 + r];
+}
+static float depth_at(const orc_volume *v, const void *depth, int is_u16, int row, int col)
+{
+    if (is_u16) return ((const unsigned short *)depth)[row * v->width + col] / v->depth_scale;
+    return ((const float *)depth)[row * v->width + col];
+}
+
+/* ------------------------------------------------------------------------------------------------------- */
+/* cube selection                                                                                          */
+/* ------------------------------------------------------------------------------------------------------- */
+/* CubeHandler::ComputeBounding, src/Integration/CubeHandler.cpp:116-145
+ * (PointCloud::LoadFromDepth PointCloud.cpp:72-100, geometry::TransformPoints Geometry.cpp:19-27) */
+void orc_volume_bounding(const orc_volume *v, const void *depth, int is_u16, const float *T, float *mx, float *mn)
+{
+    float planes[24];
+    orc_frustum_planes(v, T, planes);
+    for (int a = 0; a < 3; ++a) { mx[a] = -FLT_MAX; mn[a] = FLT_MAX; }
+    for (int i = 0; i < v->height; ++i)
+        for (int j = 0; j < v->width; ++j)
+        {
+            float z = depth_at(v, depth, is_u16, i, j);
+            if (!(z > 0)) continue;
+            float x = (j - v->cx) * z / v->fx;
+            float y = (i - v->cy) * z / v->fy;
+            float w = row_xyz1(T, 3, x, y, z);
+            float p[3] = {row_xyz1(T, 0, x, y, z) / w, row_xyz1(T, 1, x, y, z) / w, row_xyz1(T, 2, x, y, z) / w};
+            if (!orc_frustum_contains(planes, p[0], p[1], p[2])) continue;
+            for (int a = 0; a < 3; ++a)
+            {
+                mx[a] = (p[a] < mx[a]) ? mx[a] : p[a]; /* std::max(p, max) */
+                mn[a] = (mn[a] < p[a]) ? mn[a] : p[a]; /* std::min(p, min) */
+            }
+        }
+}
+/* Integrator::GetSDF, src/Integration/Integrator.cpp:8-35 (pose_inv passed in: it is loop-invariant) */
+static float get_sdf(const orc_volume *v, const void *depth, int is_u16, const float *pinv, float x, float y, float z)
+{
+    float X = row_xyz1(pinv, 0, x, y, z), Y = row_xyz1(pinv, 1, x, y, z), Z = row_xyz1(pinv, 2, x, y, z);
+    int u = cvtt_d(v->fx * X / Z + 0.5 + v->cx);
+    int w = cvtt_d(v->fy * Y / Z + 0.5 + v->cy);
+    if (w < 0 || w >= v->height || u < 0 || u >= v->width) return 999;
+    float d = depth_at(v, depth, is_u16, w, u);
+    if (d <= 0) return 999;
+    return d - Z;
+}
+void orc_volume_get_sdf(const orc_volume *v, const void *depth, int is_u16, const float *pose_cm, const float *pts, long n,
+                        float *sdf)
+{
+    float pinv[16];
+    orc_pose_inverse(pose_cm, pinv);
+    for (long i = 0; i < n; ++i) sdf[i] = get_sdf(v, depth, is_u16, pinv, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+}
+/* CubePara::GetCubeID(Point3), VoxelCube.h:63-74 */
+static int cube_id_of(float p, float res)
+{
+    int voxel = cvtt_f(floorf(p / res));
+    return cvtt_d(floor((voxel + 0.0) / CUBE));
+}
+/* CubeHandler::PrepareCubes, src/Integration/CubeHandler.cpp:147-196 */
+static long prepare_cubes(orc_volume *v, const void *depth, int is_u16, const float *pose_cm, const float *pinv,
+                          cube_t ***list_out)
+{
+    float mx[3], mn[3];
+    orc_volume_bounding(v, depth, is_u16, pose_cm, mx, mn);
+    int hi[3], lo[3];
+    for (int a = 0; a < 3; ++a) { hi[a] = cube_id_of(mx[a], v->res); lo[a] = cube_id_of(mn[a], v->res); }
+    static const int corner_voxel[8] = {0, CUBE - 1, (CUBE - 1) * CUBE, (CUBE - 1) * CUBE + CUBE - 1,
+                                        CUBE * CUBE * (CUBE - 1), CUBE * CUBE * (CUBE - 1) + CUBE - 1,
+                                        CUBE * CUBE * (CUBE - 1) + CUBE * (CUBE - 1),
+                                        CUBE * CUBE * (CUBE - 1) + CUBE * (CUBE - 1) + CUBE - 1};
+    float cube_res = v->res * CUBE;
+    long n = 0, cap = 1024;
+    cube_t **list = (cube_t **)malloc(sizeof(cube_t *) * cap);
+    for (long i = (long)lo[0] - 1; i <= (long)hi[0] + 1; ++i)
+        for (long j = (long)lo[1] - 1; j <= (long)hi[1] + 1; ++j)
+            for (long k = (long)lo[2] - 1; k <= (long)hi[2] + 1; ++k)
+            {
+                float min_sdf = FLT_MAX;
+                for (int c = 0; c < 8; ++c)
+                {
+                    const float *o = v->centroid[corner_voxel[c]];
+                    float sdf = get_sdf(v, depth, is_u16, pinv, (int)i * cube_res + o[0], (int)j * cube_res + o[1],
+                                        (int)k * cube_res + o[2]);
+                    if (min_sdf > fabsf(sdf)) min_sdf = fabsf(sdf);
+                }
+                if (min_sdf < v->trunc)
+                {
+                    cube_t *c = find_cube(v, (int)i, (int)j, (int)k);
+                    if (!c) c = add_cube(v, (int)i, (int)j, (int)k);
+                    if (n == cap) { cap *= 2; list = (cube_t **)realloc(list, sizeof(cube_t *) * cap); }
+                    list[n++] = c;
+                }
+            }
+    *list_out = list;
+    return n;
+}
+long orc_volume_prepare_cubes(orc_volume *v, const void *depth, int is_u16, const float *pose_cm, int32_t *ids, long cap)
+{
+    float pinv[16];
+    orc_pose_inverse(pose_cm, pinv);
+    cube_t **list;
+    long n = prepare_cubes(v, depth, is_u16, pose_cm, pinv, &list);
+    for (long i = 0; i < n && i < cap; ++i)
+        for (int a = 0; a < 3; ++a) ids[3 * i + a] = list[i]->id[a];
+    free(list);
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------------------- */
+/* voxel update                                                                                            */
+/* ------------------------------------------------------------------------------------------------------- */
+/* Integrator::IntegrateImage, src/Integration/Integrator.cpp:36-94; TSDFVoxel::operator+ TSDFVoxel.h:24-39 */
+static void integrate_cube(const orc_volume *v, const void *depth, int is_u16, const uint8_t *bgr, const float *pinv,
+                           cube_t *cube)
+{
+    const float ox = (float)cube->id[0] * CUBE * v->res, oy = (float)cube->id[1] * CUBE * v->res,
+                oz = (float)cube->id[2] * CUBE * v->res; /* GetGlobalPoint, VoxelCube.h:75-80 */
+    for (int n = 0; n < NVOX; ++n)
+    {
+        const float px = ox + v->centroid[n][0], py = oy + v->centroid[n][1], pz = oz + v->centroid[n][2];
+        float X = row_xyz1(pinv, 0, px, py, pz), Y = row_xyz1(pinv, 1, px, py, pz), Z = row_xyz1(pinv, 2, px, py, pz);
+        int u = cvtt_d(v->fx * X / Z + 0.5 + v->cx);
+        int w = cvtt_d(v->fy * Y / Z + 0.5 + v->cy);
+        if (w < 0 || w >= v->height || u < 0 || u >= v->width) continue;
+        float d = depth_at(v, depth, is_u16, w, u);
+        if (d <= 0) continue;
+        float new_sdf = d - Z;
+        if (fabsf(new_sdf) < v->trunc)
+        {
+            const uint8_t *px3 = bgr + 3 * ((size_t)w * v->width + u);
+            float nc[3] = {px3[0] / 255.0f, px3[1] / 255.0f, px3[2] / 255.0f};
+            voxel_t *vx = &cube->vox[n];
+            int valid = !(vx->sdf >= 1 || vx->weight <= 0);
+            if (valid && vx->weight != 0)
+            {
+                float W = vx->weight + 1.0f;
+                voxel_t r = {999, W, {-1, -1, -1}};
+                if (W != 0)
+                {
+                    r.sdf = (vx->weight * vx->sdf + 1.0f * new_sdf) / W;
+                    for (int a = 0; a < 3; ++a) r.c[a] = (vx->weight * vx->c[a] + 1.0f * nc[a]) / W;
+                }
+                *vx = r;
+            }
+            else
+            {
+                vx->sdf = new_sdf; vx->weight = 1.0f;
+                vx->c[0] = nc[0]; vx->c[1] = nc[1]; vx->c[2] = nc[2];
+            }
+        }
+    }
+}
+/* CubeHandler::IntegrateImage, src/Integration/CubeHandler.cpp:197-210 */
+long orc_volume_integrate(orc_volume *v, const void *depth, int is_u16, const uint8_t *bgr, const float *pose_cm)
+{
+    float pinv[16];
+    orc_pose_inverse(pose_cm, pinv);
+    cube_t **list;
+    long n = prepare_cubes(v, depth, is_u16, pose_cm, pinv, &list);
+    for (long i = 0; i < n; ++i) integrate_cube(v, depth, is_u16, bgr, pinv, list[i]);
+    free(list);
+    return n;
+}
+void orc_volume_download(const orc_volume *v, int32_t *ids, float *voxels)
+{
+    for (long c = 0; c < v->n_cubes; ++c)
+    {
+        for (int a = 0; a < 3; ++a) ids[3 * c + a] = v->cubes[c]->id[a];
+        memcpy(voxels + (size_t)c * NVOX * 5, v->cubes[c]->vox, sizeof(voxel_t) * NVOX);
+    }
+}
+void orc_volume_upload(orc_volume *v, const int32_t *ids, const float *voxels, long n)
+{
+    orc_volume_clear(v);
+    for (long c = 0; c < n; ++c)
+    {
+        cube_t *cube = find_cube(v, ids[3 * c], ids[3 * c + 1], ids[3 * c + 2]);
+        if (!cube) cube = add_cube(v, ids[3 * c], ids[3 * c + 1], ids[3 * c + 2]);
+        memcpy(cube->vox, voxels + (size_t)c * NVOX * 5, sizeof(voxel_t) * NVOX);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------- */
+/* Marching Cubes                                                                                          */
+/* ------------------------------------------------------------------------------------------------------- */
+/* integration::MarchingCube, src/Integration/MarchingCube.cpp:9-74 */
+int orc_marching_cube_cell(const float *corners, const float *sdf, const float *colors, float *xyz, float *rgb)
+{
+    int cs = 0;
+    for (int i = 0; i < 8; ++i)
+        if (sdf[i] > 0) cs |= 1 << i; /* DetermineCase, :18-29 */
+    uint64_t row = kMcCases[cs];
+    int n = 0;
+    for (int k = 0; k < 15; ++k)
+    {
+        int e = (int)((row >> (4 * k)) & 0xF);
+        if (e == 0xF) break;
+        int a = kMcEdgeCorners[e][0], b = kMcEdgeCorners[e][1];
+        /* InterpolateEdgeVetex, :9-16 */
+        float diff = sdf[b] - sdf[a];
+        float t = sdf[a] / diff;
+        for (int c = 0; c < 3; ++c)
+        {
+            xyz[3 * n + c] = corners[3 * a + c] - t * (corners[3 * b + c] - corners[3 * a + c]);
+            rgb[3 * n + c] = (colors[3 * a + c] + colors[3 * b + c]) / 2;
+        }
+        ++n;
+    }
+    return n;
+}
+/* CubeHandler::ExtractTriangleMesh / GenerateMeshByCube, src/Integration/CubeHandler.cpp:9-44,70-114 */
+long orc_volume_extract_mesh(const orc_volume *v, float **xyz_out, float **rgb_out)
+{
+    long n = 0, cap = 1 << 16;
+    float *xyz = (float *)malloc(sizeof(float) * 3 * cap), *rgb = (float *)malloc(sizeof(float) * 3 * cap);
+    const float cube_res = CUBE * v->res; /* VoxelCube::GetOrigin, VoxelCube.h:143-147 */
+    for (long ci = 0; ci < v->n_cubes; ++ci)
+    {
+        const cube_t *cube = v->cubes[ci];
+        /* the (up to) 8 cubes a boundary cell reaches into, indexed by offset bits x | y<<1 | z<<2 */
+        const cube_t *nb[8];
+        for (int o = 0; o < 8; ++o)
+            nb[o] = o == 0 ? cube : find_cube(v, cube->id[0] + (o & 1), cube->id[1] + ((o >> 1) & 1), cube->id[2] + ((o >> 2) & 1));
+        for (int x = 0; x < CUBE; ++x)
+            for (int y = 0; y < CUBE; ++y)
+                for (int z = 0; z < CUBE; ++z)
+                {
+                    const int ex = x == CUBE - 1, ey = y == CUBE - 1, ez = z == CUBE - 1;
+                    float corners[24], sdf[8], colors[24];
+                    int ok = 1;
+                    for (int i = 0; i < 8 && ok; ++i)
+                    {
+                        const int dx = kMcCornerOffset[i][0], dy = kMcCornerOffset[i][1], dz = kMcCornerOffset[i][2];
+                        const cube_t *nc = nb[(dx & ex) | ((dy & ey) << 1) | ((dz & ez) << 2)];
+                        if (!nc) { ok = 0; break; }
+                        const int vid = (x + dx) % CUBE + ((y + dy) % CUBE) * CUBE + ((z + dz) % CUBE) * CUBE * CUBE;
+                        const voxel_t *vx = &nc->vox[vid];
+                        if (vx->sdf >= 1 || vx->weight <= 0) { ok = 0; break; } /* !IsValid() */
+                        for (int a = 0; a < 3; ++a)
+                        {
+                            corners[3 * i + a] = nc->id[a] * cube_res + v->centroid[vid][a];
+                            colors[3 * i + a] = vx->c[a];
+                        }
+                        sdf[i] = vx->sdf;
+                    }
+                    if (!ok) continue;
+                    if (n + 15 > cap)
+                    {
+                        cap *= 2;
+                        xyz = (float *)realloc(xyz, sizeof(float) * 3 * cap);
+                        rgb = (float *)realloc(rgb, sizeof(float) * 3 * cap);
+                    }
+                    n += orc_marching_cube_cell(corners, sdf, colors, xyz + 3 * n, rgb + 3 * n);
+                }
+    }
+    *xyz_out = xyz;
+    *rgb_out = rgb;
+    return n;
+}

@@ -1,0 +1,53 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- the CPU oracle.  Never linked into, imported by or called from the product
+ * (onepiece_b200/); only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load it, and there only as the checker or as the CPU baseline.
+ *
+ * Plain-C restatement of the reference's algorithm for the hot path (file:line relative to the reference
+ * tree are given at every function in opb_oracle.c).  It is pinned, bit for bit on the integration and
+ * Marching Cubes paths, against the reference's own translation units compiled unmodified
+ * (oracle/_ref, see oracle/Makefile) by tests/test_oracle_vs_ref.py and against the committed golden
+ * fixtures in tests/golden/ (generated from oracle/_ref by tests/golden/gen_golden.py).
+ */
+#ifndef OPB_ORACLE_H
+#define OPB_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_volume orc_volume;
+
+orc_volume *orc_volume_create(float fx, float fy, float cx, float cy, int width, int height, float depth_scale,
+                              float voxel_resolution, float truncation, float near_plane, float far_plane);
+void orc_volume_destroy(orc_volume *v);
+void orc_volume_clear(orc_volume *v);
+/* Eigen Matrix4f inverse / frustum planes as the reference evaluates them (column-major in and out) */
+void orc_pose_inverse(const float *pose_cm, float *inv_cm);
+void orc_frustum_planes(const orc_volume *v, const float *pose_cm, float *planes24);
+int orc_frustum_contains(const float *planes24, float x, float y, float z);
+/* CubeHandler::ComputeBounding */
+void orc_volume_bounding(const orc_volume *v, const void *depth, int is_u16, const float *pose_cm, float *max3,
+                         float *min3);
+/* Integrator::GetSDF at n points */
+void orc_volume_get_sdf(const orc_volume *v, const void *depth, int is_u16, const float *pose_cm, const float *points,
+                        long n, float *sdf);
+/* CubeHandler::PrepareCubes: allocates, returns the list (3 ints per cube) in the reference's loop order */
+long orc_volume_prepare_cubes(orc_volume *v, const void *depth, int is_u16, const float *pose_cm, int32_t *ids, long cap);
+/* CubeHandler::IntegrateImage; returns the number of cubes listed for the frame */
+long orc_volume_integrate(orc_volume *v, const void *depth, int is_u16, const uint8_t *bgr, const float *pose_cm);
+long orc_volume_num_cubes(const orc_volume *v);
+/* ids n*3, voxels n*512*5 (sdf, weight, c0, c1, c2), insertion order */
+void orc_volume_download(const orc_volume *v, int32_t *ids, float *voxels);
+void orc_volume_upload(orc_volume *v, const int32_t *ids, const float *voxels, long n);
+/* CubeHandler::ExtractTriangleMesh: returns the vertex count (3 per triangle); buffers are malloc'ed */
+long orc_volume_extract_mesh(const orc_volume *v, float **xyz, float **rgb);
+/* integration::MarchingCube on one cell: returns the vertex count, writes up to 15 xyz / rgb triples */
+int orc_marching_cube_cell(const float *corners24, const float *sdf8, const float *colors24, float *xyz, float *rgb);
+void orc_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

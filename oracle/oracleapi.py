@@ -1,0 +1,164 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes loader for oracle/libopb_oracle.so, the plain-C restatement of the
+reference algorithm (oracle/opb_oracle.c).  Imported by tests/, bench.py's cpu_baseline / --impl reference legs
+and __graft_entry__.smoke() only; never by the product package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libopb_oracle.so")
+_LIB = None
+
+c_f, c_d, c_i, c_l, c_p = C.c_float, C.c_double, C.c_int, C.c_long, C.c_void_p
+
+
+def build(force: bool = False) -> str:
+    src = [os.path.join(_HERE, f) for f in ("opb_oracle.c", "opb_oracle.h")]
+    src.append(os.path.join(_HERE, "..", "onepiece_b200", "csrc", "opb_mc_table.h"))
+    if force or not os.path.exists(_LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src):
+        subprocess.check_call(["make", "-C", _HERE, "oracle", "-B"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    build()
+    L = C.CDLL(_LIB_PATH)
+    L.orc_volume_create.restype = c_p
+    L.orc_volume_create.argtypes = [c_f] * 4 + [c_i, c_i] + [c_f] * 5
+    L.orc_volume_destroy.argtypes = [c_p]
+    L.orc_volume_clear.argtypes = [c_p]
+    L.orc_pose_inverse.argtypes = [c_p, c_p]
+    L.orc_frustum_planes.argtypes = [c_p, c_p, c_p]
+    L.orc_frustum_contains.restype = c_i
+    L.orc_frustum_contains.argtypes = [c_p, c_f, c_f, c_f]
+    L.orc_volume_bounding.argtypes = [c_p, c_p, c_i, c_p, c_p, c_p]
+    L.orc_volume_get_sdf.argtypes = [c_p, c_p, c_i, c_p, c_p, c_l, c_p]
+    L.orc_volume_prepare_cubes.restype = c_l
+    L.orc_volume_prepare_cubes.argtypes = [c_p, c_p, c_i, c_p, c_p, c_l]
+    L.orc_volume_integrate.restype = c_l
+    L.orc_volume_integrate.argtypes = [c_p, c_p, c_i, c_p, c_p]
+    L.orc_volume_num_cubes.restype = c_l
+    L.orc_volume_num_cubes.argtypes = [c_p]
+    L.orc_volume_download.argtypes = [c_p, c_p, c_p]
+    L.orc_volume_upload.argtypes = [c_p, c_p, c_p, c_l]
+    L.orc_volume_extract_mesh.restype = c_l
+    L.orc_volume_extract_mesh.argtypes = [c_p, C.POINTER(c_p), C.POINTER(c_p)]
+    L.orc_marching_cube_cell.restype = c_i
+    L.orc_marching_cube_cell.argtypes = [c_p] * 5
+    L.orc_free.argtypes = [c_p]
+    _LIB = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(c_p) if a is not None else None
+
+
+def _pose_cm(pose):
+    return np.ascontiguousarray(np.asarray(pose, dtype=np.float32).reshape(4, 4).T).reshape(16)
+
+
+def pose_inverse(pose):
+    p = _pose_cm(pose)
+    out = np.zeros(16, np.float32)
+    lib().orc_pose_inverse(_ptr(p), _ptr(out))
+    return out.reshape(4, 4).T.copy()
+
+
+class OracleVolume:
+    """CPU restatement of one_piece::integration::CubeHandler."""
+
+    def __init__(self, cam, voxel_resolution=0.01, truncation=0.1, near=0.5, far=5.0):
+        self.L = lib()
+        self.cam = cam
+        self.h = self.L.orc_volume_create(cam.fx, cam.fy, cam.cx, cam.cy, cam.width, cam.height, cam.depth_scale,
+                                          voxel_resolution, truncation, near, far)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_volume_destroy(self.h)
+            self.h = None
+
+    def clear(self):
+        self.L.orc_volume_clear(self.h)
+
+    def frustum(self, pose, points):
+        p = _pose_cm(pose)
+        planes = np.zeros(24, np.float32)
+        self.L.orc_frustum_planes(self.h, _ptr(p), _ptr(planes))
+        pts = np.ascontiguousarray(points, np.float32)
+        mask = np.array([self.L.orc_frustum_contains(_ptr(planes), float(a), float(b), float(c)) for a, b, c in pts], bool)
+        return planes.reshape(6, 4), mask
+
+    def bounding(self, depth, pose):
+        depth = np.ascontiguousarray(depth)
+        p = _pose_cm(pose)
+        mx = np.zeros(3, np.float32)
+        mn = np.zeros(3, np.float32)
+        self.L.orc_volume_bounding(self.h, _ptr(depth), int(depth.dtype == np.uint16), _ptr(p), _ptr(mx), _ptr(mn))
+        return mx, mn
+
+    def get_sdf(self, depth, pose, points):
+        depth = np.ascontiguousarray(depth)
+        pts = np.ascontiguousarray(points, np.float32)
+        out = np.zeros(len(pts), np.float32)
+        p = _pose_cm(pose)
+        self.L.orc_volume_get_sdf(self.h, _ptr(depth), int(depth.dtype == np.uint16), _ptr(p), _ptr(pts), len(pts), _ptr(out))
+        return out
+
+    def prepare_cubes(self, depth, pose):
+        depth = np.ascontiguousarray(depth)
+        p = _pose_cm(pose)
+        cap = 1 << 22
+        ids = np.zeros((cap, 3), np.int32)
+        n = self.L.orc_volume_prepare_cubes(self.h, _ptr(depth), int(depth.dtype == np.uint16), _ptr(p), _ptr(ids), cap)
+        return ids[:n].copy()
+
+    def integrate(self, depth, bgr, pose) -> int:
+        depth = np.ascontiguousarray(depth)
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        p = _pose_cm(pose)
+        return self.L.orc_volume_integrate(self.h, _ptr(depth), int(depth.dtype == np.uint16), _ptr(bgr), _ptr(p))
+
+    def num_cubes(self) -> int:
+        return self.L.orc_volume_num_cubes(self.h)
+
+    def download(self):
+        n = self.num_cubes()
+        ids = np.zeros((n, 3), np.int32)
+        vox = np.zeros((n, 512, 5), np.float32)
+        self.L.orc_volume_download(self.h, _ptr(ids), _ptr(vox))
+        order = np.lexsort((ids[:, 2], ids[:, 1], ids[:, 0]))
+        return ids[order], vox[order]
+
+    def upload(self, ids, vox):
+        ids = np.ascontiguousarray(ids, np.int32)
+        vox = np.ascontiguousarray(vox, np.float32)
+        self.L.orc_volume_upload(self.h, _ptr(ids), _ptr(vox), len(ids))
+
+    def extract_mesh(self):
+        """-> (points [nv,3], colors [nv,3]); triangle i = vertices 3i..3i+2"""
+        xyz, rgb = c_p(), c_p()
+        n = self.L.orc_volume_extract_mesh(self.h, C.byref(xyz), C.byref(rgb))
+        pts = np.ctypeslib.as_array(C.cast(xyz, C.POINTER(c_f)), shape=(max(n, 1) * 3,))[: n * 3].reshape(n, 3).copy()
+        col = np.ctypeslib.as_array(C.cast(rgb, C.POINTER(c_f)), shape=(max(n, 1) * 3,))[: n * 3].reshape(n, 3).copy()
+        self.L.orc_free(xyz)
+        self.L.orc_free(rgb)
+        return pts, col
+
+
+def marching_cube_cell(corners, sdf, colors):
+    corners = np.ascontiguousarray(corners, np.float32)
+    sdf = np.ascontiguousarray(sdf, np.float32)
+    colors = np.ascontiguousarray(colors, np.float32)
+    xyz = np.zeros((15, 3), np.float32)
+    rgb = np.zeros((15, 3), np.float32)
+    n = lib().orc_marching_cube_cell(_ptr(corners), _ptr(sdf), _ptr(colors), _ptr(xyz), _ptr(rgb))
+    return xyz[:n], rgb[:n]

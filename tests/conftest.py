@@ -1,0 +1,64 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+def _gpu_available() -> bool:
+    try:
+        from onepiece_b200 import capi
+        return capi.lib.opb_device_count() > 0
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    # -m gpu on a box without a device must fail loudly, not skip: the product has no CPU path
+    pass
+
+
+@pytest.fixture(scope="session")
+def ref_available():
+    from oracle import refapi
+    return refapi.available("f32")
+
+
+def bits(a):
+    a = np.ascontiguousarray(a, np.float32)
+    return a.view(np.uint32)
+
+
+def assert_bit_equal(a, b, what=""):
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    same = a.view(np.uint32) == b.view(np.uint32)
+    if not same.all():
+        idx = np.argwhere(~same)
+        first = tuple(idx[0])
+        raise AssertionError(f"{what}: {len(idx)} of {same.size} floats differ bitwise; first at {first}: "
+                             f"{a[first]!r} vs {b[first]!r}")
+
+
+def canon_triangles(points, colors):
+    """Order-independent form of a 3-vertices-per-triangle mesh: rows of 18 floats sorted lexicographically."""
+    p = np.ascontiguousarray(points, np.float32).reshape(-1, 9)
+    c = np.ascontiguousarray(colors, np.float32).reshape(-1, 9)
+    a = np.concatenate([p, c], 1)
+    return a[np.lexsort(a.T[::-1])]
+
+
+def sha(a) -> str:
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
