@@ -60,6 +60,11 @@ void opb_pose_inverse(const float pose_colmajor[16], float inverse_colmajor[16])
 void opb_frustum_planes(float fx, float fy, float cy, int width, int height, float near_plane, float far_plane,
                         const float pose_colmajor[16], float planes[24]);
 
+/* Device self-test: compares the shared-reciprocal quotient used by the voxel-update kernel with div.rn on n
+ * pseudo-random operand pairs (mode 0: integer divisors 1..2^24 as in TSDFVoxel::operator+; mode 1: arbitrary
+ * operands with exponents within +-40 of 1.0 as in the projection) and returns the number of bitwise mismatches. */
+int opb_selftest_quotient(int device, uint64_t n, uint64_t seed, int mode, uint64_t *mismatches);
+
 /* ------------------------------------------------------------------------------------------------------
  * TSDF volume  (replaces one_piece::integration::CubeHandler, src/Integration/CubeHandler.h:24-366)
  * ---------------------------------------------------------------------------------------------------- */

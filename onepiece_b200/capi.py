@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libonepiece_b200.so")
+# OPB_LIB_PATH: developer hook to A/B-test alternative builds of the same library
+LIB_PATH = os.environ.get("OPB_LIB_PATH") or os.path.join(HERE, "libonepiece_b200.so")
 
 OPB_OK = 0
 OPB_ERR_INVALID = -1
@@ -66,6 +67,7 @@ SIGNATURES = {
     "opb_free": (None, [_p]),
     "opb_pose_inverse": (None, [_p, _p]),
     "opb_frustum_planes": (None, [C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_float, C.c_float, _p, _p]),
+    "opb_selftest_quotient": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
     "opb_volume_desc_default": (None, [C.POINTER(VolumeDesc)]),
     "opb_volume_create": (C.c_int, [C.POINTER(VolumeDesc), C.POINTER(_p)]),
     "opb_volume_destroy": (None, [_p]),

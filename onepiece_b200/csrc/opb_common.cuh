@@ -32,6 +32,24 @@ __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b)
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 
+// Correctly rounded a/b for several numerators sharing one divisor: y = RN(1/b) once (rcp_rn), then per
+// numerator q = RN(a*y), r = a - b*q (exact in one FMA), RN(q + r*y).  With y the correctly rounded reciprocal
+// this last step returns RN(a/b) (Markstein's quotient-refinement theorem); tests/test_division.py checks it
+// against IEEE division on 4.6e8 operand pairs, including every integer divisor up to 70,000 (the weights W of
+// TSDFVoxel::operator+) and all-ones significands.  Operands outside the guarded range take __fdiv_rn.
+__device__ __forceinline__ bool rcp_safe(float b)
+{
+    const float ab = fabsf(b);
+    return ab > 1e-18f && ab < 1e18f; // also false for NaN, 0, inf
+}
+__device__ __forceinline__ float div_by(float a, float b, float y, bool safe)
+{
+    if (!safe) return __fdiv_rn(a, b);
+    const float q = __fmul_rn(a, y);
+    const float r = __fmaf_rn(-b, q, a);
+    return __fmaf_rn(r, y, q);
+}
+
 // x86 cvttsd2si semantics: C truncation toward zero, INT_MIN ("integer indefinite") for NaN and for values
 // that do not fit -- CUDA's own conversion saturates and maps NaN to 0, which would select pixel 0.
 __device__ __forceinline__ int cvtt_x86(double d)

@@ -27,7 +27,7 @@ struct FrameCounters
     int candidate_cubes;
     int frame_cubes;
     int overflow;
-    int pad;
+    int wild_frame; // a depth value outside [1e-6, 1e6] m was seen: the update kernel takes its IEEE-division path
     unsigned long long updated_voxels;
 };
 
@@ -37,8 +37,10 @@ struct VolumeDev
     int *slot_ids;            // max_cubes * 3
     unsigned long long *keys; // table_cap
     int *vals;                // table_cap
-    int *frame_list;          // max_cubes
+    int4 *frame_list;         // max_cubes entries {slot, i, j, k}: one 16-byte load gives the update kernel all it needs
     int *n_alloc;             // cubes allocated so far
+    int *tainted;             // != 0 after an upload of values outside the range the fast quotient is exact for
+    float2 *texels;           // per-frame W*H texels {depth in metres (f32), b | g<<8 | r<<16 as raw bits}
     FrameCounters *fc;        // counters of the frame in flight
     int max_cubes;
     unsigned int table_mask;
@@ -58,7 +60,10 @@ struct FrameParams
     float pose[16];  // camera-to-world, column-major
     float pinv[16];  // Eigen-order inverse of pose, column-major
     float planes[24];
+    double cx_d, cy_d;       // (double)cx, (double)cy: second operand of the reference's double adds
+    double width_d, height_d;
     int shard_rank, shard_world, shard_axis, shard_slab;
+    int exact_division; // host decision: pose / intrinsics outside the tame range -> IEEE-division path
 };
 
 __host__ __device__ __forceinline__ bool pack_id(int i, int j, int k, unsigned long long &key)

@@ -285,3 +285,80 @@ def test_sharded_volumes_partition_the_cubes():
     order = np.lexsort((ids[:, 2], ids[:, 1], ids[:, 0]))
     assert np.array_equal(ids[order], fi)
     assert_bit_equal(vox[order], fv, "sharded union")
+
+
+def test_long_sequence_weights_up_to_120():
+    """Exercises the shared-reciprocal quotient of the blend for every integer weight W = 2..120 on real data."""
+    c0 = scenes.Camera()
+    cam = scenes.Camera(c0.fx / 8, c0.fy / 8, c0.cx / 8, c0.cy / 8, 80, 60, 1000.0)
+    gpu, ov = CubeHandler(cam, 0.04, max_cubes=4096), oracleapi.OracleVolume(cam, 0.04)
+    rng = np.random.default_rng(5)
+    for k in range(120):
+        d, c = scenes.wavy_wall(cam, k)
+        c = rng.integers(0, 256, c.shape, dtype=np.uint8)
+        T = scenes.se3_exp(rng.normal(0, 0.01, 6)).astype(np.float32)
+        gpu.IntegrateImage(d, c, T)
+        ov.integrate(d, c, T)
+    compare_volumes(gpu, ov)
+    assert gpu.GetCubeMap()[1][..., 1].max() >= 100
+
+
+def test_wild_depth_values_take_the_ieee_division_path():
+    """Depth values far outside any sensor's range (1e-9 m, 1e9 m) make the frame 'wild': the update kernel must
+    switch to IEEE division and still match the oracle bit for bit.  (+inf depth is excluded: it back-projects to
+    NaN points, and the reference's running std::max/std::min then depends on the raster position of that pixel.)"""
+    cam = small_camera()
+    gpu, ov = CubeHandler(cam, 0.02, max_cubes=8192), oracleapi.OracleVolume(cam, 0.02)
+    I = np.eye(4, dtype=np.float32)
+    d, c = scenes.wavy_wall(cam, 0)
+    gpu.IntegrateImage(d, c, I)
+    ov.integrate(d, c, I)
+    d2 = d.copy()
+    d2[10:20, 10:20] = 1e-9
+    d2[30:40, 50:60] = 1e9
+    d2[60:70, 60:90] = 3e-7
+    gpu.IntegrateImage(d2, c, I)
+    ov.integrate(d2, c, I)
+    compare_volumes(gpu, ov)
+
+
+def test_uploaded_wild_values_take_the_ieee_division_path():
+    cam = small_camera()
+    gpu, ov = CubeHandler(cam, 0.02, max_cubes=4096), oracleapi.OracleVolume(cam, 0.02)
+    I = np.eye(4, dtype=np.float32)
+    d, c = scenes.wavy_wall(cam, 0)
+    ov.integrate(d, c, I)
+    ids, vox = ov.download()
+    rng = np.random.default_rng(1)
+    vox = vox.copy()
+    n = vox.shape[0]
+    vox[: n // 4, ::3, 0] = 1e-30          # denormal-range quotients
+    vox[: n // 4, ::5, 1] = 2.5            # non-integer weights
+    vox[n // 4: n // 2, ::7, 2:] = 1e25    # huge colours
+    vox[n // 2:, ::11, 1] = 3e7            # weights above 2^24
+    vox[n // 2:, ::13, 0] = -1e-41         # denormal sdf
+    gpu.SetCubeMap(ids, vox)
+    ov.upload(ids, vox)
+    for k in range(1, 4):
+        d, c = scenes.wavy_wall(cam, k)
+        gpu.IntegrateImage(d, c, I)
+        ov.integrate(d, c, I)
+    compare_volumes(gpu, ov)
+    # Clear() makes the volume tame again
+    gpu.Clear()
+    ov.clear()
+    gpu.IntegrateImage(d, c, I)
+    ov.integrate(d, c, I)
+    compare_volumes(gpu, ov)
+
+
+def test_wild_pose_takes_the_ieee_division_path():
+    cam = small_camera()
+    gpu, ov = CubeHandler(cam, 0.02, max_cubes=8192), oracleapi.OracleVolume(cam, 0.02)
+    d, c = scenes.wavy_wall(cam, 0)
+    T = np.eye(4, dtype=np.float32)
+    T[0, 1] = 1e-9  # shear far below the tame range
+    T[2, 3] = 1e-8
+    gpu.IntegrateImage(d, c, T)
+    ov.integrate(d, c, T)
+    compare_volumes(gpu, ov)
