@@ -154,6 +154,52 @@ int opb_volume_extract_mesh(opb_volume *v, float **xyz, float **rgb, uint32_t **
 /* counts only (no download) */
 int opb_volume_count_mesh(opb_volume *v, size_t *nv, size_t *nt);
 
+/* ------------------------------------------------------------------------------------------------------
+ * ICP  (replaces one_piece::registration::PointToPlane / PointToPoint, src/Registration/ICP.h:23-26,
+ *       src/Registration/ICP.cpp:31-224)
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct opb_icp opb_icp; /* reusable device workspace; one host thread at a time */
+
+/* registration::ICPParameter (ICP.h:13-19) */
+typedef struct
+{
+    int32_t max_iteration; /* 30  */
+    double threshold;      /* 0.2 : max distance of a correspondence */
+    double scaling;        /* 1.0 : PointToPlane refuses anything else, PointToPoint scales both clouds */
+} opb_icp_params;
+
+/* registration::RegistrationResult (RegistrationResult.h:8-16) */
+typedef struct
+{
+    float T[16];          /* result.T: Kabsch fit over the final inlier pairs of the original clouds (ICP.cpp:221),
+                             column-major; NOT the iterated transform */
+    float T_iterated[16]; /* start_T after the last iteration (what the loop converged to), column-major */
+    double rmse;          /* CountInliers' sqrt(sum_error / inliers) with the final transform */
+    size_t n_inliers;     /* correspondence_set_index.size() */
+    int32_t iterations;
+    int32_t status;       /* OPB_OK, or the error the reference reports by returning a default result */
+} opb_icp_result;
+
+void opb_icp_params_default(opb_icp_params *p);
+int opb_icp_create(int device, void *stream /* cudaStream_t or NULL */, opb_icp **out);
+void opb_icp_destroy(opb_icp *c);
+/* PointToPlane(source, target, init_T, params).  xyz arrays are 3 floats per point; they may be host or
+ * device pointers.  pairs (optional): up to pairs_cap (source index, target index) int32 pairs, ascending
+ * source index like correspondence_set_index.  Returns OPB_ERR_INVALID (and result->status) when the target has
+ * no normals or scaling != 1, the case in which the reference prints an error and returns a default result. */
+int opb_icp_point_to_plane(opb_icp *c, const float *src_xyz, size_t ns, const float *tgt_xyz, const float *tgt_normals,
+                           size_t nt, const float init_T_colmajor[16], const opb_icp_params *params,
+                           opb_icp_result *result, int32_t *pairs, size_t pairs_cap);
+int opb_icp_point_to_point(opb_icp *c, const float *src_xyz, size_t ns, const float *tgt_xyz, size_t nt,
+                           const float init_T_colmajor[16], const opb_icp_params *params, opb_icp_result *result,
+                           int32_t *pairs, size_t pairs_cap);
+/* nearest-neighbour index per source point from the last search of the previous call (-1: none within the
+ * threshold), for parity tests against KDTree::KnnSearch */
+int opb_icp_last_nn(opb_icp *c, int32_t *nn, size_t n);
+/* CUDA-event timing of the last call when enabled: grid construction and the iteration loop */
+int opb_icp_set_profiling(opb_icp *c, int on);
+int opb_icp_last_timing(opb_icp *c, float *grid_build_ms, float *iterations_ms);
+
 #ifdef __cplusplus
 }
 #endif

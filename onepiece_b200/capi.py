@@ -50,6 +50,15 @@ class FrameStats(C.Structure):
     ]
 
 
+class IcpParams(C.Structure):
+    _fields_ = [("max_iteration", C.c_int32), ("threshold", C.c_double), ("scaling", C.c_double)]
+
+
+class IcpResult(C.Structure):
+    _fields_ = [("T", C.c_float * 16), ("T_iterated", C.c_float * 16), ("rmse", C.c_double), ("n_inliers", C.c_size_t),
+                ("iterations", C.c_int32), ("status", C.c_int32)]
+
+
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} is missing: build it with `python -m onepiece_b200.build` (onepiece_b200 has no CPU path)")
@@ -86,6 +95,14 @@ SIGNATURES = {
     "opb_volume_upload": (C.c_int, [_p, _p, _p, _sz]),
     "opb_volume_extract_mesh": (C.c_int, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_sz), C.POINTER(_sz)]),
     "opb_volume_count_mesh": (C.c_int, [_p, C.POINTER(_sz), C.POINTER(_sz)]),
+    "opb_icp_params_default": (None, [C.POINTER(IcpParams)]),
+    "opb_icp_create": (C.c_int, [C.c_int, _p, C.POINTER(_p)]),
+    "opb_icp_destroy": (None, [_p]),
+    "opb_icp_point_to_plane": (C.c_int, [_p, _p, _sz, _p, _p, _sz, _p, C.POINTER(IcpParams), C.POINTER(IcpResult), _p, _sz]),
+    "opb_icp_point_to_point": (C.c_int, [_p, _p, _sz, _p, _sz, _p, C.POINTER(IcpParams), C.POINTER(IcpResult), _p, _sz]),
+    "opb_icp_last_nn": (C.c_int, [_p, _p, _sz]),
+    "opb_icp_set_profiling": (C.c_int, [_p, C.c_int]),
+    "opb_icp_last_timing": (C.c_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
 }
 
 

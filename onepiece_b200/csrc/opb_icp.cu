@@ -1,0 +1,847 @@
+// K7-K9: ICP (point-to-plane and point-to-point) on the device.
+//
+// Reference path rebuilt here (file:line relative to the reference tree):
+//   registration::PointToPlane        src/Registration/ICP.cpp:146-224
+//   registration::PointToPoint        src/Registration/ICP.cpp:31-107
+//   CountInliers                      src/Registration/ICP.cpp:9-30
+//   EstimateRigidTransformationPointToPlane  ICP.cpp:108-144   (6x6 J^T J, JacobiSVD solve, Se3ToSE3)
+//   geometry::TransformPoints         src/Geometry/Geometry.cpp:19-27
+//   geometry::EstimateRigidTransformation    src/Geometry/Geometry.cpp:107-151 (Kabsch; also result.T)
+//   KDTree<>::KnnSearch(k=1)          src/Geometry/KDTree.h:177-196 (nanoflann, exact, L2_Simple distance)
+//
+// Design.  The k-d tree is replaced by a uniform grid over the target cloud (counting sort by cell, points
+// stored cell-contiguous as float4 {x,y,z,index}); a query walks Chebyshev rings of cells around its home cell
+// and stops as soon as the best squared distance is provably minimal, so the answer is the exact nearest
+// neighbour (distance formula and summation order of nanoflann's L2_Simple_Adaptor).  The walk is capped at the
+// inlier threshold: a neighbour farther than that can never pass CountInliers, so it is reported as "none".
+// One kernel launch per ICP iteration does transform + search + inlier test + Jacobian row + the 29-scalar
+// reduction (warp shuffles in fp64, fixed-order block partials -> deterministic) and, in the last CTA to
+// finish, the 6x6 solve, the SE(3) exponential and the pose update -- the host is not involved until the end.
+#include <cfloat>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/onepiece_b200.h"
+#include "opb_common.cuh"
+#include "opb_linalg.h"
+
+namespace opb
+{
+constexpr int kIcpThreads = 256;
+constexpr int kPacket = 32;             // doubles per reduction packet (29 used for point-to-plane, 17 for point-to-point)
+constexpr unsigned int kMaxCells = 1u << 26;
+
+struct IcpGrid
+{
+    float origin[3];
+    float h, inv_h;
+    int dim[3];
+};
+
+struct IcpState // device-resident solver state
+{
+    float T[16];        // current source->target transform, column-major float (start_T)
+    double packet[kPacket];
+    unsigned int ticket;
+    int iteration;
+    IcpGrid grid;
+    float bbox_lo[3], bbox_hi[3];
+    unsigned int bbox_enc[6];
+    unsigned long long n_inliers;
+    double sum_error;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// grid construction
+// ---------------------------------------------------------------------------------------------------------
+__global__ void icp_bbox_kernel(const float *pts, int n, IcpState *st)
+{
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+            const float v = pts[3 * i + a];
+            if (v == v && fabsf(v) < FLT_MAX) { lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+        }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if ((threadIdx.x & 31) == 0)
+        {
+            if (lo[a] != FLT_MAX) atomicMin(&st->bbox_enc[a], float_to_ordered(lo[a]));
+            if (hi[a] != -FLT_MAX) atomicMax(&st->bbox_enc[3 + a], float_to_ordered(hi[a]));
+        }
+    }
+}
+
+// one thread: cell size such that the grid has at most kMaxCells cells and about two points per occupied
+// cell for surface-like clouds
+__global__ void icp_grid_setup_kernel(IcpState *st, int n, float min_cell)
+{
+    float ext[3];
+    for (int a = 0; a < 3; ++a)
+    {
+        float lo = ordered_to_float(st->bbox_enc[a]), hi = ordered_to_float(st->bbox_enc[3 + a]);
+        if (!(hi >= lo)) { lo = 0.0f; hi = 0.0f; }
+        st->bbox_lo[a] = lo;
+        st->bbox_hi[a] = hi;
+        ext[a] = hi - lo;
+    }
+    const float emax = fmaxf(ext[0], fmaxf(ext[1], ext[2]));
+    // surface heuristic: area ~ product of the two largest extents, spacing ~ sqrt(area / n)
+    const float emin = fminf(ext[0], fminf(ext[1], ext[2]));
+    const float emid = ext[0] + ext[1] + ext[2] - emax - emin;
+    float h = 2.0f * sqrtf(fmaxf(emax * emid, 1e-12f) / (float)(n > 0 ? n : 1));
+    h = fmaxf(h, min_cell);
+    h = fmaxf(h, emax * 1e-6f + 1e-9f);
+    for (;;)
+    {
+        double cells = 1.0;
+        for (int a = 0; a < 3; ++a) cells *= floor((double)ext[a] / h) + 1.0;
+        if (cells <= (double)kMaxCells) break;
+        h *= 1.26f;
+    }
+    st->grid.h = h;
+    st->grid.inv_h = 1.0f / h;
+    for (int a = 0; a < 3; ++a)
+    {
+        st->grid.origin[a] = st->bbox_lo[a];
+        st->grid.dim[a] = (int)floorf(ext[a] / h) + 1;
+    }
+}
+
+__device__ __forceinline__ int cell_coord(float v, float origin, float inv_h, int dim)
+{
+    const int c = (int)floorf((v - origin) * inv_h);
+    return c < 0 ? 0 : (c >= dim ? dim - 1 : c);
+}
+__device__ __forceinline__ unsigned int cell_of(const IcpGrid &g, float x, float y, float z)
+{
+    const int cx = cell_coord(x, g.origin[0], g.inv_h, g.dim[0]);
+    const int cy = cell_coord(y, g.origin[1], g.inv_h, g.dim[1]);
+    const int cz = cell_coord(z, g.origin[2], g.inv_h, g.dim[2]);
+    return (unsigned int)cx + (unsigned int)g.dim[0] * ((unsigned int)cy + (unsigned int)g.dim[1] * (unsigned int)cz);
+}
+
+__global__ void icp_count_kernel(const float *pts, int n, const IcpState *st, unsigned int *cell_count, unsigned int *point_cell)
+{
+    const IcpGrid g = st->grid;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const float x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+        unsigned int c = 0xFFFFFFFFu; // non-finite points are left out of the grid (they can never be nearest)
+        if (x == x && y == y && z == z && fabsf(x) < FLT_MAX && fabsf(y) < FLT_MAX && fabsf(z) < FLT_MAX)
+        {
+            c = cell_of(g, x, y, z);
+            atomicAdd(&cell_count[c], 1u);
+        }
+        point_cell[i] = c;
+    }
+}
+
+// exclusive scan of the cell counts -> cell_start (n_cells + 1 entries), three phases over tiles of 8192 cells:
+// tile sums, scan of the tile sums by one CTA, per-tile scan with the tile offset
+constexpr unsigned int kScanTile = 1024u * 8u;
+constexpr unsigned int kMaxTiles = kMaxCells / kScanTile + 1;
+
+__device__ __forceinline__ unsigned int icp_n_cells(const IcpState *st)
+{
+    return (unsigned int)st->grid.dim[0] * (unsigned int)st->grid.dim[1] * (unsigned int)st->grid.dim[2];
+}
+__global__ void icp_clear_kernel(const IcpState *st, unsigned int *cell_count)
+{
+    const unsigned int n = icp_n_cells(st) + 1;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) cell_count[i] = 0u;
+}
+// block-wide inclusive scan helper over 1024 threads; returns the inclusive value, total in *total
+__device__ __forceinline__ unsigned int block_inclusive_scan_1024(unsigned int v, unsigned int *warp_sums, unsigned int *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const unsigned int m = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += m;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0)
+    {
+        unsigned int w = warp_sums[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const unsigned int m = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += m;
+        }
+        warp_sums[lane] = w;
+    }
+    __syncthreads();
+    *total = warp_sums[31];
+    return inc + (warp ? warp_sums[warp - 1] : 0u);
+}
+__global__ void __launch_bounds__(1024) icp_tile_sums_kernel(const IcpState *st, const unsigned int *cell_count, unsigned int *tile_sums)
+{
+    __shared__ unsigned int warp_sums[32];
+    const unsigned int n = icp_n_cells(st);
+    for (unsigned int tile = blockIdx.x; tile * kScanTile < n; tile += gridDim.x)
+    {
+        const unsigned int first = tile * kScanTile + threadIdx.x * 8u;
+        unsigned int local = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) local += first + k < n ? cell_count[first + k] : 0u;
+        unsigned int total;
+        block_inclusive_scan_1024(local, warp_sums, &total);
+        if (threadIdx.x == 0) tile_sums[tile] = total;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(1024) icp_scan_tiles_kernel(const IcpState *st, unsigned int *tile_sums)
+{
+    __shared__ unsigned int warp_sums[32];
+    const unsigned int n_tiles = (icp_n_cells(st) + kScanTile - 1) / kScanTile; // <= kMaxTiles <= 1025
+    unsigned int carry = 0;
+    for (unsigned int base = 0; base < n_tiles; base += 1024u)
+    {
+        const unsigned int i = base + threadIdx.x;
+        const unsigned int v = i < n_tiles ? tile_sums[i] : 0u;
+        unsigned int total;
+        const unsigned int inc = block_inclusive_scan_1024(v, warp_sums, &total);
+        if (i < n_tiles) tile_sums[i] = carry + inc - v;
+        carry += total;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(1024) icp_scan_apply_kernel(const IcpState *st, const unsigned int *cell_count,
+                                                              const unsigned int *tile_sums, unsigned int *cell_start)
+{
+    __shared__ unsigned int warp_sums[32];
+    const unsigned int n = icp_n_cells(st);
+    for (unsigned int tile = blockIdx.x; tile * kScanTile < n; tile += gridDim.x)
+    {
+        const unsigned int first = tile * kScanTile + threadIdx.x * 8u;
+        unsigned int v[8], local = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { v[k] = first + k < n ? cell_count[first + k] : 0u; local += v[k]; }
+        unsigned int total;
+        const unsigned int inc = block_inclusive_scan_1024(local, warp_sums, &total);
+        unsigned int run = tile_sums[tile] + inc - local;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (first + k < n) { cell_start[first + k] = run; run += v[k]; }
+        // the thread that owns the last cell also writes the end sentinel (= number of points in the grid)
+        if (first < n && first + 8 >= n) cell_start[n] = run;
+        __syncthreads();
+    }
+}
+
+// scatter into cell order (the order inside a cell is irrelevant: ties are broken by original index in the search)
+__global__ void icp_scatter_kernel(const float *pts, int n, const unsigned int *point_cell, const unsigned int *cell_start,
+                                   unsigned int *cell_count, float4 *sorted)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const unsigned int c = point_cell[i];
+        if (c == 0xFFFFFFFFu) continue;
+        const unsigned int pos = cell_start[c] + atomicSub(&cell_count[c], 1u) - 1u;
+        sorted[pos] = make_float4(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], __int_as_float(i));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-iteration kernel
+// ---------------------------------------------------------------------------------------------------------
+// nanoflann L2_Simple_Adaptor::evalMetric: result += diff*diff over the 3 dimensions, in order
+__device__ __forceinline__ float dist2_nanoflann(float ax, float ay, float az, float bx, float by, float bz)
+{
+    const float dx = fsub(ax, bx), dy = fsub(ay, by), dz = fsub(az, bz);
+    return fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+}
+
+// exact nearest neighbour of q within `radius`; returns the target index or -1
+__device__ int grid_nearest(const IcpGrid &g, const unsigned int *__restrict__ cell_start, const float4 *__restrict__ sorted,
+                            float qx, float qy, float qz, float radius)
+{
+    if (!(qx == qx && qy == qy && qz == qz)) return -1;
+    const float fx = (qx - g.origin[0]) * g.inv_h, fy = (qy - g.origin[1]) * g.inv_h, fz = (qz - g.origin[2]) * g.inv_h;
+    // home cell, not clamped: a query outside the grid starts its rings where it is
+    const float bound = (float)(1 << 20);
+    if (!(fabsf(fx) < bound && fabsf(fy) < bound && fabsf(fz) < bound)) return -1;
+    const int hx = (int)floorf(fx), hy = (int)floorf(fy), hz = (int)floorf(fz);
+    // distance from q to the faces of its home cell: rings up to r cover everything closer than r*h + margin
+    const float margin = fminf(fminf(fminf(fx - hx, hx + 1 - fx), fminf(fy - hy, hy + 1 - fy)), fminf(fz - hz, hz + 1 - fz)) * g.h;
+    const float slack = 1e-3f * g.h; // cell assignment is computed in float: keep the stop test conservative
+    float best = FLT_MAX;
+    int best_idx = -1;
+    const int r_max = (int)ceilf(radius * g.inv_h) + 1;
+    for (int r = 0; r <= r_max; ++r)
+    {
+        const int z0 = max(hz - r, 0), z1 = min(hz + r, g.dim[2] - 1);
+        const int y0 = max(hy - r, 0), y1 = min(hy + r, g.dim[1] - 1);
+        for (int cz = z0; cz <= z1; ++cz)
+            for (int cy = y0; cy <= y1; ++cy)
+            {
+                const bool shell_row = (abs(cz - hz) == r) || (abs(cy - hy) == r);
+                // rows on the ring's z/y faces are scanned along all of x; interior rows only at the two x ends
+                const int xa = max(hx - r, 0), xb = min(hx + r, g.dim[0] - 1);
+                if (xa > xb) continue;
+                const unsigned int row = (unsigned int)g.dim[0] * ((unsigned int)cy + (unsigned int)g.dim[1] * (unsigned int)cz);
+                if (shell_row)
+                {
+                    // cells of one row are contiguous in the sorted array: one range for the whole row
+                    const unsigned int s = cell_start[row + xa], e = cell_start[row + xb + 1];
+                    for (unsigned int k = s; k < e; ++k)
+                    {
+                        const float4 t = sorted[k];
+                        const float d = dist2_nanoflann(qx, qy, qz, t.x, t.y, t.z);
+                        const int ti = __float_as_int(t.w);
+                        if (d < best || (d == best && ti < best_idx)) { best = d; best_idx = ti; }
+                    }
+                }
+                else
+                {
+#pragma unroll
+                    for (int side = 0; side < 2; ++side)
+                    {
+                        const int cx = side ? hx + r : hx - r;
+                        if (cx < 0 || cx >= g.dim[0] || (side && r == 0)) continue;
+                        const unsigned int s = cell_start[row + cx], e = cell_start[row + cx + 1];
+                        for (unsigned int k = s; k < e; ++k)
+                        {
+                            const float4 t = sorted[k];
+                            const float d = dist2_nanoflann(qx, qy, qz, t.x, t.y, t.z);
+                            const int ti = __float_as_int(t.w);
+                            if (d < best || (d == best && ti < best_idx)) { best = d; best_idx = ti; }
+                        }
+                    }
+                }
+            }
+        const float covered = (float)r * g.h + margin - slack;
+        if (covered > 0 && best <= covered * covered) break; // nothing outside the scanned cube can be closer
+        if (covered > radius) break;                          // nothing within the inlier radius is left
+    }
+    if (best_idx >= 0 && best > radius * radius) return -1;
+    return best_idx;
+}
+
+struct IcpArgs
+{
+    const float *src;       // ns x 3 (already scaled)
+    const float *tgt;       // nt x 3
+    const float *nrm;       // nt x 3 or nullptr (point-to-point)
+    const unsigned int *cell_start;
+    const float4 *sorted;
+    int *nn;                // ns
+    double *partials;       // gridDim.x x kPacket
+    IcpState *st;
+    int ns;
+    float search_radius;
+    double sq_threshold;
+    int final_pass;         // 1: only CountInliers (rmse + pairs), no solve
+    int *pairs;             // final pass: inlier flags are turned into pairs by the compaction kernel
+    unsigned char *inlier;  // ns flags
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kIcpThreads) icp_iteration_kernel(IcpArgs a)
+{
+    __shared__ double s_part[kIcpThreads / 32][kPacket];
+    __shared__ bool s_last;
+    const float *T = a.st->T; // column-major
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[kPacket];
+#pragma unroll
+    for (int k = 0; k < kPacket; ++k) acc[k] = 0.0;
+    if (i < a.ns)
+    {
+        const float sx = a.src[3 * i], sy = a.src[3 * i + 1], sz = a.src[3 * i + 2];
+        // geometry::TransformPoints: T * (x,y,z,1) then divide by w (Geometry.cpp:19-27)
+        const float w = row_xyz1(T[3], T[7], T[11], T[15], sx, sy, sz);
+        const float px = fdiv(row_xyz1(T[0], T[4], T[8], T[12], sx, sy, sz), w);
+        const float py = fdiv(row_xyz1(T[1], T[5], T[9], T[13], sx, sy, sz), w);
+        const float pz = fdiv(row_xyz1(T[2], T[6], T[10], T[14], sx, sy, sz), w);
+        const int j = grid_nearest(a.st->grid, a.cell_start, a.sorted, px, py, pz, a.search_radius);
+        a.nn[i] = j;
+        bool inl = false;
+        if (j >= 0)
+        {
+            const float tx = a.tgt[3 * j], ty = a.tgt[3 * j + 1], tz = a.tgt[3 * j + 2];
+            // CountInliers (ICP.cpp:19-21): (R*s + t - target).squaredNorm() in float, compared as double
+            const float ex = fsub(fadd(fadd(fmul(T[0], sx), fadd(fmul(T[4], sy), fmul(T[8], sz))), T[12]), tx);
+            const float ey = fsub(fadd(fadd(fmul(T[1], sx), fadd(fmul(T[5], sy), fmul(T[9], sz))), T[13]), ty);
+            const float ez = fsub(fadd(fadd(fmul(T[2], sx), fadd(fmul(T[6], sy), fmul(T[10], sz))), T[14]), tz);
+            const double err = (double)fadd(fmul(ex, ex), fadd(fmul(ey, ey), fmul(ez, ez)));
+            if (err < a.sq_threshold)
+            {
+                inl = true;
+                acc[28] = err;
+                acc[29] = 1.0;
+                if (!a.final_pass)
+                {
+                    if (a.nrm)
+                    {
+                        // EstimateRigidTransformationPointToPlane (ICP.cpp:121-136): row = [n ; s' x n],
+                        // r = n.s' - n.t with s' the transformed source point
+                        const float nx = a.nrm[3 * j], ny = a.nrm[3 * j + 1], nz = a.nrm[3 * j + 2];
+                        const float r = fsub(dot3(nx, ny, nz, px, py, pz), dot3(nx, ny, nz, tx, ty, tz));
+                        const float row[6] = {nx, ny, nz, fsub(fmul(py, nz), fmul(pz, ny)), fsub(fmul(pz, nx), fmul(px, nz)),
+                                              fsub(fmul(px, ny), fmul(py, nx))};
+                        int k = 0;
+#pragma unroll
+                        for (int p = 0; p < 6; ++p)
+#pragma unroll
+                            for (int q = p; q < 6; ++q) acc[k++] = (double)fmul(row[p], row[q]);
+#pragma unroll
+                        for (int p = 0; p < 6; ++p) acc[21 + p] = (double)fmul(r, row[p]);
+                    }
+                    else
+                    {
+                        // PointToPoint (ICP.cpp:78-84): Kabsch sums over (transformed source, target)
+                        acc[0] = px; acc[1] = py; acc[2] = pz;
+                        acc[3] = tx; acc[4] = ty; acc[5] = tz;
+                        acc[6] = (double)px * tx; acc[7] = (double)px * ty; acc[8] = (double)px * tz;
+                        acc[9] = (double)py * tx; acc[10] = (double)py * ty; acc[11] = (double)py * tz;
+                        acc[12] = (double)pz * tx; acc[13] = (double)pz * ty; acc[14] = (double)pz * tz;
+                    }
+                }
+            }
+        }
+        if (a.final_pass) a.inlier[i] = inl;
+    }
+    // 30-scalar reduction: warp shuffles, then warps in fixed order, then CTAs in fixed order (deterministic)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 30; ++k)
+    {
+        const double s = warp_sum(acc[k]);
+        if (lane == 0) s_part[warp][k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 30)
+    {
+        double s = 0.0;
+        for (int w = 0; w < kIcpThreads / 32; ++w) s += s_part[w][threadIdx.x];
+        a.partials[(size_t)blockIdx.x * kPacket + threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&a.st->ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    {
+        // fixed-order sum over the CTA partials: 8 interleaved chains per component, then the chains in order
+        const int k = threadIdx.x & 31, chain = threadIdx.x >> 5; // kIcpThreads / 32 == 8 chains
+        double s = 0.0;
+        for (unsigned int b = chain; b < gridDim.x; b += kIcpThreads / 32) s += a.partials[(size_t)b * kPacket + k];
+        s_part[chain][k] = s;
+        __syncthreads();
+        if (threadIdx.x < 30)
+        {
+            double tot = 0.0;
+            for (int c = 0; c < kIcpThreads / 32; ++c) tot += s_part[c][threadIdx.x];
+            a.st->packet[threadIdx.x] = tot;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    IcpState *st = a.st;
+    st->ticket = 0;
+    st->sum_error = st->packet[28];
+    st->n_inliers = (unsigned long long)(st->packet[29] + 0.5);
+    if (a.final_pass) return;
+    st->iteration += 1;
+    double dT[16];
+    if (a.nrm)
+    {
+        double JTJ[36], nJTr[6], x[6];
+        int k = 0;
+        for (int p = 0; p < 6; ++p)
+            for (int q = p; q < 6; ++q) { JTJ[p * 6 + q] = st->packet[k]; JTJ[q * 6 + p] = st->packet[k]; ++k; }
+        for (int p = 0; p < 6; ++p) nJTr[p] = -st->packet[21 + p];
+        linalg::solve_normal_equations6(JTJ, nJTr, x);
+        // the reference's x is float32
+        for (int p = 0; p < 6; ++p) x[p] = (double)(float)x[p];
+        linalg::se3_exp(x, dT);
+    }
+    else
+    {
+        if (st->packet[29] < 0.5) return; // no inliers: leave T unchanged (the reference would produce NaNs here)
+        linalg::kabsch_from_sums(st->packet[29], &st->packet[0], &st->packet[3], &st->packet[6], dT);
+    }
+    // start_T = tmp_T * start_T in float (ICP.cpp:86,198)
+    float dTf[16], Tn[16];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) dTf[c * 4 + r] = (float)dT[r * 4 + c];
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 4; ++r)
+            Tn[c * 4 + r] = fadd(fadd(fadd(fmul(dTf[r], st->T[c * 4]), fmul(dTf[4 + r], st->T[c * 4 + 1])), fmul(dTf[8 + r], st->T[c * 4 + 2])),
+                                 fmul(dTf[12 + r], st->T[c * 4 + 3]));
+    for (int e = 0; e < 16; ++e) st->T[e] = Tn[e];
+}
+
+// final Kabsch sums over the inlier pairs of the ORIGINAL (unscaled) clouds + ordered compaction of the pairs
+__global__ void __launch_bounds__(kIcpThreads) icp_final_sums_kernel(const float *src, const float *tgt, const int *nn,
+                                                                     const unsigned char *inlier, int ns, float scaling,
+                                                                     double *partials, IcpState *st)
+{
+    __shared__ double s_part[kIcpThreads / 32][16];
+    __shared__ bool s_last;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+    if (i < ns && inlier[i])
+    {
+        const int j = nn[i];
+        float s[3] = {src[3 * i], src[3 * i + 1], src[3 * i + 2]}, t[3] = {tgt[3 * j], tgt[3 * j + 1], tgt[3 * j + 2]};
+        if (scaling != 1.0f)
+            for (int c = 0; c < 3; ++c) { s[c] = fdiv(s[c], scaling); t[c] = fdiv(t[c], scaling); } // ICP.cpp:93-99,208-214
+        for (int c = 0; c < 3; ++c) { acc[c] = s[c]; acc[3 + c] = t[c]; }
+        for (int p = 0; p < 3; ++p)
+            for (int q = 0; q < 3; ++q) acc[6 + 3 * p + q] = (double)s[p] * t[q];
+        acc[15] = 1.0;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+    {
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) s_part[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16)
+    {
+        double v = 0.0;
+        for (int w = 0; w < kIcpThreads / 32; ++w) v += s_part[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * kPacket + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < 16)
+    {
+        double v = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; ++b) v += partials[(size_t)b * kPacket + threadIdx.x];
+        st->packet[threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) st->ticket = 0;
+}
+
+// ordered compaction of inlier pairs (source index ascending, like the reference's push_back loop)
+__global__ void __launch_bounds__(1024) icp_compact_kernel(const int *nn, const unsigned char *inlier, int ns, int *pairs,
+                                                           unsigned long long cap)
+{
+    __shared__ unsigned int warp_sums[32];
+    __shared__ unsigned int carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ns; base += 1024)
+    {
+        const int i = base + threadIdx.x;
+        const unsigned int f = i < ns ? inlier[i] : 0u;
+        unsigned int inc = f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const unsigned int m = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += m;
+        }
+        if (lane == 31) warp_sums[warp] = inc;
+        __syncthreads();
+        if (warp == 0)
+        {
+            unsigned int w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const unsigned int m = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += m;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const unsigned int pos = carry + (warp ? warp_sums[warp - 1] : 0u) + inc - f;
+        if (f && pos < cap) { pairs[2 * (size_t)pos] = i; pairs[2 * (size_t)pos + 1] = nn[i]; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = pos + f;
+        __syncthreads();
+    }
+}
+
+__global__ void icp_scale_kernel(float *p, size_t n, float s)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = fmul(p[i], s);
+}
+
+} // namespace opb
+
+using namespace opb;
+
+struct opb_icp
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    // device buffers (grown on demand)
+    float *d_src = nullptr, *d_tgt = nullptr, *d_nrm = nullptr;
+    size_t cap_src = 0, cap_tgt = 0;
+    float4 *d_sorted = nullptr;
+    unsigned int *d_point_cell = nullptr, *d_cell_count = nullptr, *d_tile_sums = nullptr, *d_cell_start = nullptr;
+    int *d_nn = nullptr, *d_pairs = nullptr;
+    unsigned char *d_inlier = nullptr;
+    double *d_partials = nullptr;
+    size_t cap_partials = 0;
+    IcpState *d_state = nullptr;
+    IcpState *h_state = nullptr; // pinned
+    // timing
+    bool profiling = false;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    float last_build_ms = 0, last_iter_ms = 0;
+};
+
+static int icp_reserve(opb_icp *c, size_t ns, size_t nt)
+{
+    if (ns > c->cap_src)
+    {
+        cudaFree(c->d_src); cudaFree(c->d_nn); cudaFree(c->d_pairs); cudaFree(c->d_inlier);
+        c->d_src = nullptr; c->d_nn = nullptr; c->d_pairs = nullptr; c->d_inlier = nullptr; c->cap_src = 0;
+        OPB_CUDA(cudaMalloc(&c->d_src, ns * 3 * sizeof(float)));
+        OPB_CUDA(cudaMalloc(&c->d_nn, ns * sizeof(int)));
+        OPB_CUDA(cudaMalloc(&c->d_pairs, ns * 2 * sizeof(int)));
+        OPB_CUDA(cudaMalloc(&c->d_inlier, ns));
+        c->cap_src = ns;
+    }
+    if (nt > c->cap_tgt)
+    {
+        cudaFree(c->d_tgt); cudaFree(c->d_nrm); cudaFree(c->d_sorted); cudaFree(c->d_point_cell);
+        c->d_tgt = nullptr; c->d_nrm = nullptr; c->d_sorted = nullptr; c->d_point_cell = nullptr; c->cap_tgt = 0;
+        OPB_CUDA(cudaMalloc(&c->d_tgt, nt * 3 * sizeof(float)));
+        OPB_CUDA(cudaMalloc(&c->d_nrm, nt * 3 * sizeof(float)));
+        OPB_CUDA(cudaMalloc(&c->d_sorted, nt * sizeof(float4)));
+        OPB_CUDA(cudaMalloc(&c->d_point_cell, nt * sizeof(unsigned int)));
+        c->cap_tgt = nt;
+    }
+    const size_t blocks = (ns + kIcpThreads - 1) / kIcpThreads + 1;
+    if (blocks > c->cap_partials)
+    {
+        cudaFree(c->d_partials);
+        c->d_partials = nullptr; c->cap_partials = 0;
+        OPB_CUDA(cudaMalloc(&c->d_partials, blocks * kPacket * sizeof(double)));
+        c->cap_partials = blocks;
+    }
+    return OPB_OK;
+}
+
+extern "C"
+{
+int opb_icp_create(int device, void *stream, opb_icp **out)
+{
+    if (!out) { set_error("out is NULL"); return OPB_ERR_INVALID; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+        cudaGetLastError();
+        set_error("no CUDA device: onepiece_b200 has no CPU path");
+        return OPB_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return OPB_ERR_INVALID; }
+    OPB_CUDA(cudaSetDevice(device));
+    opb_icp *c = new opb_icp();
+    c->device = device;
+    cudaDeviceProp prop;
+    OPB_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    if (stream) c->stream = (cudaStream_t)stream;
+    else { OPB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    cudaError_t e = cudaMalloc(&c->d_state, sizeof(IcpState));
+    if (e == cudaSuccess) e = cudaHostAlloc(&c->h_state, sizeof(IcpState), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_cell_count, ((size_t)kMaxCells + 1) * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_tile_sums, ((size_t)kMaxTiles + 1) * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_cell_start, ((size_t)kMaxCells + 2) * sizeof(unsigned int));
+    for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+    if (e != cudaSuccess)
+    {
+        set_error("ICP workspace allocation failed: %s", cudaGetErrorString(e));
+        opb_icp_destroy(c);
+        return OPB_ERR_CUDA;
+    }
+    *out = c;
+    return OPB_OK;
+}
+
+void opb_icp_destroy(opb_icp *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_src); cudaFree(c->d_tgt); cudaFree(c->d_nrm); cudaFree(c->d_sorted); cudaFree(c->d_point_cell);
+    cudaFree(c->d_cell_count); cudaFree(c->d_tile_sums); cudaFree(c->d_cell_start); cudaFree(c->d_nn); cudaFree(c->d_pairs);
+    cudaFree(c->d_inlier); cudaFree(c->d_partials); cudaFree(c->d_state);
+    if (c->h_state) cudaFreeHost(c->h_state);
+    for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();
+    delete c;
+}
+
+int opb_icp_set_profiling(opb_icp *c, int on)
+{
+    if (!c) { set_error("icp is NULL"); return OPB_ERR_INVALID; }
+    c->profiling = on != 0;
+    return OPB_OK;
+}
+int opb_icp_last_timing(opb_icp *c, float *grid_build_ms, float *iterations_ms)
+{
+    if (!c) { set_error("icp is NULL"); return OPB_ERR_INVALID; }
+    if (grid_build_ms) *grid_build_ms = c->last_build_ms;
+    if (iterations_ms) *iterations_ms = c->last_iter_ms;
+    return OPB_OK;
+}
+
+// src/tgt/nrm may be host or device pointers (cudaMemcpyDefault)
+static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, const float *nrm, size_t nt, const float *init_T,
+                   const opb_icp_params *par, opb_icp_result *res, int32_t *pairs, size_t pairs_cap, bool point_to_plane)
+{
+    if (!c || !src || !tgt || !init_T || !par || !res) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    memset(res, 0, sizeof(*res));
+    for (int i = 0; i < 4; ++i) res->T[i * 5] = 1.0f;
+    if (ns > 0x7FFFFFF0u || nt > 0x7FFFFFF0u) { set_error("clouds above 2^31 points are not supported"); return OPB_ERR_INVALID; }
+    if (point_to_plane && (!nrm || par->scaling != 1.0))
+    {
+        // ICP.cpp:159-163: message + default RegistrationResult
+        set_error("[ERROR]::[ICPPointToPlane]::target point cloud need to have normals.");
+        res->status = OPB_ERR_INVALID;
+        return OPB_ERR_INVALID;
+    }
+    if (ns == 0 || nt == 0) { set_error("empty point cloud"); res->status = OPB_ERR_INVALID; return OPB_ERR_INVALID; }
+    OPB_CUDA(cudaSetDevice(c->device));
+    int rc = icp_reserve(c, ns, nt);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    OPB_CUDA(cudaMemcpyAsync(c->d_src, src, ns * 3 * sizeof(float), cudaMemcpyDefault, s));
+    OPB_CUDA(cudaMemcpyAsync(c->d_tgt, tgt, nt * 3 * sizeof(float), cudaMemcpyDefault, s));
+    if (point_to_plane) OPB_CUDA(cudaMemcpyAsync(c->d_nrm, nrm, nt * 3 * sizeof(float), cudaMemcpyDefault, s));
+    const float scaling = (float)par->scaling;
+    if (par->scaling != 1.0)
+    {   // PointToPoint scales both clouds (ICP.cpp:36-42)
+        icp_scale_kernel<<<c->sm_count * 4, 256, 0, s>>>(c->d_src, ns * 3, scaling);
+        icp_scale_kernel<<<c->sm_count * 4, 256, 0, s>>>(c->d_tgt, nt * 3, scaling);
+    }
+    // state
+    IcpState *h = c->h_state;
+    memset(h, 0, sizeof(IcpState));
+    memcpy(h->T, init_T, 16 * sizeof(float));
+    for (int a = 0; a < 3; ++a) { h->bbox_enc[a] = 0xFFFFFFFFu; h->bbox_enc[3 + a] = 0u; }
+    OPB_CUDA(cudaMemcpyAsync(c->d_state, h, sizeof(IcpState), cudaMemcpyHostToDevice, s));
+    if (c->profiling) OPB_CUDA(cudaEventRecord(c->ev[0], s));
+    // grid over the target
+    const int nb_t = (int)((nt + 255) / 256) < c->sm_count * 8 ? (int)((nt + 255) / 256) : c->sm_count * 8;
+    icp_bbox_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)nt, c->d_state);
+    icp_grid_setup_kernel<<<1, 1, 0, s>>>(c->d_state, (int)nt, 0.0f);
+    icp_clear_kernel<<<c->sm_count * 8, 256, 0, s>>>(c->d_state, c->d_cell_count);
+    icp_count_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)nt, c->d_state, c->d_cell_count, c->d_point_cell);
+    icp_tile_sums_kernel<<<c->sm_count * 2, 1024, 0, s>>>(c->d_state, c->d_cell_count, c->d_tile_sums);
+    icp_scan_tiles_kernel<<<1, 1024, 0, s>>>(c->d_state, c->d_tile_sums);
+    icp_scan_apply_kernel<<<c->sm_count * 2, 1024, 0, s>>>(c->d_state, c->d_cell_count, c->d_tile_sums, c->d_cell_start);
+    icp_scatter_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)nt, c->d_point_cell, c->d_cell_start, c->d_cell_count, c->d_sorted);
+    if (c->profiling) OPB_CUDA(cudaEventRecord(c->ev[1], s));
+    // iterations
+    IcpArgs a;
+    a.src = c->d_src; a.tgt = c->d_tgt; a.nrm = point_to_plane ? c->d_nrm : nullptr;
+    a.cell_start = c->d_cell_start; a.sorted = c->d_sorted; a.nn = c->d_nn; a.partials = c->d_partials; a.st = c->d_state;
+    a.ns = (int)ns;
+    a.search_radius = (float)(par->threshold * (1.0 + 1e-3)) + 1e-6f;
+    a.sq_threshold = par->threshold * par->threshold;
+    a.final_pass = 0; a.pairs = c->d_pairs; a.inlier = c->d_inlier;
+    const int nb_s = (int)((ns + kIcpThreads - 1) / kIcpThreads);
+    for (int it = 0; it < par->max_iteration; ++it) icp_iteration_kernel<<<nb_s, kIcpThreads, 0, s>>>(a);
+    // final CountInliers with the final T (ICP.cpp:90-91,206-207)
+    a.final_pass = 1;
+    icp_iteration_kernel<<<nb_s, kIcpThreads, 0, s>>>(a);
+    OPB_CUDA(cudaMemcpyAsync(h, c->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
+    icp_final_sums_kernel<<<nb_s, kIcpThreads, 0, s>>>(c->d_src, c->d_tgt, c->d_nn, c->d_inlier, (int)ns, scaling, c->d_partials, c->d_state);
+    if (pairs && pairs_cap) icp_compact_kernel<<<1, 1024, 0, s>>>(c->d_nn, c->d_inlier, (int)ns, c->d_pairs, (unsigned long long)pairs_cap);
+    if (c->profiling) OPB_CUDA(cudaEventRecord(c->ev[2], s));
+    OPB_CUDA(cudaGetLastError());
+    OPB_CUDA(cudaStreamSynchronize(s));
+    if (c->profiling)
+    {
+        cudaEventElapsedTime(&c->last_build_ms, c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&c->last_iter_ms, c->ev[1], c->ev[2]);
+    }
+    res->n_inliers = (size_t)h->n_inliers;
+    res->rmse = sqrt(h->sum_error / (double)h->n_inliers); // CountInliers: sqrt(sum_error / inliers.size())
+    res->iterations = h->iteration;
+    memcpy(res->T_iterated, h->T, 16 * sizeof(float));
+    // result.T = Kabsch over the final inlier pairs of the original clouds (ICP.cpp:103-105,221)
+    double sums[16];
+    OPB_CUDA(cudaMemcpy(sums, (const char *)c->d_state + offsetof(IcpState, packet), sizeof(sums), cudaMemcpyDeviceToHost));
+    if (sums[15] >= 0.5)
+    {
+        double Tk[16];
+        linalg::kabsch_from_sums(sums[15], &sums[0], &sums[3], &sums[6], Tk);
+        for (int r = 0; r < 4; ++r)
+            for (int col = 0; col < 4; ++col) res->T[col * 4 + r] = (float)Tk[r * 4 + col];
+    }
+    else
+        for (int e = 0; e < 16; ++e) res->T[e] = nanf(""); // the reference divides by zero pairs here
+    if (pairs && pairs_cap)
+    {
+        const size_t n = res->n_inliers < pairs_cap ? res->n_inliers : pairs_cap;
+        OPB_CUDA(cudaMemcpy(pairs, c->d_pairs, n * 2 * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    res->status = OPB_OK;
+    return OPB_OK;
+}
+
+void opb_icp_params_default(opb_icp_params *p)
+{
+    if (!p) return;
+    p->max_iteration = 30; // ICP.h:16-18
+    p->threshold = 0.2;
+    p->scaling = 1.0;
+}
+
+int opb_icp_point_to_plane(opb_icp *c, const float *src_xyz, size_t ns, const float *tgt_xyz, const float *tgt_normals, size_t nt,
+                           const float init_T[16], const opb_icp_params *params, opb_icp_result *result, int32_t *pairs,
+                           size_t pairs_cap)
+{
+    return icp_run(c, src_xyz, ns, tgt_xyz, tgt_normals, nt, init_T, params, result, pairs, pairs_cap, true);
+}
+int opb_icp_point_to_point(opb_icp *c, const float *src_xyz, size_t ns, const float *tgt_xyz, size_t nt, const float init_T[16],
+                           const opb_icp_params *params, opb_icp_result *result, int32_t *pairs, size_t pairs_cap)
+{
+    return icp_run(c, src_xyz, ns, tgt_xyz, nullptr, nt, init_T, params, result, pairs, pairs_cap, false);
+}
+// nearest-neighbour indices of the LAST search (final CountInliers pass), for tests
+int opb_icp_last_nn(opb_icp *c, int32_t *nn, size_t n)
+{
+    if (!c || !nn) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    if (n > c->cap_src) { set_error("n exceeds the last source size"); return OPB_ERR_INVALID; }
+    OPB_CUDA(cudaSetDevice(c->device));
+    OPB_CUDA(cudaMemcpy(nn, c->d_nn, n * sizeof(int), cudaMemcpyDeviceToHost));
+    return OPB_OK;
+}
+} // extern "C"

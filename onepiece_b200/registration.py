@@ -1,0 +1,101 @@
+"""Python mirror of one_piece::registration (reference src/Registration/ICP.h:13-26) over the C-ABI: same function
+names, argument meaning and result fields as the reference, computed on the GPU by libonepiece_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi
+
+
+@dataclass
+class ICPParameter:
+    """registration::ICPParameter (ICP.h:13-19)"""
+    max_iteration: int = 30
+    threshold: float = 0.2
+    scaling: float = 1.0
+
+
+@dataclass
+class RegistrationResult:
+    """registration::RegistrationResult (RegistrationResult.h:8-16)"""
+    T: np.ndarray = field(default_factory=lambda: np.eye(4, dtype=np.float32))
+    correspondence_set_index: np.ndarray = field(default_factory=lambda: np.zeros((0, 2), np.int32))
+    correspondence_set: tuple = (None, None)
+    rmse: float = 0.0
+    T_iterated: np.ndarray = field(default_factory=lambda: np.eye(4, dtype=np.float32))
+    ok: bool = True
+
+
+class PointCloud:
+    """The three arrays of geometry::PointCloud that ICP reads (PointCloud.h:52-54)."""
+
+    def __init__(self, points, normals=None):
+        self.points = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        self.normals = None if normals is None else np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+
+    def HasNormals(self):
+        return self.normals is not None and len(self.normals) == len(self.points) and len(self.points) > 0
+
+
+class _Workspace:
+    _by_device = {}
+
+    @classmethod
+    def get(cls, device=0):
+        if device not in cls._by_device:
+            h = C.c_void_p()
+            capi.check(capi.lib.opb_icp_create(device, None, C.byref(h)))
+            cls._by_device[device] = h
+        return cls._by_device[device]
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _run(source: PointCloud, target: PointCloud, init_T, icp_para: ICPParameter, plane: bool, device=0, workspace=None):
+    ws = workspace if workspace is not None else _Workspace.get(device)
+    par = capi.IcpParams(icp_para.max_iteration, icp_para.threshold, icp_para.scaling)
+    res = capi.IcpResult()
+    T0 = np.ascontiguousarray(np.asarray(init_T, np.float32).reshape(4, 4).T).reshape(16)
+    ns, nt = len(source.points), len(target.points)
+    pairs = np.zeros((max(ns, 1), 2), np.int32)
+    if plane:
+        rc = capi.lib.opb_icp_point_to_plane(ws, _ptr(source.points), ns, _ptr(target.points),
+                                             _ptr(target.normals) if target.HasNormals() else None, nt, _ptr(T0),
+                                             C.byref(par), C.byref(res), _ptr(pairs), ns)
+    else:
+        rc = capi.lib.opb_icp_point_to_point(ws, _ptr(source.points), ns, _ptr(target.points), nt, _ptr(T0), C.byref(par),
+                                             C.byref(res), _ptr(pairs), ns)
+    if rc == capi.OPB_ERR_INVALID and res.status == capi.OPB_ERR_INVALID:
+        # the reference prints the error and returns a default-constructed result (ICP.cpp:159-163)
+        print(capi.lib.opb_last_error().decode())
+        return RegistrationResult(ok=False)
+    capi.check(rc)
+    idx = pairs[: res.n_inliers].copy()
+    out = RegistrationResult()
+    out.T = np.array(res.T[:], np.float32).reshape(4, 4).T.copy()
+    out.T_iterated = np.array(res.T_iterated[:], np.float32).reshape(4, 4).T.copy()
+    out.correspondence_set_index = idx
+    out.correspondence_set = (source.points[idx[:, 0]], target.points[idx[:, 1]])
+    out.rmse = res.rmse
+    return out
+
+
+def PointToPlane(source, target, init_T=np.eye(4), icp_para=ICPParameter(), **kw):
+    """registration::PointToPlane (ICP.cpp:146-224)"""
+    return _run(source, target, init_T, icp_para, True, **kw)
+
+
+def PointToPoint(source, target, init_T=np.eye(4), icp_para=ICPParameter(), **kw):
+    """registration::PointToPoint (ICP.cpp:31-107)"""
+    return _run(source, target, init_T, icp_para, False, **kw)
+
+
+def last_nn(n, device=0):
+    nn = np.zeros(n, np.int32)
+    capi.check(capi.lib.opb_icp_last_nn(_Workspace.get(device), _ptr(nn), n))
+    return nn

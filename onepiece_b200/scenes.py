@@ -85,29 +85,34 @@ def _texture(p):
     return 128.0 + 100.0 * np.sin(7.0 * p[..., 0]) * np.sin(9.0 * p[..., 1] + 3.0 * p[..., 2])
 
 
-def room(cam: Camera = Camera(), k: int = 0, depth_u16: bool = True):
-    """Scene S2: analytic ray-cast of the inside of a 4 m box centred at (0,0,1) plus a sphere r=0.5 m at
-    (0,0,2.5), seen from room_pose(k).  Returns (depth, bgr, pose_c2w float32).  Depth is quantised to
-    uint16 millimetres like a sensor unless depth_u16=False (then float32 metres)."""
-    T = room_pose(k)
+def room(cam: Camera = Camera(), k: int = 0, depth_u16: bool = True, with_normals: bool = False, pose=None):
+    """Scene S2: analytic ray-cast of the inside of an asymmetric box room, x in [-1.4, 1.8], y in [-1.1, 1.3],
+    z in [-1, 3] m, plus a sphere r=0.45 m at (0.4,-0.3,2.2), seen from room_pose(k) (or `pose`).  (SURVEY.md's
+    symmetric 4 m box with an on-axis sphere shows the camera only the far wall and the sphere, which leaves the
+    rotation about the optical axis unconstrained; side walls, floor and ceiling are visible here, so the 6x6
+    systems of ICP and dense odometry are well conditioned.)  Returns (depth, bgr, pose_c2w float32[, normals]).  Depth is
+    quantised to uint16 millimetres like a sensor unless depth_u16=False (then float32 metres).  normals
+    (H x W x 3 float32, camera frame) are the analytic surface normals at every pixel."""
+    T = room_pose(k) if pose is None else np.asarray(pose, np.float64)
     R, t = T[:3, :3], T[:3, 3]
     u = np.arange(cam.width, dtype=np.float64)[None, :]
     v = np.arange(cam.height, dtype=np.float64)[:, None]
     d_cam = np.stack([(u - cam.cx) / cam.fx + 0 * v, (v - cam.cy) / cam.fy + 0 * u, np.ones((cam.height, cam.width))], -1)
     d = d_cam @ R.T  # world ray directions (not normalised: parameter == camera z)
     o = t
-    lo = np.array([-2.0, -2.0, -1.0])
-    hi = np.array([2.0, 2.0, 3.0])
+    lo = np.array([-1.4, -1.1, -1.0])
+    hi = np.array([1.8, 1.3, 3.0])
     with np.errstate(divide="ignore", invalid="ignore"):
         t1 = (lo - o) / d
         t2 = (hi - o) / d
     t_exit = np.min(np.maximum(t1, t2), axis=-1)  # inside the box: first wall hit
     # sphere
-    c = np.array([0.0, 0.0, 2.5])
+    c = np.array([0.4, -0.3, 2.2])
+    rad = 0.45
     oc = o - c
     a = np.sum(d * d, -1)
     b = 2.0 * np.sum(d * oc, -1)
-    cc = float(oc @ oc) - 0.25
+    cc = float(oc @ oc) - rad * rad
     disc = b * b - 4 * a * cc
     with np.errstate(invalid="ignore"):
         ts = np.where(disc > 0, (-b - np.sqrt(np.maximum(disc, 0))) / (2 * a), np.inf)
@@ -120,7 +125,19 @@ def room(cam: Camera = Camera(), k: int = 0, depth_u16: bool = True):
         depth = np.clip(np.rint(z * cam.depth_scale), 0, 65535).astype(np.uint16)
     else:
         depth = z.astype(np.float32)
-    return np.ascontiguousarray(depth), np.ascontiguousarray(bgr), T.astype(np.float32)
+    if not with_normals:
+        return np.ascontiguousarray(depth), np.ascontiguousarray(bgr), T.astype(np.float32)
+    # world-space normals: the wall that was hit (axis of the binding slab), or the sphere's radial direction
+    tm = np.maximum(t1, t2)
+    axis = np.argmin(tm, axis=-1)
+    n_w = np.zeros_like(p)
+    sign = -np.sign(np.take_along_axis(d, axis[..., None], -1))[..., 0]
+    np.put_along_axis(n_w, axis[..., None], sign[..., None], -1)
+    on_sphere = ts < t_exit
+    n_w[on_sphere] = (p[on_sphere] - c) / rad
+    n_c = n_w @ R  # world -> camera: R^T n
+    return (np.ascontiguousarray(depth), np.ascontiguousarray(bgr), T.astype(np.float32),
+            np.ascontiguousarray(n_c.astype(np.float32)))
 
 
 def backproject(depth, cam: Camera):

@@ -1,0 +1,67 @@
+"""Ad-hoc GPU probe (not a test): CUDA ICP vs the compiled reference on scene S2."""
+import sys, time
+import numpy as np
+sys.path.insert(0, ".")
+from onepiece_b200 import scenes, registration as reg
+from oracle import refapi
+
+def rot_err(A, B):
+    R = A[:3, :3].T @ B[:3, :3]
+    return float(np.arccos(np.clip((np.trace(R) - 1) / 2, -1, 1)))
+
+for scale, iters in ((4, 10), (1, 30)):
+    c0 = scenes.Camera()
+    cam = scenes.Camera(c0.fx / scale, c0.fy / scale, c0.cx / scale, c0.cy / scale, 640 // scale, 480 // scale, 1000.0)
+    d0, _, T0, n0 = scenes.room(cam, 0, with_normals=True)
+    d1, _, T1, n1 = scenes.room(cam, 3, with_normals=True)
+    tgt = scenes.backproject(d0, cam); src = scenes.backproject(d1, cam)
+    nrm = n0.reshape(-1, 3)[(d0 > 0).reshape(-1)]
+    print(f"--- {cam.width}x{cam.height}: {len(src)} -> {len(tgt)} points, {iters} iterations")
+    thr = 0.05
+    gt = np.linalg.inv(T0.astype(np.float64)) @ T1.astype(np.float64)
+    par = reg.ICPParameter(iters, thr, 1.0)
+    t0 = time.time(); g = reg.PointToPlane(reg.PointCloud(src), reg.PointCloud(tgt, nrm), np.eye(4), par); tg = time.time() - t0
+    t0 = time.time(); g = reg.PointToPlane(reg.PointCloud(src), reg.PointCloud(tgt, nrm), np.eye(4), par); tg2 = time.time() - t0
+    r32 = refapi.icp(src, tgt, nrm, np.eye(4), iters, thr, "f32")
+    r64 = refapi.icp(src, tgt, nrm, np.eye(4), iters, thr, "f64")
+    print("gpu %.4fs (2nd call %.4fs)  ref32 %.3fs ref64 %.3fs" % (tg, tg2, r32["seconds"], r64["seconds"]))
+    print("inliers gpu", len(g.correspondence_set_index), "ref32", len(r32["pairs"]), "ref64", len(r64["pairs"]))
+    print("rmse gpu %.9g ref32 %.9g ref64 %.9g" % (g.rmse, r32["rmse"], r64["rmse"]))
+    for name, T in (("gpu", g.T.astype(np.float64)), ("ref32", r32["T"])):
+        print(f"{name:6s} vs ref64: dt = {np.linalg.norm(T[:3,3]-r64['T'][:3,3]):.3e} m  drot = {rot_err(T, r64['T']):.3e} rad ; vs truth dt = {np.linalg.norm(T[:3,3]-gt[:3,3]):.3e}")
+    same = np.array_equal(g.correspondence_set_index, r32["pairs"])
+    print("pairs identical to ref32:", same)
+    if not same and len(g.correspondence_set_index) == len(r32["pairs"]):
+        diff = (g.correspondence_set_index != r32["pairs"]).any(1).sum()
+        print("  differing pairs:", diff)
+    # teacher-forced single iteration from identity: NN + system
+    st = refapi.RefIcpState(src, tgt, nrm, "f32")
+    it = st.iteration(np.eye(4), thr)
+    g1 = reg.PointToPlane(reg.PointCloud(src), reg.PointCloud(tgt, nrm), np.eye(4), reg.ICPParameter(0, thr, 1.0))
+    nn = reg.last_nn(len(src))
+    refnn = it["nn"].copy()
+    # the GPU reports -1 beyond the threshold; compare where the reference's pair is an inlier candidate
+    far = nn < 0
+    d_ref = np.linalg.norm(src - tgt[refnn], axis=1)
+    print("NN: equal %d / %d ; gpu none %d (ref dist min over those %.4f) ; mismatching within radius %d" % (
+        (nn == refnn).sum(), len(nn), far.sum(), d_ref[far].min() if far.any() else -1, ((nn != refnn) & ~far).sum()))
+    print("n_inliers ref it0", it["n_inliers"], "gpu 0-iter inliers", len(g1.correspondence_set_index))
+    ev = np.linalg.eigvalsh(it["JTJ"]); print("cond(JTJ) = %.3g" % (ev.max() / ev.min()))
+    import ctypes as C
+    from onepiece_b200 import capi
+    ws = reg._Workspace.get(0)
+    capi.lib.opb_icp_set_profiling(ws, 1)
+    reg.PointToPlane(reg.PointCloud(src), reg.PointCloud(tgt, nrm), np.eye(4), par)
+    a, b = C.c_float(0), C.c_float(0)
+    capi.lib.opb_icp_last_timing(ws, C.byref(a), C.byref(b))
+    print("timing: grid build %.3f ms, %d iterations + final %.3f ms" % (a.value, iters, b.value))
+    capi.lib.opb_icp_set_profiling(ws, 0)
+    g_1 = reg.PointToPlane(reg.PointCloud(src), reg.PointCloud(tgt, nrm), np.eye(4), reg.ICPParameter(1, thr, 1.0))
+    st64 = refapi.RefIcpState(src, tgt, nrm, "f64"); it64 = st64.iteration(np.eye(4), thr)
+    for name, T in (("gpu", g_1.T_iterated.astype(np.float64)), ("ref32", it["T"])):
+        print(f"  1 iteration {name:6s} vs ref64: dt = {np.linalg.norm(T[:3,3]-it64['T'][:3,3]):.3e}  drot = {rot_err(T, it64['T']):.3e}")
+    # point to point
+    p32 = refapi.icp(src, tgt, None, np.eye(4), 5, thr, "f32"); p64 = refapi.icp(src, tgt, None, np.eye(4), 5, thr, "f64")
+    gp = reg.PointToPoint(reg.PointCloud(src), reg.PointCloud(tgt), np.eye(4), reg.ICPParameter(5, thr, 1.0))
+    for name, T in (("gpu", gp.T.astype(np.float64)), ("ref32", p32["T"])):
+        print(f"  p2p 5 it {name:6s} vs ref64: dt = {np.linalg.norm(T[:3,3]-p64['T'][:3,3]):.3e}  drot = {rot_err(T, p64['T']):.3e}; inliers {len(gp.correspondence_set_index)} {len(p32['pairs'])}")
