@@ -26,7 +26,6 @@ if ROOT not in sys.path:
 METRIC = "frames/sec TSDF-integrate+ICP @640x480, 5mm voxel"
 UNIT = "frames/s"
 VOXEL = 0.005
-N_SCENE_FRAMES = 8  # distinct synthetic frames cycled through the stream
 
 
 def parse_args():
@@ -96,9 +95,24 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_frames(cam, rank: int):
+N_TRAJ = 9  # frames 0..8 of the S2 trajectory; step s registers frame k+1 against frame k, k = s mod 8
+ICP_ITERS = 30
+ICP_THRESHOLD = 0.05
+WORKLOAD = ("config2: S2 room stream 640x480 (u16 depth, 307,200 points/frame), per frame point-to-plane ICP "
+            "(frame k+1 -> frame k, analytic target normals, 30 iterations, threshold 0.05 m) then TSDF integration "
+            "of the frame at 5 mm voxels with the ICP pose")
+
+
+def make_stream(cam, rank: int):
+    """Per-rank synthetic stream: every rank looks at its own copy of the room (its own sub-volume)."""
     from onepiece_b200 import scenes
-    return [scenes.wavy_wall(cam, 100 * rank + k) for k in range(N_SCENE_FRAMES)]
+    frames = []
+    for k in range(N_TRAJ):
+        d, c, T, n = scenes.room(cam, k + 3 * rank, with_normals=True)
+        cloud = scenes.backproject(d, cam)
+        frames.append(dict(depth=d, bgr=c, pose=T.astype(np.float64), cloud=cloud,
+                           normals=np.ascontiguousarray(n.reshape(-1, 3)[(d > 0).reshape(-1)])))
+    return frames
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -109,41 +123,47 @@ def cpu_reference_fps(steps: int, warmup: int, budget_s: float = 25.0):
     from onepiece_b200 import scenes
     from oracle import oracleapi, refapi
     cam = scenes.Camera()
-    frames = make_frames(cam, 0)
-    I = np.eye(4, dtype=np.float32)
-    if refapi.available("f32"):
-        vol, kind = refapi.RefVolume(cam, VOXEL), "reference"
-    else:
-        vol, kind = oracleapi.OracleVolume(cam, VOXEL), "port"
+    frames = make_stream(cam, 0)
+    use_ref = refapi.available("f32")
+    vol = refapi.RefVolume(cam, VOXEL) if use_ref else oracleapi.OracleVolume(cam, VOXEL)
+    kind = "reference" if use_ref else "port"
+    cores = os.cpu_count() or 1
+
+    def step(s):
+        k = s % (N_TRAJ - 1)
+        a, b = frames[k], frames[k + 1]
+        if use_ref:
+            r = refapi.icp(b["cloud"], a["cloud"], a["normals"], np.eye(4), ICP_ITERS, ICP_THRESHOLD, "f32")
+        else:
+            r = oracleapi.icp(b["cloud"], a["cloud"], a["normals"], np.eye(4), ICP_ITERS, ICP_THRESHOLD)
+        pose = (a["pose"] @ r["T"]).astype(np.float32)
+        vol.integrate(b["depth"], b["bgr"], pose)
+
+    for s in range(warmup):
+        step(s)
     n = 0
-    t_used = 0.0
-    for k in range(warmup):
-        d, c = frames[k % len(frames)]
-        vol.integrate(d, c, I)
     t0 = time.perf_counter()
+    t_used = 0.0
     while n < steps and t_used < budget_s:
-        d, c = frames[n % len(frames)]
-        vol.integrate(d, c, I)
+        step(warmup + n)
         n += 1
         t_used = time.perf_counter() - t0
     fps = n / t_used
-    return {"value": fps, "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": f"{n} frames of CubeHandler::IntegrateImage (single-threaded in the reference), 640x480, 5 mm, "
-                      f"identity pose, after {warmup} warm-up frames; {t_used:.1f} s"}, n, t_used
+    return {"value": fps, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{n} frames of registration::PointToPlane (OpenMP nearest-neighbour search on {cores} threads, the "
+                      f"rest single-threaded) + CubeHandler::IntegrateImage (single-threaded) on the bench workload, after "
+                      f"{warmup} warm-up frames; {t_used:.1f} s"}, n, t_used
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = min(args.steps, 60)
-    cb, n, t = cpu_reference_fps(steps, min(args.warmup, 3), budget_s=120.0)
-    out = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": n, "warmup": min(args.warmup, 3),
+    W = min(args.warmup, 1)
+    cb, n, t = cpu_reference_fps(min(args.steps, 40), W, budget_s=150.0)
+    out = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": n, "warmup": W,
            "ms_per_step": 1e3 * t / n, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-           "data": "synthetic", "impl": "reference",
-           "config": {"workload": "config1: S1 wavy wall 640x480 f32 depth, 5 mm voxels, identity poses, integrate only "
-                                  "(ICP stage not yet in the step)"},
-           "cpu_baseline": cb,
+           "data": "synthetic", "impl": "reference", "config": {"workload": WORKLOAD}, "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -174,113 +194,140 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     cam = scenes.Camera()
-    frames = make_frames(cam, rank)
+    frames = make_stream(cam, rank)
     stream = torch.cuda.Stream()
-    vol = CubeHandler(cam, VOXEL, max_cubes=1 << 16, device=local, stream=stream.cuda_stream)
-    I = np.ascontiguousarray(np.eye(4, dtype=np.float32)).reshape(16)
+    vol = CubeHandler(cam, VOXEL, max_cubes=1 << 18, device=local, stream=stream.cuda_stream)
+    icp = C.c_void_p()
+    capi.check(capi.lib.opb_icp_create(local, C.c_void_p(stream.cuda_stream), C.byref(icp)))
+    par = capi.IcpParams(ICP_ITERS, ICP_THRESHOLD, 1.0)
+    res = capi.IcpResult()
+    I16 = np.ascontiguousarray(np.eye(4, dtype=np.float32)).reshape(16)
     npx = cam.width * cam.height
+    n_pts = len(frames[0]["cloud"])
 
-    # device-resident copies (for `value`) and pinned host copies (for `e2e`)
-    d_depth = [torch.from_numpy(d).cuda() for d, _ in frames]
-    d_bgr = [torch.from_numpy(c).cuda() for _, c in frames]
-    h_depth = [torch.from_numpy(d).pin_memory() for d, _ in frames]
-    h_bgr = [torch.from_numpy(c).pin_memory() for _, c in frames]
+    def dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
-    def step_device(k):
-        i = k % len(frames)
-        vol.IntegrateImageDevice(d_depth[i].data_ptr(), capi.OPB_DEPTH_F32, d_bgr[i].data_ptr(), I)
+    def pin(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
 
+    D = [{k: dev(f[k]) for k in ("depth", "bgr", "cloud", "normals")} for f in frames]   # resident in HBM: `value`
+    H = [{k: pin(f[k]) for k in ("depth", "bgr", "cloud", "normals")} for f in frames]   # pinned host: `e2e`
     stats = capi.FrameStats()
 
-    def step_e2e(k):
-        # the call a user makes: host buffers in, volume updated, per-frame result (cube/voxel counters) read back
-        i = k % len(frames)
-        capi.check(capi.lib.opb_volume_integrate(vol._h, C.c_void_p(h_depth[i].data_ptr()), capi.OPB_DEPTH_F32,
-                                                 C.c_void_p(h_bgr[i].data_ptr()), I.ctypes.data_as(C.c_void_p)))
-        capi.check(capi.lib.opb_volume_frame_stats(vol._h, C.byref(stats)))
+    def one_step(s, B, host: bool):
+        k = s % (N_TRAJ - 1)
+        a, b = B[k], B[k + 1]
+        # registration::PointToPlane(source = frame k+1, target = frame k) -> T with p_k = T p_{k+1}
+        capi.check(capi.lib.opb_icp_point_to_plane(icp, C.c_void_p(b["cloud"].data_ptr()), n_pts, C.c_void_p(a["cloud"].data_ptr()),
+                                                   C.c_void_p(a["normals"].data_ptr()), n_pts, I16.ctypes.data_as(C.c_void_p),
+                                                   C.byref(par), C.byref(res), None, 0))
+        T = np.array(res.T[:], np.float64).reshape(4, 4).T
+        pose = np.ascontiguousarray((frames[k]["pose"] @ T).astype(np.float32).T).reshape(16)
+        if host:
+            # CubeHandler::IntegrateImage with host images, then the frame's counters back on the host
+            capi.check(capi.lib.opb_volume_integrate(vol._h, C.c_void_p(b["depth"].data_ptr()), capi.OPB_DEPTH_U16,
+                                                     C.c_void_p(b["bgr"].data_ptr()), pose.ctypes.data_as(C.c_void_p)))
+            capi.check(capi.lib.opb_volume_frame_stats(vol._h, C.byref(stats)))
+        else:
+            vol.IntegrateImageDevice(b["depth"].data_ptr(), capi.OPB_DEPTH_U16, b["bgr"].data_ptr(), pose)
 
-    def timed(step_fn, steps, warmup):
-        for k in range(warmup):
-            step_fn(k)
+    def timed(steps, warmup, host):
+        B = H if host else D
+        for s in range(warmup):
+            one_step(s, B, host)
         vol.Synchronize()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            for k in range(steps):
-                step_fn(warmup + k)
-            e1.record(stream)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for s in range(steps):
+            one_step(warmup + s, B, host)
+        e1.record(stream)
         vol.Synchronize()
+        wall = time.perf_counter() - t0
         barrier()
         ms = e0.elapsed_time(e1)
         if world > 1:
-            t = torch.tensor([ms], device="cuda")
+            t = torch.tensor([ms, wall], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+            ms, wall = float(t[0].item()), float(t[1].item())
+        return ms, wall
 
     W = max(args.warmup, 3)
     K = args.steps
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev = timed(step_device, K, W)
+    ms_dev, _ = timed(K, W, host=False)
     clocks = sampler.stop() if rank == 0 else None
 
-    # same region again with per-kernel CUDA events (on the stream the kernels run on) for the roofline
+    # the same region again with per-kernel CUDA events (on the stream the kernels run on) for the rooflines
     vol.SetProfiling(True)
     vol.ProfileRead(reset=True)
-    upd = 0
-    timed(step_device, K, 0)
+    capi.lib.opb_icp_set_profiling(icp, 1)
+    icp_loop_ms, icp_grid_ms, upd_sum, cubes = 0.0, 0.0, 0, 0
+    for s in range(min(K, 50)):
+        one_step(W + s, D, False)
+        a, b = C.c_float(0), C.c_float(0)
+        capi.lib.opb_icp_last_timing(icp, C.byref(a), C.byref(b))
+        icp_grid_ms += a.value
+        icp_loop_ms += b.value
+        st = vol.FrameStats()
+        upd_sum += st.updated_voxels
+        cubes = st.frame_cubes
+    nprof_steps = min(K, 50)
     sel_ms, int_ms, nprof = vol.ProfileRead(reset=True)
     vol.SetProfiling(False)
-    st = vol.FrameStats()
-    upd = st.updated_voxels  # last frame; steady state: all frames are alike
+    capi.lib.opb_icp_set_profiling(icp, 0)
 
-    # end to end through the public call with host buffers; host wall clock is the honest clock here because the
-    # call is synchronous (H2D + kernels + D2H of the counters inside)
-    for k in range(W):
-        step_e2e(k)
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(K):
-        step_e2e(W + k)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    # end to end through the public calls with HOST buffers (pinned): H2D of both clouds + normals + depth + colour and
+    # D2H of the pose / counters inside the timed region; device events on the work stream bracket the region, the
+    # calls themselves are synchronous
+    e2e_ms, _ = timed(K, W, host=True)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     pk, pk_kind = peaks()
-    alg_bytes = upd * 2 * 20 + npx * 7
+    upd = upd_sum / max(nprof_steps, 1)
+    alg_bytes = upd * 2 * 20 + npx * (2 + 3)  # updated voxels read+written at 20 B, one pass over u16 depth + colour
     k2_ms = int_ms / max(nprof, 1)
     achieved = alg_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
+    icp_iter_ms = icp_loop_ms / nprof_steps / (ICP_ITERS + 1)
+    icp_bytes = n_pts * 12 + n_pts * 36  # N_s*12 (source) + N_inl*(12+12+12) (nn point, normal, source)
+    icp_ach = icp_bytes / (icp_iter_ms * 1e-3) / 1e9 if icp_iter_ms > 0 else 0.0
+    launches_per_step = 8 + 2 * (ICP_ITERS + 1) + 2 + 3
     out = {
         "metric": METRIC, "value": world * K / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "config1: S1 wavy wall 640x480 f32 depth, 5 mm voxels, identity poses, integrate only "
-                               "(ICP stage not yet in the step)",
-                   "voxel_m": VOXEL, "storage": "f32 20 B/voxel", "cubes_per_frame": st.frame_cubes,
-                   "updated_voxels_per_frame": int(upd), "l2": "working set 207 MB/frame > 126 MB L2 (no flush needed)",
-                   "sharding": "one independent sub-volume stream per GPU, no data-path collective"},
-        "roofline": {"bound": "hbm", "kernel": "integrate_kernel", "achieved": achieved, "peak": pk["hbm_gbs"],
-                     "peak_source": pk_kind, "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                     "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": k2_ms, "select_ms": sel_ms / max(nprof, 1),
+        "config": {"workload": WORKLOAD, "voxel_m": VOXEL, "storage": "f32 20 B/voxel", "cubes_per_frame": cubes,
+                   "updated_voxels_per_frame": int(upd), "icp_points": n_pts,
+                   "l2": "voxel working set of a frame (cubes x 10 KB) exceeds the 126 MB L2; no explicit flush",
+                   "sharding": "one independent sub-volume stream per GPU, no data-path collective",
+                   "step_breakdown_ms": {"icp_grid_build": icp_grid_ms / nprof_steps, "icp_iterations": icp_loop_ms / nprof_steps,
+                                         "cube_selection": sel_ms / max(nprof, 1), "voxel_update": k2_ms}},
+        "roofline": {"bound": "hbm", "kernel": "integrate_kernel (the kernel north_star sets the >=60% target for)",
+                     "achieved": achieved, "peak": pk["hbm_gbs"], "peak_source": pk_kind, "unit": "GB/s",
+                     "frac": achieved / pk["hbm_gbs"], "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": k2_ms,
                      "traffic": None},
-        "e2e": {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": npx * 7, "d2h_bytes_per_step": 64,
-                "clock": "host wall clock around synchronous opb_volume_integrate + opb_volume_frame_stats"},
-        "gpu_launches": 3 * K, "clocks": clocks,
+        "roofline_icp": {"bound": "hbm", "kernel": "icp_iteration_kernel + icp_solve_kernel (time-dominant; working set "
+                                                   "L2-resident, latency-bound)",
+                         "achieved": icp_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": icp_ach / pk["hbm_gbs"],
+                         "algorithmic_bytes_per_launch": int(icp_bytes), "kernel_ms": icp_iter_ms, "traffic": None},
+        "e2e": {"value": world * K / (e2e_ms * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": 3 * n_pts * 12 + npx * 5, "d2h_bytes_per_step": 256 + 64,
+                "clock": "CUDA events on the work stream around K synchronous PointToPlane + IntegrateImage + FrameStats calls "
+                         "with pinned host buffers"},
+        "gpu_launches": launches_per_step * K, "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:
-        cb, _, _ = cpu_reference_fps(60, 2, budget_s=15.0)
+        cb, _, _ = cpu_reference_fps(30, 1, budget_s=20.0)
         out["cpu_baseline"] = cb
     print(json.dumps(out), flush=True)
+    capi.lib.opb_icp_destroy(icp)
     if world > 1:
         dist.destroy_process_group()
 

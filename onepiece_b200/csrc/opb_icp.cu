@@ -43,7 +43,6 @@ struct IcpState // device-resident solver state
 {
     float T[16];        // current source->target transform, column-major float (start_T)
     double packet[kPacket];
-    unsigned int ticket;
     int iteration;
     IcpGrid grid;
     float bbox_lo[3], bbox_hi[3];
@@ -358,78 +357,91 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// adds the warp-wide sum of v to the warp's running total of packet component k
+__device__ __forceinline__ void warp_accumulate(double (*s_part)[kPacket], int warp, int lane, int k, double v)
+{
+    v = warp_sum(v);
+    if (lane == 0) s_part[warp][k] += v;
+}
+
+// One pass over the source cloud: transform, exact nearest neighbour, CountInliers test, Jacobian row, and the
+// per-CTA partial sums of the 30-scalar packet.  Persistent grid (a multiple of the SM count), grid-stride over
+// the points; every warp keeps running totals in shared memory, CTAs write their partial packet in a fixed slot.
 __global__ void __launch_bounds__(kIcpThreads) icp_iteration_kernel(IcpArgs a)
 {
     __shared__ double s_part[kIcpThreads / 32][kPacket];
-    __shared__ bool s_last;
-    const float *T = a.st->T; // column-major
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double acc[kPacket];
-#pragma unroll
-    for (int k = 0; k < kPacket; ++k) acc[k] = 0.0;
-    if (i < a.ns)
-    {
-        const float sx = a.src[3 * i], sy = a.src[3 * i + 1], sz = a.src[3 * i + 2];
-        // geometry::TransformPoints: T * (x,y,z,1) then divide by w (Geometry.cpp:19-27)
-        const float w = row_xyz1(T[3], T[7], T[11], T[15], sx, sy, sz);
-        const float px = fdiv(row_xyz1(T[0], T[4], T[8], T[12], sx, sy, sz), w);
-        const float py = fdiv(row_xyz1(T[1], T[5], T[9], T[13], sx, sy, sz), w);
-        const float pz = fdiv(row_xyz1(T[2], T[6], T[10], T[14], sx, sy, sz), w);
-        const int j = grid_nearest(a.st->grid, a.cell_start, a.sorted, px, py, pz, a.search_radius);
-        a.nn[i] = j;
-        bool inl = false;
-        if (j >= 0)
-        {
-            const float tx = a.tgt[3 * j], ty = a.tgt[3 * j + 1], tz = a.tgt[3 * j + 2];
-            // CountInliers (ICP.cpp:19-21): (R*s + t - target).squaredNorm() in float, compared as double
-            const float ex = fsub(fadd(fadd(fmul(T[0], sx), fadd(fmul(T[4], sy), fmul(T[8], sz))), T[12]), tx);
-            const float ey = fsub(fadd(fadd(fmul(T[1], sx), fadd(fmul(T[5], sy), fmul(T[9], sz))), T[13]), ty);
-            const float ez = fsub(fadd(fadd(fmul(T[2], sx), fadd(fmul(T[6], sy), fmul(T[10], sz))), T[14]), tz);
-            const double err = (double)fadd(fmul(ex, ex), fadd(fmul(ey, ey), fmul(ez, ez)));
-            if (err < a.sq_threshold)
-            {
-                inl = true;
-                acc[28] = err;
-                acc[29] = 1.0;
-                if (!a.final_pass)
-                {
-                    if (a.nrm)
-                    {
-                        // EstimateRigidTransformationPointToPlane (ICP.cpp:121-136): row = [n ; s' x n],
-                        // r = n.s' - n.t with s' the transformed source point
-                        const float nx = a.nrm[3 * j], ny = a.nrm[3 * j + 1], nz = a.nrm[3 * j + 2];
-                        const float r = fsub(dot3(nx, ny, nz, px, py, pz), dot3(nx, ny, nz, tx, ty, tz));
-                        const float row[6] = {nx, ny, nz, fsub(fmul(py, nz), fmul(pz, ny)), fsub(fmul(pz, nx), fmul(px, nz)),
-                                              fsub(fmul(px, ny), fmul(py, nx))};
-                        int k = 0;
-#pragma unroll
-                        for (int p = 0; p < 6; ++p)
-#pragma unroll
-                            for (int q = p; q < 6; ++q) acc[k++] = (double)fmul(row[p], row[q]);
-#pragma unroll
-                        for (int p = 0; p < 6; ++p) acc[21 + p] = (double)fmul(r, row[p]);
-                    }
-                    else
-                    {
-                        // PointToPoint (ICP.cpp:78-84): Kabsch sums over (transformed source, target)
-                        acc[0] = px; acc[1] = py; acc[2] = pz;
-                        acc[3] = tx; acc[4] = ty; acc[5] = tz;
-                        acc[6] = (double)px * tx; acc[7] = (double)px * ty; acc[8] = (double)px * tz;
-                        acc[9] = (double)py * tx; acc[10] = (double)py * ty; acc[11] = (double)py * tz;
-                        acc[12] = (double)pz * tx; acc[13] = (double)pz * ty; acc[14] = (double)pz * tz;
-                    }
-                }
-            }
-        }
-        if (a.final_pass) a.inlier[i] = inl;
-    }
-    // 30-scalar reduction: warp shuffles, then warps in fixed order, then CTAs in fixed order (deterministic)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < 30; ++k)
+    if (lane < 30) s_part[warp][lane] = 0.0;
+    __syncwarp();
+    const float *T = a.st->T; // column-major
+    const int stride = gridDim.x * blockDim.x;
+    // all lanes of a warp run the same number of trips (shuffles inside)
+    for (int base = blockIdx.x * blockDim.x + warp * 32; base < a.ns; base += stride)
     {
-        const double s = warp_sum(acc[k]);
-        if (lane == 0) s_part[warp][k] = s;
+        const int i = base + lane;
+        bool inl = false;
+        float px = 0, py = 0, pz = 0, tx = 0, ty = 0, tz = 0;
+        double err = 0.0;
+        int j = -1;
+        if (i < a.ns)
+        {
+            const float sx = a.src[3 * i], sy = a.src[3 * i + 1], sz = a.src[3 * i + 2];
+            // geometry::TransformPoints: T * (x,y,z,1) then divide by w (Geometry.cpp:19-27)
+            const float w = row_xyz1(T[3], T[7], T[11], T[15], sx, sy, sz);
+            px = fdiv(row_xyz1(T[0], T[4], T[8], T[12], sx, sy, sz), w);
+            py = fdiv(row_xyz1(T[1], T[5], T[9], T[13], sx, sy, sz), w);
+            pz = fdiv(row_xyz1(T[2], T[6], T[10], T[14], sx, sy, sz), w);
+            j = grid_nearest(a.st->grid, a.cell_start, a.sorted, px, py, pz, a.search_radius);
+            a.nn[i] = j;
+            if (j >= 0)
+            {
+                tx = a.tgt[3 * j]; ty = a.tgt[3 * j + 1]; tz = a.tgt[3 * j + 2];
+                // CountInliers (ICP.cpp:19-21): (R*s + t - target).squaredNorm() in float, compared as double
+                const float ex = fsub(fadd(fadd(fmul(T[0], sx), fadd(fmul(T[4], sy), fmul(T[8], sz))), T[12]), tx);
+                const float ey = fsub(fadd(fadd(fmul(T[1], sx), fadd(fmul(T[5], sy), fmul(T[9], sz))), T[13]), ty);
+                const float ez = fsub(fadd(fadd(fmul(T[2], sx), fadd(fmul(T[6], sy), fmul(T[10], sz))), T[14]), tz);
+                err = (double)fadd(fmul(ex, ex), fadd(fmul(ey, ey), fmul(ez, ez)));
+                inl = err < a.sq_threshold;
+            }
+            if (a.final_pass) a.inlier[i] = inl;
+        }
+        if (!__any_sync(0xffffffffu, inl)) continue;
+        warp_accumulate(s_part, warp, lane, 28, inl ? err : 0.0);
+        warp_accumulate(s_part, warp, lane, 29, inl ? 1.0 : 0.0);
+        if (a.final_pass) continue;
+        if (a.nrm)
+        {
+            // EstimateRigidTransformationPointToPlane (ICP.cpp:121-136): row = [n ; s' x n], r = n.s' - n.t with
+            // s' the transformed source point; all in float like the reference, summed in double
+            float row[6] = {0, 0, 0, 0, 0, 0}, r = 0;
+            if (inl)
+            {
+                const float nx = a.nrm[3 * j], ny = a.nrm[3 * j + 1], nz = a.nrm[3 * j + 2];
+                r = fsub(dot3(nx, ny, nz, px, py, pz), dot3(nx, ny, nz, tx, ty, tz));
+                row[0] = nx; row[1] = ny; row[2] = nz;
+                row[3] = fsub(fmul(py, nz), fmul(pz, ny));
+                row[4] = fsub(fmul(pz, nx), fmul(px, nz));
+                row[5] = fsub(fmul(px, ny), fmul(py, nx));
+            }
+            int k = 0;
+#pragma unroll
+            for (int p = 0; p < 6; ++p)
+#pragma unroll
+                for (int q = p; q < 6; ++q) warp_accumulate(s_part, warp, lane, k++, (double)fmul(row[p], row[q]));
+#pragma unroll
+            for (int p = 0; p < 6; ++p) warp_accumulate(s_part, warp, lane, 21 + p, (double)fmul(r, row[p]));
+        }
+        else
+        {
+            // PointToPoint (ICP.cpp:78-84): Kabsch sums over (transformed source, target)
+            const double P[3] = {inl ? px : 0.0, inl ? py : 0.0, inl ? pz : 0.0}, Q[3] = {inl ? tx : 0.0, inl ? ty : 0.0, inl ? tz : 0.0};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { warp_accumulate(s_part, warp, lane, c, P[c]); warp_accumulate(s_part, warp, lane, 3 + c, Q[c]); }
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) warp_accumulate(s_part, warp, lane, 6 + 3 * p + q, P[p] * Q[q]);
+        }
     }
     __syncthreads();
     if (threadIdx.x < 30)
@@ -438,17 +450,17 @@ __global__ void __launch_bounds__(kIcpThreads) icp_iteration_kernel(IcpArgs a)
         for (int w = 0; w < kIcpThreads / 32; ++w) s += s_part[w][threadIdx.x];
         a.partials[(size_t)blockIdx.x * kPacket + threadIdx.x] = s;
     }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(&a.st->ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+}
+
+// Sums the CTA partials in a fixed order, then solves and updates the pose (one CTA).
+__global__ void __launch_bounds__(kIcpThreads) icp_solve_kernel(IcpArgs a, int n_partials)
+{
+    __shared__ double s_part[kIcpThreads / 32][kPacket];
     {
-        // fixed-order sum over the CTA partials: 8 interleaved chains per component, then the chains in order
-        const int k = threadIdx.x & 31, chain = threadIdx.x >> 5; // kIcpThreads / 32 == 8 chains
+        // 8 interleaved chains per component, then the chains in order: deterministic
+        const int k = threadIdx.x & 31, chain = threadIdx.x >> 5;
         double s = 0.0;
-        for (unsigned int b = chain; b < gridDim.x; b += kIcpThreads / 32) s += a.partials[(size_t)b * kPacket + k];
+        for (int b = chain; b < n_partials; b += kIcpThreads / 32) s += a.partials[(size_t)b * kPacket + k];
         s_part[chain][k] = s;
         __syncthreads();
         if (threadIdx.x < 30)
@@ -461,7 +473,6 @@ __global__ void __launch_bounds__(kIcpThreads) icp_iteration_kernel(IcpArgs a)
     __syncthreads();
     if (threadIdx.x != 0) return;
     IcpState *st = a.st;
-    st->ticket = 0;
     st->sum_error = st->packet[28];
     st->n_inliers = (unsigned long long)(st->packet[29] + 0.5);
     if (a.final_pass) return;
@@ -495,34 +506,37 @@ __global__ void __launch_bounds__(kIcpThreads) icp_iteration_kernel(IcpArgs a)
     for (int e = 0; e < 16; ++e) st->T[e] = Tn[e];
 }
 
-// final Kabsch sums over the inlier pairs of the ORIGINAL (unscaled) clouds + ordered compaction of the pairs
+// final Kabsch sums over the inlier pairs of the ORIGINAL (unscaled) clouds (per-CTA partials, 16 components)
 __global__ void __launch_bounds__(kIcpThreads) icp_final_sums_kernel(const float *src, const float *tgt, const int *nn,
                                                                      const unsigned char *inlier, int ns, float scaling,
-                                                                     double *partials, IcpState *st)
+                                                                     double *partials)
 {
-    __shared__ double s_part[kIcpThreads / 32][16];
-    __shared__ bool s_last;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double acc[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) acc[k] = 0.0;
-    if (i < ns && inlier[i])
-    {
-        const int j = nn[i];
-        float s[3] = {src[3 * i], src[3 * i + 1], src[3 * i + 2]}, t[3] = {tgt[3 * j], tgt[3 * j + 1], tgt[3 * j + 2]};
-        if (scaling != 1.0f)
-            for (int c = 0; c < 3; ++c) { s[c] = fdiv(s[c], scaling); t[c] = fdiv(t[c], scaling); } // ICP.cpp:93-99,208-214
-        for (int c = 0; c < 3; ++c) { acc[c] = s[c]; acc[3 + c] = t[c]; }
-        for (int p = 0; p < 3; ++p)
-            for (int q = 0; q < 3; ++q) acc[6 + 3 * p + q] = (double)s[p] * t[q];
-        acc[15] = 1.0;
-    }
+    __shared__ double s_part[kIcpThreads / 32][kPacket];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
+    if (lane < 16) s_part[warp][lane] = 0.0;
+    __syncwarp();
+    const int stride = gridDim.x * blockDim.x;
+    for (int base = blockIdx.x * blockDim.x + warp * 32; base < ns; base += stride)
     {
-        const double v = warp_sum(acc[k]);
-        if (lane == 0) s_part[warp][k] = v;
+        const int i = base + lane;
+        const bool inl = i < ns && inlier[i];
+        if (!__any_sync(0xffffffffu, inl)) continue;
+        double S[3] = {0, 0, 0}, Q[3] = {0, 0, 0};
+        if (inl)
+        {
+            const int j = nn[i];
+            float s[3] = {src[3 * i], src[3 * i + 1], src[3 * i + 2]}, t[3] = {tgt[3 * j], tgt[3 * j + 1], tgt[3 * j + 2]};
+            if (scaling != 1.0f)
+                for (int c = 0; c < 3; ++c) { s[c] = fdiv(s[c], scaling); t[c] = fdiv(t[c], scaling); } // ICP.cpp:93-99,208-214
+            for (int c = 0; c < 3; ++c) { S[c] = s[c]; Q[c] = t[c]; }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { warp_accumulate(s_part, warp, lane, c, S[c]); warp_accumulate(s_part, warp, lane, 3 + c, Q[c]); }
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) warp_accumulate(s_part, warp, lane, 6 + 3 * p + q, S[p] * Q[q]);
+        warp_accumulate(s_part, warp, lane, 15, inl ? 1.0 : 0.0);
     }
     __syncthreads();
     if (threadIdx.x < 16)
@@ -531,19 +545,22 @@ __global__ void __launch_bounds__(kIcpThreads) icp_final_sums_kernel(const float
         for (int w = 0; w < kIcpThreads / 32; ++w) v += s_part[w][threadIdx.x];
         partials[(size_t)blockIdx.x * kPacket + threadIdx.x] = v;
     }
-    __threadfence();
+}
+__global__ void __launch_bounds__(kIcpThreads) icp_final_reduce_kernel(const double *partials, int n_partials, IcpState *st)
+{
+    __shared__ double s_part[kIcpThreads / 32][kPacket];
+    const int k = threadIdx.x & 31, chain = threadIdx.x >> 5;
+    double s = 0.0;
+    if (k < 16)
+        for (int b = chain; b < n_partials; b += kIcpThreads / 32) s += partials[(size_t)b * kPacket + k];
+    s_part[chain][k] = s;
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
     if (threadIdx.x < 16)
     {
-        double v = 0.0;
-        for (unsigned int b = 0; b < gridDim.x; ++b) v += partials[(size_t)b * kPacket + threadIdx.x];
-        st->packet[threadIdx.x] = v;
+        double tot = 0.0;
+        for (int c = 0; c < kIcpThreads / 32; ++c) tot += s_part[c][threadIdx.x];
+        st->packet[threadIdx.x] = tot;
     }
-    if (threadIdx.x == 0) st->ticket = 0;
 }
 
 // ordered compaction of inlier pairs (source index ascending, like the reference's push_back loop)
@@ -775,13 +792,20 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     a.search_radius = (float)(par->threshold * (1.0 + 1e-3)) + 1e-6f;
     a.sq_threshold = par->threshold * par->threshold;
     a.final_pass = 0; a.pairs = c->d_pairs; a.inlier = c->d_inlier;
-    const int nb_s = (int)((ns + kIcpThreads - 1) / kIcpThreads);
-    for (int it = 0; it < par->max_iteration; ++it) icp_iteration_kernel<<<nb_s, kIcpThreads, 0, s>>>(a);
+    const int nb_need = (int)((ns + kIcpThreads - 1) / kIcpThreads);
+    const int nb_s = nb_need < c->sm_count * 4 ? nb_need : c->sm_count * 4; // persistent grid
+    for (int it = 0; it < par->max_iteration; ++it)
+    {
+        icp_iteration_kernel<<<nb_s, kIcpThreads, 0, s>>>(a);
+        icp_solve_kernel<<<1, kIcpThreads, 0, s>>>(a, nb_s);
+    }
     // final CountInliers with the final T (ICP.cpp:90-91,206-207)
     a.final_pass = 1;
     icp_iteration_kernel<<<nb_s, kIcpThreads, 0, s>>>(a);
+    icp_solve_kernel<<<1, kIcpThreads, 0, s>>>(a, nb_s);
     OPB_CUDA(cudaMemcpyAsync(h, c->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
-    icp_final_sums_kernel<<<nb_s, kIcpThreads, 0, s>>>(c->d_src, c->d_tgt, c->d_nn, c->d_inlier, (int)ns, scaling, c->d_partials, c->d_state);
+    icp_final_sums_kernel<<<nb_s, kIcpThreads, 0, s>>>(c->d_src, c->d_tgt, c->d_nn, c->d_inlier, (int)ns, scaling, c->d_partials);
+    icp_final_reduce_kernel<<<1, kIcpThreads, 0, s>>>(c->d_partials, nb_s, c->d_state);
     if (pairs && pairs_cap) icp_compact_kernel<<<1, 1024, 0, s>>>(c->d_nn, c->d_inlier, (int)ns, c->d_pairs, (unsigned long long)pairs_cap);
     if (c->profiling) OPB_CUDA(cudaEventRecord(c->ev[2], s));
     OPB_CUDA(cudaGetLastError());

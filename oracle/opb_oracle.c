@@ -497,3 +497,280 @@ long orc_volume_extract_mesh(const orc_volume *v, float **xyz_out, float **rgb_o
     *rgb_out = rgb;
     return n;
 }
+
+/* ------------------------------------------------------------------------------------------------------- */
+/* registration                                                                                            */
+/* ------------------------------------------------------------------------------------------------------- */
+/* cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (row-major); eigenvalues on the diagonal of A */
+static void jacobi_eig(double *A, double *V, int n)
+{
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) V[i * n + j] = i == j;
+    for (int sweep = 0; sweep < 60; ++sweep)
+    {
+        double off = 0;
+        for (int i = 0; i < n; ++i)
+            for (int j = i + 1; j < n; ++j) off += A[i * n + j] * A[i * n + j];
+        if (off < 1e-300) break;
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q)
+            {
+                if (A[p * n + q] == 0) continue;
+                double th = (A[q * n + q] - A[p * n + p]) / (2 * A[p * n + q]);
+                double t = (th >= 0 ? 1 : -1) / (fabs(th) + sqrt(th * th + 1));
+                double c = 1 / sqrt(t * t + 1), s = t * c;
+                for (int k = 0; k < n; ++k)
+                {
+                    double a = A[k * n + p], b = A[k * n + q];
+                    A[k * n + p] = c * a - s * b; A[k * n + q] = s * a + c * b;
+                }
+                for (int k = 0; k < n; ++k)
+                {
+                    double a = A[p * n + k], b = A[q * n + k];
+                    A[p * n + k] = c * a - s * b; A[q * n + k] = s * a + c * b;
+                }
+                for (int k = 0; k < n; ++k)
+                {
+                    double a = V[k * n + p], b = V[k * n + q];
+                    V[k * n + p] = c * a - s * b; V[k * n + q] = s * a + c * b;
+                }
+            }
+    }
+}
+/* JacobiSVD(JTJ).solve(b), ICP.cpp:137-138: minimum-norm least squares; singular values below
+ * epsilon(float) * 6 * max are treated as zero (Eigen's default rank threshold for the float build) */
+static void solve_pinv6(const double *A_in, const double *b, double *x)
+{
+    double A[36], V[36];
+    memcpy(A, A_in, sizeof(A));
+    jacobi_eig(A, V, 6);
+    double lmax = 0;
+    for (int i = 0; i < 6; ++i) lmax = fmax(lmax, fabs(A[i * 6 + i]));
+    for (int i = 0; i < 6; ++i) x[i] = 0;
+    for (int k = 0; k < 6; ++k)
+    {
+        double l = A[k * 6 + k];
+        if (!(fabs(l) > 6 * 1.1920929e-7 * lmax)) continue;
+        double pr = 0;
+        for (int i = 0; i < 6; ++i) pr += V[i * 6 + k] * b[i];
+        for (int i = 0; i < 6; ++i) x[i] += V[i * 6 + k] * pr / l;
+    }
+}
+/* geometry::Se3ToSE3 -> Sophus::SE3Group::exp (se3.hpp:468-489, so3.hpp:388-412); T row-major here */
+static void se3_exp_rm(const double *x, double *T)
+{
+    const double *w = x + 3;
+    double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = sqrt(th2);
+    double O[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0}, O2[9], R[9], V[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+        {
+            O2[i * 3 + j] = 0;
+            for (int k = 0; k < 3; ++k) O2[i * 3 + j] += O[i * 3 + k] * O[k * 3 + j];
+        }
+    double a, b, c; /* R = I + a O + b O^2 ; V = I + b O + c O^2 */
+    if (th < 1e-10) { a = 1; b = 0.5; c = 1.0 / 6; }
+    else { a = sin(th) / th; b = (1 - cos(th)) / th2; c = (th - sin(th)) / (th2 * th); }
+    for (int i = 0; i < 9; ++i)
+    {
+        R[i] = (i % 4 == 0) + a * O[i] + b * O2[i];
+        V[i] = (i % 4 == 0) + b * O[i] + c * O2[i];
+    }
+    for (int i = 0; i < 3; ++i)
+    {
+        for (int j = 0; j < 3; ++j) T[i * 4 + j] = R[i * 3 + j];
+        T[i * 4 + 3] = V[i * 3] * x[0] + V[i * 3 + 1] * x[1] + V[i * 3 + 2] * x[2];
+    }
+    T[12] = T[13] = T[14] = 0; T[15] = 1;
+}
+void orc_se3_exp(const double *x6, double *T_cm)
+{
+    double T[16];
+    se3_exp_rm(x6, T);
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) T_cm[c * 4 + r] = T[r * 4 + c];
+}
+/* geometry::EstimateRigidTransformation (Geometry.cpp:107-151) from pair lists, double; T row-major */
+static void kabsch(const float *a, const float *b, long n, double *T)
+{
+    double ma[3] = {0, 0, 0}, mb[3] = {0, 0, 0}, W[9] = {0};
+    for (long i = 0; i < n; ++i)
+        for (int c = 0; c < 3; ++c) { ma[c] += a[3 * i + c]; mb[c] += b[3 * i + c]; }
+    for (int c = 0; c < 3; ++c) { ma[c] /= n; mb[c] /= n; }
+    for (long i = 0; i < n; ++i)
+        for (int p = 0; p < 3; ++p)
+            for (int q = 0; q < 3; ++q) W[p * 3 + q] += (a[3 * i + p] - ma[p]) * (b[3 * i + q] - mb[q]);
+    /* SVD of W through the eigen-decomposition of W^T W */
+    double WtW[9], V[9], U[9], sig[3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+        {
+            WtW[i * 3 + j] = 0;
+            for (int k = 0; k < 3; ++k) WtW[i * 3 + j] += W[k * 3 + i] * W[k * 3 + j];
+        }
+    jacobi_eig(WtW, V, 3);
+    int ord[3] = {0, 1, 2};
+    for (int i = 0; i < 2; ++i)
+        for (int j = i + 1; j < 3; ++j)
+            if (WtW[ord[j] * 4] > WtW[ord[i] * 4]) { int t = ord[i]; ord[i] = ord[j]; ord[j] = t; }
+    double Vs[9];
+    for (int c = 0; c < 3; ++c)
+    {
+        sig[c] = sqrt(fmax(WtW[ord[c] * 4], 0));
+        for (int i = 0; i < 3; ++i) Vs[i * 3 + c] = V[i * 3 + ord[c]];
+    }
+    for (int c = 0; c < 3; ++c)
+        for (int i = 0; i < 3; ++i)
+        {
+            double u = W[i * 3] * Vs[c] + W[i * 3 + 1] * Vs[3 + c] + W[i * 3 + 2] * Vs[6 + c];
+            U[i * 3 + c] = sig[c] > 0 ? u / sig[c] : 0;
+        }
+    if (!(sig[2] > 1e-14 * sig[0]))
+    {   /* rank 2: third left vector = u0 x u1 */
+        U[2] = U[3] * U[7] - U[6] * U[4]; U[5] = U[6] * U[1] - U[0] * U[7]; U[8] = U[0] * U[4] - U[3] * U[1];
+    }
+    double R[9];
+    for (int pass = 0; pass < 2; ++pass)
+    {
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j)
+            {
+                R[i * 3 + j] = 0;
+                for (int k = 0; k < 3; ++k) R[i * 3 + j] += Vs[i * 3 + k] * U[j * 3 + k]; /* R = V U^T */
+            }
+        double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
+        if (det >= 0 || pass) break;
+        for (int i = 0; i < 3; ++i) Vs[i * 3 + 2] = -Vs[i * 3 + 2];
+    }
+    for (int i = 0; i < 3; ++i)
+    {
+        for (int j = 0; j < 3; ++j) T[i * 4 + j] = R[i * 3 + j];
+        T[i * 4 + 3] = mb[i] - (R[i * 3] * ma[0] + R[i * 3 + 1] * ma[1] + R[i * 3 + 2] * ma[2]);
+    }
+    T[12] = T[13] = T[14] = 0; T[15] = 1;
+}
+/* KDTree::KnnSearch(k = 1) (KDTree.h:177-196): exact; distance as nanoflann's L2_Simple_Adaptor sums it */
+void orc_nearest(const float *q, long nq, const float *t, long nt, int32_t *nn)
+{
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < nq; ++i)
+    {
+        float best = FLT_MAX;
+        int bi = -1;
+        const float qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
+        for (long j = 0; j < nt; ++j)
+        {
+            float dx = qx - t[3 * j], dy = qy - t[3 * j + 1], dz = qz - t[3 * j + 2];
+            float d = dx * dx + dy * dy + dz * dz;
+            if (d < best) { best = d; bi = (int)j; }
+        }
+        nn[i] = bi;
+    }
+}
+/* CountInliers (ICP.cpp:9-30); T column-major float */
+static long count_inliers(const float *src, const float *tgt, const int32_t *nn, long ns, const float *T, double thr,
+                          int32_t *pairs, double *rmse)
+{
+    double sum = 0, thr2 = thr * thr;
+    long n = 0;
+    for (long i = 0; i < ns; ++i)
+    {
+        if (nn[i] < 0) continue;
+        const float *s = src + 3 * i, *t = tgt + 3 * nn[i];
+        float e[3];
+        for (int r = 0; r < 3; ++r) e[r] = ((T[r] * s[0] + (T[4 + r] * s[1] + T[8 + r] * s[2])) + T[12 + r]) - t[r];
+        double err = e[0] * e[0] + (e[1] * e[1] + e[2] * e[2]);
+        if (err < thr2) { pairs[2 * n] = (int32_t)i; pairs[2 * n + 1] = nn[i]; ++n; sum += err; }
+    }
+    *rmse = sqrt(sum / n);
+    return n;
+}
+long orc_icp(const float *src_in, long ns, const float *tgt_in, const float *nrm, long nt, const float *init_T, int max_it,
+             double thr, double scaling, double *out_T, double *out_T_iter, int32_t *pairs, double *rmse)
+{
+    float *src = (float *)malloc(sizeof(float) * 3 * ns), *tgt = (float *)malloc(sizeof(float) * 3 * nt);
+    memcpy(src, src_in, sizeof(float) * 3 * ns);
+    memcpy(tgt, tgt_in, sizeof(float) * 3 * nt);
+    if (scaling != 1)
+    {
+        if (nrm) { free(src); free(tgt); return -1; } /* ICP.cpp:159-163 */
+        for (long i = 0; i < 3 * ns; ++i) src[i] = src[i] * (float)scaling;
+        for (long i = 0; i < 3 * nt; ++i) tgt[i] = tgt[i] * (float)scaling;
+    }
+    float T[16];
+    memcpy(T, init_T, sizeof(T));
+    float *tp = (float *)malloc(sizeof(float) * 3 * ns);
+    int32_t *nn = (int32_t *)malloc(sizeof(int32_t) * ns);
+    long n_in = 0;
+    for (int it = 0; it <= max_it; ++it)
+    {
+        /* geometry::TransformPoints (Geometry.cpp:19-27) */
+        for (long i = 0; i < ns; ++i)
+        {
+            const float *s = src + 3 * i;
+            float w = row_xyz1(T, 3, s[0], s[1], s[2]);
+            for (int r = 0; r < 3; ++r) tp[3 * i + r] = row_xyz1(T, r, s[0], s[1], s[2]) / w;
+        }
+        orc_nearest(tp, ns, tgt, nt, nn);
+        n_in = count_inliers(src, tgt, nn, ns, T, thr, pairs, rmse);
+        if (it == max_it) break; /* final CountInliers with the final T (ICP.cpp:90,206) */
+        double dT[16];
+        if (nrm)
+        {   /* EstimateRigidTransformationPointToPlane (ICP.cpp:108-144) */
+            double JTJ[36] = {0}, nJTr[6] = {0}, x[6];
+            for (long k = 0; k < n_in; ++k)
+            {
+                const float *p = tp + 3 * pairs[2 * k], *t = tgt + 3 * pairs[2 * k + 1], *n = nrm + 3 * pairs[2 * k + 1];
+                float r = dot3(n, p) - dot3(n, t);
+                float row[6] = {n[0], n[1], n[2], p[1] * n[2] - p[2] * n[1], p[2] * n[0] - p[0] * n[2], p[0] * n[1] - p[1] * n[0]};
+                for (int a = 0; a < 6; ++a)
+                {
+                    for (int b = 0; b < 6; ++b) JTJ[a * 6 + b] += (double)(row[a] * row[b]);
+                    nJTr[a] -= (double)(r * row[a]);
+                }
+            }
+            solve_pinv6(JTJ, nJTr, x);
+            for (int a = 0; a < 6; ++a) x[a] = (float)x[a];
+            se3_exp_rm(x, dT);
+        }
+        else
+        {   /* PointToPoint (ICP.cpp:78-86) */
+            if (n_in == 0) break;
+            float *a = (float *)malloc(sizeof(float) * 3 * n_in), *b = (float *)malloc(sizeof(float) * 3 * n_in);
+            for (long k = 0; k < n_in; ++k)
+                for (int c = 0; c < 3; ++c) { a[3 * k + c] = tp[3 * pairs[2 * k] + c]; b[3 * k + c] = tgt[3 * pairs[2 * k + 1] + c]; }
+            kabsch(a, b, n_in, dT);
+            free(a); free(b);
+        }
+        /* start_T = tmp_T * start_T in float */
+        float dTf[16], Tn[16];
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) dTf[c * 4 + r] = (float)dT[r * 4 + c];
+        for (int c = 0; c < 4; ++c)
+            for (int r = 0; r < 4; ++r)
+                Tn[c * 4 + r] = ((dTf[r] * T[c * 4] + dTf[4 + r] * T[c * 4 + 1]) + dTf[8 + r] * T[c * 4 + 2]) + dTf[12 + r] * T[c * 4 + 3];
+        memcpy(T, Tn, sizeof(T));
+    }
+    for (int i = 0; i < 16; ++i) out_T_iter[i] = T[i];
+    /* result.T: Kabsch over the inlier pairs of the (un-scaled) clouds (ICP.cpp:93-105,208-221) */
+    if (n_in > 0)
+    {
+        float *a = (float *)malloc(sizeof(float) * 3 * n_in), *b = (float *)malloc(sizeof(float) * 3 * n_in);
+        for (long k = 0; k < n_in; ++k)
+            for (int c = 0; c < 3; ++c)
+            {
+                float sv = src[3 * pairs[2 * k] + c], tv = tgt[3 * pairs[2 * k + 1] + c];
+                if (scaling != 1) { sv = sv / (float)scaling; tv = tv / (float)scaling; }
+                a[3 * k + c] = sv; b[3 * k + c] = tv;
+            }
+        double Tk[16];
+        kabsch(a, b, n_in, Tk);
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) out_T[c * 4 + r] = Tk[r * 4 + c];
+        free(a); free(b);
+    }
+    else
+        for (int i = 0; i < 16; ++i) out_T[i] = NAN;
+    free(src); free(tgt); free(tp); free(nn);
+    return n_in;
+}

@@ -47,6 +47,23 @@ long orc_volume_extract_mesh(const orc_volume *v, float **xyz, float **rgb);
 int orc_marching_cube_cell(const float *corners24, const float *sdf8, const float *colors24, float *xyz, float *rgb);
 void orc_free(void *p);
 
+/* ---- registration (src/Registration/ICP.cpp) ------------------------------------------------------------
+ * Point clouds are 3 floats per point.  Per-point arithmetic (transform, inlier test, Jacobian rows, nearest
+ * neighbour distances) is float32 in the reference's operation order; the 6x6 / Kabsch sums are accumulated in
+ * double and solved in double (the reference accumulates sequentially in float32 -- its own deviation from its
+ * -DUSING_FLOAT64 build is the noise floor), so poses are pinned to oracle/_ref within a
+ * tolerance, index sets exactly. */
+/* exact nearest neighbour (nanoflann L2_Simple distance, ties -> lowest index) of every query; brute force */
+void orc_nearest(const float *query, long nq, const float *target, long nt, int32_t *nn);
+/* registration::PointToPlane (tgt_nrm != NULL) / PointToPoint (NULL).  T in/out column-major.  out_T = the
+ * Kabsch fit the reference returns as result.T; out_T_iter = the iterated transform.  pairs: 2 ints per inlier.
+ * Returns the inlier count, or -1 for the reference's "default result" error path. */
+long orc_icp(const float *src, long ns, const float *tgt, const float *tgt_nrm, long nt, const float *init_T_cm,
+             int max_iteration, double threshold, double scaling, double *out_T_cm, double *out_T_iter_cm,
+             int32_t *pairs, double *rmse);
+/* geometry::Se3ToSE3 (Sophus SE3 exp), double, column-major out */
+void orc_se3_exp(const double *x6, double *T_cm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,10 @@ def lib():
     L.orc_marching_cube_cell.restype = c_i
     L.orc_marching_cube_cell.argtypes = [c_p] * 5
     L.orc_free.argtypes = [c_p]
+    L.orc_nearest.argtypes = [c_p, c_l, c_p, c_l, c_p]
+    L.orc_icp.restype = c_l
+    L.orc_icp.argtypes = [c_p, c_l, c_p, c_p, c_l, c_p, c_i, c_d, c_d, c_p, c_p, c_p, c_p]
+    L.orc_se3_exp.argtypes = [c_p, c_p]
     _LIB = L
     return L
 
@@ -162,3 +166,36 @@ def marching_cube_cell(corners, sdf, colors):
     rgb = np.zeros((15, 3), np.float32)
     n = lib().orc_marching_cube_cell(_ptr(corners), _ptr(sdf), _ptr(colors), _ptr(xyz), _ptr(rgb))
     return xyz[:n], rgb[:n]
+
+
+def nearest(query, target):
+    q = np.ascontiguousarray(query, np.float32)
+    t = np.ascontiguousarray(target, np.float32)
+    nn = np.zeros(len(q), np.int32)
+    lib().orc_nearest(_ptr(q), len(q), _ptr(t), len(t), _ptr(nn))
+    return nn
+
+
+def icp(src, tgt, tgt_normals, init_T, max_iter=30, threshold=0.2, scaling=1.0):
+    """CPU restatement of registration::PointToPlane / PointToPoint -> dict(T, T_iterated, pairs, rmse) or None for
+    the reference's error path."""
+    src = np.ascontiguousarray(src, np.float32)
+    tgt = np.ascontiguousarray(tgt, np.float32)
+    nrm = np.ascontiguousarray(tgt_normals, np.float32) if tgt_normals is not None else None
+    T0 = _pose_cm(init_T)
+    T = np.zeros(16)
+    Ti = np.zeros(16)
+    pairs = np.zeros((max(len(src), 1), 2), np.int32)
+    rmse = c_d(0)
+    n = lib().orc_icp(_ptr(src), len(src), _ptr(tgt), _ptr(nrm), len(tgt), _ptr(T0), max_iter, threshold, scaling, _ptr(T),
+                      _ptr(Ti), _ptr(pairs), C.byref(rmse))
+    if n < 0:
+        return None
+    return dict(T=T.reshape(4, 4).T.copy(), T_iterated=Ti.reshape(4, 4).T.copy(), pairs=pairs[:n].copy(), rmse=rmse.value)
+
+
+def se3_exp(x):
+    x = np.ascontiguousarray(x, np.float64)
+    T = np.zeros(16)
+    lib().orc_se3_exp(_ptr(x), _ptr(T))
+    return T.reshape(4, 4).T.copy()

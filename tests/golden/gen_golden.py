@@ -59,5 +59,31 @@ def main():
     integrate_fixture("integrate_small_trunc", cam, 0.04, 0.3, [(0, I), (1, T2)])
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--icp" not in sys.argv:
     main()
+
+
+def icp_fixture():
+    """S2 frame pair at 160x120: inputs + the float64 reference's result (truth) + the float32 reference's result
+    (its own deviation from float64 is the noise floor pose parity is gated on)."""
+    cam = small_camera()
+    d0, _, _, n0 = scenes.room(cam, 0, with_normals=True)
+    d1, _, _, _ = scenes.room(cam, 3, with_normals=True)
+    tgt = scenes.backproject(d0, cam)
+    src = scenes.backproject(d1, cam)
+    nrm = np.ascontiguousarray(n0.reshape(-1, 3)[(d0 > 0).reshape(-1)])
+    out = dict(src=src, tgt=tgt, nrm=nrm, max_iter=np.int32(10), threshold=np.float64(0.05))
+    for mode, normals in (("plane", nrm), ("point", None)):
+        r64 = refapi.icp(src, tgt, normals, np.eye(4), 10, 0.05, "f64")
+        r32 = refapi.icp(src, tgt, normals, np.eye(4), 10, 0.05, "f32")
+        out[f"{mode}_T64"] = r64["T"]
+        out[f"{mode}_T32"] = r32["T"]
+        out[f"{mode}_rmse64"] = np.float64(r64["rmse"])
+        out[f"{mode}_pairs64"] = r64["pairs"]
+        out[f"{mode}_pairs32_equal"] = np.bool_(np.array_equal(r64["pairs"], r32["pairs"]))
+    np.savez_compressed(os.path.join(OUT, "icp_small.npz"), **out)
+    print("icp_small", os.path.getsize(os.path.join(OUT, "icp_small.npz")))
+
+
+if __name__ == "__main__" and "--icp" in sys.argv:
+    icp_fixture()

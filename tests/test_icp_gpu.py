@@ -1,0 +1,117 @@
+"""Parity of the CUDA ICP (through the C-ABI) with the oracle and the golden float64 reference outputs."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from onepiece_b200 import registration as reg
+from onepiece_b200 import scenes
+from oracle import oracleapi
+
+pytestmark = pytest.mark.gpu
+
+
+def pose_delta(A, B):
+    A = np.asarray(A, np.float64)
+    B = np.asarray(B, np.float64)
+    R = A[:3, :3].T @ B[:3, :3]
+    ang = np.linalg.norm([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]]) / 2
+    return float(np.linalg.norm(A[:3, 3] - B[:3, 3])), float(ang)
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(GOLDEN, "icp_small.npz"))
+
+
+@pytest.mark.parametrize("mode", ["plane", "point"])
+def test_golden_float64_reference(g, mode):
+    src, tgt = reg.PointCloud(g["src"]), reg.PointCloud(g["tgt"], g["nrm"] if mode == "plane" else None)
+    par = reg.ICPParameter(int(g["max_iter"]), float(g["threshold"]), 1.0)
+    r = (reg.PointToPlane if mode == "plane" else reg.PointToPoint)(src, tgt, np.eye(4), par)
+    dt, dr = pose_delta(r.T, g[f"{mode}_T64"])
+    ft, fr = pose_delta(g[f"{mode}_T32"], g[f"{mode}_T64"])
+    # north_star tolerance 1e-5 m / 1e-4 rad; result.T is float32, so allow its quantisation (1e-7 at ~1 m)
+    assert dt < 1e-5 and dr < 1e-4, (dt, dr, "float32 reference's own deviation:", ft, fr)
+    assert np.array_equal(r.correspondence_set_index, g[f"{mode}_pairs64"])
+    assert abs(r.rmse - float(g[f"{mode}_rmse64"])) < 1e-7
+    assert r.correspondence_set[0].shape == (len(r.correspondence_set_index), 3)
+
+
+def test_nearest_neighbour_is_exact(g):
+    """max_iteration = 0: one search under init_T.  Every pair within the threshold must be the exact nearest
+    neighbour the oracle's brute force finds (the GPU reports 'none' beyond the threshold by design)."""
+    T0 = np.eye(4, dtype=np.float32)
+    T0[:3, 3] = [0.01, -0.02, 0.015]
+    thr = 0.03
+    src = g["src"]
+    reg.PointToPoint(reg.PointCloud(src), reg.PointCloud(g["tgt"]), T0, reg.ICPParameter(0, thr, 1.0))
+    nn = reg.last_nn(len(src))
+    moved = (src @ T0[:3, :3].T + T0[:3, 3]).astype(np.float32)
+    ref = oracleapi.nearest(moved, g["tgt"])
+    dist = np.linalg.norm(moved - g["tgt"][ref], axis=1)
+    found = nn >= 0
+    assert np.array_equal(nn[found], ref[found])
+    assert np.all(dist[~found] > thr * 0.999) and np.all(dist[found] <= thr * 1.002)
+    assert found.sum() > 0.5 * len(src)
+
+
+@pytest.mark.parametrize("mode", ["plane", "point"])
+def test_vs_oracle_with_initial_guess_and_clutter(g, mode):
+    rng = np.random.default_rng(3)
+    src = g["src"].copy()
+    src[::50] += rng.normal(0, 0.5, src[::50].shape).astype(np.float32)  # gross outliers
+    src[7] = np.nan  # a non-finite point never matches
+    T0 = scenes.se3_exp([0.004, -0.003, 0.002, 0.002, -0.001, 0.003]).astype(np.float32)
+    nrm = g["nrm"] if mode == "plane" else None
+    par = reg.ICPParameter(8, 0.04, 1.0)
+    r = (reg.PointToPlane if mode == "plane" else reg.PointToPoint)(reg.PointCloud(src), reg.PointCloud(g["tgt"], nrm), T0, par)
+    o = oracleapi.icp(src, g["tgt"], nrm, T0, 8, 0.04)
+    dt, dr = pose_delta(r.T, o["T"])
+    assert dt < 1e-5 and dr < 1e-4, (dt, dr)
+    dti, dri = pose_delta(r.T_iterated, o["T_iterated"])
+    assert dti < 1e-5 and dri < 1e-4
+    a, b = r.correspondence_set_index, o["pairs"]
+    # pairs may differ only where a float32-level difference of the iterated pose flips a near-tie
+    common = len(set(map(tuple, a)) & set(map(tuple, b)))
+    assert common >= 0.999 * max(len(a), len(b))
+    assert abs(r.rmse - o["rmse"]) < 1e-6
+
+
+def test_reference_error_paths():
+    rng = np.random.default_rng(4)
+    t = rng.normal(0, 1, (2000, 3)).astype(np.float32)
+    s = (t + 0.01).astype(np.float32)
+    n = np.tile(np.array([0, 0, 1], np.float32), (2000, 1))
+    # target without normals / scaling != 1: the reference prints an error and returns a default result
+    r = reg.PointToPlane(reg.PointCloud(s), reg.PointCloud(t), np.eye(4), reg.ICPParameter(3, 0.5, 1.0))
+    assert not r.ok and len(r.correspondence_set_index) == 0
+    r = reg.PointToPlane(reg.PointCloud(s), reg.PointCloud(t, n), np.eye(4), reg.ICPParameter(3, 0.5, 2.0))
+    assert not r.ok
+    # PointToPoint with scaling solves the same problem in scaled units
+    a = reg.PointToPoint(reg.PointCloud(s), reg.PointCloud(t), np.eye(4), reg.ICPParameter(3, 0.5, 1.0))
+    b = reg.PointToPoint(reg.PointCloud(s), reg.PointCloud(t), np.eye(4), reg.ICPParameter(3, 1.0, 2.0))
+    o = oracleapi.icp(s, t, None, np.eye(4), 3, 1.0, scaling=2.0)
+    assert pose_delta(a.T, b.T)[0] < 1e-5 and pose_delta(b.T, o["T"])[0] < 1e-5
+    # clouds farther apart than the threshold: no inliers, result.T is NaN like the reference's 0/0
+    far = reg.PointToPoint(reg.PointCloud(s + 100), reg.PointCloud(t), np.eye(4), reg.ICPParameter(2, 0.05, 1.0))
+    assert len(far.correspondence_set_index) == 0 and np.all(np.isnan(far.T))
+
+
+def test_full_size_frame_pair_recovers_the_motion():
+    """640x480 (307,200 points), the bench's ICP workload: deterministic, and the recovered motion agrees with the
+    analytic camera motion to sensor quantisation."""
+    cam = scenes.Camera()
+    d0, _, T0, n0 = scenes.room(cam, 0, with_normals=True)
+    d1, _, T1 = scenes.room(cam, 1)
+    tgt, src = scenes.backproject(d0, cam), scenes.backproject(d1, cam)
+    nrm = n0.reshape(-1, 3)
+    par = reg.ICPParameter(30, 0.05, 1.0)
+    r1 = reg.PointToPlane(reg.PointCloud(src), reg.PointCloud(tgt, nrm), np.eye(4), par)
+    r2 = reg.PointToPlane(reg.PointCloud(src), reg.PointCloud(tgt, nrm), np.eye(4), par)
+    assert np.array_equal(r1.T, r2.T) and np.array_equal(r1.correspondence_set_index, r2.correspondence_set_index)
+    truth = np.linalg.inv(T0.astype(np.float64)) @ T1.astype(np.float64)
+    dt, dr = pose_delta(r1.T_iterated, truth)
+    assert dt < 2e-3 and dr < 2e-3
+    assert len(r1.correspondence_set_index) > 0.99 * len(src)
