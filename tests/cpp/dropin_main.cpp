@@ -1,0 +1,99 @@
+// Reads like example/ImageSequenceIntegration.cpp:20-53 and example/ICPTest.cpp:14-34 of the reference, minus
+// file IO and the viewer: the reference's caller code compiled UNCHANGED against the drop-in classes of
+// onepiece_b200/cpp.  Inputs come from raw binary files written by tests/test_dropin_cpp.py; results are written
+// back as raw binary for comparison with the oracle.
+#include <fstream>
+#include <iostream>
+#include <vector>
+
+#include "Geometry/PointCloud.h"
+#include "Geometry/TriangleMesh.h"
+#include "Integration/CubeHandler.h"
+#include "Registration/ICP.h"
+
+using namespace one_piece;
+
+template <typename T> std::vector<T> ReadAll(const std::string &path)
+{
+    std::ifstream f(path, std::ios::binary);
+    f.seekg(0, f.end);
+    size_t n = f.tellg();
+    f.seekg(0, f.beg);
+    std::vector<T> v(n / sizeof(T));
+    f.read((char *)v.data(), n);
+    return v;
+}
+template <typename T> void WriteAll(const std::string &path, const std::vector<T> &v)
+{
+    std::ofstream f(path, std::ios::binary);
+    f.write((const char *)v.data(), v.size() * sizeof(T));
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 3) { std::cout << "usage: dropin_main <dir> <n_frames>" << std::endl; return 2; }
+    const std::string dir = argv[1];
+    const int n_frames = atoi(argv[2]);
+    const int W = 160, H = 120;
+    camera::PinholeCamera camera(514.817f / 4, 515.375f / 4, 318.771f / 4, 238.447f / 4, W, H, 1000.0f);
+
+    // --- example/ImageSequenceIntegration.cpp:20-53 ---------------------------------------------------------
+    integration::CubeHandler cube_handler(camera);
+    cube_handler.SetVoxelResolution(0.02);
+    std::vector<float> poses = ReadAll<float>(dir + "/poses.bin"); // row-major 4x4 per frame, like trajectory.txt
+    for (int i = 0; i < n_frames; ++i)
+    {
+        std::vector<float> d = ReadAll<float>(dir + "/depth" + std::to_string(i) + ".bin");
+        std::vector<unsigned char> c = ReadAll<unsigned char>(dir + "/bgr" + std::to_string(i) + ".bin");
+        cv::Mat depth(H, W, CV_32FC1, d.data()), rgb(H, W, CV_8UC3, c.data());
+        geometry::TransformationMatrix pose;
+        for (int r = 0; r < 4; ++r)
+            for (int col = 0; col < 4; ++col) pose(r, col) = poses[16 * i + 4 * r + col];
+        cube_handler.IntegrateImage(depth, rgb, pose);
+    }
+    geometry::TriangleMesh mesh;
+    cube_handler.ExtractTriangleMesh(mesh);
+    std::vector<float> mesh_out;
+    for (size_t i = 0; i < mesh.points.size(); ++i)
+        for (int k = 0; k < 3; ++k) mesh_out.push_back(mesh.points[i](k));
+    WriteAll(dir + "/mesh_points.bin", mesh_out);
+    integration::CubeMap m = cube_handler.GetCubeMap();
+    std::vector<float> vox;
+    std::vector<int> ids;
+    for (auto it = m.begin(); it != m.end(); ++it)
+    {
+        for (int k = 0; k < 3; ++k) ids.push_back(it->first(k));
+        for (int j = 0; j < 512; ++j)
+        {
+            vox.push_back(it->second.voxels[j].sdf);
+            vox.push_back(it->second.voxels[j].weight);
+            for (int k = 0; k < 3; ++k) vox.push_back(it->second.voxels[j].color(k));
+        }
+    }
+    WriteAll(dir + "/ids.bin", ids);
+    WriteAll(dir + "/voxels.bin", vox);
+    cube_handler.WriteToFile(dir + "/volume.cubes");
+
+    // --- example/ICPTest.cpp:14-34 ---------------------------------------------------------------------------
+    geometry::PointCloud s_pcd, t_pcd;
+    std::vector<float> s = ReadAll<float>(dir + "/src.bin"), t = ReadAll<float>(dir + "/tgt.bin"), n = ReadAll<float>(dir + "/nrm.bin");
+    for (size_t i = 0; i < s.size() / 3; ++i) s_pcd.points.push_back(geometry::Point3(s[3 * i], s[3 * i + 1], s[3 * i + 2]));
+    for (size_t i = 0; i < t.size() / 3; ++i)
+    {
+        t_pcd.points.push_back(geometry::Point3(t[3 * i], t[3 * i + 1], t[3 * i + 2]));
+        t_pcd.normals.push_back(geometry::Point3(n[3 * i], n[3 * i + 1], n[3 * i + 2]));
+    }
+    registration::ICPParameter icp_para;
+    icp_para.threshold = 0.05;
+    icp_para.max_iteration = 10;
+    auto result = registration::PointToPlane(s_pcd, t_pcd, geometry::TransformationMatrix::Identity(), icp_para);
+    std::vector<double> icp_out;
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) icp_out.push_back(result->T(r, c));
+    icp_out.push_back(result->rmse);
+    icp_out.push_back((double)result->correspondence_set_index.size());
+    WriteAll(dir + "/icp.bin", icp_out);
+    std::cout << "dropin ok: " << m.size() << " cubes, " << mesh.triangles.size() << " triangles, "
+              << result->correspondence_set_index.size() << " ICP inliers" << std::endl;
+    return 0;
+}

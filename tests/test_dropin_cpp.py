@@ -1,0 +1,68 @@
+"""The reference's caller code (example/ImageSequenceIntegration.cpp / example/ICPTest.cpp style) compiled
+unchanged against the drop-in C++ classes in onepiece_b200/cpp, run on the GPU and compared with the oracle.
+The binary is built in the build container (tests/cpp/Makefile needs the reference's headers) and travels to the
+GPU box with the snapshot."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_bit_equal
+from onepiece_b200 import scenes
+from oracle import oracleapi
+
+BIN = os.path.join(ROOT, "tests", "cpp", "dropin_main.bin")
+
+
+def test_dropin_sources_cite_and_mirror_the_reference_api():
+    hdr = open(os.path.join(ROOT, "onepiece_b200", "cpp", "Integration", "CubeHandler.h")).read()
+    for name in ("SetVoxelResolution", "SetTruncation", "SetCamera", "SetFarPlane", "SetNearPlane", "IntegrateImage",
+                 "ExtractTriangleMesh", "GetCubeMap", "SetCubeMap", "HasCube", "Clear", "GetPointCloud", "WriteToFile",
+                 "ReadFromFile", "PrepareCubes", "ComputeBounding"):
+        assert name in hdr, name
+    assert "namespace integration" in hdr and "class CubeHandler" in hdr
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(BIN), reason="tests/cpp/dropin_main.bin not built (needs the reference headers)")
+def test_reference_caller_code_runs_on_the_gpu(tmp_path):
+    c0 = scenes.Camera()
+    cam = scenes.Camera(c0.fx / 4, c0.fy / 4, c0.cx / 4, c0.cy / 4, 160, 120, 1000.0)
+    ov = oracleapi.OracleVolume(cam, 0.02)
+    poses = []
+    n_frames = 3
+    for k in range(n_frames):
+        d, c = scenes.wavy_wall(cam, k)
+        T = scenes.se3_exp(np.array([0.02, -0.01, 0.01, 0.01, -0.02, 0.005]) * k).astype(np.float32)
+        d.tofile(tmp_path / f"depth{k}.bin")
+        c.tofile(tmp_path / f"bgr{k}.bin")
+        poses.append(T)
+        ov.integrate(d, c, T)
+    np.stack(poses).astype(np.float32).tofile(tmp_path / "poses.bin")
+    d0, _, _, n0 = scenes.room(cam, 0, with_normals=True)
+    d1, _, _ = scenes.room(cam, 3)
+    tgt, src = scenes.backproject(d0, cam), scenes.backproject(d1, cam)
+    nrm = np.ascontiguousarray(n0.reshape(-1, 3))
+    src.tofile(tmp_path / "src.bin"); tgt.tofile(tmp_path / "tgt.bin"); nrm.tofile(tmp_path / "nrm.bin")
+    out = subprocess.run([BIN, str(tmp_path), str(n_frames)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "dropin ok" in out.stdout
+    # the reference prints one line per IntegrateImage call; the drop-in keeps that behaviour
+    assert out.stdout.count("Finish image integration") == n_frames
+    ids = np.fromfile(tmp_path / "ids.bin", np.int32).reshape(-1, 3)
+    vox = np.fromfile(tmp_path / "voxels.bin", np.float32).reshape(-1, 512, 5)
+    order = np.lexsort((ids[:, 2], ids[:, 1], ids[:, 0]))
+    oi, ovx = ov.download()
+    assert np.array_equal(ids[order], oi)
+    assert_bit_equal(vox[order], ovx, "voxels through the C++ drop-in")
+    mesh = np.fromfile(tmp_path / "mesh_points.bin", np.float32).reshape(-1, 3)
+    op, _ = ov.extract_mesh()
+    assert len(mesh) == len(op)
+    icp = np.fromfile(tmp_path / "icp.bin", np.float64)
+    o = oracleapi.icp(src, tgt, nrm, np.eye(4), 10, 0.05)
+    assert np.linalg.norm(icp[:16].reshape(4, 4)[:3, 3] - o["T"][:3, 3]) < 1e-5
+    assert int(icp[17]) == len(o["pairs"])
+    # the .cubes file the drop-in wrote has the reference's layout: [u32 n_cubes] then per cube 3 id floats ... -2
+    raw = np.fromfile(tmp_path / "volume.cubes", np.float32)
+    assert raw[:1].view(np.uint32)[0] == len(oi) and (raw == -2.0).sum() >= len(oi)
