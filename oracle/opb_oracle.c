@@ -774,3 +774,435 @@ long orc_icp(const float *src_in, long ns, const float *tgt_in, const float *nrm
     free(src); free(tgt); free(tp); free(nn);
     return n_in;
 }
+
+/* ------------------------------------------------------------------------------------------------------- */
+/* dense RGB-D odometry                                                                                    */
+/* ------------------------------------------------------------------------------------------------------- */
+#define MAX_DIFF_DEPTH 0.05 /* OdometryPredefined.h:4-19 */
+#define SOBEL_SCALE 0.125
+#define LAMBDA_HYBRID_DEPTH 0.5
+#define ODO_MAX_DEPTH 4
+#define ODO_MIN_DEPTH 0.5
+#define MAX_INLIER_RATIO_DENSE 0.9
+#define MIN_INLIER_RATIO_DENSE 0.3
+#define ODO_LEVELS 3
+
+static int refl101(int i, int n)
+{
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+    return i;
+}
+/* cv::cvtColor(CV_RGB2GRAY) on 8-bit data (ImageProcessing.cpp:21-24), OpenCV 4.x fixed point: the FIRST stored
+ * byte takes the red coefficient (the reference hands it BGR data from imread) */
+void orc_gray_u8(const uint8_t *bgr, int n, uint8_t *gray)
+{
+    for (int i = 0; i < n; ++i)
+        gray[i] = (uint8_t)((9798 * bgr[3 * i] + 19235 * bgr[3 * i + 1] + 3735 * bgr[3 * i + 2] + 16384) >> 15);
+}
+/* cv::GaussianBlur(3x3, sigma 0) (ImageProcessing.cpp:43-46): separable [1/4 1/2 1/4], BORDER_REFLECT_101, rows first */
+void orc_blur3(const float *src, int w, int h, float *dst)
+{
+    float *tmp = (float *)malloc(sizeof(float) * w * h);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+            tmp[y * w + x] = 0.5f * src[y * w + x] + 0.25f * (src[y * w + refl101(x - 1, w)] + src[y * w + refl101(x + 1, w)]);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+            dst[y * w + x] = 0.5f * tmp[y * w + x] + 0.25f * (tmp[refl101(y - 1, h) * w + x] + tmp[refl101(y + 1, h) * w + x]);
+    free(tmp);
+}
+/* cv::pyrDown (ImageProcessing.cpp:16): separable [1 4 6 4 1], BORDER_REFLECT_101, every second sample, /256 */
+void orc_pyr_down(const float *src, int w, int h, float *dst)
+{
+    const int ow = w / 2, oh = h / 2;
+    float *tmp = (float *)malloc(sizeof(float) * ow * h);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < ow; ++x)
+        {
+            const float *r = src + y * w;
+            const int c = 2 * x;
+            tmp[y * ow + x] = r[refl101(c, w)] * 6.0f + (r[refl101(c - 1, w)] + r[refl101(c + 1, w)]) * 4.0f + r[refl101(c - 2, w)] +
+                              r[refl101(c + 2, w)];
+        }
+    for (int y = 0; y < oh; ++y)
+        for (int x = 0; x < ow; ++x)
+        {
+            const int c = 2 * y;
+            dst[y * ow + x] = (tmp[refl101(c, h) * ow + x] * 6.0f + (tmp[refl101(c - 1, h) * ow + x] + tmp[refl101(c + 1, h) * ow + x]) * 4.0f +
+                               tmp[refl101(c - 2, h) * ow + x] + tmp[refl101(c + 2, h) * ow + x]) * (1.0f / 256.0f);
+        }
+    free(tmp);
+}
+/* cv::Sobel(CV_32F, ksize 3) (ImageProcessing.cpp:25-33): derivative [-1 0 1] along one axis, [1 2 1] along the other */
+void orc_sobel3(const float *src, int w, int h, int dx, float *dst)
+{
+    float *tmp = (float *)malloc(sizeof(float) * w * h);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+        {
+            const float l = src[y * w + refl101(x - 1, w)], r = src[y * w + refl101(x + 1, w)];
+            tmp[y * w + x] = dx ? r - l : l + 2.0f * src[y * w + x] + r;
+        }
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+        {
+            const float u = tmp[refl101(y - 1, h) * w + x], d = tmp[refl101(y + 1, h) * w + x];
+            dst[y * w + x] = dx ? u + 2.0f * tmp[y * w + x] + d : d - u;
+        }
+    free(tmp);
+}
+
+struct orc_frame
+{
+    int w, h, is_u16, preprocessed;
+    uint8_t *bgr;
+    void *depth;
+    float *img[6][ODO_LEVELS]; /* gray, depth, gray dx, gray dy, depth dx, depth dy */
+};
+orc_frame *orc_frame_create(const uint8_t *bgr, const void *depth, int is_u16, int w, int h)
+{
+    orc_frame *f = (orc_frame *)calloc(1, sizeof(orc_frame));
+    f->w = w; f->h = h; f->is_u16 = is_u16;
+    f->bgr = (uint8_t *)malloc((size_t)w * h * 3);
+    memcpy(f->bgr, bgr, (size_t)w * h * 3);
+    f->depth = malloc((size_t)w * h * (is_u16 ? 2 : 4));
+    memcpy(f->depth, depth, (size_t)w * h * (is_u16 ? 2 : 4));
+    return f;
+}
+void orc_frame_destroy(orc_frame *f)
+{
+    if (!f) return;
+    for (int a = 0; a < 6; ++a)
+        for (int l = 0; l < ODO_LEVELS; ++l) free(f->img[a][l]);
+    free(f->bgr); free(f->depth); free(f);
+}
+long orc_frame_image(const orc_frame *f, int what, int level, float *out)
+{
+    const long n = (long)(f->w >> level) * (f->h >> level);
+    if (out && f->img[what][level]) memcpy(out, f->img[what][level], sizeof(float) * n);
+    return n;
+}
+/* Odometry::InitializeRGBDDenseTracking (Odometry.cpp:609-620): gray/255 and NaN-masked metric depth, both blurred */
+static void odo_initialize(const uint8_t *bgr, const void *depth, int is_u16, int w, int h, float depth_scale, float *gray, float *d32)
+{
+    const int n = w * h;
+    uint8_t *g8 = (uint8_t *)malloc(n);
+    float *tmp = (float *)malloc(sizeof(float) * n);
+    orc_gray_u8(bgr, n, g8);
+    for (int i = 0; i < n; ++i) tmp[i] = g8[i] / 255.0f; /* ConvertColorToIntensity32F, DenseOdometryFunction.cpp:59-71 */
+    orc_blur3(tmp, w, h, gray);
+    /* ConvertDepthTo32FNaN, DenseOdometryFunction.cpp:26-57 */
+    for (int i = 0; i < n; ++i)
+    {
+        if (is_u16)
+        {
+            const unsigned short v = ((const unsigned short *)depth)[i];
+            tmp[i] = (v > ODO_MIN_DEPTH * depth_scale && v < ODO_MAX_DEPTH * depth_scale) ? v / depth_scale : NAN;
+        }
+        else
+        {
+            const float v = ((const float *)depth)[i];
+            tmp[i] = (v > ODO_MIN_DEPTH && v < ODO_MAX_DEPTH) ? v : NAN;
+        }
+    }
+    orc_blur3(tmp, w, h, d32);
+    free(g8); free(tmp);
+}
+/* Odometry::CreateImagePyramid (Odometry.cpp:436-449) for the levels above 0 plus the Sobel images of all levels */
+static void odo_pyramids(orc_frame *f)
+{
+    for (int l = 1; l < ODO_LEVELS; ++l)
+        for (int a = 0; a < 2; ++a)
+        {
+            free(f->img[a][l]);
+            f->img[a][l] = (float *)malloc(sizeof(float) * (f->w >> l) * (f->h >> l));
+            orc_pyr_down(f->img[a][l - 1], f->w >> (l - 1), f->h >> (l - 1), f->img[a][l]);
+        }
+    for (int l = 0; l < ODO_LEVELS; ++l)
+        for (int a = 0; a < 2; ++a)
+            for (int dx = 1; dx >= 0; --dx)
+            {
+                const int slot = 2 + 2 * a + (1 - dx); /* gray dx, gray dy, depth dx, depth dy */
+                free(f->img[slot][l]);
+                f->img[slot][l] = (float *)malloc(sizeof(float) * (f->w >> l) * (f->h >> l));
+                orc_sobel3(f->img[a][l], f->w >> l, f->h >> l, dx, f->img[slot][l]);
+            }
+}
+static void mat3_mul(const float *A, const float *B, float *C) /* row-major; Eigen lazy product: a0b0 + (a1b1 + a2b2) */
+{
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) C[i * 3 + j] = A[i * 3] * B[j] + (A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j]);
+}
+/* ComputeCorrespondencePixelWise + AddElementToCorrespondenceMap (DenseOdometryFunction.cpp:8-25,72-128).
+ * T column-major float.  pairs: (v_s,u_s,v_t,u_t) in raster order of the source; returns the count. */
+static long odo_correspondences(const float *sd, const float *td, int w, int h, float fx, float fy, float cx, float cy, const float *T,
+                                uint32_t *pairs, long cap)
+{
+    /* K, K^-1 (closed form of Eigen's 3x3 inverse for an upper-triangular camera matrix is NOT assumed: the generic
+     * cofactor formula is evaluated like Eigen's compute_inverse_size3), K R K^-1 and K t */
+    const float K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
+    const float R[9] = {T[0], T[4], T[8], T[1], T[5], T[9], T[2], T[6], T[10]}, t[3] = {T[12], T[13], T[14]};
+    float cof[9], Kinv[9], KR[9], M[9], Kt[3];
+    /* cofactor_3x3<i,j> = m(i1,j1)*m(i2,j2) - m(i1,j2)*m(i2,j1) with (i1,i2) = ((i+1)%3,(i+2)%3); inverse(i,j) = cof(j,i)*invdet */
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+        {
+            const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+            cof[i * 3 + j] = K[i1 * 3 + j1] * K[i2 * 3 + j2] - K[i1 * 3 + j2] * K[i2 * 3 + j1];
+        }
+    /* determinant from the first column of cofactors: (cof(0,0), cof(1,0), cof(2,0)) . matrix.col(0) */
+    const float det = (cof[0] * K[0] + cof[3] * K[3]) + cof[6] * K[6];
+    const float invdet = 1.0f / det;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Kinv[i * 3 + j] = cof[j * 3 + i] * invdet;
+    mat3_mul(K, R, KR);
+    mat3_mul(KR, Kinv, M);
+    for (int i = 0; i < 3; ++i) Kt[i] = K[i * 3] * t[0] + (K[i * 3 + 1] * t[1] + K[i * 3 + 2] * t[2]);
+
+    float *wd = (float *)malloc(sizeof(float) * w * h);
+    int *wm = (int *)malloc(sizeof(int) * w * h);
+    for (int i = 0; i < w * h; ++i) { wd[i] = -1; wm[i] = -1; }
+    for (int i = 0; i < h; ++i)
+        for (int j = 0; j < w; ++j)
+        {
+            const float d_s = sd[i * w + j];
+            if (isnan(d_s)) continue;
+            float uv[3];
+            for (int r = 0; r < 3; ++r)
+                uv[r] = ((d_s * M[r * 3]) * (float)j + ((d_s * M[r * 3 + 1]) * (float)i + (d_s * M[r * 3 + 2]) * 1.0f)) + Kt[r];
+            const float tds = uv[2];
+            const int u_t = cvtt_d(uv[0] / tds + 0.5), v_t = cvtt_d(uv[1] / tds + 0.5);
+            if (u_t >= 0 && u_t < w && v_t >= 0 && v_t < h)
+            {
+                const float d_t = td[v_t * w + u_t];
+                if (!isnan(d_t) && fabsf(d_t - tds) < MAX_DIFF_DEPTH)
+                {
+                    const float existing = wd[v_t * w + u_t];
+                    if (existing == -1 || existing > tds) { wm[i * w + j] = v_t * w + u_t; wd[i * w + j] = tds; }
+                }
+            }
+        }
+    long n = 0;
+    for (int i = 0; i < h; ++i)
+        for (int j = 0; j < w; ++j)
+            if (wd[i * w + j] != -1)
+            {
+                if (pairs && n < cap)
+                {
+                    pairs[4 * n] = i; pairs[4 * n + 1] = j;
+                    pairs[4 * n + 2] = wm[i * w + j] / w; pairs[4 * n + 3] = wm[i * w + j] % w;
+                }
+                ++n;
+            }
+    free(wd); free(wm);
+    return n;
+}
+long orc_correspondences(const float *sd, const float *td, int w, int h, float fx, float fy, float cx, float cy, const float *T,
+                         uint32_t *pairs, long cap)
+{
+    return odo_correspondences(sd, td, w, h, fx, fy, cx, cy, T, pairs, cap);
+}
+/* NormalizeIntensity (DenseOdometryFunction.cpp:129-144) + tool::LinearTransform (ImageProcessing.cpp:56-63) */
+static void odo_normalize(float *sg, float *tg, int w, int h, const uint32_t *pairs, long n)
+{
+    float mean_s = 0, mean_t = 0;
+    for (long k = 0; k < n; ++k)
+    {
+        mean_s += sg[pairs[4 * k] * w + pairs[4 * k + 1]];
+        mean_t += tg[pairs[4 * k + 2] * w + pairs[4 * k + 3]];
+    }
+    mean_s /= (float)n;
+    mean_t /= (float)n;
+    const float ss = (float)(0.5 / mean_s), st = (float)(0.5 / mean_t);
+    for (int i = 0; i < w * h; ++i) sg[i] = sg[i] * ss + 0.0f;
+    for (int i = 0; i < w * h; ++i) tg[i] = tg[i] * st + 0.0f;
+}
+/* DoSingleIteration{,PhotoTerm,DepthTerm} (DenseOdometryFunction.cpp:146-475): Jacobian rows in float exactly as the
+ * reference writes them; J^T J, J^T r summed in double (the reference sums sequentially in float32) */
+static long odo_iteration(orc_frame *S, orc_frame *Tg, int l, float fx, float fy, float cx, float cy, float *T, int term,
+                          uint32_t *pairs, long cap, double *sums_out /* 36 JTJ, 6 JTr, sum r^2; may be NULL */)
+{
+    const int w = S->w >> l, h = S->h >> l;
+    const long n = odo_correspondences(S->img[1][l], Tg->img[1][l], w, h, fx, fy, cx, cy, T, pairs, cap);
+    double JTJ[36] = {0}, nJTr[6] = {0}, r2 = 0;
+    const float sq_dep = (float)sqrt(LAMBDA_HYBRID_DEPTH), sq_img = (float)sqrt(1.0 - LAMBDA_HYBRID_DEPTH);
+    for (long k = 0; k < n; ++k)
+    {
+        const int v_s = pairs[4 * k], u_s = pairs[4 * k + 1], v_t = pairs[4 * k + 2], u_t = pairs[4 * k + 3];
+        /* source_XYZ[v_s][u_s] (TransformToMatXYZ, Geometry.cpp:72-106) */
+        const float z = S->img[1][l][v_s * w + u_s];
+        float p[3] = {-1, -1, -1};
+        if (z > 0) { p[0] = (u_s - cx) * z / fx; p[1] = (v_s - cy) * z / fy; p[2] = z; }
+        float q[3];
+        for (int r = 0; r < 3; ++r) q[r] = (T[r] * p[0] + (T[4 + r] * p[1] + T[8 + r] * p[2])) + T[12 + r];
+        const float invz = (float)(1. / q[2]);
+        float J[2][6], res[2];
+        int rows = 0;
+        if (term == 0 || term == 1)
+        {
+            const float diff = Tg->img[0][l][v_t * w + u_t] - S->img[0][l][v_s * w + u_s];
+            const float gx = (float)(SOBEL_SCALE * Tg->img[2][l][v_t * w + u_t]), gy = (float)(SOBEL_SCALE * Tg->img[3][l][v_t * w + u_t]);
+            const float c0 = gx * fx * invz, c1 = gy * fy * invz, c2 = -(c0 * q[0] + c1 * q[1]) * invz;
+            const float s = term == 0 ? sq_img : 1.0f;
+            float *j = J[rows];
+            j[0] = c0; j[1] = c1; j[2] = c2;
+            j[3] = -q[2] * c1 + q[1] * c2; j[4] = q[2] * c0 - q[0] * c2; j[5] = -q[1] * c0 + q[0] * c1;
+            if (term == 0) for (int a = 0; a < 6; ++a) j[a] = s * j[a];
+            res[rows] = term == 0 ? s * diff : diff;
+            ++rows;
+        }
+        if (term == 0 || term == 2)
+        {
+            float gx = (float)(SOBEL_SCALE * Tg->img[4][l][v_t * w + u_t]), gy = (float)(SOBEL_SCALE * Tg->img[5][l][v_t * w + u_t]);
+            if (isnan(gx)) gx = 0;
+            if (isnan(gy)) gy = 0;
+            const float diff = Tg->img[1][l][v_t * w + u_t] - q[2];
+            const float d0 = gx * fx * invz, d1 = gy * fy * invz, d2 = -(d0 * q[0] + d1 * q[1]) * invz;
+            float *j = J[rows];
+            j[0] = d0; j[1] = d1; j[2] = d2 - 1.0f;
+            j[3] = (-q[2] * d1 + q[1] * d2) - q[1]; j[4] = (q[2] * d0 - q[0] * d2) + q[0]; j[5] = -q[1] * d0 + q[0] * d1;
+            if (term == 0) for (int a = 0; a < 6; ++a) j[a] = sq_dep * j[a];
+            res[rows] = term == 0 ? sq_dep * diff : diff;
+            ++rows;
+        }
+        for (int r = 0; r < rows; ++r)
+            for (int a = 0; a < 6; ++a)
+            {
+                for (int b = 0; b < 6; ++b) JTJ[a * 6 + b] += (double)(J[r][a] * J[r][b]);
+                nJTr[a] -= (double)(J[r][a] * res[r]);
+            }
+        for (int r = 0; r < rows; ++r) r2 += (double)(res[r] * res[r]);
+    }
+    if (sums_out)
+    {
+        memcpy(sums_out, JTJ, sizeof(JTJ));
+        for (int a = 0; a < 6; ++a) sums_out[36 + a] = -nJTr[a];
+        sums_out[42] = r2;
+    }
+    /* delta = JTJ.ldlt().solve(-JTr); T = Se3ToSE3(delta) * T */
+    double x[6], dT[16];
+    solve_pinv6(JTJ, nJTr, x);
+    for (int a = 0; a < 6; ++a) x[a] = (float)x[a];
+    se3_exp_rm(x, dT);
+    float dTf[16], Tn[16];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) dTf[c * 4 + r] = (float)dT[r * 4 + c];
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 4; ++r)
+            Tn[c * 4 + r] = ((dTf[r] * T[c * 4] + dTf[4 + r] * T[c * 4 + 1]) + dTf[8 + r] * T[c * 4 + 2]) + dTf[12 + r] * T[c * 4 + 3];
+    memcpy(T, Tn, sizeof(Tn));
+    return n;
+}
+/* Odometry::MultiScaleComputing (Odometry.cpp:621-685) + the result assembly of DenseTracking (:596-607) */
+static void odo_multiscale(orc_frame *S, orc_frame *Tg, float fx, float fy, float cx, float cy, const float *init_T, int term,
+                           orc_tracking_result *out, uint32_t *pixel_pairs, long cap)
+{
+    static const int iters[ODO_LEVELS] = {4, 8, 16}; /* Odometry.h:170, indexed by level */
+    const int w = S->w, h = S->h;
+    float T[16];
+    memcpy(T, init_T, sizeof(T));
+    uint32_t *pairs = (uint32_t *)malloc(sizeof(uint32_t) * 4 * (size_t)w * h);
+    float cam[ODO_LEVELS][4] = {{fx, fy, cx, cy}};
+    for (int l = 1; l < ODO_LEVELS; ++l)
+        for (int a = 0; a < 4; ++a) cam[l][a] = cam[l - 1][a] / 2; /* GenerateNextPyramid, Camera.h:38-42 */
+    long n = 0;
+    out->iterations = 0;
+    for (int l = ODO_LEVELS - 1; l >= 0; --l)
+        for (int j = 0; j != iters[l]; ++j)
+        {
+            n = odo_iteration(S, Tg, l, cam[l][0], cam[l][1], cam[l][2], cam[l][3], T, term, pairs, (long)w * h, NULL);
+            if (out->iterations < 64)
+            {
+                out->corr_per_iteration[out->iterations] = n;
+                for (int e = 0; e < 16; ++e) out->T_per_iteration[out->iterations][e] = T[e];
+            }
+            out->iterations++;
+            if ((float)n / (h * w) > MAX_INLIER_RATIO_DENSE) break;
+        }
+    /* correspondence_set pairs xyz_s[v_s][u_s] with xyz_t[v_s][u_s] -- the SAME source pixel on the target's XYZ image
+     * (reference quirk, Odometry.cpp:672-682); rmse = ComputeReprojectionError3D (Geometry.cpp:45-59) */
+    double sum = 0;
+    const int wl = w >> (n ? 0 : 0);
+    for (long k = 0; k < n; ++k)
+    {
+        const int v_s = pairs[4 * k], u_s = pairs[4 * k + 1];
+        float a[3] = {-1, -1, -1}, b[3] = {-1, -1, -1};
+        const float zs = S->img[1][0][v_s * wl + u_s], zt = Tg->img[1][0][v_s * wl + u_s];
+        if (zs > 0) { a[0] = (u_s - cx) * zs / fx; a[1] = (v_s - cy) * zs / fy; a[2] = zs; }
+        if (zt > 0) { b[0] = (u_s - cx) * zt / fx; b[1] = (v_s - cy) * zt / fy; b[2] = zt; }
+        /* TransformPoint: T*(x,y,z,1) then /w, minus second, squaredNorm, accumulated in double */
+        const float wv = row_xyz1(T, 3, a[0], a[1], a[2]);
+        float e[3];
+        for (int r = 0; r < 3; ++r) e[r] = row_xyz1(T, r, a[0], a[1], a[2]) / wv - b[r];
+        sum += (double)(e[0] * e[0] + (e[1] * e[1] + e[2] * e[2]));
+    }
+    out->rmse = sqrt(sum / n);
+    out->n_correspondences = n;
+    out->tracking_success = (float)n / (h * w) >= MIN_INLIER_RATIO_DENSE;
+    for (int e = 0; e < 16; ++e) out->T[e] = T[e];
+    if (pixel_pairs) memcpy(pixel_pairs, pairs, sizeof(uint32_t) * 4 * (size_t)(n < cap ? n : cap));
+    free(pairs);
+}
+static void odo_preprocess(orc_frame *f, float depth_scale)
+{
+    const int n = f->w * f->h;
+    for (int a = 0; a < 2; ++a) { free(f->img[a][0]); f->img[a][0] = (float *)malloc(sizeof(float) * n); }
+    odo_initialize(f->bgr, f->depth, f->is_u16, f->w, f->h, depth_scale, f->img[0][0], f->img[1][0]);
+    odo_pyramids(f);
+    f->preprocessed = 1;
+}
+void orc_dense_tracking_frames(orc_frame *S, orc_frame *Tg, float fx, float fy, float cx, float cy, float depth_scale,
+                               const float *init_T, int term, orc_tracking_result *out, uint32_t *pixel_pairs, long cap)
+{
+    /* Odometry.cpp:571-587: pre-process once per frame (IsPreprocessedDense) */
+    if (!S->preprocessed) odo_preprocess(S, depth_scale);
+    if (!Tg->preprocessed) odo_preprocess(Tg, depth_scale);
+    /* :588-595: correspondences at identity on the level-0 depth, then NormalizeIntensity on frame.gray IN PLACE -- which
+     * is also pyramid level 0 (CreatePyramid pushes the same cv::Mat header), but not levels 1-2 nor any Sobel image */
+    const int w = S->w, h = S->h;
+    const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    uint32_t *pairs = (uint32_t *)malloc(sizeof(uint32_t) * 4 * (size_t)w * h);
+    const long n = odo_correspondences(S->img[1][0], Tg->img[1][0], w, h, fx, fy, cx, cy, I, pairs, (long)w * h);
+    odo_normalize(S->img[0][0], Tg->img[0][0], w, h, pairs, n);
+    free(pairs);
+    odo_multiscale(S, Tg, fx, fy, cx, cy, init_T, term, out, pixel_pairs, cap);
+}
+void orc_dense_tracking(const uint8_t *sb, const uint8_t *tb, const void *sdp, const void *tdp, int is_u16, int w, int h, float fx,
+                        float fy, float cx, float cy, float depth_scale, const float *init_T, int term, orc_tracking_result *out,
+                        uint32_t *pixel_pairs, long cap)
+{
+    /* Odometry.cpp:463-523: initialise both, normalise the full-resolution gray images, THEN build the pyramids */
+    orc_frame *S = orc_frame_create(sb, sdp, is_u16, w, h), *Tg = orc_frame_create(tb, tdp, is_u16, w, h);
+    const int n_px = w * h;
+    for (int a = 0; a < 2; ++a)
+    {
+        S->img[a][0] = (float *)malloc(sizeof(float) * n_px);
+        Tg->img[a][0] = (float *)malloc(sizeof(float) * n_px);
+    }
+    odo_initialize(sb, sdp, is_u16, w, h, depth_scale, S->img[0][0], S->img[1][0]);
+    odo_initialize(tb, tdp, is_u16, w, h, depth_scale, Tg->img[0][0], Tg->img[1][0]);
+    const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    uint32_t *pairs = (uint32_t *)malloc(sizeof(uint32_t) * 4 * (size_t)n_px);
+    const long n = odo_correspondences(S->img[1][0], Tg->img[1][0], w, h, fx, fy, cx, cy, I, pairs, n_px);
+    odo_normalize(S->img[0][0], Tg->img[0][0], w, h, pairs, n);
+    free(pairs);
+    odo_pyramids(S);
+    odo_pyramids(Tg);
+    odo_multiscale(S, Tg, fx, fy, cx, cy, init_T, term, out, pixel_pairs, cap);
+    orc_frame_destroy(S);
+    orc_frame_destroy(Tg);
+}
+
+/* one teacher-forced iteration at `level` (frames must be pre-processed): T_cm in/out, sums = 36 JTJ + 6 JTr + sum r^2 */
+long orc_single_iteration(orc_frame *S, orc_frame *Tg, int level, float fx, float fy, float cx, float cy, float *T_cm, int term,
+                          double *sums43, uint32_t *pairs, long cap)
+{
+    for (int l = 0; l < level; ++l) { fx /= 2; fy /= 2; cx /= 2; cy /= 2; }
+    return odo_iteration(S, Tg, level, fx, fy, cx, cy, T_cm, term, pairs, cap, sums43);
+}
+/* pre-process without tracking (Odometry.cpp:571-587) */
+void orc_frame_preprocess(orc_frame *f, float depth_scale)
+{
+    if (!f->preprocessed) odo_preprocess(f, depth_scale);
+}

@@ -64,6 +64,50 @@ long orc_icp(const float *src, long ns, const float *tgt, const float *tgt_nrm, 
 /* geometry::Se3ToSE3 (Sophus SE3 exp), double, column-major out */
 void orc_se3_exp(const double *x6, double *T_cm);
 
+/* ---- dense RGB-D odometry (src/Odometry/Odometry.cpp:436-685, DenseOdometryFunction.cpp) -----------------
+ * The five OpenCV filters the path calls (cvtColor RGB2GRAY, GaussianBlur 3x3, pyrDown, Sobel 3x3; OpenCV is an
+ * un-vendored dependency, README pins 3.4) are DEFINED here by explicit formulas (opb_oracle.c) and cross-checked
+ * against cv2 4.13 in tests/test_odometry_filters.py: parity at that boundary is unpinned by the reference. */
+void orc_gray_u8(const uint8_t *bgr, int n_pixels, uint8_t *gray);         /* cvtColor(CV_RGB2GRAY) on the stored bytes */
+void orc_blur3(const float *src, int w, int h, float *dst);                /* GaussianBlur(3x3, sigma 0), REFLECT_101 */
+void orc_pyr_down(const float *src, int w, int h, float *dst);             /* pyrDown to (w/2, h/2) */
+void orc_sobel3(const float *src, int w, int h, int dx, float *dst);       /* Sobel(CV_32F, dx, 1-dx, ksize 3) */
+
+typedef struct orc_frame orc_frame; /* geometry::RGBDFrame's dense cache: gray, depth32f, 6 pyramids */
+orc_frame *orc_frame_create(const uint8_t *bgr, const void *depth, int is_u16, int w, int h);
+void orc_frame_destroy(orc_frame *f);
+/* what: 0 gray pyramid, 1 depth pyramid, 2 gray dx, 3 gray dy, 4 depth dx, 5 depth dy; returns w*h of the level */
+long orc_frame_image(const orc_frame *f, int what, int level, float *out);
+
+typedef struct
+{
+    double T[16];            /* column-major */
+    double rmse;
+    int tracking_success;
+    long n_correspondences;
+    int iterations;
+    long corr_per_iteration[64];
+    double T_per_iteration[64][16];
+} orc_tracking_result;
+
+/* Odometry::DenseTracking(RGBDFrame &source, RGBDFrame &target, initial_T, term_type) (Odometry.cpp:526-608): frames are
+ * pre-processed on first use and their level-0 gray is re-normalised IN PLACE on every call, like the reference.
+ * pixel_pairs (optional): 4 uint32 per correspondence (v_s, u_s, v_t, u_t), raster order of the source. */
+void orc_dense_tracking_frames(orc_frame *source, orc_frame *target, float fx, float fy, float cx, float cy, float depth_scale,
+                               const float *init_T_cm, int term_type, orc_tracking_result *out, uint32_t *pixel_pairs, long cap);
+/* Odometry::DenseTracking(cv::Mat overload) (Odometry.cpp:463-523): normalises before building the pyramids */
+void orc_dense_tracking(const uint8_t *src_bgr, const uint8_t *tgt_bgr, const void *src_depth, const void *tgt_depth, int is_u16,
+                        int w, int h, float fx, float fy, float cx, float cy, float depth_scale, const float *init_T_cm,
+                        int term_type, orc_tracking_result *out, uint32_t *pixel_pairs, long cap);
+/* ComputeCorrespondencePixelWise (DenseOdometryFunction.cpp:72-128) on two NaN-masked depth maps; returns the count */
+long orc_correspondences(const float *src_depth, const float *tgt_depth, int w, int h, float fx, float fy, float cx, float cy,
+                         const float *T_cm, uint32_t *pixel_pairs, long cap);
+
+/* teacher-forced single iteration at a pyramid level (intrinsics of level 0); sums43 = 36 JTJ, 6 JTr, sum r^2 */
+long orc_single_iteration(orc_frame *source, orc_frame *target, int level, float fx, float fy, float cx, float cy, float *T_cm,
+                          int term_type, double *sums43, uint32_t *pixel_pairs, long cap);
+void orc_frame_preprocess(orc_frame *f, float depth_scale);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,22 @@ def lib():
     L.orc_icp.restype = c_l
     L.orc_icp.argtypes = [c_p, c_l, c_p, c_p, c_l, c_p, c_i, c_d, c_d, c_p, c_p, c_p, c_p]
     L.orc_se3_exp.argtypes = [c_p, c_p]
+    L.orc_gray_u8.argtypes = [c_p, c_i, c_p]
+    L.orc_blur3.argtypes = [c_p, c_i, c_i, c_p]
+    L.orc_pyr_down.argtypes = [c_p, c_i, c_i, c_p]
+    L.orc_sobel3.argtypes = [c_p, c_i, c_i, c_i, c_p]
+    L.orc_frame_create.restype = c_p
+    L.orc_frame_create.argtypes = [c_p, c_p, c_i, c_i, c_i]
+    L.orc_frame_destroy.argtypes = [c_p]
+    L.orc_frame_image.restype = c_l
+    L.orc_frame_image.argtypes = [c_p, c_i, c_i, c_p]
+    L.orc_dense_tracking_frames.argtypes = [c_p, c_p] + [c_f] * 5 + [c_p, c_i, c_p, c_p, c_l]
+    L.orc_dense_tracking.argtypes = [c_p, c_p, c_p, c_p, c_i, c_i, c_i] + [c_f] * 5 + [c_p, c_i, c_p, c_p, c_l]
+    L.orc_correspondences.restype = c_l
+    L.orc_correspondences.argtypes = [c_p, c_p, c_i, c_i] + [c_f] * 4 + [c_p, c_p, c_l]
+    L.orc_single_iteration.restype = c_l
+    L.orc_single_iteration.argtypes = [c_p, c_p, c_i] + [c_f] * 4 + [c_p, c_i, c_p, c_p, c_l]
+    L.orc_frame_preprocess.argtypes = [c_p, c_f]
     _LIB = L
     return L
 
@@ -199,3 +215,113 @@ def se3_exp(x):
     T = np.zeros(16)
     lib().orc_se3_exp(_ptr(x), _ptr(T))
     return T.reshape(4, 4).T.copy()
+
+
+class TrackingResult(C.Structure):
+    _fields_ = [("T", c_d * 16), ("rmse", c_d), ("tracking_success", c_i), ("n_correspondences", c_l), ("iterations", c_i),
+                ("corr_per_iteration", c_l * 64), ("T_per_iteration", (c_d * 16) * 64)]
+
+
+def _tracking_dict(r, pairs):
+    k = min(r.iterations, 64)
+    return dict(T=np.array(r.T[:]).reshape(4, 4).T.copy(), rmse=r.rmse, success=bool(r.tracking_success),
+                pairs=pairs[: r.n_correspondences].copy(), corr_per_iteration=np.array(r.corr_per_iteration[:k]),
+                T_per_iteration=np.stack([np.array(r.T_per_iteration[i][:]).reshape(4, 4).T for i in range(k)]) if k else None)
+
+
+def gray_u8(bgr):
+    b = np.ascontiguousarray(bgr, np.uint8)
+    out = np.zeros(b.shape[:2], np.uint8)
+    lib().orc_gray_u8(_ptr(b), out.size, _ptr(out))
+    return out
+
+
+def blur3(img):
+    a = np.ascontiguousarray(img, np.float32)
+    out = np.zeros_like(a)
+    lib().orc_blur3(_ptr(a), a.shape[1], a.shape[0], _ptr(out))
+    return out
+
+
+def pyr_down(img):
+    a = np.ascontiguousarray(img, np.float32)
+    out = np.zeros((a.shape[0] // 2, a.shape[1] // 2), np.float32)
+    lib().orc_pyr_down(_ptr(a), a.shape[1], a.shape[0], _ptr(out))
+    return out
+
+
+def sobel3(img, dx):
+    a = np.ascontiguousarray(img, np.float32)
+    out = np.zeros_like(a)
+    lib().orc_sobel3(_ptr(a), a.shape[1], a.shape[0], int(dx), _ptr(out))
+    return out
+
+
+class OracleFrame:
+    """CPU restatement of geometry::RGBDFrame's dense-tracking cache (RGBDFrame.h:33-44)."""
+
+    def __init__(self, bgr, depth):
+        self.L = lib()
+        b = np.ascontiguousarray(bgr, np.uint8)
+        d = np.ascontiguousarray(depth)
+        self.h_, self.w_ = d.shape
+        self.h = self.L.orc_frame_create(_ptr(b), _ptr(d), int(d.dtype == np.uint16), self.w_, self.h_)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_frame_destroy(self.h)
+            self.h = None
+
+    def image(self, what, level):
+        out = np.zeros((self.h_ >> level, self.w_ >> level), np.float32)
+        self.L.orc_frame_image(self.h, what, level, _ptr(out))
+        return out
+
+    def images(self):
+        return [[self.image(a, l) for l in range(3)] for a in range(6)]
+
+    def preprocess(self, depth_scale=1000.0):
+        self.L.orc_frame_preprocess(self.h, depth_scale)
+        return self
+
+
+def dense_tracking_frames(source: OracleFrame, target: OracleFrame, cam, init_T=np.eye(4), term_type=0):
+    r = TrackingResult()
+    pairs = np.zeros((source.w_ * source.h_, 4), np.uint32)
+    T0 = _pose_cm(init_T)
+    lib().orc_dense_tracking_frames(source.h, target.h, cam.fx, cam.fy, cam.cx, cam.cy, cam.depth_scale, _ptr(T0), term_type,
+                                    C.byref(r), _ptr(pairs), len(pairs))
+    return _tracking_dict(r, pairs)
+
+
+def dense_tracking(src_bgr, tgt_bgr, src_depth, tgt_depth, cam, init_T=np.eye(4), term_type=0):
+    r = TrackingResult()
+    sb, tb = np.ascontiguousarray(src_bgr, np.uint8), np.ascontiguousarray(tgt_bgr, np.uint8)
+    sd, td = np.ascontiguousarray(src_depth), np.ascontiguousarray(tgt_depth)
+    h, w = sd.shape
+    pairs = np.zeros((w * h, 4), np.uint32)
+    T0 = _pose_cm(init_T)
+    lib().orc_dense_tracking(_ptr(sb), _ptr(tb), _ptr(sd), _ptr(td), int(sd.dtype == np.uint16), w, h, cam.fx, cam.fy, cam.cx, cam.cy,
+                             cam.depth_scale, _ptr(T0), term_type, C.byref(r), _ptr(pairs), len(pairs))
+    return _tracking_dict(r, pairs)
+
+
+def correspondences(src_depth, tgt_depth, cam, T):
+    sd = np.ascontiguousarray(src_depth, np.float32)
+    td = np.ascontiguousarray(tgt_depth, np.float32)
+    h, w = sd.shape
+    Tcm = _pose_cm(T)
+    pairs = np.zeros((w * h, 4), np.uint32)
+    n = lib().orc_correspondences(_ptr(sd), _ptr(td), w, h, cam.fx, cam.fy, cam.cx, cam.cy, _ptr(Tcm), _ptr(pairs), w * h)
+    return pairs[:n].copy()
+
+
+def single_iteration(source: OracleFrame, target: OracleFrame, cam, level, T, term_type=0):
+    """One teacher-forced solver iteration at a pyramid level -> dict(T, JTJ, JTr, r2, pairs)"""
+    Tcm = _pose_cm(T)
+    sums = np.zeros(43)
+    pairs = np.zeros(((source.w_ >> level) * (source.h_ >> level), 4), np.uint32)
+    n = lib().orc_single_iteration(source.h, target.h, level, cam.fx, cam.fy, cam.cx, cam.cy, _ptr(Tcm), term_type, _ptr(sums),
+                                   _ptr(pairs), len(pairs))
+    return dict(T=Tcm.reshape(4, 4).T.astype(np.float64), JTJ=sums[:36].reshape(6, 6).copy(), JTr=sums[36:42].copy(), r2=sums[42],
+                pairs=pairs[:n].copy())

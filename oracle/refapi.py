@@ -60,6 +60,13 @@ def lib(kind: str = "f32"):
     L.ref_icp_iteration.argtypes = [c_p, c_p, c_d, c_p, c_p, c_p, c_p, c_p, c_p]
     L.ref_se3_exp.argtypes = [c_p, c_p]
     L.ref_kabsch.argtypes = [c_p, c_p, c_l, c_p]
+    L.ref_correspondences.restype = c_l
+    L.ref_correspondences.argtypes = [c_p, c_p, c_i, c_i] + [c_f] * 4 + [c_p, c_p, c_l]
+    L.ref_normalize_intensity.argtypes = [c_p, c_p, c_i, c_i, c_p, c_l]
+    L.ref_multiscale.restype = c_l
+    L.ref_multiscale.argtypes = [c_p, c_p, c_i, c_i] + [c_f] * 4 + [c_p, c_i, c_p, c_p, c_p, c_p, c_l, c_p, c_p, c_p]
+    L.ref_single_iteration.restype = c_l
+    L.ref_single_iteration.argtypes = [c_p, c_p, c_i, c_i, c_i] + [c_f] * 4 + [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_l]
     if kind == "f32":
         L.ref_load_from_depth.restype = c_l
         L.ref_load_from_depth.argtypes = [c_p, c_i, c_i, c_i] + [c_f] * 5 + [c_p]
@@ -264,3 +271,74 @@ def estimate_normals(xyz, radius=0.1, knn=30):
     out = np.zeros_like(xyz)
     dt = lib("f32").ref_estimate_normals(_ptr(xyz), len(xyz), radius, knn, _ptr(out))
     return out, dt
+
+
+def correspondences(src_depth, tgt_depth, cam, T, kind="f32"):
+    """odometry::ComputeCorrespondencePixelWise on NaN-masked float32 depth maps -> [n,4] (v_s,u_s,v_t,u_t)"""
+    sd = np.ascontiguousarray(src_depth, np.float32)
+    td = np.ascontiguousarray(tgt_depth, np.float32)
+    h, w = sd.shape
+    Tcm = np.ascontiguousarray(np.asarray(T, np.float64).T).reshape(16)
+    pairs = np.zeros((w * h, 4), np.uint32)
+    n = lib(kind).ref_correspondences(_ptr(sd), _ptr(td), w, h, cam.fx, cam.fy, cam.cx, cam.cy, _ptr(Tcm), _ptr(pairs), w * h)
+    return pairs[:n].copy()
+
+
+def normalize_intensity(src_gray, tgt_gray, pairs, kind="f32"):
+    s = np.ascontiguousarray(src_gray, np.float32).copy()
+    t = np.ascontiguousarray(tgt_gray, np.float32).copy()
+    p = np.ascontiguousarray(pairs, np.uint32)
+    lib(kind).ref_normalize_intensity(_ptr(s), _ptr(t), s.shape[1], s.shape[0], _ptr(p), len(p))
+    return s, t
+
+
+def multiscale(src_imgs, tgt_imgs, cam, init_T, term=0, kind="f32"):
+    """Odometry::MultiScaleComputing over caller-supplied pyramids.  *_imgs[what][level] float32 arrays with
+    what = 0 gray, 1 depth, 2 gray dx, 3 gray dy, 4 depth dx, 5 depth dy."""
+    keep = []
+
+    def table(imgs):
+        arr = (c_p * 18)()
+        for a in range(6):
+            for l in range(3):
+                m = np.ascontiguousarray(imgs[a][l], np.float32)
+                keep.append(m)
+                arr[a * 3 + l] = m.ctypes.data
+        return arr
+    h, w = src_imgs[0][0].shape
+    sa, ta = table(src_imgs), table(tgt_imgs)
+    T0 = np.ascontiguousarray(np.asarray(init_T, np.float64).T).reshape(16)
+    Tout = np.zeros(16)
+    rmse = c_d(0)
+    ok = c_i(0)
+    nit = c_i(0)
+    pairs = np.zeros((w * h, 4), np.uint32)
+    cpi = np.zeros(64, np.int64)
+    tpi = np.zeros((64, 16))
+    n = lib(kind).ref_multiscale(sa, ta, w, h, cam.fx, cam.fy, cam.cx, cam.cy, _ptr(T0), term, _ptr(Tout), C.byref(rmse), C.byref(ok),
+                                 _ptr(pairs), w * h, _ptr(cpi), _ptr(tpi), C.byref(nit))
+    k = nit.value
+    return dict(T=_from_cm(Tout), rmse=rmse.value, success=bool(ok.value), pairs=pairs[:n].copy(), corr_per_iteration=cpi[:k].copy(),
+                T_per_iteration=np.stack([_from_cm(t) for t in tpi[:k]]) if k else np.zeros((0, 4, 4)))
+
+
+def single_iteration(src_imgs, tgt_imgs, cam, level, T, term=0, kind="f32"):
+    """One teacher-forced iteration of the reference at a pyramid level -> dict(T, JTJ, JTr, r2, pairs)"""
+    keep = []
+
+    def table(imgs):
+        arr = (c_p * 18)()
+        for a in range(6):
+            for l in range(3):
+                m = np.ascontiguousarray(imgs[a][l], np.float32)
+                keep.append(m)
+                arr[a * 3 + l] = m.ctypes.data
+        return arr
+    h, w = src_imgs[0][0].shape
+    sa, ta = table(src_imgs), table(tgt_imgs)
+    T0 = np.ascontiguousarray(np.asarray(T, np.float64).T).reshape(16)
+    Tout, JTJ, JTr, r2 = np.zeros(16), np.zeros(36), np.zeros(6), c_d(0)
+    pairs = np.zeros(((w >> level) * (h >> level), 4), np.uint32)
+    n = lib(kind).ref_single_iteration(sa, ta, level, w, h, cam.fx, cam.fy, cam.cx, cam.cy, _ptr(T0), term, _ptr(Tout), _ptr(JTJ),
+                                       _ptr(JTr), C.byref(r2), _ptr(pairs), len(pairs))
+    return dict(T=_from_cm(Tout), JTJ=JTJ.reshape(6, 6), JTr=JTr, r2=r2.value, pairs=pairs[:n].copy())
