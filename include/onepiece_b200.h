@@ -200,6 +200,81 @@ int opb_icp_last_nn(opb_icp *c, int32_t *nn, size_t n);
 int opb_icp_set_profiling(opb_icp *c, int on);
 int opb_icp_last_timing(opb_icp *c, float *grid_build_ms, float *iterations_ms);
 
+
+/* ------------------------------------------------------------------------------------------------------
+ * Dense RGB-D odometry  (replaces one_piece::odometry::Odometry::DenseTracking, src/Odometry/Odometry.h:78-84,
+ *                        src/Odometry/Odometry.cpp:436-685, src/Odometry/DenseOdometryFunction.cpp)
+ * ---------------------------------------------------------------------------------------------------- */
+#define OPB_ODO_MAX_LEVELS 6
+#define OPB_ODO_MAX_TRACE 64
+
+typedef struct opb_odometry opb_odometry; /* Odometry object: camera, schedule, device workspace; one host thread at a time */
+typedef struct opb_frame opb_frame;       /* geometry::RGBDFrame's dense-tracking cache on the device (RGBDFrame.h:33-44) */
+
+typedef struct
+{
+    /* camera::PinholeCamera of level 0 (Odometry::SetCamera, Odometry.h:86-89); levels halve it (Camera.h:38-42) */
+    float fx, fy, cx, cy;
+    int32_t width, height; /* both divisible by 2^(levels-1) */
+    float depth_scale;
+    /* Odometry::SetMultiScale (Odometry.h:101-105): multi_scale_level and iter_count_per_level, indexed by LEVEL
+     * (level 0 = full resolution runs last); reference default 3 levels, {4, 8, 16} */
+    int32_t levels;
+    int32_t iterations[OPB_ODO_MAX_LEVELS];
+    int32_t device;
+    void *stream; /* optional cudaStream_t */
+} opb_odometry_desc;
+
+/* odometry::DenseTrackingResult (Odometry.h:29-37) plus a per-iteration trace for parity tests */
+typedef struct
+{
+    float T[16];               /* source -> target, column-major */
+    double rmse;               /* ComputeReprojectionError3D over correspondence_set (Odometry.cpp:606) */
+    int32_t tracking_success;  /* correspondences / (W*H) >= MIN_INLIER_RATIO_DENSE (Odometry.cpp:684) */
+    int32_t status;
+    size_t n_correspondences;  /* pixel_correspondence_set.size() */
+    int32_t iterations;        /* executed solver iterations (a level ends early above MAX_INLIER_RATIO_DENSE) */
+    int32_t corr_per_iteration[OPB_ODO_MAX_TRACE];
+    float T_per_iteration[OPB_ODO_MAX_TRACE][16];
+} opb_tracking_result;
+
+void opb_odometry_desc_default(opb_odometry_desc *desc);
+int opb_odometry_create(const opb_odometry_desc *desc, opb_odometry **out);
+void opb_odometry_destroy(opb_odometry *o);
+int opb_odometry_set_profiling(opb_odometry *o, int on);
+int opb_odometry_last_timing(opb_odometry *o, float *tracking_ms);
+
+/* geometry::RGBDFrame(rgb, depth) (RGBDFrame.h:14-19): uploads the raw images (host or device pointers; returns when
+ * the copies are done).  depth_type other than OPB_DEPTH_F32 / OPB_DEPTH_U16 -> OPB_ERR_UNSUPPORTED (the reference
+ * prints "Unknown depth image type" and exits, DenseOdometryFunction.cpp:51-55). */
+int opb_frame_create(opb_odometry *o, const uint8_t *bgr, const void *depth, int depth_type, opb_frame **out);
+void opb_frame_destroy(opb_frame *f);
+/* InitializeRGBDDenseTracking + CreateImagePyramid (Odometry.cpp:571-587,609-620,436-449); idempotent like
+ * RGBDFrame::IsPreprocessedDense */
+int opb_frame_preprocess(opb_odometry *o, opb_frame *f);
+int opb_frame_is_preprocessed(const opb_frame *f);
+/* download one cached image: what = 0 gray, 1 depth32f, 2 gray dx, 3 gray dy, 4 depth dx, 5 depth dy */
+int opb_frame_image(opb_odometry *o, opb_frame *f, int what, int level, float *out);
+
+/* DenseTracking(RGBDFrame &source, RGBDFrame &target, initial_T, term_type) (Odometry.cpp:526-608).  Both frames are
+ * MUTATED like the reference's: caches are filled on first use and the level-0 gray image is re-normalised in place on
+ * every call.  term_type 0 hybrid / 1 photometric / 2 geometric.  Optional outputs, up to pairs_cap entries each:
+ *   pixel_pairs  4 x uint32 per correspondence (v_s, u_s, v_t, u_t), raster order of the source
+ *   corr_xyz     6 x float  per correspondence: correspondence_set[i].first / .second (Odometry.cpp:672-682) */
+int opb_odometry_dense_tracking_frames(opb_odometry *o, opb_frame *source, opb_frame *target, const float init_T_colmajor[16],
+                                       int term_type, opb_tracking_result *result, uint32_t *pixel_pairs, size_t pairs_cap,
+                                       float *corr_xyz);
+/* DenseTracking(source_color, target_color, source_depth, target_depth, initial_T, term_type) (Odometry.cpp:463-523):
+ * intensities are normalised BEFORE the pyramids are built (unlike the RGBDFrame overload). */
+int opb_odometry_dense_tracking(opb_odometry *o, const uint8_t *src_bgr, const uint8_t *tgt_bgr, const void *src_depth,
+                                const void *tgt_depth, int depth_type, const float init_T_colmajor[16], int term_type,
+                                opb_tracking_result *result, uint32_t *pixel_pairs, size_t pairs_cap, float *corr_xyz);
+/* One DoSingleIteration{,PhotoTerm,DepthTerm} (DenseOdometryFunction.cpp:382-475) at a pyramid level from a given pose
+ * (teacher forcing, for parity tests): T in/out; sums43 = J^T J (36, row-major), J^T r (6), sum r^2; the
+ * correspondence list of that iteration. */
+int opb_odometry_single_iteration(opb_odometry *o, opb_frame *source, opb_frame *target, int level, float T_inout_colmajor[16],
+                                  int term_type, double sums43[43], uint32_t *pixel_pairs, size_t pairs_cap, size_t *n_pairs);
+
 #ifdef __cplusplus
 }
 #endif

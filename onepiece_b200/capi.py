@@ -59,6 +59,22 @@ class IcpResult(C.Structure):
                 ("iterations", C.c_int32), ("status", C.c_int32)]
 
 
+OPB_ODO_MAX_LEVELS = 6
+OPB_ODO_MAX_TRACE = 64
+
+
+class OdometryDesc(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("width", C.c_int32), ("height", C.c_int32),
+                ("depth_scale", C.c_float), ("levels", C.c_int32), ("iterations", C.c_int32 * OPB_ODO_MAX_LEVELS), ("device", C.c_int32),
+                ("stream", C.c_void_p)]
+
+
+class TrackingResult(C.Structure):
+    _fields_ = [("T", C.c_float * 16), ("rmse", C.c_double), ("tracking_success", C.c_int32), ("status", C.c_int32),
+                ("n_correspondences", C.c_size_t), ("iterations", C.c_int32), ("corr_per_iteration", C.c_int32 * OPB_ODO_MAX_TRACE),
+                ("T_per_iteration", (C.c_float * 16) * OPB_ODO_MAX_TRACE)]
+
+
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} is missing: build it with `python -m onepiece_b200.build` (onepiece_b200 has no CPU path)")
@@ -103,6 +119,19 @@ SIGNATURES = {
     "opb_icp_last_nn": (C.c_int, [_p, _p, _sz]),
     "opb_icp_set_profiling": (C.c_int, [_p, C.c_int]),
     "opb_icp_last_timing": (C.c_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "opb_odometry_desc_default": (None, [C.POINTER(OdometryDesc)]),
+    "opb_odometry_create": (C.c_int, [C.POINTER(OdometryDesc), C.POINTER(_p)]),
+    "opb_odometry_destroy": (None, [_p]),
+    "opb_odometry_set_profiling": (C.c_int, [_p, C.c_int]),
+    "opb_odometry_last_timing": (C.c_int, [_p, C.POINTER(C.c_float)]),
+    "opb_frame_create": (C.c_int, [_p, _p, _p, C.c_int, C.POINTER(_p)]),
+    "opb_frame_destroy": (None, [_p]),
+    "opb_frame_preprocess": (C.c_int, [_p, _p]),
+    "opb_frame_is_preprocessed": (C.c_int, [_p]),
+    "opb_frame_image": (C.c_int, [_p, _p, C.c_int, C.c_int, _p]),
+    "opb_odometry_dense_tracking_frames": (C.c_int, [_p, _p, _p, _p, C.c_int, C.POINTER(TrackingResult), _p, _sz, _p]),
+    "opb_odometry_dense_tracking": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, _p, C.c_int, C.POINTER(TrackingResult), _p, _sz, _p]),
+    "opb_odometry_single_iteration": (C.c_int, [_p, _p, _p, C.c_int, _p, C.c_int, _p, _p, _sz, C.POINTER(_sz)]),
 }
 
 

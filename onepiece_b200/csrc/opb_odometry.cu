@@ -1,0 +1,1086 @@
+// K4-K6: dense RGB-D odometry (photometric + geometric, coarse to fine) on the device.
+//
+// Reference path rebuilt here (file:line relative to the reference tree):
+//   Odometry::DenseTracking (both overloads)        src/Odometry/Odometry.cpp:463-523, 526-608
+//   Odometry::InitializeRGBDDenseTracking           src/Odometry/Odometry.cpp:609-620
+//   Odometry::CreateImagePyramid / XYZ pyramid      src/Odometry/Odometry.cpp:436-461, src/Geometry/Geometry.cpp:72-106
+//   Odometry::MultiScaleComputing                   src/Odometry/Odometry.cpp:621-685
+//   ConvertDepthTo32FNaN / ConvertColorToIntensity32F   src/Odometry/DenseOdometryFunction.cpp:26-71
+//   ComputeCorrespondencePixelWise                  src/Odometry/DenseOdometryFunction.cpp:8-25,72-128
+//   NormalizeIntensity                              src/Odometry/DenseOdometryFunction.cpp:129-144
+//   ComputeJacobian{Hybrid,Photo,Depth}Term, ComputeJTJandJTr*, DoSingleIteration*   :146-475
+//   tool::CreatePyramid / SobelFiltering / GaussianFiltering / Convert2Gray / LinearTransform
+//                                                   src/Tool/ImageProcessing.cpp:6-63 (OpenCV calls; OpenCV is not
+//                                                   vendored by the reference: the filter arithmetic is the one
+//                                                   DESIGN.md section 2 defines and the tests check against cv2)
+//
+// Design.  A frame's dense cache (geometry::RGBDFrame: gray, depth32f, 6 three-level pyramids) lives in one device
+// allocation (3.2 MB at 640x480, L2-resident); the XYZ image is never materialised, back-projection is three flops.
+// One solver iteration is two launches:
+//   odo_candidates_kernel  thread = source pixel: warp it with d * K R K^-1 (u,v,1) + K t, test the target depth
+//                          -> candidate {target pixel, transformed depth}
+//   odo_iteration_kernel   thread = source pixel: resolves the reference's order-dependent occlusion filter exactly
+//                          (the accept decision of pixel s is NOT(accept(t(s))) along a chain of strictly decreasing
+//                          raster indices; the chain is walked to its first unconditional node), evaluates the two
+//                          Jacobian rows in float exactly as the reference writes them, accumulates the 29 scalars
+//                          (21 J^T J + 6 J^T r + sum r^2 + count) in double: registers -> warp shuffles -> per-CTA
+//                          partial in a fixed slot; the last CTA to finish sums the partials in a fixed order
+//                          (deterministic), solves the 6x6 system, applies the SE(3) exponential and updates the pose.
+// The host never sees a pose until the coarse-to-fine schedule is over; the reference's data-dependent early exit
+// of a level (correspondence ratio > 0.9) is a device flag later launches of that level test.
+#include <cfloat>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/onepiece_b200.h"
+#include "opb_common.cuh"
+#include "opb_linalg.h"
+
+namespace opb
+{
+constexpr int kOdoThreads = 256;
+constexpr int kOdoPacket = 32; // doubles per partial (29 used)
+constexpr int kMaxLevels = OPB_ODO_MAX_LEVELS;
+constexpr int kMaxTrace = OPB_ODO_MAX_TRACE;
+
+struct OdoCam
+{
+    float fx, fy, cx, cy;
+    int w, h;
+};
+
+struct OdoState // device-resident solver state
+{
+    float T[16]; // source -> target, column-major float
+    double packet[kOdoPacket];
+    unsigned int blocks_done;
+    int iteration;        // executed iterations
+    int break_level;      // level whose remaining iterations are skipped (-1: none)
+    int last_count;       // correspondences of the last executed iteration
+    int n_pairs;          // result of the last ordered compaction
+    float mean_src, mean_tgt; // NormalizeIntensity
+    double rmse_sum;
+    int trace_count[kMaxTrace];
+    float trace_T[kMaxTrace][16];
+};
+
+struct FrameImages // pointers into one frame's allocation; what: 0 gray, 1 depth, 2 gray dx, 3 gray dy, 4 depth dx, 5 depth dy
+{
+    float *img[6][kMaxLevels];
+};
+
+__device__ __forceinline__ int reflect101(int i, int n)
+{
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+    return i;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K4: per-frame pre-processing
+// ---------------------------------------------------------------------------------------------------------
+// ConvertColorToIntensity32F (cvtColor RGB2GRAY on the stored bytes, 15-bit fixed point, then / 255) and
+// ConvertDepthTo32FNaN (metres, NaN outside (0.5, 4))
+__global__ void odo_convert_kernel(const uint8_t *__restrict__ bgr, const void *__restrict__ depth, int is_u16, float depth_scale,
+                                   int n, float *__restrict__ gray, float *__restrict__ d32)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int g8 = (9798 * (int)bgr[3 * i] + 19235 * (int)bgr[3 * i + 1] + 3735 * (int)bgr[3 * i + 2] + 16384) >> 15;
+    gray[i] = fdiv((float)g8, 255.0f);
+    float out = __int_as_float(0x7fc00000);
+    if (is_u16)
+    {
+        const unsigned short v = ((const unsigned short *)depth)[i];
+        // `v > MIN_DEPTH * depth_scale`: the literal is double
+        if ((double)v > 0.5 * (double)depth_scale && (double)v < 4.0 * (double)depth_scale) out = fdiv((float)v, depth_scale);
+    }
+    else
+    {
+        const float v = ((const float *)depth)[i];
+        if (v > 0.5f && v < 4.0f) out = v;
+    }
+    d32[i] = out;
+}
+
+// GaussianBlur 3x3 sigma 0: separable [1/4 1/2 1/4], rows first, BORDER_REFLECT_101; blockIdx.z picks the image
+__global__ void odo_blur3_kernel(const float *__restrict__ src0, const float *__restrict__ src1, int w, int h, float *__restrict__ dst0,
+                                 float *__restrict__ dst1)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const float *src = blockIdx.z ? src1 : src0;
+    float *dst = blockIdx.z ? dst1 : dst0;
+    const int xl = reflect101(x - 1, w), xr = reflect101(x + 1, w);
+    float t[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+        const float *r = src + (size_t)reflect101(y - 1 + k, h) * w;
+        t[k] = fadd(fmul(0.5f, r[x]), fmul(0.25f, fadd(r[xl], r[xr])));
+    }
+    dst[(size_t)y * w + x] = fadd(fmul(0.5f, t[1]), fmul(0.25f, fadd(t[0], t[2])));
+}
+
+// pyrDown to (w/2, h/2): separable [1 4 6 4 1], every second sample, / 256 after the column pass
+__global__ void odo_pyrdown_kernel(const float *__restrict__ src0, const float *__restrict__ src1, int w, int h, float *__restrict__ dst0,
+                                   float *__restrict__ dst1)
+{
+    const int ow = w / 2, oh = h / 2;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= ow || y >= oh) return;
+    const float *src = blockIdx.z ? src1 : src0;
+    float *dst = blockIdx.z ? dst1 : dst0;
+    int xs[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) xs[k] = reflect101(2 * x - 2 + k, w);
+    float t[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+    {
+        const float *r = src + (size_t)reflect101(2 * y - 2 + k, h) * w;
+        t[k] = fadd(fadd(fadd(fmul(r[xs[2]], 6.0f), fmul(fadd(r[xs[1]], r[xs[3]]), 4.0f)), r[xs[0]]), r[xs[4]]);
+    }
+    dst[(size_t)y * ow + x] = fmul(fadd(fadd(fadd(fmul(t[2], 6.0f), fmul(fadd(t[1], t[3]), 4.0f)), t[0]), t[4]), 1.0f / 256.0f);
+}
+
+// Sobel 3x3 (CV_32F): blockIdx.z = 4 * level + 2 * image + (0: dx, 1: dy) over all levels of both pyramids
+__global__ void odo_sobel_kernel(FrameImages f, int w0, int h0, int levels)
+{
+    const int level = blockIdx.z >> 2, a = (blockIdx.z >> 1) & 1, dy = blockIdx.z & 1;
+    if (level >= levels) return;
+    const int w = w0 >> level, h = h0 >> level;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const float *src = f.img[a][level];
+    float *dst = f.img[2 + 2 * a + dy][level];
+    const int xl = reflect101(x - 1, w), xr = reflect101(x + 1, w);
+    float t[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+        const float *r = src + (size_t)reflect101(y - 1 + k, h) * w;
+        t[k] = dy ? fadd(fadd(r[xl], fmul(2.0f, r[x])), r[xr]) : fsub(r[xr], r[xl]);
+    }
+    dst[(size_t)y * w + x] = dy ? fsub(t[2], t[0]) : fadd(fadd(t[0], fmul(2.0f, t[1])), t[2]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5: correspondences
+// ---------------------------------------------------------------------------------------------------------
+// K R K^-1 and K t in float, Eigen's evaluation order: 3x3 inverse by cofactors (compute_inverse_size3), lazy 3x3
+// products coefficient by coefficient as a0*b0 + (a1*b1 + a2*b2)
+__device__ void warp_matrices(const OdoCam &cam, const float *T, float *M, float *Kt)
+{
+    const float K[9] = {cam.fx, 0, cam.cx, 0, cam.fy, cam.cy, 0, 0, 1};
+    const float R[9] = {T[0], T[4], T[8], T[1], T[5], T[9], T[2], T[6], T[10]};
+    float cof[9], Kinv[9], KR[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+        {
+            const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+            cof[i * 3 + j] = fsub(fmul(K[i1 * 3 + j1], K[i2 * 3 + j2]), fmul(K[i1 * 3 + j2], K[i2 * 3 + j1]));
+        }
+    const float det = fadd(fadd(fmul(cof[0], K[0]), fmul(cof[3], K[3])), fmul(cof[6], K[6]));
+    const float invdet = fdiv(1.0f, det);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Kinv[i * 3 + j] = fmul(cof[j * 3 + i], invdet);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) KR[i * 3 + j] = dot3(K[i * 3], K[i * 3 + 1], K[i * 3 + 2], R[j], R[3 + j], R[6 + j]);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) M[i * 3 + j] = dot3(KR[i * 3], KR[i * 3 + 1], KR[i * 3 + 2], Kinv[j], Kinv[3 + j], Kinv[6 + j]);
+    for (int i = 0; i < 3; ++i) Kt[i] = dot3(K[i * 3], K[i * 3 + 1], K[i * 3 + 2], T[12], T[13], T[14]);
+}
+
+struct OdoArgs
+{
+    FrameImages src, tgt;
+    OdoCam cam;      // of this level
+    int level;
+    int term;        // 0 hybrid, 1 photo, 2 depth
+    int full_pixels; // width * height of level 0 (the early-exit ratio always uses the full resolution, Odometry.cpp:668)
+    int2 *cand;      // per source pixel {target pixel index or -1, transformed depth bits}
+    unsigned char *accepted;
+    double *partials;
+    OdoState *st;
+    const float *T_override; // identity for the NormalizeIntensity correspondences, else nullptr (= st->T)
+};
+
+__global__ void __launch_bounds__(kOdoThreads) odo_candidates_kernel(OdoArgs a)
+{
+    if (a.st->break_level == a.level && !a.T_override) return;
+    __shared__ float sM[12];
+    if (threadIdx.x == 0) warp_matrices(a.cam, a.T_override ? a.T_override : a.st->T, sM, sM + 9);
+    __syncthreads();
+    const int w = a.cam.w, h = a.cam.h, n = w * h;
+    const float *__restrict__ sd = a.src.img[1][a.level];
+    const float *__restrict__ td = a.tgt.img[1][a.level];
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x)
+    {
+        const int i = s / w, j = s - i * w;
+        const float d_s = sd[s];
+        int2 c = make_int2(-1, 0);
+        if (d_s == d_s)
+        {
+            float uv[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                uv[r] = fadd(fadd(fmul(fmul(d_s, sM[r * 3]), (float)j), fadd(fmul(fmul(d_s, sM[r * 3 + 1]), (float)i), fmul(d_s, sM[r * 3 + 2]))),
+                             sM[9 + r]);
+            const float tds = uv[2];
+            // (int)(x / z + 0.5): float division, double add, truncation (x86 semantics)
+            const int u_t = cvtt_x86(__dadd_rn((double)fdiv(uv[0], tds), 0.5));
+            const int v_t = cvtt_x86(__dadd_rn((double)fdiv(uv[1], tds), 0.5));
+            if (u_t >= 0 && u_t < w && v_t >= 0 && v_t < h)
+            {
+                const float d_t = td[v_t * w + u_t];
+                if (d_t == d_t && (double)fabsf(fsub(d_t, tds)) < 0.05) c = make_int2(v_t * w + u_t, __float_as_int(tds));
+            }
+        }
+        a.cand[s] = c;
+    }
+}
+
+// AddElementToCorrespondenceMap, resolved without the raster-order loop.  The reference accepts source pixel s (a valid
+// candidate with target t and transformed depth d) iff wraping_depth[t] == -1 or wraping_depth[t] > d at the moment s is
+// visited, where wraping_depth[t] was written when SOURCE pixel t was accepted earlier in raster order.  Hence
+//   t >= s, t not a valid candidate, or d(t) > d(s)  ->  accept(s) = true
+//   otherwise                                         ->  accept(s) = !accept(t)
+// and t < s strictly along such a chain, so walking it terminates at an unconditional "true".
+__device__ __forceinline__ bool resolve_accept(const int2 *__restrict__ cand, int s, int2 c)
+{
+    if (c.x < 0) return false;
+    bool acc = true;
+    int cur = s;
+    for (;;)
+    {
+        const int t = c.x;
+        if (t >= cur) break;
+        const int2 ct = cand[t];
+        if (ct.x < 0) break;
+        if (__int_as_float(ct.y) > __int_as_float(c.y)) break;
+        acc = !acc;
+        cur = t;
+        c = ct;
+    }
+    return acc;
+}
+
+__device__ __forceinline__ double warp_sum_d(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// One Jacobian row pair of a correspondence, float arithmetic in the reference's order (DenseOdometryFunction.cpp:146-296);
+// adds its products to the per-thread double accumulators acc[0..20] (upper triangle of J^T J), acc[21..26] (J^T r), acc[27] (r^2)
+template <int TERM>
+__device__ __forceinline__ void accumulate_rows(const OdoArgs &a, const float *T, int s, int t, double *acc)
+{
+    const int l = a.level, w = a.cam.w;
+    const int v_s = s / w, u_s = s - v_s * w;
+    const float fx = a.cam.fx, fy = a.cam.fy;
+    // source_XYZ[v_s][u_s] (TransformToMatXYZ, Geometry.cpp:72-106)
+    const float z = a.src.img[1][l][s];
+    float p0 = -1.0f, p1 = -1.0f, p2 = -1.0f;
+    if (z > 0)
+    {
+        p0 = fdiv(fmul(fsub((float)u_s, a.cam.cx), z), fx);
+        p1 = fdiv(fmul(fsub((float)v_s, a.cam.cy), z), fy);
+        p2 = z;
+    }
+    // R * p + t: Eigen's fixed-size order m0 + (m1 + m2), then + t
+    const float q0 = fadd(fadd(fmul(T[0], p0), fadd(fmul(T[4], p1), fmul(T[8], p2))), T[12]);
+    const float q1 = fadd(fadd(fmul(T[1], p0), fadd(fmul(T[5], p1), fmul(T[9], p2))), T[13]);
+    const float q2 = fadd(fadd(fmul(T[2], p0), fadd(fmul(T[6], p1), fmul(T[10], p2))), T[14]);
+    const float invz = (float)(1.0 / (double)q2);
+    const float sq = 0.70710678118654752440f; // (float)sqrt(0.5) == (float)sqrt(1 - 0.5)
+    float J[2][6], res[2];
+    int rows = 0;
+    if (TERM == 0 || TERM == 1)
+    {
+        const float diff = fsub(a.tgt.img[0][l][t], a.src.img[0][l][s]);
+        const float gx = fmul(0.125f, a.tgt.img[2][l][t]), gy = fmul(0.125f, a.tgt.img[3][l][t]);
+        const float c0 = fmul(fmul(gx, fx), invz), c1 = fmul(fmul(gy, fy), invz);
+        const float c2 = fmul(-fadd(fmul(c0, q0), fmul(c1, q1)), invz);
+        float *j = J[rows];
+        j[0] = c0; j[1] = c1; j[2] = c2;
+        j[3] = fadd(fmul(-q2, c1), fmul(q1, c2));
+        j[4] = fsub(fmul(q2, c0), fmul(q0, c2));
+        j[5] = fadd(fmul(-q1, c0), fmul(q0, c1));
+        if (TERM == 0)
+        {
+#pragma unroll
+            for (int e = 0; e < 6; ++e) j[e] = fmul(sq, j[e]);
+            res[rows] = fmul(sq, diff);
+        }
+        else res[rows] = diff;
+        ++rows;
+    }
+    if (TERM == 0 || TERM == 2)
+    {
+        float gx = fmul(0.125f, a.tgt.img[4][l][t]), gy = fmul(0.125f, a.tgt.img[5][l][t]);
+        if (gx != gx) gx = 0.0f;
+        if (gy != gy) gy = 0.0f;
+        const float diff = fsub(a.tgt.img[1][l][t], q2);
+        const float d0 = fmul(fmul(gx, fx), invz), d1 = fmul(fmul(gy, fy), invz);
+        const float d2 = fmul(-fadd(fmul(d0, q0), fmul(d1, q1)), invz);
+        float *j = J[rows];
+        j[0] = d0; j[1] = d1; j[2] = fsub(d2, 1.0f);
+        j[3] = fsub(fadd(fmul(-q2, d1), fmul(q1, d2)), q1);
+        j[4] = fadd(fsub(fmul(q2, d0), fmul(q0, d2)), q0);
+        j[5] = fadd(fmul(-q1, d0), fmul(q0, d1));
+        if (TERM == 0)
+        {
+#pragma unroll
+            for (int e = 0; e < 6; ++e) j[e] = fmul(sq, j[e]);
+            res[rows] = fmul(sq, diff);
+        }
+        else res[rows] = diff;
+        ++rows;
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+    {
+        if (r >= rows) break;
+        int k = 0;
+#pragma unroll
+        for (int p = 0; p < 6; ++p)
+#pragma unroll
+            for (int q = p; q < 6; ++q) acc[k++] += (double)fmul(J[r][p], J[r][q]);
+#pragma unroll
+        for (int p = 0; p < 6; ++p) acc[21 + p] += (double)fmul(J[r][p], res[r]);
+        acc[27] += (double)fmul(res[r], res[r]);
+    }
+}
+
+// the pose update of DoSingleIteration (DenseOdometryFunction.cpp:402-411), run by one thread of the last CTA
+__device__ void solve_and_update(const OdoArgs &a, OdoState *st)
+{
+    const double *P = st->packet;
+    const int n = (int)(P[28] + 0.5);
+    double JTJ[36], nJTr[6], x[6], dT[16];
+    int k = 0;
+    for (int p = 0; p < 6; ++p)
+        for (int q = p; q < 6; ++q) { JTJ[p * 6 + q] = P[k]; JTJ[q * 6 + p] = P[k]; ++k; }
+    for (int p = 0; p < 6; ++p) nJTr[p] = -P[21 + p];
+    linalg::solve_normal_equations6(JTJ, nJTr, x);
+    for (int p = 0; p < 6; ++p) x[p] = (double)(float)x[p]; // the reference's delta is float32
+    linalg::se3_exp(x, dT);
+    float dTf[16], Tn[16];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) dTf[c * 4 + r] = (float)dT[r * 4 + c];
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 4; ++r)
+            Tn[c * 4 + r] = fadd(fadd(fadd(fmul(dTf[r], st->T[c * 4]), fmul(dTf[4 + r], st->T[c * 4 + 1])), fmul(dTf[8 + r], st->T[c * 4 + 2])),
+                                 fmul(dTf[12 + r], st->T[c * 4 + 3]));
+    for (int e = 0; e < 16; ++e) st->T[e] = Tn[e];
+    const int it = st->iteration;
+    if (it < kMaxTrace)
+    {
+        st->trace_count[it] = n;
+        for (int e = 0; e < 16; ++e) st->trace_T[it][e] = Tn[e];
+    }
+    st->iteration = it + 1;
+    st->last_count = n;
+    // if ((float)correspondences.size() / (height * width) > MAX_INLIER_RATIO_DENSE) break;   (Odometry.cpp:668)
+    if ((double)fdiv((float)n, (float)a.full_pixels) > 0.9) st->break_level = a.level;
+}
+
+// mode 0: solver iteration; mode 1: only the accept flags and the count (NormalizeIntensity / teacher-forced listing)
+template <int TERM, int MODE>
+__global__ void __launch_bounds__(kOdoThreads) odo_iteration_kernel(OdoArgs a)
+{
+    if (MODE == 0 && a.st->break_level == a.level) return;
+    __shared__ double s_part[kOdoThreads / 32][kOdoPacket];
+    __shared__ float sT[16];
+    __shared__ bool s_last;
+    if (threadIdx.x < 16) sT[threadIdx.x] = a.st->T[threadIdx.x];
+    __syncthreads();
+    const int n = a.cam.w * a.cam.h;
+    double acc[29];
+#pragma unroll
+    for (int k = 0; k < 29; ++k) acc[k] = 0.0;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x)
+    {
+        const int2 c = a.cand[s];
+        const bool ok = resolve_accept(a.cand, s, c);
+        a.accepted[s] = ok;
+        if (!ok) continue;
+        acc[28] += 1.0;
+        if (MODE == 0) accumulate_rows<TERM>(a, sT, s, c.x, acc);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 29; ++k)
+    {
+        const double v = warp_sum_d(acc[k]);
+        if (lane == 0) s_part[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 29)
+    {
+        double v = 0.0;
+        for (int wp = 0; wp < kOdoThreads / 32; ++wp) v += s_part[wp][threadIdx.x];
+        a.partials[(size_t)blockIdx.x * kOdoPacket + threadIdx.x] = v;
+    }
+    // last CTA: fixed-order sum of the partials, then the solve
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&a.st->blocks_done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    {
+        const int k = threadIdx.x & 31, chain = threadIdx.x >> 5;
+        double v = 0.0;
+        if (k < 29)
+            for (unsigned int b = chain; b < gridDim.x; b += kOdoThreads / 32) v += __ldcg(&a.partials[(size_t)b * kOdoPacket + k]);
+        s_part[chain][k] = v;
+        __syncthreads();
+        if (threadIdx.x < 29)
+        {
+            double tot = 0.0;
+            for (int c = 0; c < kOdoThreads / 32; ++c) tot += s_part[c][threadIdx.x];
+            a.st->packet[threadIdx.x] = tot;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    a.st->blocks_done = 0;
+    if (MODE == 0) solve_and_update(a, a.st);
+    else a.st->last_count = (int)(a.st->packet[28] + 0.5);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ordered compaction of the accepted pixels (raster order of the source, like the reference's second loop)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kCompactTile = 1024;
+__device__ __forceinline__ unsigned int block_scan_1024(unsigned int v, unsigned int *warp_sums, unsigned int *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const unsigned int m = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += m;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0)
+    {
+        unsigned int ws = warp_sums[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const unsigned int m = __shfl_up_sync(0xffffffffu, ws, o);
+            if (lane >= o) ws += m;
+        }
+        warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    *total = warp_sums[31];
+    const unsigned int r = inc + (warp ? warp_sums[warp - 1] : 0u);
+    __syncthreads();
+    return r;
+}
+__global__ void __launch_bounds__(1024) odo_tile_counts_kernel(const unsigned char *__restrict__ accepted, int n, unsigned int *tile_counts)
+{
+    __shared__ unsigned int warp_sums[32];
+    const int i = blockIdx.x * kCompactTile + threadIdx.x;
+    unsigned int total;
+    block_scan_1024(i < n ? accepted[i] : 0u, warp_sums, &total);
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) odo_tile_scan_kernel(unsigned int *tile_counts, int n_tiles, OdoState *st)
+{
+    __shared__ unsigned int warp_sums[32];
+    unsigned int carry = 0;
+    for (int base = 0; base < n_tiles; base += 1024)
+    {
+        const int i = base + threadIdx.x;
+        const unsigned int v = i < n_tiles ? tile_counts[i] : 0u;
+        unsigned int total;
+        const unsigned int inc = block_scan_1024(v, warp_sums, &total);
+        if (i < n_tiles) tile_counts[i] = carry + inc - v;
+        carry += total;
+    }
+    if (threadIdx.x == 0) st->n_pairs = (int)carry;
+}
+// pairs: (v_s, u_s, v_t, u_t) per accepted pixel
+__global__ void __launch_bounds__(1024) odo_compact_kernel(const unsigned char *__restrict__ accepted, const int2 *__restrict__ cand, int n,
+                                                           int w, const unsigned int *__restrict__ tile_offsets, uint4 *__restrict__ pairs)
+{
+    __shared__ unsigned int warp_sums[32];
+    const int i = blockIdx.x * kCompactTile + threadIdx.x;
+    const unsigned int f = i < n ? accepted[i] : 0u;
+    unsigned int total;
+    const unsigned int inc = block_scan_1024(f, warp_sums, &total);
+    if (!f) return;
+    const unsigned int pos = tile_offsets[blockIdx.x] + inc - 1u;
+    const int t = cand[i].x;
+    pairs[pos] = make_uint4((unsigned int)(i / w), (unsigned int)(i % w), (unsigned int)(t / w), (unsigned int)(t % w));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// NormalizeIntensity: the reference's means are SEQUENTIAL float32 sums over the correspondence list
+// (DenseOdometryFunction.cpp:131-141); 0.5 / mean then scales the image, so the sum has to be reproduced bit for bit.
+// One warp per image: lanes fetch 32 values at a time (coalesced gathers, independent of the sum), every lane then
+// adds them in list order -- the dependent chain is one FADD per element.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) odo_sequential_mean_kernel(const uint4 *__restrict__ pairs, OdoState *st, const float *__restrict__ sgray,
+                                                                 const float *__restrict__ tgray, int w)
+{
+    const int which = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = st->n_pairs;
+    const float *img = which ? tgray : sgray;
+    float sum = 0.0f;
+    float next = 0.0f;
+    if (lane < n)
+    {
+        const uint4 p = pairs[lane];
+        next = which ? img[p.z * w + p.w] : img[p.x * w + p.y];
+    }
+    for (int base = 0; base < n; base += 32)
+    {
+        const float v = next;
+        const int i = base + 32 + lane;
+        next = 0.0f;
+        if (i < n)
+        {
+            const uint4 p = pairs[i];
+            next = which ? img[p.z * w + p.w] : img[p.x * w + p.y];
+        }
+        const int m = n - base < 32 ? n - base : 32;
+        if (m == 32)
+        {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) sum = fadd(sum, __shfl_sync(0xffffffffu, v, k));
+        }
+        else
+            for (int k = 0; k < m; ++k) sum = fadd(sum, __shfl_sync(0xffffffffu, v, k));
+    }
+    if (lane == 0)
+    {
+        const float mean = fdiv(sum, (float)n); // mean /= (float)correspondence.size()
+        if (which) st->mean_tgt = mean; else st->mean_src = mean;
+    }
+}
+// tool::LinearTransform(image, 0.5 / mean, 0.0): the scale is computed in double and passed as float
+__global__ void odo_scale_kernel(float *__restrict__ sgray, float *__restrict__ tgray, int n, const OdoState *st)
+{
+    const float ss = (float)(0.5 / (double)st->mean_src), ts = (float)(0.5 / (double)st->mean_tgt);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        sgray[i] = fadd(fmul(sgray[i], ss), 0.0f);
+        if (tgray != sgray) tgray[i] = fadd(fmul(tgray[i], ts), 0.0f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// result assembly: correspondence_set pairs xyz_s[v_s][u_s] with xyz_t[v_s][u_s] (the SAME pixel on the target's
+// XYZ image -- reference quirk, Odometry.cpp:672-682) and rmse = ComputeReprojectionError3D (Geometry.cpp:45-59)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void backproject(const OdoCam &cam, float z, int u, int v, float *p)
+{
+    p[0] = p[1] = p[2] = -1.0f;
+    if (z > 0)
+    {
+        p[0] = fdiv(fmul(fsub((float)u, cam.cx), z), cam.fx);
+        p[1] = fdiv(fmul(fsub((float)v, cam.cy), z), cam.fy);
+        p[2] = z;
+    }
+}
+__global__ void __launch_bounds__(kOdoThreads) odo_rmse_kernel(const uint4 *__restrict__ pairs, OdoState *st, const float *__restrict__ sdepth,
+                                                               const float *__restrict__ tdepth, OdoCam cam, float *__restrict__ corr_xyz)
+{
+    const int n = st->n_pairs;
+    const float *T = st->T;
+    double sum = 0.0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+    {
+        const uint4 p = pairs[k];
+        const int s = p.x * cam.w + p.y;
+        float a[3], b[3];
+        backproject(cam, sdepth[s], (int)p.y, (int)p.x, a);
+        backproject(cam, tdepth[s], (int)p.y, (int)p.x, b);
+        if (corr_xyz)
+        {
+            float *o = corr_xyz + 6 * (size_t)k;
+            o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; o[3] = b[0]; o[4] = b[1]; o[5] = b[2];
+        }
+        // TransformPoint: T * (x, y, z, 1), head<3>() / w
+        const float wv = row_xyz1(T[3], T[7], T[11], T[15], a[0], a[1], a[2]);
+        const float e0 = fsub(fdiv(row_xyz1(T[0], T[4], T[8], T[12], a[0], a[1], a[2]), wv), b[0]);
+        const float e1 = fsub(fdiv(row_xyz1(T[1], T[5], T[9], T[13], a[0], a[1], a[2]), wv), b[1]);
+        const float e2 = fsub(fdiv(row_xyz1(T[2], T[6], T[10], T[14], a[0], a[1], a[2]), wv), b[2]);
+        sum += (double)fadd(fmul(e0, e0), fadd(fmul(e1, e1), fmul(e2, e2)));
+    }
+    sum = warp_sum_d(sum);
+    if ((threadIdx.x & 31) == 0 && sum != 0.0) atomicAdd(&st->rmse_sum, sum);
+}
+
+} // namespace opb
+
+using namespace opb;
+
+struct opb_odometry
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    opb_odometry_desc desc;
+    OdoCam cams[kMaxLevels];
+    int2 *d_cand = nullptr;
+    unsigned char *d_accepted = nullptr;
+    double *d_partials = nullptr;
+    unsigned int *d_tiles = nullptr;
+    uint4 *d_pairs = nullptr;
+    float *d_corr_xyz = nullptr;
+    float *d_identity = nullptr;
+    float *d_tmp = nullptr; // 2 images: un-blurred gray and depth
+    OdoState *d_state = nullptr;
+    OdoState *h_state = nullptr; // pinned
+    int max_blocks = 0;
+    bool profiling = false;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    float last_ms = 0;
+};
+
+struct opb_frame
+{
+    opb_odometry *owner = nullptr; // identity check only, never dereferenced on destruction
+    int device = 0;
+    int w = 0, h = 0, depth_type = 0;
+    uint8_t *d_bgr = nullptr;
+    void *d_depth = nullptr;
+    float *d_images = nullptr;
+    FrameImages im;
+    bool initialized = false; // gray + depth32f
+    bool preprocessed = false; // + pyramids (IsPreprocessedDense)
+};
+
+static size_t level_pixels(const opb_odometry *o, int l) { return (size_t)(o->desc.width >> l) * (size_t)(o->desc.height >> l); }
+
+static void setup_cameras(opb_odometry *o)
+{
+    // Odometry::CreatePyramidCameras (Odometry.h:110-120) / PinholeCamera::GenerateNextPyramid (Camera.h:38-42)
+    o->cams[0] = {o->desc.fx, o->desc.fy, o->desc.cx, o->desc.cy, o->desc.width, o->desc.height};
+    for (int l = 1; l < kMaxLevels; ++l)
+        o->cams[l] = {o->cams[l - 1].fx / 2, o->cams[l - 1].fy / 2, o->cams[l - 1].cx / 2, o->cams[l - 1].cy / 2, o->cams[l - 1].w / 2,
+                      o->cams[l - 1].h / 2};
+}
+
+static int check_desc(const opb_odometry_desc *d)
+{
+    if (d->width <= 0 || d->height <= 0 || (long long)d->width * d->height > (1 << 26)) { set_error("bad image size %dx%d", d->width, d->height); return OPB_ERR_INVALID; }
+    if (d->levels < 1 || d->levels > kMaxLevels) { set_error("levels must be 1..%d", kMaxLevels); return OPB_ERR_INVALID; }
+    if ((d->width >> (d->levels - 1)) < 2 || (d->height >> (d->levels - 1)) < 2) { set_error("image too small for %d levels", d->levels); return OPB_ERR_INVALID; }
+    int total = 0;
+    for (int l = 0; l < d->levels; ++l)
+    {
+        if (d->iterations[l] < 0) { set_error("negative iteration count"); return OPB_ERR_INVALID; }
+        total += d->iterations[l];
+    }
+    if (!(d->fx != 0.0f && d->fy != 0.0f)) { set_error("zero focal length"); return OPB_ERR_INVALID; }
+    (void)total;
+    return OPB_OK;
+}
+
+extern "C"
+{
+void opb_odometry_desc_default(opb_odometry_desc *d)
+{
+    if (!d) return;
+    memset(d, 0, sizeof(*d));
+    // camera::PinholeCamera() (Camera.h:94-105)
+    d->fx = 514.817f; d->fy = 515.375f; d->cx = 318.771f; d->cy = 238.447f;
+    d->width = 640; d->height = 480; d->depth_scale = 1000.0f;
+    d->levels = 3;       // Odometry.h:168
+    d->iterations[0] = 4; d->iterations[1] = 8; d->iterations[2] = 16; // Odometry.h:170, indexed by level
+}
+
+void opb_odometry_destroy(opb_odometry *o)
+{
+    if (!o) return;
+    cudaSetDevice(o->device);
+    if (o->stream) cudaStreamSynchronize(o->stream);
+    cudaFree(o->d_cand); cudaFree(o->d_accepted); cudaFree(o->d_partials); cudaFree(o->d_tiles); cudaFree(o->d_pairs);
+    cudaFree(o->d_corr_xyz); cudaFree(o->d_identity); cudaFree(o->d_tmp); cudaFree(o->d_state);
+    if (o->h_state) cudaFreeHost(o->h_state);
+    for (int i = 0; i < 2; ++i) if (o->ev[i]) cudaEventDestroy(o->ev[i]);
+    if (o->own_stream && o->stream) cudaStreamDestroy(o->stream);
+    cudaGetLastError();
+    delete o;
+}
+
+int opb_odometry_create(const opb_odometry_desc *desc, opb_odometry **out)
+{
+    if (!desc || !out) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    *out = nullptr;
+    int rc = check_desc(desc);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+        cudaGetLastError();
+        set_error("no CUDA device: onepiece_b200 has no CPU path");
+        return OPB_ERR_CUDA;
+    }
+    if (desc->device < 0 || desc->device >= ndev) { set_error("device %d out of range (%d devices)", desc->device, ndev); return OPB_ERR_INVALID; }
+    OPB_CUDA(cudaSetDevice(desc->device));
+    opb_odometry *o = new opb_odometry();
+    o->device = desc->device;
+    o->desc = *desc;
+    setup_cameras(o);
+    cudaDeviceProp prop;
+    OPB_CUDA(cudaGetDeviceProperties(&prop, desc->device));
+    o->sm_count = prop.multiProcessorCount;
+    if (desc->stream) o->stream = (cudaStream_t)desc->stream;
+    else { OPB_CUDA(cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking)); o->own_stream = true; }
+    const size_t n = level_pixels(o, 0);
+    o->max_blocks = o->sm_count * 4;
+    const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    cudaError_t e = cudaMalloc(&o->d_cand, n * sizeof(int2));
+    if (e == cudaSuccess) e = cudaMalloc(&o->d_accepted, n);
+    if (e == cudaSuccess) e = cudaMalloc(&o->d_partials, (size_t)o->max_blocks * kOdoPacket * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&o->d_tiles, (n / kCompactTile + 2) * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&o->d_pairs, n * sizeof(uint4));
+    if (e == cudaSuccess) e = cudaMalloc(&o->d_corr_xyz, n * 6 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&o->d_identity, sizeof(I));
+    if (e == cudaSuccess) e = cudaMalloc(&o->d_tmp, 2 * n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&o->d_state, sizeof(OdoState));
+    if (e == cudaSuccess) e = cudaHostAlloc(&o->h_state, sizeof(OdoState), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMemcpy(o->d_identity, I, sizeof(I), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(o->d_state, 0, sizeof(OdoState));
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&o->ev[i]);
+    if (e != cudaSuccess)
+    {
+        set_error("odometry workspace allocation failed: %s", cudaGetErrorString(e));
+        opb_odometry_destroy(o);
+        return OPB_ERR_CUDA;
+    }
+    *out = o;
+    return OPB_OK;
+}
+
+int opb_odometry_set_profiling(opb_odometry *o, int on)
+{
+    if (!o) { set_error("odometry is NULL"); return OPB_ERR_INVALID; }
+    o->profiling = on != 0;
+    return OPB_OK;
+}
+int opb_odometry_last_timing(opb_odometry *o, float *tracking_ms)
+{
+    if (!o) { set_error("odometry is NULL"); return OPB_ERR_INVALID; }
+    if (tracking_ms) *tracking_ms = o->last_ms;
+    return OPB_OK;
+}
+
+void opb_frame_destroy(opb_frame *f)
+{
+    if (!f) return;
+    cudaSetDevice(f->device); // cudaFree synchronises the device: no kernel can still be reading the frame
+    cudaFree(f->d_bgr); cudaFree(f->d_depth); cudaFree(f->d_images);
+    cudaGetLastError();
+    delete f;
+}
+
+// geometry::RGBDFrame(rgb, depth) (RGBDFrame.h:14-19): keeps the raw images; the dense cache is filled on first use
+int opb_frame_create(opb_odometry *o, const uint8_t *bgr, const void *depth, int depth_type, opb_frame **out)
+{
+    if (!o || !bgr || !depth || !out) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    *out = nullptr;
+    if (depth_type != OPB_DEPTH_F32 && depth_type != OPB_DEPTH_U16)
+    {
+        // ConvertDepthTo32FNaN: "Unknown depth image type" + exit(1) in the reference (DenseOdometryFunction.cpp:51-55)
+        set_error("[ImageProcessing]::[ERROR]::Unknown depth image type: %d", depth_type);
+        return OPB_ERR_UNSUPPORTED;
+    }
+    OPB_CUDA(cudaSetDevice(o->device));
+    opb_frame *f = new opb_frame();
+    f->owner = o; f->device = o->device; f->w = o->desc.width; f->h = o->desc.height; f->depth_type = depth_type;
+    const size_t n = level_pixels(o, 0);
+    size_t total = 0;
+    for (int l = 0; l < o->desc.levels; ++l) total += 6 * level_pixels(o, l);
+    cudaError_t e = cudaMalloc(&f->d_bgr, n * 3);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_depth, n * (depth_type == OPB_DEPTH_U16 ? 2 : 4));
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_images, total * sizeof(float));
+    if (e != cudaSuccess)
+    {
+        set_error("frame allocation failed: %s", cudaGetErrorString(e));
+        opb_frame_destroy(f);
+        return OPB_ERR_CUDA;
+    }
+    float *p = f->d_images;
+    memset(&f->im, 0, sizeof(f->im));
+    for (int a = 0; a < 6; ++a)
+        for (int l = 0; l < o->desc.levels; ++l) { f->im.img[a][l] = p; p += level_pixels(o, l); }
+    e = cudaMemcpyAsync(f->d_bgr, bgr, n * 3, cudaMemcpyDefault, o->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_depth, depth, n * (depth_type == OPB_DEPTH_U16 ? 2 : 4), cudaMemcpyDefault, o->stream);
+    if (e != cudaSuccess)
+    {
+        set_error("frame upload failed: %s", cudaGetErrorString(e));
+        opb_frame_destroy(f);
+        return OPB_ERR_CUDA;
+    }
+    if (cudaStreamSynchronize(o->stream) != cudaSuccess)
+    {
+        set_error("frame upload failed");
+        opb_frame_destroy(f);
+        return OPB_ERR_CUDA;
+    }
+    *out = f;
+    return OPB_OK;
+}
+} // extern "C"
+
+static const dim3 kImgBlock(32, 8);
+static dim3 img_grid(int w, int h, int z) { return dim3((w + 31) / 32, (h + 7) / 8, z); }
+
+// InitializeRGBDDenseTracking (Odometry.cpp:609-620)
+static int frame_initialize(opb_odometry *o, opb_frame *f)
+{
+    const int n = (int)level_pixels(o, 0);
+    cudaStream_t s = o->stream;
+    odo_convert_kernel<<<(n + 255) / 256, 256, 0, s>>>(f->d_bgr, f->d_depth, f->depth_type == OPB_DEPTH_U16, o->desc.depth_scale, n, o->d_tmp,
+                                                       o->d_tmp + n);
+    odo_blur3_kernel<<<img_grid(f->w, f->h, 2), kImgBlock, 0, s>>>(o->d_tmp, o->d_tmp + n, f->w, f->h, f->im.img[0][0], f->im.img[1][0]);
+    OPB_CUDA(cudaGetLastError());
+    f->initialized = true;
+    return OPB_OK;
+}
+// CreateImagePyramid (Odometry.cpp:436-449)
+static int frame_pyramids(opb_odometry *o, opb_frame *f)
+{
+    cudaStream_t s = o->stream;
+    for (int l = 1; l < o->desc.levels; ++l)
+        odo_pyrdown_kernel<<<img_grid(f->w >> l, f->h >> l, 2), kImgBlock, 0, s>>>(f->im.img[0][l - 1], f->im.img[1][l - 1], f->w >> (l - 1),
+                                                                                  f->h >> (l - 1), f->im.img[0][l], f->im.img[1][l]);
+    odo_sobel_kernel<<<img_grid(f->w, f->h, 4 * o->desc.levels), kImgBlock, 0, s>>>(f->im, f->w, f->h, o->desc.levels);
+    OPB_CUDA(cudaGetLastError());
+    f->preprocessed = true;
+    return OPB_OK;
+}
+
+static int grid_for(const opb_odometry *o, size_t n)
+{
+    const size_t need = (n + kOdoThreads - 1) / kOdoThreads;
+    return (int)(need < (size_t)o->max_blocks ? need : (size_t)o->max_blocks);
+}
+
+static OdoArgs make_args(opb_odometry *o, opb_frame *S, opb_frame *T, int level, int term)
+{
+    OdoArgs a;
+    a.src = S->im; a.tgt = T->im; a.cam = o->cams[level]; a.level = level; a.term = term;
+    a.full_pixels = o->desc.width * o->desc.height;
+    a.cand = o->d_cand; a.accepted = o->d_accepted; a.partials = o->d_partials; a.st = o->d_state; a.T_override = nullptr;
+    return a;
+}
+
+static void launch_iteration(opb_odometry *o, const OdoArgs &a, bool count_only)
+{
+    const size_t n = (size_t)a.cam.w * a.cam.h;
+    const int nb = grid_for(o, n);
+    cudaStream_t s = o->stream;
+    odo_candidates_kernel<<<nb, kOdoThreads, 0, s>>>(a);
+    if (count_only) odo_iteration_kernel<0, 1><<<nb, kOdoThreads, 0, s>>>(a);
+    else if (a.term == 0) odo_iteration_kernel<0, 0><<<nb, kOdoThreads, 0, s>>>(a);
+    else if (a.term == 1) odo_iteration_kernel<1, 0><<<nb, kOdoThreads, 0, s>>>(a);
+    else odo_iteration_kernel<2, 0><<<nb, kOdoThreads, 0, s>>>(a);
+}
+
+// accepted flags + candidates of level `level` -> ordered pair list in o->d_pairs, count in state.n_pairs
+static void launch_compaction(opb_odometry *o, int level)
+{
+    const int n = (int)level_pixels(o, level);
+    const int tiles = (n + kCompactTile - 1) / kCompactTile;
+    cudaStream_t s = o->stream;
+    odo_tile_counts_kernel<<<tiles, 1024, 0, s>>>(o->d_accepted, n, o->d_tiles);
+    odo_tile_scan_kernel<<<1, 1024, 0, s>>>(o->d_tiles, tiles, o->d_state);
+    odo_compact_kernel<<<tiles, 1024, 0, s>>>(o->d_accepted, o->d_cand, n, o->cams[level].w, o->d_tiles, o->d_pairs);
+}
+
+// the identity-pose correspondences + NormalizeIntensity on both level-0 gray images, in place (Odometry.cpp:588-595)
+static void launch_normalize(opb_odometry *o, opb_frame *S, opb_frame *T)
+{
+    OdoArgs a = make_args(o, S, T, 0, 0);
+    a.T_override = o->d_identity;
+    launch_iteration(o, a, true);
+    launch_compaction(o, 0);
+    cudaStream_t s = o->stream;
+    odo_sequential_mean_kernel<<<1, 64, 0, s>>>(o->d_pairs, o->d_state, S->im.img[0][0], T->im.img[0][0], o->cams[0].w);
+    const int n = (int)level_pixels(o, 0);
+    odo_scale_kernel<<<grid_for(o, n), kOdoThreads, 0, s>>>(S->im.img[0][0], T->im.img[0][0], n, o->d_state);
+}
+
+static int reset_state(opb_odometry *o, const float *init_T)
+{
+    OdoState *h = o->h_state;
+    memset(h, 0, sizeof(OdoState));
+    memcpy(h->T, init_T, 16 * sizeof(float));
+    h->break_level = -1;
+    OPB_CUDA(cudaMemcpyAsync(o->d_state, h, sizeof(OdoState), cudaMemcpyHostToDevice, o->stream));
+    return OPB_OK;
+}
+
+// MultiScaleComputing + result assembly; both frames pre-processed
+static int run_tracking(opb_odometry *o, opb_frame *S, opb_frame *T, int term, opb_tracking_result *res, uint32_t *pixel_pairs,
+                        size_t pairs_cap, float *corr_xyz)
+{
+    cudaStream_t s = o->stream;
+    for (int l = o->desc.levels - 1; l >= 0; --l)
+    {
+        OdoArgs a = make_args(o, S, T, l, term);
+        for (int j = 0; j < o->desc.iterations[l]; ++j) launch_iteration(o, a, false);
+    }
+    // the correspondences of the last executed iteration, in raster order (level 0 unless its iteration count is 0;
+    // the reference then indexes the level-0 XYZ images with the coarser level's pixel coordinates, and so does this)
+    int last_level = -1;
+    for (int l = 0; l < o->desc.levels && last_level < 0; ++l)
+        if (o->desc.iterations[l] > 0) last_level = l;
+    if (last_level >= 0) launch_compaction(o, last_level);
+    const int n0 = (int)level_pixels(o, 0);
+    odo_rmse_kernel<<<grid_for(o, n0), kOdoThreads, 0, s>>>(o->d_pairs, o->d_state, S->im.img[1][0], T->im.img[1][0], o->cams[0],
+                                                            corr_xyz ? o->d_corr_xyz : nullptr);
+    OPB_CUDA(cudaGetLastError());
+    OPB_CUDA(cudaMemcpyAsync(o->h_state, o->d_state, sizeof(OdoState), cudaMemcpyDeviceToHost, s));
+    if (o->profiling) OPB_CUDA(cudaEventRecord(o->ev[1], s));
+    OPB_CUDA(cudaStreamSynchronize(s));
+    if (o->profiling) cudaEventElapsedTime(&o->last_ms, o->ev[0], o->ev[1]);
+    const OdoState *h = o->h_state;
+    memset(res, 0, sizeof(*res));
+    memcpy(res->T, h->T, sizeof(res->T));
+    res->n_correspondences = (size_t)h->n_pairs;
+    res->iterations = h->iteration;
+    res->rmse = sqrt(h->rmse_sum / (double)h->n_pairs);
+    // return (float)correspondences.size() / (height * width) >= MIN_INLIER_RATIO_DENSE;   (Odometry.cpp:684)
+    res->tracking_success = (double)((float)h->n_pairs / (float)(o->desc.width * o->desc.height)) >= 0.3;
+    const int nt = h->iteration < kMaxTrace ? h->iteration : kMaxTrace;
+    for (int i = 0; i < nt; ++i)
+    {
+        res->corr_per_iteration[i] = h->trace_count[i];
+        memcpy(res->T_per_iteration[i], h->trace_T[i], 16 * sizeof(float));
+    }
+    const size_t np = (size_t)h->n_pairs;
+    if (pixel_pairs && pairs_cap)
+        OPB_CUDA(cudaMemcpy(pixel_pairs, o->d_pairs, (np < pairs_cap ? np : pairs_cap) * sizeof(uint4), cudaMemcpyDeviceToHost));
+    if (corr_xyz && pairs_cap)
+        OPB_CUDA(cudaMemcpy(corr_xyz, o->d_corr_xyz, (np < pairs_cap ? np : pairs_cap) * 6 * sizeof(float), cudaMemcpyDeviceToHost));
+    res->status = OPB_OK;
+    return OPB_OK;
+}
+
+static int check_pair(opb_odometry *o, opb_frame *S, opb_frame *T, int term)
+{
+    if (!o || !S || !T) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    if (S->owner != o || T->owner != o) { set_error("frame belongs to another odometry object"); return OPB_ERR_INVALID; }
+    if (term < 0 || term > 2) { set_error("term_type must be 0 (hybrid), 1 (photo) or 2 (geometry)"); return OPB_ERR_INVALID; }
+    return OPB_OK;
+}
+
+extern "C"
+{
+int opb_frame_preprocess(opb_odometry *o, opb_frame *f)
+{
+    if (!o || !f || f->owner != o) { set_error("bad frame"); return OPB_ERR_INVALID; }
+    OPB_CUDA(cudaSetDevice(o->device));
+    if (f->preprocessed) return OPB_OK;
+    int rc = frame_initialize(o, f);
+    if (rc == OPB_OK) rc = frame_pyramids(o, f);
+    return rc;
+}
+
+int opb_frame_is_preprocessed(const opb_frame *f) { return f && f->preprocessed; }
+
+int opb_frame_image(opb_odometry *o, opb_frame *f, int what, int level, float *out)
+{
+    if (!o || !f || !out || f->owner != o) { set_error("bad argument"); return OPB_ERR_INVALID; }
+    if (what < 0 || what >= 6 || level < 0 || level >= o->desc.levels) { set_error("no such image"); return OPB_ERR_INVALID; }
+    if (!f->preprocessed) { set_error("frame is not pre-processed"); return OPB_ERR_INVALID; }
+    OPB_CUDA(cudaSetDevice(o->device));
+    OPB_CUDA(cudaMemcpyAsync(out, f->im.img[what][level], level_pixels(o, level) * sizeof(float), cudaMemcpyDeviceToHost, o->stream));
+    OPB_CUDA(cudaStreamSynchronize(o->stream));
+    return OPB_OK;
+}
+
+int opb_odometry_dense_tracking_frames(opb_odometry *o, opb_frame *source, opb_frame *target, const float init_T[16], int term_type,
+                                       opb_tracking_result *result, uint32_t *pixel_pairs, size_t pairs_cap, float *corr_xyz)
+{
+    int rc = check_pair(o, source, target, term_type);
+    if (rc) return rc;
+    if (!init_T || !result) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    OPB_CUDA(cudaSetDevice(o->device));
+    if (o->profiling) OPB_CUDA(cudaEventRecord(o->ev[0], o->stream));
+    // Odometry.cpp:571-587: pre-process once per frame
+    if ((rc = opb_frame_preprocess(o, source))) return rc;
+    if ((rc = opb_frame_preprocess(o, target))) return rc;
+    if ((rc = reset_state(o, init_T))) return rc;
+    launch_normalize(o, source, target);
+    return run_tracking(o, source, target, term_type, result, pixel_pairs, pairs_cap, corr_xyz);
+}
+
+int opb_odometry_dense_tracking(opb_odometry *o, const uint8_t *src_bgr, const uint8_t *tgt_bgr, const void *src_depth,
+                                const void *tgt_depth, int depth_type, const float init_T[16], int term_type,
+                                opb_tracking_result *result, uint32_t *pixel_pairs, size_t pairs_cap, float *corr_xyz)
+{
+    if (!o || !init_T || !result) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    if (term_type < 0 || term_type > 2) { set_error("term_type must be 0 (hybrid), 1 (photo) or 2 (geometry)"); return OPB_ERR_INVALID; }
+    opb_frame *S = nullptr, *T = nullptr;
+    OPB_CUDA(cudaSetDevice(o->device));
+    if (o->profiling) OPB_CUDA(cudaEventRecord(o->ev[0], o->stream));
+    int rc = opb_frame_create(o, src_bgr, src_depth, depth_type, &S);
+    if (rc == OPB_OK) rc = opb_frame_create(o, tgt_bgr, tgt_depth, depth_type, &T);
+    // Odometry.cpp:482-509: initialise both, normalise the full-resolution gray images, THEN build the pyramids
+    if (rc == OPB_OK) rc = frame_initialize(o, S);
+    if (rc == OPB_OK) rc = frame_initialize(o, T);
+    if (rc == OPB_OK) rc = reset_state(o, init_T);
+    if (rc == OPB_OK)
+    {
+        launch_normalize(o, S, T);
+        rc = frame_pyramids(o, S);
+    }
+    if (rc == OPB_OK) rc = frame_pyramids(o, T);
+    if (rc == OPB_OK) rc = run_tracking(o, S, T, term_type, result, pixel_pairs, pairs_cap, corr_xyz);
+    opb_frame_destroy(S);
+    opb_frame_destroy(T);
+    return rc;
+}
+
+int opb_odometry_single_iteration(opb_odometry *o, opb_frame *source, opb_frame *target, int level, float T_inout[16], int term_type,
+                                  double sums43[43], uint32_t *pixel_pairs, size_t pairs_cap, size_t *n_pairs)
+{
+    int rc = check_pair(o, source, target, term_type);
+    if (rc) return rc;
+    if (!T_inout || level < 0 || level >= o->desc.levels) { set_error("bad argument"); return OPB_ERR_INVALID; }
+    OPB_CUDA(cudaSetDevice(o->device));
+    if ((rc = opb_frame_preprocess(o, source))) return rc;
+    if ((rc = opb_frame_preprocess(o, target))) return rc;
+    if ((rc = reset_state(o, T_inout))) return rc;
+    OdoArgs a = make_args(o, source, target, level, term_type);
+    launch_iteration(o, a, false);
+    launch_compaction(o, level);
+    OPB_CUDA(cudaGetLastError());
+    OPB_CUDA(cudaMemcpyAsync(o->h_state, o->d_state, sizeof(OdoState), cudaMemcpyDeviceToHost, o->stream));
+    OPB_CUDA(cudaStreamSynchronize(o->stream));
+    const OdoState *h = o->h_state;
+    memcpy(T_inout, h->T, 16 * sizeof(float));
+    if (sums43)
+    {
+        int k = 0;
+        for (int p = 0; p < 6; ++p)
+            for (int q = p; q < 6; ++q) { sums43[p * 6 + q] = h->packet[k]; sums43[q * 6 + p] = h->packet[k]; ++k; }
+        for (int p = 0; p < 6; ++p) sums43[36 + p] = h->packet[21 + p];
+        sums43[42] = h->packet[27];
+    }
+    if (n_pairs) *n_pairs = (size_t)h->n_pairs;
+    const size_t np = (size_t)h->n_pairs;
+    if (pixel_pairs && pairs_cap)
+        OPB_CUDA(cudaMemcpy(pixel_pairs, o->d_pairs, (np < pairs_cap ? np : pairs_cap) * sizeof(uint4), cudaMemcpyDeviceToHost));
+    return OPB_OK;
+}
+} // extern "C"

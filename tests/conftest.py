@@ -39,10 +39,14 @@ def bits(a):
     return a.view(np.uint32)
 
 
-def assert_bit_equal(a, b, what=""):
+def assert_bit_equal(a, b, what="", nan_payload=True):
+    """nan_payload=False: NaNs compare equal whatever their sign/payload bits (x86 SSE and the GPU canonicalise differently)"""
     a = np.ascontiguousarray(a, np.float32)
     b = np.ascontiguousarray(b, np.float32)
     assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    if not nan_payload:
+        a = np.where(np.isnan(a), np.float32(np.nan), a).astype(np.float32)
+        b = np.where(np.isnan(b), np.float32(np.nan), b).astype(np.float32)
     same = a.view(np.uint32) == b.view(np.uint32)
     if not same.all():
         idx = np.argwhere(~same)
