@@ -242,7 +242,9 @@ void opb_odometry_desc_default(opb_odometry_desc *desc);
 int opb_odometry_create(const opb_odometry_desc *desc, opb_odometry **out);
 void opb_odometry_destroy(opb_odometry *o);
 int opb_odometry_set_profiling(opb_odometry *o, int on);
-int opb_odometry_last_timing(opb_odometry *o, float *tracking_ms);
+/* CUDA-event time of the last tracking call (pre-processing of new frames included) and the mean time per solver
+ * iteration that the last CTA spent on the fixed-order partial sum + 6x6 solve + pose update (%globaltimer) */
+int opb_odometry_last_timing(opb_odometry *o, float *tracking_ms, float *solve_tail_us);
 
 /* geometry::RGBDFrame(rgb, depth) (RGBDFrame.h:14-19): uploads the raw images (host or device pointers; returns when
  * the copies are done).  depth_type other than OPB_DEPTH_F32 / OPB_DEPTH_U16 -> OPB_ERR_UNSUPPORTED (the reference

@@ -14,9 +14,10 @@
 // and stops as soon as the best squared distance is provably minimal, so the answer is the exact nearest
 // neighbour (distance formula and summation order of nanoflann's L2_Simple_Adaptor).  The walk is capped at the
 // inlier threshold: a neighbour farther than that can never pass CountInliers, so it is reported as "none".
-// One kernel launch per ICP iteration does transform + search + inlier test + Jacobian row + the 29-scalar
-// reduction (warp shuffles in fp64, fixed-order block partials -> deterministic) and, in the last CTA to
-// finish, the 6x6 solve, the SE(3) exponential and the pose update -- the host is not involved until the end.
+// An ICP iteration is two launches.  icp_search_kernel: transform + exact nearest neighbour, eight lanes per query (one
+// grid row each) so the row lookups of a query are in flight together.  icp_accumulate_kernel: inlier test + Jacobian row +
+// the 30-scalar reduction (per-thread fp64 accumulators, warp shuffles, fixed-order CTA partials -> deterministic) and, in
+// the last CTA to finish, the 6x6 solve, the SE(3) exponential and the pose update -- the host is not involved until the end.
 #include <cfloat>
 #include <cstdlib>
 #include <cstring>
@@ -49,6 +50,7 @@ struct IcpState // device-resident solver state
     unsigned int bbox_enc[6];
     unsigned long long n_inliers;
     double sum_error;
+    unsigned int blocks_done;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -266,72 +268,6 @@ __device__ __forceinline__ float dist2_nanoflann(float ax, float ay, float az, f
     return fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
 }
 
-// exact nearest neighbour of q within `radius`; returns the target index or -1
-__device__ int grid_nearest(const IcpGrid &g, const unsigned int *__restrict__ cell_start, const float4 *__restrict__ sorted,
-                            float qx, float qy, float qz, float radius)
-{
-    if (!(qx == qx && qy == qy && qz == qz)) return -1;
-    const float fx = (qx - g.origin[0]) * g.inv_h, fy = (qy - g.origin[1]) * g.inv_h, fz = (qz - g.origin[2]) * g.inv_h;
-    // home cell, not clamped: a query outside the grid starts its rings where it is
-    const float bound = (float)(1 << 20);
-    if (!(fabsf(fx) < bound && fabsf(fy) < bound && fabsf(fz) < bound)) return -1;
-    const int hx = (int)floorf(fx), hy = (int)floorf(fy), hz = (int)floorf(fz);
-    // distance from q to the faces of its home cell: rings up to r cover everything closer than r*h + margin
-    const float margin = fminf(fminf(fminf(fx - hx, hx + 1 - fx), fminf(fy - hy, hy + 1 - fy)), fminf(fz - hz, hz + 1 - fz)) * g.h;
-    const float slack = 1e-3f * g.h; // cell assignment is computed in float: keep the stop test conservative
-    float best = FLT_MAX;
-    int best_idx = -1;
-    const int r_max = (int)ceilf(radius * g.inv_h) + 1;
-    for (int r = 0; r <= r_max; ++r)
-    {
-        const int z0 = max(hz - r, 0), z1 = min(hz + r, g.dim[2] - 1);
-        const int y0 = max(hy - r, 0), y1 = min(hy + r, g.dim[1] - 1);
-        for (int cz = z0; cz <= z1; ++cz)
-            for (int cy = y0; cy <= y1; ++cy)
-            {
-                const bool shell_row = (abs(cz - hz) == r) || (abs(cy - hy) == r);
-                // rows on the ring's z/y faces are scanned along all of x; interior rows only at the two x ends
-                const int xa = max(hx - r, 0), xb = min(hx + r, g.dim[0] - 1);
-                if (xa > xb) continue;
-                const unsigned int row = (unsigned int)g.dim[0] * ((unsigned int)cy + (unsigned int)g.dim[1] * (unsigned int)cz);
-                if (shell_row)
-                {
-                    // cells of one row are contiguous in the sorted array: one range for the whole row
-                    const unsigned int s = cell_start[row + xa], e = cell_start[row + xb + 1];
-                    for (unsigned int k = s; k < e; ++k)
-                    {
-                        const float4 t = sorted[k];
-                        const float d = dist2_nanoflann(qx, qy, qz, t.x, t.y, t.z);
-                        const int ti = __float_as_int(t.w);
-                        if (d < best || (d == best && ti < best_idx)) { best = d; best_idx = ti; }
-                    }
-                }
-                else
-                {
-#pragma unroll
-                    for (int side = 0; side < 2; ++side)
-                    {
-                        const int cx = side ? hx + r : hx - r;
-                        if (cx < 0 || cx >= g.dim[0] || (side && r == 0)) continue;
-                        const unsigned int s = cell_start[row + cx], e = cell_start[row + cx + 1];
-                        for (unsigned int k = s; k < e; ++k)
-                        {
-                            const float4 t = sorted[k];
-                            const float d = dist2_nanoflann(qx, qy, qz, t.x, t.y, t.z);
-                            const int ti = __float_as_int(t.w);
-                            if (d < best || (d == best && ti < best_idx)) { best = d; best_idx = ti; }
-                        }
-                    }
-                }
-            }
-        const float covered = (float)r * g.h + margin - slack;
-        if (covered > 0 && best <= covered * covered) break; // nothing outside the scanned cube can be closer
-        if (covered > radius) break;                          // nothing within the inlier radius is left
-    }
-    if (best_idx >= 0 && best > radius * radius) return -1;
-    return best_idx;
-}
-
 struct IcpArgs
 {
     const float *src;       // ns x 3 (already scaled)
@@ -350,6 +286,142 @@ struct IcpArgs
     unsigned char *inlier;  // ns flags
 };
 
+// geometry::TransformPoints: T * (x,y,z,1) then divide by w (Geometry.cpp:19-27)
+__device__ __forceinline__ void transform_point(const float *T, float sx, float sy, float sz, float &px, float &py, float &pz)
+{
+    const float w = row_xyz1(T[3], T[7], T[11], T[15], sx, sy, sz);
+    px = fdiv(row_xyz1(T[0], T[4], T[8], T[12], sx, sy, sz), w);
+    py = fdiv(row_xyz1(T[1], T[5], T[9], T[13], sx, sy, sz), w);
+    pz = fdiv(row_xyz1(T[2], T[6], T[10], T[14], sx, sy, sz), w);
+}
+
+// scans cells [xa, xb] (clipped to the grid) of row (cy, cz) into the running best (distance, index); ties go to the
+// smaller target index
+__device__ __forceinline__ void scan_cells(const IcpGrid &g, const unsigned int *__restrict__ cell_start, const float4 *__restrict__ sorted,
+                                           int xa, int xb, int cy, int cz, float qx, float qy, float qz, float &bd, int &bi)
+{
+    xa = max(xa, 0);
+    xb = min(xb, g.dim[0] - 1);
+    if (xa > xb || cy < 0 || cy >= g.dim[1] || cz < 0 || cz >= g.dim[2]) return;
+    const unsigned int row = (unsigned int)g.dim[0] * ((unsigned int)cy + (unsigned int)g.dim[1] * (unsigned int)cz);
+    const unsigned int s = __ldg(&cell_start[row + xa]), e = __ldg(&cell_start[row + xb + 1]);
+    for (unsigned int k = s; k < e; ++k)
+    {
+        const float4 t = __ldg(&sorted[k]);
+        const float d = dist2_nanoflann(qx, qy, qz, t.x, t.y, t.z);
+        const int ti = __float_as_int(t.w);
+        if (d < bd || (d == bd && ti < bi)) { bd = d; bi = ti; }
+    }
+}
+
+// One query against the grid.  Cells of a grid row (fixed y, z) are contiguous in the sorted array, so the search works
+// on rows: the home cell first, then the rows of growing Chebyshev rings in (y, z) around it.  A row is visited once, and
+// only the x-interval of it that can still hold a point at least as close as the current best (or the inlier radius) --
+// the pruning of a k-d tree descent, on a grid.  Ring r complete means every point within (r + m) cells of the query has
+// been seen, m = distance to the nearest y/z face of the home cell; the walk stops there once the best is that close.
+// All gap arithmetic is in cell units and shrunk by `slack` because cell assignment itself is rounded in float.
+struct RowPruner
+{
+    float fx, ay, az;       // x position in cell units; position inside the home cell along y, z
+    float inv_h2, r2cap, slack;
+    __device__ __forceinline__ float gap(float a, int d) const
+    {
+        if (d == 0) return 0.0f;
+        return fmaxf((d < 0 ? a : 1.0f - a) + (float)(abs(d) - 1) - slack, 0.0f);
+    }
+    // x-interval [xlo, xhi] of row (dy, dz) worth scanning given the best so far; false if none
+    __device__ __forceinline__ bool interval(int dy, int dz, float bd, int &xlo, int &xhi) const
+    {
+        const float gy = gap(ay, dy), gz = gap(az, dz);
+        const float rem = fminf(bd, r2cap) * inv_h2 - (gy * gy + gz * gz);
+        if (!(rem >= 0.0f)) return false;
+        const float half = sqrtf(rem) + slack;
+        xlo = (int)floorf(fx - half);
+        xhi = (int)floorf(fx + half);
+        return true;
+    }
+};
+
+__device__ int grid_nearest(const IcpGrid &g, const unsigned int *__restrict__ cell_start, const float4 *__restrict__ sorted, float qx,
+                            float qy, float qz, float radius)
+{
+    const float fx = (qx - g.origin[0]) * g.inv_h, fy = (qy - g.origin[1]) * g.inv_h, fz = (qz - g.origin[2]) * g.inv_h;
+    const float bound = (float)(1 << 20);
+    if (!(qx == qx && qy == qy && qz == qz && fabsf(fx) < bound && fabsf(fy) < bound && fabsf(fz) < bound)) return -1;
+    // home cell, not clamped: a query outside the grid starts where it is
+    const int hx = (int)floorf(fx), hy = (int)floorf(fy), hz = (int)floorf(fz);
+    RowPruner pr;
+    pr.fx = fx; pr.ay = fy - hy; pr.az = fz - hz;
+    pr.inv_h2 = g.inv_h * g.inv_h;
+    pr.r2cap = radius * radius; // a neighbour farther than this is reported as "none" anyway
+    pr.slack = 1e-3f;
+    float bd = __int_as_float(0x7f800000);
+    int bi = -1;
+    int xlo, xhi;
+    scan_cells(g, cell_start, sorted, hx, hx, hy, hz, qx, qy, qz, bd, bi);
+    // ring 0: the rest of the home row
+    if (pr.interval(0, 0, bd, xlo, xhi))
+    {
+        if (xlo < hx) scan_cells(g, cell_start, sorted, xlo, hx - 1, hy, hz, qx, qy, qz, bd, bi);
+        if (xhi > hx) scan_cells(g, cell_start, sorted, hx + 1, xhi, hy, hz, qx, qy, qz, bd, bi);
+    }
+    const float m_yz = fminf(fminf(pr.ay, 1.0f - pr.ay), fminf(pr.az, 1.0f - pr.az));
+    const float radius_cells = radius * g.inv_h;
+    const int r_max = (int)ceilf(radius_cells) + 1;
+    for (int r = 1; r <= r_max; ++r)
+    {
+        // everything within `covered` cells has been seen once ring r-1 is complete
+        const float covered = (float)(r - 1) + m_yz - pr.slack;
+        if (covered > 0.0f && bi >= 0 && bd * pr.inv_h2 <= covered * covered) break;
+        if (covered > radius_cells) break;
+        if (r == 1)
+        {
+            // the eight rows around the home row: lanes walk their own list of surviving rows (nearest first), so a warp
+            // iterates as often as its busiest lane has rows and every iteration scans different rows in different lanes
+            unsigned int mask = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b)
+            {
+                const int dy = (b == 0 || b == 4 || b == 5) ? -1 : ((b == 1 || b == 6 || b == 7) ? 1 : 0);
+                const int dz = (b == 2 || b == 4 || b == 6) ? -1 : ((b == 3 || b == 5 || b == 7) ? 1 : 0);
+                if (pr.interval(dy, dz, bd, xlo, xhi)) mask |= 1u << b;
+            }
+            while (mask)
+            {
+                const int b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                // bit b -> (dy, dz):  0:(-1,0) 1:(+1,0) 2:(0,-1) 3:(0,+1) 4:(-1,-1) 5:(-1,+1) 6:(+1,-1) 7:(+1,+1)
+                const int dy = (b == 0 || b == 4 || b == 5) ? -1 : ((b == 1 || b == 6 || b == 7) ? 1 : 0);
+                const int dz = (b == 2 || b == 4 || b == 6) ? -1 : ((b == 3 || b == 5 || b == 7) ? 1 : 0);
+                if (pr.interval(dy, dz, bd, xlo, xhi)) scan_cells(g, cell_start, sorted, xlo, xhi, hy + dy, hz + dz, qx, qy, qz, bd, bi);
+            }
+        }
+        else
+        {
+            for (int dz = -r; dz <= r; ++dz)
+                for (int dy = -r; dy <= r; dy += (abs(dz) == r ? 1 : 2 * r))
+                    if (pr.interval(dy, dz, bd, xlo, xhi)) scan_cells(g, cell_start, sorted, xlo, xhi, hy + dy, hz + dz, qx, qy, qz, bd, bi);
+        }
+    }
+    if (bi >= 0 && bd > pr.r2cap) return -1;
+    return bi;
+}
+
+// K7: exact nearest neighbour of every transformed source point, one thread per query
+__global__ void __launch_bounds__(kIcpThreads) icp_search_kernel(IcpArgs a)
+{
+    __shared__ float sT[16];
+    if (threadIdx.x < 16) sT[threadIdx.x] = a.st->T[threadIdx.x];
+    __syncthreads();
+    const IcpGrid g = a.st->grid;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.ns; i += gridDim.x * blockDim.x)
+    {
+        float px, py, pz;
+        transform_point(sT, a.src[3 * i], a.src[3 * i + 1], a.src[3 * i + 2], px, py, pz);
+        a.nn[i] = grid_nearest(g, a.cell_start, a.sorted, px, py, pz, a.search_radius);
+    }
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -364,115 +436,9 @@ __device__ __forceinline__ void warp_accumulate(double (*s_part)[kPacket], int w
     if (lane == 0) s_part[warp][k] += v;
 }
 
-// One pass over the source cloud: transform, exact nearest neighbour, CountInliers test, Jacobian row, and the
-// per-CTA partial sums of the 30-scalar packet.  Persistent grid (a multiple of the SM count), grid-stride over
-// the points; every warp keeps running totals in shared memory, CTAs write their partial packet in a fixed slot.
-__global__ void __launch_bounds__(kIcpThreads) icp_iteration_kernel(IcpArgs a)
+// the pose update of one iteration (ICP.cpp:78-86, 137-143, 198), run by one thread of the last CTA
+__device__ void icp_solve_and_update(const IcpArgs &a, IcpState *st)
 {
-    __shared__ double s_part[kIcpThreads / 32][kPacket];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane < 30) s_part[warp][lane] = 0.0;
-    __syncwarp();
-    const float *T = a.st->T; // column-major
-    const int stride = gridDim.x * blockDim.x;
-    // all lanes of a warp run the same number of trips (shuffles inside)
-    for (int base = blockIdx.x * blockDim.x + warp * 32; base < a.ns; base += stride)
-    {
-        const int i = base + lane;
-        bool inl = false;
-        float px = 0, py = 0, pz = 0, tx = 0, ty = 0, tz = 0;
-        double err = 0.0;
-        int j = -1;
-        if (i < a.ns)
-        {
-            const float sx = a.src[3 * i], sy = a.src[3 * i + 1], sz = a.src[3 * i + 2];
-            // geometry::TransformPoints: T * (x,y,z,1) then divide by w (Geometry.cpp:19-27)
-            const float w = row_xyz1(T[3], T[7], T[11], T[15], sx, sy, sz);
-            px = fdiv(row_xyz1(T[0], T[4], T[8], T[12], sx, sy, sz), w);
-            py = fdiv(row_xyz1(T[1], T[5], T[9], T[13], sx, sy, sz), w);
-            pz = fdiv(row_xyz1(T[2], T[6], T[10], T[14], sx, sy, sz), w);
-            j = grid_nearest(a.st->grid, a.cell_start, a.sorted, px, py, pz, a.search_radius);
-            a.nn[i] = j;
-            if (j >= 0)
-            {
-                tx = a.tgt[3 * j]; ty = a.tgt[3 * j + 1]; tz = a.tgt[3 * j + 2];
-                // CountInliers (ICP.cpp:19-21): (R*s + t - target).squaredNorm() in float, compared as double
-                const float ex = fsub(fadd(fadd(fmul(T[0], sx), fadd(fmul(T[4], sy), fmul(T[8], sz))), T[12]), tx);
-                const float ey = fsub(fadd(fadd(fmul(T[1], sx), fadd(fmul(T[5], sy), fmul(T[9], sz))), T[13]), ty);
-                const float ez = fsub(fadd(fadd(fmul(T[2], sx), fadd(fmul(T[6], sy), fmul(T[10], sz))), T[14]), tz);
-                err = (double)fadd(fmul(ex, ex), fadd(fmul(ey, ey), fmul(ez, ez)));
-                inl = err < a.sq_threshold;
-            }
-            if (a.final_pass) a.inlier[i] = inl;
-        }
-        if (!__any_sync(0xffffffffu, inl)) continue;
-        warp_accumulate(s_part, warp, lane, 28, inl ? err : 0.0);
-        warp_accumulate(s_part, warp, lane, 29, inl ? 1.0 : 0.0);
-        if (a.final_pass) continue;
-        if (a.nrm)
-        {
-            // EstimateRigidTransformationPointToPlane (ICP.cpp:121-136): row = [n ; s' x n], r = n.s' - n.t with
-            // s' the transformed source point; all in float like the reference, summed in double
-            float row[6] = {0, 0, 0, 0, 0, 0}, r = 0;
-            if (inl)
-            {
-                const float nx = a.nrm[3 * j], ny = a.nrm[3 * j + 1], nz = a.nrm[3 * j + 2];
-                r = fsub(dot3(nx, ny, nz, px, py, pz), dot3(nx, ny, nz, tx, ty, tz));
-                row[0] = nx; row[1] = ny; row[2] = nz;
-                row[3] = fsub(fmul(py, nz), fmul(pz, ny));
-                row[4] = fsub(fmul(pz, nx), fmul(px, nz));
-                row[5] = fsub(fmul(px, ny), fmul(py, nx));
-            }
-            int k = 0;
-#pragma unroll
-            for (int p = 0; p < 6; ++p)
-#pragma unroll
-                for (int q = p; q < 6; ++q) warp_accumulate(s_part, warp, lane, k++, (double)fmul(row[p], row[q]));
-#pragma unroll
-            for (int p = 0; p < 6; ++p) warp_accumulate(s_part, warp, lane, 21 + p, (double)fmul(r, row[p]));
-        }
-        else
-        {
-            // PointToPoint (ICP.cpp:78-84): Kabsch sums over (transformed source, target)
-            const double P[3] = {inl ? px : 0.0, inl ? py : 0.0, inl ? pz : 0.0}, Q[3] = {inl ? tx : 0.0, inl ? ty : 0.0, inl ? tz : 0.0};
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { warp_accumulate(s_part, warp, lane, c, P[c]); warp_accumulate(s_part, warp, lane, 3 + c, Q[c]); }
-#pragma unroll
-            for (int p = 0; p < 3; ++p)
-#pragma unroll
-                for (int q = 0; q < 3; ++q) warp_accumulate(s_part, warp, lane, 6 + 3 * p + q, P[p] * Q[q]);
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < 30)
-    {
-        double s = 0.0;
-        for (int w = 0; w < kIcpThreads / 32; ++w) s += s_part[w][threadIdx.x];
-        a.partials[(size_t)blockIdx.x * kPacket + threadIdx.x] = s;
-    }
-}
-
-// Sums the CTA partials in a fixed order, then solves and updates the pose (one CTA).
-__global__ void __launch_bounds__(kIcpThreads) icp_solve_kernel(IcpArgs a, int n_partials)
-{
-    __shared__ double s_part[kIcpThreads / 32][kPacket];
-    {
-        // 8 interleaved chains per component, then the chains in order: deterministic
-        const int k = threadIdx.x & 31, chain = threadIdx.x >> 5;
-        double s = 0.0;
-        for (int b = chain; b < n_partials; b += kIcpThreads / 32) s += a.partials[(size_t)b * kPacket + k];
-        s_part[chain][k] = s;
-        __syncthreads();
-        if (threadIdx.x < 30)
-        {
-            double tot = 0.0;
-            for (int c = 0; c < kIcpThreads / 32; ++c) tot += s_part[c][threadIdx.x];
-            a.st->packet[threadIdx.x] = tot;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    IcpState *st = a.st;
     st->sum_error = st->packet[28];
     st->n_inliers = (unsigned long long)(st->packet[29] + 0.5);
     if (a.final_pass) return;
@@ -504,6 +470,133 @@ __global__ void __launch_bounds__(kIcpThreads) icp_solve_kernel(IcpArgs a, int n
             Tn[c * 4 + r] = fadd(fadd(fadd(fmul(dTf[r], st->T[c * 4]), fmul(dTf[4 + r], st->T[c * 4 + 1])), fmul(dTf[8 + r], st->T[c * 4 + 2])),
                                  fmul(dTf[12 + r], st->T[c * 4 + 3]));
     for (int e = 0; e < 16; ++e) st->T[e] = Tn[e];
+}
+
+// K8: CountInliers test, Jacobian row and the 30-scalar packet over the pairs (i, nn[i]).  Per-thread double accumulators
+// -> warp shuffles -> one partial per CTA in a fixed slot; the last CTA to finish sums the partials in a fixed order
+// (deterministic), solves and updates the pose.  PLANE: point-to-plane rows, else the Kabsch sums of point-to-point.
+template <bool PLANE>
+__global__ void __launch_bounds__(kIcpThreads) icp_accumulate_kernel(IcpArgs a)
+{
+    __shared__ double s_part[kIcpThreads / 32][kPacket];
+    __shared__ float sT[16];
+    __shared__ bool s_last;
+    if (threadIdx.x < 16) sT[threadIdx.x] = a.st->T[threadIdx.x];
+    __syncthreads();
+    const float *T = sT; // column-major
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NA = PLANE ? 27 : 15;
+    double acc[NA], err_sum = 0.0, cnt = 0.0;
+#pragma unroll
+    for (int k = 0; k < NA; ++k) acc[k] = 0.0;
+    const bool sums = !a.final_pass;
+    const int *__restrict__ nn = a.nn;
+    const float *__restrict__ src = a.src;
+    const float *__restrict__ tgt = a.tgt;
+    const float *__restrict__ nrm = a.nrm;
+    // two points per trip: their index / coordinate loads are issued together (the trips are latency-bound gathers)
+#pragma unroll 2
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.ns; i += gridDim.x * blockDim.x)
+    {
+        const int j = __ldg(&nn[i]);
+        bool inl = false;
+        if (j >= 0)
+        {
+            const float sx = __ldg(&src[3 * i]), sy = __ldg(&src[3 * i + 1]), sz = __ldg(&src[3 * i + 2]);
+            const float tx = __ldg(&tgt[3 * j]), ty = __ldg(&tgt[3 * j + 1]), tz = __ldg(&tgt[3 * j + 2]);
+            // CountInliers (ICP.cpp:19-21): (R*s + t - target).squaredNorm() in float, compared as double
+            const float ex = fsub(fadd(fadd(fmul(T[0], sx), fadd(fmul(T[4], sy), fmul(T[8], sz))), T[12]), tx);
+            const float ey = fsub(fadd(fadd(fmul(T[1], sx), fadd(fmul(T[5], sy), fmul(T[9], sz))), T[13]), ty);
+            const float ez = fsub(fadd(fadd(fmul(T[2], sx), fadd(fmul(T[6], sy), fmul(T[10], sz))), T[14]), tz);
+            const double err = (double)fadd(fmul(ex, ex), fadd(fmul(ey, ey), fmul(ez, ez)));
+            inl = err < a.sq_threshold;
+            if (inl)
+            {
+                err_sum += err;
+                cnt += 1.0;
+                if (sums)
+                {
+                    float px, py, pz;
+                    transform_point(T, sx, sy, sz, px, py, pz);
+                    if (PLANE)
+                    {
+                        // EstimateRigidTransformationPointToPlane (ICP.cpp:121-136): row = [n ; s' x n], r = n.s' - n.t with
+                        // s' the transformed source point; all in float like the reference, summed in double
+                        const float nx = __ldg(&nrm[3 * j]), ny = __ldg(&nrm[3 * j + 1]), nz = __ldg(&nrm[3 * j + 2]);
+                        const float r = fsub(dot3(nx, ny, nz, px, py, pz), dot3(nx, ny, nz, tx, ty, tz));
+                        const float row[6] = {nx, ny, nz, fsub(fmul(py, nz), fmul(pz, ny)), fsub(fmul(pz, nx), fmul(px, nz)),
+                                              fsub(fmul(px, ny), fmul(py, nx))};
+                        int k = 0;
+#pragma unroll
+                        for (int p = 0; p < 6; ++p)
+#pragma unroll
+                            for (int q = p; q < 6; ++q) acc[k++] += (double)fmul(row[p], row[q]);
+#pragma unroll
+                        for (int p = 0; p < 6; ++p) acc[21 + p] += (double)fmul(r, row[p]);
+                    }
+                    else
+                    {
+                        // PointToPoint (ICP.cpp:78-84): Kabsch sums over (transformed source, target)
+                        const double P[3] = {px, py, pz}, Q[3] = {tx, ty, tz};
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) { acc[c] += P[c]; acc[3 + c] += Q[c]; }
+#pragma unroll
+                        for (int p = 0; p < 3; ++p)
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) acc[6 + 3 * p + q] += P[p] * Q[q];
+                    }
+                }
+            }
+        }
+        if (a.final_pass) a.inlier[i] = inl;
+    }
+    if (lane < 30) s_part[warp][lane] = 0.0;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < NA; ++k)
+    {
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) s_part[warp][k] = v;
+    }
+    err_sum = warp_sum(err_sum);
+    cnt = warp_sum(cnt);
+    if (lane == 0) { s_part[warp][28] = err_sum; s_part[warp][29] = cnt; }
+    __syncthreads();
+    if (threadIdx.x < 30)
+    {
+        double v = 0.0;
+        for (int w = 0; w < kIcpThreads / 32; ++w) v += s_part[w][threadIdx.x];
+        a.partials[(size_t)blockIdx.x * kPacket + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&a.st->blocks_done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    {
+        // 8 interleaved chains per component, then the chains in order: deterministic
+        const int k = threadIdx.x & 31, chain = threadIdx.x >> 5;
+        double v = 0.0;
+        if (k < 30)
+        {
+#pragma unroll 8
+            for (unsigned int b = chain; b < gridDim.x; b += kIcpThreads / 32) v += __ldcg(&a.partials[(size_t)b * kPacket + k]);
+        }
+        __syncthreads();
+        s_part[chain][k] = v;
+        __syncthreads();
+        if (threadIdx.x < 30)
+        {
+            double tot = 0.0;
+            for (int c = 0; c < kIcpThreads / 32; ++c) tot += s_part[c][threadIdx.x];
+            a.st->packet[threadIdx.x] = tot;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    a.st->blocks_done = 0;
+    icp_solve_and_update(a, a.st);
 }
 
 // final Kabsch sums over the inlier pairs of the ORIGINAL (unscaled) clouds (per-CTA partials, 16 components)
@@ -793,19 +886,22 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     a.sq_threshold = par->threshold * par->threshold;
     a.final_pass = 0; a.pairs = c->d_pairs; a.inlier = c->d_inlier;
     const int nb_need = (int)((ns + kIcpThreads - 1) / kIcpThreads);
-    const int nb_s = nb_need < c->sm_count * 4 ? nb_need : c->sm_count * 4; // persistent grid
-    for (int it = 0; it < par->max_iteration; ++it)
+    // developer knobs for grid-size sweeps (CTAs per SM); the defaults are the measured optimum on B200
+    static const int k_search = getenv("OPB_ICP_SEARCH_CTAS") ? atoi(getenv("OPB_ICP_SEARCH_CTAS")) : 8;
+    static const int k_accum = getenv("OPB_ICP_ACCUM_CTAS") ? atoi(getenv("OPB_ICP_ACCUM_CTAS")) : 2;
+    const int nb_s = nb_need < c->sm_count * k_search ? nb_need : c->sm_count * k_search; // search: grid-stride over the points
+    const int nb_a = nb_need < c->sm_count * k_accum ? nb_need : c->sm_count * k_accum;   // accumulate: few partials for the last CTA to sum
+    for (int it = 0; it <= par->max_iteration; ++it)
     {
-        icp_iteration_kernel<<<nb_s, kIcpThreads, 0, s>>>(a);
-        icp_solve_kernel<<<1, kIcpThreads, 0, s>>>(a, nb_s);
+        // the last pass is the final CountInliers with the final T (ICP.cpp:90-91,206-207)
+        a.final_pass = it == par->max_iteration;
+        icp_search_kernel<<<nb_s, kIcpThreads, 0, s>>>(a);
+        if (point_to_plane) icp_accumulate_kernel<true><<<nb_a, kIcpThreads, 0, s>>>(a);
+        else icp_accumulate_kernel<false><<<nb_a, kIcpThreads, 0, s>>>(a);
     }
-    // final CountInliers with the final T (ICP.cpp:90-91,206-207)
-    a.final_pass = 1;
-    icp_iteration_kernel<<<nb_s, kIcpThreads, 0, s>>>(a);
-    icp_solve_kernel<<<1, kIcpThreads, 0, s>>>(a, nb_s);
     OPB_CUDA(cudaMemcpyAsync(h, c->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
-    icp_final_sums_kernel<<<nb_s, kIcpThreads, 0, s>>>(c->d_src, c->d_tgt, c->d_nn, c->d_inlier, (int)ns, scaling, c->d_partials);
-    icp_final_reduce_kernel<<<1, kIcpThreads, 0, s>>>(c->d_partials, nb_s, c->d_state);
+    icp_final_sums_kernel<<<nb_a, kIcpThreads, 0, s>>>(c->d_src, c->d_tgt, c->d_nn, c->d_inlier, (int)ns, scaling, c->d_partials);
+    icp_final_reduce_kernel<<<1, kIcpThreads, 0, s>>>(c->d_partials, nb_a, c->d_state);
     if (pairs && pairs_cap) icp_compact_kernel<<<1, 1024, 0, s>>>(c->d_nn, c->d_inlier, (int)ns, c->d_pairs, (unsigned long long)pairs_cap);
     if (c->profiling) OPB_CUDA(cudaEventRecord(c->ev[2], s));
     OPB_CUDA(cudaGetLastError());

@@ -24,6 +24,16 @@ namespace opb
 {
 namespace linalg
 {
+// 1 / x, correctly rounded on both sides (the device intrinsic avoids the generic division routine: the solves below run
+// on a single thread at the end of every solver iteration, so their latency is on the critical path)
+OPB_HD double recip(double x)
+{
+#ifdef __CUDA_ARCH__
+    return __drcp_rn(x);
+#else
+    return 1.0 / x;
+#endif
+}
 // cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (row-major, n <= 6); A is destroyed,
 // eigenvalues end up on its diagonal, V holds the eigenvectors as columns
 template <int N>
@@ -93,46 +103,68 @@ OPB_HD void solve_sym6_pinv(const double *A_in, const double *b, double *x, doub
 }
 
 // x = A^-1 b by LDL^T when A (6x6 symmetric, row-major) is comfortably positive definite; returns false (x
-// untouched) when a pivot ratio suggests the rank decision of solve_sym6_pinv could matter
+// untouched) when a pivot ratio suggests the rank decision of solve_sym6_pinv could matter.  Every loop has a
+// compile-time trip count and is unrolled, so on the device L, D and y live in registers (this runs on ONE thread at
+// the end of every solver iteration: its latency is on the critical path of the whole loop).
 OPB_HD bool solve_sym6_ldlt(const double *A, const double *b, double *x)
 {
-    double L[36], D[6];
+    double L[36], D[6], invD[6];
     double dmax = 0.0, dmin = 1e300;
+#pragma unroll
     for (int j = 0; j < 6; ++j)
     {
         double d = A[j * 6 + j];
-        for (int k = 0; k < j; ++k) d -= L[j * 6 + k] * L[j * 6 + k] * D[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            if (k < j) d -= L[j * 6 + k] * L[j * 6 + k] * D[k];
         if (!(d > 0.0)) return false;
         D[j] = d;
         dmax = fmax(dmax, d);
         dmin = fmin(dmin, d);
-        for (int i = j + 1; i < 6; ++i)
-        {
-            double v = A[i * 6 + j];
-            for (int k = 0; k < j; ++k) v -= L[i * 6 + k] * L[j * 6 + k] * D[k];
-            L[i * 6 + j] = v / d;
-        }
+        const double inv_d = recip(d);
+        invD[j] = inv_d;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+            if (i > j)
+            {
+                double v = A[i * 6 + j];
+#pragma unroll
+                for (int k = 0; k < 6; ++k)
+                    if (k < j) v -= L[i * 6 + k] * L[j * 6 + k] * D[k];
+                L[i * 6 + j] = v * inv_d;
+            }
     }
     if (!(dmin > 1e-4 * dmax)) return false;
     double y[6];
+#pragma unroll
     for (int i = 0; i < 6; ++i)
     {
         double v = b[i];
-        for (int k = 0; k < i; ++k) v -= L[i * 6 + k] * y[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            if (k < i) v -= L[i * 6 + k] * y[k];
         y[i] = v;
     }
+#pragma unroll
     for (int i = 5; i >= 0; --i)
     {
-        double v = y[i] / D[i];
-        for (int k = i + 1; k < 6; ++k) v -= L[k * 6 + i] * x[k];
+        double v = y[i] * invD[i];
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            if (k > i) v -= L[k * 6 + i] * x[k];
         x[i] = v;
     }
     return true;
 }
-// the solve both solver loops use: direct when well conditioned, pseudo-inverse otherwise
+// the solve both solver loops use: direct when well conditioned, pseudo-inverse otherwise (kept out of line on the
+// device so that its dynamically indexed arrays do not drag the common path into local memory)
+#ifdef __CUDACC__
+__host__ __device__ __noinline__
+#endif
+inline void solve_sym6_pinv_cold(const double *A, const double *b, double *x) { solve_sym6_pinv(A, b, x); }
 OPB_HD void solve_normal_equations6(const double *A, const double *b, double *x)
 {
-    if (!solve_sym6_ldlt(A, b, x)) solve_sym6_pinv(A, b, x);
+    if (!solve_sym6_ldlt(A, b, x)) solve_sym6_pinv_cold(A, b, x);
 }
 
 // 4x4 row-major helpers
@@ -163,12 +195,14 @@ OPB_HD void se3_exp(const double *x, double *T)
     }
     else
     {
-        imag = sin(0.5 * theta) / theta;
-        real = cos(0.5 * theta);
+        double sh, ch;
+        sincos(0.5 * theta, &sh, &ch);
+        imag = sh * recip(theta);
+        real = ch;
     }
     double qw = real, qx = imag * wx, qy = imag * wy, qz = imag * wz;
-    const double qn = sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
-    qw /= qn; qx /= qn; qy /= qn; qz /= qn;
+    const double inv_qn = recip(sqrt(qw * qw + qx * qx + qy * qy + qz * qz));
+    qw *= inv_qn; qx *= inv_qn; qy *= inv_qn; qz *= inv_qn;
     double R[9] = {1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw),
                    2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw),
                    2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)};
@@ -187,7 +221,10 @@ OPB_HD void se3_exp(const double *x, double *T)
         for (int i = 0; i < 9; ++i) V[i] = R[i]; // Sophus uses V = R in the small-angle branch
     else
     {
-        const double a = (1.0 - cos(theta)) / theta_sq, b = (theta - sin(theta)) / (theta_sq * theta);
+        double st, ct;
+        sincos(theta, &st, &ct);
+        const double inv_t2 = recip(theta_sq);
+        const double a = (1.0 - ct) * inv_t2, b = (theta - st) * inv_t2 * recip(theta);
         for (int i = 0; i < 9; ++i) V[i] = (i % 4 == 0 ? 1.0 : 0.0) + a * O[i] + b * O2[i];
     }
     for (int i = 0; i < 3; ++i)

@@ -61,6 +61,7 @@ struct OdoState // device-resident solver state
     int n_pairs;          // result of the last ordered compaction
     float mean_src, mean_tgt; // NormalizeIntensity
     double rmse_sum;
+    unsigned long long tail_ns; // profiling: time the last CTA spent summing partials + solving, accumulated over the call
     int trace_count[kMaxTrace];
     float trace_T[kMaxTrace][16];
 };
@@ -432,12 +433,17 @@ __global__ void __launch_bounds__(kOdoThreads) odo_iteration_kernel(OdoArgs a)
     if (threadIdx.x == 0) s_last = atomicAdd(&a.st->blocks_done, 1u) == gridDim.x - 1;
     __syncthreads();
     if (!s_last) return;
+    unsigned long long t_tail = 0;
+    if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_tail));
     __threadfence();
     {
         const int k = threadIdx.x & 31, chain = threadIdx.x >> 5;
         double v = 0.0;
         if (k < 29)
+        {
+#pragma unroll 8
             for (unsigned int b = chain; b < gridDim.x; b += kOdoThreads / 32) v += __ldcg(&a.partials[(size_t)b * kOdoPacket + k]);
+        }
         s_part[chain][k] = v;
         __syncthreads();
         if (threadIdx.x < 29)
@@ -452,6 +458,9 @@ __global__ void __launch_bounds__(kOdoThreads) odo_iteration_kernel(OdoArgs a)
     a.st->blocks_done = 0;
     if (MODE == 0) solve_and_update(a, a.st);
     else a.st->last_count = (int)(a.st->packet[28] + 0.5);
+    unsigned long long t_end;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+    a.st->tail_ns += t_end - t_tail;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -528,42 +537,172 @@ __global__ void __launch_bounds__(1024) odo_compact_kernel(const unsigned char *
 // ---------------------------------------------------------------------------------------------------------
 // NormalizeIntensity: the reference's means are SEQUENTIAL float32 sums over the correspondence list
 // (DenseOdometryFunction.cpp:131-141); 0.5 / mean then scales the image, so the sum has to be reproduced bit for bit.
-// One warp per image: lanes fetch 32 values at a time (coalesced gathers, independent of the sum), every lane then
-// adds them in list order -- the dependent chain is one FADD per element.
+//
+// One CTA per image.  All warps gather the next chunk of values (list order) into shared memory while warp 0 folds the
+// current chunk into the running sum S, 32 values per step.  A step is exact without 32 dependent additions whenever S
+// stays inside its binade [2^e, 2^(e+1)): there fl(S + x) = S + U * rne(x / U) with U = ulp(S) = 2^(e-23), because S is
+// a multiple of U -- so the 32 roundings are independent, their integer sum is a shuffle reduction, and S advances by
+// one exact integer add.  Steps that cross a binade, hit a rounding tie (whose direction depends on the parity of the
+// running sum) or see a negative / non-finite value take the literal path: 32 dependent float additions in list order.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) odo_sequential_mean_kernel(const uint4 *__restrict__ pairs, OdoState *st, const float *__restrict__ sgray,
-                                                                 const float *__restrict__ tgray, int w)
+constexpr int kMeanThreads = 1024;
+constexpr int kMeanChunk = 4096;
+constexpr int kMeanSteps = kMeanChunk / 32; // 128 steps of 32 values per chunk, 4 per warp
+
+__device__ __forceinline__ float sequential_add32(float sum, float v, int count)
 {
-    const int which = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = st->n_pairs;
-    const float *img = which ? tgray : sgray;
-    float sum = 0.0f;
-    float next = 0.0f;
-    if (lane < n)
+    if (count == 32)
     {
-        const uint4 p = pairs[lane];
-        next = which ? img[p.z * w + p.w] : img[p.x * w + p.y];
-    }
-    for (int base = 0; base < n; base += 32)
-    {
-        const float v = next;
-        const int i = base + 32 + lane;
-        next = 0.0f;
-        if (i < n)
-        {
-            const uint4 p = pairs[i];
-            next = which ? img[p.z * w + p.w] : img[p.x * w + p.y];
-        }
-        const int m = n - base < 32 ? n - base : 32;
-        if (m == 32)
-        {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) sum = fadd(sum, __shfl_sync(0xffffffffu, v, k));
-        }
-        else
-            for (int k = 0; k < m; ++k) sum = fadd(sum, __shfl_sync(0xffffffffu, v, k));
+        for (int k = 0; k < 32; ++k) sum = fadd(sum, __shfl_sync(0xffffffffu, v, k));
     }
-    if (lane == 0)
+    else
+        for (int k = 0; k < count; ++k) sum = fadd(sum, __shfl_sync(0xffffffffu, v, k));
+    return sum;
+}
+// the binade of a running sum as its biased exponent, or -1 when the shortcut does not apply (zero, tiny, huge, negative, NaN)
+__device__ __forceinline__ int binade_of(float sum)
+{
+    const unsigned int sb = __float_as_uint(sum);
+    const int e = (int)(sb >> 23) & 0xff;
+    return (e >= 64 && e <= 200 && !(sb >> 31)) ? e : -1;
+}
+// 32 values against the binade e: the integer number of ulps they add (warp-uniform), or -1 if any lane needs the literal path
+__device__ __forceinline__ int ulps_of_step(float x, int e)
+{
+    const float inv_u = __uint_as_float((unsigned int)(277 - e) << 23); // 2^(23 - (e - 127))
+    const float mq = x * inv_u;                                         // exact power-of-two scaling
+    const float r = rintf(mq);
+    const bool lane_ok = e >= 0 && x >= 0.0f && mq < 16777216.0f && fabsf(mq - r) != 0.5f;
+    int t = lane_ok ? (int)r : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o); // < 2^29
+    return __all_sync(0xffffffffu, lane_ok) ? t : -1;
+}
+// sum advanced by `ulps` units of its binade e (exact); false if that would leave the binade
+__device__ __forceinline__ bool advance_in_binade(float &sum, int e, int ulps)
+{
+    const int si = (int)(sum * __uint_as_float((unsigned int)(277 - e) << 23)); // exact: in [2^23, 2^24)
+    const int sn = si + ulps;
+    if (ulps < 0 || sn > (1 << 24)) return false;
+    sum = (float)sn * __uint_as_float((unsigned int)(e - 23) << 23); // exact
+    return true;
+}
+
+__global__ void __launch_bounds__(kMeanThreads) odo_sequential_mean_kernel(const uint4 *__restrict__ pairs, OdoState *st,
+                                                                           const float *__restrict__ sgray, const float *__restrict__ tgray, int w)
+{
+    __shared__ float buf[2][kMeanChunk];
+    __shared__ int s_tot[kMeanSteps];
+    __shared__ float s_sum;
+    const int which = blockIdx.x; // 0: source image at (v_s, u_s), 1: target image at (v_t, u_t)
+    const float *img = which ? tgray : sgray;
+    const int n = st->n_pairs;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int PER = kMeanChunk / kMeanThreads;
+    float regs[PER];
+    auto gather = [&](int chunk) {
+#pragma unroll
+        for (int k = 0; k < PER; ++k)
+        {
+            const int i = chunk * kMeanChunk + k * kMeanThreads + threadIdx.x;
+            float v = 0.0f;
+            if (i < n)
+            {
+                const uint4 p = pairs[i];
+                v = which ? img[p.z * w + p.w] : img[p.x * w + p.y];
+            }
+            regs[k] = v;
+        }
+    };
+    auto stash = [&](int b) {
+#pragma unroll
+        for (int k = 0; k < PER; ++k) buf[b][k * kMeanThreads + threadIdx.x] = regs[k];
+    };
+    const int n_chunks = (n + kMeanChunk - 1) / kMeanChunk;
+    float sum = 0.0f; // meaningful in warp 0
+    if (threadIdx.x == 0) s_sum = 0.0f;
+    if (n_chunks > 0)
+    {
+        gather(0);
+        stash(0);
+    }
+    __syncthreads();
+    for (int c = 0; c < n_chunks; ++c)
+    {
+        if (c + 1 < n_chunks) gather(c + 1); // loads in flight during this chunk
+        const float *cur = buf[c & 1];
+        const int m = min(kMeanChunk, n - c * kMeanChunk);
+        const int n_steps = (m + 31) / 32;
+        // every warp: the ulp totals of its four steps, speculating that the sum stays in the binade it has now
+        const int e_spec = binade_of(s_sum);
+#pragma unroll
+        for (int q = 0; q < kMeanSteps / (kMeanThreads / 32); ++q)
+        {
+            const int step = warp * (kMeanSteps / (kMeanThreads / 32)) + q;
+            const int idx = step * 32 + lane;
+            const int t = ulps_of_step(idx < m ? cur[idx] : 0.0f, e_spec);
+            if (lane == 0) s_tot[step] = t;
+        }
+        __syncthreads();
+        if (warp == 0)
+        {
+            // prefix over the 128 step totals: apply as many leading steps as stay valid in one exact integer add
+            int tot[4], local = 0;
+            bool bad_seen = false;
+            int good[4]; // running in-lane prefix, valid while no bad step was seen
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+            {
+                const int step = lane * 4 + q;
+                tot[q] = step < n_steps ? s_tot[step] : 0;
+                bad_seen = bad_seen || tot[q] < 0;
+                local += tot[q] < 0 ? 0 : tot[q];
+                good[q] = local;
+            }
+            int inc = local;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            const int before = inc - local; // ulps of all steps of earlier lanes
+            const int si0 = e_spec >= 0 ? (int)(sum * __uint_as_float((unsigned int)(277 - e_spec) << 23)) : 0;
+            // first step (in this lane) that cannot be applied in bulk
+            int first_fail = 4;
+#pragma unroll
+            for (int q = 3; q >= 0; --q)
+                if (tot[q] < 0 || e_spec < 0 || (long long)si0 + before + good[q] > (1 << 24)) first_fail = q;
+            const unsigned int fail_mask = __ballot_sync(0xffffffffu, first_fail < 4 && lane * 4 + first_fail < n_steps);
+            int f = n_steps; // first step to handle one by one
+            int applied = 0; // ulps of the steps before f
+            if (fail_mask)
+            {
+                const int fl = __ffs(fail_mask) - 1;
+                const int fq = __shfl_sync(0xffffffffu, first_fail, fl);
+                f = fl * 4 + fq;
+                const int g = fq > 0 ? good[fq - 1] : 0; // only meaningful on lane fl
+                applied = __shfl_sync(0xffffffffu, before + g, fl);
+            }
+            else
+                applied = __shfl_sync(0xffffffffu, inc, 31);
+            if (e_spec >= 0 && f > 0) advance_in_binade(sum, e_spec, applied);
+            // the rest of the chunk step by step: own binade per step, literal 32 additions when the shortcut fails
+            for (int step = f; step < n_steps; ++step)
+            {
+                const int idx = step * 32 + lane;
+                const float x = idx < m ? cur[idx] : 0.0f;
+                const int e = binade_of(sum);
+                const int t = ulps_of_step(x, e);
+                if (!(e >= 0 && advance_in_binade(sum, e, t))) sum = sequential_add32(sum, x, min(32, m - step * 32));
+            }
+            if (lane == 0) s_sum = sum;
+        }
+        if (c + 1 < n_chunks) stash((c + 1) & 1);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
     {
         const float mean = fdiv(sum, (float)n); // mean /= (float)correspondence.size()
         if (which) st->mean_tgt = mean; else st->mean_src = mean;
@@ -774,10 +913,11 @@ int opb_odometry_set_profiling(opb_odometry *o, int on)
     o->profiling = on != 0;
     return OPB_OK;
 }
-int opb_odometry_last_timing(opb_odometry *o, float *tracking_ms)
+int opb_odometry_last_timing(opb_odometry *o, float *tracking_ms, float *solve_tail_us)
 {
     if (!o) { set_error("odometry is NULL"); return OPB_ERR_INVALID; }
     if (tracking_ms) *tracking_ms = o->last_ms;
+    if (solve_tail_us) *solve_tail_us = o->h_state->iteration > 0 ? (float)o->h_state->tail_ns * 1e-3f / (float)(o->h_state->iteration + 1) : 0.0f;
     return OPB_OK;
 }
 
@@ -913,7 +1053,7 @@ static void launch_normalize(opb_odometry *o, opb_frame *S, opb_frame *T)
     launch_iteration(o, a, true);
     launch_compaction(o, 0);
     cudaStream_t s = o->stream;
-    odo_sequential_mean_kernel<<<1, 64, 0, s>>>(o->d_pairs, o->d_state, S->im.img[0][0], T->im.img[0][0], o->cams[0].w);
+    odo_sequential_mean_kernel<<<2, kMeanThreads, 0, s>>>(o->d_pairs, o->d_state, S->im.img[0][0], T->im.img[0][0], o->cams[0].w);
     const int n = (int)level_pixels(o, 0);
     odo_scale_kernel<<<grid_for(o, n), kOdoThreads, 0, s>>>(S->im.img[0][0], T->im.img[0][0], n, o->d_state);
 }

@@ -110,8 +110,9 @@ class Odometry:
         capi.check(capi.lib.opb_odometry_set_profiling(self.handle, int(on)))
 
     def last_tracking_ms(self):
-        ms = C.c_float(0)
-        capi.check(capi.lib.opb_odometry_last_timing(self.handle, C.byref(ms)))
+        ms, tail = C.c_float(0), C.c_float(0)
+        capi.check(capi.lib.opb_odometry_last_timing(self.handle, C.byref(ms), C.byref(tail)))
+        self.last_solve_tail_us = tail.value
         return ms.value
 
     def _result(self, res, pairs, xyz):

@@ -1,4 +1,5 @@
-// Reads like example/ImageSequenceIntegration.cpp:20-53 and example/ICPTest.cpp:14-34 of the reference, minus
+// Reads like example/ImageSequenceIntegration.cpp:20-53, example/ICPTest.cpp:14-34 and example/DenseOdometry.cpp:14-31 of the
+// reference, minus
 // file IO and the viewer: the reference's caller code compiled UNCHANGED against the drop-in classes of
 // onepiece_b200/cpp.  Inputs come from raw binary files written by tests/test_dropin_cpp.py; results are written
 // back as raw binary for comparison with the oracle.
@@ -8,7 +9,9 @@
 
 #include "Geometry/PointCloud.h"
 #include "Geometry/TriangleMesh.h"
+#include "Geometry/RGBDFrame.h"
 #include "Integration/CubeHandler.h"
+#include "Odometry/Odometry.h"
 #include "Registration/ICP.h"
 
 using namespace one_piece;
@@ -93,7 +96,36 @@ int main(int argc, char **argv)
     icp_out.push_back(result->rmse);
     icp_out.push_back((double)result->correspondence_set_index.size());
     WriteAll(dir + "/icp.bin", icp_out);
+    // --- example/DenseOdometry.cpp:14-31 (+ the chained use of example/DenseFusion/DenseSlam.cpp:22) ---------
+    odometry::Odometry rgbd_odometry(camera);
+    std::vector<double> odo_out;
+    {
+        std::vector<unsigned short> sd = ReadAll<unsigned short>(dir + "/odo_depth1.bin"), td = ReadAll<unsigned short>(dir + "/odo_depth0.bin");
+        std::vector<unsigned char> sc = ReadAll<unsigned char>(dir + "/odo_bgr1.bin"), tc = ReadAll<unsigned char>(dir + "/odo_bgr0.bin");
+        cv::Mat source_rgb(H, W, CV_8UC3, sc.data()), source_depth(H, W, CV_16UC1, sd.data());
+        cv::Mat target_rgb(H, W, CV_8UC3, tc.data()), target_depth(H, W, CV_16UC1, td.data());
+        geometry::RGBDFrame source_frame(source_rgb, source_depth);
+        geometry::RGBDFrame target_frame(target_rgb, target_depth);
+        geometry::Matrix4 T = geometry::Matrix4::Identity();
+        for (int call = 0; call < 2; ++call) // the second call re-normalises the cached frames, like the reference
+        {
+            auto tracking_result = rgbd_odometry.DenseTracking(source_frame, target_frame, T, 0);
+            for (int r = 0; r < 4; ++r)
+                for (int c = 0; c < 4; ++c) odo_out.push_back(tracking_result->T(r, c));
+            odo_out.push_back(tracking_result->rmse);
+            odo_out.push_back((double)tracking_result->pixel_correspondence_set.size());
+            odo_out.push_back(tracking_result->tracking_success ? 1.0 : 0.0);
+            odo_out.push_back((double)tracking_result->correspondence_set.size());
+            odo_out.push_back(source_frame.IsPreprocessedDense() && target_frame.IsPreprocessedDense() ? 1.0 : 0.0);
+        }
+        auto mat_result = rgbd_odometry.DenseTracking(source_rgb, target_rgb, source_depth, target_depth, T, 0);
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) odo_out.push_back(mat_result->T(r, c));
+        odo_out.push_back(mat_result->rmse);
+        odo_out.push_back((double)mat_result->pixel_correspondence_set.size());
+    }
+    WriteAll(dir + "/odometry.bin", odo_out);
     std::cout << "dropin ok: " << m.size() << " cubes, " << mesh.triangles.size() << " triangles, "
-              << result->correspondence_set_index.size() << " ICP inliers" << std::endl;
+              << result->correspondence_set_index.size() << " ICP inliers, " << (size_t)odo_out[17] << " odometry correspondences" << std::endl;
     return 0;
 }

@@ -45,6 +45,11 @@ def test_reference_caller_code_runs_on_the_gpu(tmp_path):
     tgt, src = scenes.backproject(d0, cam), scenes.backproject(d1, cam)
     nrm = np.ascontiguousarray(n0.reshape(-1, 3))
     src.tofile(tmp_path / "src.bin"); tgt.tofile(tmp_path / "tgt.bin"); nrm.tofile(tmp_path / "nrm.bin")
+    # example/DenseOdometry.cpp inputs: two S2 frames (uint16 depth, like a sensor)
+    _, c0_bgr, _ = scenes.room(cam, 0)
+    _, c1_bgr, _ = scenes.room(cam, 3)
+    d0.tofile(tmp_path / "odo_depth0.bin"); c0_bgr.tofile(tmp_path / "odo_bgr0.bin")
+    d1.tofile(tmp_path / "odo_depth1.bin"); c1_bgr.tofile(tmp_path / "odo_bgr1.bin")
     out = subprocess.run([BIN, str(tmp_path), str(n_frames)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "dropin ok" in out.stdout
@@ -63,6 +68,17 @@ def test_reference_caller_code_runs_on_the_gpu(tmp_path):
     o = oracleapi.icp(src, tgt, nrm, np.eye(4), 10, 0.05)
     assert np.linalg.norm(icp[:16].reshape(4, 4)[:3, 3] - o["T"][:3, 3]) < 1e-5
     assert int(icp[17]) == len(o["pairs"])
+    # Odometry::DenseTracking through the drop-in: two chained calls on the same RGBDFrames, then the cv::Mat overload
+    odo = np.fromfile(tmp_path / "odometry.bin", np.float64)
+    S, T = oracleapi.OracleFrame(c1_bgr, d1), oracleapi.OracleFrame(c0_bgr, d0)
+    for call in range(2):
+        o = oracleapi.dense_tracking_frames(S, T, cam, np.eye(4), 0)
+        rec = odo[call * 21:(call + 1) * 21]
+        assert np.abs(rec[:16].reshape(4, 4) - o["T"]).max() < 1e-6, f"DenseTracking call {call}"
+        assert abs(rec[16] - o["rmse"]) < 1e-7 and int(rec[17]) == len(o["pairs"]) and bool(rec[18]) == o["success"]
+        assert int(rec[19]) == len(o["pairs"]) and rec[20] == 1.0
+    om = oracleapi.dense_tracking(c1_bgr, c0_bgr, d1, d0, cam, np.eye(4), 0)
+    assert np.abs(odo[42:58].reshape(4, 4) - om["T"]).max() < 1e-6 and int(odo[59]) == len(om["pairs"])
     # the .cubes file the drop-in wrote has the reference's layout: [u32 n_cubes] then per cube 3 id floats ... -2
     raw = np.fromfile(tmp_path / "volume.cubes", np.float32)
     assert raw[:1].view(np.uint32)[0] == len(oi) and (raw == -2.0).sum() >= len(oi)
