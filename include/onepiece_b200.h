@@ -154,6 +154,23 @@ int opb_volume_extract_mesh(opb_volume *v, float **xyz, float **rgb, uint32_t **
 /* counts only (no download) */
 int opb_volume_count_mesh(opb_volume *v, size_t *nv, size_t *nt);
 
+/* Marching Cubes over a volume partitioned across GPUs (no counterpart in the single-process
+ * reference, whose GenerateMeshByCube reads the +x/+y/+z neighbour cubes from the same map, CubeHandler.cpp:83-99).
+ * With sub-volume ownership (shard_* above) the +1 neighbours of the cubes in the last layer of a slab live on the owner
+ * of the next slab.  Before extracting its part of the mesh every rank
+ *   1. exports the cubes in the FIRST layer of its slabs: ids (3 x int32 per cube) and the one voxel layer Marching Cubes
+ *      reads from them (axis coordinate 0; 5 planes sdf, weight, c0, c1, c2 x 64 voxels = 320 floats per cube),
+ *   2. sends both buffers to rank-1 and receives those of rank+1 (mod world; the host program's transport -- NCCL
+ *      send/recv on the device buffers in onepiece_b200/fusion.py),
+ *   3. imports what it received as ghost cubes: visible to the mesh kernels as neighbours only; never integrated,
+ *      downloaded or meshed themselves.  Ghosts are dropped by opb_volume_halo_clear and by the next integrate / upload /
+ *      clear.
+ * ids / layers may be host or device pointers.  Export with ids == layers == NULL only counts (*n). */
+int opb_volume_halo_export(opb_volume *v, int32_t *ids, float *layers, size_t cap_cubes, size_t *n);
+int opb_volume_halo_import(opb_volume *v, const int32_t *ids, const float *layers, size_t n);
+int opb_volume_halo_clear(opb_volume *v);
+int opb_volume_num_ghost_cubes(opb_volume *v, size_t *n);
+
 /* ------------------------------------------------------------------------------------------------------
  * ICP  (replaces one_piece::registration::PointToPlane / PointToPoint, src/Registration/ICP.h:23-26,
  *       src/Registration/ICP.cpp:31-224)
@@ -178,6 +195,8 @@ typedef struct
     size_t n_inliers;     /* correspondence_set_index.size() */
     int32_t iterations;
     int32_t status;       /* OPB_OK, or the error the reference reports by returning a default result */
+    size_t n_local_pairs; /* pairs written by this call: n_inliers, or this rank's share of them when the source
+                             cloud is split across ranks (opb_icp_comm_attach) */
 } opb_icp_result;
 
 void opb_icp_params_default(opb_icp_params *p);
@@ -193,6 +212,24 @@ int opb_icp_point_to_plane(opb_icp *c, const float *src_xyz, size_t ns, const fl
 int opb_icp_point_to_point(opb_icp *c, const float *src_xyz, size_t ns, const float *tgt_xyz, size_t nt,
                            const float init_T_colmajor[16], const opb_icp_params *params, opb_icp_result *result,
                            int32_t *pairs, size_t pairs_cap);
+/* One registration over several GPUs (no counterpart in the reference).  The source points are split
+ * across the ranks, every rank holds the whole target; each iteration every rank reduces its share to the 30-scalar packet
+ * (21 J^T J + 6 J^T r + 2 error + count) and the packets are summed across ranks inside the reduction kernel's last CTA through
+ * peer memory: plain stores into every peer's mailbox over NVLink, a flag, a bounded wait, a fixed-order sum.  All ranks then
+ * solve the identical 6x6 system, so T, rmse and n_inliers of the result are global and identical on every rank; pairs holds
+ * the rank's own inliers with LOCAL source indices (n_local_pairs of them).  Setup, once per workspace:
+ *   1. opb_icp_comm_buffer  -> this rank's mailbox: device pointer and cudaIpc handle (64 bytes to send to the peers)
+ *   2. peers in other processes open the handle with opb_ipc_open; workspaces of the same process use the pointer itself
+ *   3. opb_icp_comm_attach(rank, world, buffers) on every rank, buffers[r] = mailbox of rank r as visible from this process
+ * Afterwards opb_icp_point_to_plane / opb_icp_point_to_point are COLLECTIVE calls: every rank must make them in the same
+ * order with its share of the source and identical target, init_T and params (a missing peer makes the call fail with
+ * OPB_ERR_CUDA after 4 s instead of hanging).  A rank's share may be empty. */
+#define OPB_IPC_HANDLE_BYTES 64
+int opb_icp_comm_buffer(opb_icp *c, void **d_buffer, unsigned char ipc_handle[OPB_IPC_HANDLE_BYTES]);
+int opb_ipc_open(int device, const unsigned char ipc_handle[OPB_IPC_HANDLE_BYTES], void **d_ptr);
+int opb_ipc_close(int device, void *d_ptr);
+int opb_icp_comm_attach(opb_icp *c, int rank, int world, void *const *buffers);
+int opb_icp_comm_detach(opb_icp *c);
 /* nearest-neighbour index per source point from the last search of the previous call (-1: none within the
  * threshold), for parity tests against KDTree::KnnSearch */
 int opb_icp_last_nn(opb_icp *c, int32_t *nn, size_t n);

@@ -56,7 +56,7 @@ class IcpParams(C.Structure):
 
 class IcpResult(C.Structure):
     _fields_ = [("T", C.c_float * 16), ("T_iterated", C.c_float * 16), ("rmse", C.c_double), ("n_inliers", C.c_size_t),
-                ("iterations", C.c_int32), ("status", C.c_int32)]
+                ("iterations", C.c_int32), ("status", C.c_int32), ("n_local_pairs", C.c_size_t)]
 
 
 OPB_ODO_MAX_LEVELS = 6
@@ -111,11 +111,20 @@ SIGNATURES = {
     "opb_volume_upload": (C.c_int, [_p, _p, _p, _sz]),
     "opb_volume_extract_mesh": (C.c_int, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_sz), C.POINTER(_sz)]),
     "opb_volume_count_mesh": (C.c_int, [_p, C.POINTER(_sz), C.POINTER(_sz)]),
+    "opb_volume_halo_export": (C.c_int, [_p, _p, _p, _sz, C.POINTER(_sz)]),
+    "opb_volume_halo_import": (C.c_int, [_p, _p, _p, _sz]),
+    "opb_volume_halo_clear": (C.c_int, [_p]),
+    "opb_volume_num_ghost_cubes": (C.c_int, [_p, C.POINTER(_sz)]),
     "opb_icp_params_default": (None, [C.POINTER(IcpParams)]),
     "opb_icp_create": (C.c_int, [C.c_int, _p, C.POINTER(_p)]),
     "opb_icp_destroy": (None, [_p]),
     "opb_icp_point_to_plane": (C.c_int, [_p, _p, _sz, _p, _p, _sz, _p, C.POINTER(IcpParams), C.POINTER(IcpResult), _p, _sz]),
     "opb_icp_point_to_point": (C.c_int, [_p, _p, _sz, _p, _sz, _p, C.POINTER(IcpParams), C.POINTER(IcpResult), _p, _sz]),
+    "opb_icp_comm_buffer": (C.c_int, [_p, C.POINTER(_p), _p]),
+    "opb_ipc_open": (C.c_int, [C.c_int, _p, C.POINTER(_p)]),
+    "opb_ipc_close": (C.c_int, [C.c_int, _p]),
+    "opb_icp_comm_attach": (C.c_int, [_p, C.c_int, C.c_int, _p]),
+    "opb_icp_comm_detach": (C.c_int, [_p]),
     "opb_icp_last_nn": (C.c_int, [_p, _p, _sz]),
     "opb_icp_set_profiling": (C.c_int, [_p, C.c_int]),
     "opb_icp_last_timing": (C.c_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

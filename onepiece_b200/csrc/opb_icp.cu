@@ -51,7 +51,76 @@ struct IcpState // device-resident solver state
     unsigned long long n_inliers;
     double sum_error;
     unsigned int blocks_done;
+    unsigned long long n_inliers_local; // this rank's share when the source is split across ranks (== n_inliers otherwise)
 };
+
+// ---------------------------------------------------------------------------------------------------------
+// cross-GPU exchange of the reduction packet: when the source points of one registration are split
+// across ranks, every rank reduces its share to the same 30-scalar packet and the packets are summed across ranks INSIDE the
+// reduction kernel's tail -- the last CTA stores its packet into every peer's mailbox over NVLink (plain peer stores into
+// cudaIpc-mapped memory), raises a flag there, waits for the flags of all ranks in its own mailbox, adds the packets in rank
+// order (so every rank gets the bit-identical sum and solves the identical 6x6 system redundantly) and goes on to the solve.
+// No NCCL call, no host round trip: the 31 iterations of a call stay one uninterrupted stream of launches.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kMaxRanks = 16;
+struct IcpMailbox
+{
+    unsigned long long flag[2][kMaxRanks];   // [parity of the exchange number][writer rank] = exchange number
+    double data[2][kMaxRanks][kPacket];      // [parity][writer rank][component]
+    unsigned long long epoch;                // exchanges completed by the owner of this mailbox (local use only)
+    int error;                               // set when a peer did not answer within the time limit
+};
+struct IcpComm
+{
+    IcpMailbox *box[kMaxRanks]; // box[rank] is this rank's own mailbox, the others are peer mappings
+    int rank, world;
+};
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Sum of packet[0..n) over all ranks, in rank order; called by every thread of ONE CTA (>= 32 threads) on every rank the same
+// number of times.  Two mailbox halves alternate: a rank can be at most one exchange ahead of a peer, because finishing an
+// exchange needs the peer's packet of that exchange.
+__device__ void comm_allreduce(const IcpComm &cm, double *packet, int n)
+{
+    if (cm.world <= 1) return;
+    IcpMailbox *mine = cm.box[cm.rank];
+    __shared__ unsigned long long s_epoch;
+    if (threadIdx.x == 0) s_epoch = mine->epoch + 1;
+    __syncthreads();
+    const unsigned long long ep = s_epoch;
+    const int par = (int)(ep & 1);
+    for (int idx = threadIdx.x; idx < cm.world * n; idx += blockDim.x)
+    {
+        const int r = idx / n, k = idx - r * n;
+        cm.box[r]->data[par][cm.rank][k] = packet[k];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < cm.world)
+    {
+        *(volatile unsigned long long *)&cm.box[threadIdx.x]->flag[par][cm.rank] = ep;
+        volatile unsigned long long *f = &mine->flag[par][threadIdx.x];
+        const unsigned long long t0 = global_timer_ns();
+        while (*f < ep) // 4 s: a peer died or never made the call; once that happened the call is lost, do not wait again
+            if (*(volatile int *)&mine->error || global_timer_ns() - t0 > 4000000000ull) { mine->error = 1; break; }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < n)
+    {
+        double s = 0.0;
+        for (int r = 0; r < cm.world; ++r) s += *(volatile double *)&mine->data[par][r][threadIdx.x];
+        packet[threadIdx.x] = s;
+    }
+    if (threadIdx.x == 0) mine->epoch = ep;
+    __syncthreads();
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // grid construction
@@ -284,6 +353,7 @@ struct IcpArgs
     int final_pass;         // 1: only CountInliers (rmse + pairs), no solve
     int *pairs;             // final pass: inlier flags are turned into pairs by the compaction kernel
     unsigned char *inlier;  // ns flags
+    IcpComm comm;           // world <= 1: single GPU
 };
 
 // geometry::TransformPoints: T * (x,y,z,1) then divide by w (Geometry.cpp:19-27)
@@ -594,6 +664,8 @@ __global__ void __launch_bounds__(kIcpThreads) icp_accumulate_kernel(IcpArgs a)
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0) a.st->n_inliers_local = (unsigned long long)(a.st->packet[29] + 0.5);
+    comm_allreduce(a.comm, a.st->packet, 30);
     if (threadIdx.x != 0) return;
     a.st->blocks_done = 0;
     icp_solve_and_update(a, a.st);
@@ -639,7 +711,7 @@ __global__ void __launch_bounds__(kIcpThreads) icp_final_sums_kernel(const float
         partials[(size_t)blockIdx.x * kPacket + threadIdx.x] = v;
     }
 }
-__global__ void __launch_bounds__(kIcpThreads) icp_final_reduce_kernel(const double *partials, int n_partials, IcpState *st)
+__global__ void __launch_bounds__(kIcpThreads) icp_final_reduce_kernel(const double *partials, int n_partials, IcpState *st, IcpComm comm)
 {
     __shared__ double s_part[kIcpThreads / 32][kPacket];
     const int k = threadIdx.x & 31, chain = threadIdx.x >> 5;
@@ -654,6 +726,8 @@ __global__ void __launch_bounds__(kIcpThreads) icp_final_reduce_kernel(const dou
         for (int c = 0; c < kIcpThreads / 32; ++c) tot += s_part[c][threadIdx.x];
         st->packet[threadIdx.x] = tot;
     }
+    __syncthreads();
+    comm_allreduce(comm, st->packet, 16);
 }
 
 // ordered compaction of inlier pairs (source index ascending, like the reference's push_back loop)
@@ -724,6 +798,9 @@ struct opb_icp
     size_t cap_partials = 0;
     IcpState *d_state = nullptr;
     IcpState *h_state = nullptr; // pinned
+    // cross-GPU exchange (opb_icp_comm_*)
+    IcpMailbox *d_mailbox = nullptr;
+    IcpComm comm = {};
     // timing
     bool profiling = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -808,7 +885,7 @@ void opb_icp_destroy(opb_icp *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_src); cudaFree(c->d_tgt); cudaFree(c->d_nrm); cudaFree(c->d_sorted); cudaFree(c->d_point_cell);
     cudaFree(c->d_cell_count); cudaFree(c->d_tile_sums); cudaFree(c->d_cell_start); cudaFree(c->d_nn); cudaFree(c->d_pairs);
-    cudaFree(c->d_inlier); cudaFree(c->d_partials); cudaFree(c->d_state);
+    cudaFree(c->d_inlier); cudaFree(c->d_partials); cudaFree(c->d_state); cudaFree(c->d_mailbox);
     if (c->h_state) cudaFreeHost(c->h_state);
     for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -845,7 +922,7 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
         res->status = OPB_ERR_INVALID;
         return OPB_ERR_INVALID;
     }
-    if (ns == 0 || nt == 0) { set_error("empty point cloud"); res->status = OPB_ERR_INVALID; return OPB_ERR_INVALID; }
+    if (nt == 0 || (ns == 0 && c->comm.world <= 1)) { set_error("empty point cloud"); res->status = OPB_ERR_INVALID; return OPB_ERR_INVALID; }
     OPB_CUDA(cudaSetDevice(c->device));
     int rc = icp_reserve(c, ns, nt);
     if (rc) return rc;
@@ -885,7 +962,8 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     a.search_radius = (float)(par->threshold * (1.0 + 1e-3)) + 1e-6f;
     a.sq_threshold = par->threshold * par->threshold;
     a.final_pass = 0; a.pairs = c->d_pairs; a.inlier = c->d_inlier;
-    const int nb_need = (int)((ns + kIcpThreads - 1) / kIcpThreads);
+    a.comm = c->comm;
+    const int nb_need = ns ? (int)((ns + kIcpThreads - 1) / kIcpThreads) : 1; // an empty share still takes part in the exchange
     // developer knobs for grid-size sweeps (CTAs per SM); the defaults are the measured optimum on B200
     static const int k_search = getenv("OPB_ICP_SEARCH_CTAS") ? atoi(getenv("OPB_ICP_SEARCH_CTAS")) : 8;
     static const int k_accum = getenv("OPB_ICP_ACCUM_CTAS") ? atoi(getenv("OPB_ICP_ACCUM_CTAS")) : 2;
@@ -901,7 +979,7 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     }
     OPB_CUDA(cudaMemcpyAsync(h, c->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
     icp_final_sums_kernel<<<nb_a, kIcpThreads, 0, s>>>(c->d_src, c->d_tgt, c->d_nn, c->d_inlier, (int)ns, scaling, c->d_partials);
-    icp_final_reduce_kernel<<<1, kIcpThreads, 0, s>>>(c->d_partials, nb_a, c->d_state);
+    icp_final_reduce_kernel<<<1, kIcpThreads, 0, s>>>(c->d_partials, nb_a, c->d_state, c->comm);
     if (pairs && pairs_cap) icp_compact_kernel<<<1, 1024, 0, s>>>(c->d_nn, c->d_inlier, (int)ns, c->d_pairs, (unsigned long long)pairs_cap);
     if (c->profiling) OPB_CUDA(cudaEventRecord(c->ev[2], s));
     OPB_CUDA(cudaGetLastError());
@@ -911,7 +989,19 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
         cudaEventElapsedTime(&c->last_build_ms, c->ev[0], c->ev[1]);
         cudaEventElapsedTime(&c->last_iter_ms, c->ev[1], c->ev[2]);
     }
+    if (c->comm.world > 1)
+    {
+        int err = 0;
+        OPB_CUDA(cudaMemcpy(&err, &c->d_mailbox->error, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err)
+        {
+            set_error("ICP packet exchange timed out: a peer rank did not make the matching call");
+            res->status = OPB_ERR_CUDA;
+            return OPB_ERR_CUDA;
+        }
+    }
     res->n_inliers = (size_t)h->n_inliers;
+    res->n_local_pairs = (size_t)h->n_inliers_local;
     res->rmse = sqrt(h->sum_error / (double)h->n_inliers); // CountInliers: sqrt(sum_error / inliers.size())
     res->iterations = h->iteration;
     memcpy(res->T_iterated, h->T, 16 * sizeof(float));
@@ -929,7 +1019,7 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
         for (int e = 0; e < 16; ++e) res->T[e] = nanf(""); // the reference divides by zero pairs here
     if (pairs && pairs_cap)
     {
-        const size_t n = res->n_inliers < pairs_cap ? res->n_inliers : pairs_cap;
+        const size_t n = res->n_local_pairs < pairs_cap ? res->n_local_pairs : pairs_cap;
         OPB_CUDA(cudaMemcpy(pairs, c->d_pairs, n * 2 * sizeof(int), cudaMemcpyDeviceToHost));
     }
     res->status = OPB_OK;
@@ -954,6 +1044,66 @@ int opb_icp_point_to_point(opb_icp *c, const float *src_xyz, size_t ns, const fl
                            const opb_icp_params *params, opb_icp_result *result, int32_t *pairs, size_t pairs_cap)
 {
     return icp_run(c, src_xyz, ns, tgt_xyz, nullptr, nt, init_T, params, result, pairs, pairs_cap, false);
+}
+int opb_icp_comm_buffer(opb_icp *c, void **d_buffer, unsigned char ipc_handle[OPB_IPC_HANDLE_BYTES])
+{
+    if (!c || !d_buffer) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == OPB_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+    OPB_CUDA(cudaSetDevice(c->device));
+    if (!c->d_mailbox)
+    {
+        OPB_CUDA(cudaMalloc(&c->d_mailbox, sizeof(IcpMailbox)));
+        OPB_CUDA(cudaMemset(c->d_mailbox, 0, sizeof(IcpMailbox)));
+    }
+    *d_buffer = c->d_mailbox;
+    if (ipc_handle)
+    {
+        cudaIpcMemHandle_t h;
+        OPB_CUDA(cudaIpcGetMemHandle(&h, c->d_mailbox));
+        memcpy(ipc_handle, &h, sizeof(h));
+    }
+    return OPB_OK;
+}
+int opb_ipc_open(int device, const unsigned char ipc_handle[OPB_IPC_HANDLE_BYTES], void **d_ptr)
+{
+    if (!ipc_handle || !d_ptr) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    OPB_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof(h));
+    OPB_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return OPB_OK;
+}
+int opb_ipc_close(int device, void *d_ptr)
+{
+    if (!d_ptr) return OPB_OK;
+    OPB_CUDA(cudaSetDevice(device));
+    OPB_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return OPB_OK;
+}
+int opb_icp_comm_attach(opb_icp *c, int rank, int world, void *const *buffers)
+{
+    if (!c || !buffers) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) { set_error("rank %d of world %d is out of range (max %d ranks)", rank, world, kMaxRanks); return OPB_ERR_INVALID; }
+    if (!c->d_mailbox || buffers[rank] != (void *)c->d_mailbox) { set_error("buffers[rank] must be this workspace's own opb_icp_comm_buffer"); return OPB_ERR_INVALID; }
+    OPB_CUDA(cudaSetDevice(c->device));
+    OPB_CUDA(cudaStreamSynchronize(c->stream));
+    OPB_CUDA(cudaMemset(c->d_mailbox, 0, sizeof(IcpMailbox)));
+    for (int r = 0; r < world; ++r)
+    {
+        if (!buffers[r]) { set_error("buffers[%d] is NULL", r); return OPB_ERR_INVALID; }
+        c->comm.box[r] = (IcpMailbox *)buffers[r];
+    }
+    c->comm.rank = rank;
+    c->comm.world = world;
+    return OPB_OK;
+}
+int opb_icp_comm_detach(opb_icp *c)
+{
+    if (!c) { set_error("icp is NULL"); return OPB_ERR_INVALID; }
+    OPB_CUDA(cudaSetDevice(c->device));
+    OPB_CUDA(cudaStreamSynchronize(c->stream));
+    c->comm = IcpComm{};
+    return OPB_OK;
 }
 // nearest-neighbour indices of the LAST search (final CountInliers pass), for tests
 int opb_icp_last_nn(opb_icp *c, int32_t *nn, size_t n)

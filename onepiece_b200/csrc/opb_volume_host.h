@@ -39,6 +39,10 @@ struct opb_volume
     // marching-cubes scratch
     void *mesh_scratch = nullptr;
     size_t mesh_scratch_bytes = 0;
+    // ghost cubes received from the owner of the next slab (opb_halo.cu): slots [max_cubes - n_ghost, max_cubes)
+    int n_ghost = 0;
+    void *halo_scratch = nullptr;
+    size_t halo_scratch_bytes = 0;
 
     int profile_acquire(opb::ProfileSlot **out);
     int profile_drain();
@@ -47,4 +51,8 @@ struct opb_volume
 namespace opb
 {
 void build_frame_params(const opb_volume *v, const float *pose_cm, int depth_type, FrameParams &p);
+// enqueue on the volume's stream: slots [first, first+n) back to the TSDFVoxel defaults; hash table rebuilt from slots [0, n_alloc)
+int volume_reinit_slots(opb_volume *v, size_t first, size_t n);
+int volume_rebuild_table(opb_volume *v, int n_alloc);
+int halo_drop_ghosts(opb_volume *v); // opb_halo.cu
 }

@@ -1,0 +1,200 @@
+"""Sub-volume fusion across the GPUs of one box: one process per GPU, `torch.distributed` for the
+plumbing.  The reference is single-process; this is the host side of the partitioned path the north star asks for:
+
+  * integration needs no data-path collective: every rank sees the frame and updates the cubes it owns
+    (`opb_volume_desc.shard_*`, slabs of `slab` cubes along `axis`, owner = floor(id/slab) mod world);
+  * before Marching Cubes each rank sends the first voxel layer of the cubes at the low face of its slabs to the owner
+    of the previous slab (`exchange_halo`), because GenerateMeshByCube (reference src/Integration/CubeHandler.cpp:83-99)
+    reads the +x/+y/+z neighbour cubes;
+  * the mesh is the concatenation of the per-rank meshes (TriangleMesh::LoadFromMeshes semantics,
+    src/Geometry/TriangleMesh.cpp:73-94): `gather_mesh`.
+
+Everything here is transport and bookkeeping; the arithmetic is in libonepiece_b200.so.  The functions take any "volume"
+object with HaloCount / HaloExport / HaloImport, so the N>1 host logic is testable with `gloo` on CPU tensors."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+LAYER_FLOATS = 5 * 64  # sdf, weight, c0, c1, c2 of the 64 voxels of one cube layer
+
+
+def owner_of(cube_ids, axis: int, slab: int, world: int):
+    """Rank owning each cube: floor_mod(floor_div(id[axis], slab), world) -- the rule of select_kernel (csrc/opb_volume.cu)."""
+    c = np.asarray(cube_ids)[..., axis]
+    return np.mod(np.floor_divide(c, slab), world)
+
+
+def halo_peers(rank: int, world: int):
+    """(destination of this rank's boundary layer, source of the layer this rank needs)."""
+    return (rank - 1) % world, (rank + 1) % world
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous split of n items (source points of an ICP, image rows of the odometry) into world nearly equal parts."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def exchange_halo(volume, rank: int, world: int, device="cpu", group=None) -> int:
+    """Boundary-cube exchange before Marching Cubes.  Returns the number of ghost cubes imported.  Collective: every rank
+    of the group must call it."""
+    if world <= 1:
+        return 0
+    dst, src = halo_peers(rank, world)
+    n_send = volume.HaloCount()
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    mine = torch.tensor([n_send], dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts, mine, group=group)
+    n_recv = int(counts[src].item())
+    ids_s = torch.empty((max(n_send, 1), 3), dtype=torch.int32, device=device)
+    lay_s = torch.empty((max(n_send, 1), LAYER_FLOATS), dtype=torch.float32, device=device)
+    if n_send:
+        got = volume.HaloExport(ids_s.data_ptr(), lay_s.data_ptr(), n_send)
+        assert got == n_send
+    ids_r = torch.empty((max(n_recv, 1), 3), dtype=torch.int32, device=device)
+    lay_r = torch.empty((max(n_recv, 1), LAYER_FLOATS), dtype=torch.float32, device=device)
+    if torch.device(device).type == "cuda":
+        torch.cuda.synchronize()
+    ops = []
+    if n_send:
+        ops += [dist.P2POp(dist.isend, ids_s[:n_send], dst, group), dist.P2POp(dist.isend, lay_s[:n_send], dst, group)]
+    if n_recv:
+        ops += [dist.P2POp(dist.irecv, ids_r[:n_recv], src, group), dist.P2POp(dist.irecv, lay_r[:n_recv], src, group)]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    if torch.device(device).type == "cuda":
+        torch.cuda.synchronize()
+    if n_recv:
+        volume.HaloImport(ids_r.data_ptr(), lay_r.data_ptr(), n_recv)
+    return n_recv
+
+
+def gather_mesh(points, colors, rank: int, world: int, device="cpu", dst: int = 0, group=None):
+    """Concatenation of the per-rank meshes on rank `dst` (three fresh vertices per triangle, so concatenating vertex
+    arrays concatenates triangles).  Returns (points, colors) on dst, (None, None) elsewhere."""
+    pts = torch.from_numpy(np.ascontiguousarray(points, np.float32).reshape(-1, 3))
+    col = torch.from_numpy(np.ascontiguousarray(colors, np.float32).reshape(-1, 3))
+    if world <= 1:
+        return pts.numpy(), col.numpy()
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts, torch.tensor([len(pts)], dtype=torch.int64, device=device), group=group)
+    counts = [int(c) for c in counts.tolist()]
+    payload = torch.cat([pts, col], 1).to(device)  # [n, 6]
+    if rank != dst:
+        if len(payload):
+            dist.send(payload, dst, group=group)
+        return None, None
+    parts = []
+    for r in range(world):
+        if r == dst:
+            parts.append(payload)
+        elif counts[r]:
+            buf = torch.empty((counts[r], 6), dtype=torch.float32, device=device)
+            dist.recv(buf, r, group=group)
+            parts.append(buf)
+    allv = torch.cat(parts, 0).cpu().numpy()
+    return np.ascontiguousarray(allv[:, :3]), np.ascontiguousarray(allv[:, 3:])
+
+
+class ShardedCubeHandler:
+    """One rank's part of a CubeHandler partitioned over the process group: same method names as the reference class
+    (src/Integration/CubeHandler.h) for the calls the fusion mains make."""
+
+    def __init__(self, camera, voxel_resolution=0.01, truncation=0.1, max_cubes=1 << 17, axis=0, slab=4, device_index=0,
+                 group=None, **kw):
+        from .volume import CubeHandler
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.group = group
+        self.device = torch.device("cuda", device_index)
+        self.volume = CubeHandler(camera, voxel_resolution, truncation, max_cubes=max_cubes, device=device_index,
+                                  shard=(self.rank, self.world, axis, slab), **kw)
+
+    def IntegrateImage(self, depth, rgb, pose):
+        """Every rank is given the same frame and pose (the host program broadcasts or loads it per rank)."""
+        self.volume.IntegrateImage(depth, rgb, pose)
+
+    def ExtractTriangleMesh(self, dst: int = 0):
+        """Halo exchange, per-rank Marching Cubes, concatenation on rank dst -> (points, colors, triangles) or Nones."""
+        exchange_halo(self.volume, self.rank, self.world, self.device, self.group)
+        pts, col, _ = self.volume.ExtractTriangleMesh()
+        self.volume.HaloClear()
+        p, c = gather_mesh(pts, col, self.rank, self.world, self.device, dst, self.group)
+        if p is None:
+            return None, None, None
+        tri = np.arange(len(p), dtype=np.uint32).reshape(-1, 3)
+        return p, c, tri
+
+
+class SplitICP:
+    """registration::PointToPlane / PointToPoint (reference src/Registration/ICP.cpp:31-224) with the source cloud split
+    across the ranks of the process group: each rank searches and reduces its share, the 30-scalar packets meet in the
+    reduction kernel over peer memory (include/onepiece_b200.h, opb_icp_comm_*).  Construction and every call are collective."""
+
+    def __init__(self, device_index: int, group=None, stream=None):
+        import ctypes as C
+
+        from . import capi
+        self._C, self._capi = C, capi
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device_index = device_index
+        self.ws = C.c_void_p()
+        capi.check(capi.lib.opb_icp_create(device_index, C.c_void_p(stream) if stream else None, C.byref(self.ws)))
+        self._opened = []
+        if self.world > 1:
+            own = C.c_void_p()
+            handle = (C.c_ubyte * 64)()
+            capi.check(capi.lib.opb_icp_comm_buffer(self.ws, C.byref(own), handle))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            bufs = (C.c_void_p * self.world)()
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    bufs[r] = own.value
+                else:
+                    p = C.c_void_p()
+                    capi.check(capi.lib.opb_ipc_open(device_index, (C.c_ubyte * 64).from_buffer_copy(h), C.byref(p)))
+                    self._opened.append(p)
+                    bufs[r] = p.value
+            capi.check(capi.lib.opb_icp_comm_attach(self.ws, self.rank, self.world, bufs))
+            dist.barrier(group=group)  # nobody starts exchanging before every mailbox is mapped everywhere
+
+    def close(self):
+        capi = self._capi
+        if self.ws:
+            if self.world > 1:
+                capi.lib.opb_icp_comm_detach(self.ws)
+                dist.barrier(group=self.group)  # peers may still be reading this mailbox until they detached too
+            for p in self._opened:
+                capi.lib.opb_ipc_close(self.device_index, p)
+            capi.lib.opb_icp_destroy(self.ws)
+            self.ws = None
+
+    def _run(self, source, target, init_T, icp_para, plane, gather_pairs):
+        from . import registration as reg
+        lo, hi = shard_range(len(source.points), self.rank, self.world)
+        part = reg.PointCloud(source.points[lo:hi])
+        r = reg._run(part, target, init_T, icp_para, plane, self.device_index, self.ws)
+        idx = r.correspondence_set_index
+        idx[:, 0] += lo
+        if gather_pairs and self.world > 1:
+            parts = [None] * self.world
+            dist.all_gather_object(parts, idx, group=self.group)
+            idx = np.concatenate(parts)  # rank order == ascending source index, as the reference's push_back loop
+        r.correspondence_set_index = idx
+        r.correspondence_set = (source.points[idx[:, 0]], target.points[idx[:, 1]])
+        return r
+
+    def PointToPlane(self, source, target, init_T=np.eye(4), icp_para=None, gather_pairs=True):
+        from . import registration as reg
+        return self._run(source, target, init_T, icp_para or reg.ICPParameter(), True, gather_pairs)
+
+    def PointToPoint(self, source, target, init_T=np.eye(4), icp_para=None, gather_pairs=True):
+        from . import registration as reg
+        return self._run(source, target, init_T, icp_para or reg.ICPParameter(), False, gather_pairs)

@@ -75,7 +75,7 @@ def _run(source: PointCloud, target: PointCloud, init_T, icp_para: ICPParameter,
         print(capi.lib.opb_last_error().decode())
         return RegistrationResult(ok=False)
     capi.check(rc)
-    idx = pairs[: res.n_inliers].copy()
+    idx = pairs[: res.n_local_pairs].copy()
     out = RegistrationResult()
     out.T = np.array(res.T[:], np.float32).reshape(4, 4).T.copy()
     out.T_iterated = np.array(res.T_iterated[:], np.float32).reshape(4, 4).T.copy()

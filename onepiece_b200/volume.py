@@ -152,6 +152,29 @@ class CubeHandler:
         vox = np.ascontiguousarray(vox, np.float32)
         capi.check(capi.lib.opb_volume_upload(self._h, _ptr(ids), _ptr(vox), len(ids)))
 
+    # -- boundary-cube exchange for multi-GPU Marching Cubes (include/onepiece_b200.h, opb_volume_halo_*) -----------
+    def HaloCount(self) -> int:
+        n = C.c_size_t(0)
+        capi.check(capi.lib.opb_volume_halo_export(self._h, None, None, 0, C.byref(n)))
+        return n.value
+
+    def HaloExport(self, ids, layers, cap: int) -> int:
+        """ids: int32[cap,3], layers: float32[cap,5,64]; numpy arrays or raw host/device addresses.  -> cubes written"""
+        n = C.c_size_t(0)
+        capi.check(capi.lib.opb_volume_halo_export(self._h, _ptr(ids), _ptr(layers), cap, C.byref(n)))
+        return n.value
+
+    def HaloImport(self, ids, layers, n: int):
+        capi.check(capi.lib.opb_volume_halo_import(self._h, _ptr(ids), _ptr(layers), n))
+
+    def HaloClear(self):
+        capi.check(capi.lib.opb_volume_halo_clear(self._h))
+
+    def NumGhostCubes(self) -> int:
+        n = C.c_size_t(0)
+        capi.check(capi.lib.opb_volume_num_ghost_cubes(self._h, C.byref(n)))
+        return n.value
+
     # -- Marching Cubes ---------------------------------------------------------------------------------
     def ExtractTriangleMesh(self):
         """CubeHandler::ExtractTriangleMesh -> (points [nv,3] f32, colors [nv,3] f32, triangles [nt,3] u32)."""

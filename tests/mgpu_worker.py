@@ -1,0 +1,68 @@
+"""torchrun worker of tests/test_fusion_gpu.py (one process per GPU, NCCL): partitioned fusion + halo exchange + Marching
+Cubes against the unsharded volume, and the split ICP against the single-GPU call.  Prints "MGPU OK" on rank 0."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    from conftest import assert_bit_equal, canon_triangles
+    from fusion_common import small_scene
+    from onepiece_b200 import fusion, registration as reg
+    from onepiece_b200.volume import CubeHandler
+    from test_fusion_gpu import _icp_inputs
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cam, res, frames, ids, vox, (opts, ocol) = small_scene()
+    # 1. partitioned fusion: every rank integrates the same frames into the cubes it owns; halo; MC; gather
+    sh = fusion.ShardedCubeHandler(cam, res, max_cubes=4096, axis=0, slab=2, device_index=local)
+    for d, c, pose in frames:
+        sh.IntegrateImage(d, c, pose)
+    P, Cc, tri = sh.ExtractTriangleMesh(0)
+    owned = torch.tensor([sh.volume.NumCubes()], device="cuda")
+    dist.all_reduce(owned)
+    if rank == 0:
+        assert int(owned.item()) == len(ids), (int(owned.item()), len(ids))
+        assert np.array_equal(canon_triangles(P, Cc), canon_triangles(opts, ocol)), "sharded mesh differs from the oracle mesh"
+        assert len(tri) * 3 == len(P)
+    # 2. split ICP over peer memory vs the single-GPU call on this rank's device
+    src, tgt, nrm = _icp_inputs(quarter=False)
+    par = reg.ICPParameter(10, 0.05, 1.0)
+    whole = reg.PointToPlane(reg.PointCloud(src), reg.PointCloud(tgt, nrm), np.eye(4), par, device=local)
+    sp = fusion.SplitICP(local)
+    for _ in range(2):
+        r = sp.PointToPlane(reg.PointCloud(src), reg.PointCloud(tgt, nrm), np.eye(4), par)
+    assert np.array_equal(r.correspondence_set_index, whole.correspondence_set_index), "split ICP pairs differ"
+    assert np.abs(r.T_iterated - whole.T_iterated).max() < 1e-6 and np.abs(r.T - whole.T).max() < 1e-6
+    Ts = [None] * world
+    dist.all_gather_object(Ts, r.T_iterated.tobytes())
+    assert all(t == Ts[0] for t in Ts), "ranks disagree on the pose"
+    # timing of the split call vs the whole call (reported, not asserted)
+    import time
+    for name, fn in (("whole", lambda: reg.PointToPlane(reg.PointCloud(src), reg.PointCloud(tgt, nrm), np.eye(4), par, device=local)),
+                     ("split", lambda: sp.PointToPlane(reg.PointCloud(src), reg.PointCloud(tgt, nrm), np.eye(4), par, gather_pairs=False))):
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            fn()
+        torch.cuda.synchronize(); dist.barrier()
+        if rank == 0:
+            print(f"ICP {name}: {(time.perf_counter() - t0) * 100:.3f} ms per call ({len(src)} source points, world {world})")
+    sp.close()
+    dist.barrier()
+    if rank == 0:
+        print("MGPU OK")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
