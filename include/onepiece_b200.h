@@ -172,6 +172,29 @@ int opb_volume_halo_clear(opb_volume *v);
 int opb_volume_num_ghost_cubes(opb_volume *v, size_t *n);
 
 /* ------------------------------------------------------------------------------------------------------
+ * Depth pre-filter  (replaces one_piece::tool::ConvertDepthTo32F and tool::BilateralFilter,
+ *                    src/Tool/ImageProcessing.cpp:64-91 -- the two calls every fusion main makes right before
+ *                    IntegrateImage: example/ImageSequenceIntegration.cpp:36-38, example/DenseFusion/DenseFusion.cpp:92-95)
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct opb_prefilter opb_prefilter; /* device workspace for one image size; one host thread at a time */
+int opb_prefilter_create(int device, void *stream /* cudaStream_t or NULL */, int width, int height, opb_prefilter **out);
+void opb_prefilter_destroy(opb_prefilter *f);
+/* converted = ConvertDepthTo32F(depth, depth_scale): float copy, or u16 / depth_scale clamped at 0 (ImageProcessing.cpp:68-91);
+ * filtered  = cv::bilateralFilter(converted, d, sigma_color, sigma_space), BORDER_REFLECT_101 -- tool::BilateralFilter calls
+ *             it with (range = 7, 0.03, 4.5) (ImageProcessing.cpp:64-67).
+ * depth / converted / filtered may be host or device pointers; converted and filtered are optional (NULL: the result only
+ * stays in the workspace, see opb_prefilter_device_result).  Unknown depth_type -> OPB_ERR_UNSUPPORTED (the reference exits). */
+int opb_prefilter_run(opb_prefilter *f, const void *depth, int depth_type, float depth_scale, int d, double sigma_color,
+                      double sigma_space, float *converted, float *filtered);
+/* device pointer of the last filtered image (valid until the next run; ordered on the workspace's stream) */
+const float *opb_prefilter_device_result(opb_prefilter *f);
+int opb_prefilter_synchronize(opb_prefilter *f);
+/* ConvertDepthTo32F + BilateralFilter + CubeHandler::IntegrateImage(filtered_depth, rgb, pose) as the fusion mains chain them,
+ * without the filtered image leaving the device.  Host buffers, synchronous. */
+int opb_volume_integrate_prefiltered(opb_volume *v, opb_prefilter *f, const void *depth, int depth_type, const uint8_t *bgr,
+                                     const float pose_colmajor[16], int d, double sigma_color, double sigma_space);
+
+/* ------------------------------------------------------------------------------------------------------
  * ICP  (replaces one_piece::registration::PointToPlane / PointToPoint, src/Registration/ICP.h:23-26,
  *       src/Registration/ICP.cpp:31-224)
  * ---------------------------------------------------------------------------------------------------- */

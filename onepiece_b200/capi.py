@@ -115,6 +115,12 @@ SIGNATURES = {
     "opb_volume_halo_import": (C.c_int, [_p, _p, _p, _sz]),
     "opb_volume_halo_clear": (C.c_int, [_p]),
     "opb_volume_num_ghost_cubes": (C.c_int, [_p, C.POINTER(_sz)]),
+    "opb_prefilter_create": (C.c_int, [C.c_int, _p, C.c_int, C.c_int, C.POINTER(_p)]),
+    "opb_prefilter_destroy": (None, [_p]),
+    "opb_prefilter_run": (C.c_int, [_p, _p, C.c_int, C.c_float, C.c_int, C.c_double, C.c_double, _p, _p]),
+    "opb_prefilter_device_result": (_p, [_p]),
+    "opb_prefilter_synchronize": (C.c_int, [_p]),
+    "opb_volume_integrate_prefiltered": (C.c_int, [_p, _p, _p, C.c_int, _p, _p, C.c_int, C.c_double, C.c_double]),
     "opb_icp_params_default": (None, [C.POINTER(IcpParams)]),
     "opb_icp_create": (C.c_int, [C.c_int, _p, C.POINTER(_p)]),
     "opb_icp_destroy": (None, [_p]),

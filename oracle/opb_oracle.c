@@ -1206,3 +1206,106 @@ void orc_frame_preprocess(orc_frame *f, float depth_scale)
 {
     if (!f->preprocessed) odo_preprocess(f, depth_scale);
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Caller-side depth pre-filter: what every fusion main runs right before IntegrateImage
+ * (example/ImageSequenceIntegration.cpp:36-38, example/DenseFusion/DenseFusion.cpp:92-95).
+ * ------------------------------------------------------------------------------------------------------- */
+/* tool::ConvertDepthTo32F (src/Tool/ImageProcessing.cpp:68-91) */
+void orc_convert_depth_32f(const void *depth, int is_u16, long n, float depth_scale, float *out)
+{
+    for (long i = 0; i < n; ++i)
+    {
+        if (is_u16)
+        {
+            out[i] = ((const unsigned short *)depth)[i] / depth_scale;
+            if (out[i] < 0) out[i] = 0;
+        }
+        else
+            out[i] = ((const float *)depth)[i];
+    }
+}
+/* tool::BilateralFilter (ImageProcessing.cpp:64-67) = cv::bilateralFilter(src, dst, d, sigma_color, sigma_space) on a
+ * CV_32FC1 image, BORDER_REFLECT_101.  OpenCV is a third-party dependency that is not in the reference tree (README pins
+ * "OpenCV 3.4"); this restates its published float algorithm (modules/imgproc/src/bilateral_filter.dispatch.cpp,
+ * bilateralFilter_32f): circular mask of radius d/2; spatial weights exp(-r^2/(2 sigma_space^2)); the range weight
+ * exp(-dv^2/(2 sigma_color^2)) read from a (1<<12)-bin table over [0, max-min] with linear interpolation; weighted mean.
+ * Summation order (neighbours in raster order, then the centre pixel with weight 1) and separately rounded float
+ * operations are chosen to be closest to cv2 4.13's non-dispatched code path; OpenCV's own code paths differ from each other
+ * in the last bits (tests/golden/gen_golden_filters.py records both), so this boundary is pinned to a tolerance only. */
+void orc_bilateral_tables(float vmin, float vmax, int d, double sigma_color, double sigma_space, float *lut4098, float *scale_index,
+                          float *space_weight, int *space_dy, int *space_dx, int *n_taps)
+{
+    const int K = 1 << 12, radius = d / 2;
+    const double gc = -0.5 / (sigma_color * sigma_color), gs = -0.5 / (sigma_space * sigma_space);
+    const float len = (float)((double)vmax - (double)vmin);
+    *scale_index = K / len;
+    float last = 1.0f;
+    for (int i = 0; i < K + 2; ++i)
+    {
+        if (last > 0.0f)
+        {
+            const double val = i / *scale_index;
+            lut4098[i] = (float)exp(val * val * gc);
+            last = lut4098[i];
+        }
+        else
+            lut4098[i] = 0.0f;
+    }
+    int m = 0;
+    for (int i = -radius; i <= radius; ++i)
+        for (int j = -radius; j <= radius; ++j)
+        {
+            const double r = sqrt((double)i * i + (double)j * j);
+            if (r > radius || (i == 0 && j == 0)) continue;
+            space_weight[m] = (float)exp(r * r * gs);
+            space_dy[m] = i;
+            space_dx[m] = j;
+            ++m;
+        }
+    *n_taps = m;
+}
+void orc_bilateral_filter(const float *src, int w, int h, int d, double sigma_color, double sigma_space, float *dst)
+{
+    /* OpenCV's argument normalisation */
+    if (sigma_color <= 0) sigma_color = 1;
+    if (sigma_space <= 0) sigma_space = 1;
+    int radius = d <= 0 ? (int)lround(sigma_space * 1.5) : d / 2;
+    if (radius < 1) radius = 1;
+    d = radius * 2 + 1;
+    float vmin = src[0], vmax = src[0];
+    for (long i = 1; i < (long)w * h; ++i)
+    {
+        if (src[i] < vmin) vmin = src[i];
+        if (src[i] > vmax) vmax = src[i];
+    }
+    if (fabs((double)vmin - (double)vmax) < FLT_EPSILON)
+    {
+        memcpy(dst, src, sizeof(float) * (size_t)w * h);
+        return;
+    }
+    float *lut = (float *)malloc(sizeof(float) * 4098), *sw = (float *)malloc(sizeof(float) * d * d), scale;
+    int *dy = (int *)malloc(sizeof(int) * d * d), *dx = (int *)malloc(sizeof(int) * d * d), taps;
+    orc_bilateral_tables(vmin, vmax, d, sigma_color, sigma_space, lut, &scale, sw, dy, dx, &taps);
+#pragma omp parallel for
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+        {
+            const float v0 = src[(long)y * w + x];
+            float sum = 0.0f, wsum = 0.0f;
+            for (int k = 0; k < taps; ++k)
+            {
+                const float v = src[(long)refl101(y + dy[k], h) * w + refl101(x + dx[k], w)];
+                float alpha = fabsf(v - v0) * scale;
+                const int idx = (int)alpha; /* cvFloor of a non-negative value */
+                alpha -= (float)idx;
+                const float wk = sw[k] * (lut[idx] + alpha * (lut[idx + 1] - lut[idx]));
+                sum += v * wk;
+                wsum += wk;
+            }
+            sum += v0;
+            wsum += 1.0f;
+            dst[(long)y * w + x] = sum / wsum;
+        }
+    free(lut); free(sw); free(dy); free(dx);
+}

@@ -108,6 +108,11 @@ long orc_single_iteration(orc_frame *source, orc_frame *target, int level, float
                           int term_type, double *sums43, uint32_t *pixel_pairs, long cap);
 void orc_frame_preprocess(orc_frame *f, float depth_scale);
 
+
+/* caller-side depth pre-filter: tool::ConvertDepthTo32F (ImageProcessing.cpp:68-91), tool::BilateralFilter (:64-67) */
+void orc_convert_depth_32f(const void *depth, int is_u16, long n, float depth_scale, float *out);
+void orc_bilateral_filter(const float *src, int w, int h, int d, double sigma_color, double sigma_space, float *dst);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,8 @@ def lib():
     L.orc_single_iteration.restype = c_l
     L.orc_single_iteration.argtypes = [c_p, c_p, c_i] + [c_f] * 4 + [c_p, c_i, c_p, c_p, c_l]
     L.orc_frame_preprocess.argtypes = [c_p, c_f]
+    L.orc_convert_depth_32f.argtypes = [c_p, c_i, c_l, c_f, c_p]
+    L.orc_bilateral_filter.argtypes = [c_p, c_i, c_i, c_i, c_d, c_d, c_p]
     _LIB = L
     return L
 
@@ -325,3 +327,19 @@ def single_iteration(source: OracleFrame, target: OracleFrame, cam, level, T, te
                                    _ptr(pairs), len(pairs))
     return dict(T=Tcm.reshape(4, 4).T.astype(np.float64), JTJ=sums[:36].reshape(6, 6).copy(), JTr=sums[36:42].copy(), r2=sums[42],
                 pairs=pairs[:n].copy())
+
+
+def convert_depth_32f(depth, depth_scale):
+    """tool::ConvertDepthTo32F"""
+    depth = np.ascontiguousarray(depth)
+    out = np.zeros(depth.shape, np.float32)
+    lib().orc_convert_depth_32f(_ptr(depth), int(depth.dtype == np.uint16), depth.size, depth_scale, _ptr(out))
+    return out
+
+
+def bilateral_filter(src, d=7, sigma_color=0.03, sigma_space=4.5):
+    """tool::BilateralFilter(source, target, range = 7) = cv::bilateralFilter(source, target, range, 0.03, 4.5)"""
+    src = np.ascontiguousarray(src, np.float32)
+    out = np.zeros_like(src)
+    lib().orc_bilateral_filter(_ptr(src), src.shape[1], src.shape[0], d, sigma_color, sigma_space, _ptr(out))
+    return out

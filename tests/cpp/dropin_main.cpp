@@ -13,6 +13,7 @@
 #include "Integration/CubeHandler.h"
 #include "Odometry/Odometry.h"
 #include "Registration/ICP.h"
+#include "Tool/ImageProcessing.h"
 
 using namespace one_piece;
 
@@ -125,6 +126,22 @@ int main(int argc, char **argv)
         odo_out.push_back((double)mat_result->pixel_correspondence_set.size());
     }
     WriteAll(dir + "/odometry.bin", odo_out);
+    // --- example/ImageSequenceIntegration.cpp:33-40: the depth pre-filter in front of IntegrateImage ------------
+    {
+        std::vector<unsigned short> raw = ReadAll<unsigned short>(dir + "/odo_depth1.bin");
+        std::vector<unsigned char> c = ReadAll<unsigned char>(dir + "/odo_bgr1.bin");
+        cv::Mat depth(H, W, CV_16UC1, raw.data()), rgb(H, W, CV_8UC3, c.data());
+        cv::Mat refined_depth, filtered_depth;
+        tool::ConvertDepthTo32F(depth, refined_depth, camera.GetDepthScale());
+        tool::BilateralFilter(refined_depth, filtered_depth);
+        integration::CubeHandler filtered_handler(camera);
+        filtered_handler.SetVoxelResolution(0.02);
+        filtered_handler.IntegrateImage(filtered_depth, rgb, geometry::TransformationMatrix::Identity());
+        WriteAll(dir + "/refined_depth.bin", std::vector<float>((float *)refined_depth.data, (float *)refined_depth.data + W * H));
+        WriteAll(dir + "/filtered_depth.bin", std::vector<float>((float *)filtered_depth.data, (float *)filtered_depth.data + W * H));
+        std::vector<double> n_cubes(1, (double)filtered_handler.GetCubeMap().size());
+        WriteAll(dir + "/filtered_cubes.bin", n_cubes);
+    }
     std::cout << "dropin ok: " << m.size() << " cubes, " << mesh.triangles.size() << " triangles, "
               << result->correspondence_set_index.size() << " ICP inliers, " << (size_t)odo_out[17] << " odometry correspondences" << std::endl;
     return 0;

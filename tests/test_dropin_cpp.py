@@ -79,6 +79,14 @@ def test_reference_caller_code_runs_on_the_gpu(tmp_path):
         assert int(rec[19]) == len(o["pairs"]) and rec[20] == 1.0
     om = oracleapi.dense_tracking(c1_bgr, c0_bgr, d1, d0, cam, np.eye(4), 0)
     assert np.abs(odo[42:58].reshape(4, 4) - om["T"]).max() < 1e-6 and int(odo[59]) == len(om["pairs"])
+    # tool::ConvertDepthTo32F + tool::BilateralFilter through the drop-in, then IntegrateImage of the filtered depth
+    oc = oracleapi.convert_depth_32f(d1, cam.depth_scale)
+    of = oracleapi.bilateral_filter(oc)
+    assert_bit_equal(np.fromfile(tmp_path / "refined_depth.bin", np.float32).reshape(d1.shape), oc, "ConvertDepthTo32F drop-in")
+    assert_bit_equal(np.fromfile(tmp_path / "filtered_depth.bin", np.float32).reshape(d1.shape), of, "BilateralFilter drop-in")
+    ovf = oracleapi.OracleVolume(cam, 0.02)
+    ovf.integrate(of, c1_bgr, np.eye(4, dtype=np.float32))
+    assert int(np.fromfile(tmp_path / "filtered_cubes.bin", np.float64)[0]) == ovf.num_cubes()
     # the .cubes file the drop-in wrote has the reference's layout: [u32 n_cubes] then per cube 3 id floats ... -2
     raw = np.fromfile(tmp_path / "volume.cubes", np.float32)
     assert raw[:1].view(np.uint32)[0] == len(oi) and (raw == -2.0).sum() >= len(oi)
