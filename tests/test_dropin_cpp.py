@@ -54,7 +54,7 @@ def test_reference_caller_code_runs_on_the_gpu(tmp_path):
     assert out.returncode == 0, out.stdout + out.stderr
     assert "dropin ok" in out.stdout
     # the reference prints one line per IntegrateImage call; the drop-in keeps that behaviour
-    assert out.stdout.count("Finish image integration") == n_frames
+    assert out.stdout.count("Finish image integration") == n_frames + 1  # + the pre-filtered frame at the end
     ids = np.fromfile(tmp_path / "ids.bin", np.int32).reshape(-1, 3)
     vox = np.fromfile(tmp_path / "voxels.bin", np.float32).reshape(-1, 512, 5)
     order = np.lexsort((ids[:, 2], ids[:, 1], ids[:, 0]))
