@@ -154,6 +154,25 @@ int opb_volume_extract_mesh(opb_volume *v, float **xyz, float **rgb, uint32_t **
 /* counts only (no download) */
 int opb_volume_count_mesh(opb_volume *v, size_t *nv, size_t *nt);
 
+/* CubeHandler::Transform (CubeHandler.h:242-298: trilinear, ReadVoxelInterpolate VoxelCube.cpp:6-50) and
+ * CubeHandler::TransformNearest (:299-338): resamples the volume under the rigid transform trans into a NEW volume on the
+ * same device (*out; release with opb_volume_destroy).  Bit-identical to the reference, including its quirk:
+ * TransformNearest does not copy the voxel resolution into its result, whose cubes are therefore allocated -- and later
+ * meshed -- with CubePara's default 0.01 while the values are sampled at the source resolution.
+ *   result_voxel_resolution  VoxelResolution of the result; <= 0: the source's.  (What the reference does: the source's
+ *                            for Transform, 0.01 for TransformNearest.)
+ *   result_max_cubes         block-pool capacity of the result; <= 0: sized automatically (grown and retried if needed)
+ * The result is never sharded (shard_world = 1). */
+int opb_volume_transform(opb_volume *src, const float trans_colmajor[16], int nearest, float result_voxel_resolution,
+                         int32_t result_max_cubes, opb_volume **out);
+/* CubeHandler::Merge(another) (CubeHandler.h:145-167): cubes missing from dst are copied, voxels of common cubes are
+ * combined with TSDFVoxel::operator+ (weighted mean).  Different voxel resolutions -> OPB_ERR_INVALID and no change (the
+ * reference prints "[Warning]::[MergeVoxelHash]::Voxel resolution is not identical." and returns).  Merge(another, trans)
+ * (:168-177) is opb_volume_transform(another, trans, 0, ...) followed by this call.  Both volumes on one device. */
+int opb_volume_merge(opb_volume *dst, opb_volume *another);
+/* the descriptor a volume currently runs with (e.g. of a transform result) */
+int opb_volume_get_desc(opb_volume *v, opb_volume_desc *out);
+
 /* Marching Cubes over a volume partitioned across GPUs (no counterpart in the single-process
  * reference, whose GenerateMeshByCube reads the +x/+y/+z neighbour cubes from the same map, CubeHandler.cpp:83-99).
  * With sub-volume ownership (shard_* above) the +1 neighbours of the cubes in the last layer of a slab live on the owner

@@ -238,6 +238,57 @@ std::shared_ptr<geometry::PointCloud> CubeHandler::GetPointCloud() const
                 }
     return std::make_shared<geometry::PointCloud>(pcd);
 }
+// CubeHandler.h:242-298 (trilinear) and :299-338 (nearest).  Like the reference, Transform copies c_para into the result and
+// TransformNearest does not: its result keeps CubePara's default VoxelResolution (0.01).
+static std::shared_ptr<CubeHandler> MakeResult(const camera::PinholeCamera &camera) { return std::make_shared<CubeHandler>(camera); }
+std::shared_ptr<CubeHandler> CubeHandler::Transform(const geometry::TransformationMatrix &trans) const
+{
+    EnsureVolume();
+    std::shared_ptr<CubeHandler> after_trans = MakeResult(camera);
+    after_trans->far = far; after_trans->near = near; after_trans->truncation = truncation; after_trans->device = device;
+    after_trans->c_para = c_para;
+    float t[16];
+    PoseToArray(trans, t);
+    Check(opb_volume_transform(volume, t, 0, after_trans->c_para.VoxelResolution, 0, &after_trans->volume), "Transform");
+    opb_volume_desc d;
+    if (after_trans->volume && opb_volume_get_desc(after_trans->volume, &d) == OPB_OK) after_trans->max_cubes = d.max_cubes;
+    return after_trans;
+}
+std::shared_ptr<CubeHandler> CubeHandler::TransformNearest(const geometry::TransformationMatrix &trans)
+{
+    EnsureVolume();
+    std::shared_ptr<CubeHandler> after_trans = MakeResult(camera);
+    after_trans->far = far; after_trans->near = near; after_trans->truncation = truncation; after_trans->device = device;
+    float t[16];
+    PoseToArray(trans, t);
+    Check(opb_volume_transform(volume, t, 1, after_trans->c_para.VoxelResolution, 0, &after_trans->volume), "TransformNearest");
+    opb_volume_desc d;
+    if (after_trans->volume && opb_volume_get_desc(after_trans->volume, &d) == OPB_OK) after_trans->max_cubes = d.max_cubes;
+    return after_trans;
+}
+// CubeHandler.h:145-167
+void CubeHandler::Merge(const CubeHandler &another)
+{
+    if (c_para.VoxelResolution != another.c_para.VoxelResolution)
+    {
+        std::cout << YELLOW << "[Warning]::[MergeVoxelHash]::Voxel resolution is not identical." << RESET << std::endl;
+        return;
+    }
+    EnsureVolume();
+    another.EnsureVolume();
+    Check(opb_volume_merge(volume, another.volume), "Merge");
+}
+// CubeHandler.h:168-177
+void CubeHandler::Merge(const CubeHandler &another, const geometry::TransformationMatrix &trans)
+{
+    if (c_para.VoxelResolution != another.c_para.VoxelResolution)
+    {
+        std::cout << YELLOW << "[Warning]::[MergeVoxelHash]::Voxel resolution is not identical." << RESET << std::endl;
+        return;
+    }
+    auto another_ptr = another.Transform(trans);
+    Merge(*another_ptr);
+}
 // CubeHandler.h:113-128: the same float stream ([u32 n] then per cube VoxelCube::WriteToBuffer, VoxelCube.h:128-142)
 bool CubeHandler::WriteToFile(const std::string &filename) const
 {

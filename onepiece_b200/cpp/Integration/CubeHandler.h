@@ -65,6 +65,12 @@ class CubeHandler
     bool WriteToFile(const std::string &filename) const;
     bool ReadFromFile(const std::string &filename);
 
+    // CubeHandler.h:145-177,242-338: volume resampling / merging, on the device
+    void Merge(const CubeHandler &another);
+    void Merge(const CubeHandler &another, const geometry::TransformationMatrix &trans);
+    std::shared_ptr<CubeHandler> Transform(const geometry::TransformationMatrix &trans) const;
+    std::shared_ptr<CubeHandler> TransformNearest(const geometry::TransformationMatrix &trans);
+
     size_t CubeCount() const;
 
   protected:

@@ -97,6 +97,37 @@ __device__ __forceinline__ int table_find(const VolumeDev &v, int i, int j, int 
     }
 }
 
+// slot of a cube, allocating it from the pool (bump pointer) on first sight; -1 and fc->overflow on a full pool / table
+__device__ __forceinline__ int table_find_or_insert(const VolumeDev &v, int i, int j, int k)
+{
+    unsigned long long key;
+    if (!pack_id(i, j, k, key)) { v.fc->overflow = 1; return -1; }
+    unsigned int h = hash_key(key) & v.table_mask;
+    for (unsigned int probe = 0; probe <= v.table_mask; ++probe)
+    {
+        const unsigned long long prev = atomicCAS(&v.keys[h], kEmptyKey, key);
+        if (prev == kEmptyKey)
+        {
+            const int slot = atomicAdd(v.n_alloc, 1);
+            if (slot >= v.max_cubes)
+            {
+                v.fc->overflow = 1;
+                v.vals[h] = -1;
+                return -1;
+            }
+            v.vals[h] = slot;
+            v.slot_ids[3 * slot] = i;
+            v.slot_ids[3 * slot + 1] = j;
+            v.slot_ids[3 * slot + 2] = k;
+            return slot;
+        }
+        if (prev == key) return v.vals[h]; // inserted by an earlier frame (a cube is tested once per frame)
+        h = (h + 1) & v.table_mask;
+    }
+    v.fc->overflow = 1;
+    return -1;
+}
+
 // VoxelCentroidOffSet component (VoxelCube.h:48-61): x*VoxelResolution + half_resolution
 __device__ __forceinline__ float centroid_offset(int x, float res, float half_res)
 {

@@ -152,6 +152,45 @@ class CubeHandler:
         vox = np.ascontiguousarray(vox, np.float32)
         capi.check(capi.lib.opb_volume_upload(self._h, _ptr(ids), _ptr(vox), len(ids)))
 
+    # -- resampling and merging (CubeHandler.h:145-177,242-338) ----------------------------------------------
+    @classmethod
+    def _adopt(cls, handle, camera):
+        o = cls.__new__(cls)
+        o._h = handle
+        o.camera = camera
+        o.desc = capi.VolumeDesc()
+        capi.check(capi.lib.opb_volume_get_desc(handle, C.byref(o.desc)))
+        return o
+
+    def _transform(self, trans, nearest, result_resolution, max_cubes):
+        out = C.c_void_p()
+        t = pose_colmajor(trans)
+        capi.check(capi.lib.opb_volume_transform(self._h, _ptr(t), int(nearest), result_resolution, max_cubes, C.byref(out)))
+        return CubeHandler._adopt(out, self.camera)
+
+    def Transform(self, trans, max_cubes: int = 0):
+        """CubeHandler::Transform(trans) -> new CubeHandler (trilinear resampling; c_para is copied)."""
+        return self._transform(trans, False, 0.0, max_cubes)
+
+    def TransformNearest(self, trans, max_cubes: int = 0, result_resolution: float = 0.01):
+        """CubeHandler::TransformNearest(trans) -> new CubeHandler.  The reference forgets to copy c_para, so its result runs
+        at CubePara's default VoxelResolution 0.01: that is the default here too (pass 0 for the source resolution)."""
+        return self._transform(trans, True, result_resolution, max_cubes)
+
+    def Merge(self, another, trans=None) -> bool:
+        """CubeHandler::Merge(another[, trans]); False (and a warning, like the reference) when the resolutions differ."""
+        if trans is not None:
+            if self.desc.voxel_resolution != another.desc.voxel_resolution:   # checked before transforming (CubeHandler.h:170-174)
+                print("[Warning]::[MergeVoxelHash]::Voxel resolution is not identical.")
+                return False
+            another = another.Transform(trans)
+        rc = capi.lib.opb_volume_merge(self._h, another._h)
+        if rc == capi.OPB_ERR_INVALID and b"MergeVoxelHash" in capi.lib.opb_last_error():
+            print(capi.lib.opb_last_error().decode())
+            return False
+        capi.check(rc)
+        return True
+
     # -- boundary-cube exchange for multi-GPU Marching Cubes (include/onepiece_b200.h, opb_volume_halo_*) -----------
     def HaloCount(self) -> int:
         n = C.c_size_t(0)

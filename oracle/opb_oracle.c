@@ -421,6 +421,164 @@ void orc_volume_upload(orc_volume *v, const int32_t *ids, const float *voxels, l
 }
 
 /* ------------------------------------------------------------------------------------------------------- */
+/* Volume resampling and merging                                                    */
+/* ------------------------------------------------------------------------------------------------------- */
+static const voxel_t kDefaultVoxel = {999, 0, {-1, -1, -1}};
+/* TSDFVoxel::operator+ (TSDFVoxel.h:24-39) */
+static voxel_t vox_plus(voxel_t a, voxel_t b)
+{
+    if (a.weight == 0) return b;
+    if (b.weight == 0) return a;
+    voxel_t r = kDefaultVoxel;
+    r.weight = a.weight + b.weight;
+    if (r.weight != 0)
+    {
+        r.sdf = (a.weight * a.sdf + b.weight * b.sdf) / r.weight;
+        for (int c = 0; c < 3; ++c) r.c[c] = (a.weight * a.c[c] + b.weight * b.c[c]) / r.weight;
+    }
+    return r;
+}
+/* TSDFVoxel::add (TSDFVoxel.h:40-53): direct addition */
+static voxel_t vox_add(voxel_t a, voxel_t b)
+{
+    if (a.weight == 0) return b;
+    if (b.weight == 0) return a;
+    voxel_t r;
+    r.weight = a.weight + b.weight;
+    r.sdf = a.sdf + b.sdf;
+    for (int c = 0; c < 3; ++c) r.c[c] = a.c[c] + b.c[c];
+    return r;
+}
+/* TSDFVoxel::operator* (TSDFVoxel.h:58-70) */
+static voxel_t vox_mul(voxel_t a, float w)
+{
+    if (w == 0 || a.weight == 0) return kDefaultVoxel;
+    voxel_t r;
+    r.weight = a.weight * w;
+    r.sdf = a.sdf * w;
+    for (int c = 0; c < 3; ++c) r.c[c] = a.c[c] * w;
+    return r;
+}
+/* TSDFVoxel::operator/ (TSDFVoxel.h:71-74): multiplication by the reciprocal */
+static voxel_t vox_div(voxel_t a, float w) { return vox_mul(a, 1 / w); }
+/* one level of ReadVoxelInterpolate (VoxelCube.cpp:16-47): blend of a and b along one axis with weight t */
+static voxel_t vox_lerp(voxel_t a, voxel_t b, float t)
+{
+    voxel_t r = kDefaultVoxel;
+    if (a.weight != 0 || b.weight != 0)
+        r = vox_div(vox_add(vox_mul(a, 1 - t), vox_mul(b, t)), (1 - t) * (float)(a.weight != 0) + t * (float)(b.weight != 0));
+    return r;
+}
+/* ReadVoxelInterpolate (src/Integration/VoxelCube.cpp:6-50): n0 = voxel coordinates of neighbour 0 */
+static voxel_t read_voxel_interpolate(const int *n0, const voxel_t *v8, const float *pos, float res)
+{
+    const float xw = (pos[0] - n0[0] * res) / res, yw = (pos[1] - n0[1] * res) / res, zw = (pos[2] - n0[2] * res) / res;
+    const voxel_t r1 = vox_lerp(v8[0], v8[1], xw), r2 = vox_lerp(v8[2], v8[3], xw);
+    const voxel_t z1 = vox_lerp(r1, r2, yw);
+    const voxel_t r3 = vox_lerp(v8[4], v8[5], xw), r4 = vox_lerp(v8[6], v8[7], xw);
+    const voxel_t z2 = vox_lerp(r3, r4, yw);
+    return vox_lerp(z1, z2, zw);
+}
+/* CubePara::GetCubeID(Point3i) / GetVoxelID(Point3i) (VoxelCube.h:63-67,81-86) */
+static int cube_of_voxel(int p) { return (int)floor((p + 0.0) / CUBE); }
+/* trans * Vector4(x,y,z,1) then head<3>() / w (CubeHandler.h:205-208): Eigen gemv order for all four rows */
+static void transform_h(const float *m, float x, float y, float z, float *out)
+{
+    const float w = row_xyz1(m, 3, x, y, z);
+    out[0] = row_xyz1(m, 0, x, y, z) / w;
+    out[1] = row_xyz1(m, 1, x, y, z) / w;
+    out[2] = row_xyz1(m, 2, x, y, z) / w;
+}
+static void global_point(const int *id, int n, float res, float *out)
+{
+    /* CubePara::GetGlobalPoint + VoxelCentroidOffSet (VoxelCube.h:48-61,75-80) for an arbitrary resolution */
+    const int xyz[3] = {n & 7, (n >> 3) & 7, n >> 6};
+    const float half = res / 2;
+    for (int a = 0; a < 3; ++a) out[a] = (float)id[a] * CUBE * res + (xyz[a] * res + half);
+}
+static const voxel_t *voxel_at(const orc_volume *v, const int *p, voxel_t *tmp)
+{
+    const int c[3] = {cube_of_voxel(p[0]), cube_of_voxel(p[1]), cube_of_voxel(p[2])};
+    const cube_t *cube = find_cube(v, c[0], c[1], c[2]);
+    *tmp = kDefaultVoxel;
+    if (!cube) return tmp;
+    return &cube->vox[(p[0] - c[0] * CUBE) + (p[1] - c[1] * CUBE) * CUBE + (p[2] - c[2] * CUBE) * CUBE * CUBE];
+}
+/* CubeHandler::Transform (CubeHandler.h:242-298, AddTransformedCube :199-225) and TransformNearest (:299-338,
+ * AddTransformedCubeNearest :226-241).  alloc_res is the VoxelResolution of the RESULT handler, which the reference uses
+ * for the allocation pass: Transform copies c_para (alloc_res = source resolution); TransformNearest forgets to
+ * (:299-305), so its result handler keeps CubePara's default 0.01 whatever the source resolution was. */
+orc_volume *orc_volume_transform(const orc_volume *v, const float *trans_cm, int nearest, float alloc_res)
+{
+    orc_volume *r = orc_volume_create(v->fx, v->fy, v->cx, v->cy, v->width, v->height, v->depth_scale, alloc_res, v->trunc,
+                                      v->near_plane, v->far_plane);
+    for (long c = 0; c < v->n_cubes; ++c)
+        for (int n = 0; n < NVOX; ++n)
+        {
+            float g[3], p[3];
+            global_point(v->cubes[c]->id, n, alloc_res, g);
+            transform_h(trans_cm, g[0], g[1], g[2], p);
+            if (!nearest)
+                for (int a = 0; a < 3; ++a) p[a] = p[a] - alloc_res / 2;
+            const int n0[3] = {cvtt_f(floorf(p[0] / alloc_res)), cvtt_f(floorf(p[1] / alloc_res)), cvtt_f(floorf(p[2] / alloc_res))};
+            for (int i = 0; i < (nearest ? 1 : 8); ++i)
+            {
+                const int q[3] = {cube_of_voxel(n0[0] + (i & 1)), cube_of_voxel(n0[1] + ((i >> 1) & 1)), cube_of_voxel(n0[2] + (i >> 2))};
+                if (!find_cube(r, q[0], q[1], q[2])) add_cube(r, q[0], q[1], q[2]);
+            }
+        }
+    float inv[16];
+    orc_pose_inverse(trans_cm, inv); /* trans.inverse(), evaluated per voxel in the reference */
+    const float res = v->res;        /* the second pass runs with the SOURCE handler's c_para (a member function of it) */
+    for (long c = 0; c < r->n_cubes; ++c)
+        for (int n = 0; n < NVOX; ++n)
+        {
+            float g[3], p[3];
+            voxel_t tmp[8], got;
+            global_point(r->cubes[c]->id, n, res, g);
+            transform_h(inv, g[0], g[1], g[2], p);
+            if (nearest)
+            {
+                const int q[3] = {cvtt_f(floorf(p[0] / res)), cvtt_f(floorf(p[1] / res)), cvtt_f(floorf(p[2] / res))};
+                got = *voxel_at(v, q, &tmp[0]);
+            }
+            else
+            {
+                for (int a = 0; a < 3; ++a) p[a] = p[a] - res / 2;
+                const int n0[3] = {cvtt_f(floorf(p[0] / res)), cvtt_f(floorf(p[1] / res)), cvtt_f(floorf(p[2] / res))};
+                voxel_t v8[8];
+                for (int i = 0; i < 8; ++i)
+                {
+                    const int q[3] = {n0[0] + (i & 1), n0[1] + ((i >> 1) & 1), n0[2] + (i >> 2)};
+                    v8[i] = *voxel_at(v, q, &tmp[i]);
+                }
+                got = read_voxel_interpolate(n0, v8, p, res);
+            }
+            r->cubes[c]->vox[n] = vox_plus(r->cubes[c]->vox[n], got); /* += on a fresh voxel */
+        }
+    return r;
+}
+/* CubeHandler::Merge(another) (CubeHandler.h:145-167); returns 0, or -1 for the resolution mismatch the reference only warns about */
+int orc_volume_merge(orc_volume *v, const orc_volume *other)
+{
+    if (v->res != other->res) return -1;
+    for (long c = 0; c < other->n_cubes; ++c)
+    {
+        const cube_t *o = other->cubes[c];
+        cube_t *mine = find_cube(v, o->id[0], o->id[1], o->id[2]);
+        if (!mine)
+        {
+            mine = add_cube(v, o->id[0], o->id[1], o->id[2]);
+            memcpy(mine->vox, o->vox, sizeof(o->vox));
+        }
+        else
+            for (int n = 0; n < NVOX; ++n) mine->vox[n] = vox_plus(mine->vox[n], o->vox[n]);
+    }
+    return 0;
+}
+float orc_volume_resolution(const orc_volume *v) { return v->res; }
+
+/* ------------------------------------------------------------------------------------------------------- */
 /* Marching Cubes                                                                                          */
 /* ------------------------------------------------------------------------------------------------------- */
 /* integration::MarchingCube, src/Integration/MarchingCube.cpp:9-74 */

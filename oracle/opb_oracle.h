@@ -109,6 +109,11 @@ long orc_single_iteration(orc_frame *source, orc_frame *target, int level, float
 void orc_frame_preprocess(orc_frame *f, float depth_scale);
 
 
+/* CubeHandler::Transform / TransformNearest (CubeHandler.h:242-338) -> new volume; CubeHandler::Merge (:145-167) */
+orc_volume *orc_volume_transform(const orc_volume *v, const float *trans_cm, int nearest, float alloc_res);
+int orc_volume_merge(orc_volume *v, const orc_volume *other);
+float orc_volume_resolution(const orc_volume *v);
+
 /* caller-side depth pre-filter: tool::ConvertDepthTo32F (ImageProcessing.cpp:68-91), tool::BilateralFilter (:64-67) */
 void orc_convert_depth_32f(const void *depth, int is_u16, long n, float depth_scale, float *out);
 void orc_bilateral_filter(const float *src, int w, int h, int d, double sigma_color, double sigma_space, float *dst);

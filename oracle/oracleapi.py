@@ -73,6 +73,12 @@ def lib():
     L.orc_single_iteration.restype = c_l
     L.orc_single_iteration.argtypes = [c_p, c_p, c_i] + [c_f] * 4 + [c_p, c_i, c_p, c_p, c_l]
     L.orc_frame_preprocess.argtypes = [c_p, c_f]
+    L.orc_volume_transform.restype = c_p
+    L.orc_volume_transform.argtypes = [c_p, c_p, c_i, c_f]
+    L.orc_volume_merge.restype = c_i
+    L.orc_volume_merge.argtypes = [c_p, c_p]
+    L.orc_volume_resolution.restype = c_f
+    L.orc_volume_resolution.argtypes = [c_p]
     L.orc_convert_depth_32f.argtypes = [c_p, c_i, c_l, c_f, c_p]
     L.orc_bilateral_filter.argtypes = [c_p, c_i, c_i, c_i, c_d, c_d, c_p]
     _LIB = L
@@ -164,6 +170,23 @@ class OracleVolume:
         ids = np.ascontiguousarray(ids, np.int32)
         vox = np.ascontiguousarray(vox, np.float32)
         self.L.orc_volume_upload(self.h, _ptr(ids), _ptr(vox), len(ids))
+
+    def transform(self, trans, nearest: bool, alloc_res=None):
+        """CubeHandler::Transform / TransformNearest -> new OracleVolume.  alloc_res None = what the reference does:
+        the source resolution for Transform, CubePara's default 0.01 for TransformNearest (it forgets to copy c_para)."""
+        if alloc_res is None:
+            alloc_res = 0.01 if nearest else self.L.orc_volume_resolution(self.h)
+        p = _pose_cm(trans)
+        o = OracleVolume.__new__(OracleVolume)
+        o.L, o.cam = self.L, self.cam
+        o.h = self.L.orc_volume_transform(self.h, _ptr(p), int(nearest), alloc_res)
+        return o
+
+    def merge(self, other) -> int:
+        return self.L.orc_volume_merge(self.h, other.h)
+
+    def resolution(self) -> float:
+        return self.L.orc_volume_resolution(self.h)
 
     def extract_mesh(self):
         """-> (points [nv,3], colors [nv,3]); triangle i = vertices 3i..3i+2"""

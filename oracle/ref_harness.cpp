@@ -55,6 +55,7 @@ struct RefVolume
 struct HandlerPeek : public integration::CubeHandler
 {
     const integration::CubeMap &map() const { return cube_map; }
+    const integration::CubePara &para() const { return c_para; }
 };
 
 geometry::TransformationMatrix PoseFromColMajor(const float *p)
@@ -190,6 +191,25 @@ void ref_volume_upload(void *h, const int32_t *ids, const float *voxels, long n)
     ((RefVolume *)h)->handler.SetCubeMap(m);
     if (!was_quiet) std::cout.clear();
 }
+// CubeHandler::Transform (CubeHandler.h:242-298) / TransformNearest (:299-338): returns a new handle holding the result
+void *ref_volume_transform(void *h, const float *trans_cm, int nearest)
+{
+    RefVolume *v = (RefVolume *)h;
+    geometry::TransformationMatrix T = PoseFromColMajor(trans_cm);
+    std::shared_ptr<integration::CubeHandler> r = nearest ? v->handler.TransformNearest(T) : v->handler.Transform(T);
+    RefVolume *out = new RefVolume();
+    out->cam = v->cam;
+    out->handler = *r;
+    return out;
+}
+// CubeHandler::Merge(another) (CubeHandler.h:145-167)
+void ref_volume_merge(void *h, void *other) { ((RefVolume *)h)->handler.Merge(((RefVolume *)other)->handler); }
+// CubeHandler::Merge(another, trans) (CubeHandler.h:168-177)
+void ref_volume_merge_transformed(void *h, void *other, const float *trans_cm)
+{
+    ((RefVolume *)h)->handler.Merge(((RefVolume *)other)->handler, PoseFromColMajor(trans_cm));
+}
+float ref_volume_resolution(void *h) { return (float)static_cast<HandlerPeek *>(&((RefVolume *)h)->handler)->para().VoxelResolution; }
 // CubeHandler::ExtractTriangleMesh (CubeHandler.cpp:9-44). Returns seconds; sizes through out params.
 double ref_volume_extract_mesh(void *h, long *n_points, long *n_triangles)
 {

@@ -46,6 +46,12 @@ def lib(kind: str = "f32"):
     L.ref_volume_write.argtypes = [c_p, C.c_char_p]
     L.ref_volume_read.restype = C.c_bool
     L.ref_volume_read.argtypes = [c_p, C.c_char_p]
+    L.ref_volume_transform.restype = c_p
+    L.ref_volume_transform.argtypes = [c_p, c_p, c_i]
+    L.ref_volume_merge.argtypes = [c_p, c_p]
+    L.ref_volume_merge_transformed.argtypes = [c_p, c_p, c_p]
+    L.ref_volume_resolution.restype = c_f
+    L.ref_volume_resolution.argtypes = [c_p]
     L.ref_marching_cube_cell.restype = c_i
     L.ref_marching_cube_cell.argtypes = [c_p] * 5
     L.ref_frustum.argtypes = [c_f] * 4 + [c_i, c_i, c_p, c_f, c_f, c_p, c_p, c_l, c_p]
@@ -145,6 +151,27 @@ class RefVolume:
         ids = np.ascontiguousarray(ids, np.int32)
         vox = np.ascontiguousarray(vox, np.float32)
         self.L.ref_volume_upload(self.h, _ptr(ids), _ptr(vox), len(ids))
+
+    @classmethod
+    def _wrap(cls, L, cam, handle):
+        o = cls.__new__(cls)
+        o.L, o.cam, o.h = L, cam, handle
+        return o
+
+    def transform(self, trans, nearest: bool):
+        """CubeHandler::Transform / TransformNearest -> new RefVolume"""
+        p = _pose_cm(trans)
+        return RefVolume._wrap(self.L, self.cam, self.L.ref_volume_transform(self.h, _ptr(p), int(nearest)))
+
+    def merge(self, other, trans=None):
+        if trans is None:
+            self.L.ref_volume_merge(self.h, other.h)
+        else:
+            p = _pose_cm(trans)
+            self.L.ref_volume_merge_transformed(self.h, other.h, _ptr(p))
+
+    def resolution(self) -> float:
+        return self.L.ref_volume_resolution(self.h)
 
     def extract_mesh(self):
         """-> (seconds, points [nv,3], colors [nv,3], triangles [nt,3])"""

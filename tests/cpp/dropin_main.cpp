@@ -77,6 +77,32 @@ int main(int argc, char **argv)
     WriteAll(dir + "/ids.bin", ids);
     WriteAll(dir + "/voxels.bin", vox);
     cube_handler.WriteToFile(dir + "/volume.cubes");
+    // example/ImageSequenceIntegration.cpp:48-53: resample the volume into the frame of the middle pose, mesh the result
+    {
+        geometry::TransformationMatrix mid;
+        for (int r = 0; r < 4; ++r)
+            for (int col = 0; col < 4; ++col) mid(r, col) = poses[16 * (n_frames / 2) + 4 * r + col];
+        auto transformed_cube_handler = cube_handler.TransformNearest(mid);
+        geometry::TriangleMesh tmesh;
+        transformed_cube_handler->ExtractTriangleMesh(tmesh);
+        // example/MergeMultipleSubmaps.cpp:40-41
+        integration::CubeHandler merged(camera);
+        merged.SetVoxelResolution(0.02);
+        auto transformed_handler = cube_handler.Transform(mid);
+        merged.Merge(*transformed_handler);
+        merged.Merge(cube_handler);
+        std::vector<double> out;
+        out.push_back((double)transformed_cube_handler->GetCubeMap().size());
+        out.push_back((double)tmesh.points.size());
+        out.push_back((double)transformed_handler->GetCubeMap().size());
+        out.push_back((double)merged.GetCubeMap().size());
+        double wsum = 0;
+        integration::CubeMap mm = merged.GetCubeMap();
+        for (auto it = mm.begin(); it != mm.end(); ++it)
+            for (int j = 0; j < 512; ++j) wsum += it->second.voxels[j].weight;
+        out.push_back(wsum);
+        WriteAll(dir + "/resample.bin", out);
+    }
 
     // --- example/ICPTest.cpp:14-34 ---------------------------------------------------------------------------
     geometry::PointCloud s_pcd, t_pcd;

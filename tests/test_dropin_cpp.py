@@ -79,6 +79,17 @@ def test_reference_caller_code_runs_on_the_gpu(tmp_path):
         assert int(rec[19]) == len(o["pairs"]) and rec[20] == 1.0
     om = oracleapi.dense_tracking(c1_bgr, c0_bgr, d1, d0, cam, np.eye(4), 0)
     assert np.abs(odo[42:58].reshape(4, 4) - om["T"]).max() < 1e-6 and int(odo[59]) == len(om["pairs"])
+    # TransformNearest (+ its forgotten c_para), Transform and Merge through the drop-in
+    rs = np.fromfile(tmp_path / "resample.bin", np.float64)
+    mid = poses[n_frames // 2]
+    on = ov.transform(mid, True)
+    ot = ov.transform(mid, False)
+    om = oracleapi.OracleVolume(cam, 0.02)
+    om.merge(ot)
+    om.merge(ov)
+    assert int(rs[0]) == on.num_cubes() and int(rs[1]) == len(on.extract_mesh()[0])
+    assert int(rs[2]) == ot.num_cubes() and int(rs[3]) == om.num_cubes()
+    assert rs[4] == float(om.download()[1][:, :, 1].astype(np.float64).sum())
     # tool::ConvertDepthTo32F + tool::BilateralFilter through the drop-in, then IntegrateImage of the filtered depth
     oc = oracleapi.convert_depth_32f(d1, cam.depth_scale)
     of = oracleapi.bilateral_filter(oc)
