@@ -154,6 +154,25 @@ int opb_volume_extract_mesh(opb_volume *v, float **xyz, float **rgb, uint32_t **
 /* counts only (no download) */
 int opb_volume_count_mesh(opb_volume *v, size_t *nv, size_t *nt);
 
+/* TriangleMesh::ClusteringSimplify(grid_len) (src/Geometry/TriangleMesh.cpp:53-58 -> ClusteringSimplification,
+ * src/Geometry/MeshSimplification.cpp:579-657, UpdateMesh :114-139, CompactMesh :314-343): vertex clustering on a hashed grid
+ * -- the first vertex (in triangle order) of every grid cell becomes its representative and moves to the mean of the vertex
+ * references that fell into the cell, triangles with two corners in one cell are dropped, unreferenced vertices removed.
+ * Bit-identical to the reference (the float sums are taken in its order), same vertex and triangle order.  For meshes
+ * without normals, which is what ExtractTriangleMesh produces (with normals the reference recomputes them afterwards:
+ * call opb_mesh_compute_normals on the result).  Inputs may be host or device pointers; colors may be NULL; outputs are
+ * malloc'ed by the library (opb_free).  grid_len <= 0 -> OPB_ERR_INVALID (the reference prints an error and returns the mesh
+ * unchanged). */
+int opb_mesh_clustering_simplify(int device, const float *points, const float *colors, size_t nv, const uint32_t *triangles, size_t nt,
+                                 float grid_len, float **out_points, float **out_colors, uint32_t **out_triangles, size_t *out_nv,
+                                 size_t *out_nt);
+/* TriangleMesh::ComputeNormals (src/Geometry/TriangleMesh.cpp:95-127): unit face normals, vertex normal = normalised sum of
+ * the normals of the faces referencing the vertex, summed in the reference's order.  normals: 3 x nv floats, host or device. */
+int opb_mesh_compute_normals(int device, const float *points, size_t nv, const uint32_t *triangles, size_t nt, float *normals);
+/* ExtractTriangleMesh + ClusteringSimplify(grid_len) as the fusion mains chain them (example/DenseFusion/DenseFusion.cpp:99-105)
+ * without the raw mesh leaving the device.  Buffers are malloc'ed by the library: release with opb_free. */
+int opb_volume_extract_mesh_clustered(opb_volume *v, float grid_len, float **xyz, float **rgb, uint32_t **tri, size_t *nv, size_t *nt);
+
 /* CubeHandler::Transform (CubeHandler.h:242-298: trilinear, ReadVoxelInterpolate VoxelCube.cpp:6-50) and
  * CubeHandler::TransformNearest (:299-338): resamples the volume under the rigid transform trans into a NEW volume on the
  * same device (*out; release with opb_volume_destroy).  Bit-identical to the reference, including its quirk:

@@ -246,12 +246,60 @@ static int mesh_count(opb_volume *v, int *n_slots_out, unsigned int **d_counts_o
     *d_counts_out = d_counts;
     return OPB_OK;
 }
+__global__ void iota_kernel(unsigned int *a, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] = (unsigned int)i;
+}
 } // namespace opb
 
 using namespace opb;
 
 extern "C"
 {
+// ExtractTriangleMesh followed by TriangleMesh::ClusteringSimplify(grid_len), the pair every fusion main runs before writing
+// its PLY (example/DenseFusion/DenseFusion.cpp:99-105): the raw mesh (72 B per triangle) never leaves the device.
+int opb_volume_extract_mesh_clustered(opb_volume *v, float grid_len, float **xyz, float **rgb, uint32_t **tri, size_t *nv, size_t *nt)
+{
+    if (!v || !xyz || !rgb || !tri || !nv || !nt) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    *xyz = *rgb = nullptr; *tri = nullptr; *nv = *nt = 0;
+    if (!(grid_len > 0)) { set_error("[ClusteringMeshSimplification]::[ERROR]::Grid length cannot be less than 0."); return OPB_ERR_INVALID; }
+    OPB_CUDA(cudaSetDevice(v->desc.device));
+    int n_slots;
+    unsigned int *d_counts;
+    unsigned long long tris;
+    int rc = mesh_count(v, &n_slots, &d_counts, &tris);
+    if (rc || tris == 0) return rc;
+    if (tris > 0x2AAAAAAAull) { set_error("mesh of %llu triangles exceeds 32-bit vertex indices", tris); return OPB_ERR_CAPACITY; }
+    const size_t nfl = (size_t)tris * 9;
+    float *d_xyz = nullptr, *d_rgb = nullptr;
+    unsigned int *d_tri = nullptr;
+    cudaError_t e = cudaMalloc(&d_xyz, nfl * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_rgb, nfl * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_tri, (size_t)tris * 3 * sizeof(unsigned int));
+    if (e != cudaSuccess)
+    {
+        cudaFree(d_xyz); cudaFree(d_rgb); cudaFree(d_tri);
+        set_error("cudaMalloc of the mesh buffers failed: %s", cudaGetErrorString(e));
+        return OPB_ERR_CUDA;
+    }
+    const float res = v->desc.voxel_resolution;
+    mc_emit_kernel<<<n_slots, 512, 0, v->stream>>>(v->dev, n_slots, d_counts, res, (float)kCube * res, res / 2, d_xyz, d_rgb);
+    iota_kernel<<<v->sm_count * 8, 256, 0, v->stream>>>(d_tri, (size_t)tris * 3); // three fresh vertices per triangle
+    float *r_p = nullptr, *r_c = nullptr;
+    unsigned int *r_t = nullptr;
+    size_t r_nv = 0, r_nt = 0;
+    rc = cudaGetLastError() == cudaSuccess ? OPB_OK : OPB_ERR_CUDA;
+    if (rc == OPB_OK)
+        rc = clustering_simplify_device(v->sm_count, v->stream, d_xyz, d_rgb, (size_t)tris * 3, d_tri, (size_t)tris, grid_len, &r_p, &r_c, &r_t, &r_nv, &r_nt);
+    else set_error("mesh extraction failed");
+    cudaFree(d_xyz); cudaFree(d_rgb); cudaFree(d_tri);
+    if (rc) return rc;
+    rc = mesh_result_to_host(v->stream, r_p, r_c, r_t, r_nv, r_nt, xyz, rgb, tri);
+    if (rc) return rc;
+    *nv = r_nv; *nt = r_nt;
+    return OPB_OK;
+}
+
 int opb_volume_count_mesh(opb_volume *v, size_t *nv, size_t *nt)
 {
     if (!v || !nv || !nt) { set_error("NULL argument"); return OPB_ERR_INVALID; }

@@ -55,4 +55,10 @@ void build_frame_params(const opb_volume *v, const float *pose_cm, int depth_typ
 int volume_reinit_slots(opb_volume *v, size_t first, size_t n);
 int volume_rebuild_table(opb_volume *v, int n_alloc);
 int halo_drop_ghosts(opb_volume *v); // opb_halo.cu
+// opb_meshpost.cu: TriangleMesh::ClusteringSimplify on device-resident arrays (outputs are cudaMalloc'ed), and the download
+// of such a result into malloc'ed host buffers (frees the device copies)
+int clustering_simplify_device(int sm_count, cudaStream_t s, const float *d_points, const float *d_colors, size_t nv, const unsigned int *d_tri,
+                               size_t nt, float grid_len, float **o_points, float **o_colors, unsigned int **o_tri, size_t *o_nv, size_t *o_nt);
+int mesh_result_to_host(cudaStream_t s, float *d_points, float *d_colors, unsigned int *d_tri, size_t nv, size_t nt, float **points, float **colors,
+                        uint32_t **triangles);
 }

@@ -230,6 +230,31 @@ class CubeHandler:
             capi.lib.opb_free(p)
         return pts, col, t
 
+    def ExtractTriangleMeshClustered(self, grid_len: float):
+        """ExtractTriangleMesh followed by TriangleMesh::ClusteringSimplify(grid_len) (example/DenseFusion/DenseFusion.cpp:99-105)
+        with the raw mesh staying on the device -> onepiece_b200.mesh.TriangleMesh"""
+        from .mesh import TriangleMesh, _take
+        xyz, rgb, tri = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nv, nt = C.c_size_t(0), C.c_size_t(0)
+        capi.check(capi.lib.opb_volume_extract_mesh_clustered(self._h, grid_len, C.byref(xyz), C.byref(rgb), C.byref(tri), C.byref(nv), C.byref(nt)))
+        return TriangleMesh(_take(xyz, C.c_float, nv.value * 3, (nv.value, 3)), _take(rgb, C.c_float, nv.value * 3, (nv.value, 3)),
+                            _take(tri, C.c_uint32, nt.value * 3, (nt.value, 3)))
+
+    # -- the reference's .cubes stream (CubeHandler.h:40-69,113-128) ---------------------------------------
+    def WriteToFile(self, filename: str) -> bool:
+        from . import formats
+        ids, vox = self.GetCubeMap()
+        formats.write_cubes(filename, ids, vox)
+        return True
+
+    def ReadFromFile(self, filename: str) -> bool:
+        from . import formats
+        got = formats.read_cubes(filename)
+        if got is None:
+            return False
+        self.SetCubeMap(*got)
+        return True
+
     def CountMesh(self):
         nv, nt = C.c_size_t(0), C.c_size_t(0)
         capi.check(capi.lib.opb_volume_count_mesh(self._h, C.byref(nv), C.byref(nt)))

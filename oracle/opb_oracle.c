@@ -1467,3 +1467,127 @@ void orc_bilateral_filter(const float *src, int w, int h, int d, double sigma_co
         }
     free(lut); free(sw); free(dy); free(dx);
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Mesh post-processing: what the fusion mains run on the Marching-Cubes output before writing the
+ * PLY (example/DenseFusion/DenseFusion.cpp:105, example/ImageSequenceIntegration.cpp:56).
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct
+{
+    int key[3];
+    int rep;     /* grid_map[..].first: the first vertex (in triangle order) that fell into the cell */
+    int count;   /* grid_map[..].second */
+    float sum[3];/* grid_to_point[..] */
+    int used;
+} cell_t;
+static unsigned long cell_hash(const int *k)
+{
+    return ((unsigned long)(long)k[0] * 73856093ul) ^ ((unsigned long)(long)k[1] * 19349663ul) ^ ((unsigned long)(long)k[2] * 83492791ul);
+}
+/* TriangleMesh::ClusteringSimplify (src/Geometry/TriangleMesh.cpp:53-58) = ClusteringSimplification
+ * (src/Geometry/MeshSimplification.cpp:579-657) + UpdateMesh (:114-139) + CompactMesh (:314-343) on a mesh WITHOUT normals
+ * (Marching-Cubes output; with normals CompactMesh would recompute them, see orc_compute_normals).
+ * points/colors are updated in place and compacted, triangles likewise; returns the new counts.  colors may be NULL. */
+int orc_clustering_simplify(float *points, float *colors, long *n_points, uint32_t *tri, long *n_tris, float grid_len)
+{
+    if (grid_len <= 0) return -1; /* "[ClusteringMeshSimplification]::[ERROR]::Grid length cannot be less than 0." */
+    const long nt = *n_tris, nv = *n_points;
+    long cap = 16;
+    while (cap < 6 * nt + 16) cap <<= 1;
+    cell_t *cells = (cell_t *)calloc(cap, sizeof(cell_t));
+    unsigned char *deleted = (unsigned char *)calloc((size_t)(nt > 0 ? nt : 1), 1);
+    for (long i = 0; i < nt; ++i)
+    {
+        cell_t *c3[3];
+        const uint32_t vtx[3] = {tri[3 * i], tri[3 * i + 1], tri[3 * i + 2]};
+        for (int k = 0; k < 3; ++k)
+        {
+            const float *p = points + 3 * (long)vtx[k];
+            /* GetGridIndex (:575-578) */
+            const int key[3] = {(int)floorf(p[0] / grid_len), (int)floorf(p[1] / grid_len), (int)floorf(p[2] / grid_len)};
+            unsigned long h = cell_hash(key) & (cap - 1);
+            while (cells[h].used && (cells[h].key[0] != key[0] || cells[h].key[1] != key[1] || cells[h].key[2] != key[2])) h = (h + 1) & (cap - 1);
+            cell_t *c = &cells[h];
+            if (!c->used)
+            {
+                c->used = 1; c->key[0] = key[0]; c->key[1] = key[1]; c->key[2] = key[2];
+                c->rep = (int)vtx[k]; c->count = 1;
+                c->sum[0] = p[0]; c->sum[1] = p[1]; c->sum[2] = p[2];
+            }
+            else
+            {
+                c->sum[0] += p[0]; c->sum[1] += p[1]; c->sum[2] += p[2];
+                c->count += 1;
+            }
+            c3[k] = c;
+        }
+        const int v1 = c3[0]->rep, v2 = c3[1]->rep, v3 = c3[2]->rep;
+        if (v1 == v2 || v1 == v3 || v2 == v3) deleted[i] = 1;
+        else { tri[3 * i] = v1; tri[3 * i + 1] = v2; tri[3 * i + 2] = v3; }
+    }
+    /* UpdateMesh: drop deleted triangles, move every representative to the mean of its cell */
+    long kept = 0;
+    for (long i = 0; i < nt; ++i)
+    {
+        if (deleted[i]) continue;
+        tri[3 * kept] = tri[3 * i]; tri[3 * kept + 1] = tri[3 * i + 1]; tri[3 * kept + 2] = tri[3 * i + 2];
+        ++kept;
+    }
+    for (long h = 0; h < cap; ++h)
+        if (cells[h].used)
+            for (int a = 0; a < 3; ++a) points[3 * (long)cells[h].rep + a] = cells[h].sum[a] / (float)cells[h].count;
+    /* CompactMesh: keep the points some triangle still references, in index order */
+    long *remap = (long *)malloc(sizeof(long) * (nv ? nv : 1));
+    for (long i = 0; i < nv; ++i) remap[i] = -1;
+    for (long i = 0; i < 3 * kept; ++i) remap[tri[i]] = 0;
+    long re_local = 0;
+    for (long i = 0; i < nv; ++i)
+    {
+        if (remap[i] < 0) continue;
+        for (int a = 0; a < 3; ++a) points[3 * re_local + a] = points[3 * i + a];
+        if (colors)
+            for (int a = 0; a < 3; ++a) colors[3 * re_local + a] = colors[3 * i + a];
+        remap[i] = re_local++;
+    }
+    for (long i = 0; i < 3 * kept; ++i) tri[i] = (uint32_t)remap[tri[i]];
+    *n_points = re_local;
+    *n_tris = kept;
+    free(cells); free(deleted); free(remap);
+    return 0;
+}
+/* Eigen Vector3f::normalize(): z = squaredNorm() (redux order a0 + (a1 + a2)); if (z > 0) v /= sqrt(z) */
+static void normalize3(float *v)
+{
+    const float z = v[0] * v[0] + (v[1] * v[1] + v[2] * v[2]);
+    if (z > 0)
+    {
+        const float n = sqrtf(z);
+        v[0] /= n; v[1] /= n; v[2] /= n;
+    }
+}
+/* TriangleMesh::ComputeNormals (src/Geometry/TriangleMesh.cpp:95-127): unit face normals, vertex normal = normalised sum of
+ * the normals of the faces that reference the vertex, in reference order (ascending triangle index, UpdateReferences
+ * MeshSimplification.cpp:531-541 -- a triangle naming a vertex twice contributes twice). */
+void orc_compute_normals(const float *points, long n_points, const uint32_t *tri, long n_tris, float *normals)
+{
+    float *fn = (float *)malloc(sizeof(float) * 3 * (n_tris ? n_tris : 1));
+    for (long i = 0; i < n_tris; ++i)
+    {
+        const float *p1 = points + 3 * (long)tri[3 * i], *p2 = points + 3 * (long)tri[3 * i + 1], *p3 = points + 3 * (long)tri[3 * i + 2];
+        const float a[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]}, b[3] = {p3[0] - p1[0], p3[1] - p1[1], p3[2] - p1[2]};
+        float *n = fn + 3 * i;
+        n[0] = a[1] * b[2] - a[2] * b[1];
+        n[1] = a[2] * b[0] - a[0] * b[2];
+        n[2] = a[0] * b[1] - a[1] * b[0];
+        normalize3(n);
+    }
+    for (long i = 0; i < 3 * n_points; ++i) normals[i] = 0;
+    for (long i = 0; i < n_tris; ++i)
+        for (int k = 0; k < 3; ++k)
+        {
+            float *v = normals + 3 * (long)tri[3 * i + k];
+            v[0] += fn[3 * i]; v[1] += fn[3 * i + 1]; v[2] += fn[3 * i + 2];
+        }
+    for (long i = 0; i < n_points; ++i) normalize3(normals + 3 * i);
+    free(fn);
+}

@@ -114,6 +114,11 @@ orc_volume *orc_volume_transform(const orc_volume *v, const float *trans_cm, int
 int orc_volume_merge(orc_volume *v, const orc_volume *other);
 float orc_volume_resolution(const orc_volume *v);
 
+/* TriangleMesh::ClusteringSimplify (TriangleMesh.cpp:53-58, MeshSimplification.cpp:579-657,114-139,314-343) in place; 0 or -1 */
+int orc_clustering_simplify(float *points, float *colors, long *n_points, uint32_t *tri, long *n_tris, float grid_len);
+/* TriangleMesh::ComputeNormals (TriangleMesh.cpp:95-127) */
+void orc_compute_normals(const float *points, long n_points, const uint32_t *tri, long n_tris, float *normals);
+
 /* caller-side depth pre-filter: tool::ConvertDepthTo32F (ImageProcessing.cpp:68-91), tool::BilateralFilter (:64-67) */
 void orc_convert_depth_32f(const void *depth, int is_u16, long n, float depth_scale, float *out);
 void orc_bilateral_filter(const float *src, int w, int h, int d, double sigma_color, double sigma_space, float *dst);

@@ -73,6 +73,9 @@ def lib():
     L.orc_single_iteration.restype = c_l
     L.orc_single_iteration.argtypes = [c_p, c_p, c_i] + [c_f] * 4 + [c_p, c_i, c_p, c_p, c_l]
     L.orc_frame_preprocess.argtypes = [c_p, c_f]
+    L.orc_clustering_simplify.restype = c_i
+    L.orc_clustering_simplify.argtypes = [c_p, c_p, c_p, c_p, c_p, c_f]
+    L.orc_compute_normals.argtypes = [c_p, c_l, c_p, c_l, c_p]
     L.orc_volume_transform.restype = c_p
     L.orc_volume_transform.argtypes = [c_p, c_p, c_i, c_f]
     L.orc_volume_merge.restype = c_i
@@ -365,4 +368,26 @@ def bilateral_filter(src, d=7, sigma_color=0.03, sigma_space=4.5):
     src = np.ascontiguousarray(src, np.float32)
     out = np.zeros_like(src)
     lib().orc_bilateral_filter(_ptr(src), src.shape[1], src.shape[0], d, sigma_color, sigma_space, _ptr(out))
+    return out
+
+
+def clustering_simplify(points, colors, triangles, grid_len):
+    """TriangleMesh::ClusteringSimplify(grid_len) -> (points, colors, triangles) of the simplified mesh, or None for the
+    reference's error path (grid_len <= 0)."""
+    pts = np.array(points, np.float32, copy=True).reshape(-1, 3)
+    col = None if colors is None else np.array(colors, np.float32, copy=True).reshape(-1, 3)
+    tri = np.array(triangles, np.uint32, copy=True).reshape(-1, 3)
+    nv, nt = c_l(len(pts)), c_l(len(tri))
+    rc = lib().orc_clustering_simplify(_ptr(pts), _ptr(col), C.byref(nv), _ptr(tri), C.byref(nt), grid_len)
+    if rc != 0:
+        return None
+    return pts[: nv.value].copy(), (None if col is None else col[: nv.value].copy()), tri[: nt.value].copy()
+
+
+def compute_normals(points, triangles):
+    """TriangleMesh::ComputeNormals"""
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    tri = np.ascontiguousarray(triangles, np.uint32).reshape(-1, 3)
+    out = np.zeros_like(pts)
+    lib().orc_compute_normals(_ptr(pts), len(pts), _ptr(tri), len(tri), _ptr(out))
     return out

@@ -210,6 +210,68 @@ void ref_volume_merge_transformed(void *h, void *other, const float *trans_cm)
     ((RefVolume *)h)->handler.Merge(((RefVolume *)other)->handler, PoseFromColMajor(trans_cm));
 }
 float ref_volume_resolution(void *h) { return (float)static_cast<HandlerPeek *>(&((RefVolume *)h)->handler)->para().VoxelResolution; }
+// TriangleMesh::ClusteringSimplify (TriangleMesh.cpp:53-58) on caller-supplied arrays; results copied back (buffers must hold
+// the input sizes).  with_normals != 0: the mesh gets ComputeNormals() first, so CompactMesh recomputes them (normals out).
+// Returns seconds spent in ClusteringSimplify.
+double ref_clustering_simplify(float *points, float *colors, long *n_points, uint32_t *tri, long *n_tris, float grid_len, int with_normals,
+                               float *normals)
+{
+    geometry::TriangleMesh mesh;
+    mesh.points.resize(*n_points);
+    if (colors) mesh.colors.resize(*n_points);
+    for (long i = 0; i < *n_points; ++i)
+    {
+        mesh.points[i] = geometry::Point3(points[3 * i], points[3 * i + 1], points[3 * i + 2]);
+        if (colors) mesh.colors[i] = geometry::Point3(colors[3 * i], colors[3 * i + 1], colors[3 * i + 2]);
+    }
+    mesh.triangles.resize(*n_tris);
+    for (long i = 0; i < *n_tris; ++i) mesh.triangles[i] = geometry::Point3ui(tri[3 * i], tri[3 * i + 1], tri[3 * i + 2]);
+    if (with_normals) mesh.ComputeNormals();
+    double t0 = Now();
+    auto out = mesh.ClusteringSimplify(grid_len);
+    double dt = Now() - t0;
+    *n_points = (long)out->points.size();
+    *n_tris = (long)out->triangles.size();
+    for (long i = 0; i < *n_points; ++i)
+        for (int k = 0; k < 3; ++k)
+        {
+            points[3 * i + k] = (float)out->points[i](k);
+            if (colors) colors[3 * i + k] = (float)out->colors[i](k);
+            if (with_normals && normals) normals[3 * i + k] = (float)out->normals[i](k);
+        }
+    for (long i = 0; i < *n_tris; ++i)
+        for (int k = 0; k < 3; ++k) tri[3 * i + k] = out->triangles[i](k);
+    return dt;
+}
+// TriangleMesh::WriteToPLY (TriangleMesh.cpp:128-131 -> tool::WritePLY, PLYManager.cpp:188-276)
+bool ref_write_ply(const char *path, const float *points, const float *normals, const float *colors, long n_points, const uint32_t *tri, long n_tris)
+{
+    geometry::TriangleMesh mesh;
+    mesh.points.resize(n_points);
+    if (normals) mesh.normals.resize(n_points);
+    if (colors) mesh.colors.resize(n_points);
+    for (long i = 0; i < n_points; ++i)
+    {
+        mesh.points[i] = geometry::Point3(points[3 * i], points[3 * i + 1], points[3 * i + 2]);
+        if (normals) mesh.normals[i] = geometry::Point3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]);
+        if (colors) mesh.colors[i] = geometry::Point3(colors[3 * i], colors[3 * i + 1], colors[3 * i + 2]);
+    }
+    mesh.triangles.resize(n_tris);
+    for (long i = 0; i < n_tris; ++i) mesh.triangles[i] = geometry::Point3ui(tri[3 * i], tri[3 * i + 1], tri[3 * i + 2]);
+    return mesh.WriteToPLY(path);
+}
+// TriangleMesh::ComputeNormals (TriangleMesh.cpp:95-127)
+void ref_compute_normals(const float *points, long n_points, const uint32_t *tri, long n_tris, float *normals)
+{
+    geometry::TriangleMesh mesh;
+    mesh.points.resize(n_points);
+    for (long i = 0; i < n_points; ++i) mesh.points[i] = geometry::Point3(points[3 * i], points[3 * i + 1], points[3 * i + 2]);
+    mesh.triangles.resize(n_tris);
+    for (long i = 0; i < n_tris; ++i) mesh.triangles[i] = geometry::Point3ui(tri[3 * i], tri[3 * i + 1], tri[3 * i + 2]);
+    mesh.ComputeNormals();
+    for (long i = 0; i < n_points; ++i)
+        for (int k = 0; k < 3; ++k) normals[3 * i + k] = (float)mesh.normals[i](k);
+}
 // CubeHandler::ExtractTriangleMesh (CubeHandler.cpp:9-44). Returns seconds; sizes through out params.
 double ref_volume_extract_mesh(void *h, long *n_points, long *n_triangles)
 {

@@ -52,6 +52,11 @@ def lib(kind: str = "f32"):
     L.ref_volume_merge_transformed.argtypes = [c_p, c_p, c_p]
     L.ref_volume_resolution.restype = c_f
     L.ref_volume_resolution.argtypes = [c_p]
+    L.ref_clustering_simplify.restype = c_d
+    L.ref_clustering_simplify.argtypes = [c_p, c_p, c_p, c_p, c_p, c_f, c_i, c_p]
+    L.ref_compute_normals.argtypes = [c_p, c_l, c_p, c_l, c_p]
+    L.ref_write_ply.restype = C.c_bool
+    L.ref_write_ply.argtypes = [C.c_char_p, c_p, c_p, c_p, c_l, c_p, c_l]
     L.ref_marching_cube_cell.restype = c_i
     L.ref_marching_cube_cell.argtypes = [c_p] * 5
     L.ref_frustum.argtypes = [c_f] * 4 + [c_i, c_i, c_p, c_f, c_f, c_p, c_p, c_l, c_p]
@@ -369,3 +374,32 @@ def single_iteration(src_imgs, tgt_imgs, cam, level, T, term=0, kind="f32"):
     n = lib(kind).ref_single_iteration(sa, ta, level, w, h, cam.fx, cam.fy, cam.cx, cam.cy, _ptr(T0), term, _ptr(Tout), _ptr(JTJ),
                                        _ptr(JTr), C.byref(r2), _ptr(pairs), len(pairs))
     return dict(T=_from_cm(Tout), JTJ=JTJ.reshape(6, 6), JTr=JTr, r2=r2.value, pairs=pairs[:n].copy())
+
+
+def clustering_simplify(points, colors, triangles, grid_len, with_normals=False, kind="f32"):
+    """TriangleMesh::ClusteringSimplify of the compiled reference -> (points, colors, triangles, normals or None, seconds)"""
+    pts = np.array(points, np.float32, copy=True).reshape(-1, 3)
+    col = None if colors is None else np.array(colors, np.float32, copy=True).reshape(-1, 3)
+    tri = np.array(triangles, np.uint32, copy=True).reshape(-1, 3)
+    nrm = np.zeros_like(pts) if with_normals else None
+    nv, nt = c_l(len(pts)), c_l(len(tri))
+    dt = lib(kind).ref_clustering_simplify(_ptr(pts), _ptr(col), C.byref(nv), _ptr(tri), C.byref(nt), grid_len, int(with_normals), _ptr(nrm))
+    return (pts[: nv.value].copy(), None if col is None else col[: nv.value].copy(), tri[: nt.value].copy(),
+            None if nrm is None else nrm[: nv.value].copy(), dt)
+
+
+def compute_normals(points, triangles, kind="f32"):
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    tri = np.ascontiguousarray(triangles, np.uint32).reshape(-1, 3)
+    out = np.zeros_like(pts)
+    lib(kind).ref_compute_normals(_ptr(pts), len(pts), _ptr(tri), len(tri), _ptr(out))
+    return out
+
+
+def write_ply(path, points, normals, colors, triangles, kind="f32"):
+    """TriangleMesh::WriteToPLY of the compiled reference"""
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    nrm = None if normals is None else np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+    col = None if colors is None else np.ascontiguousarray(colors, np.float32).reshape(-1, 3)
+    tri = np.ascontiguousarray(triangles, np.uint32).reshape(-1, 3)
+    return lib(kind).ref_write_ply(str(path).encode(), _ptr(pts), _ptr(nrm), _ptr(col), len(pts), _ptr(tri), len(tri))
