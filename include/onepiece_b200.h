@@ -294,6 +294,11 @@ int opb_icp_comm_detach(opb_icp *c);
 /* nearest-neighbour index per source point from the last search of the previous call (-1: none within the
  * threshold), for parity tests against KDTree::KnnSearch */
 int opb_icp_last_nn(opb_icp *c, int32_t *nn, size_t n);
+/* how many exact grid searches the last call performed, of n_source * (max_iteration + 1) queries: the others kept the
+ * certified nearest neighbour of an earlier pass (see csrc/opb_icp.cu, icp_certify_kernel) */
+int opb_icp_last_search_count(opb_icp *c, uint64_t *full_searches);
+/* the same per pass (pass 0 searches everything), for the first min(cap, 64) passes */
+int opb_icp_last_search_trace(opb_icp *c, uint32_t *per_pass, int cap);
 /* CUDA-event timing of the last call when enabled: grid construction and the iteration loop */
 int opb_icp_set_profiling(opb_icp *c, int on);
 int opb_icp_last_timing(opb_icp *c, float *grid_build_ms, float *iterations_ms);

@@ -138,6 +138,8 @@ SIGNATURES = {
     "opb_ipc_close": (C.c_int, [C.c_int, _p]),
     "opb_icp_comm_attach": (C.c_int, [_p, C.c_int, C.c_int, _p]),
     "opb_icp_comm_detach": (C.c_int, [_p]),
+    "opb_icp_last_search_count": (C.c_int, [_p, C.POINTER(C.c_uint64)]),
+    "opb_icp_last_search_trace": (C.c_int, [_p, _p, C.c_int]),
     "opb_icp_last_nn": (C.c_int, [_p, _p, _sz]),
     "opb_icp_set_profiling": (C.c_int, [_p, C.c_int]),
     "opb_icp_last_timing": (C.c_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

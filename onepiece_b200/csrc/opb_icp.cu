@@ -14,8 +14,10 @@
 // and stops as soon as the best squared distance is provably minimal, so the answer is the exact nearest
 // neighbour (distance formula and summation order of nanoflann's L2_Simple_Adaptor).  The walk is capped at the
 // inlier threshold: a neighbour farther than that can never pass CountInliers, so it is reported as "none".
-// An ICP iteration is two launches.  icp_search_kernel: transform + exact nearest neighbour, eight lanes per query (one
-// grid row each) so the row lookups of a query are in flight together.  icp_accumulate_kernel: inlier test + Jacobian row +
+// An ICP iteration is three launches.  icp_certify_kernel: which queries provably keep the nearest neighbour of their last
+// full search (the pose barely moves once the iteration has converged) -- they are answered from the stored index, the rest
+// go on a work list.  icp_search_kernel: transform + exact nearest neighbour + certificate for the queries on the list.
+// icp_accumulate_kernel: inlier test + Jacobian row +
 // the 30-scalar reduction (per-thread fp64 accumulators, warp shuffles, fixed-order CTA partials -> deterministic) and, in
 // the last CTA to finish, the 6x6 solve, the SE(3) exponential and the pose update -- the host is not involved until the end.
 #include <cfloat>
@@ -52,6 +54,10 @@ struct IcpState // device-resident solver state
     double sum_error;
     unsigned int blocks_done;
     unsigned long long n_inliers_local; // this rank's share when the source is split across ranks (== n_inliers otherwise)
+    unsigned int wl_count;              // queries of the current pass whose nearest neighbour could not be certified
+    unsigned long long searched_total;  // full searches done over the whole call (profiling)
+    unsigned int searched_per_pass[64]; // ... and per pass (the first 64)
+    unsigned int pass;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -354,6 +360,13 @@ struct IcpArgs
     int *pairs;             // final pass: inlier flags are turned into pairs by the compaction kernel
     unsigned char *inlier;  // ns flags
     IcpComm comm;           // world <= 1: single GPU
+    // nearest-neighbour certificates (see icp_certify_kernel)
+    float4 *qref;           // ns: query position at the point's last full search; w = displacement budget (NaN: none yet)
+    int2 *nn_ref;           // ns: nearest neighbour found by that search (-1 = none within the inlier radius) and the runner-up
+    float *budget2;         // ns: displacement budget of the two-candidate certificate
+    unsigned int *worklist; // ns
+    float guard;            // extra radius every full search covers beyond its nearest neighbour, in grid cells
+    int certify;            // 0: every pass searches every point (reference behaviour of the search, for A/B tests)
 };
 
 // geometry::TransformPoints: T * (x,y,z,1) then divide by w (Geometry.cpp:19-27)
@@ -367,8 +380,21 @@ __device__ __forceinline__ void transform_point(const float *T, float sx, float 
 
 // scans cells [xa, xb] (clipped to the grid) of row (cy, cz) into the running best (distance, index); ties go to the
 // smaller target index
+// running result of a walk: the two nearest points seen (distance, target index; ties go to the smaller index) and the
+// third smallest distance
+struct Nearest2
+{
+    float d1, d2, d3;
+    int i1, i2;
+};
+__device__ __forceinline__ void nearest2_push(Nearest2 &b, float d, int ti)
+{
+    if (d < b.d1 || (d == b.d1 && ti < b.i1)) { b.d3 = b.d2; b.d2 = b.d1; b.i2 = b.i1; b.d1 = d; b.i1 = ti; }
+    else if (d < b.d2 || (d == b.d2 && ti < b.i2)) { b.d3 = b.d2; b.d2 = d; b.i2 = ti; }
+    else if (d < b.d3) b.d3 = d;
+}
 __device__ __forceinline__ void scan_cells(const IcpGrid &g, const unsigned int *__restrict__ cell_start, const float4 *__restrict__ sorted,
-                                           int xa, int xb, int cy, int cz, float qx, float qy, float qz, float &bd, int &bi)
+                                           int xa, int xb, int cy, int cz, float qx, float qy, float qz, Nearest2 &b)
 {
     xa = max(xa, 0);
     xb = min(xb, g.dim[0] - 1);
@@ -378,9 +404,7 @@ __device__ __forceinline__ void scan_cells(const IcpGrid &g, const unsigned int 
     for (unsigned int k = s; k < e; ++k)
     {
         const float4 t = __ldg(&sorted[k]);
-        const float d = dist2_nanoflann(qx, qy, qz, t.x, t.y, t.z);
-        const int ti = __float_as_int(t.w);
-        if (d < bd || (d == bd && ti < bi)) { bd = d; bi = ti; }
+        nearest2_push(b, dist2_nanoflann(qx, qy, qz, t.x, t.y, t.z), __float_as_int(t.w));
     }
 }
 
@@ -393,17 +417,17 @@ __device__ __forceinline__ void scan_cells(const IcpGrid &g, const unsigned int 
 struct RowPruner
 {
     float fx, ay, az;       // x position in cell units; position inside the home cell along y, z
-    float inv_h2, r2cap, slack;
+    float inv_h2, slack;
     __device__ __forceinline__ float gap(float a, int d) const
     {
         if (d == 0) return 0.0f;
         return fmaxf((d < 0 ? a : 1.0f - a) + (float)(abs(d) - 1) - slack, 0.0f);
     }
-    // x-interval [xlo, xhi] of row (dy, dz) worth scanning given the best so far; false if none
-    __device__ __forceinline__ bool interval(int dy, int dz, float bd, int &xlo, int &xhi) const
+    // x-interval [xlo, xhi] of row (dy, dz) worth scanning given the squared search bound eb; false if none
+    __device__ __forceinline__ bool interval(int dy, int dz, float eb, int &xlo, int &xhi) const
     {
         const float gy = gap(ay, dy), gz = gap(az, dz);
-        const float rem = fminf(bd, r2cap) * inv_h2 - (gy * gy + gz * gz);
+        const float rem = eb * inv_h2 - (gy * gy + gz * gz);
         if (!(rem >= 0.0f)) return false;
         const float half = sqrtf(rem) + slack;
         xlo = (int)floorf(fx - half);
@@ -412,49 +436,79 @@ struct RowPruner
     }
 };
 
-__device__ int grid_nearest(const IcpGrid &g, const unsigned int *__restrict__ cell_start, const float4 *__restrict__ sorted, float qx,
-                            float qy, float qz, float radius)
+struct NnResult
 {
+    int index;      // exact nearest neighbour, -1 if none within the inlier radius
+    int index2;     // second nearest (valid when budget2 > 0)
+    float budget;   // how far the query may move and keep `index` as its strictly nearest neighbour (or keep having none)
+    float budget2;  // ... and keep {index, index2} as its two nearest (see icp_certify_kernel)
+};
+
+// Squared radius the walk has to cover: the best distance so far plus the guard, never beyond inlier radius + guard.
+__device__ __forceinline__ float search_bound(float bd, float guard, float cap_g2)
+{
+    const float r = sqrtf(bd) + guard; // +inf stays +inf
+    return fminf(r * r, cap_g2);
+}
+
+// Exact nearest neighbour with a certificate.  The walk covers every target point within C = sqrt(d1) + guard of the query
+// (d1 = squared distance of the nearest one; C is at most inlier radius + guard), so besides the nearest neighbour it knows
+// a lower bound L2 on the distance of every OTHER point: the second smallest distance seen, or C.  A query that has moved by
+// less than (L2 - sqrt(d1)) / 2 still has the same, strictly nearest neighbour -- no search needed.  If the second nearest
+// point lies inside C as well, the same argument one level up (L3 = third smallest distance seen, or C) says how far the
+// query may move before a third point can interfere: until then the answer is the nearer of the two stored candidates, which
+// settles the queries that sit on the bisector of two target points.  A query with no neighbour within the inlier radius has
+// none as long as it moved by less than (nearest distance seen or C) - inlier radius.  All budgets are shrunk by 1e-4
+// relative and 1 um absolute, orders of magnitude above the float rounding of the distance arithmetic they stand in for.
+__device__ NnResult grid_nearest(const IcpGrid &g, const unsigned int *__restrict__ cell_start, const float4 *__restrict__ sorted, float qx,
+                                 float qy, float qz, float radius, float guard)
+{
+    NnResult out;
+    out.index = out.index2 = -1;
+    out.budget = out.budget2 = -1.0f;
     const float fx = (qx - g.origin[0]) * g.inv_h, fy = (qy - g.origin[1]) * g.inv_h, fz = (qz - g.origin[2]) * g.inv_h;
     const float bound = (float)(1 << 20);
-    if (!(qx == qx && qy == qy && qz == qz && fabsf(fx) < bound && fabsf(fy) < bound && fabsf(fz) < bound)) return -1;
+    if (!(qx == qx && qy == qy && qz == qz && fabsf(fx) < bound && fabsf(fy) < bound && fabsf(fz) < bound)) return out;
     // home cell, not clamped: a query outside the grid starts where it is
     const int hx = (int)floorf(fx), hy = (int)floorf(fy), hz = (int)floorf(fz);
     RowPruner pr;
     pr.fx = fx; pr.ay = fy - hy; pr.az = fz - hz;
     pr.inv_h2 = g.inv_h * g.inv_h;
-    pr.r2cap = radius * radius; // a neighbour farther than this is reported as "none" anyway
     pr.slack = 1e-3f;
-    float bd = __int_as_float(0x7f800000);
-    int bi = -1;
+    const float r2cap = radius * radius; // a neighbour farther than this is reported as "none" anyway
+    const float cap_g = radius + guard, cap_g2 = cap_g * cap_g;
+    const float inf = __int_as_float(0x7f800000);
+    Nearest2 nb;
+    nb.d1 = nb.d2 = nb.d3 = inf;
+    nb.i1 = nb.i2 = -1;
     int xlo, xhi;
-    scan_cells(g, cell_start, sorted, hx, hx, hy, hz, qx, qy, qz, bd, bi);
+    scan_cells(g, cell_start, sorted, hx, hx, hy, hz, qx, qy, qz, nb);
     // ring 0: the rest of the home row
-    if (pr.interval(0, 0, bd, xlo, xhi))
+    if (pr.interval(0, 0, search_bound(nb.d1, guard, cap_g2), xlo, xhi))
     {
-        if (xlo < hx) scan_cells(g, cell_start, sorted, xlo, hx - 1, hy, hz, qx, qy, qz, bd, bi);
-        if (xhi > hx) scan_cells(g, cell_start, sorted, hx + 1, xhi, hy, hz, qx, qy, qz, bd, bi);
+        if (xlo < hx) scan_cells(g, cell_start, sorted, xlo, hx - 1, hy, hz, qx, qy, qz, nb);
+        if (xhi > hx) scan_cells(g, cell_start, sorted, hx + 1, xhi, hy, hz, qx, qy, qz, nb);
     }
     const float m_yz = fminf(fminf(pr.ay, 1.0f - pr.ay), fminf(pr.az, 1.0f - pr.az));
-    const float radius_cells = radius * g.inv_h;
+    const float radius_cells = cap_g * g.inv_h;
     const int r_max = (int)ceilf(radius_cells) + 1;
     for (int r = 1; r <= r_max; ++r)
     {
         // everything within `covered` cells has been seen once ring r-1 is complete
         const float covered = (float)(r - 1) + m_yz - pr.slack;
-        if (covered > 0.0f && bi >= 0 && bd * pr.inv_h2 <= covered * covered) break;
+        float eb = search_bound(nb.d1, guard, cap_g2);
+        if (covered > 0.0f && nb.i1 >= 0 && eb * pr.inv_h2 <= covered * covered) break;
         if (covered > radius_cells) break;
         if (r == 1)
         {
-            // the eight rows around the home row: lanes walk their own list of surviving rows (nearest first), so a warp
-            // iterates as often as its busiest lane has rows and every iteration scans different rows in different lanes
+            // the eight rows around the home row, nearest first; the bound shrinks as better points turn up
             unsigned int mask = 0;
 #pragma unroll
             for (int b = 0; b < 8; ++b)
             {
                 const int dy = (b == 0 || b == 4 || b == 5) ? -1 : ((b == 1 || b == 6 || b == 7) ? 1 : 0);
                 const int dz = (b == 2 || b == 4 || b == 6) ? -1 : ((b == 3 || b == 5 || b == 7) ? 1 : 0);
-                if (pr.interval(dy, dz, bd, xlo, xhi)) mask |= 1u << b;
+                if (pr.interval(dy, dz, eb, xlo, xhi)) mask |= 1u << b;
             }
             while (mask)
             {
@@ -463,32 +517,121 @@ __device__ int grid_nearest(const IcpGrid &g, const unsigned int *__restrict__ c
                 // bit b -> (dy, dz):  0:(-1,0) 1:(+1,0) 2:(0,-1) 3:(0,+1) 4:(-1,-1) 5:(-1,+1) 6:(+1,-1) 7:(+1,+1)
                 const int dy = (b == 0 || b == 4 || b == 5) ? -1 : ((b == 1 || b == 6 || b == 7) ? 1 : 0);
                 const int dz = (b == 2 || b == 4 || b == 6) ? -1 : ((b == 3 || b == 5 || b == 7) ? 1 : 0);
-                if (pr.interval(dy, dz, bd, xlo, xhi)) scan_cells(g, cell_start, sorted, xlo, xhi, hy + dy, hz + dz, qx, qy, qz, bd, bi);
+                if (pr.interval(dy, dz, eb, xlo, xhi))
+                {
+                    scan_cells(g, cell_start, sorted, xlo, xhi, hy + dy, hz + dz, qx, qy, qz, nb);
+                    eb = search_bound(nb.d1, guard, cap_g2);
+                }
             }
         }
         else
         {
             for (int dz = -r; dz <= r; ++dz)
                 for (int dy = -r; dy <= r; dy += (abs(dz) == r ? 1 : 2 * r))
-                    if (pr.interval(dy, dz, bd, xlo, xhi)) scan_cells(g, cell_start, sorted, xlo, xhi, hy + dy, hz + dz, qx, qy, qz, bd, bi);
+                    if (pr.interval(dy, dz, eb, xlo, xhi))
+                    {
+                        scan_cells(g, cell_start, sorted, xlo, xhi, hy + dy, hz + dz, qx, qy, qz, nb);
+                        eb = search_bound(nb.d1, guard, cap_g2);
+                    }
         }
     }
-    if (bi >= 0 && bd > pr.r2cap) return -1;
-    return bi;
+    const float shrink = 1.0f - 1e-4f, abs_slack = 1e-6f;
+    if (nb.i1 >= 0 && nb.d1 <= r2cap)
+    {
+        const float r1 = sqrtf(nb.d1), r2 = sqrtf(nb.d2);
+        const float C = fminf(r1 + guard, cap_g);       // everything closer than this has been seen
+        out.index = nb.i1;
+        out.budget = 0.5f * (fminf(r2, C) - r1) * shrink - abs_slack;
+        if (nb.i2 >= 0 && r2 < C)
+        {
+            out.index2 = nb.i2;
+            out.budget2 = 0.5f * (fminf(sqrtf(nb.d3), C) - r2) * shrink - abs_slack;
+        }
+    }
+    else
+    {
+        const float nearest = nb.i1 >= 0 ? fminf(sqrtf(nb.d1), cap_g) : cap_g; // nothing is closer than this
+        out.budget = (nearest - radius) * shrink - abs_slack;
+    }
+    return out;
 }
 
-// K7: exact nearest neighbour of every transformed source point, one thread per query
+// K7a: which queries keep their nearest neighbour.  One thread per source point: the query is transformed with the current
+// pose exactly as the search would, compared with where it stood at its last full search, and if it moved by less than that
+// search's budget the stored neighbour (or the nearer of the two stored candidates) is still the exact answer, re-tested
+// against the inlier radius with the search's own distance arithmetic; otherwise the point goes on the work list of the
+// search kernel.  A pass over already converged iterations thus costs one streaming read instead of a grid walk per point.
+__global__ void __launch_bounds__(kIcpThreads) icp_certify_kernel(IcpArgs a)
+{
+    __shared__ float sT[16];
+    if (threadIdx.x < 16) sT[threadIdx.x] = a.st->T[threadIdx.x];
+    __syncthreads();
+    const float r2cap = a.search_radius * a.search_radius;
+    const int lane = threadIdx.x & 31;
+    const int n_round = (a.ns + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x)
+    {
+        bool todo = false;
+        if (i < a.ns)
+        {
+            float px, py, pz;
+            transform_point(sT, a.src[3 * i], a.src[3 * i + 1], a.src[3 * i + 2], px, py, pz);
+            const float4 q = a.qref[i];
+            const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
+            const float moved = sqrtf(dx * dx + dy * dy + dz * dz) * (1.0f + 1e-6f);
+            int nn = -1;
+            if (moved < q.w) // false for the NaN budget of a point that was never searched
+            {
+                const int j = a.nn_ref[i].x;
+                if (j >= 0)
+                {
+                    const float d = dist2_nanoflann(px, py, pz, __ldg(&a.tgt[3 * j]), __ldg(&a.tgt[3 * j + 1]), __ldg(&a.tgt[3 * j + 2]));
+                    if (!(d > r2cap)) nn = j;
+                }
+                a.nn[i] = nn;
+            }
+            else if (moved < a.budget2[i])
+            {
+                const int2 jj = a.nn_ref[i];
+                const float da = dist2_nanoflann(px, py, pz, __ldg(&a.tgt[3 * jj.x]), __ldg(&a.tgt[3 * jj.x + 1]), __ldg(&a.tgt[3 * jj.x + 2]));
+                const float db = dist2_nanoflann(px, py, pz, __ldg(&a.tgt[3 * jj.y]), __ldg(&a.tgt[3 * jj.y + 1]), __ldg(&a.tgt[3 * jj.y + 2]));
+                const bool first = da < db || (da == db && jj.x < jj.y);
+                if (!((first ? da : db) > r2cap)) nn = first ? jj.x : jj.y;
+                a.nn[i] = nn;
+            }
+            else
+                todo = true;
+        }
+        // warp-aggregated append
+        const unsigned int m = __ballot_sync(0xffffffffu, todo);
+        if (m)
+        {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(&a.st->wl_count, (unsigned int)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (todo) a.worklist[base + __popc(m & ((1u << lane) - 1u))] = (unsigned int)i;
+        }
+    }
+}
+
+// K7b: exact nearest neighbour (and certificate) of the queries on the work list, one thread per query
 __global__ void __launch_bounds__(kIcpThreads) icp_search_kernel(IcpArgs a)
 {
     __shared__ float sT[16];
     if (threadIdx.x < 16) sT[threadIdx.x] = a.st->T[threadIdx.x];
     __syncthreads();
     const IcpGrid g = a.st->grid;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.ns; i += gridDim.x * blockDim.x)
+    const int n = (int)a.st->wl_count;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x)
     {
+        const int i = (int)a.worklist[w];
         float px, py, pz;
         transform_point(sT, a.src[3 * i], a.src[3 * i + 1], a.src[3 * i + 2], px, py, pz);
-        a.nn[i] = grid_nearest(g, a.cell_start, a.sorted, px, py, pz, a.search_radius);
+        const NnResult r = grid_nearest(g, a.cell_start, a.sorted, px, py, pz, a.search_radius, a.certify ? a.guard * g.h : 0.0f);
+        a.nn[i] = r.index;
+        a.nn_ref[i] = make_int2(r.index, r.index2);
+        a.qref[i] = make_float4(px, py, pz, a.certify ? r.budget : -1.0f);
+        a.budget2[i] = a.certify ? r.budget2 : -1.0f;
     }
 }
 
@@ -668,6 +811,10 @@ __global__ void __launch_bounds__(kIcpThreads) icp_accumulate_kernel(IcpArgs a)
     comm_allreduce(a.comm, a.st->packet, 30);
     if (threadIdx.x != 0) return;
     a.st->blocks_done = 0;
+    a.st->searched_total += a.st->wl_count;
+    if (a.st->pass < 64) a.st->searched_per_pass[a.st->pass] = a.st->wl_count;
+    a.st->pass += 1;
+    a.st->wl_count = 0; // the next pass builds its own work list
     icp_solve_and_update(a, a.st);
 }
 
@@ -794,6 +941,12 @@ struct opb_icp
     unsigned int *d_point_cell = nullptr, *d_cell_count = nullptr, *d_tile_sums = nullptr, *d_cell_start = nullptr;
     int *d_nn = nullptr, *d_pairs = nullptr;
     unsigned char *d_inlier = nullptr;
+    float4 *d_qref = nullptr;          // nearest-neighbour certificates (icp_certify_kernel)
+    int2 *d_nn_ref = nullptr;
+    float *d_budget2 = nullptr;
+    unsigned int *d_worklist = nullptr;
+    unsigned long long last_searched = 0; // full searches of the last call (of ns * (max_iteration + 1) queries)
+    unsigned int last_searched_per_pass[64] = {0};
     double *d_partials = nullptr;
     size_t cap_partials = 0;
     IcpState *d_state = nullptr;
@@ -812,7 +965,14 @@ static int icp_reserve(opb_icp *c, size_t ns, size_t nt)
     if (ns > c->cap_src)
     {
         cudaFree(c->d_src); cudaFree(c->d_nn); cudaFree(c->d_pairs); cudaFree(c->d_inlier);
+        cudaFree(c->d_qref); cudaFree(c->d_nn_ref); cudaFree(c->d_worklist); cudaFree(c->d_budget2);
+        c->d_budget2 = nullptr;
         c->d_src = nullptr; c->d_nn = nullptr; c->d_pairs = nullptr; c->d_inlier = nullptr; c->cap_src = 0;
+        c->d_qref = nullptr; c->d_nn_ref = nullptr; c->d_worklist = nullptr;
+        OPB_CUDA(cudaMalloc(&c->d_qref, ns * sizeof(float4)));
+        OPB_CUDA(cudaMalloc(&c->d_nn_ref, ns * sizeof(int2)));
+        OPB_CUDA(cudaMalloc(&c->d_budget2, ns * sizeof(float)));
+        OPB_CUDA(cudaMalloc(&c->d_worklist, ns * sizeof(unsigned int)));
         OPB_CUDA(cudaMalloc(&c->d_src, ns * 3 * sizeof(float)));
         OPB_CUDA(cudaMalloc(&c->d_nn, ns * sizeof(int)));
         OPB_CUDA(cudaMalloc(&c->d_pairs, ns * 2 * sizeof(int)));
@@ -886,6 +1046,7 @@ void opb_icp_destroy(opb_icp *c)
     cudaFree(c->d_src); cudaFree(c->d_tgt); cudaFree(c->d_nrm); cudaFree(c->d_sorted); cudaFree(c->d_point_cell);
     cudaFree(c->d_cell_count); cudaFree(c->d_tile_sums); cudaFree(c->d_cell_start); cudaFree(c->d_nn); cudaFree(c->d_pairs);
     cudaFree(c->d_inlier); cudaFree(c->d_partials); cudaFree(c->d_state); cudaFree(c->d_mailbox);
+    cudaFree(c->d_qref); cudaFree(c->d_nn_ref); cudaFree(c->d_worklist); cudaFree(c->d_budget2);
     if (c->h_state) cudaFreeHost(c->h_state);
     for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -963,16 +1124,25 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     a.sq_threshold = par->threshold * par->threshold;
     a.final_pass = 0; a.pairs = c->d_pairs; a.inlier = c->d_inlier;
     a.comm = c->comm;
+    // nearest-neighbour certificates: a NaN budget marks "never searched"
+    a.qref = c->d_qref; a.nn_ref = c->d_nn_ref; a.worklist = c->d_worklist; a.budget2 = c->d_budget2;
+    static const float k_guard = getenv("OPB_ICP_GUARD") ? (float)atof(getenv("OPB_ICP_GUARD")) : 0.125f;
+    static const int k_certify = getenv("OPB_ICP_CERTIFY") ? atoi(getenv("OPB_ICP_CERTIFY")) : 1;
+    a.guard = k_guard; a.certify = k_certify;
+    if (ns) OPB_CUDA(cudaMemsetAsync(c->d_qref, 0xFF, ns * sizeof(float4), s));
     const int nb_need = ns ? (int)((ns + kIcpThreads - 1) / kIcpThreads) : 1; // an empty share still takes part in the exchange
     // developer knobs for grid-size sweeps (CTAs per SM); the defaults are the measured optimum on B200
     static const int k_search = getenv("OPB_ICP_SEARCH_CTAS") ? atoi(getenv("OPB_ICP_SEARCH_CTAS")) : 8;
     static const int k_accum = getenv("OPB_ICP_ACCUM_CTAS") ? atoi(getenv("OPB_ICP_ACCUM_CTAS")) : 2;
     const int nb_s = nb_need < c->sm_count * k_search ? nb_need : c->sm_count * k_search; // search: grid-stride over the points
     const int nb_a = nb_need < c->sm_count * k_accum ? nb_need : c->sm_count * k_accum;   // accumulate: few partials for the last CTA to sum
+    static const int k_cert = getenv("OPB_ICP_CERTIFY_CTAS") ? atoi(getenv("OPB_ICP_CERTIFY_CTAS")) : 8;
+    const int nb_c = nb_need < c->sm_count * k_cert ? nb_need : c->sm_count * k_cert;
     for (int it = 0; it <= par->max_iteration; ++it)
     {
         // the last pass is the final CountInliers with the final T (ICP.cpp:90-91,206-207)
         a.final_pass = it == par->max_iteration;
+        icp_certify_kernel<<<nb_c, kIcpThreads, 0, s>>>(a);
         icp_search_kernel<<<nb_s, kIcpThreads, 0, s>>>(a);
         if (point_to_plane) icp_accumulate_kernel<true><<<nb_a, kIcpThreads, 0, s>>>(a);
         else icp_accumulate_kernel<false><<<nb_a, kIcpThreads, 0, s>>>(a);
@@ -1000,6 +1170,8 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
             return OPB_ERR_CUDA;
         }
     }
+    c->last_searched = h->searched_total;
+    memcpy(c->last_searched_per_pass, h->searched_per_pass, sizeof(c->last_searched_per_pass));
     res->n_inliers = (size_t)h->n_inliers;
     res->n_local_pairs = (size_t)h->n_inliers_local;
     res->rmse = sqrt(h->sum_error / (double)h->n_inliers); // CountInliers: sqrt(sum_error / inliers.size())
@@ -1044,6 +1216,18 @@ int opb_icp_point_to_point(opb_icp *c, const float *src_xyz, size_t ns, const fl
                            const opb_icp_params *params, opb_icp_result *result, int32_t *pairs, size_t pairs_cap)
 {
     return icp_run(c, src_xyz, ns, tgt_xyz, nullptr, nt, init_T, params, result, pairs, pairs_cap, false);
+}
+int opb_icp_last_search_count(opb_icp *c, uint64_t *full_searches)
+{
+    if (!c || !full_searches) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    *full_searches = c->last_searched;
+    return OPB_OK;
+}
+int opb_icp_last_search_trace(opb_icp *c, uint32_t *per_pass, int cap)
+{
+    if (!c || !per_pass) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    for (int i = 0; i < cap && i < 64; ++i) per_pass[i] = c->last_searched_per_pass[i];
+    return OPB_OK;
 }
 int opb_icp_comm_buffer(opb_icp *c, void **d_buffer, unsigned char ipc_handle[OPB_IPC_HANDLE_BYTES])
 {

@@ -115,3 +115,65 @@ def test_full_size_frame_pair_recovers_the_motion():
     dt, dr = pose_delta(r1.T_iterated, truth)
     assert dt < 2e-3 and dr < 2e-3
     assert len(r1.correspondence_set_index) > 0.99 * len(src)
+
+
+@pytest.mark.parametrize("iters", [1, 2, 3, 6, 12])
+def test_certified_neighbours_are_the_exact_ones(iters):
+    """After a few iterations most queries keep the neighbour of an earlier full search because they provably moved less than
+    that search's budget (icp_certify_kernel).  The neighbours of the FINAL pass -- certified or searched -- must be the exact
+    nearest neighbours the oracle's brute force finds for the final pose."""
+    import ctypes as C
+
+    from onepiece_b200 import capi
+    c0 = scenes.Camera()
+    cam = scenes.Camera(c0.fx / 2, c0.fy / 2, c0.cx / 2, c0.cy / 2, 320, 240, 1000.0)
+    d0, _, _, n0 = scenes.room(cam, 0, with_normals=True)
+    d1, _, _ = scenes.room(cam, 4)
+    tgt, src = scenes.backproject(d0, cam), scenes.backproject(d1, cam)
+    nrm = np.ascontiguousarray(n0.reshape(-1, 3)[(d0 > 0).reshape(-1)])
+    thr = 0.05
+    r = reg.PointToPlane(reg.PointCloud(src), reg.PointCloud(tgt, nrm), np.eye(4), reg.ICPParameter(iters, thr, 1.0))
+    nn = reg.last_nn(len(src))
+    n_search = C.c_uint64(0)
+    capi.check(capi.lib.opb_icp_last_search_count(reg._Workspace.get(0), C.byref(n_search)))
+    total = len(src) * (iters + 1)
+    assert 0 < n_search.value <= total
+    if iters >= 6:
+        assert n_search.value < 0.6 * total, (n_search.value, total)   # the converged passes are answered from certificates
+    T = r.T_iterated.astype(np.float32)
+    # geometry::TransformPoints in float, as the search kernel does it
+    moved = np.stack([(T[k, 0] * src[:, 0] + T[k, 1] * src[:, 1]) + T[k, 2] * src[:, 2] + T[k, 3] for k in range(3)], 1).astype(np.float32)
+    ref = oracleapi.nearest(moved, tgt)
+    dist = np.linalg.norm(moved.astype(np.float64) - tgt[ref], axis=1)
+    found = nn >= 0
+    clear = np.abs(dist - thr) > 1e-4          # away from the inlier radius the found / not-found decision is unambiguous here
+    assert np.array_equal(nn[found], ref[found])
+    assert np.all(dist[~found & clear] > thr) and np.all(dist[found & clear] < thr)
+    assert found.mean() > 0.9
+
+
+def test_certification_does_not_change_the_result(tmp_path):
+    """The same registration with certificates switched off (every pass searches every point): identical pairs and pose bits."""
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from onepiece_b200 import registration as reg, scenes\n"
+        "cam = scenes.Camera()\n"
+        "d0, _, _, n0 = scenes.room(cam, 0, with_normals=True); d1, _, _ = scenes.room(cam, 2)\n"
+        "tgt, src = scenes.backproject(d0, cam), scenes.backproject(d1, cam)\n"
+        "nrm = np.ascontiguousarray(n0.reshape(-1, 3)[(d0 > 0).reshape(-1)])\n"
+        "r = reg.PointToPlane(reg.PointCloud(src), reg.PointCloud(tgt, nrm), np.eye(4), reg.ICPParameter(30, 0.05, 1.0))\n"
+        "np.savez(sys.argv[1], T=r.T, Ti=r.T_iterated, pairs=r.correspondence_set_index, rmse=r.rmse)\n" % ROOT)
+    out = {}
+    for flag in ("1", "0"):
+        path = str(tmp_path / f"icp_{flag}.npz")
+        env = dict(os.environ, OPB_ICP_CERTIFY=flag)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+        out[flag] = np.load(path)
+    assert np.array_equal(out["1"]["pairs"], out["0"]["pairs"])
+    assert np.array_equal(out["1"]["Ti"].view(np.uint32), out["0"]["Ti"].view(np.uint32))
+    assert np.array_equal(out["1"]["T"].view(np.uint32), out["0"]["T"].view(np.uint32))
+    assert float(out["1"]["rmse"]) == float(out["0"]["rmse"])
