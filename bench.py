@@ -39,6 +39,19 @@ def parse_args():
     return ap.parse_args()
 
 
+def measured_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` summary of this round"""
+    import glob
+    import re
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_{kernel}_ncu_full.md")), reverse=True):
+        tot = 0.0
+        for m in re.finditer(r"dram__bytes_(?:read|write)\.sum \| ([0-9.]+) \| (\w+)", open(path).read()):
+            tot += float(m.group(1)) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(2), 1.0)
+        if tot:
+            return int(tot), os.path.relpath(path, ROOT)
+    return None, None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -359,7 +372,9 @@ def run_ours(args):
     icp_iter_ms = icp_loop_ms / nprof_steps / (ICP_ITERS + 1)
     icp_bytes = n_pts * 12 + n_pts * 36  # N_s*12 (source) + N_inl*(12+12+12) (nn point, normal, source)
     icp_ach = icp_bytes / (icp_iter_ms * 1e-3) / 1e9 if icp_iter_ms > 0 else 0.0
-    launches_per_step = 8 + 2 * (ICP_ITERS + 1) + 2 + 3  # grid build, (search + accumulate) x 31, Kabsch sums, pack/select/integrate
+    launches_per_step = 8 + 3 * (ICP_ITERS + 1) + 2 + 3  # grid build, (certify + search + accumulate) x 31, Kabsch sums, pack/select/integrate
+    searched = C.c_uint64(0)
+    capi.lib.opb_icp_last_search_count(icp, C.byref(searched))
     out = {
         "metric": METRIC, "value": world * K / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -373,9 +388,9 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "integrate_kernel (the kernel north_star sets the >=60% target for)",
                      "achieved": achieved, "peak": pk["hbm_gbs"], "peak_source": pk_kind, "unit": "GB/s",
                      "frac": achieved / pk["hbm_gbs"], "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": k2_ms,
-                     "traffic": None},
-        "roofline_icp": {"bound": "hbm", "kernel": "icp_search_kernel + icp_accumulate_kernel, one ICP iteration (time-dominant; working set "
-                                                   "L2-resident, latency-bound)",
+                     "traffic": measured_traffic("integrate_kernel")[0], "traffic_source": measured_traffic("integrate_kernel")[1]},
+        "roofline_icp": {"bound": "hbm", "kernel": "icp_certify_kernel + icp_search_kernel + icp_accumulate_kernel, one ICP pass (time-dominant; "
+                                                   "working set L2-resident, latency-bound)",
                          "achieved": icp_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": icp_ach / pk["hbm_gbs"],
                          "algorithmic_bytes_per_launch": int(icp_bytes), "kernel_ms": icp_iter_ms, "traffic": None},
         "e2e": {"value": world * K / (e2e_ms * 1e-3), "unit": UNIT,

@@ -877,20 +877,27 @@ __global__ void __launch_bounds__(kIcpThreads) icp_final_reduce_kernel(const dou
     comm_allreduce(comm, st->packet, 16);
 }
 
-// ordered compaction of inlier pairs (source index ascending, like the reference's push_back loop)
-__global__ void __launch_bounds__(1024) icp_compact_kernel(const int *nn, const unsigned char *inlier, int ns, int *pairs,
-                                                           unsigned long long cap)
+// ordered compaction of inlier pairs (source index ascending, like the reference's push_back loop): inliers per tile of 1024
+// points, exclusive scan of the tile counts by one CTA, then every tile places its own pairs
+constexpr int kPairTile = 1024;
+__global__ void __launch_bounds__(kPairTile) icp_pair_count_kernel(const unsigned char *inlier, int ns, unsigned int *tile_counts)
+{
+    const int i = blockIdx.x * kPairTile + threadIdx.x;
+    const int n = __syncthreads_count(i < ns && inlier[i]);
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = (unsigned int)n;
+}
+__global__ void __launch_bounds__(1024) icp_pair_scan_kernel(unsigned int *tile_counts, int n_tiles)
 {
     __shared__ unsigned int warp_sums[32];
     __shared__ unsigned int carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < ns; base += 1024)
+    for (int base = 0; base < n_tiles; base += 1024)
     {
         const int i = base + threadIdx.x;
-        const unsigned int f = i < ns ? inlier[i] : 0u;
-        unsigned int inc = f;
+        const unsigned int v = i < n_tiles ? tile_counts[i] : 0u;
+        unsigned int inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1)
         {
@@ -911,12 +918,38 @@ __global__ void __launch_bounds__(1024) icp_compact_kernel(const int *nn, const 
             warp_sums[lane] = w;
         }
         __syncthreads();
-        const unsigned int pos = carry + (warp ? warp_sums[warp - 1] : 0u) + inc - f;
-        if (f && pos < cap) { pairs[2 * (size_t)pos] = i; pairs[2 * (size_t)pos + 1] = nn[i]; }
+        const unsigned int excl = carry + (warp ? warp_sums[warp - 1] : 0u) + inc - v;
+        if (i < n_tiles) tile_counts[i] = excl;
         __syncthreads();
-        if (threadIdx.x == 1023) carry = pos + f;
+        if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
     }
+}
+__global__ void __launch_bounds__(kPairTile) icp_pair_write_kernel(const int *nn, const unsigned char *inlier, int ns, const unsigned int *tile_off,
+                                                                   int *pairs, unsigned long long cap)
+{
+    __shared__ unsigned int warp_sums[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * kPairTile + threadIdx.x;
+    const unsigned int f = i < ns ? inlier[i] : 0u;
+    const unsigned int ballot = __ballot_sync(0xffffffffu, f != 0);
+    if (lane == 0) warp_sums[warp] = (unsigned int)__popc(ballot);
+    __syncthreads();
+    if (warp == 0)
+    {
+        unsigned int w = warp_sums[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const unsigned int m = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += m;
+        }
+        warp_sums[lane] = w; // inclusive
+    }
+    __syncthreads();
+    if (!f) return;
+    const unsigned long long pos = (unsigned long long)tile_off[blockIdx.x] + (warp ? warp_sums[warp - 1] : 0u) + __popc(ballot & ((1u << lane) - 1u));
+    if (pos < cap) { pairs[2 * pos] = i; pairs[2 * pos + 1] = nn[i]; }
 }
 
 __global__ void icp_scale_kernel(float *p, size_t n, float s)
@@ -944,6 +977,7 @@ struct opb_icp
     float4 *d_qref = nullptr;          // nearest-neighbour certificates (icp_certify_kernel)
     int2 *d_nn_ref = nullptr;
     float *d_budget2 = nullptr;
+    unsigned int *d_pair_tiles = nullptr; // inlier count / offset per tile of 1024 source points
     unsigned int *d_worklist = nullptr;
     unsigned long long last_searched = 0; // full searches of the last call (of ns * (max_iteration + 1) queries)
     unsigned int last_searched_per_pass[64] = {0};
@@ -957,6 +991,9 @@ struct opb_icp
     // timing
     bool profiling = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    // uploads that overlap the grid construction
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy[3] = {nullptr, nullptr, nullptr};
     float last_build_ms = 0, last_iter_ms = 0;
 };
 
@@ -972,6 +1009,9 @@ static int icp_reserve(opb_icp *c, size_t ns, size_t nt)
         OPB_CUDA(cudaMalloc(&c->d_qref, ns * sizeof(float4)));
         OPB_CUDA(cudaMalloc(&c->d_nn_ref, ns * sizeof(int2)));
         OPB_CUDA(cudaMalloc(&c->d_budget2, ns * sizeof(float)));
+        cudaFree(c->d_pair_tiles);
+        c->d_pair_tiles = nullptr;
+        OPB_CUDA(cudaMalloc(&c->d_pair_tiles, (ns / kPairTile + 2) * sizeof(unsigned int)));
         OPB_CUDA(cudaMalloc(&c->d_worklist, ns * sizeof(unsigned int)));
         OPB_CUDA(cudaMalloc(&c->d_src, ns * 3 * sizeof(float)));
         OPB_CUDA(cudaMalloc(&c->d_nn, ns * sizeof(int)));
@@ -1028,6 +1068,8 @@ int opb_icp_create(int device, void *stream, opb_icp **out)
     if (e == cudaSuccess) e = cudaMalloc(&c->d_tile_sums, ((size_t)kMaxTiles + 1) * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_cell_start, ((size_t)kMaxCells + 2) * sizeof(unsigned int));
     for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess)
     {
         set_error("ICP workspace allocation failed: %s", cudaGetErrorString(e));
@@ -1046,9 +1088,11 @@ void opb_icp_destroy(opb_icp *c)
     cudaFree(c->d_src); cudaFree(c->d_tgt); cudaFree(c->d_nrm); cudaFree(c->d_sorted); cudaFree(c->d_point_cell);
     cudaFree(c->d_cell_count); cudaFree(c->d_tile_sums); cudaFree(c->d_cell_start); cudaFree(c->d_nn); cudaFree(c->d_pairs);
     cudaFree(c->d_inlier); cudaFree(c->d_partials); cudaFree(c->d_state); cudaFree(c->d_mailbox);
-    cudaFree(c->d_qref); cudaFree(c->d_nn_ref); cudaFree(c->d_worklist); cudaFree(c->d_budget2);
+    cudaFree(c->d_qref); cudaFree(c->d_nn_ref); cudaFree(c->d_worklist); cudaFree(c->d_budget2); cudaFree(c->d_pair_tiles);
     if (c->h_state) cudaFreeHost(c->h_state);
     for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 3; ++i) if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     cudaGetLastError();
     delete c;
@@ -1088,12 +1132,20 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     int rc = icp_reserve(c, ns, nt);
     if (rc) return rc;
     cudaStream_t s = c->stream;
-    OPB_CUDA(cudaMemcpyAsync(c->d_src, src, ns * 3 * sizeof(float), cudaMemcpyDefault, s));
+    // The target goes first on the work stream (the grid is built from it); the source and the normals follow on the copy
+    // stream and arrive under the grid construction: the first certify pass waits for the source, the first accumulation
+    // for the normals.  (Calls are synchronous, so nothing of an earlier call can still be reading these buffers.)
     OPB_CUDA(cudaMemcpyAsync(c->d_tgt, tgt, nt * 3 * sizeof(float), cudaMemcpyDefault, s));
-    if (point_to_plane) OPB_CUDA(cudaMemcpyAsync(c->d_nrm, nrm, nt * 3 * sizeof(float), cudaMemcpyDefault, s));
+    OPB_CUDA(cudaEventRecord(c->ev_copy[0], s));
+    OPB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[0], 0)); // keep the link for the target alone first
+    if (ns) OPB_CUDA(cudaMemcpyAsync(c->d_src, src, ns * 3 * sizeof(float), cudaMemcpyDefault, c->copy_stream));
+    OPB_CUDA(cudaEventRecord(c->ev_copy[1], c->copy_stream));
+    if (point_to_plane) OPB_CUDA(cudaMemcpyAsync(c->d_nrm, nrm, nt * 3 * sizeof(float), cudaMemcpyDefault, c->copy_stream));
+    OPB_CUDA(cudaEventRecord(c->ev_copy[2], c->copy_stream));
     const float scaling = (float)par->scaling;
     if (par->scaling != 1.0)
     {   // PointToPoint scales both clouds (ICP.cpp:36-42)
+        OPB_CUDA(cudaStreamWaitEvent(s, c->ev_copy[1], 0));
         icp_scale_kernel<<<c->sm_count * 4, 256, 0, s>>>(c->d_src, ns * 3, scaling);
         icp_scale_kernel<<<c->sm_count * 4, 256, 0, s>>>(c->d_tgt, nt * 3, scaling);
     }
@@ -1142,15 +1194,23 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     {
         // the last pass is the final CountInliers with the final T (ICP.cpp:90-91,206-207)
         a.final_pass = it == par->max_iteration;
+        if (it == 0) OPB_CUDA(cudaStreamWaitEvent(s, c->ev_copy[1], 0)); // source points uploaded
         icp_certify_kernel<<<nb_c, kIcpThreads, 0, s>>>(a);
         icp_search_kernel<<<nb_s, kIcpThreads, 0, s>>>(a);
+        if (it == 0) OPB_CUDA(cudaStreamWaitEvent(s, c->ev_copy[2], 0)); // target normals uploaded
         if (point_to_plane) icp_accumulate_kernel<true><<<nb_a, kIcpThreads, 0, s>>>(a);
         else icp_accumulate_kernel<false><<<nb_a, kIcpThreads, 0, s>>>(a);
     }
     OPB_CUDA(cudaMemcpyAsync(h, c->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
     icp_final_sums_kernel<<<nb_a, kIcpThreads, 0, s>>>(c->d_src, c->d_tgt, c->d_nn, c->d_inlier, (int)ns, scaling, c->d_partials);
     icp_final_reduce_kernel<<<1, kIcpThreads, 0, s>>>(c->d_partials, nb_a, c->d_state, c->comm);
-    if (pairs && pairs_cap) icp_compact_kernel<<<1, 1024, 0, s>>>(c->d_nn, c->d_inlier, (int)ns, c->d_pairs, (unsigned long long)pairs_cap);
+    if (pairs && pairs_cap && ns)
+    {
+        const int n_tiles = (int)((ns + kPairTile - 1) / kPairTile);
+        icp_pair_count_kernel<<<n_tiles, kPairTile, 0, s>>>(c->d_inlier, (int)ns, c->d_pair_tiles);
+        icp_pair_scan_kernel<<<1, 1024, 0, s>>>(c->d_pair_tiles, n_tiles);
+        icp_pair_write_kernel<<<n_tiles, kPairTile, 0, s>>>(c->d_nn, c->d_inlier, (int)ns, c->d_pair_tiles, c->d_pairs, (unsigned long long)pairs_cap);
+    }
     if (c->profiling) OPB_CUDA(cudaEventRecord(c->ev[2], s));
     OPB_CUDA(cudaGetLastError());
     OPB_CUDA(cudaStreamSynchronize(s));

@@ -58,6 +58,30 @@ def main():
         if rank == 0:
             print(f"ICP {name}: {(time.perf_counter() - t0) * 100:.3f} ms per call ({len(src)} source points, world {world})")
     sp.close()
+    # 3. BASELINE.json config 4 at one quarter of its GPU count: 1280x960 depth, 2 mm voxels, volume partitioned over the ranks
+    #    by slabs of 8 cubes, boundary-cube exchange over NCCL, Marching Cubes per rank -- the vertex count must be the
+    #    unsharded volume's (north_star: "Marching-Cubes mesh vertex count identical")
+    from onepiece_b200 import scenes
+    c0 = scenes.Camera()
+    big = scenes.Camera(2 * c0.fx, 2 * c0.fy, 2 * c0.cx, 2 * c0.cy, 1280, 960, 1000.0)
+    sh4 = fusion.ShardedCubeHandler(big, 0.002, max_cubes=1 << 18, axis=0, slab=8, device_index=local)
+    whole = CubeHandler(big, 0.002, max_cubes=1 << 18, device=local) if rank == 0 else None
+    for k in range(2):
+        d, c = scenes.wavy_wall(big, k)
+        sh4.IntegrateImage(d, c, np.eye(4, dtype=np.float32))
+        if whole is not None:
+            whole.IntegrateImage(d, c, np.eye(4, dtype=np.float32))
+    bare = sh4.volume.CountMesh()[0]
+    n_ghost = fusion.exchange_halo(sh4.volume, rank, world, sh4.device)
+    mine = sh4.volume.CountMesh()[0]
+    tot = torch.tensor([sh4.volume.NumCubes(), bare, mine, n_ghost], device="cuda", dtype=torch.int64)
+    dist.all_reduce(tot)
+    if rank == 0:
+        cubes, bare_sum, full_sum, ghosts = (int(x) for x in tot.tolist())
+        assert cubes == whole.NumCubes(), (cubes, whole.NumCubes())
+        assert full_sum == whole.CountMesh()[0] > bare_sum, (full_sum, whole.CountMesh()[0], bare_sum)
+        print(f"config 4 slice: {cubes} cubes over {world} ranks, {ghosts} boundary cubes exchanged "
+              f"({ghosts * 1292 / 1e6:.1f} MB instead of {ghosts * 10240 / 1e6:.1f} MB), {full_sum} mesh vertices = unsharded")
     dist.barrier()
     if rank == 0:
         print("MGPU OK")
