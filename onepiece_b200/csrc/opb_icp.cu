@@ -688,12 +688,20 @@ __device__ void icp_solve_and_update(const IcpArgs &a, IcpState *st)
 // K8: CountInliers test, Jacobian row and the 30-scalar packet over the pairs (i, nn[i]).  Per-thread double accumulators
 // -> warp shuffles -> one partial per CTA in a fixed slot; the last CTA to finish sums the partials in a fixed order
 // (deterministic), solves and updates the pose.  PLANE: point-to-plane rows, else the Kabsch sums of point-to-point.
-template <bool PLANE>
-__global__ void __launch_bounds__(kIcpThreads) icp_accumulate_kernel(IcpArgs a)
+struct IcpShared
 {
-    __shared__ double s_part[kIcpThreads / 32][kPacket];
-    __shared__ float sT[16];
-    __shared__ bool s_last;
+    double part[kIcpThreads / 32][kPacket];
+    float T[16];
+    bool last;
+};
+// returns true in every thread of the CTA that finished last (the one that summed the partials, solved and updated the pose)
+template <bool PLANE>
+__device__ __forceinline__ bool accumulate_pass(const IcpArgs &a, IcpShared &sh)
+{
+    double (*s_part)[kPacket] = sh.part;
+    float *sT = sh.T;
+    bool &s_last = sh.last;
+    __syncthreads(); // the previous user of the shared block is done
     if (threadIdx.x < 16) sT[threadIdx.x] = a.st->T[threadIdx.x];
     __syncthreads();
     const float *T = sT; // column-major
@@ -785,7 +793,7 @@ __global__ void __launch_bounds__(kIcpThreads) icp_accumulate_kernel(IcpArgs a)
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(&a.st->blocks_done, 1u) == gridDim.x - 1;
     __syncthreads();
-    if (!s_last) return;
+    if (!s_last) return false;
     __threadfence();
     {
         // 8 interleaved chains per component, then the chains in order: deterministic
@@ -809,13 +817,96 @@ __global__ void __launch_bounds__(kIcpThreads) icp_accumulate_kernel(IcpArgs a)
     __syncthreads();
     if (threadIdx.x == 0) a.st->n_inliers_local = (unsigned long long)(a.st->packet[29] + 0.5);
     comm_allreduce(a.comm, a.st->packet, 30);
-    if (threadIdx.x != 0) return;
+    if (threadIdx.x != 0) return true;
     a.st->blocks_done = 0;
     a.st->searched_total += a.st->wl_count;
     if (a.st->pass < 64) a.st->searched_per_pass[a.st->pass] = a.st->wl_count;
-    a.st->pass += 1;
     a.st->wl_count = 0; // the next pass builds its own work list
     icp_solve_and_update(a, a.st);
+    return true;
+}
+template <bool PLANE>
+__global__ void __launch_bounds__(kIcpThreads) icp_accumulate_kernel(IcpArgs a)
+{
+    __shared__ IcpShared sh;
+    if (accumulate_pass<PLANE>(a, sh) && threadIdx.x == 0) a.st->pass += 1;
+}
+
+// The whole iteration loop as ONE persistent launch (cooperative: every CTA is resident).  A pass is what the three kernels
+// above do, without their launch gaps and without the round trip of the work list: every thread certifies its own points
+// and searches the ones that fail on the spot, then accumulates the same points; the last CTA to arrive sums the partials,
+// exchanges the packet with the peer ranks, solves, updates the pose and releases the grid into the next pass (one
+// grid-wide barrier per pass, built on the pass counter).  Point-to-thread assignment, per-CTA partials and the order of
+// every sum are those of the separate kernels, so the results are bit-identical to theirs.
+template <bool PLANE>
+__global__ void __launch_bounds__(kIcpThreads, 2) icp_loop_kernel(IcpArgs a, int n_pass)
+{
+    __shared__ IcpShared sh;
+    const IcpGrid g = a.st->grid;
+    const float r2cap = a.search_radius * a.search_radius;
+    const float guard = a.certify ? a.guard * g.h : 0.0f;
+    for (int pass = 0; pass < n_pass; ++pass)
+    {
+        a.final_pass = pass == n_pass - 1;
+        __syncthreads();
+        if (threadIdx.x < 16) sh.T[threadIdx.x] = a.st->T[threadIdx.x];
+        __syncthreads();
+        unsigned int searched = 0;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.ns; i += gridDim.x * blockDim.x)
+        {
+            float px, py, pz;
+            transform_point(sh.T, a.src[3 * i], a.src[3 * i + 1], a.src[3 * i + 2], px, py, pz);
+            const float4 q = a.qref[i];
+            const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
+            const float moved = sqrtf(dx * dx + dy * dy + dz * dz) * (1.0f + 1e-6f);
+            int nn = -1;
+            if (moved < q.w)
+            {
+                const int j = a.nn_ref[i].x;
+                if (j >= 0)
+                {
+                    const float d = dist2_nanoflann(px, py, pz, __ldg(&a.tgt[3 * j]), __ldg(&a.tgt[3 * j + 1]), __ldg(&a.tgt[3 * j + 2]));
+                    if (!(d > r2cap)) nn = j;
+                }
+            }
+            else if (moved < a.budget2[i])
+            {
+                const int2 jj = a.nn_ref[i];
+                const float da = dist2_nanoflann(px, py, pz, __ldg(&a.tgt[3 * jj.x]), __ldg(&a.tgt[3 * jj.x + 1]), __ldg(&a.tgt[3 * jj.x + 2]));
+                const float db = dist2_nanoflann(px, py, pz, __ldg(&a.tgt[3 * jj.y]), __ldg(&a.tgt[3 * jj.y + 1]), __ldg(&a.tgt[3 * jj.y + 2]));
+                const bool first = da < db || (da == db && jj.x < jj.y);
+                if (!((first ? da : db) > r2cap)) nn = first ? jj.x : jj.y;
+            }
+            else
+            {
+                const NnResult r = grid_nearest(g, a.cell_start, a.sorted, px, py, pz, a.search_radius, guard);
+                nn = r.index;
+                a.nn_ref[i] = make_int2(r.index, r.index2);
+                a.qref[i] = make_float4(px, py, pz, a.certify ? r.budget : -1.0f);
+                a.budget2[i] = a.certify ? r.budget2 : -1.0f;
+                ++searched;
+            }
+            a.nn[i] = nn;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) searched += __shfl_xor_sync(0xffffffffu, searched, o);
+        if ((threadIdx.x & 31) == 0 && searched) atomicAdd(&a.st->wl_count, searched);
+        // every thread reads back only the nn entries it wrote itself: no grid-wide ordering is needed before this
+        const bool last = accumulate_pass<PLANE>(a, sh);
+        if (pass == n_pass - 1) break;
+        if (threadIdx.x == 0)
+        {
+            if (last)
+            {
+                __threadfence();
+                atomicExch(&a.st->pass, (unsigned int)(pass + 1)); // releases the grid
+            }
+            else
+                while (*(volatile unsigned int *)&a.st->pass <= (unsigned int)pass) { }
+            __threadfence();
+        }
+        __syncthreads();
+    }
 }
 
 // final Kabsch sums over the inlier pairs of the ORIGINAL (unscaled) clouds (per-CTA partials, 16 components)
@@ -991,6 +1082,8 @@ struct opb_icp
     // timing
     bool profiling = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    int coop_ctas_per_sm = 0; // resident CTAs per SM of the persistent loop kernel; 0: cooperative launch unavailable
+    bool peers_share_device = false; // a peer rank runs on this very GPU: two persistent grids could not be resident together
     // uploads that overlap the grid construction
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[3] = {nullptr, nullptr, nullptr};
@@ -1070,6 +1163,15 @@ int opb_icp_create(int device, void *stream, opb_icp **out)
     for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
     for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess)
+    {
+        int coop = 0, occ_plane = 0, occ_point = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_plane, icp_loop_kernel<true>, kIcpThreads, 0) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_point, icp_loop_kernel<false>, kIcpThreads, 0) == cudaSuccess)
+            c->coop_ctas_per_sm = occ_plane < occ_point ? occ_plane : occ_point;
+        cudaGetLastError();
+    }
     if (e != cudaSuccess)
     {
         set_error("ICP workspace allocation failed: %s", cudaGetErrorString(e));
@@ -1190,7 +1292,22 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     const int nb_a = nb_need < c->sm_count * k_accum ? nb_need : c->sm_count * k_accum;   // accumulate: few partials for the last CTA to sum
     static const int k_cert = getenv("OPB_ICP_CERTIFY_CTAS") ? atoi(getenv("OPB_ICP_CERTIFY_CTAS")) : 8;
     const int nb_c = nb_need < c->sm_count * k_cert ? nb_need : c->sm_count * k_cert;
-    for (int it = 0; it <= par->max_iteration; ++it)
+    static const int k_persistent = getenv("OPB_ICP_PERSISTENT") ? atoi(getenv("OPB_ICP_PERSISTENT")) : 1;
+    bool looped = false;
+    if (k_persistent && c->coop_ctas_per_sm > 0 && !c->peers_share_device)
+    {
+        // one cooperative launch for all passes; grid = the accumulate grid (2 CTAs per SM), which fixes the order of the sums
+        const int per_sm = c->coop_ctas_per_sm < k_accum ? c->coop_ctas_per_sm : k_accum;
+        const int nb_l = nb_need < c->sm_count * per_sm ? nb_need : c->sm_count * per_sm;
+        int n_pass = par->max_iteration + 1;
+        OPB_CUDA(cudaStreamWaitEvent(s, c->ev_copy[1], 0)); // source points uploaded
+        OPB_CUDA(cudaStreamWaitEvent(s, c->ev_copy[2], 0)); // target normals uploaded
+        void *kargs[] = {(void *)&a, (void *)&n_pass};
+        const void *fn = point_to_plane ? (const void *)icp_loop_kernel<true> : (const void *)icp_loop_kernel<false>;
+        OPB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(nb_l), dim3(kIcpThreads), kargs, 0, s));
+        looped = true;
+    }
+    for (int it = 0; !looped && it <= par->max_iteration; ++it)
     {
         // the last pass is the final CountInliers with the final T (ICP.cpp:90-91,206-207)
         a.final_pass = it == par->max_iteration;
@@ -1332,11 +1449,17 @@ int opb_icp_comm_attach(opb_icp *c, int rank, int world, void *const *buffers)
     OPB_CUDA(cudaSetDevice(c->device));
     OPB_CUDA(cudaStreamSynchronize(c->stream));
     OPB_CUDA(cudaMemset(c->d_mailbox, 0, sizeof(IcpMailbox)));
+    c->peers_share_device = false;
     for (int r = 0; r < world; ++r)
     {
         if (!buffers[r]) { set_error("buffers[%d] is NULL", r); return OPB_ERR_INVALID; }
         c->comm.box[r] = (IcpMailbox *)buffers[r];
+        // A peer on this very GPU (tests, oversubscription): its persistent loop kernel and ours could not be resident at the
+        // same time, and each waits for the other's packet -- such workspaces run the loop as separate launches instead.
+        cudaPointerAttributes attr;
+        if (r != rank && cudaPointerGetAttributes(&attr, buffers[r]) == cudaSuccess && attr.device == c->device) c->peers_share_device = true;
     }
+    cudaGetLastError();
     c->comm.rank = rank;
     c->comm.world = world;
     return OPB_OK;
@@ -1347,6 +1470,7 @@ int opb_icp_comm_detach(opb_icp *c)
     OPB_CUDA(cudaSetDevice(c->device));
     OPB_CUDA(cudaStreamSynchronize(c->stream));
     c->comm = IcpComm{};
+    c->peers_share_device = false;
     return OPB_OK;
 }
 // nearest-neighbour indices of the LAST search (final CountInliers pass), for tests

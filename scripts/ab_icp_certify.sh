@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B of the nearest-neighbour certificates in the ICP loop: bench step breakdown with them on / off and for several guards
-for cfg in "OPB_ICP_CERTIFY=1 OPB_ICP_GUARD=0.03" "OPB_ICP_CERTIFY=1 OPB_ICP_GUARD=0.0625" "OPB_ICP_CERTIFY=1 OPB_ICP_GUARD=0.125" "OPB_ICP_CERTIFY=1 OPB_ICP_CERTIFY_CTAS=2" "OPB_ICP_CERTIFY=1 OPB_ICP_CERTIFY_CTAS=8" "OPB_ICP_CERTIFY=1 OPB_ICP_SEARCH_CTAS=4"; do
+for cfg in "OPB_ICP_PERSISTENT=0" "OPB_ICP_PERSISTENT=1" "OPB_ICP_PERSISTENT=1 OPB_ICP_ACCUM_CTAS=1" "OPB_ICP_PERSISTENT=1 OPB_ICP_CERTIFY=0"; do
   echo "== $cfg"
   env $cfg python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-odometry | python -c "
 import json,sys
