@@ -160,7 +160,7 @@ __global__ void icp_bbox_kernel(const float *pts, int n, IcpState *st)
 
 // one thread: cell size such that the grid has at most kMaxCells cells and about two points per occupied
 // cell for surface-like clouds
-__global__ void icp_grid_setup_kernel(IcpState *st, int n, float min_cell)
+__global__ void icp_grid_setup_kernel(IcpState *st, int n, float min_cell, unsigned int max_cells)
 {
     float ext[3];
     for (int a = 0; a < 3; ++a)
@@ -182,7 +182,7 @@ __global__ void icp_grid_setup_kernel(IcpState *st, int n, float min_cell)
     {
         double cells = 1.0;
         for (int a = 0; a < 3; ++a) cells *= floor((double)ext[a] / h) + 1.0;
-        if (cells <= (double)kMaxCells) break;
+        if (cells <= (double)max_cells) break;
         h *= 1.26f;
     }
     st->grid.h = h;
@@ -401,7 +401,8 @@ __device__ __forceinline__ void scan_cells(const IcpGrid &g, const unsigned int 
     if (xa > xb || cy < 0 || cy >= g.dim[1] || cz < 0 || cz >= g.dim[2]) return;
     const unsigned int row = (unsigned int)g.dim[0] * ((unsigned int)cy + (unsigned int)g.dim[1] * (unsigned int)cz);
     const unsigned int s = __ldg(&cell_start[row + xa]), e = __ldg(&cell_start[row + xb + 1]);
-    for (unsigned int k = s; k < e; ++k)
+    unsigned int k = s;
+    for (; k < e; ++k)
     {
         const float4 t = __ldg(&sorted[k]);
         nearest2_push(b, dist2_nanoflann(qx, qy, qz, t.x, t.y, t.z), __float_as_int(t.w));
@@ -1261,7 +1262,9 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     // grid over the target
     const int nb_t = (int)((nt + 255) / 256) < c->sm_count * 8 ? (int)((nt + 255) / 256) : c->sm_count * 8;
     icp_bbox_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)nt, c->d_state);
-    icp_grid_setup_kernel<<<1, 1, 0, s>>>(c->d_state, (int)nt, 0.0f);
+    // developer knob: cap on the number of grid cells (the construction streams over all of them, the searches prefer many)
+    static const unsigned int k_max_cells = getenv("OPB_ICP_MAX_CELLS") ? (unsigned int)atoll(getenv("OPB_ICP_MAX_CELLS")) : kMaxCells;
+    icp_grid_setup_kernel<<<1, 1, 0, s>>>(c->d_state, (int)nt, 0.0f, k_max_cells < kMaxCells ? k_max_cells : kMaxCells);
     icp_clear_kernel<<<c->sm_count * 8, 256, 0, s>>>(c->d_state, c->d_cell_count);
     icp_count_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)nt, c->d_state, c->d_cell_count, c->d_point_cell);
     icp_tile_sums_kernel<<<c->sm_count * 2, 1024, 0, s>>>(c->d_state, c->d_cell_count, c->d_tile_sums);
