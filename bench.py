@@ -372,7 +372,10 @@ def run_ours(args):
     icp_iter_ms = icp_loop_ms / nprof_steps / (ICP_ITERS + 1)
     icp_bytes = n_pts * 12 + n_pts * 36  # N_s*12 (source) + N_inl*(12+12+12) (nn point, normal, source)
     icp_ach = icp_bytes / (icp_iter_ms * 1e-3) / 1e9 if icp_iter_ms > 0 else 0.0
-    launches_per_step = 8 + 3 * (ICP_ITERS + 1) + 2 + 3  # grid build, (certify + search + accumulate) x 31, Kabsch sums, pack/select/integrate
+    icp_launches = C.c_int(0)
+    capi.lib.opb_icp_last_launch_count(icp, C.byref(icp_launches))
+    # ICP: grid build 8, the 31 passes (one persistent launch, or certify + search + accumulate each), Kabsch sums 2; volume: pack, select, integrate
+    launches_per_step = icp_launches.value + 3
     searched = C.c_uint64(0)
     capi.lib.opb_icp_last_search_count(icp, C.byref(searched))
     out = {

@@ -297,6 +297,8 @@ int opb_icp_last_nn(opb_icp *c, int32_t *nn, size_t n);
 /* how many exact grid searches the last call performed, of n_source * (max_iteration + 1) queries: the others kept the
  * certified nearest neighbour of an earlier pass (see csrc/opb_icp.cu, icp_certify_kernel) */
 int opb_icp_last_search_count(opb_icp *c, uint64_t *full_searches);
+/* kernels the last call launched (grid construction 8, the pass loop 1 as a persistent launch or 3 per pass, final sums 2, ...) */
+int opb_icp_last_launch_count(opb_icp *c, int *launches);
 /* the same per pass (pass 0 searches everything), for the first min(cap, 64) passes */
 int opb_icp_last_search_trace(opb_icp *c, uint32_t *per_pass, int cap);
 /* CUDA-event timing of the last call when enabled: grid construction and the iteration loop */

@@ -1073,6 +1073,7 @@ struct opb_icp
     unsigned int *d_worklist = nullptr;
     unsigned long long last_searched = 0; // full searches of the last call (of ns * (max_iteration + 1) queries)
     unsigned int last_searched_per_pass[64] = {0};
+    int last_launches = 0;                // kernels launched by the last call
     double *d_partials = nullptr;
     size_t cap_partials = 0;
     IcpState *d_state = nullptr;
@@ -1297,6 +1298,7 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     const int nb_c = nb_need < c->sm_count * k_cert ? nb_need : c->sm_count * k_cert;
     static const int k_persistent = getenv("OPB_ICP_PERSISTENT") ? atoi(getenv("OPB_ICP_PERSISTENT")) : 1;
     bool looped = false;
+    c->last_launches = 8 + 3 * (par->max_iteration + 1) + 2 + (pairs && pairs_cap && ns ? 3 : 0) + (par->scaling != 1.0 ? 2 : 0);
     if (k_persistent && c->coop_ctas_per_sm > 0 && !c->peers_share_device)
     {
         // one cooperative launch for all passes; grid = the accumulate grid (2 CTAs per SM), which fixes the order of the sums
@@ -1309,6 +1311,7 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
         const void *fn = point_to_plane ? (const void *)icp_loop_kernel<true> : (const void *)icp_loop_kernel<false>;
         OPB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(nb_l), dim3(kIcpThreads), kargs, 0, s));
         looped = true;
+        c->last_launches = 8 + 1 + 2 + (pairs && pairs_cap && ns ? 3 : 0) + (par->scaling != 1.0 ? 2 : 0);
     }
     for (int it = 0; !looped && it <= par->max_iteration; ++it)
     {
@@ -1401,6 +1404,12 @@ int opb_icp_last_search_count(opb_icp *c, uint64_t *full_searches)
 {
     if (!c || !full_searches) { set_error("NULL argument"); return OPB_ERR_INVALID; }
     *full_searches = c->last_searched;
+    return OPB_OK;
+}
+int opb_icp_last_launch_count(opb_icp *c, int *launches)
+{
+    if (!c || !launches) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    *launches = c->last_launches;
     return OPB_OK;
 }
 int opb_icp_last_search_trace(opb_icp *c, uint32_t *per_pass, int cap)
