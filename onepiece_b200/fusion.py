@@ -118,6 +118,34 @@ class ShardedCubeHandler:
         """Every rank is given the same frame and pose (the host program broadcasts or loads it per rank)."""
         self.volume.IntegrateImage(depth, rgb, pose)
 
+    def IntegrateImageBroadcast(self, depth, rgb, pose, src: int = 0):
+        """The frame lives on rank `src` only (the others pass None): depth, colour and pose are broadcast over NCCL into
+        device buffers and integrated from there -- no host copy on the receiving ranks."""
+        from . import capi
+        from .volume import depth_type_of, pose_colmajor
+        cam = self.volume.camera
+        meta = torch.zeros(17, dtype=torch.float32, device=self.device)  # depth type + pose
+        if self.rank == src:
+            depth = np.ascontiguousarray(depth)
+            meta[0] = float(depth_type_of(depth))
+            meta[1:] = torch.from_numpy(pose_colmajor(pose))
+        if self.world > 1:
+            dist.broadcast(meta, src, group=self.group)
+        dtype = int(meta[0].item())
+        np_dt = np.uint16 if dtype == capi.OPB_DEPTH_U16 else np.float32
+        if self.rank == src:
+            d_depth = torch.from_numpy(depth.view(np.int16) if np_dt is np.uint16 else depth).to(self.device)
+            d_rgb = torch.from_numpy(np.ascontiguousarray(rgb, np.uint8)).to(self.device)
+        else:
+            d_depth = torch.empty((cam.height, cam.width), dtype=torch.int16 if np_dt is np.uint16 else torch.float32, device=self.device)
+            d_rgb = torch.empty((cam.height, cam.width, 3), dtype=torch.uint8, device=self.device)
+        if self.world > 1:
+            dist.broadcast(d_depth.view(torch.uint8), src, group=self.group)  # raw bytes: NCCL has no 16-bit integer type
+            dist.broadcast(d_rgb, src, group=self.group)
+        torch.cuda.synchronize(self.device)   # the volume runs on its own stream
+        self.volume.IntegrateImageDevice(d_depth.data_ptr(), dtype, d_rgb.data_ptr(), np.ascontiguousarray(meta[1:].cpu().numpy()))
+        self.volume.Synchronize()             # the broadcast buffers may be released after this
+
     def ExtractTriangleMesh(self, dst: int = 0):
         """Halo exchange, per-rank Marching Cubes, concatenation on rank dst -> (points, colors, triangles) or Nones."""
         exchange_halo(self.volume, self.rank, self.world, self.device, self.group)

@@ -103,7 +103,10 @@ def main():
             pose = pose @ r5.T_iterated.astype(np.float64)
         prev = (cloud, nrm5)
         p32 = pose.astype(np.float32)
-        sh5.IntegrateImage(d, c, p32)
+        if k % 2:
+            sh5.IntegrateImage(d, c, p32)               # every rank loaded the frame itself
+        else:
+            sh5.IntegrateImageBroadcast(d if rank == 0 else None, c if rank == 0 else None, p32 if rank == 0 else None, src=0)
         if whole5 is not None:
             whole5.IntegrateImage(d, c, p32)
     poses = [None] * world
