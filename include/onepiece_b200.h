@@ -350,6 +350,9 @@ int opb_odometry_set_profiling(opb_odometry *o, int on);
 /* CUDA-event time of the last tracking call (pre-processing of new frames included) and the mean time per solver
  * iteration that the last CTA spent on the fixed-order partial sum + 6x6 solve + pose update (%globaltimer) */
 int opb_odometry_last_timing(opb_odometry *o, float *tracking_ms, float *solve_tail_us);
+/* persistent solver loop of the last tracking call, seen from CTA 0 (%globaltimer ns summed over the iterations): candidate
+ * pass, mid-iteration grid barrier, reduction (+ solve when CTA 0 finished last), wait for the release into the next iteration */
+int opb_odometry_last_phases(opb_odometry *o, uint64_t phase_ns[4]);
 
 /* geometry::RGBDFrame(rgb, depth) (RGBDFrame.h:14-19): uploads the raw images (host or device pointers; returns when
  * the copies are done).  depth_type other than OPB_DEPTH_F32 / OPB_DEPTH_U16 -> OPB_ERR_UNSUPPORTED (the reference

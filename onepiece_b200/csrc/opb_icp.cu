@@ -802,8 +802,25 @@ __device__ __forceinline__ bool accumulate_pass(const IcpArgs &a, IcpShared &sh)
         double v = 0.0;
         if (k < 30)
         {
+            constexpr int kChains = kIcpThreads / 32, kInFlight = 40;
+            if (gridDim.x <= kChains * kInFlight)
+            {
+                // all loads of the chain in flight at once, then the additions in the chain's fixed order (x + 0.0 == x)
+                double t[kInFlight];
+#pragma unroll
+                for (int u = 0; u < kInFlight; ++u)
+                {
+                    const unsigned int b = chain + u * kChains;
+                    t[u] = b < gridDim.x ? __ldcg(&a.partials[(size_t)b * kPacket + k]) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < kInFlight; ++u) v += t[u];
+            }
+            else
+            {
 #pragma unroll 8
-            for (unsigned int b = chain; b < gridDim.x; b += kIcpThreads / 32) v += __ldcg(&a.partials[(size_t)b * kPacket + k]);
+                for (unsigned int b = chain; b < gridDim.x; b += kChains) v += __ldcg(&a.partials[(size_t)b * kPacket + k]);
+            }
         }
         __syncthreads();
         s_part[chain][k] = v;

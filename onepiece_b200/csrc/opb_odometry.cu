@@ -62,6 +62,7 @@ struct OdoState // device-resident solver state
     float mean_src, mean_tgt; // NormalizeIntensity
     double rmse_sum;
     unsigned long long tail_ns; // profiling: time the last CTA spent summing partials + solving, accumulated over the call
+    unsigned long long phase_ns[4]; // persistent loop, CTA 0: candidates, mid barrier, reduction (+ solve if last), release wait
     int trace_count[kMaxTrace];
     float trace_T[kMaxTrace][16];
 };
@@ -208,10 +209,9 @@ struct OdoArgs
     const float *T_override; // identity for the NormalizeIntensity correspondences, else nullptr (= st->T)
 };
 
-__global__ void __launch_bounds__(kOdoThreads) odo_candidates_kernel(OdoArgs a)
+__device__ __forceinline__ void candidates_phase(const OdoArgs &a, float *sM)
 {
-    if (a.st->break_level == a.level && !a.T_override) return;
-    __shared__ float sM[12];
+    __syncthreads(); // the previous user of the shared block is done
     if (threadIdx.x == 0) warp_matrices(a.cam, a.T_override ? a.T_override : a.st->T, sM, sM + 9);
     __syncthreads();
     const int w = a.cam.w, h = a.cam.h, n = w * h;
@@ -241,6 +241,12 @@ __global__ void __launch_bounds__(kOdoThreads) odo_candidates_kernel(OdoArgs a)
         }
         a.cand[s] = c;
     }
+}
+__global__ void __launch_bounds__(kOdoThreads) odo_candidates_kernel(OdoArgs a)
+{
+    if (a.st->break_level == a.level && !a.T_override) return;
+    __shared__ float sM[12];
+    candidates_phase(a, sM);
 }
 
 // AddElementToCorrespondenceMap, resolved without the raster-order loop.  The reference accepts source pixel s (a valid
@@ -391,13 +397,21 @@ __device__ void solve_and_update(const OdoArgs &a, OdoState *st)
 }
 
 // mode 0: solver iteration; mode 1: only the accept flags and the count (NormalizeIntensity / teacher-forced listing)
-template <int TERM, int MODE>
-__global__ void __launch_bounds__(kOdoThreads) odo_iteration_kernel(OdoArgs a)
+struct OdoShared
 {
-    if (MODE == 0 && a.st->break_level == a.level) return;
-    __shared__ double s_part[kOdoThreads / 32][kOdoPacket];
-    __shared__ float sT[16];
-    __shared__ bool s_last;
+    double part[kOdoThreads / 32][kOdoPacket];
+    float T[16];
+    float M[12];
+    bool last;
+};
+// returns true in every thread of the CTA that finished last (the one that summed the partials and solved)
+template <int TERM, int MODE>
+__device__ __forceinline__ bool iteration_phase(const OdoArgs &a, OdoShared &sh)
+{
+    double (*s_part)[kOdoPacket] = sh.part;
+    float *sT = sh.T;
+    bool &s_last = sh.last;
+    __syncthreads(); // the previous user of the shared block is done
     if (threadIdx.x < 16) sT[threadIdx.x] = a.st->T[threadIdx.x];
     __syncthreads();
     const int n = a.cam.w * a.cam.h;
@@ -432,7 +446,7 @@ __global__ void __launch_bounds__(kOdoThreads) odo_iteration_kernel(OdoArgs a)
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(&a.st->blocks_done, 1u) == gridDim.x - 1;
     __syncthreads();
-    if (!s_last) return;
+    if (!s_last) return false;
     unsigned long long t_tail = 0;
     if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_tail));
     __threadfence();
@@ -454,13 +468,93 @@ __global__ void __launch_bounds__(kOdoThreads) odo_iteration_kernel(OdoArgs a)
         }
     }
     __syncthreads();
-    if (threadIdx.x != 0) return;
+    if (threadIdx.x != 0) return true;
     a.st->blocks_done = 0;
     if (MODE == 0) solve_and_update(a, a.st);
     else a.st->last_count = (int)(a.st->packet[28] + 0.5);
     unsigned long long t_end;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
     a.st->tail_ns += t_end - t_tail;
+    return true;
+}
+template <int TERM, int MODE>
+__global__ void __launch_bounds__(kOdoThreads) odo_iteration_kernel(OdoArgs a)
+{
+    if (MODE == 0 && a.st->break_level == a.level) return;
+    __shared__ OdoShared sh;
+    iteration_phase<TERM, MODE>(a, sh);
+}
+
+// MultiScaleComputing (Odometry.cpp:621-685) as ONE persistent cooperative launch: all levels, all iterations.  An iteration
+// is the two phases of the kernels above separated by a grid-wide barrier (the acceptance test of a pixel reads the
+// candidates of other pixels); the last CTA to finish the reduction solves, updates the pose and releases the grid into the
+// next iteration.  Coarse levels keep the whole grid alive but idle: their iterations cost two barriers and the solve instead
+// of two launches.
+__device__ __forceinline__ unsigned long long timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct OdoLoopArgs
+{
+    OdoArgs base;
+    OdoCam cams[kMaxLevels];
+    int iterations[kMaxLevels];
+    int levels;
+    unsigned int *sync; // [0] arrivals of the mid-iteration barrier (monotonic), [1] iterations released
+};
+template <int TERM>
+__global__ void __launch_bounds__(kOdoThreads, 2) odo_loop_kernel(OdoLoopArgs L)
+{
+    __shared__ OdoShared sh;
+    unsigned int n_sync = 0; // barriers passed so far, identical in every thread of the grid
+    for (int l = L.levels - 1; l >= 0; --l)
+    {
+        OdoArgs a = L.base;
+        a.level = l;
+        a.cam = L.cams[l];
+        for (int j = 0; j < L.iterations[l]; ++j)
+        {
+            // written by the previous iteration's solve, which every CTA has waited for: uniform over the grid
+            if (*(volatile int *)&a.st->break_level == l) break;
+            const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
+            unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+            if (stamp) t0 = timer_ns();
+            candidates_phase(a, sh.M);
+            if (stamp) t1 = timer_ns();
+            ++n_sync;
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                __threadfence();
+                atomicAdd(&L.sync[0], 1u);
+                while (*(volatile unsigned int *)&L.sync[0] < n_sync * gridDim.x) { }
+                __threadfence();
+            }
+            __syncthreads();
+            if (stamp) t2 = timer_ns();
+            const bool last = iteration_phase<TERM, 0>(a, sh);
+            if (stamp) t3 = timer_ns();
+            if (threadIdx.x == 0)
+            {
+                if (last)
+                {
+                    __threadfence();
+                    atomicExch(&L.sync[1], n_sync); // releases the grid
+                }
+                else
+                    while (*(volatile unsigned int *)&L.sync[1] < n_sync) { }
+                __threadfence();
+            }
+            __syncthreads();
+            if (stamp)
+            {
+                t4 = timer_ns();
+                a.st->phase_ns[0] += t1 - t0; a.st->phase_ns[1] += t2 - t1; a.st->phase_ns[2] += t3 - t2; a.st->phase_ns[3] += t4 - t3;
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -785,6 +879,8 @@ struct opb_odometry
     OdoState *d_state = nullptr;
     OdoState *h_state = nullptr; // pinned
     int max_blocks = 0;
+    unsigned int *d_sync = nullptr; // barrier words of the persistent loop kernel
+    int coop_ctas_per_sm = 0;       // resident CTAs per SM of odo_loop_kernel; 0: cooperative launch unavailable
     bool profiling = false;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     float last_ms = 0;
@@ -849,7 +945,7 @@ void opb_odometry_destroy(opb_odometry *o)
     cudaSetDevice(o->device);
     if (o->stream) cudaStreamSynchronize(o->stream);
     cudaFree(o->d_cand); cudaFree(o->d_accepted); cudaFree(o->d_partials); cudaFree(o->d_tiles); cudaFree(o->d_pairs);
-    cudaFree(o->d_corr_xyz); cudaFree(o->d_identity); cudaFree(o->d_tmp); cudaFree(o->d_state);
+    cudaFree(o->d_corr_xyz); cudaFree(o->d_identity); cudaFree(o->d_tmp); cudaFree(o->d_state); cudaFree(o->d_sync);
     if (o->h_state) cudaFreeHost(o->h_state);
     for (int i = 0; i < 2; ++i) if (o->ev[i]) cudaEventDestroy(o->ev[i]);
     if (o->own_stream && o->stream) cudaStreamDestroy(o->stream);
@@ -896,6 +992,17 @@ int opb_odometry_create(const opb_odometry_desc *desc, opb_odometry **out)
     if (e == cudaSuccess) e = cudaHostAlloc(&o->h_state, sizeof(OdoState), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMemcpy(o->d_identity, I, sizeof(I), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(o->d_state, 0, sizeof(OdoState));
+    if (e == cudaSuccess) e = cudaMalloc(&o->d_sync, 4 * sizeof(unsigned int));
+    if (e == cudaSuccess)
+    {
+        int coop = 0, occ[3] = {0, 0, 0};
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, desc->device);
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], odo_loop_kernel<0>, kOdoThreads, 0) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], odo_loop_kernel<1>, kOdoThreads, 0) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], odo_loop_kernel<2>, kOdoThreads, 0) == cudaSuccess)
+            o->coop_ctas_per_sm = occ[0] < occ[1] ? (occ[0] < occ[2] ? occ[0] : occ[2]) : (occ[1] < occ[2] ? occ[1] : occ[2]);
+        cudaGetLastError();
+    }
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&o->ev[i]);
     if (e != cudaSuccess)
     {
@@ -911,6 +1018,12 @@ int opb_odometry_set_profiling(opb_odometry *o, int on)
 {
     if (!o) { set_error("odometry is NULL"); return OPB_ERR_INVALID; }
     o->profiling = on != 0;
+    return OPB_OK;
+}
+int opb_odometry_last_phases(opb_odometry *o, uint64_t phase_ns[4])
+{
+    if (!o || !phase_ns) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    for (int i = 0; i < 4; ++i) phase_ns[i] = o->h_state->phase_ns[i];
     return OPB_OK;
 }
 int opb_odometry_last_timing(opb_odometry *o, float *tracking_ms, float *solve_tail_us)
@@ -1073,11 +1186,28 @@ static int run_tracking(opb_odometry *o, opb_frame *S, opb_frame *T, int term, o
                         size_t pairs_cap, float *corr_xyz)
 {
     cudaStream_t s = o->stream;
-    for (int l = o->desc.levels - 1; l >= 0; --l)
+    static const int k_persistent = getenv("OPB_ODO_PERSISTENT") ? atoi(getenv("OPB_ODO_PERSISTENT")) : 1;
+    if (k_persistent && o->coop_ctas_per_sm > 0)
     {
-        OdoArgs a = make_args(o, S, T, l, term);
-        for (int j = 0; j < o->desc.iterations[l]; ++j) launch_iteration(o, a, false);
+        OdoLoopArgs L;
+        L.base = make_args(o, S, T, 0, term);
+        for (int l = 0; l < kMaxLevels; ++l) { L.cams[l] = o->cams[l]; L.iterations[l] = l < o->desc.levels ? o->desc.iterations[l] : 0; }
+        L.levels = o->desc.levels;
+        L.sync = o->d_sync;
+        OPB_CUDA(cudaMemsetAsync(o->d_sync, 0, 4 * sizeof(unsigned int), s));
+        const int per_sm = o->coop_ctas_per_sm < 2 ? o->coop_ctas_per_sm : 2;
+        int nb = grid_for(o, level_pixels(o, 0));
+        if (nb > o->sm_count * per_sm) nb = o->sm_count * per_sm;
+        void *kargs[] = {(void *)&L};
+        const void *fn = term == 0 ? (const void *)odo_loop_kernel<0> : (term == 1 ? (const void *)odo_loop_kernel<1> : (const void *)odo_loop_kernel<2>);
+        OPB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(nb), dim3(kOdoThreads), kargs, 0, s));
     }
+    else
+        for (int l = o->desc.levels - 1; l >= 0; --l)
+        {
+            OdoArgs a = make_args(o, S, T, l, term);
+            for (int j = 0; j < o->desc.iterations[l]; ++j) launch_iteration(o, a, false);
+        }
     // the correspondences of the last executed iteration, in raster order (level 0 unless its iteration count is 0;
     // the reference then indexes the level-0 XYZ images with the coarser level's pixel coordinates, and so does this)
     int last_level = -1;
