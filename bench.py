@@ -384,6 +384,7 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "voxel_m": VOXEL, "storage": "f32 20 B/voxel", "cubes_per_frame": cubes,
                    "updated_voxels_per_frame": int(upd), "icp_points": n_pts,
+                   "icp_exact_searches_per_frame": int(searched.value), "icp_queries_per_frame": n_pts * (ICP_ITERS + 1),
                    "l2": "voxel working set of a frame (cubes x 10 KB) exceeds the 126 MB L2; no explicit flush",
                    "sharding": "one independent sub-volume stream per GPU, no data-path collective",
                    "step_breakdown_ms": {"icp_grid_build": icp_grid_ms / nprof_steps, "icp_iterations": icp_loop_ms / nprof_steps,

@@ -31,6 +31,8 @@
 #include <cfloat>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <vector>
 
 #include "../../include/onepiece_b200.h"
@@ -860,6 +862,29 @@ __global__ void __launch_bounds__(kOdoThreads) odo_rmse_kernel(const uint4 *__re
 
 using namespace opb;
 
+// Device buffers of released frames, kept for the next frame of the same size: a tracking loop creates and releases one
+// RGBDFrame per image, and cudaMalloc / cudaFree (which synchronises the device) cost more than the tracking itself.
+// Shared between the odometry object and its frames so that either may be destroyed first.
+struct FrameBuffers
+{
+    uint8_t *bgr = nullptr;
+    void *depth = nullptr;
+    float *images = nullptr;
+};
+struct FramePool
+{
+    int device = 0;
+    std::mutex lock;
+    std::vector<FrameBuffers> free_sets;
+    ~FramePool()
+    {
+        cudaSetDevice(device);
+        for (FrameBuffers &b : free_sets) { cudaFree(b.bgr); cudaFree(b.depth); cudaFree(b.images); }
+        cudaGetLastError();
+    }
+};
+constexpr size_t kFramePoolCap = 8;
+
 struct opb_odometry
 {
     int device = 0;
@@ -879,6 +904,7 @@ struct opb_odometry
     OdoState *d_state = nullptr;
     OdoState *h_state = nullptr; // pinned
     int max_blocks = 0;
+    std::shared_ptr<FramePool> frame_pool;
     unsigned int *d_sync = nullptr; // barrier words of the persistent loop kernel
     int coop_ctas_per_sm = 0;       // resident CTAs per SM of odo_loop_kernel; 0: cooperative launch unavailable
     bool profiling = false;
@@ -888,6 +914,7 @@ struct opb_odometry
 
 struct opb_frame
 {
+    std::shared_ptr<FramePool> pool;
     opb_odometry *owner = nullptr; // identity check only, never dereferenced on destruction
     int device = 0;
     int w = 0, h = 0, depth_type = 0;
@@ -972,6 +999,8 @@ int opb_odometry_create(const opb_odometry_desc *desc, opb_odometry **out)
     o->device = desc->device;
     o->desc = *desc;
     setup_cameras(o);
+    o->frame_pool = std::make_shared<FramePool>();
+    o->frame_pool->device = desc->device;
     cudaDeviceProp prop;
     OPB_CUDA(cudaGetDeviceProperties(&prop, desc->device));
     o->sm_count = prop.multiProcessorCount;
@@ -1037,9 +1066,25 @@ int opb_odometry_last_timing(opb_odometry *o, float *tracking_ms, float *solve_t
 void opb_frame_destroy(opb_frame *f)
 {
     if (!f) return;
-    cudaSetDevice(f->device); // cudaFree synchronises the device: no kernel can still be reading the frame
-    cudaFree(f->d_bgr); cudaFree(f->d_depth); cudaFree(f->d_images);
-    cudaGetLastError();
+    bool kept = false;
+    if (f->pool && f->d_bgr && f->d_depth && f->d_images)
+    {
+        // the next user of these buffers uploads on the odometry's stream, i.e. after every kernel that still reads them
+        std::lock_guard<std::mutex> g(f->pool->lock);
+        if (f->pool->free_sets.size() < kFramePoolCap)
+        {
+            FrameBuffers b;
+            b.bgr = f->d_bgr; b.depth = f->d_depth; b.images = f->d_images;
+            f->pool->free_sets.push_back(b);
+            kept = true;
+        }
+    }
+    if (!kept)
+    {
+        cudaSetDevice(f->device); // cudaFree synchronises the device: no kernel can still be reading the frame
+        cudaFree(f->d_bgr); cudaFree(f->d_depth); cudaFree(f->d_images);
+        cudaGetLastError();
+    }
     delete f;
 }
 
@@ -1060,9 +1105,23 @@ int opb_frame_create(opb_odometry *o, const uint8_t *bgr, const void *depth, int
     const size_t n = level_pixels(o, 0);
     size_t total = 0;
     for (int l = 0; l < o->desc.levels; ++l) total += 6 * level_pixels(o, l);
-    cudaError_t e = cudaMalloc(&f->d_bgr, n * 3);
-    if (e == cudaSuccess) e = cudaMalloc(&f->d_depth, n * (depth_type == OPB_DEPTH_U16 ? 2 : 4));
-    if (e == cudaSuccess) e = cudaMalloc(&f->d_images, total * sizeof(float));
+    f->pool = o->frame_pool;
+    cudaError_t e = cudaSuccess;
+    {
+        std::lock_guard<std::mutex> g(f->pool->lock);
+        if (!f->pool->free_sets.empty())
+        {
+            const FrameBuffers b = f->pool->free_sets.back();
+            f->pool->free_sets.pop_back();
+            f->d_bgr = b.bgr; f->d_depth = b.depth; f->d_images = b.images;
+        }
+    }
+    if (!f->d_images)
+    {
+        e = cudaMalloc(&f->d_bgr, n * 3);
+        if (e == cudaSuccess) e = cudaMalloc(&f->d_depth, n * 4); // sized for float depth, so that any frame can reuse it
+        if (e == cudaSuccess) e = cudaMalloc(&f->d_images, total * sizeof(float));
+    }
     if (e != cudaSuccess)
     {
         set_error("frame allocation failed: %s", cudaGetErrorString(e));
