@@ -166,6 +166,12 @@ int opb_volume_count_mesh(opb_volume *v, size_t *nv, size_t *nt);
 int opb_mesh_clustering_simplify(int device, const float *points, const float *colors, size_t nv, const uint32_t *triangles, size_t nt,
                                  float grid_len, float **out_points, float **out_colors, uint32_t **out_triangles, size_t *out_nv,
                                  size_t *out_nt);
+/* PointCloud::DownSample(grid_len) (src/Geometry/PointCloud.cpp:145-189; SURVEY.md §8f rank 5, first item): voxel-grid
+ * down-sampling -- one output point per occupied grid cell, in the order in which the cells are first met, each the mean of
+ * the cell's points summed in input order (bit-identical to the reference); colors / normals (optional, 3 floats per point)
+ * are averaged alike.  Inputs host or device; outputs malloc'ed by the library (opb_free). */
+int opb_pointcloud_downsample(int device, const float *points, const float *colors, const float *normals, size_t n, float grid_len,
+                              float **out_points, float **out_colors, float **out_normals, size_t *out_n);
 /* TriangleMesh::ComputeNormals (src/Geometry/TriangleMesh.cpp:95-127): unit face normals, vertex normal = normalised sum of
  * the normals of the faces referencing the vertex, summed in the reference's order.  normals: 3 x nv floats, host or device. */
 int opb_mesh_compute_normals(int device, const float *points, size_t nv, const uint32_t *triangles, size_t nt, float *normals);

@@ -113,6 +113,7 @@ SIGNATURES = {
     "opb_volume_count_mesh": (C.c_int, [_p, C.POINTER(_sz), C.POINTER(_sz)]),
     "opb_mesh_clustering_simplify": (C.c_int, [C.c_int, _p, _p, _sz, _p, _sz, C.c_float, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p),
                                                C.POINTER(_sz), C.POINTER(_sz)]),
+    "opb_pointcloud_downsample": (C.c_int, [C.c_int, _p, _p, _p, _sz, C.c_float, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_sz)]),
     "opb_mesh_compute_normals": (C.c_int, [C.c_int, _p, _sz, _p, _sz, _p]),
     "opb_volume_extract_mesh_clustered": (C.c_int, [_p, C.c_float, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_sz), C.POINTER(_sz)]),
     "opb_volume_transform": (C.c_int, [_p, _p, C.c_int, C.c_float, C.c_int32, C.POINTER(_p)]),

@@ -72,8 +72,9 @@ __global__ void __launch_bounds__(1024) post_scan_kernel(unsigned int *counts, i
 struct ClusterDev
 {
     const float *points;      // nv x 3
-    const unsigned int *tri;  // nt x 3
+    const unsigned int *tri;  // nt x 3 vertex references; nullptr: reference s is point s itself (point-cloud down-sampling)
     int nv, nt;
+    int nref;                 // 3 * nt, or the number of points
     float grid_len;
     unsigned long long *keys; // hash table of cells (cap entries)
     unsigned int *vals;       // dense cell index per table entry
@@ -105,13 +106,15 @@ __device__ __forceinline__ bool cell_key(const ClusterDev &d, unsigned int v, un
     return true;
 }
 
+__device__ __forceinline__ unsigned int ref_vertex(const ClusterDev &d, int s) { return d.tri ? d.tri[s] : (unsigned int)s; }
+
 // A1: register the cell of every vertex reference; the inserting thread draws the dense cell index
 __global__ void __launch_bounds__(256) cluster_insert_kernel(ClusterDev d)
 {
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < 3 * d.nt; s += gridDim.x * blockDim.x)
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < d.nref; s += gridDim.x * blockDim.x)
     {
         unsigned long long key;
-        if (!cell_key(d, d.tri[s], key)) { *d.bad = 1; continue; }
+        if (!cell_key(d, ref_vertex(d, s), key)) { *d.bad = 1; continue; }
         unsigned int h = (unsigned int)cluster_hash(key) & d.cap_mask;
         for (;;)
         {
@@ -125,10 +128,10 @@ __global__ void __launch_bounds__(256) cluster_insert_kernel(ClusterDev d)
 // A2: dense cell of every reference + population count per cell
 __global__ void __launch_bounds__(256) cluster_lookup_kernel(ClusterDev d)
 {
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < 3 * d.nt; s += gridDim.x * blockDim.x)
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < d.nref; s += gridDim.x * blockDim.x)
     {
         unsigned long long key;
-        if (!cell_key(d, d.tri[s], key)) continue;
+        if (!cell_key(d, ref_vertex(d, s), key)) continue;
         unsigned int h = (unsigned int)cluster_hash(key) & d.cap_mask;
         while (d.keys[h] != key) h = (h + 1) & d.cap_mask;
         const unsigned int c = d.vals[h];
@@ -139,12 +142,54 @@ __global__ void __launch_bounds__(256) cluster_lookup_kernel(ClusterDev d)
 // C: group the references per cell (order inside a cell is fixed by the next kernel)
 __global__ void __launch_bounds__(256) cluster_scatter_kernel(ClusterDev d)
 {
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < 3 * d.nt; s += gridDim.x * blockDim.x)
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < d.nref; s += gridDim.x * blockDim.x)
     {
         const unsigned int c = d.ref_cell[s];
         d.members[d.cell_off[c] + atomicAdd(&d.cell_fill[c], 1u)] = (unsigned int)s;
     }
 }
+// Segments too long for a per-thread insertion sort (a coarse grid puts thousands of references into one cell) are listed ...
+constexpr int kSmallSegment = 64;
+__global__ void __launch_bounds__(256) find_big_segments_kernel(const unsigned int *fill, int n_segments, unsigned int *big_list, unsigned int *n_big)
+{
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_segments; c += gridDim.x * blockDim.x)
+        if (fill[c] > (unsigned int)kSmallSegment) big_list[atomicAdd(n_big, 1u)] = (unsigned int)c;
+}
+// ... and sorted by one CTA each: bottom-up merge sort, every element finds its place in the merged run by binary search in
+// the sibling run (the keys are distinct reference numbers)
+__global__ void __launch_bounds__(1024) sort_big_segments_kernel(unsigned int *members, unsigned int *scratch, const unsigned int *off,
+                                                                 const unsigned int *fill, const unsigned int *big_list, const unsigned int *n_big)
+{
+    for (unsigned int b = blockIdx.x; b < *n_big; b += gridDim.x)
+    {
+        const unsigned int c = big_list[b], n = fill[c];
+        unsigned int *src = members + off[c], *dst = scratch + off[c];
+        for (unsigned int w = 1; w < n; w <<= 1)
+        {
+            for (unsigned int i = threadIdx.x; i < n; i += blockDim.x)
+            {
+                const unsigned int base = i / (2 * w) * (2 * w);
+                const unsigned int mid = min(base + w, n), end = min(base + 2 * w, n);
+                const unsigned int key = src[i];
+                unsigned int lo = i < mid ? mid : base, hi = i < mid ? end : mid; // the sibling run
+                while (lo < hi)
+                {
+                    const unsigned int m = (lo + hi) >> 1;
+                    if (src[m] < key) lo = m + 1;
+                    else hi = m;
+                }
+                const unsigned int pos = i < mid ? i + (lo - mid) : (lo - base) + base + (i - mid);
+                dst[pos] = key;
+            }
+            __syncthreads();
+            unsigned int *t = src; src = dst; dst = t;
+        }
+        if (src != members + off[c])
+            for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+}
+
 // D: thread = cell.  Members into ascending reference order (the order of the reference's loop), then the sequential float
 // sum grid_to_point[cell] += p (MeshSimplification.cpp:611-613) and points[rep] = sum / count (:135).
 __global__ void __launch_bounds__(128) cluster_reduce_kernel(ClusterDev d, int n_cells)
@@ -153,19 +198,19 @@ __global__ void __launch_bounds__(128) cluster_reduce_kernel(ClusterDev d, int n
     {
         unsigned int *m = d.members + d.cell_off[c];
         const int n = (int)d.cell_fill[c];
-        for (int i = 1; i < n; ++i)
+        for (int i = 1; i < n && n <= kSmallSegment; ++i) // longer segments were sorted by sort_big_segments_kernel
         {
             const unsigned int v = m[i];
             int j = i - 1;
             while (j >= 0 && m[j] > v) { m[j + 1] = m[j]; --j; }
             m[j + 1] = v;
         }
-        const unsigned int rep = d.tri[m[0]];
+        const unsigned int rep = ref_vertex(d, (int)m[0]);
         const float *p0 = d.points + 3 * (size_t)rep;
         float sx = p0[0], sy = p0[1], sz = p0[2];
         for (int i = 1; i < n; ++i)
         {
-            const float *p = d.points + 3 * (size_t)d.tri[m[i]];
+            const float *p = d.points + 3 * (size_t)ref_vertex(d, (int)m[i]);
             sx = fadd(sx, p[0]); sy = fadd(sy, p[1]); sz = fadd(sz, p[2]);
         }
         const float cnt = (float)n;
@@ -228,6 +273,42 @@ __global__ void __launch_bounds__(256) cluster_remap_kernel(unsigned int *out_tr
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out_tri[i] = vertex_off[out_tri[i]];
 }
 
+// ---- PointCloud::DownSample (src/Geometry/PointCloud.cpp:145-189) -----------------------------------------------------------
+// The same grouping with the points themselves as references: the first point of a cell (input order) opens the output slot,
+// the others are added in input order, the slot is divided by the population.  Colours and normals ride along: an attribute
+// is summed over the members the cluster kernels left in ascending order.
+__global__ void __launch_bounds__(128) downsample_attribute_kernel(ClusterDev d, int n_cells, const float *attr, float *cell_attr)
+{
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += gridDim.x * blockDim.x)
+    {
+        const unsigned int *m = d.members + d.cell_off[c];
+        const int n = (int)d.cell_fill[c];
+        const float *a0 = attr + 3 * (size_t)m[0];
+        float sx = a0[0], sy = a0[1], sz = a0[2];
+        for (int i = 1; i < n; ++i)
+        {
+            const float *a = attr + 3 * (size_t)m[i];
+            sx = fadd(sx, a[0]); sy = fadd(sy, a[1]); sz = fadd(sz, a[2]);
+        }
+        const float cnt = (float)n;
+        cell_attr[3 * c] = fdiv(sx, cnt); cell_attr[3 * c + 1] = fdiv(sy, cnt); cell_attr[3 * c + 2] = fdiv(sz, cnt);
+    }
+}
+__global__ void __launch_bounds__(256) downsample_mark_kernel(ClusterDev d, int n_cells, unsigned int *first_flag)
+{
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += gridDim.x * blockDim.x) first_flag[d.cell_rep[c]] = 1u;
+}
+// output slot of a cell = rank of its first point among all first points (the order in which the reference opens slots)
+__global__ void __launch_bounds__(256) downsample_place_kernel(ClusterDev d, int n_cells, const unsigned int *slot_of_point, const float *cell_attr,
+                                                               float *out)
+{
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += gridDim.x * blockDim.x)
+    {
+        const size_t o = slot_of_point[d.cell_rep[c]];
+        out[3 * o] = cell_attr[3 * c]; out[3 * o + 1] = cell_attr[3 * c + 1]; out[3 * o + 2] = cell_attr[3 * c + 2];
+    }
+}
+
 // ---- ComputeNormals -------------------------------------------------------------------------------------------------
 // Eigen Vector3f::normalize(): z = squaredNorm() in Eigen's 3-term order a0 + (a1 + a2); if (z > 0) v /= sqrt(z)
 __device__ __forceinline__ void normalize3(float &x, float &y, float &z)
@@ -272,7 +353,7 @@ __global__ void __launch_bounds__(128) normals_vertex_kernel(const float *face_n
     {
         unsigned int *m = members + vertex_off[v];
         const int n = (int)vertex_fill[v];
-        for (int i = 1; i < n; ++i)
+        for (int i = 1; i < n && n <= kSmallSegment; ++i) // longer segments were sorted by sort_big_segments_kernel
         {
             const unsigned int x = m[i];
             int j = i - 1;
@@ -323,10 +404,10 @@ int clustering_simplify_device(int sm_count, cudaStream_t s, const float *d_poin
     while (cap < 2 * nref) cap <<= 1;
     Arena A;
     A.cap = cap * 12 + nref * 4 * 2 + nref * 4 * 3 /* cell arrays, worst case one cell per reference */ + nref * 4 * 4 + nt * 4 * 5 + nv * 4 * 5 +
-            nv * 12 + 64 * 256;
+            nv * 12 + nref * 4 * 2 /* big-segment list and sort scratch */ + 64 * 256;
     OPB_CUDA(cudaMalloc(&A.base, A.cap));
     ClusterDev d;
-    d.points = d_points; d.tri = d_tri; d.nv = (int)nv; d.nt = (int)nt; d.grid_len = grid_len;
+    d.points = d_points; d.tri = d_tri; d.nv = (int)nv; d.nt = (int)nt; d.nref = (int)nref; d.grid_len = grid_len;
     d.keys = A.take<unsigned long long>(cap);
     d.vals = A.take<unsigned int>(cap);
     d.cap_mask = (unsigned int)(cap - 1);
@@ -339,6 +420,7 @@ int clustering_simplify_device(int sm_count, cudaStream_t s, const float *d_poin
     d.cell_rep = A.take<unsigned int>(nref);
     d.cell_mean = A.take<float>(3 * nref);
     unsigned int *tri_new = A.take<unsigned int>(nref), *keep = A.take<unsigned int>(nt + 1), *vertex_used = A.take<unsigned int>(nv + 1);
+    unsigned int *big_list = A.take<unsigned int>(nref / kSmallSegment + 1), *sort_scratch = A.take<unsigned int>(nref);
     float *points2 = A.take<float>(3 * nv);
     int rc = OPB_OK;
     float *out_p = nullptr, *out_c = nullptr;
@@ -361,6 +443,8 @@ int clustering_simplify_device(int sm_count, cudaStream_t s, const float *d_poin
         cluster_lookup_kernel<<<grid_for(nref, sm_count), 256, 0, s>>>(d);
         post_scan_kernel<<<1, 1024, 0, s>>>(d.cell_off, n_cells, counters + 4);
         cluster_scatter_kernel<<<grid_for(nref, sm_count), 256, 0, s>>>(d);
+        find_big_segments_kernel<<<grid_for(n_cells, sm_count), 256, 0, s>>>(d.cell_fill, n_cells, big_list, counters + 5);
+        sort_big_segments_kernel<<<sm_count * 2, 1024, 0, s>>>(d.members, sort_scratch, d.cell_off, d.cell_fill, big_list, counters + 5);
         cluster_reduce_kernel<<<grid_for((size_t)n_cells * 2, sm_count, 16), 128, 0, s>>>(d, n_cells);
         cluster_triangles_kernel<<<grid_for(nt, sm_count), 256, 0, s>>>(d, tri_new, keep);
         post_scan_kernel<<<1, 1024, 0, s>>>(keep, (int)nt, counters + 2);
@@ -475,6 +559,108 @@ int opb_mesh_clustering_simplify(int device, const float *points, const float *c
     return OPB_OK;
 }
 
+int opb_pointcloud_downsample(int device, const float *points, const float *colors, const float *normals, size_t n, float grid_len,
+                              float **out_points, float **out_colors, float **out_normals, size_t *out_n)
+{
+    if (!points || !out_points || !out_n || (colors && !out_colors) || (normals && !out_normals)) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    *out_points = nullptr; *out_n = 0;
+    if (out_colors) *out_colors = nullptr;
+    if (out_normals) *out_normals = nullptr;
+    if (!(grid_len > 0)) { set_error("grid_len must be > 0"); return OPB_ERR_INVALID; }
+    if (n == 0) return OPB_OK;
+    if (n > 0x7FFFFFF0u) { set_error("point cloud too large for 32-bit indices"); return OPB_ERR_CAPACITY; }
+    int sm = 0;
+    int rc = post_device(device, &sm);
+    if (rc) return rc;
+    size_t cap = 1024;
+    while (cap < 2 * n) cap <<= 1;
+    const int n_attr = 1 + (colors ? 1 : 0) + (normals ? 1 : 0);
+    Arena A;
+    A.cap = cap * 12 + n * 4 * 10 + n * 12 * (size_t)(2 * n_attr + 1) + 64 * 256;
+    OPB_CUDA(cudaMalloc(&A.base, A.cap));
+    ClusterDev d;
+    float *d_in[3] = {A.take<float>(3 * n), colors ? A.take<float>(3 * n) : nullptr, normals ? A.take<float>(3 * n) : nullptr};
+    const float *h_in[3] = {points, colors, normals};
+    d.points = d_in[0]; d.tri = nullptr; d.nv = (int)n; d.nt = 0; d.nref = (int)n; d.grid_len = grid_len;
+    d.keys = A.take<unsigned long long>(cap);
+    d.vals = A.take<unsigned int>(cap);
+    d.cap_mask = (unsigned int)(cap - 1);
+    unsigned int *counters = A.take<unsigned int>(8);
+    d.n_cells = counters; d.bad = (int *)(counters + 1);
+    d.ref_cell = A.take<unsigned int>(n);
+    d.members = A.take<unsigned int>(n);
+    d.cell_off = A.take<unsigned int>(n + 1);
+    d.cell_fill = A.take<unsigned int>(n);
+    d.cell_rep = A.take<unsigned int>(n);
+    d.cell_mean = A.take<float>(3 * n);
+    unsigned int *first_flag = A.take<unsigned int>(n + 1);
+    float *cell_attr = A.take<float>(3 * n), *d_out = A.take<float>(3 * n);
+    unsigned int *big_list = A.take<unsigned int>(n / kSmallSegment + 1), *sort_scratch = A.take<unsigned int>(n);
+    cudaStream_t s = nullptr;
+    float *h_out[3] = {nullptr, nullptr, nullptr};
+    do
+    {
+#define OPB_TRY(expr) if ((expr) != cudaSuccess) { set_error("%s failed: %s", #expr, cudaGetErrorString(cudaGetLastError())); rc = OPB_ERR_CUDA; break; }
+        if (A.used > A.cap) { set_error("internal: scratch arena too small"); rc = OPB_ERR_CAPACITY; break; }
+        for (int a = 0; a < 3 && rc == OPB_OK; ++a)
+            if (d_in[a] && cudaMemcpyAsync(d_in[a], h_in[a], n * 3 * sizeof(float), cudaMemcpyDefault, s) != cudaSuccess)
+            {
+                set_error("point cloud upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = OPB_ERR_CUDA;
+            }
+        if (rc) break;
+        OPB_TRY(cudaMemsetAsync(d.keys, 0xFF, cap * sizeof(unsigned long long), s));
+        OPB_TRY(cudaMemsetAsync(counters, 0, 8 * sizeof(unsigned int), s));
+        OPB_TRY(cudaMemsetAsync(d.cell_off, 0, (n + 1) * sizeof(unsigned int), s));
+        OPB_TRY(cudaMemsetAsync(d.cell_fill, 0, n * sizeof(unsigned int), s));
+        OPB_TRY(cudaMemsetAsync(first_flag, 0, (n + 1) * sizeof(unsigned int), s));
+        cluster_insert_kernel<<<grid_for(n, sm), 256, 0, s>>>(d);
+        unsigned int h_counters[8];
+        OPB_TRY(cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, s));
+        OPB_TRY(cudaStreamSynchronize(s));
+        if (h_counters[1]) { set_error("point cloud has a point outside +-2^20 grid cells (or NaN)"); rc = OPB_ERR_INVALID; break; }
+        const int n_cells = (int)h_counters[0];
+        cluster_lookup_kernel<<<grid_for(n, sm), 256, 0, s>>>(d);
+        post_scan_kernel<<<1, 1024, 0, s>>>(d.cell_off, n_cells, counters + 4);
+        cluster_scatter_kernel<<<grid_for(n, sm), 256, 0, s>>>(d);
+        find_big_segments_kernel<<<grid_for(n_cells, sm), 256, 0, s>>>(d.cell_fill, n_cells, big_list, counters + 5);
+        sort_big_segments_kernel<<<sm * 2, 1024, 0, s>>>(d.members, sort_scratch, d.cell_off, d.cell_fill, big_list, counters + 5);
+        cluster_reduce_kernel<<<grid_for((size_t)n_cells * 2, sm, 16), 128, 0, s>>>(d, n_cells); // sorts the members; mean position
+        downsample_mark_kernel<<<grid_for(n_cells, sm), 256, 0, s>>>(d, n_cells, first_flag);
+        post_scan_kernel<<<1, 1024, 0, s>>>(first_flag, (int)n, counters + 2);
+        OPB_TRY(cudaGetLastError());
+        for (int a = 0; a < 3 && rc == OPB_OK; ++a)
+        {
+            if (!d_in[a]) continue;
+            const float *means = d.cell_mean;
+            if (a > 0)
+            {
+                downsample_attribute_kernel<<<grid_for((size_t)n_cells * 2, sm, 16), 128, 0, s>>>(d, n_cells, d_in[a], cell_attr);
+                means = cell_attr;
+            }
+            downsample_place_kernel<<<grid_for(n_cells, sm), 256, 0, s>>>(d, n_cells, first_flag, means, d_out);
+            h_out[a] = (float *)malloc((size_t)n_cells * 3 * sizeof(float) + 4);
+            if (!h_out[a]) { set_error("host allocation failed"); rc = OPB_ERR_CAPACITY; break; }
+            if (cudaMemcpyAsync(h_out[a], d_out, (size_t)n_cells * 3 * sizeof(float), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                cudaStreamSynchronize(s) != cudaSuccess)
+            {
+                set_error("down-sampling failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = OPB_ERR_CUDA;
+            }
+        }
+        if (rc) break;
+        *out_points = h_out[0];
+        if (colors) *out_colors = h_out[1];
+        if (normals) *out_normals = h_out[2];
+        *out_n = (size_t)n_cells;
+        h_out[0] = h_out[1] = h_out[2] = nullptr;
+#undef OPB_TRY
+    } while (0);
+    cudaFree(A.base);
+    for (int a = 0; a < 3; ++a) free(h_out[a]);
+    return rc;
+}
+
 int opb_mesh_compute_normals(int device, const float *points, size_t nv, const uint32_t *triangles, size_t nt, float *normals)
 {
     if (!points || !triangles || !normals) { set_error("NULL argument"); return OPB_ERR_INVALID; }
@@ -485,11 +671,12 @@ int opb_mesh_compute_normals(int device, const float *points, size_t nv, const u
     if (rc) return rc;
     const size_t nref = 3 * nt;
     Arena A;
-    A.cap = nv * 12 * 2 + nref * 4 * 2 + nt * 12 + nv * 4 * 2 + 64 * 256;
+    A.cap = nv * 12 * 2 + nref * 4 * 4 + nt * 12 + nv * 4 * 2 + 64 * 256;
     OPB_CUDA(cudaMalloc(&A.base, A.cap));
     float *d_p = A.take<float>(3 * nv), *d_n = A.take<float>(3 * nv), *face_n = A.take<float>(3 * (nt ? nt : 1));
     unsigned int *d_t = A.take<unsigned int>(nref ? nref : 1), *members = A.take<unsigned int>(nref ? nref : 1);
     unsigned int *v_off = A.take<unsigned int>(nv + 1), *v_fill = A.take<unsigned int>(nv + 1), *counters = A.take<unsigned int>(8);
+    unsigned int *big_list = A.take<unsigned int>(nref / kSmallSegment + 2), *sort_scratch = A.take<unsigned int>(nref ? nref : 1);
     cudaStream_t s = nullptr;
     do
     {
@@ -506,6 +693,8 @@ int opb_mesh_compute_normals(int device, const float *points, size_t nv, const u
         if (h_counters[1]) { set_error("mesh has a triangle naming a missing vertex"); rc = OPB_ERR_INVALID; break; }
         post_scan_kernel<<<1, 1024, 0, s>>>(v_off, (int)nv, counters);
         if (nt) normals_scatter_kernel<<<grid_for(nref, sm), 256, 0, s>>>(d_t, (int)nt, v_off, v_fill, members);
+        find_big_segments_kernel<<<grid_for(nv, sm), 256, 0, s>>>(v_fill, (int)nv, big_list, counters + 5);
+        sort_big_segments_kernel<<<sm * 2, 1024, 0, s>>>(members, sort_scratch, v_off, v_fill, big_list, counters + 5);
         normals_vertex_kernel<<<grid_for(nv * 2, sm, 16), 128, 0, s>>>(face_n, v_off, v_fill, members, (int)nv, d_n);
         OPB_TRY(cudaGetLastError());
         OPB_TRY(cudaMemcpyAsync(normals, d_n, nv * 3 * sizeof(float), cudaMemcpyDefault, s));

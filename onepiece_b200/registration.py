@@ -39,6 +39,26 @@ class PointCloud:
     def HasNormals(self):
         return self.normals is not None and len(self.normals) == len(self.points) and len(self.points) > 0
 
+    def DownSample(self, grid_len: float, colors=None, device: int = 0):
+        """PointCloud::DownSample(grid_len) (reference src/Geometry/PointCloud.cpp:145-189) on the GPU -> new PointCloud
+        (and the averaged colours when `colors` is given: returns (cloud, colors))."""
+        col = None if colors is None else np.ascontiguousarray(colors, np.float32).reshape(-1, 3)
+        nrm = self.normals if self.HasNormals() else None
+        op, oc, on = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n = C.c_size_t(0)
+        capi.check(capi.lib.opb_pointcloud_downsample(device, _ptr(self.points), _ptr(col), _ptr(nrm), len(self.points), grid_len,
+                                                      C.byref(op), C.byref(oc) if col is not None else None,
+                                                      C.byref(on) if nrm is not None else None, C.byref(n)))
+
+        def take(p):
+            if not p.value:
+                return np.zeros((0, 3), np.float32)
+            a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n.value * 3,)).reshape(-1, 3).copy()
+            capi.lib.opb_free(p)
+            return a
+        out = PointCloud(take(op), take(on) if nrm is not None else None)
+        return (out, take(oc)) if col is not None else out
+
 
 class _Workspace:
     _by_device = {}

@@ -1591,3 +1591,56 @@ void orc_compute_normals(const float *points, long n_points, const uint32_t *tri
     for (long i = 0; i < n_points; ++i) normalize3(normals + 3 * i);
     free(fn);
 }
+
+/* PointCloud::DownSample (src/Geometry/PointCloud.cpp:145-189): voxel-grid down-sampling.  The first point (in input order) of
+ * every grid cell opens an output slot, later points of the cell are added to it in input order (float sums), every slot is
+ * finally divided by its population; colours and normals (optional) are treated alike.  Returns the number of output points;
+ * outputs must hold n entries. */
+long orc_downsample(const float *points, const float *colors, const float *normals, long n, float grid_len, float *out_points,
+                    float *out_colors, float *out_normals)
+{
+    long cap = 16;
+    while (cap < 2 * n + 16) cap <<= 1;
+    cell_t *cells = (cell_t *)calloc(cap, sizeof(cell_t)); /* rep = output slot, count = population */
+    long ptr = 0;
+    for (long i = 0; i < n; ++i)
+    {
+        const float *p = points + 3 * i;
+        const int key[3] = {(int)floorf(p[0] / grid_len), (int)floorf(p[1] / grid_len), (int)floorf(p[2] / grid_len)};
+        unsigned long h = cell_hash(key) & (cap - 1);
+        while (cells[h].used && (cells[h].key[0] != key[0] || cells[h].key[1] != key[1] || cells[h].key[2] != key[2])) h = (h + 1) & (cap - 1);
+        cell_t *c = &cells[h];
+        if (!c->used)
+        {
+            c->used = 1; c->key[0] = key[0]; c->key[1] = key[1]; c->key[2] = key[2];
+            c->rep = (int)ptr; c->count = 1;
+            for (int a = 0; a < 3; ++a)
+            {
+                out_points[3 * ptr + a] = p[a];
+                if (colors) out_colors[3 * ptr + a] = colors[3 * i + a];
+                if (normals) out_normals[3 * ptr + a] = normals[3 * i + a];
+            }
+            ++ptr;
+        }
+        else
+        {
+            for (int a = 0; a < 3; ++a)
+            {
+                out_points[3 * (long)c->rep + a] += p[a];
+                if (colors) out_colors[3 * (long)c->rep + a] += colors[3 * i + a];
+                if (normals) out_normals[3 * (long)c->rep + a] += normals[3 * i + a];
+            }
+            c->count += 1;
+        }
+    }
+    for (long h = 0; h < cap; ++h)
+        if (cells[h].used)
+            for (int a = 0; a < 3; ++a)
+            {
+                out_points[3 * (long)cells[h].rep + a] /= (float)cells[h].count;
+                if (colors) out_colors[3 * (long)cells[h].rep + a] /= (float)cells[h].count;
+                if (normals) out_normals[3 * (long)cells[h].rep + a] /= (float)cells[h].count;
+            }
+    free(cells);
+    return ptr;
+}

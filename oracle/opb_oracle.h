@@ -119,6 +119,10 @@ int orc_clustering_simplify(float *points, float *colors, long *n_points, uint32
 /* TriangleMesh::ComputeNormals (TriangleMesh.cpp:95-127) */
 void orc_compute_normals(const float *points, long n_points, const uint32_t *tri, long n_tris, float *normals);
 
+/* PointCloud::DownSample (PointCloud.cpp:145-189); returns the number of output points */
+long orc_downsample(const float *points, const float *colors, const float *normals, long n, float grid_len, float *out_points,
+                    float *out_colors, float *out_normals);
+
 /* caller-side depth pre-filter: tool::ConvertDepthTo32F (ImageProcessing.cpp:68-91), tool::BilateralFilter (:64-67) */
 void orc_convert_depth_32f(const void *depth, int is_u16, long n, float depth_scale, float *out);
 void orc_bilateral_filter(const float *src, int w, int h, int d, double sigma_color, double sigma_space, float *dst);

@@ -76,6 +76,8 @@ def lib():
     L.orc_clustering_simplify.restype = c_i
     L.orc_clustering_simplify.argtypes = [c_p, c_p, c_p, c_p, c_p, c_f]
     L.orc_compute_normals.argtypes = [c_p, c_l, c_p, c_l, c_p]
+    L.orc_downsample.restype = c_l
+    L.orc_downsample.argtypes = [c_p, c_p, c_p, c_l, c_f, c_p, c_p, c_p]
     L.orc_volume_transform.restype = c_p
     L.orc_volume_transform.argtypes = [c_p, c_p, c_i, c_f]
     L.orc_volume_merge.restype = c_i
@@ -391,3 +393,15 @@ def compute_normals(points, triangles):
     out = np.zeros_like(pts)
     lib().orc_compute_normals(_ptr(pts), len(pts), _ptr(tri), len(tri), _ptr(out))
     return out
+
+
+def downsample(points, colors, normals, grid_len):
+    """PointCloud::DownSample(grid_len) -> (points, colors or None, normals or None)"""
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    col = None if colors is None else np.ascontiguousarray(colors, np.float32).reshape(-1, 3)
+    nrm = None if normals is None else np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+    op = np.zeros_like(pts)
+    oc = None if col is None else np.zeros_like(pts)
+    on = None if nrm is None else np.zeros_like(pts)
+    n = lib().orc_downsample(_ptr(pts), _ptr(col), _ptr(nrm), len(pts), grid_len, _ptr(op), _ptr(oc), _ptr(on))
+    return op[:n].copy(), None if oc is None else oc[:n].copy(), None if on is None else on[:n].copy()

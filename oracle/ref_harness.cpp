@@ -243,6 +243,33 @@ double ref_clustering_simplify(float *points, float *colors, long *n_points, uin
         for (int k = 0; k < 3; ++k) tri[3 * i + k] = out->triangles[i](k);
     return dt;
 }
+#ifndef USING_FLOAT64
+// PointCloud::DownSample (PointCloud.cpp:145-189); outputs hold n entries, returns the number written
+long ref_downsample(const float *points, const float *colors, const float *normals, long n, float grid_len, float *out_points,
+                    float *out_colors, float *out_normals)
+{
+    geometry::PointCloud pcd;
+    pcd.points.resize(n);
+    if (colors) pcd.colors.resize(n);
+    if (normals) pcd.normals.resize(n);
+    for (long i = 0; i < n; ++i)
+    {
+        pcd.points[i] = geometry::Point3(points[3 * i], points[3 * i + 1], points[3 * i + 2]);
+        if (colors) pcd.colors[i] = geometry::Point3(colors[3 * i], colors[3 * i + 1], colors[3 * i + 2]);
+        if (normals) pcd.normals[i] = geometry::Point3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]);
+    }
+    auto out = pcd.DownSample(grid_len);
+    const long m = (long)out->points.size();
+    for (long i = 0; i < m; ++i)
+        for (int k = 0; k < 3; ++k)
+        {
+            out_points[3 * i + k] = (float)out->points[i](k);
+            if (colors) out_colors[3 * i + k] = (float)out->colors[i](k);
+            if (normals) out_normals[3 * i + k] = (float)out->normals[i](k);
+        }
+    return m;
+}
+#endif
 // TriangleMesh::WriteToPLY (TriangleMesh.cpp:128-131 -> tool::WritePLY, PLYManager.cpp:188-276)
 bool ref_write_ply(const char *path, const float *points, const float *normals, const float *colors, long n_points, const uint32_t *tri, long n_tris)
 {

@@ -81,6 +81,8 @@ def lib(kind: str = "f32"):
     if kind == "f32":
         L.ref_load_from_depth.restype = c_l
         L.ref_load_from_depth.argtypes = [c_p, c_i, c_i, c_i] + [c_f] * 5 + [c_p]
+        L.ref_downsample.restype = c_l
+        L.ref_downsample.argtypes = [c_p, c_p, c_p, c_l, c_f, c_p, c_p, c_p]
         L.ref_estimate_normals.restype = c_d
         L.ref_estimate_normals.argtypes = [c_p, c_l, c_f, c_i, c_p]
     L.ref_set_quiet(1)
@@ -403,3 +405,15 @@ def write_ply(path, points, normals, colors, triangles, kind="f32"):
     col = None if colors is None else np.ascontiguousarray(colors, np.float32).reshape(-1, 3)
     tri = np.ascontiguousarray(triangles, np.uint32).reshape(-1, 3)
     return lib(kind).ref_write_ply(str(path).encode(), _ptr(pts), _ptr(nrm), _ptr(col), len(pts), _ptr(tri), len(tri))
+
+
+def downsample(points, colors, normals, grid_len):
+    """PointCloud::DownSample of the compiled reference (float32 build)"""
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    col = None if colors is None else np.ascontiguousarray(colors, np.float32).reshape(-1, 3)
+    nrm = None if normals is None else np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+    op = np.zeros_like(pts)
+    oc = None if col is None else np.zeros_like(pts)
+    on = None if nrm is None else np.zeros_like(pts)
+    n = lib("f32").ref_downsample(_ptr(pts), _ptr(col), _ptr(nrm), len(pts), grid_len, _ptr(op), _ptr(oc), _ptr(on))
+    return op[:n].copy(), None if oc is None else oc[:n].copy(), None if on is None else on[:n].copy()

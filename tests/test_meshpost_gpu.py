@@ -90,3 +90,29 @@ def test_cubes_file_round_trip_through_the_device(tmp_path):
     assert_bit_equal(ovx, expect, "volume after .cubes round trip")
     assert other.CountMesh() == gv.CountMesh()         # Marching Cubes only reads what the format stores
     assert not other.ReadFromFile(str(tmp_path / "missing.cubes"))
+
+
+@pytest.mark.parametrize("grid", [0.01, 0.05, 0.5])
+def test_point_cloud_downsample(grid):
+    """PointCloud::DownSample on the device: same points in the same order, colours and normals averaged alike; grid 0.5 puts
+    thousands of points into one cell (the long-segment sort)."""
+    from onepiece_b200 import registration as reg
+    from test_oracle_meshpost import _room_cloud
+    pts, col, nrm = _room_cloud()
+    cloud, gc = reg.PointCloud(pts, nrm).DownSample(grid, colors=col)
+    op, oc, on = oracleapi.downsample(pts, col, nrm, grid)
+    assert len(cloud.points) == len(op)
+    assert_bit_equal(cloud.points, op, "points")
+    assert_bit_equal(gc, oc, "colours")
+    assert_bit_equal(cloud.normals, on, "normals")
+    plain = reg.PointCloud(pts).DownSample(grid)
+    assert_bit_equal(plain.points, op, "points only") and plain.normals is None
+    assert len(reg.PointCloud(np.zeros((0, 3), np.float32)).DownSample(grid).points) == 0
+
+
+def test_clustering_with_cells_that_hold_thousands_of_vertices():
+    from onepiece_b200.mesh import TriangleMesh
+    _, pts, col, tri = _volume_and_mesh()
+    for grid in (0.3, 1.5):
+        m = TriangleMesh(pts, col, tri).ClusteringSimplify(grid)
+        _same(m, oracleapi.clustering_simplify(pts, col, tri, grid), f"grid {grid}")

@@ -105,3 +105,25 @@ def test_trajectory_round_trip(tmp_path):
     formats.write_trajectory(str(tmp_path / "trajectory.txt"), poses)
     back = formats.read_trajectory(str(tmp_path / "trajectory.txt"))
     assert len(back) == 4 and all(np.array_equal(a, b) for a, b in zip(poses, back))
+
+
+def _room_cloud():
+    from onepiece_b200 import scenes
+    c0 = scenes.Camera()
+    cam = scenes.Camera(c0.fx / 2, c0.fy / 2, c0.cx / 2, c0.cy / 2, 320, 240, 1000.0)
+    d, c, _, n = scenes.room(cam, 0, with_normals=True)
+    m = (d > 0).reshape(-1)
+    return scenes.backproject(d, cam), (c.reshape(-1, 3)[m] / 255.0).astype(np.float32), np.ascontiguousarray(n.reshape(-1, 3)[m])
+
+
+@pytest.mark.parametrize("grid", [0.01, 0.05, 0.5])
+def test_downsample_matches_the_compiled_reference(ref_available, grid):
+    if not ref_available:
+        pytest.skip("oracle/_ref not built")
+    pts, col, nrm = _room_cloud()
+    a, b = oracleapi.downsample(pts, col, nrm, grid), refapi.downsample(pts, col, nrm, grid)
+    assert len(a[0]) == len(b[0]) < len(pts)
+    for x, y, what in zip(a, b, ("points", "colours", "normals")):
+        assert_bit_equal(x, y, "down-sampled " + what)
+    a, b = oracleapi.downsample(pts, None, None, grid), refapi.downsample(pts, None, None, grid)
+    assert_bit_equal(a[0], b[0], "points only") and a[1] is None and a[2] is None
