@@ -634,16 +634,13 @@ __global__ void __launch_bounds__(1024) odo_compact_kernel(const unsigned char *
 // NormalizeIntensity: the reference's means are SEQUENTIAL float32 sums over the correspondence list
 // (DenseOdometryFunction.cpp:131-141); 0.5 / mean then scales the image, so the sum has to be reproduced bit for bit.
 //
-// One CTA per image.  All warps gather the next chunk of values (list order) into shared memory while warp 0 folds the
-// current chunk into the running sum S, 32 values per step.  A step is exact without 32 dependent additions whenever S
+// One CTA per image.  All warps gather the next chunk of 32 K values (list order) into registers while the current chunk,
+// staged in shared memory, is folded into the running sum S, 32 values per step.  A step is exact without 32 dependent additions whenever S
 // stays inside its binade [2^e, 2^(e+1)): there fl(S + x) = S + U * rne(x / U) with U = ulp(S) = 2^(e-23), because S is
 // a multiple of U -- so the 32 roundings are independent, their integer sum is a shuffle reduction, and S advances by
 // one exact integer add.  Steps that cross a binade, hit a rounding tie (whose direction depends on the parity of the
 // running sum) or see a negative / non-finite value take the literal path: 32 dependent float additions in list order.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kMeanThreads = 1024;
-constexpr int kMeanChunk = 4096;
-constexpr int kMeanSteps = kMeanChunk / 32; // 128 steps of 32 values per chunk, 4 per warp
 
 __device__ __forceinline__ float sequential_add32(float sum, float v, int count)
 {
@@ -685,120 +682,144 @@ __device__ __forceinline__ bool advance_in_binade(float &sum, int e, int ulps)
     return true;
 }
 
-__global__ void __launch_bounds__(kMeanThreads) odo_sequential_mean_kernel(const uint4 *__restrict__ pairs, OdoState *st,
-                                                                           const float *__restrict__ sgray, const float *__restrict__ tgray, int w)
+// the two intensity lists of NormalizeIntensity (source image at (v_s, u_s), target image at (v_t, u_t)), gathered by the whole
+// grid into contiguous arrays: the sequential kernel below runs on two SMs only and must not do 2 x 300 k scattered loads
+__global__ void __launch_bounds__(256) odo_gather_gray_kernel(const uint4 *__restrict__ pairs, const OdoState *st, const float *__restrict__ sgray,
+                                                              const float *__restrict__ tgray, int w, float *__restrict__ vals, int stride)
 {
-    __shared__ float buf[2][kMeanChunk];
-    __shared__ int s_tot[kMeanSteps];
-    __shared__ float s_sum;
-    const int which = blockIdx.x; // 0: source image at (v_s, u_s), 1: target image at (v_t, u_t)
-    const float *img = which ? tgray : sgray;
     const int n = st->n_pairs;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int PER = kMeanChunk / kMeanThreads;
-    float regs[PER];
-    auto gather = [&](int chunk) {
-#pragma unroll
-        for (int k = 0; k < PER; ++k)
-        {
-            const int i = chunk * kMeanChunk + k * kMeanThreads + threadIdx.x;
-            float v = 0.0f;
-            if (i < n)
-            {
-                const uint4 p = pairs[i];
-                v = which ? img[p.z * w + p.w] : img[p.x * w + p.y];
-            }
-            regs[k] = v;
-        }
-    };
-    auto stash = [&](int b) {
-#pragma unroll
-        for (int k = 0; k < PER; ++k) buf[b][k * kMeanThreads + threadIdx.x] = regs[k];
-    };
-    const int n_chunks = (n + kMeanChunk - 1) / kMeanChunk;
-    float sum = 0.0f; // meaningful in warp 0
-    if (threadIdx.x == 0) s_sum = 0.0f;
-    if (n_chunks > 0)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
-        gather(0);
-        stash(0);
+        const uint4 p = pairs[i];
+        vals[i] = sgray[p.x * w + p.y];
+        vals[stride + i] = tgray[p.z * w + p.w];
     }
-    __syncthreads();
-    for (int c = 0; c < n_chunks; ++c)
+}
+
+// Step totals for every binade the running sum can visit: totals[which][b][step] = integer number of ulps the 32 values of
+// `step` add to a sum in binade kBinLo + b, or -1 when a value needs the literal path there.  One warp per (list, step), the
+// whole grid: this is the part of the work that does not depend on the running sum.
+constexpr int kBinLo = 121, kBinN = 32; // biased exponents 121..152: sums from 2^-6 up to 2^26
+__global__ void __launch_bounds__(256) odo_mean_totals_kernel(const float *__restrict__ vals, int stride, const OdoState *st, int *__restrict__ totals,
+                                                              int max_steps)
+{
+    const int n = st->n_pairs, n_steps = (n + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int ws = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ws < 2 * n_steps; ws += warps)
     {
-        if (c + 1 < n_chunks) gather(c + 1); // loads in flight during this chunk
-        const float *cur = buf[c & 1];
-        const int m = min(kMeanChunk, n - c * kMeanChunk);
-        const int n_steps = (m + 31) / 32;
-        // every warp: the ulp totals of its four steps, speculating that the sum stays in the binade it has now
-        const int e_spec = binade_of(s_sum);
-#pragma unroll
-        for (int q = 0; q < kMeanSteps / (kMeanThreads / 32); ++q)
+        const int which = ws >= n_steps, step = ws - which * n_steps;
+        const int idx = step * 32 + lane;
+        const float x = idx < n ? vals[(size_t)which * stride + idx] : 0.0f;
+        int mine = -1;
+#pragma unroll 8
+        for (int b = 0; b < kBinN; ++b)
         {
-            const int step = warp * (kMeanSteps / (kMeanThreads / 32)) + q;
-            const int idx = step * 32 + lane;
-            const int t = ulps_of_step(idx < m ? cur[idx] : 0.0f, e_spec);
-            if (lane == 0) s_tot[step] = t;
+            const int t = ulps_of_step(x, kBinLo + b);
+            if (lane == b) mine = t;
         }
-        __syncthreads();
-        if (warp == 0)
+        totals[((size_t)which * kBinN + lane) * max_steps + step] = mine;
+    }
+}
+
+// The sequential part, one warp per list: the running sum S walks the steps; while it stays in a binade the totals of that
+// binade are folded 32 steps at a time (prefix scan, one exact integer add), a step that would leave the binade or that holds
+// a rounding tie is taken on its own -- its own binade, literal 32 additions when the shortcut fails -- and so are the steps
+// after it until 16 in a row took the shortcut (while the sum is small its ulp is close to the values' own and ties abound).
+__global__ void __launch_bounds__(32) odo_sequential_mean_kernel(const float *__restrict__ vals, int stride, const int *__restrict__ totals,
+                                                                 int max_steps, OdoState *st)
+{
+    const int which = blockIdx.x; // 0: source image at (v_s, u_s), 1: target image at (v_t, u_t)
+    const float *__restrict__ list = vals + (size_t)which * stride;
+    const int n = st->n_pairs, n_steps = (n + 31) / 32;
+    const int lane = threadIdx.x;
+    float sum = 0.0f;
+    int pos = 0;
+    while (pos < n_steps)
+    {
+        const int e_spec = binade_of(sum);
+        const int b = e_spec - kBinLo;
+        int f = pos;
+        if (e_spec >= 0 && b >= 0 && b < kBinN)
         {
-            // prefix over the 128 step totals: apply as many leading steps as stay valid in one exact integer add
-            int tot[4], local = 0;
-            bool bad_seen = false;
-            int good[4]; // running in-lane prefix, valid while no bad step was seen
+            const int *__restrict__ tot = totals + ((size_t)which * kBinN + b) * max_steps;
+            const int si0 = (int)(sum * __uint_as_float((unsigned int)(277 - e_spec) << 23));
+            int carry = 0, applied = 0;
+            bool failed = false;
+            f = n_steps;
+            // rows of 32 steps, sixteen rows of totals in flight at a time (a row costs one global-memory latency otherwise)
+            for (int r0 = pos >> 5; r0 * 32 < n_steps && !failed; r0 += 16)
+            {
+                int tq[16];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-            {
-                const int step = lane * 4 + q;
-                tot[q] = step < n_steps ? s_tot[step] : 0;
-                bad_seen = bad_seen || tot[q] < 0;
-                local += tot[q] < 0 ? 0 : tot[q];
-                good[q] = local;
-            }
-            int inc = local;
+                for (int q = 0; q < 16; ++q)
+                {
+                    const int step = (r0 + q) * 32 + lane;
+                    tq[q] = step >= pos && step < n_steps ? tot[step] : 0;
+                }
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1)
-            {
-                const int v = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += v;
-            }
-            const int before = inc - local; // ulps of all steps of earlier lanes
-            const int si0 = e_spec >= 0 ? (int)(sum * __uint_as_float((unsigned int)(277 - e_spec) << 23)) : 0;
-            // first step (in this lane) that cannot be applied in bulk
-            int first_fail = 4;
+                for (int q = 0; q < 16; ++q)
+                {
+                    if (failed || (r0 + q) * 32 >= n_steps) break;
+                    const int r = r0 + q;
+                    const int step = r * 32 + lane;
+                    const bool valid = step >= pos && step < n_steps;
+                    const int t = tq[q];
+                    const bool bad = valid && t < 0;
+                    const int own = bad ? 0 : t;
+                    int inc = own;
 #pragma unroll
-            for (int q = 3; q >= 0; --q)
-                if (tot[q] < 0 || e_spec < 0 || (long long)si0 + before + good[q] > (1 << 24)) first_fail = q;
-            const unsigned int fail_mask = __ballot_sync(0xffffffffu, first_fail < 4 && lane * 4 + first_fail < n_steps);
-            int f = n_steps; // first step to handle one by one
-            int applied = 0; // ulps of the steps before f
-            if (fail_mask)
-            {
-                const int fl = __ffs(fail_mask) - 1;
-                const int fq = __shfl_sync(0xffffffffu, first_fail, fl);
-                f = fl * 4 + fq;
-                const int g = fq > 0 ? good[fq - 1] : 0; // only meaningful on lane fl
-                applied = __shfl_sync(0xffffffffu, before + g, fl);
+                    for (int o = 1; o < 32; o <<= 1)
+                    {
+                        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc += v;
+                    }
+                    const bool over = valid && (long long)si0 + carry + inc > (1 << 24); // this step would leave the binade
+                    const unsigned int mask = __ballot_sync(0xffffffffu, bad || over);
+                    if (mask)
+                    {
+                        const int fl = __ffs(mask) - 1;
+                        f = r * 32 + fl;
+                        applied = carry + __shfl_sync(0xffffffffu, inc - own, fl); // ulps of the steps before f
+                        failed = true;
+                    }
+                    else
+                        carry += __shfl_sync(0xffffffffu, inc, 31);
+                }
             }
-            else
-                applied = __shfl_sync(0xffffffffu, inc, 31);
-            if (e_spec >= 0 && f > 0) advance_in_binade(sum, e_spec, applied);
-            // the rest of the chunk step by step: own binade per step, literal 32 additions when the shortcut fails
-            for (int step = f; step < n_steps; ++step)
+            if (!failed) applied = carry;
+            if (applied > 0) advance_in_binade(sum, e_spec, applied);
+        }
+        int calm = 0;
+        while (f < n_steps && calm < 16)
+        {
+            // the values of the next 16 steps in flight together
+            float xq[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
             {
-                const int idx = step * 32 + lane;
-                const float x = idx < m ? cur[idx] : 0.0f;
+                const int idx = (f + q) * 32 + lane;
+                xq[q] = idx < n ? list[idx] : 0.0f;
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+            {
+                if (f >= n_steps || calm >= 16) break;
+                const float x = xq[q];
                 const int e = binade_of(sum);
                 const int t = ulps_of_step(x, e);
-                if (!(e >= 0 && advance_in_binade(sum, e, t))) sum = sequential_add32(sum, x, min(32, m - step * 32));
+                if (e >= 0 && t >= 0 && advance_in_binade(sum, e, t)) ++calm;
+                else
+                {
+                    sum = sequential_add32(sum, x, min(32, n - f * 32));
+                    calm = 0;
+                }
+                ++f;
             }
-            if (lane == 0) s_sum = sum;
         }
-        if (c + 1 < n_chunks) stash((c + 1) & 1);
-        __syncthreads();
+        pos = f;
     }
-    if (threadIdx.x == 0)
+    if (lane == 0)
     {
         const float mean = fdiv(sum, (float)n); // mean /= (float)correspondence.size()
         if (which) st->mean_tgt = mean; else st->mean_src = mean;
@@ -905,6 +926,8 @@ struct opb_odometry
     OdoState *h_state = nullptr; // pinned
     int max_blocks = 0;
     std::shared_ptr<FramePool> frame_pool;
+    float *d_vals = nullptr;        // NormalizeIntensity: the two gathered intensity lists
+    int *d_mean_totals = nullptr;   // ... and their step totals per binade
     unsigned int *d_sync = nullptr; // barrier words of the persistent loop kernel
     int coop_ctas_per_sm = 0;       // resident CTAs per SM of odo_loop_kernel; 0: cooperative launch unavailable
     bool profiling = false;
@@ -972,7 +995,7 @@ void opb_odometry_destroy(opb_odometry *o)
     cudaSetDevice(o->device);
     if (o->stream) cudaStreamSynchronize(o->stream);
     cudaFree(o->d_cand); cudaFree(o->d_accepted); cudaFree(o->d_partials); cudaFree(o->d_tiles); cudaFree(o->d_pairs);
-    cudaFree(o->d_corr_xyz); cudaFree(o->d_identity); cudaFree(o->d_tmp); cudaFree(o->d_state); cudaFree(o->d_sync);
+    cudaFree(o->d_corr_xyz); cudaFree(o->d_identity); cudaFree(o->d_tmp); cudaFree(o->d_state); cudaFree(o->d_sync); cudaFree(o->d_vals); cudaFree(o->d_mean_totals);
     if (o->h_state) cudaFreeHost(o->h_state);
     for (int i = 0; i < 2; ++i) if (o->ev[i]) cudaEventDestroy(o->ev[i]);
     if (o->own_stream && o->stream) cudaStreamDestroy(o->stream);
@@ -1022,6 +1045,8 @@ int opb_odometry_create(const opb_odometry_desc *desc, opb_odometry **out)
     if (e == cudaSuccess) e = cudaMemcpy(o->d_identity, I, sizeof(I), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(o->d_state, 0, sizeof(OdoState));
     if (e == cudaSuccess) e = cudaMalloc(&o->d_sync, 4 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&o->d_vals, 2 * n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&o->d_mean_totals, 2 * (size_t)kBinN * ((n + 31) / 32) * sizeof(int));
     if (e == cudaSuccess)
     {
         int coop = 0, occ[3] = {0, 0, 0};
@@ -1225,8 +1250,13 @@ static void launch_normalize(opb_odometry *o, opb_frame *S, opb_frame *T)
     launch_iteration(o, a, true);
     launch_compaction(o, 0);
     cudaStream_t s = o->stream;
-    odo_sequential_mean_kernel<<<2, kMeanThreads, 0, s>>>(o->d_pairs, o->d_state, S->im.img[0][0], T->im.img[0][0], o->cams[0].w);
-    const int n = (int)level_pixels(o, 0);
+    const int n0 = (int)level_pixels(o, 0);
+    odo_gather_gray_kernel<<<grid_for(o, n0), kOdoThreads, 0, s>>>(o->d_pairs, o->d_state, S->im.img[0][0], T->im.img[0][0], o->cams[0].w,
+                                                                  o->d_vals, n0);
+    const int max_steps = (n0 + 31) / 32;
+    odo_mean_totals_kernel<<<grid_for(o, (size_t)n0 * 2), kOdoThreads, 0, s>>>(o->d_vals, n0, o->d_state, o->d_mean_totals, max_steps);
+    odo_sequential_mean_kernel<<<2, 32, 0, s>>>(o->d_vals, n0, o->d_mean_totals, max_steps, o->d_state);
+    const int n = n0;
     odo_scale_kernel<<<grid_for(o, n), kOdoThreads, 0, s>>>(S->im.img[0][0], T->im.img[0][0], n, o->d_state);
 }
 
