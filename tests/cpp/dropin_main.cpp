@@ -61,6 +61,10 @@ int main(int argc, char **argv)
     for (size_t i = 0; i < mesh.points.size(); ++i)
         for (int k = 0; k < 3; ++k) mesh_out.push_back(mesh.points[i](k));
     WriteAll(dir + "/mesh_points.bin", mesh_out);
+    std::vector<float> mesh_colors;
+    for (size_t i = 0; i < mesh.colors.size(); ++i)
+        for (int k = 0; k < 3; ++k) mesh_colors.push_back(mesh.colors[i](k));
+    WriteAll(dir + "/mesh_colors.bin", mesh_colors);
     integration::CubeMap m = cube_handler.GetCubeMap();
     std::vector<float> vox;
     std::vector<int> ids;
@@ -102,6 +106,22 @@ int main(int argc, char **argv)
             for (int j = 0; j < 512; ++j) wsum += it->second.voxels[j].weight;
         out.push_back(wsum);
         WriteAll(dir + "/resample.bin", out);
+    }
+    // example/DenseFusion/DenseFusion.cpp:99-105 and example/MergeMultipleSubmaps.cpp:45-46: simplify the extracted mesh, normals,
+    // then a down-sampled point cloud of its vertices (example/ReadPLYPointCloud.cpp:24)
+    {
+        auto c_mesh = mesh.ClusteringSimplify(0.02);
+        if (!c_mesh->HasNormals()) c_mesh->ComputeNormals();
+        auto pcd = c_mesh->GetPointCloud()->DownSample(0.05);
+        std::vector<float> post;
+        post.push_back((float)c_mesh->points.size());
+        post.push_back((float)c_mesh->triangles.size());
+        post.push_back((float)pcd->points.size());
+        for (size_t i = 0; i < c_mesh->points.size(); ++i)
+            for (int k = 0; k < 3; ++k) { post.push_back(c_mesh->points[i](k)); post.push_back(c_mesh->normals[i](k)); }
+        for (size_t i = 0; i < pcd->points.size(); ++i)
+            for (int k = 0; k < 3; ++k) { post.push_back(pcd->points[i](k)); post.push_back(pcd->normals[i](k)); post.push_back(pcd->colors[i](k)); }
+        WriteAll(dir + "/meshpost.bin", post);
     }
 
     // --- example/ICPTest.cpp:14-34 ---------------------------------------------------------------------------

@@ -90,6 +90,22 @@ def test_reference_caller_code_runs_on_the_gpu(tmp_path):
     assert int(rs[0]) == on.num_cubes() and int(rs[1]) == len(on.extract_mesh()[0])
     assert int(rs[2]) == ot.num_cubes() and int(rs[3]) == om.num_cubes()
     assert rs[4] == float(om.download()[1][:, :, 1].astype(np.float64).sum())
+    # ClusteringSimplify -> ComputeNormals -> DownSample through the drop-in definitions (onepiece_b200/cpp/Geometry/MeshPost.cpp)
+    post = np.fromfile(tmp_path / "meshpost.bin", np.float32)
+    # (vertex clustering depends on the triangle order, so the oracle is fed the mesh in the order the drop-in extracted it)
+    op = mesh
+    oc = np.fromfile(tmp_path / "mesh_colors.bin", np.float32).reshape(-1, 3)
+    cp, cc, ct = oracleapi.clustering_simplify(op, oc, np.arange(len(op), dtype=np.uint32).reshape(-1, 3), 0.02)
+    cn = oracleapi.compute_normals(cp, ct)
+    dp, dc, dn = oracleapi.downsample(cp, cc, cn, 0.05)
+    assert (int(post[0]), int(post[1]), int(post[2])) == (len(cp), len(ct), len(dp))
+    body = post[3:3 + 6 * len(cp)].reshape(-1, 3, 2)
+    assert_bit_equal(body[:, :, 0], cp, "clustered points through the drop-in")
+    assert_bit_equal(body[:, :, 1], cn, "normals through the drop-in")
+    rest = post[3 + 6 * len(cp):].reshape(-1, 3, 3)
+    assert_bit_equal(rest[:, :, 0], dp, "down-sampled points through the drop-in")
+    assert_bit_equal(rest[:, :, 1], dn, "down-sampled normals")
+    assert_bit_equal(rest[:, :, 2], dc, "down-sampled colours")
     # tool::ConvertDepthTo32F + tool::BilateralFilter through the drop-in, then IntegrateImage of the filtered depth
     oc = oracleapi.convert_depth_32f(d1, cam.depth_scale)
     of = oracleapi.bilateral_filter(oc)
