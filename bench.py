@@ -36,6 +36,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-odometry", action="store_true", help="skip the secondary DenseTracking measurement (config 3)")
+    ap.add_argument("--no-partitioned", action="store_true", help="N > 1: skip the secondary one-stream-over-all-ranks measurement")
     return ap.parse_args()
 
 
@@ -244,6 +245,66 @@ def bench_dense_odometry(frames, cam, device, steps, with_cpu):
 
 
 # ----------------------------------------------------------------------------------------------------------
+# secondary measurement at N > 1 (BASELINE.json config 5 in miniature): ONE stream fused by all ranks together --
+# per frame a point-to-plane ICP whose source points are split across the ranks (6x6 packet exchanged over peer memory inside
+# the solver kernel), then the frame integrated into the volume partitioned by cube ownership; at the end the boundary-cube
+# exchange over NCCL and Marching Cubes per rank.  Host buffers, wall clock between barriers (strong scaling: it shows what
+# the collectives cost at 640x480, not a speed-up -- the solvers are latency-bound at this size).
+# ----------------------------------------------------------------------------------------------------------
+def bench_partitioned(cam, local, rank, world, steps):
+    import torch
+    import torch.distributed as dist
+
+    from onepiece_b200 import fusion, registration as reg
+    frames = make_stream(cam, 0)   # every rank looks at the SAME stream here
+    sp = fusion.SplitICP(local)
+    sh = fusion.ShardedCubeHandler(cam, VOXEL, max_cubes=1 << 17, axis=0, slab=8, device_index=local)
+    par = reg.ICPParameter(ICP_ITERS, ICP_THRESHOLD, 1.0)
+    def pinned(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+
+    clouds = []
+    for f in frames:
+        pc = reg.PointCloud(f["cloud"], f["normals"])
+        pc.points, pc.normals = pinned(pc.points), pinned(pc.normals)
+        f["depth"], f["bgr"] = pinned(f["depth"]), pinned(f["bgr"])
+        clouds.append(pc)
+
+    def step(s):
+        k = s % (N_TRAJ - 1)
+        r = sp.PointToPlane(clouds[k + 1], clouds[k], np.eye(4), par, gather_pairs=False)
+        pose = (frames[k]["pose"] @ r.T.astype(np.float64)).astype(np.float32)
+        sh.IntegrateImage(frames[k + 1]["depth"], frames[k + 1]["bgr"], pose)
+
+    for s in range(3):
+        step(s)
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for s in range(steps):
+        step(3 + s)
+    torch.cuda.synchronize(); dist.barrier()
+    dt = time.perf_counter() - t0
+    fusion.exchange_halo(sh.volume, rank, world, sh.device)   # first exchange: NCCL sets up its peer-to-peer channels
+    sh.volume.HaloClear()
+    torch.cuda.synchronize(); dist.barrier()
+    t1 = time.perf_counter()
+    n_ghost = fusion.exchange_halo(sh.volume, rank, world, sh.device)
+    torch.cuda.synchronize(); dist.barrier()
+    t2 = time.perf_counter()
+    nv, nt = sh.volume.CountMesh()
+    torch.cuda.synchronize(); dist.barrier()
+    t3 = time.perf_counter()
+    tot = torch.tensor([sh.volume.NumCubes(), n_ghost, nv], device="cuda", dtype=torch.int64)
+    dist.all_reduce(tot)
+    sp.close()
+    return {"what": "one 640x480 stream fused by all ranks: split point-to-plane ICP (peer-memory packet exchange) + partitioned "
+                    "integration per frame, host buffers; then halo exchange (NCCL) + Marching Cubes count",
+            "frames_per_s": steps / dt, "ms_per_frame": 1e3 * dt / steps, "steps": steps, "cubes_total": int(tot[0]),
+            "boundary_cubes_exchanged": int(tot[1]), "halo_exchange_ms": 1e3 * (t2 - t1), "marching_cubes_count_ms": 1e3 * (t3 - t2),
+            "mesh_vertices_total": int(tot[2])}
+
+
+# ----------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -360,6 +421,10 @@ def run_ours(args):
     # calls themselves are synchronous
     e2e_ms, _ = timed(K, W, host=True)
 
+    partitioned = None
+    if world > 1 and not args.no_partitioned:
+        vol.close()  # make room: the partitioned volume is a second pool on the same GPU
+        partitioned = bench_partitioned(cam, local, rank, world, min(K, 50))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -403,6 +468,8 @@ def run_ours(args):
                          "with pinned host buffers"},
         "gpu_launches": launches_per_step * K, "clocks": clocks,
     }
+    if partitioned is not None:
+        out["partitioned_fusion"] = partitioned
     if not args.no_cpu_baseline and world == 1:
         cb, _, _ = cpu_reference_fps(30, 1, budget_s=20.0)
         out["cpu_baseline"] = cb

@@ -208,8 +208,8 @@ class SplitICP:
         from . import registration as reg
         lo, hi = shard_range(len(source.points), self.rank, self.world)
         part = reg.PointCloud(source.points[lo:hi])
-        r = reg._run(part, target, init_T, icp_para, plane, self.device_index, self.ws)
-        idx = r.correspondence_set_index
+        r = reg._run(part, target, init_T, icp_para, plane, self.device_index, self.ws, want_pairs=gather_pairs)
+        idx = r.correspondence_set_index  # empty when gather_pairs is False: the inliers then stay on the device
         idx[:, 0] += lo
         if gather_pairs and self.world > 1:
             parts = [None] * self.world

@@ -76,26 +76,28 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-def _run(source: PointCloud, target: PointCloud, init_T, icp_para: ICPParameter, plane: bool, device=0, workspace=None):
+def _run(source: PointCloud, target: PointCloud, init_T, icp_para: ICPParameter, plane: bool, device=0, workspace=None,
+         want_pairs: bool = True):
     ws = workspace if workspace is not None else _Workspace.get(device)
     par = capi.IcpParams(icp_para.max_iteration, icp_para.threshold, icp_para.scaling)
     res = capi.IcpResult()
     T0 = np.ascontiguousarray(np.asarray(init_T, np.float32).reshape(4, 4).T).reshape(16)
     ns, nt = len(source.points), len(target.points)
-    pairs = np.zeros((max(ns, 1), 2), np.int32)
+    pairs = np.zeros((max(ns, 1), 2), np.int32) if want_pairs else None
+    cap = ns if want_pairs else 0
     if plane:
         rc = capi.lib.opb_icp_point_to_plane(ws, _ptr(source.points), ns, _ptr(target.points),
                                              _ptr(target.normals) if target.HasNormals() else None, nt, _ptr(T0),
-                                             C.byref(par), C.byref(res), _ptr(pairs), ns)
+                                             C.byref(par), C.byref(res), _ptr(pairs), cap)
     else:
         rc = capi.lib.opb_icp_point_to_point(ws, _ptr(source.points), ns, _ptr(target.points), nt, _ptr(T0), C.byref(par),
-                                             C.byref(res), _ptr(pairs), ns)
+                                             C.byref(res), _ptr(pairs), cap)
     if rc == capi.OPB_ERR_INVALID and res.status == capi.OPB_ERR_INVALID:
         # the reference prints the error and returns a default-constructed result (ICP.cpp:159-163)
         print(capi.lib.opb_last_error().decode())
         return RegistrationResult(ok=False)
     capi.check(rc)
-    idx = pairs[: res.n_local_pairs].copy()
+    idx = pairs[: res.n_local_pairs].copy() if want_pairs else np.zeros((0, 2), np.int32)
     out = RegistrationResult()
     out.T = np.array(res.T[:], np.float32).reshape(4, 4).T.copy()
     out.T_iterated = np.array(res.T_iterated[:], np.float32).reshape(4, 4).T.copy()
