@@ -424,7 +424,10 @@ def run_ours(args):
     partitioned = None
     if world > 1 and not args.no_partitioned:
         vol.close()  # make room: the partitioned volume is a second pool on the same GPU
-        partitioned = bench_partitioned(cam, local, rank, world, min(K, 50))
+        try:
+            partitioned = bench_partitioned(cam, local, rank, world, min(K, 50))
+        except Exception as exc:  # noqa: BLE001  -- a secondary measurement must never cost the headline line
+            partitioned = {"error": f"{type(exc).__name__}: {exc}"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
