@@ -24,6 +24,7 @@ struct opb_volume
     bool own_stream = false;
     int sm_count = 0;
     int integrate_grid = 0;
+    int integrate_pipe_grid = 0; // grid of integrate_pipelined_kernel
     // double-buffered device staging for host frames
     void *stage_depth[2] = {nullptr, nullptr};
     unsigned char *stage_bgr[2] = {nullptr, nullptr};
