@@ -331,5 +331,34 @@ bool CubeHandler::ReadFromFile(const std::string &filename)
     std::cout << GREEN << "[CubeHandler]::[INFO]::Load TSDF field done!(From BinaryFile) " << RESET << std::endl;
     return true;
 }
+// CubeHandler.h:73-111: [size word][cube count] then per cube 3 id floats and VoxelCube::ReadFromBufferFloat (VoxelCube.h:168-194)
+bool CubeHandler::ReadFromFileFloat(const std::string &filename)
+{
+    std::ifstream ifs(filename, std::ifstream::binary);
+    if (!ifs) return false;
+    std::vector<float> buffer;
+    ifs.seekg(0, ifs.end);
+    size_t length = ifs.tellg();
+    ifs.seekg(0, ifs.beg);
+    buffer.resize(length / sizeof(float));
+    ifs.read((char *)&buffer[0], length);
+    if (buffer.size() < 2) return false;
+    unsigned int cube_size = buffer[1];
+    size_t ptr = 2;
+    CubeMap m;
+    for (size_t i = 0; i < cube_size; ++i)
+    {
+        float x = buffer[ptr++], y = buffer[ptr++], z = buffer[ptr++];
+        CubeID cube_id = CubeID(x, y, z);
+        m[cube_id] = VoxelCube(cube_id);
+        m[cube_id].ReadFromBufferFloat(buffer, ptr);
+    }
+    bool quiet = std::cout.fail();
+    std::cout.setstate(std::ios_base::failbit);
+    SetCubeMap(m);
+    if (!quiet) std::cout.clear();
+    std::cout << GREEN << "[CubeHandler]::[INFO]::Load TSDF field done!(From BinaryFile) " << RESET << std::endl;
+    return true;
+}
 } // namespace integration
 } // namespace one_piece

@@ -64,6 +64,7 @@ class CubeHandler
     void SetCubeMap(const CubeMap &_cube_map);
     bool WriteToFile(const std::string &filename) const;
     bool ReadFromFile(const std::string &filename);
+    bool ReadFromFileFloat(const std::string &filename); // the older stream with a size word and separate colour records (:73-111)
 
     // CubeHandler.h:145-177,242-338: volume resampling / merging, on the device
     void Merge(const CubeHandler &another);
