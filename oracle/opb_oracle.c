@@ -1644,3 +1644,158 @@ long orc_downsample(const float *points, const float *colors, const float *norma
     free(cells);
     return ptr;
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * PointCloud::EstimateNormals (src/Geometry/PointCloud.cpp:102-144): the step in front of registration::PointToPlane when
+ * the clouds come without normals (example/ICPTest.cpp:27-33).  For every point: the knn nearest points (nanoflann
+ * knnSearch: ascending squared distance, the point itself first), cut where the SQUARED distance exceeds `radius`
+ * (KDTree.h:248-254 compares dist^2 with radius), then geometry::FitPlane (Geometry.cpp:172-199): float mean, float
+ * covariance W, Eigen::JacobiSVD<MatrixX>(W), normal = third column of U, normalised.
+ * Eigen 3.3.7 (vendored in the reference, 3rdparty/Eigen) is restated for the 3x3 float case: SVD/JacobiSVD.h:660-780,
+ * misc/RealSvd2x2.h:19-50, Jacobi/Jacobi.h:83-113 (makeJacobi), :300-420 (apply_rotation_in_the_plane: x' = c x + s y,
+ * y' = -s x + c y, no FMA in the reference's SSE build).  Neighbours at exactly equal distance are ordered by index here;
+ * nanoflann orders them by tree traversal, so clouds with exact ties can differ in the last bits of W.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct { float c, s; } jrot_t;
+/* JacobiRotation::makeJacobi(x, y, z) */
+static jrot_t make_jacobi(float x, float y, float z)
+{
+    jrot_t r;
+    const float deno = 2.0f * fabsf(y);
+    if (deno < FLT_MIN) { r.c = 1.0f; r.s = 0.0f; return r; }
+    const float tau = (x - z) / deno;
+    const float w = sqrtf(tau * tau + 1.0f);
+    const float t = tau > 0.0f ? 1.0f / (tau + w) : 1.0f / (tau - w);
+    const float sign_t = t > 0.0f ? 1.0f : -1.0f;
+    const float n = 1.0f / sqrtf(t * t + 1.0f);
+    r.s = -sign_t * (y / fabsf(y)) * fabsf(t) * n;
+    r.c = n;
+    return r;
+}
+/* apply_rotation_in_the_plane on two strided 3-vectors (or 2-vectors) */
+static void rot_apply(float *x, int incx, float *y, int incy, int n, jrot_t j)
+{
+    if (j.c == 1.0f && j.s == 0.0f) return;
+    for (int i = 0; i < n; ++i)
+    {
+        const float xi = x[i * incx], yi = y[i * incy];
+        x[i * incx] = j.c * xi + j.s * yi;
+        y[i * incy] = -j.s * xi + j.c * yi;
+    }
+}
+/* JacobiSVD<MatrixXf>(W 3x3, ComputeThinU | ComputeThinV): U (row-major 3x3) and the singular values, sorted descending */
+static void jacobi_svd3(const float *Win, float *U, float *sv)
+{
+    float W[9]; /* row-major work matrix */
+    float scale = 0.0f;
+    for (int i = 0; i < 9; ++i) if (fabsf(Win[i]) > scale) scale = fabsf(Win[i]);
+    if (scale == 0.0f) scale = 1.0f;
+    for (int i = 0; i < 9; ++i) W[i] = Win[i] / scale;
+    for (int i = 0; i < 9; ++i) U[i] = (i % 4 == 0) ? 1.0f : 0.0f;
+    const float precision = 2.0f * FLT_EPSILON, consider_zero = FLT_MIN;
+    float max_diag = fmaxf(fabsf(W[0]), fmaxf(fabsf(W[4]), fabsf(W[8])));
+    int finished = 0;
+    while (!finished)
+    {
+        finished = 1;
+        for (int p = 1; p < 3; ++p)
+            for (int q = 0; q < p; ++q)
+            {
+                const float threshold = fmaxf(consider_zero, precision * max_diag);
+                if (fabsf(W[p * 3 + q]) > threshold || fabsf(W[q * 3 + p]) > threshold)
+                {
+                    finished = 0;
+                    /* real_2x2_jacobi_svd */
+                    float m[4] = {W[p * 3 + p], W[p * 3 + q], W[q * 3 + p], W[q * 3 + q]};
+                    jrot_t rot1;
+                    const float t = m[0] + m[3], d = m[2] - m[1];
+                    if (fabsf(d) < FLT_MIN) { rot1.s = 0.0f; rot1.c = 1.0f; }
+                    else
+                    {
+                        const float u = t / d;
+                        const float tmp = sqrtf(1.0f + u * u);
+                        rot1.s = 1.0f / tmp;
+                        rot1.c = u / tmp;
+                    }
+                    rot_apply(&m[0], 1, &m[2], 1, 2, rot1);                 /* m.applyOnTheLeft(0, 1, rot1): rows 0 and 1 */
+                    const jrot_t j_right = make_jacobi(m[0], m[1], m[3]);
+                    const jrot_t jrt = {j_right.c, -j_right.s};             /* transpose() */
+                    const jrot_t j_left = {rot1.c * jrt.c - rot1.s * jrt.s, rot1.c * jrt.s + rot1.s * jrt.c}; /* rot1 * j_right^T */
+                    const jrot_t jlt = {j_left.c, -j_left.s};
+                    rot_apply(&W[p * 3], 1, &W[q * 3], 1, 3, j_left);       /* workMatrix.applyOnTheLeft(p, q, j_left): rows */
+                    rot_apply(&U[p], 3, &U[q], 3, 3, (jrot_t){jlt.c, -jlt.s}); /* U.applyOnTheRight(p, q, j_left^T): columns, with (j^T)^T */
+                    rot_apply(&W[p], 3, &W[q], 3, 3, jrt);                  /* workMatrix.applyOnTheRight(p, q, j_right): columns, with j^T */
+                    max_diag = fmaxf(max_diag, fmaxf(fabsf(W[p * 3 + p]), fabsf(W[q * 3 + q])));
+                }
+            }
+    }
+    for (int i = 0; i < 3; ++i)
+    {
+        const float a = W[i * 3 + i];
+        sv[i] = fabsf(a);
+        if (a < 0.0f)
+            for (int r = 0; r < 3; ++r) U[r * 3 + i] = -U[r * 3 + i];
+    }
+    for (int i = 0; i < 3; ++i) sv[i] *= scale;
+    for (int i = 0; i < 3; ++i)
+    {
+        int pos = i;
+        for (int k = i + 1; k < 3; ++k) if (sv[k] > sv[pos]) pos = k;
+        if (sv[pos] == 0.0f) break;
+        if (pos != i)
+        {
+            const float tmp = sv[i]; sv[i] = sv[pos]; sv[pos] = tmp;
+            for (int r = 0; r < 3; ++r) { const float u = U[r * 3 + i]; U[r * 3 + i] = U[r * 3 + pos]; U[r * 3 + pos] = u; }
+        }
+    }
+}
+/* geometry::FitPlane (Geometry.cpp:172-199) on the listed points -> normal; zero for fewer than 3 points */
+static void fit_plane_normal(const float *pts, const int *idx, int n, float *normal)
+{
+    normal[0] = normal[1] = normal[2] = 0.0f;
+    if (n < 3) return;
+    float sum[3] = {0, 0, 0};
+    for (int i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) sum[a] += pts[3 * (long)idx[i] + a];
+    const float mean[3] = {sum[0] / (float)n, sum[1] / (float)n, sum[2] / (float)n};
+    float W[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n; ++i)
+    {
+        const float d[3] = {pts[3 * (long)idx[i]] - mean[0], pts[3 * (long)idx[i] + 1] - mean[1], pts[3 * (long)idx[i] + 2] - mean[2]};
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) W[r * 3 + c] += d[r] * d[c];
+    }
+    for (int i = 0; i < 9; ++i) W[i] = W[i] / (float)n;
+    float U[9], sv[3];
+    jacobi_svd3(W, U, sv);
+    normal[0] = U[2]; normal[1] = U[5]; normal[2] = U[8];
+    normalize3(normal);
+}
+void orc_estimate_normals(const float *pts, long n, float radius, int knn, float *normals)
+{
+#pragma omp parallel
+    {
+        float *bd = (float *)malloc(sizeof(float) * (knn + 1));
+        int *bi = (int *)malloc(sizeof(int) * (knn + 1));
+#pragma omp for schedule(dynamic, 64)
+        for (long i = 0; i < n; ++i)
+        {
+            int cnt = 0;
+            const float *q = pts + 3 * i;
+            for (long j = 0; j < n; ++j)
+            {
+                const float dx = q[0] - pts[3 * j], dy = q[1] - pts[3 * j + 1], dz = q[2] - pts[3 * j + 2];
+                const float d = (dx * dx + dy * dy) + dz * dz; /* L2_Simple_Adaptor: result += diff * diff, in order */
+                if (cnt == knn && !(d < bd[cnt - 1])) continue;
+                int k = cnt < knn ? cnt : knn - 1;
+                while (k > 0 && bd[k - 1] > d) { bd[k] = bd[k - 1]; bi[k] = bi[k - 1]; --k; }
+                bd[k] = d; bi[k] = (int)j;
+                if (cnt < knn) ++cnt;
+            }
+            int in_radius = 0;
+            while (in_radius < cnt && !(bd[in_radius] > radius)) ++in_radius;
+            fit_plane_normal(pts, bi, in_radius, normals + 3 * i);
+        }
+        free(bd); free(bi);
+    }
+}

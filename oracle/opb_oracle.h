@@ -123,6 +123,9 @@ void orc_compute_normals(const float *points, long n_points, const uint32_t *tri
 long orc_downsample(const float *points, const float *colors, const float *normals, long n, float grid_len, float *out_points,
                     float *out_colors, float *out_normals);
 
+/* PointCloud::EstimateNormals (PointCloud.cpp:102-144): knn nearest points within sqrt(radius), FitPlane, Eigen JacobiSVD */
+void orc_estimate_normals(const float *pts, long n, float radius, int knn, float *normals);
+
 /* caller-side depth pre-filter: tool::ConvertDepthTo32F (ImageProcessing.cpp:68-91), tool::BilateralFilter (:64-67) */
 void orc_convert_depth_32f(const void *depth, int is_u16, long n, float depth_scale, float *out);
 void orc_bilateral_filter(const float *src, int w, int h, int d, double sigma_color, double sigma_space, float *dst);

@@ -76,6 +76,7 @@ def lib():
     L.orc_clustering_simplify.restype = c_i
     L.orc_clustering_simplify.argtypes = [c_p, c_p, c_p, c_p, c_p, c_f]
     L.orc_compute_normals.argtypes = [c_p, c_l, c_p, c_l, c_p]
+    L.orc_estimate_normals.argtypes = [c_p, c_l, c_f, c_i, c_p]
     L.orc_downsample.restype = c_l
     L.orc_downsample.argtypes = [c_p, c_p, c_p, c_l, c_f, c_p, c_p, c_p]
     L.orc_volume_transform.restype = c_p
@@ -405,3 +406,11 @@ def downsample(points, colors, normals, grid_len):
     on = None if nrm is None else np.zeros_like(pts)
     n = lib().orc_downsample(_ptr(pts), _ptr(col), _ptr(nrm), len(pts), grid_len, _ptr(op), _ptr(oc), _ptr(on))
     return op[:n].copy(), None if oc is None else oc[:n].copy(), None if on is None else on[:n].copy()
+
+
+def estimate_normals(points, radius=0.1, knn=30):
+    """PointCloud::EstimateNormals(radius, knn)"""
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    out = np.zeros_like(pts)
+    lib().orc_estimate_normals(_ptr(pts), len(pts), radius, knn, _ptr(out))
+    return out
