@@ -279,6 +279,14 @@ int opb_icp_point_to_plane(opb_icp *c, const float *src_xyz, size_t ns, const fl
 int opb_icp_point_to_point(opb_icp *c, const float *src_xyz, size_t ns, const float *tgt_xyz, size_t nt,
                            const float init_T_colmajor[16], const opb_icp_params *params, opb_icp_result *result,
                            int32_t *pairs, size_t pairs_cap);
+/* PointCloud::EstimateNormals(radius = 0.1, knn = 30) (src/Geometry/PointCloud.cpp:102-144), the step in front of PointToPlane
+ * when the clouds come without normals (example/ICPTest.cpp:27-33): per point the knn nearest points (the point itself
+ * included) whose SQUARED distance does not exceed `radius` (the reference's KnnRadiusSearch compares dist^2 with radius,
+ * KDTree.h:248-254), geometry::FitPlane on them (Geometry.cpp:172-199: float mean and covariance, Eigen JacobiSVD, third
+ * column of U, normalised); fewer than 3 points -> the zero vector.  Bit-identical to the reference when no two neighbours of
+ * a point are at exactly the same distance; exact ties are ordered by index here and by k-d tree traversal there.
+ * xyz / normals: 3 floats per point, host or device pointers; knn <= 64. */
+int opb_icp_estimate_normals(opb_icp *c, const float *xyz, size_t n, float radius, int knn, float *normals);
 /* One registration over several GPUs (no counterpart in the reference).  The source points are split
  * across the ranks, every rank holds the whole target; each iteration every rank reduces its share to the 30-scalar packet
  * (21 J^T J + 6 J^T r + 2 error + count) and the packets are summed across ranks inside the reduction kernel's last CTA through

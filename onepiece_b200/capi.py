@@ -140,6 +140,7 @@ SIGNATURES = {
     "opb_icp_comm_attach": (C.c_int, [_p, C.c_int, C.c_int, _p]),
     "opb_icp_comm_detach": (C.c_int, [_p]),
     "opb_icp_last_search_count": (C.c_int, [_p, C.POINTER(C.c_uint64)]),
+    "opb_icp_estimate_normals": (C.c_int, [_p, _p, _sz, C.c_float, C.c_int, _p]),
     "opb_icp_last_launch_count": (C.c_int, [_p, C.POINTER(C.c_int)]),
     "opb_icp_last_search_trace": (C.c_int, [_p, _p, C.c_int]),
     "opb_icp_last_nn": (C.c_int, [_p, _p, _sz]),

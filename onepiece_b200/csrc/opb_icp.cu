@@ -1066,6 +1066,244 @@ __global__ void icp_scale_kernel(float *p, size_t n, float s)
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = fmul(p[i], s);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// PointCloud::EstimateNormals (src/Geometry/PointCloud.cpp:102-144) on the grid of the ICP search: the step in front of
+// registration::PointToPlane when the clouds come without normals (example/ICPTest.cpp:27-33).
+//   KDTree::KnnRadiusSearch  src/Geometry/KDTree.h:230-255   knn nearest (ascending squared distance, the point itself first),
+//                                                           cut where the SQUARED distance exceeds `radius`
+//   geometry::FitPlane       src/Geometry/Geometry.cpp:172-199   float mean, float covariance, JacobiSVD, third column of U
+//   Eigen 3.3.7 JacobiSVD<MatrixXf> for a 3x3 matrix: SVD/JacobiSVD.h:660-780, misc/RealSvd2x2.h:19-50, Jacobi/Jacobi.h:83-113
+// One thread per point: exact k-nearest walk over grid rows (bound = the current k-th distance), the list kept sorted by
+// (distance, index) in local memory; then the plane fit in the reference's float operation order.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kKnnMax = 64;
+struct KnnList
+{
+    float d[kKnnMax];
+    int i[kKnnMax];
+    int n, k;
+};
+__device__ __forceinline__ void knn_push(KnnList &L, float d, int idx)
+{
+    if (L.n == L.k)
+    {
+        const float wd = L.d[L.n - 1];
+        if (!(d < wd || (d == wd && idx < L.i[L.n - 1]))) return;
+    }
+    int pos = L.n < L.k ? L.n : L.k - 1;
+    while (pos > 0 && (L.d[pos - 1] > d || (L.d[pos - 1] == d && L.i[pos - 1] > idx)))
+    {
+        L.d[pos] = L.d[pos - 1];
+        L.i[pos] = L.i[pos - 1];
+        --pos;
+    }
+    L.d[pos] = d;
+    L.i[pos] = idx;
+    if (L.n < L.k) ++L.n;
+}
+__device__ __forceinline__ void knn_scan_cells(const IcpGrid &g, const unsigned int *__restrict__ cell_start, const float4 *__restrict__ sorted,
+                                               int xa, int xb, int cy, int cz, float qx, float qy, float qz, float cap2, KnnList &L)
+{
+    xa = max(xa, 0);
+    xb = min(xb, g.dim[0] - 1);
+    if (xa > xb || cy < 0 || cy >= g.dim[1] || cz < 0 || cz >= g.dim[2]) return;
+    const unsigned int row = (unsigned int)g.dim[0] * ((unsigned int)cy + (unsigned int)g.dim[1] * (unsigned int)cz);
+    const unsigned int s = __ldg(&cell_start[row + xa]), e = __ldg(&cell_start[row + xb + 1]);
+    for (unsigned int k = s; k < e; ++k)
+    {
+        const float4 t = __ldg(&sorted[k]);
+        const float d = dist2_nanoflann(qx, qy, qz, t.x, t.y, t.z);
+        if (!(d > cap2)) knn_push(L, d, __float_as_int(t.w));
+    }
+}
+struct Rot { float c, s; };
+// JacobiRotation::makeJacobi(x, y, z) (Jacobi.h:83-113)
+__device__ __forceinline__ Rot make_jacobi(float x, float y, float z)
+{
+    Rot r;
+    const float deno = fmul(2.0f, fabsf(y));
+    if (deno < FLT_MIN) { r.c = 1.0f; r.s = 0.0f; return r; }
+    const float tau = fdiv(fsub(x, z), deno);
+    const float w = __fsqrt_rn(fadd(fmul(tau, tau), 1.0f));
+    const float t = tau > 0.0f ? fdiv(1.0f, fadd(tau, w)) : fdiv(1.0f, fsub(tau, w));
+    const float sign_t = t > 0.0f ? 1.0f : -1.0f;
+    const float n = fdiv(1.0f, __fsqrt_rn(fadd(fmul(t, t), 1.0f)));
+    r.s = fmul(fmul(fmul(-sign_t, fdiv(y, fabsf(y))), fabsf(t)), n);
+    r.c = n;
+    return r;
+}
+// apply_rotation_in_the_plane: x' = c x + s y, y' = -s x + c y
+__device__ __forceinline__ void rot_apply(float &x, float &y, Rot j)
+{
+    const float xi = x, yi = y;
+    x = fadd(fmul(j.c, xi), fmul(j.s, yi));
+    y = fadd(fmul(-j.s, xi), fmul(j.c, yi));
+}
+// third column of U of JacobiSVD(W) after the descending sort; W row-major
+__device__ void svd3_smallest_direction(const float *Win, float *normal)
+{
+    float W[3][3], U[3][3];
+    float scale = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) scale = fmaxf(scale, fabsf(Win[i]));
+    if (scale == 0.0f) scale = 1.0f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { W[r][c] = fdiv(Win[r * 3 + c], scale); U[r][c] = r == c ? 1.0f : 0.0f; }
+    const float precision = 2.0f * FLT_EPSILON;
+    float max_diag = fmaxf(fabsf(W[0][0]), fmaxf(fabsf(W[1][1]), fabsf(W[2][2])));
+    bool finished = false;
+    for (int sweep = 0; sweep < 64 && !finished; ++sweep) // converges in a handful of sweeps; the cap only guards NaN input
+    {
+        finished = true;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq)
+        {
+            const int p = pq == 0 ? 1 : 2, q = pq == 2 ? 1 : 0; // (1,0), (2,0), (2,1)
+            const float threshold = fmaxf(FLT_MIN, fmul(precision, max_diag));
+            if (fabsf(W[p][q]) > threshold || fabsf(W[q][p]) > threshold)
+            {
+                finished = false;
+                // real_2x2_jacobi_svd (RealSvd2x2.h:19-50)
+                float m00 = W[p][p], m01 = W[p][q], m10 = W[q][p], m11 = W[q][q];
+                Rot rot1;
+                const float t = fadd(m00, m11), d = fsub(m10, m01);
+                if (fabsf(d) < FLT_MIN) { rot1.s = 0.0f; rot1.c = 1.0f; }
+                else
+                {
+                    const float u = fdiv(t, d);
+                    const float tmp = __fsqrt_rn(fadd(1.0f, fmul(u, u)));
+                    rot1.s = fdiv(1.0f, tmp);
+                    rot1.c = fdiv(u, tmp);
+                }
+                if (!(rot1.c == 1.0f && rot1.s == 0.0f)) { rot_apply(m00, m10, rot1); rot_apply(m01, m11, rot1); }
+                const Rot j_right = make_jacobi(m00, m01, m11);
+                const Rot jrt = {j_right.c, -j_right.s};
+                const Rot j_left = {fsub(fmul(rot1.c, jrt.c), fmul(rot1.s, jrt.s)), fadd(fmul(rot1.c, jrt.s), fmul(rot1.s, jrt.c))};
+                if (!(j_left.c == 1.0f && j_left.s == 0.0f))
+                {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) rot_apply(W[p][c], W[q][c], j_left); // rows p, q
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) rot_apply(U[r][p], U[r][q], j_left); // U.applyOnTheRight(p, q, j_left^T) applies (j_left^T)^T
+                }
+                if (!(jrt.c == 1.0f && jrt.s == 0.0f))
+                {
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) rot_apply(W[r][p], W[r][q], jrt);    // columns p, q with j_right^T
+                }
+                max_diag = fmaxf(max_diag, fmaxf(fabsf(W[p][p]), fabsf(W[q][q])));
+            }
+        }
+    }
+    float sv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+    {
+        const float a = W[i][i];
+        sv[i] = fmul(fabsf(a), scale);
+        if (a < 0.0f)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) U[r][i] = -U[r][i];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+    {
+        int pos = i;
+#pragma unroll
+        for (int k = i + 1; k < 3; ++k) if (sv[k] > sv[pos]) pos = k;
+        if (sv[pos] == 0.0f) break;
+        if (pos != i)
+        {
+            const float tmp = sv[i]; sv[i] = sv[pos]; sv[pos] = tmp;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { const float u = U[r][i]; U[r][i] = U[r][pos]; U[r][pos] = u; }
+        }
+    }
+    normal[0] = U[0][2]; normal[1] = U[1][2]; normal[2] = U[2][2];
+}
+
+__global__ void __launch_bounds__(128) estimate_normals_kernel(const float *__restrict__ pts, int n, const IcpState *st,
+                                                               const unsigned int *__restrict__ cell_start, const float4 *__restrict__ sorted,
+                                                               float radius, int knn, float *__restrict__ normals)
+{
+    const IcpGrid g = st->grid;
+    const float cap2 = radius;            // the reference compares the squared distance with `radius` itself
+    const float cap = sqrtf(radius) * (1.0f + 1e-6f);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const float qx = pts[3 * i], qy = pts[3 * i + 1], qz = pts[3 * i + 2];
+        KnnList L;
+        L.n = 0;
+        L.k = knn;
+        const float fx = (qx - g.origin[0]) * g.inv_h, fy = (qy - g.origin[1]) * g.inv_h, fz = (qz - g.origin[2]) * g.inv_h;
+        float nrm[3] = {0.0f, 0.0f, 0.0f};
+        if (qx == qx && qy == qy && qz == qz && fabsf(fx) < 1048576.0f && fabsf(fy) < 1048576.0f && fabsf(fz) < 1048576.0f)
+        {
+            const int hx = (int)floorf(fx), hy = (int)floorf(fy), hz = (int)floorf(fz);
+            RowPruner pr;
+            pr.fx = fx; pr.ay = fy - hy; pr.az = fz - hz;
+            pr.inv_h2 = g.inv_h * g.inv_h;
+            pr.slack = 1e-3f;
+            const float m_yz = fminf(fminf(pr.ay, 1.0f - pr.ay), fminf(pr.az, 1.0f - pr.az));
+            const float cap_cells = cap * g.inv_h;
+            const int r_max = (int)ceilf(cap_cells) + 1;
+            for (int r = 0; r <= r_max; ++r)
+            {
+                if (r > 0)
+                {
+                    // everything within `covered` cells has been seen once ring r-1 is complete
+                    const float covered = (float)(r - 1) + m_yz - pr.slack;
+                    if (covered > 0.0f && L.n == L.k && L.d[L.n - 1] * pr.inv_h2 <= covered * covered) break;
+                    if (covered > cap_cells) break;
+                }
+                for (int dz = -r; dz <= r; ++dz)
+                    for (int dy = -r; dy <= r; dy += (abs(dz) == r || r == 0 ? 1 : 2 * r))
+                    {
+                        // bound: the k-th distance once the list is full, the radius before; ties at the bound must be seen
+                        const float eb = L.n == L.k ? fminf(L.d[L.n - 1], cap * cap) : cap * cap;
+                        int xlo, xhi;
+                        if (pr.interval(dy, dz, eb * (1.0f + 1e-6f), xlo, xhi)) knn_scan_cells(g, cell_start, sorted, xlo, xhi, hy + dy, hz + dz, qx, qy, qz, cap2, L);
+                    }
+            }
+            // FitPlane (Geometry.cpp:172-199)
+            if (L.n >= 3)
+            {
+                float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+                for (int k = 0; k < L.n; ++k)
+                {
+                    const int j = L.i[k];
+                    sx = fadd(sx, pts[3 * j]); sy = fadd(sy, pts[3 * j + 1]); sz = fadd(sz, pts[3 * j + 2]);
+                }
+                const float cnt = (float)L.n;
+                const float mx = fdiv(sx, cnt), my = fdiv(sy, cnt), mz = fdiv(sz, cnt);
+                float W[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                for (int k = 0; k < L.n; ++k)
+                {
+                    const int j = L.i[k];
+                    const float d[3] = {fsub(pts[3 * j], mx), fsub(pts[3 * j + 1], my), fsub(pts[3 * j + 2], mz)};
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int b = 0; b < 3; ++b) W[a * 3 + b] = fadd(W[a * 3 + b], fmul(d[a], d[b]));
+                }
+#pragma unroll
+                for (int a = 0; a < 9; ++a) W[a] = fdiv(W[a], cnt);
+                svd3_smallest_direction(W, nrm);
+                // normal.normalize(): squaredNorm in Eigen's order a0 + (a1 + a2), division by the root if positive
+                const float n2 = fadd(fmul(nrm[0], nrm[0]), fadd(fmul(nrm[1], nrm[1]), fmul(nrm[2], nrm[2])));
+                if (n2 > 0.0f)
+                {
+                    const float nn = __fsqrt_rn(n2);
+                    nrm[0] = fdiv(nrm[0], nn); nrm[1] = fdiv(nrm[1], nn); nrm[2] = fdiv(nrm[2], nn);
+                }
+            }
+        }
+        normals[3 * i] = nrm[0]; normals[3 * i + 1] = nrm[1]; normals[3 * i + 2] = nrm[2];
+    }
+}
+
 } // namespace opb
 
 using namespace opb;
@@ -1277,7 +1515,7 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     for (int a = 0; a < 3; ++a) { h->bbox_enc[a] = 0xFFFFFFFFu; h->bbox_enc[3 + a] = 0u; }
     OPB_CUDA(cudaMemcpyAsync(c->d_state, h, sizeof(IcpState), cudaMemcpyHostToDevice, s));
     if (c->profiling) OPB_CUDA(cudaEventRecord(c->ev[0], s));
-    // grid over the target
+    // grid over the target (opb_icp_estimate_normals builds the same grid over its cloud)
     const int nb_t = (int)((nt + 255) / 256) < c->sm_count * 8 ? (int)((nt + 255) / 256) : c->sm_count * 8;
     icp_bbox_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)nt, c->d_state);
     // developer knob: cap on the number of grid cells (the construction streams over all of them, the searches prefer many)
@@ -1427,6 +1665,42 @@ int opb_icp_last_search_count(opb_icp *c, uint64_t *full_searches)
 {
     if (!c || !full_searches) { set_error("NULL argument"); return OPB_ERR_INVALID; }
     *full_searches = c->last_searched;
+    return OPB_OK;
+}
+int opb_icp_estimate_normals(opb_icp *c, const float *xyz, size_t n, float radius, int knn, float *normals)
+{
+    if (!c || !xyz || !normals) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    if (knn < 1 || knn > kKnnMax) { set_error("knn must be 1..%d", kKnnMax); return OPB_ERR_INVALID; }
+    if (!(radius > 0)) { set_error("radius must be > 0"); return OPB_ERR_INVALID; }
+    if (n == 0) return OPB_OK;
+    if (n > 0x7FFFFFF0u) { set_error("clouds above 2^31 points are not supported"); return OPB_ERR_INVALID; }
+    OPB_CUDA(cudaSetDevice(c->device));
+    int rc = icp_reserve(c, n, n);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    OPB_CUDA(cudaMemcpyAsync(c->d_tgt, xyz, n * 3 * sizeof(float), cudaMemcpyDefault, s));
+    IcpState *h = c->h_state;
+    memset(h, 0, sizeof(IcpState));
+    for (int a = 0; a < 3; ++a) { h->bbox_enc[a] = 0xFFFFFFFFu; h->bbox_enc[3 + a] = 0u; }
+    OPB_CUDA(cudaMemcpyAsync(c->d_state, h, sizeof(IcpState), cudaMemcpyHostToDevice, s));
+    const int nb_t = (int)((n + 255) / 256) < c->sm_count * 8 ? (int)((n + 255) / 256) : c->sm_count * 8;
+    unsigned long long max_cells = 16ull * n;
+    if (max_cells < (1u << 20)) max_cells = 1u << 20;
+    if (max_cells > kMaxCells) max_cells = kMaxCells;
+    icp_bbox_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)n, c->d_state);
+    icp_grid_setup_kernel<<<1, 1, 0, s>>>(c->d_state, (int)n, 0.0f, (unsigned int)max_cells);
+    icp_clear_kernel<<<c->sm_count * 8, 256, 0, s>>>(c->d_state, c->d_cell_count);
+    icp_count_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)n, c->d_state, c->d_cell_count, c->d_point_cell);
+    icp_tile_sums_kernel<<<c->sm_count * 2, 1024, 0, s>>>(c->d_state, c->d_cell_count, c->d_tile_sums);
+    icp_scan_tiles_kernel<<<1, 1024, 0, s>>>(c->d_state, c->d_tile_sums);
+    icp_scan_apply_kernel<<<c->sm_count * 2, 1024, 0, s>>>(c->d_state, c->d_cell_count, c->d_tile_sums, c->d_cell_start);
+    icp_scatter_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)n, c->d_point_cell, c->d_cell_start, c->d_cell_count, c->d_sorted);
+    // the normals land in the workspace's normal buffer, then go to wherever the caller's pointer lives
+    const int nb = (int)((n + 127) / 128) < c->sm_count * 16 ? (int)((n + 127) / 128) : c->sm_count * 16;
+    estimate_normals_kernel<<<nb, 128, 0, s>>>(c->d_tgt, (int)n, c->d_state, c->d_cell_start, c->d_sorted, radius, knn, c->d_nrm);
+    OPB_CUDA(cudaGetLastError());
+    OPB_CUDA(cudaMemcpyAsync(normals, c->d_nrm, n * 3 * sizeof(float), cudaMemcpyDefault, s));
+    OPB_CUDA(cudaStreamSynchronize(s));
     return OPB_OK;
 }
 int opb_icp_last_launch_count(opb_icp *c, int *launches)

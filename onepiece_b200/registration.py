@@ -39,6 +39,12 @@ class PointCloud:
     def HasNormals(self):
         return self.normals is not None and len(self.normals) == len(self.points) and len(self.points) > 0
 
+    def EstimateNormals(self, radius: float = 0.1, knn: int = 30, device: int = 0):
+        """PointCloud::EstimateNormals(radius, knn) (reference src/Geometry/PointCloud.cpp:102-144) on the GPU; fills self.normals"""
+        self.normals = np.zeros_like(self.points)
+        capi.check(capi.lib.opb_icp_estimate_normals(_Workspace.get(device), _ptr(self.points), len(self.points), radius, knn,
+                                                     _ptr(self.normals)))
+
     def DownSample(self, grid_len: float, colors=None, device: int = 0):
         """PointCloud::DownSample(grid_len) (reference src/Geometry/PointCloud.cpp:145-189) on the GPU -> new PointCloud
         (and the averaged colours when `colors` is given: returns (cloud, colors))."""

@@ -177,3 +177,32 @@ def test_certification_does_not_change_the_result(tmp_path):
     assert np.array_equal(out["1"]["Ti"].view(np.uint32), out["0"]["Ti"].view(np.uint32))
     assert np.array_equal(out["1"]["T"].view(np.uint32), out["0"]["T"].view(np.uint32))
     assert float(out["1"]["rmse"]) == float(out["0"]["rmse"])
+
+
+def test_estimate_normals_matches_the_oracle_bit_for_bit():
+    """PointCloud::EstimateNormals on the device: exact 30-nearest search on the grid + FitPlane + the JacobiSVD restatement.
+    Same neighbour order rule as the oracle (distance, then index), so even the tie-ridden raw cloud must agree bit for bit."""
+    from onepiece_b200 import capi
+    c0 = scenes.Camera()
+    cam = scenes.Camera(c0.fx / 4, c0.fy / 4, c0.cx / 4, c0.cy / 4, 160, 120, 1000.0)
+    d, _, _, n_true = scenes.room(cam, 0, with_normals=True)
+    pts = scenes.backproject(d, cam)
+    jit = (pts + np.random.default_rng(0).normal(0, 1e-4, pts.shape)).astype(np.float32)
+    for cloud, what in ((jit, "tie-free cloud"), (pts, "raw cloud")):
+        pc = reg.PointCloud(cloud)
+        pc.EstimateNormals()
+        ref = oracleapi.estimate_normals(cloud)
+        same = (pc.normals.view(np.uint32) == ref.view(np.uint32)).all(1)
+        assert same.all(), f"{what}: {np.count_nonzero(~same)} of {len(cloud)} normals differ, first at {np.argmax(~same)}"
+    # the estimated normals are the surface normals up to sign (away from the room's edges)
+    nt = n_true.reshape(-1, 3)[(d > 0).reshape(-1)]
+    assert np.median(np.abs((pc.normals * nt).sum(1))) > 0.999
+    # other parameters, and the reference's corner cases
+    pc = reg.PointCloud(jit)
+    pc.EstimateNormals(0.0004, 12)                 # squared-distance cut at 2 cm
+    assert np.array_equal(pc.normals.view(np.uint32), oracleapi.estimate_normals(jit, 0.0004, 12).view(np.uint32))
+    far = reg.PointCloud(np.array([[0, 0, 0], [10, 0, 0], [0, 10, 0], [10, 10, 0]], np.float32))
+    far.EstimateNormals()
+    assert not far.normals.any()                   # fewer than three points in range: FitPlane returns the zero vector
+    with pytest.raises(capi.OpbError):
+        pc.EstimateNormals(0.1, 65)
