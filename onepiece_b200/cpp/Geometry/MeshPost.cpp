@@ -5,6 +5,8 @@
 //       (the body of TriangleMesh::ClusteringSimplify, src/Geometry/TriangleMesh.cpp:53-58)
 //   geometry::TriangleMesh::ComputeNormals()                     reference src/Geometry/TriangleMesh.cpp:95-127
 //   geometry::PointCloud::DownSample(float) const                reference src/Geometry/PointCloud.cpp:145-189
+//   geometry::PointCloud::EstimateNormals(float, int)            reference src/Geometry/PointCloud.cpp:102-144 (bit-identical unless
+//       two neighbours of a point are at exactly the same distance: nanoflann orders such ties by tree traversal)
 // Signatures are the reference's own (its headers are included unchanged).  To integrate, delete those three bodies from the
 // reference's sources and add this file -- or, without touching the reference, put this object in front of the reference's
 // on the link line with -Wl,--allow-multiple-definition, which is what tests/cpp/Makefile does.
@@ -78,6 +80,21 @@ void TriangleMesh::ComputeNormals()
     for (size_t i = 0; i < triangles.size(); ++i)
         for (int k = 0; k < 3; ++k) t[3 * i + k] = triangles[i](k);
     if (opb_mesh_compute_normals(0, p.data(), points.size(), t.data(), triangles.size(), n.data()) != OPB_OK) { Report("ComputeNormals"); return; }
+    Unflatten(n.data(), points.size(), normals);
+}
+
+void PointCloud::EstimateNormals(float radius, int knn)
+{
+    static opb_icp *ws = nullptr; // callers are single-threaded; one search workspace per process
+    if (!ws && opb_icp_create(0, nullptr, &ws) != OPB_OK)
+    {
+        Report("EstimateNormals");
+        std::exit(1); // no device: there is no CPU path
+    }
+    std::cout << BLUE << "[EstimateNormals]::[INFO]::RadiusSearch " << knn << " nearest points, radius: " << radius << RESET << std::endl;
+    std::vector<float> p, n(points.size() * 3);
+    Flatten(points, p);
+    if (opb_icp_estimate_normals(ws, p.data(), points.size(), radius, knn, n.data()) != OPB_OK) { Report("EstimateNormals"); return; }
     Unflatten(n.data(), points.size(), normals);
 }
 

@@ -133,6 +133,17 @@ int main(int argc, char **argv)
         t_pcd.points.push_back(geometry::Point3(t[3 * i], t[3 * i + 1], t[3 * i + 2]));
         t_pcd.normals.push_back(geometry::Point3(n[3 * i], n[3 * i + 1], n[3 * i + 2]));
     }
+    // example/ICPTest.cpp:27-29: normals from the cloud itself when none are given (checked separately; the registration below
+    // keeps the analytic ones)
+    {
+        geometry::PointCloud e_pcd;
+        e_pcd.points = t_pcd.points;
+        e_pcd.EstimateNormals();
+        std::vector<float> en;
+        for (size_t i = 0; i < e_pcd.normals.size(); ++i)
+            for (int k = 0; k < 3; ++k) en.push_back(e_pcd.normals[i](k));
+        WriteAll(dir + "/estimated_normals.bin", en);
+    }
     registration::ICPParameter icp_para;
     icp_para.threshold = 0.05;
     icp_para.max_iteration = 10;

@@ -68,6 +68,9 @@ def test_reference_caller_code_runs_on_the_gpu(tmp_path):
     o = oracleapi.icp(src, tgt, nrm, np.eye(4), 10, 0.05)
     assert np.linalg.norm(icp[:16].reshape(4, 4)[:3, 3] - o["T"][:3, 3]) < 1e-5
     assert int(icp[17]) == len(o["pairs"])
+    # PointCloud::EstimateNormals through the drop-in (example/ICPTest.cpp:27-29)
+    en = np.fromfile(tmp_path / "estimated_normals.bin", np.float32).reshape(-1, 3)
+    assert_bit_equal(en, oracleapi.estimate_normals(tgt), "EstimateNormals through the drop-in")
     # Odometry::DenseTracking through the drop-in: two chained calls on the same RGBDFrames, then the cv::Mat overload
     odo = np.fromfile(tmp_path / "odometry.bin", np.float64)
     S, T = oracleapi.OracleFrame(c1_bgr, d1), oracleapi.OracleFrame(c0_bgr, d0)
