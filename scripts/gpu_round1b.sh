@@ -7,7 +7,7 @@ timeout 400 python bench.py --impl reference --steps 10 --warmup 1 > gpurun_out/
 timeout 600 python scripts/gpu_probe_neighbours.py > gpurun_out/neighbours.json 2> gpurun_out/neighbours.err; echo "neighbours exit $?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches_bench.csv \
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu launches exit $?"
-for spec in integrate_kernel:5 icp_loop_kernel:8 odo_loop_kernel:3; do
+for spec in integrate_pipelined_kernel:5 icp_loop_kernel:8 odo_loop_kernel:3; do
   k=${spec%%:*}; skip=${spec##*:}
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -f -o gpurun_out/full_$k \
       python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-odometry > gpurun_out/ncu_full_$k.log 2>&1; echo "ncu $k exit $?"
