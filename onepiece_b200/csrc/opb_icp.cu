@@ -131,7 +131,7 @@ __device__ void comm_allreduce(const IcpComm &cm, double *packet, int n)
 // ---------------------------------------------------------------------------------------------------------
 // grid construction
 // ---------------------------------------------------------------------------------------------------------
-__global__ void icp_bbox_kernel(const float *pts, int n, IcpState *st)
+__device__ __forceinline__ void icp_bbox_kernel_body(const float *pts, int n, IcpState *st)
 {
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -157,10 +157,11 @@ __global__ void icp_bbox_kernel(const float *pts, int n, IcpState *st)
         }
     }
 }
+__global__ void icp_bbox_kernel(const float *pts, int n, IcpState *st) { icp_bbox_kernel_body(pts, n, st); }
 
 // one thread: cell size such that the grid has at most kMaxCells cells and about two points per occupied
 // cell for surface-like clouds
-__global__ void icp_grid_setup_kernel(IcpState *st, int n, float min_cell, unsigned int max_cells)
+__device__ __forceinline__ void icp_grid_setup_kernel_body(IcpState *st, int n, float min_cell, unsigned int max_cells)
 {
     float ext[3];
     for (int a = 0; a < 3; ++a)
@@ -193,6 +194,7 @@ __global__ void icp_grid_setup_kernel(IcpState *st, int n, float min_cell, unsig
         st->grid.dim[a] = (int)floorf(ext[a] / h) + 1;
     }
 }
+__global__ void icp_grid_setup_kernel(IcpState *st, int n, float min_cell, unsigned int max_cells) { icp_grid_setup_kernel_body(st, n, min_cell, max_cells); }
 
 __device__ __forceinline__ int cell_coord(float v, float origin, float inv_h, int dim)
 {
@@ -207,7 +209,7 @@ __device__ __forceinline__ unsigned int cell_of(const IcpGrid &g, float x, float
     return (unsigned int)cx + (unsigned int)g.dim[0] * ((unsigned int)cy + (unsigned int)g.dim[1] * (unsigned int)cz);
 }
 
-__global__ void icp_count_kernel(const float *pts, int n, const IcpState *st, unsigned int *cell_count, unsigned int *point_cell)
+__device__ __forceinline__ void icp_count_kernel_body(const float *pts, int n, const IcpState *st, unsigned int *cell_count, unsigned int *point_cell)
 {
     const IcpGrid g = st->grid;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -222,6 +224,7 @@ __global__ void icp_count_kernel(const float *pts, int n, const IcpState *st, un
         point_cell[i] = c;
     }
 }
+__global__ void icp_count_kernel(const float *pts, int n, const IcpState *st, unsigned int *cell_count, unsigned int *point_cell) { icp_count_kernel_body(pts, n, st, cell_count, point_cell); }
 
 // exclusive scan of the cell counts -> cell_start (n_cells + 1 entries), three phases over tiles of 8192 cells:
 // tile sums, scan of the tile sums by one CTA, per-tile scan with the tile offset
@@ -232,11 +235,12 @@ __device__ __forceinline__ unsigned int icp_n_cells(const IcpState *st)
 {
     return (unsigned int)st->grid.dim[0] * (unsigned int)st->grid.dim[1] * (unsigned int)st->grid.dim[2];
 }
-__global__ void icp_clear_kernel(const IcpState *st, unsigned int *cell_count)
+__device__ __forceinline__ void icp_clear_kernel_body(const IcpState *st, unsigned int *cell_count)
 {
     const unsigned int n = icp_n_cells(st) + 1;
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) cell_count[i] = 0u;
 }
+__global__ void icp_clear_kernel(const IcpState *st, unsigned int *cell_count) { icp_clear_kernel_body(st, cell_count); }
 // block-wide inclusive scan helper over 1024 threads; returns the inclusive value, total in *total
 __device__ __forceinline__ unsigned int block_inclusive_scan_1024(unsigned int v, unsigned int *warp_sums, unsigned int *total)
 {
@@ -265,7 +269,7 @@ __device__ __forceinline__ unsigned int block_inclusive_scan_1024(unsigned int v
     *total = warp_sums[31];
     return inc + (warp ? warp_sums[warp - 1] : 0u);
 }
-__global__ void __launch_bounds__(1024) icp_tile_sums_kernel(const IcpState *st, const unsigned int *cell_count, unsigned int *tile_sums)
+__device__ __forceinline__ void icp_tile_sums_kernel_body(const IcpState *st, const unsigned int *cell_count, unsigned int *tile_sums)
 {
     __shared__ unsigned int warp_sums[32];
     const unsigned int n = icp_n_cells(st);
@@ -281,7 +285,8 @@ __global__ void __launch_bounds__(1024) icp_tile_sums_kernel(const IcpState *st,
         __syncthreads();
     }
 }
-__global__ void __launch_bounds__(1024) icp_scan_tiles_kernel(const IcpState *st, unsigned int *tile_sums)
+__global__ void __launch_bounds__(1024) icp_tile_sums_kernel(const IcpState *st, const unsigned int *cell_count, unsigned int *tile_sums) { icp_tile_sums_kernel_body(st, cell_count, tile_sums); }
+__device__ __forceinline__ void icp_scan_tiles_kernel_body(const IcpState *st, unsigned int *tile_sums)
 {
     __shared__ unsigned int warp_sums[32];
     const unsigned int n_tiles = (icp_n_cells(st) + kScanTile - 1) / kScanTile; // <= kMaxTiles <= 1025
@@ -297,7 +302,8 @@ __global__ void __launch_bounds__(1024) icp_scan_tiles_kernel(const IcpState *st
         __syncthreads();
     }
 }
-__global__ void __launch_bounds__(1024) icp_scan_apply_kernel(const IcpState *st, const unsigned int *cell_count,
+__global__ void __launch_bounds__(1024) icp_scan_tiles_kernel(const IcpState *st, unsigned int *tile_sums) { icp_scan_tiles_kernel_body(st, tile_sums); }
+__device__ __forceinline__ void icp_scan_apply_kernel_body(const IcpState *st, const unsigned int *cell_count,
                                                               const unsigned int *tile_sums, unsigned int *cell_start)
 {
     __shared__ unsigned int warp_sums[32];
@@ -319,9 +325,11 @@ __global__ void __launch_bounds__(1024) icp_scan_apply_kernel(const IcpState *st
         __syncthreads();
     }
 }
+__global__ void __launch_bounds__(1024) icp_scan_apply_kernel(const IcpState *st, const unsigned int *cell_count,
+                                                              const unsigned int *tile_sums, unsigned int *cell_start) { icp_scan_apply_kernel_body(st, cell_count, tile_sums, cell_start); }
 
 // scatter into cell order (the order inside a cell is irrelevant: ties are broken by original index in the search)
-__global__ void icp_scatter_kernel(const float *pts, int n, const unsigned int *point_cell, const unsigned int *cell_start,
+__device__ __forceinline__ void icp_scatter_kernel_body(const float *pts, int n, const unsigned int *point_cell, const unsigned int *cell_start,
                                    unsigned int *cell_count, float4 *sorted)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -331,6 +339,45 @@ __global__ void icp_scatter_kernel(const float *pts, int n, const unsigned int *
         const unsigned int pos = cell_start[c] + atomicSub(&cell_count[c], 1u) - 1u;
         sorted[pos] = make_float4(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], __int_as_float(i));
     }
+}
+__global__ void icp_scatter_kernel(const float *pts, int n, const unsigned int *point_cell, const unsigned int *cell_start,
+                                   unsigned int *cell_count, float4 *sorted) { icp_scatter_kernel_body(pts, n, point_cell, cell_start, cell_count, sorted); }
+
+// The whole grid construction as ONE cooperative launch: the eight phases above separated by grid-wide barriers instead of
+// kernel boundaries (eight launches of a few microseconds of work each cost more in launch latency than in work).
+__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int &generation)
+{
+    ++generation;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*(volatile unsigned int *)counter < generation * gridDim.x) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(1024, 1) icp_grid_build_kernel(const float *pts, int n, IcpState *st, float min_cell, unsigned int max_cells,
+                                                                 unsigned int *cell_count, unsigned int *point_cell, unsigned int *tile_sums,
+                                                                 unsigned int *cell_start, float4 *sorted, unsigned int *sync)
+{
+    unsigned int generation = 0;
+    icp_bbox_kernel_body(pts, n, st);
+    grid_barrier(sync, generation);
+    if (blockIdx.x == 0 && threadIdx.x == 0) icp_grid_setup_kernel_body(st, n, min_cell, max_cells);
+    grid_barrier(sync, generation);
+    icp_clear_kernel_body(st, cell_count);
+    grid_barrier(sync, generation);
+    icp_count_kernel_body(pts, n, st, cell_count, point_cell);
+    grid_barrier(sync, generation);
+    icp_tile_sums_kernel_body(st, cell_count, tile_sums);
+    grid_barrier(sync, generation);
+    if (blockIdx.x == 0) icp_scan_tiles_kernel_body(st, tile_sums);
+    grid_barrier(sync, generation);
+    icp_scan_apply_kernel_body(st, cell_count, tile_sums, cell_start);
+    grid_barrier(sync, generation);
+    icp_scatter_kernel_body(pts, n, point_cell, cell_start, cell_count, sorted);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1340,6 +1387,8 @@ struct opb_icp
     bool profiling = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     int coop_ctas_per_sm = 0; // resident CTAs per SM of the persistent loop kernel; 0: cooperative launch unavailable
+    int grid_ctas_per_sm = 0; // the same for the fused grid construction
+    unsigned int *d_grid_sync = nullptr;
     bool peers_share_device = false; // a peer rank runs on this very GPU: two persistent grids could not be resident together
     // uploads that overlap the grid construction
     cudaStream_t copy_stream = nullptr;
@@ -1390,6 +1439,44 @@ static int icp_reserve(opb_icp *c, size_t ns, size_t nt)
     return OPB_OK;
 }
 
+// uniform grid over the nt points in c->d_tgt (bounding box in c->d_state already reset): cell_start + cell-sorted points
+static int icp_build_grid(opb_icp *c, size_t nt)
+{
+    cudaStream_t s = c->stream;
+    // Cap on the number of grid cells: the construction streams over all of them (clear, count, scan) while only a few
+    // passes of a registration still walk the grid, so about 16 cells per target point is the measured sweet spot
+    // (640x480 frame: construction 0.134 -> 0.105 ms, pass loop +0.01 ms).  OPB_ICP_MAX_CELLS overrides it.
+    static const long long k_cells_env = getenv("OPB_ICP_MAX_CELLS") ? atoll(getenv("OPB_ICP_MAX_CELLS")) : 0;
+    unsigned long long max_cells = k_cells_env > 0 ? (unsigned long long)k_cells_env : 16ull * nt;
+    if (max_cells < (1u << 20)) max_cells = 1u << 20;
+    if (max_cells > kMaxCells) max_cells = kMaxCells;
+    static const int k_fused = getenv("OPB_ICP_FUSED_GRID") ? atoi(getenv("OPB_ICP_FUSED_GRID")) : 1;
+    if (k_fused && c->grid_ctas_per_sm > 0)
+    {
+        // one cooperative launch, grid-wide barriers between the phases
+        OPB_CUDA(cudaMemsetAsync(c->d_grid_sync, 0, sizeof(unsigned int), s));
+        const float *pts = c->d_tgt;
+        int n = (int)nt;
+        float min_cell = 0.0f;
+        unsigned int mc = (unsigned int)max_cells;
+        void *kargs[] = {(void *)&pts, (void *)&n, (void *)&c->d_state, (void *)&min_cell, (void *)&mc, (void *)&c->d_cell_count,
+                         (void *)&c->d_point_cell, (void *)&c->d_tile_sums, (void *)&c->d_cell_start, (void *)&c->d_sorted, (void *)&c->d_grid_sync};
+        OPB_CUDA(cudaLaunchCooperativeKernel((const void *)icp_grid_build_kernel, dim3(c->sm_count * c->grid_ctas_per_sm), dim3(1024), kargs, 0, s));
+        return OPB_OK;
+    }
+    const int nb_t = (int)((nt + 255) / 256) < c->sm_count * 8 ? (int)((nt + 255) / 256) : c->sm_count * 8;
+    icp_bbox_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)nt, c->d_state);
+    icp_grid_setup_kernel<<<1, 1, 0, s>>>(c->d_state, (int)nt, 0.0f, (unsigned int)max_cells);
+    icp_clear_kernel<<<c->sm_count * 8, 256, 0, s>>>(c->d_state, c->d_cell_count);
+    icp_count_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)nt, c->d_state, c->d_cell_count, c->d_point_cell);
+    icp_tile_sums_kernel<<<c->sm_count * 2, 1024, 0, s>>>(c->d_state, c->d_cell_count, c->d_tile_sums);
+    icp_scan_tiles_kernel<<<1, 1024, 0, s>>>(c->d_state, c->d_tile_sums);
+    icp_scan_apply_kernel<<<c->sm_count * 2, 1024, 0, s>>>(c->d_state, c->d_cell_count, c->d_tile_sums, c->d_cell_start);
+    icp_scatter_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)nt, c->d_point_cell, c->d_cell_start, c->d_cell_count, c->d_sorted);
+    OPB_CUDA(cudaGetLastError());
+    return OPB_OK;
+}
+
 extern "C"
 {
 int opb_icp_create(int device, void *stream, opb_icp **out)
@@ -1427,6 +1514,10 @@ int opb_icp_create(int device, void *stream, opb_icp **out)
         if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_plane, icp_loop_kernel<true>, kIcpThreads, 0) == cudaSuccess &&
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_point, icp_loop_kernel<false>, kIcpThreads, 0) == cudaSuccess)
             c->coop_ctas_per_sm = occ_plane < occ_point ? occ_plane : occ_point;
+        int occ_grid = 0;
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_grid, icp_grid_build_kernel, 1024, 0) == cudaSuccess &&
+            cudaMalloc(&c->d_grid_sync, sizeof(unsigned int)) == cudaSuccess)
+            c->grid_ctas_per_sm = occ_grid > 2 ? 2 : occ_grid;
         cudaGetLastError();
     }
     if (e != cudaSuccess)
@@ -1448,6 +1539,7 @@ void opb_icp_destroy(opb_icp *c)
     cudaFree(c->d_cell_count); cudaFree(c->d_tile_sums); cudaFree(c->d_cell_start); cudaFree(c->d_nn); cudaFree(c->d_pairs);
     cudaFree(c->d_inlier); cudaFree(c->d_partials); cudaFree(c->d_state); cudaFree(c->d_mailbox);
     cudaFree(c->d_qref); cudaFree(c->d_nn_ref); cudaFree(c->d_worklist); cudaFree(c->d_budget2); cudaFree(c->d_pair_tiles);
+    cudaFree(c->d_grid_sync);
     if (c->h_state) cudaFreeHost(c->h_state);
     for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 3; ++i) if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
@@ -1516,23 +1608,8 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     OPB_CUDA(cudaMemcpyAsync(c->d_state, h, sizeof(IcpState), cudaMemcpyHostToDevice, s));
     if (c->profiling) OPB_CUDA(cudaEventRecord(c->ev[0], s));
     // grid over the target (opb_icp_estimate_normals builds the same grid over its cloud)
-    const int nb_t = (int)((nt + 255) / 256) < c->sm_count * 8 ? (int)((nt + 255) / 256) : c->sm_count * 8;
-    icp_bbox_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)nt, c->d_state);
-    // developer knob: cap on the number of grid cells (the construction streams over all of them, the searches prefer many)
-    // Cap on the number of grid cells: the construction streams over all of them (clear, count, scan) while only a few
-    // passes of a registration still walk the grid, so about 16 cells per target point is the measured sweet spot
-    // (640x480 frame: construction 0.134 -> 0.091 ms, pass loop +0.01 ms).  OPB_ICP_MAX_CELLS overrides it.
-    static const long long k_cells_env = getenv("OPB_ICP_MAX_CELLS") ? atoll(getenv("OPB_ICP_MAX_CELLS")) : 0;
-    unsigned long long max_cells = k_cells_env > 0 ? (unsigned long long)k_cells_env : 16ull * nt;
-    if (max_cells < (1u << 20)) max_cells = 1u << 20;
-    if (max_cells > kMaxCells) max_cells = kMaxCells;
-    icp_grid_setup_kernel<<<1, 1, 0, s>>>(c->d_state, (int)nt, 0.0f, (unsigned int)max_cells);
-    icp_clear_kernel<<<c->sm_count * 8, 256, 0, s>>>(c->d_state, c->d_cell_count);
-    icp_count_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)nt, c->d_state, c->d_cell_count, c->d_point_cell);
-    icp_tile_sums_kernel<<<c->sm_count * 2, 1024, 0, s>>>(c->d_state, c->d_cell_count, c->d_tile_sums);
-    icp_scan_tiles_kernel<<<1, 1024, 0, s>>>(c->d_state, c->d_tile_sums);
-    icp_scan_apply_kernel<<<c->sm_count * 2, 1024, 0, s>>>(c->d_state, c->d_cell_count, c->d_tile_sums, c->d_cell_start);
-    icp_scatter_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)nt, c->d_point_cell, c->d_cell_start, c->d_cell_count, c->d_sorted);
+    rc = icp_build_grid(c, nt);
+    if (rc) return rc;
     if (c->profiling) OPB_CUDA(cudaEventRecord(c->ev[1], s));
     // iterations
     IcpArgs a;
@@ -1572,7 +1649,7 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
         const void *fn = point_to_plane ? (const void *)icp_loop_kernel<true> : (const void *)icp_loop_kernel<false>;
         OPB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(nb_l), dim3(kIcpThreads), kargs, 0, s));
         looped = true;
-        c->last_launches = 8 + 1 + 2 + (pairs && pairs_cap && ns ? 3 : 0) + (par->scaling != 1.0 ? 2 : 0);
+        c->last_launches = (c->grid_ctas_per_sm > 0 ? 1 : 8) + 1 + 2 + (pairs && pairs_cap && ns ? 3 : 0) + (par->scaling != 1.0 ? 2 : 0);
     }
     for (int it = 0; !looped && it <= par->max_iteration; ++it)
     {
@@ -1683,18 +1760,8 @@ int opb_icp_estimate_normals(opb_icp *c, const float *xyz, size_t n, float radiu
     memset(h, 0, sizeof(IcpState));
     for (int a = 0; a < 3; ++a) { h->bbox_enc[a] = 0xFFFFFFFFu; h->bbox_enc[3 + a] = 0u; }
     OPB_CUDA(cudaMemcpyAsync(c->d_state, h, sizeof(IcpState), cudaMemcpyHostToDevice, s));
-    const int nb_t = (int)((n + 255) / 256) < c->sm_count * 8 ? (int)((n + 255) / 256) : c->sm_count * 8;
-    unsigned long long max_cells = 16ull * n;
-    if (max_cells < (1u << 20)) max_cells = 1u << 20;
-    if (max_cells > kMaxCells) max_cells = kMaxCells;
-    icp_bbox_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)n, c->d_state);
-    icp_grid_setup_kernel<<<1, 1, 0, s>>>(c->d_state, (int)n, 0.0f, (unsigned int)max_cells);
-    icp_clear_kernel<<<c->sm_count * 8, 256, 0, s>>>(c->d_state, c->d_cell_count);
-    icp_count_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)n, c->d_state, c->d_cell_count, c->d_point_cell);
-    icp_tile_sums_kernel<<<c->sm_count * 2, 1024, 0, s>>>(c->d_state, c->d_cell_count, c->d_tile_sums);
-    icp_scan_tiles_kernel<<<1, 1024, 0, s>>>(c->d_state, c->d_tile_sums);
-    icp_scan_apply_kernel<<<c->sm_count * 2, 1024, 0, s>>>(c->d_state, c->d_cell_count, c->d_tile_sums, c->d_cell_start);
-    icp_scatter_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)n, c->d_point_cell, c->d_cell_start, c->d_cell_count, c->d_sorted);
+    rc = icp_build_grid(c, n);
+    if (rc) return rc;
     // the normals land in the workspace's normal buffer, then go to wherever the caller's pointer lives
     const int nb = (int)((n + 127) / 128) < c->sm_count * 16 ? (int)((n + 127) / 128) : c->sm_count * 16;
     estimate_normals_kernel<<<nb, 128, 0, s>>>(c->d_tgt, (int)n, c->d_state, c->d_cell_start, c->d_sorted, radius, knn, c->d_nrm);

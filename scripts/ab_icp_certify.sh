@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B of the nearest-neighbour certificates in the ICP loop: bench step breakdown with them on / off and for several guards
-for cfg in "OPB_ICP_PERSISTENT=1" "OPB_ICP_PERSISTENT=0"; do
+for cfg in "OPB_ICP_FUSED_GRID=0" "OPB_ICP_FUSED_GRID=1" "OPB_ICP_FUSED_GRID=0" "OPB_ICP_FUSED_GRID=1"; do
   echo "== $cfg"
   env $cfg python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-odometry | python -c "
 import json,sys
