@@ -1451,9 +1451,10 @@ static int icp_build_grid(opb_icp *c, size_t nt)
     if (max_cells < (1u << 20)) max_cells = 1u << 20;
     if (max_cells > kMaxCells) max_cells = kMaxCells;
     static const int k_fused = getenv("OPB_ICP_FUSED_GRID") ? atoi(getenv("OPB_ICP_FUSED_GRID")) : 1;
-    if (k_fused && c->grid_ctas_per_sm > 0)
+    if (k_fused && c->grid_ctas_per_sm > 0 && !c->peers_share_device)
     {
-        // one cooperative launch, grid-wide barriers between the phases
+        // one cooperative launch, grid-wide barriers between the phases (not when a peer rank shares this GPU: its kernels may
+        // be spinning on our packet while ours waits for the whole device to be free)
         OPB_CUDA(cudaMemsetAsync(c->d_grid_sync, 0, sizeof(unsigned int), s));
         const float *pts = c->d_tgt;
         int n = (int)nt;
@@ -1649,7 +1650,7 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
         const void *fn = point_to_plane ? (const void *)icp_loop_kernel<true> : (const void *)icp_loop_kernel<false>;
         OPB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(nb_l), dim3(kIcpThreads), kargs, 0, s));
         looped = true;
-        c->last_launches = (c->grid_ctas_per_sm > 0 ? 1 : 8) + 1 + 2 + (pairs && pairs_cap && ns ? 3 : 0) + (par->scaling != 1.0 ? 2 : 0);
+        c->last_launches = (c->grid_ctas_per_sm > 0 && !c->peers_share_device ? 1 : 8) + 1 + 2 + (pairs && pairs_cap && ns ? 3 : 0) + (par->scaling != 1.0 ? 2 : 0);
     }
     for (int it = 0; !looped && it <= par->max_iteration; ++it)
     {
