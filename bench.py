@@ -402,7 +402,7 @@ def run_ours(args):
     vol.ProfileRead(reset=True)
     capi.lib.opb_icp_set_profiling(icp, 1)
     icp_loop_ms, icp_grid_ms, upd_sum, cubes = 0.0, 0.0, 0, 0
-    for s in range(min(K, 50)):
+    for s in range(min(K, 100)):
         one_step(W + s, D, False)
         a, b = C.c_float(0), C.c_float(0)
         capi.lib.opb_icp_last_timing(icp, C.byref(a), C.byref(b))
@@ -411,7 +411,7 @@ def run_ours(args):
         st = vol.FrameStats()
         upd_sum += st.updated_voxels
         cubes = st.frame_cubes
-    nprof_steps = min(K, 50)
+    nprof_steps = min(K, 100)
     sel_ms, int_ms, nprof = vol.ProfileRead(reset=True)
     vol.SetProfiling(False)
     capi.lib.opb_icp_set_profiling(icp, 0)
