@@ -1124,28 +1124,33 @@ __global__ void icp_scale_kernel(float *p, size_t n, float s)
 // (distance, index) in local memory; then the plane fit in the reference's float operation order.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kKnnMax = 64;
+constexpr int kKnnThreads = 128;
+// the sorted candidate list of a thread lives in shared memory, entry k of thread t at [k * kKnnThreads + t] (a list in local
+// memory costs a DRAM round trip per shifted entry: 289 MB of writes for a 640x480 cloud)
 struct KnnList
 {
-    float d[kKnnMax];
-    int i[kKnnMax];
+    float *d;
+    int *i;
     int n, k;
+    __device__ __forceinline__ float &dist(int e) { return d[e * kKnnThreads]; }
+    __device__ __forceinline__ int &index(int e) { return i[e * kKnnThreads]; }
 };
 __device__ __forceinline__ void knn_push(KnnList &L, float d, int idx)
 {
     if (L.n == L.k)
     {
-        const float wd = L.d[L.n - 1];
-        if (!(d < wd || (d == wd && idx < L.i[L.n - 1]))) return;
+        const float wd = L.dist(L.n - 1);
+        if (!(d < wd || (d == wd && idx < L.index(L.n - 1)))) return;
     }
     int pos = L.n < L.k ? L.n : L.k - 1;
-    while (pos > 0 && (L.d[pos - 1] > d || (L.d[pos - 1] == d && L.i[pos - 1] > idx)))
+    while (pos > 0 && (L.dist(pos - 1) > d || (L.dist(pos - 1) == d && L.index(pos - 1) > idx)))
     {
-        L.d[pos] = L.d[pos - 1];
-        L.i[pos] = L.i[pos - 1];
+        L.dist(pos) = L.dist(pos - 1);
+        L.index(pos) = L.index(pos - 1);
         --pos;
     }
-    L.d[pos] = d;
-    L.i[pos] = idx;
+    L.dist(pos) = d;
+    L.index(pos) = idx;
     if (L.n < L.k) ++L.n;
 }
 __device__ __forceinline__ void knn_scan_cells(const IcpGrid &g, const unsigned int *__restrict__ cell_start, const float4 *__restrict__ sorted,
@@ -1271,10 +1276,11 @@ __device__ void svd3_smallest_direction(const float *Win, float *normal)
     normal[0] = U[0][2]; normal[1] = U[1][2]; normal[2] = U[2][2];
 }
 
-__global__ void __launch_bounds__(128) estimate_normals_kernel(const float *__restrict__ pts, int n, const IcpState *st,
+__global__ void __launch_bounds__(kKnnThreads) estimate_normals_kernel(const float *__restrict__ pts, int n, const IcpState *st,
                                                                const unsigned int *__restrict__ cell_start, const float4 *__restrict__ sorted,
                                                                float radius, int knn, float *__restrict__ normals)
 {
+    extern __shared__ float knn_smem[]; // knn x kKnnThreads distances, then as many indices
     const IcpGrid g = st->grid;
     const float cap2 = radius;            // the reference compares the squared distance with `radius` itself
     const float cap = sqrtf(radius) * (1.0f + 1e-6f);
@@ -1282,6 +1288,8 @@ __global__ void __launch_bounds__(128) estimate_normals_kernel(const float *__re
     {
         const float qx = pts[3 * i], qy = pts[3 * i + 1], qz = pts[3 * i + 2];
         KnnList L;
+        L.d = knn_smem + threadIdx.x;
+        L.i = reinterpret_cast<int *>(knn_smem + knn * kKnnThreads) + threadIdx.x;
         L.n = 0;
         L.k = knn;
         const float fx = (qx - g.origin[0]) * g.inv_h, fy = (qy - g.origin[1]) * g.inv_h, fz = (qz - g.origin[2]) * g.inv_h;
@@ -1302,14 +1310,14 @@ __global__ void __launch_bounds__(128) estimate_normals_kernel(const float *__re
                 {
                     // everything within `covered` cells has been seen once ring r-1 is complete
                     const float covered = (float)(r - 1) + m_yz - pr.slack;
-                    if (covered > 0.0f && L.n == L.k && L.d[L.n - 1] * pr.inv_h2 <= covered * covered) break;
+                    if (covered > 0.0f && L.n == L.k && L.dist(L.n - 1) * pr.inv_h2 <= covered * covered) break;
                     if (covered > cap_cells) break;
                 }
                 for (int dz = -r; dz <= r; ++dz)
                     for (int dy = -r; dy <= r; dy += (abs(dz) == r || r == 0 ? 1 : 2 * r))
                     {
                         // bound: the k-th distance once the list is full, the radius before; ties at the bound must be seen
-                        const float eb = L.n == L.k ? fminf(L.d[L.n - 1], cap * cap) : cap * cap;
+                        const float eb = L.n == L.k ? fminf(L.dist(L.n - 1), cap * cap) : cap * cap;
                         int xlo, xhi;
                         if (pr.interval(dy, dz, eb * (1.0f + 1e-6f), xlo, xhi)) knn_scan_cells(g, cell_start, sorted, xlo, xhi, hy + dy, hz + dz, qx, qy, qz, cap2, L);
                     }
@@ -1320,7 +1328,7 @@ __global__ void __launch_bounds__(128) estimate_normals_kernel(const float *__re
                 float sx = 0.0f, sy = 0.0f, sz = 0.0f;
                 for (int k = 0; k < L.n; ++k)
                 {
-                    const int j = L.i[k];
+                    const int j = L.index(k);
                     sx = fadd(sx, pts[3 * j]); sy = fadd(sy, pts[3 * j + 1]); sz = fadd(sz, pts[3 * j + 2]);
                 }
                 const float cnt = (float)L.n;
@@ -1328,7 +1336,7 @@ __global__ void __launch_bounds__(128) estimate_normals_kernel(const float *__re
                 float W[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
                 for (int k = 0; k < L.n; ++k)
                 {
-                    const int j = L.i[k];
+                    const int j = L.index(k);
                     const float d[3] = {fsub(pts[3 * j], mx), fsub(pts[3 * j + 1], my), fsub(pts[3 * j + 2], mz)};
 #pragma unroll
                     for (int a = 0; a < 3; ++a)
@@ -1764,8 +1772,13 @@ int opb_icp_estimate_normals(opb_icp *c, const float *xyz, size_t n, float radiu
     rc = icp_build_grid(c, n);
     if (rc) return rc;
     // the normals land in the workspace's normal buffer, then go to wherever the caller's pointer lives
-    const int nb = (int)((n + 127) / 128) < c->sm_count * 16 ? (int)((n + 127) / 128) : c->sm_count * 16;
-    estimate_normals_kernel<<<nb, 128, 0, s>>>(c->d_tgt, (int)n, c->d_state, c->d_cell_start, c->d_sorted, radius, knn, c->d_nrm);
+    const size_t knn_smem = (size_t)knn * kKnnThreads * (sizeof(float) + sizeof(int));
+    OPB_CUDA(cudaFuncSetAttribute(estimate_normals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kKnnMax * kKnnThreads * 8)));
+    int per_sm = 0;
+    OPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, estimate_normals_kernel, kKnnThreads, knn_smem));
+    if (per_sm < 1) per_sm = 1;
+    const int nb = (int)((n + kKnnThreads - 1) / kKnnThreads) < c->sm_count * per_sm * 2 ? (int)((n + kKnnThreads - 1) / kKnnThreads) : c->sm_count * per_sm * 2;
+    estimate_normals_kernel<<<nb, kKnnThreads, knn_smem, s>>>(c->d_tgt, (int)n, c->d_state, c->d_cell_start, c->d_sorted, radius, knn, c->d_nrm);
     OPB_CUDA(cudaGetLastError());
     OPB_CUDA(cudaMemcpyAsync(normals, c->d_nrm, n * 3 * sizeof(float), cudaMemcpyDefault, s));
     OPB_CUDA(cudaStreamSynchronize(s));
