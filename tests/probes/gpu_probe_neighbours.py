@@ -8,7 +8,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from onepiece_b200 import imageproc, scenes  # noqa: E402
 from onepiece_b200.mesh import TriangleMesh  # noqa: E402
 from onepiece_b200.volume import CubeHandler  # noqa: E402

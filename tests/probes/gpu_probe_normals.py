@@ -1,7 +1,7 @@
 """Full-size timing of PointCloud::EstimateNormals: device vs the compiled reference (nanoflann + Eigen on one core)."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from onepiece_b200 import registration as reg, scenes
 from oracle import refapi
 cam = scenes.Camera()
