@@ -45,17 +45,17 @@ def test_no_cpu_fallback_without_a_device():
 
 
 def test_product_never_imports_the_oracle():
-    """Only tests/, bench.py and __graft_entry__.py may touch oracle/."""
-    pkg = os.path.join(ROOT, "onepiece_b200")
+    """Only tests/, bench.py and __graft_entry__.py may touch oracle/: neither the package nor the developer scripts do."""
     offenders = []
-    for dirpath, _, files in os.walk(pkg):
-        if os.path.basename(dirpath) in ("build", "__pycache__"):
-            continue
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
-                src = open(os.path.join(dirpath, f), errors="replace").read()
-                if re.search(r"(from|import)\s+oracle\b|oracle/|opb_oracle|libopref", src):
-                    offenders.append(os.path.join(dirpath, f))
+    for top in ("onepiece_b200", "scripts", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            if os.path.basename(dirpath) in ("build", "__pycache__"):
+                continue
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp", ".sh")):
+                    src = open(os.path.join(dirpath, f), errors="replace").read()
+                    if re.search(r"(from|import)\s+oracle\b|oracle/|opb_oracle|libopref", src):
+                        offenders.append(os.path.join(dirpath, f))
     assert not offenders, offenders
 
 
