@@ -1771,31 +1771,530 @@ static void fit_plane_normal(const float *pts, const int *idx, int n, float *nor
     normal[0] = U[2]; normal[1] = U[5]; normal[2] = U[8];
     normalize3(normal);
 }
-void orc_estimate_normals(const float *pts, long n, float radius, int knn, float *normals)
+void orc_estimate_normals(const float *pts, long n, float radius, int knn, float *normals);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * nanoflann kd-tree as the reference drives it (src/Geometry/KDTree.h:60-262 over the vendored, locally modified
+ * 3rdparty/nanoflann/include/nanoflann.hpp): L2_Simple_Adaptor<float>, DIM 3, leaf_max_size 10.
+ *   build    nanoflann.hpp:843-1010  (computeMinMax, divideTree, middleSplit_, planeSplit)
+ *   search   nanoflann.hpp:1012-1028,1228-1295,1354-1417 (computeInitialDistances, findNeighbors, searchLevel)
+ *   results  nanoflann.hpp:150-214 (KNNResultSet), :216-262 (RadiusResultSet with the max_neighbors early stop added
+ *            by the reference), :1285-1295 (radiusSearch + std::sort by distance only)
+ * Everything here is what decides WHICH neighbours come back and IN WHAT ORDER when distances tie or when the radius
+ * search stops early, which the float sums downstream (FitPlane, FPFH) depend on.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct { int left, right, child1, child2, divfeat; float divlow, divhigh; } kd_node;
+typedef struct
 {
+    const float *pts;
+    long n;
+    int *vind;
+    kd_node *nodes;
+    int n_nodes, leaf_max;
+    float root_lo[3], root_hi[3];
+} kd_tree;
+
+static void kd_minmax(const kd_tree *t, const int *ind, int count, int e, float *mn, float *mx)
+{
+    *mn = *mx = t->pts[3 * ind[0] + e];
+    for (int i = 1; i < count; ++i)
+    {
+        const float v = t->pts[3 * ind[i] + e];
+        if (v < *mn) *mn = v;
+        if (v > *mx) *mx = v;
+    }
+}
+/* nanoflann.hpp:974-1010, unsigned IndexType semantics (the "right &&" guards) kept */
+static void kd_plane_split(const kd_tree *t, int *ind, unsigned count, int cutfeat, float cutval, unsigned *lim1, unsigned *lim2)
+{
+    unsigned left = 0, right = count - 1;
+    for (;;)
+    {
+        while (left <= right && t->pts[3 * ind[left] + cutfeat] < cutval) ++left;
+        while (right && left <= right && t->pts[3 * ind[right] + cutfeat] >= cutval) --right;
+        if (left > right || !right) break;
+        int tmp = ind[left]; ind[left] = ind[right]; ind[right] = tmp;
+        ++left; --right;
+    }
+    *lim1 = left;
+    right = count - 1;
+    for (;;)
+    {
+        while (left <= right && t->pts[3 * ind[left] + cutfeat] <= cutval) ++left;
+        while (right && left <= right && t->pts[3 * ind[right] + cutfeat] > cutval) --right;
+        if (left > right || !right) break;
+        int tmp = ind[left]; ind[left] = ind[right]; ind[right] = tmp;
+        ++left; --right;
+    }
+    *lim2 = left;
+}
+/* lo/hi: in = the loose box handed down by the parent, out = the tight box of the subtree (divideTree's bbox reference) */
+static int kd_divide(kd_tree *t, int left, int right, float *lo, float *hi)
+{
+    const int id = t->n_nodes++;
+    kd_node *node = &t->nodes[id];
+    node->left = left; node->right = right;
+    if (right - left <= t->leaf_max)
+    {
+        node->child1 = node->child2 = -1; node->divfeat = -1; node->divlow = node->divhigh = 0.0f;
+        for (int i = 0; i < 3; ++i) lo[i] = hi[i] = t->pts[3 * t->vind[left] + i];
+        for (int k = left + 1; k < right; ++k)
+            for (int i = 0; i < 3; ++i)
+            {
+                const float v = t->pts[3 * t->vind[k] + i];
+                if (lo[i] > v) lo[i] = v;
+                if (hi[i] < v) hi[i] = v;
+            }
+        return id;
+    }
+    /* middleSplit_ :916-963 */
+    int *ind = t->vind + left;
+    const unsigned count = (unsigned)(right - left);
+    const float eps = 0.00001f;
+    float max_span = hi[0] - lo[0];
+    for (int i = 1; i < 3; ++i) { const float span = hi[i] - lo[i]; if (span > max_span) max_span = span; }
+    float max_spread = -1.0f;
+    int cutfeat = 0;
+    for (int i = 0; i < 3; ++i)
+    {
+        const float span = hi[i] - lo[i];
+        if (span > (1 - eps) * max_span)
+        {
+            float mn, mx;
+            kd_minmax(t, ind, (int)count, i, &mn, &mx);
+            const float spread = mx - mn;
+            if (spread > max_spread) { cutfeat = i; max_spread = spread; }
+        }
+    }
+    const float split_val = (lo[cutfeat] + hi[cutfeat]) / 2;
+    float mn, mx, cutval;
+    kd_minmax(t, ind, (int)count, cutfeat, &mn, &mx);
+    if (split_val < mn) cutval = mn; else if (split_val > mx) cutval = mx; else cutval = split_val;
+    unsigned lim1, lim2, idx;
+    kd_plane_split(t, ind, count, cutfeat, cutval, &lim1, &lim2);
+    if (lim1 > count / 2) idx = lim1; else if (lim2 < count / 2) idx = lim2; else idx = count / 2;
+
+    float llo[3], lhi[3], rlo[3], rhi[3];
+    memcpy(llo, lo, sizeof llo); memcpy(lhi, hi, sizeof lhi); memcpy(rlo, lo, sizeof rlo); memcpy(rhi, hi, sizeof rhi);
+    lhi[cutfeat] = cutval;
+    const int c1 = kd_divide(t, left, left + (int)idx, llo, lhi);
+    rlo[cutfeat] = cutval;
+    const int c2 = kd_divide(t, left + (int)idx, right, rlo, rhi);
+    node = &t->nodes[id];
+    node->child1 = c1; node->child2 = c2; node->divfeat = cutfeat;
+    node->divlow = lhi[cutfeat]; node->divhigh = rlo[cutfeat];
+    for (int i = 0; i < 3; ++i) { lo[i] = llo[i] < rlo[i] ? llo[i] : rlo[i]; hi[i] = lhi[i] > rhi[i] ? lhi[i] : rhi[i]; }
+    return id;
+}
+static kd_tree *kd_build(const float *pts, long n, int leaf_max)
+{
+    kd_tree *t = (kd_tree *)calloc(1, sizeof *t);
+    t->pts = pts; t->n = n; t->leaf_max = leaf_max;
+    t->vind = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    t->nodes = (kd_node *)malloc(sizeof(kd_node) * (size_t)(2 * n + 1));
+    for (long i = 0; i < n; ++i) t->vind[i] = (int)i;
+    if (n == 0) return t;
+    /* computeBoundingBox :1324-1350 */
+    for (int i = 0; i < 3; ++i) t->root_lo[i] = t->root_hi[i] = pts[i];
+    for (long k = 1; k < n; ++k)
+        for (int i = 0; i < 3; ++i)
+        {
+            if (pts[3 * k + i] < t->root_lo[i]) t->root_lo[i] = pts[3 * k + i];
+            if (pts[3 * k + i] > t->root_hi[i]) t->root_hi[i] = pts[3 * k + i];
+        }
+    kd_divide(t, 0, (int)n, t->root_lo, t->root_hi);
+    return t;
+}
+static void kd_free(kd_tree *t) { free(t->vind); free(t->nodes); free(t); }
+
+/* result sets: mode 0 = KNNResultSet(capacity), mode 1 = RadiusResultSet(radius, max_neighbors) */
+typedef struct
+{
+    int mode, capacity, count;
+    float radius;
+    int *index;
+    float *dist;
+} kd_result;
+static float kd_worst(const kd_result *r) { return r->mode == 0 ? r->dist[r->capacity - 1] : r->radius; }
+static int kd_add(kd_result *r, float dist, int index)
+{
+    if (r->mode == 0)
+    {
+        int i;
+        for (i = r->count; i > 0; --i)
+        {
+            if (r->dist[i - 1] > dist)
+            {
+                if (i < r->capacity) { r->dist[i] = r->dist[i - 1]; r->index[i] = r->index[i - 1]; }
+            }
+            else break;
+        }
+        if (i < r->capacity) { r->dist[i] = dist; r->index[i] = index; }
+        if (r->count < r->capacity) r->count++;
+        return 1;
+    }
+    if (r->capacity > 0 && r->count >= r->capacity) return 0; /* the reference's max_neighbors stop, :253-255 */
+    if (dist < r->radius) { r->index[r->count] = index; r->dist[r->count] = dist; r->count++; }
+    return 1;
+}
+static int kd_search_level(const kd_tree *t, kd_result *r, const float *q, int node_id, float mindistsq, float *dists, float eps_error)
+{
+    const kd_node *node = &t->nodes[node_id];
+    if (node->child1 < 0)
+    {
+        const float worst = kd_worst(r);
+        for (int i = node->left; i < node->right; ++i)
+        {
+            const int index = t->vind[i];
+            float d = 0.0f;
+            for (int k = 0; k < 3; ++k) { const float diff = q[k] - t->pts[3 * index + k]; d += diff * diff; }
+            if (d < worst)
+                if (!kd_add(r, d, index)) return 0;
+        }
+        return 1;
+    }
+    const int idx = node->divfeat;
+    const float val = q[idx];
+    const float diff1 = val - node->divlow, diff2 = val - node->divhigh;
+    int best, other;
+    float cut_dist;
+    if ((diff1 + diff2) < 0) { best = node->child1; other = node->child2; cut_dist = (val - node->divhigh) * (val - node->divhigh); }
+    else { best = node->child2; other = node->child1; cut_dist = (val - node->divlow) * (val - node->divlow); }
+    if (!kd_search_level(t, r, q, best, mindistsq, dists, eps_error)) return 0;
+    const float dst = dists[idx];
+    mindistsq = mindistsq + cut_dist - dst;
+    dists[idx] = cut_dist;
+    if (mindistsq * eps_error <= kd_worst(r))
+        if (!kd_search_level(t, r, q, other, mindistsq, dists, eps_error)) return 0;
+    dists[idx] = dst;
+    return 1;
+}
+static void kd_find(const kd_tree *t, kd_result *r, const float *q, float eps)
+{
+    if (t->n == 0) return;
+    const float eps_error = 1 + eps;
+    float dists[3] = {0, 0, 0}, distsq = 0.0f;
+    for (int i = 0; i < 3; ++i)
+    {
+        if (q[i] < t->root_lo[i]) { dists[i] = (q[i] - t->root_lo[i]) * (q[i] - t->root_lo[i]); distsq += dists[i]; }
+        if (q[i] > t->root_hi[i]) { dists[i] = (q[i] - t->root_hi[i]) * (q[i] - t->root_hi[i]); distsq += dists[i]; }
+    }
+    kd_search_level(t, r, q, 0, distsq, dists, eps_error);
+}
+
+/* libstdc++ std::sort (bits/stl_algo.h: __introsort_loop, __move_median_to_first, __unguarded_partition,
+ * __final_insertion_sort, threshold 16) on (index, distance) pairs compared by distance only -- IndexDist_Sorter,
+ * nanoflann.hpp:206-214.  Not a stable sort: the order of equal distances is whatever this exact algorithm leaves.
+ * When the depth limit 2*floor(log2 n) runs out the range is heap-sorted (__partial_sort(first, last, last):
+ * __make_heap, __sort_heap over __adjust_heap / __push_heap, bits/stl_heap.h) -- reached about once per few thousand
+ * 250-element radius searches. */
+typedef struct { int index; float dist; } kd_pair;
+#define KD_LESS(a, b) ((a).dist < (b).dist)
+static void kd_swap(kd_pair *a, kd_pair *b) { kd_pair t = *a; *a = *b; *b = t; }
+static void kd_adjust_heap(kd_pair *first, long hole, long len, kd_pair value)
+{
+    const long top = hole;
+    long child = hole;
+    while (child < (len - 1) / 2)
+    {
+        child = 2 * (child + 1);
+        if (KD_LESS(first[child], first[child - 1])) child--;
+        first[hole] = first[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2)
+    {
+        child = 2 * (child + 1);
+        first[hole] = first[child - 1];
+        hole = child - 1;
+    }
+    long parent = (hole - 1) / 2;
+    while (hole > top && KD_LESS(first[parent], value))
+    {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+static void kd_heap_sort(kd_pair *first, kd_pair *last)
+{
+    const long len = last - first;
+    if (len >= 2)
+        for (long parent = (len - 2) / 2;; --parent)
+        {
+            kd_adjust_heap(first, parent, len, first[parent]);
+            if (parent == 0) break;
+        }
+    while (last - first > 1)
+    {
+        --last;
+        kd_pair value = *last;
+        *last = *first;
+        kd_adjust_heap(first, 0, last - first, value);
+    }
+}
+static int kd_introsort_loop(kd_pair *first, kd_pair *last, int depth_limit)
+{
+    while (last - first > 16)
+    {
+        if (depth_limit == 0) { kd_heap_sort(first, last); return 0; }
+        --depth_limit;
+        kd_pair *mid = first + (last - first) / 2, *a = first + 1, *b = mid, *c = last - 1;
+        if (KD_LESS(*a, *b))
+        {
+            if (KD_LESS(*b, *c)) kd_swap(first, b);
+            else if (KD_LESS(*a, *c)) kd_swap(first, c);
+            else kd_swap(first, a);
+        }
+        else if (KD_LESS(*a, *c)) kd_swap(first, a);
+        else if (KD_LESS(*b, *c)) kd_swap(first, c);
+        else kd_swap(first, b);
+        kd_pair *lo = first + 1, *hi = last;
+        for (;;)
+        {
+            while (KD_LESS(*lo, *first)) ++lo;
+            --hi;
+            while (KD_LESS(*first, *hi)) --hi;
+            if (!(lo < hi)) break;
+            kd_swap(lo, hi);
+            ++lo;
+        }
+        if (kd_introsort_loop(lo, last, depth_limit)) return -1;
+        last = lo;
+    }
+    return 0;
+}
+static void kd_unguarded_linear_insert(kd_pair *last)
+{
+    kd_pair val = *last, *next = last - 1;
+    while (KD_LESS(val, *next)) { *last = *next; last = next; --next; }
+    *last = val;
+}
+static void kd_insertion_sort(kd_pair *first, kd_pair *last)
+{
+    if (first == last) return;
+    for (kd_pair *i = first + 1; i != last; ++i)
+    {
+        if (KD_LESS(*i, *first))
+        {
+            kd_pair val = *i;
+            memmove(first + 1, first, sizeof(kd_pair) * (size_t)(i - first));
+            *first = val;
+        }
+        else kd_unguarded_linear_insert(i);
+    }
+}
+static int kd_std_sort(kd_pair *first, long n)
+{
+    if (n == 0) return 0;
+    int lg = 0;
+    for (long m = n; m > 1; m >>= 1) ++lg;
+    if (kd_introsort_loop(first, first + n, 2 * lg)) return -1;
+    if (n > 16)
+    {
+        kd_insertion_sort(first, first + 16);
+        for (kd_pair *i = first + 16; i != first + n; ++i) kd_unguarded_linear_insert(i);
+    }
+    else kd_insertion_sort(first, first + n);
+    return 0;
+}
+
+/* KDTree<3>::KnnSearch (mode 0, KDTree.h:176-195), RadiusSearch (mode 1, :125-143: the L2 "radius" is compared with
+ * SQUARED distances, at most (size_t)(max_result * 2.5) hits are collected in traversal order, sorted, cut to
+ * max_result) and KnnRadiusSearch (mode 2, :230-256).  idx/dist need room for max(k, (int)(k * 2.5)) entries. */
+static int kd_query(const kd_tree *t, const float *q, int mode, int k, float radius, int *idx, float *dist)
+{
+    kd_result r;
+    r.index = idx; r.dist = dist; r.count = 0; r.radius = radius;
+    if (mode == 1)
+    {
+        r.mode = 1; r.capacity = (int)(size_t)(k * 2.5);
+        kd_find(t, &r, q, 1e-8f);
+        kd_pair *tmp = (kd_pair *)malloc(sizeof(kd_pair) * (size_t)(r.count + 1));
+        for (int i = 0; i < r.count; ++i) { tmp[i].index = idx[i]; tmp[i].dist = dist[i]; }
+        if (kd_std_sort(tmp, r.count)) { free(tmp); return -1; }
+        int cnt = r.count > k ? k : r.count;
+        for (int i = 0; i < cnt; ++i) { idx[i] = tmp[i].index; dist[i] = tmp[i].dist; }
+        free(tmp);
+        return cnt;
+    }
+    r.mode = 0; r.capacity = k;
+    if (k > 0) dist[k - 1] = FLT_MAX;
+    kd_find(t, &r, q, 0.0f);
+    if (mode == 0) return r.count;
+    int in_radius = 0;
+    for (; in_radius != r.count; ++in_radius)
+        if (dist[in_radius] > radius) break;
+    return in_radius;
+}
+void orc_kdtree_search(const float *pts, long n, const float *queries, long nq, int mode, int k, float radius, long cap,
+                       int32_t *out_index, float *out_dist, int32_t *out_count)
+{
+    kd_tree *t = kd_build(pts, n, 10);
+    const int room = (k > (int)(k * 2.5) ? k : (int)(k * 2.5)) + 1;
 #pragma omp parallel
     {
-        float *bd = (float *)malloc(sizeof(float) * (knn + 1));
-        int *bi = (int *)malloc(sizeof(int) * (knn + 1));
+        int *idx = (int *)malloc(sizeof(int) * (size_t)room);
+        float *dist = (float *)malloc(sizeof(float) * (size_t)room);
+#pragma omp for schedule(dynamic, 64)
+        for (long q = 0; q < nq; ++q)
+        {
+            const int cnt = kd_query(t, queries + 3 * q, mode, k, radius, idx, dist);
+            out_count[q] = cnt;
+            for (long j = 0; j < cap; ++j)
+            {
+                out_index[q * cap + j] = j < cnt ? idx[j] : -1;
+                out_dist[q * cap + j] = j < cnt ? dist[j] : -1.0f;
+            }
+        }
+        free(idx); free(dist);
+    }
+    kd_free(t);
+}
+/* the built tree, for checking a device build: vind (n ints) and the nodes in pre-order, 5 ints + 2 floats each
+ * (left, right, child1, child2, divfeat; divlow, divhigh) with children renumbered in pre-order; returns node count */
+long orc_kdtree_dump(const float *pts, long n, int32_t *vind, int32_t *node_ints, float *node_floats, float *root_box)
+{
+    kd_tree *t = kd_build(pts, n, 10);
+    for (long i = 0; i < n; ++i) vind[i] = t->vind[i];
+    for (int i = 0; i < t->n_nodes; ++i)
+    {
+        const kd_node *nd = &t->nodes[i]; /* kd_divide numbers nodes in pre-order already */
+        node_ints[5 * i] = nd->left; node_ints[5 * i + 1] = nd->right; node_ints[5 * i + 2] = nd->child1;
+        node_ints[5 * i + 3] = nd->child2; node_ints[5 * i + 4] = nd->divfeat;
+        node_floats[2 * i] = nd->divlow; node_floats[2 * i + 1] = nd->divhigh;
+    }
+    for (int i = 0; i < 3; ++i) { root_box[i] = t->root_lo[i]; root_box[3 + i] = t->root_hi[i]; }
+    const long nn = t->n_nodes;
+    kd_free(t);
+    return nn;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * registration::ComputeFPFHFeature (src/Registration/3DFeature.cpp:7-131): pair descriptor, SPFH histograms over the
+ * radius-search neighbours (first hit skipped), distance-weighted sum.  Eigen's fixed-size dot/norm reduce as
+ * x + (y + z).  The angle goes through the double-precision ::atan2 (no <cmath> overload is visible unqualified).
+ * ------------------------------------------------------------------------------------------------------------------ */
+#ifndef M_PI
+#define M_PI 3.14159265358979323846 /* math.h value; hidden by -std=c11 */
+#endif
+static void cross3(const float *a, const float *b, float *o)
+{
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+static int fpfh_pair_bins(const float *ps, const float *ns, const float *pt, const float *nt, int *bins)
+{
+    float d[3] = {ps[0] - pt[0], ps[1] - pt[1], ps[2] - pt[2]};
+    const float distance = sqrtf(dot3(d, d));
+    float dir[3] = {(pt[0] - ps[0]) / distance, (pt[1] - ps[1]) / distance, (pt[2] - ps[2]) / distance};
+    float v[3], w[3], desc[3];
+    cross3(ns, dir, v);
+    if (sqrtf(dot3(v, v)) == 0) { desc[0] = desc[1] = desc[2] = 0.0f; }
+    else
+    {
+        cross3(ns, v, w);
+        float diff[3] = {pt[0] - ps[0], pt[1] - ps[1], pt[2] - ps[2]};
+        desc[1] = dot3(v, nt);
+        desc[2] = dot3(ns, diff) / distance;
+        desc[0] = (float)atan2(dot3(w, nt), dot3(ns, nt));
+    }
+    bins[0] = (int)floor(11 * (desc[0] + M_PI) / (2.0 * M_PI));
+    bins[1] = (int)floor(11 * (desc[1] + 1) / 2.0);
+    bins[2] = (int)floor(11 * (desc[2] + 1) / 2.0);
+    for (int k = 0; k < 3; ++k) { if (bins[k] > 10) bins[k] = 10; if (bins[k] < 0) bins[k] = 0; }
+    return 0;
+}
+int orc_fpfh(const float *pts, const float *normals, long n, int knn, float radius, float *features)
+{
+    kd_tree *t = kd_build(pts, n, 10);
+    const int room = (knn > (int)(knn * 2.5) ? knn : (int)(knn * 2.5)) + 1;
+    float *spfh = (float *)calloc((size_t)n * 33 + 1, sizeof(float));
+    int *nbr = (int *)malloc(sizeof(int) * (size_t)n * (size_t)(knn > 0 ? knn : 1));
+    int *nbr_count = (int *)calloc((size_t)n + 1, sizeof(int));
+    int failed = 0;
+#pragma omp parallel
+    {
+        int *idx = (int *)malloc(sizeof(int) * (size_t)room);
+        float *dist = (float *)malloc(sizeof(float) * (size_t)room);
 #pragma omp for schedule(dynamic, 64)
         for (long i = 0; i < n; ++i)
         {
-            int cnt = 0;
-            const float *q = pts + 3 * i;
-            for (long j = 0; j < n; ++j)
+            int points_num = kd_query(t, pts + 3 * i, 1, knn, radius, idx, dist);
+            if (points_num < 0) { failed = 1; continue; }
+            float *h = spfh + 33 * i;
+            if (points_num - 1 > 0)
             {
-                const float dx = q[0] - pts[3 * j], dy = q[1] - pts[3 * j + 1], dz = q[2] - pts[3 * j + 2];
-                const float d = (dx * dx + dy * dy) + dz * dz; /* L2_Simple_Adaptor: result += diff * diff, in order */
-                if (cnt == knn && !(d < bd[cnt - 1])) continue;
-                int k = cnt < knn ? cnt : knn - 1;
-                while (k > 0 && bd[k - 1] > d) { bd[k] = bd[k - 1]; bi[k] = bi[k - 1]; --k; }
-                bd[k] = d; bi[k] = (int)j;
-                if (cnt < knn) ++cnt;
+                if (points_num > knn) points_num = knn;
+                const double each = 100 / (points_num - 1);
+                nbr_count[i] = points_num - 1;
+                for (int j = 1; j != points_num; ++j)
+                {
+                    nbr[i * knn + j - 1] = idx[j];
+                    int bins[3];
+                    fpfh_pair_bins(pts + 3 * i, normals + 3 * i, pts + 3 * idx[j], normals + 3 * idx[j], bins);
+                    h[bins[0]] = (float)(h[bins[0]] + each);
+                    h[bins[1] + 11] = (float)(h[bins[1] + 11] + each);
+                    h[bins[2] + 22] = (float)(h[bins[2] + 22] + each);
+                }
             }
-            int in_radius = 0;
-            while (in_radius < cnt && !(bd[in_radius] > radius)) ++in_radius;
+        }
+        free(idx); free(dist);
+    }
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long i = 0; i < n; ++i)
+    {
+        double sum[3] = {0, 0, 0};
+        float *f = features + 33 * i;
+        for (int e = 0; e < 33; ++e) f[e] = 0.0f;
+        for (int j = 0; j < nbr_count[i]; ++j)
+        {
+            const int nb = nbr[i * knn + j];
+            float d[3] = {pts[3 * i] - pts[3 * nb], pts[3 * i + 1] - pts[3 * nb + 1], pts[3 * i + 2] - pts[3 * nb + 2]};
+            const float dist = sqrtf(dot3(d, d));
+            if (dist != 0.0)
+            {
+                const float w_d = 1 / dist;
+                const float *s = spfh + 33 * nb;
+                for (int e = 0; e < 33; ++e) f[e] = f[e] + w_d * s[e];
+                for (int b = 0; b < 3; ++b)
+                {
+                    float bs = 0.0f;
+                    for (int e = 0; e < 11; ++e) bs += s[11 * b + e]; /* integer-valued: exact in any order */
+                    sum[b] += bs;
+                }
+            }
+        }
+        for (int b = 0; b < 3; ++b)
+        {
+            const float scale = (float)(100.0 / sum[b]);
+            for (int e = 0; e < 11; ++e) f[11 * b + e] = f[11 * b + e] * scale;
+        }
+        for (int e = 0; e < 33; ++e) f[e] = f[e] + spfh[33 * i + e];
+    }
+    free(spfh); free(nbr); free(nbr_count);
+    kd_free(t);
+    return failed ? -1 : 0;
+}
+
+/* PointCloud::EstimateNormals (PointCloud.cpp:102-144): KnnRadiusSearch(knn, radius) in the kd-tree's own visiting order
+ * (ties included), then FitPlane */
+void orc_estimate_normals(const float *pts, long n, float radius, int knn, float *normals)
+{
+    kd_tree *t = kd_build(pts, n, 10);
+#pragma omp parallel
+    {
+        float *bd = (float *)malloc(sizeof(float) * (size_t)(knn + 1));
+        int *bi = (int *)malloc(sizeof(int) * (size_t)(knn + 1));
+#pragma omp for schedule(dynamic, 64)
+        for (long i = 0; i < n; ++i)
+        {
+            const int in_radius = kd_query(t, pts + 3 * i, 2, knn, radius, bi, bd);
             fit_plane_normal(pts, bi, in_radius, normals + 3 * i);
         }
         free(bd); free(bi);
     }
+    kd_free(t);
 }

@@ -126,6 +126,14 @@ long orc_downsample(const float *points, const float *colors, const float *norma
 /* PointCloud::EstimateNormals (PointCloud.cpp:102-144): knn nearest points within sqrt(radius), FitPlane, Eigen JacobiSVD */
 void orc_estimate_normals(const float *pts, long n, float radius, int knn, float *normals);
 
+/* geometry::KDTree<3> searches (KDTree.h:93-256 over the vendored nanoflann): mode 0 KnnSearch, 1 RadiusSearch, 2 KnnRadiusSearch;
+ * nq rows of `cap` entries, -1 padded */
+void orc_kdtree_search(const float *pts, long n, const float *queries, long nq, int mode, int k, float radius, long cap,
+                       int32_t *out_index, float *out_dist, int32_t *out_count);
+long orc_kdtree_dump(const float *pts, long n, int32_t *vind, int32_t *node_ints, float *node_floats, float *root_box);
+/* registration::ComputeFPFHFeature (3DFeature.cpp:83-131): n x 33 floats; -1 if std::sort's heap fallback would be needed */
+int orc_fpfh(const float *pts, const float *normals, long n, int knn, float radius, float *features);
+
 /* caller-side depth pre-filter: tool::ConvertDepthTo32F (ImageProcessing.cpp:68-91), tool::BilateralFilter (:64-67) */
 void orc_convert_depth_32f(const void *depth, int is_u16, long n, float depth_scale, float *out);
 void orc_bilateral_filter(const float *src, int w, int h, int d, double sigma_color, double sigma_space, float *dst);

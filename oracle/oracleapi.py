@@ -77,6 +77,11 @@ def lib():
     L.orc_clustering_simplify.argtypes = [c_p, c_p, c_p, c_p, c_p, c_f]
     L.orc_compute_normals.argtypes = [c_p, c_l, c_p, c_l, c_p]
     L.orc_estimate_normals.argtypes = [c_p, c_l, c_f, c_i, c_p]
+    L.orc_kdtree_search.argtypes = [c_p, c_l, c_p, c_l, c_i, c_i, c_f, c_l, c_p, c_p, c_p]
+    L.orc_kdtree_dump.restype = c_l
+    L.orc_kdtree_dump.argtypes = [c_p, c_l, c_p, c_p, c_p, c_p]
+    L.orc_fpfh.restype = c_i
+    L.orc_fpfh.argtypes = [c_p, c_p, c_l, c_i, c_f, c_p]
     L.orc_downsample.restype = c_l
     L.orc_downsample.argtypes = [c_p, c_p, c_p, c_l, c_f, c_p, c_p, c_p]
     L.orc_volume_transform.restype = c_p
@@ -413,4 +418,42 @@ def estimate_normals(points, radius=0.1, knn=30):
     pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
     out = np.zeros_like(pts)
     lib().orc_estimate_normals(_ptr(pts), len(pts), radius, knn, _ptr(out))
+    return out
+
+
+KD_KNN, KD_RADIUS, KD_KNN_RADIUS = 0, 1, 2
+
+
+def kdtree_search(points, queries, mode, k, radius=0.0):
+    """geometry::KDTree<3>::{KnnSearch, RadiusSearch, KnnRadiusSearch} -> (index [nq,k] -1 padded, dist, count)"""
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    qs = np.ascontiguousarray(queries, np.float32).reshape(-1, 3)
+    idx = np.zeros((len(qs), k), np.int32)
+    dist = np.zeros((len(qs), k), np.float32)
+    cnt = np.zeros(len(qs), np.int32)
+    lib().orc_kdtree_search(_ptr(pts), len(pts), _ptr(qs), len(qs), mode, k, radius, k, _ptr(idx), _ptr(dist), _ptr(cnt))
+    return idx, dist, cnt
+
+
+def kdtree_dump(points):
+    """the nanoflann tree over `points`: vind, nodes in pre-order (ints [m,5]: left,right,child1,child2,divfeat; floats
+    [m,2]: divlow,divhigh), root box (lo xyz, hi xyz)"""
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    n = len(pts)
+    vind = np.zeros(n, np.int32)
+    ni = np.zeros((2 * n + 1, 5), np.int32)
+    nf = np.zeros((2 * n + 1, 2), np.float32)
+    box = np.zeros(6, np.float32)
+    m = lib().orc_kdtree_dump(_ptr(pts), n, _ptr(vind), _ptr(ni), _ptr(nf), _ptr(box))
+    return vind, ni[:m].copy(), nf[:m].copy(), box
+
+
+def fpfh(points, normals, knn=100, radius=0.1):
+    """registration::ComputeFPFHFeature -> [n,33]"""
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    nrm = np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+    out = np.zeros((len(pts), 33), np.float32)
+    rc = lib().orc_fpfh(_ptr(pts), _ptr(nrm), len(pts), knn, radius, _ptr(out))
+    if rc != 0:
+        raise RuntimeError("orc_fpfh: std::sort heap fallback reached (not restated)")
     return out

@@ -27,6 +27,9 @@
 #include "Integration/Frustum.h"
 #include "Integration/MarchingCube.h"
 #include "Registration/ICP.h"
+#ifndef USING_FLOAT64
+#include "Registration/3DFeature.h"
+#endif
 
 using namespace one_piece;
 typedef geometry::scalar scalar;
@@ -527,6 +530,48 @@ double ref_estimate_normals(const float *xyz, long n, float radius, int knn, flo
     double dt = Now() - t0;
     for (long i = 0; i < n; ++i)
         for (int k = 0; k < 3; ++k) normals[3 * i + k] = pcd.normals[i](k);
+    return dt;
+}
+// geometry::KDTree<3>::KnnSearch / RadiusSearch (KDTree.h:93-196) on a tree built over `xyz`, queried with
+// `queries`: out_index/out_dist are nq rows of `cap` entries (-1 padded), out_count the entries returned
+void ref_kdtree_search(const float *xyz, long n, const float *queries, long nq, int mode, int k, float radius, long cap,
+                       int32_t *out_index, float *out_dist, int32_t *out_count)
+{
+    geometry::Point3List pts;
+    ToList(xyz, n, pts);
+    geometry::KDTree<> tree;
+    tree.BuildTree(pts);
+    for (long q = 0; q < nq; ++q)
+    {
+        std::vector<int> indices;
+        std::vector<float> dists;
+        geometry::Point3 query(queries[3 * q], queries[3 * q + 1], queries[3 * q + 2]);
+        if (mode == 0)
+            tree.KnnSearch(query, indices, dists, k, geometry::SearchParameter(1024));
+        else if (mode == 1)
+            tree.RadiusSearch(query, indices, dists, radius, (size_t)k, geometry::SearchParameter(1024));
+        else
+            tree.KnnRadiusSearch(query, indices, dists, k, radius, geometry::SearchParameter(1024));
+        out_count[q] = (int32_t)indices.size();
+        for (long j = 0; j < cap; ++j)
+        {
+            out_index[q * cap + j] = j < (long)indices.size() ? indices[j] : -1;
+            out_dist[q * cap + j] = j < (long)dists.size() ? dists[j] : -1.0f;
+        }
+    }
+}
+// registration::ComputeFPFHFeature (3DFeature.cpp:83-131): n rows of 33 floats
+double ref_fpfh(const float *xyz, const float *normals, long n, int knn, float radius, float *features)
+{
+    geometry::PointCloud pcd;
+    ToList(xyz, n, pcd.points);
+    ToList(normals, n, pcd.normals);
+    registration::FeatureSet fs;
+    double t0 = Now();
+    registration::ComputeFPFHFeature(pcd, fs, knn, radius);
+    double dt = Now() - t0;
+    for (long i = 0; i < n; ++i)
+        for (int k = 0; k < 33; ++k) features[33 * i + k] = fs[i](k);
     return dt;
 }
 #endif

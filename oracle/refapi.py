@@ -83,6 +83,9 @@ def lib(kind: str = "f32"):
         L.ref_load_from_depth.argtypes = [c_p, c_i, c_i, c_i] + [c_f] * 5 + [c_p]
         L.ref_downsample.restype = c_l
         L.ref_downsample.argtypes = [c_p, c_p, c_p, c_l, c_f, c_p, c_p, c_p]
+        L.ref_kdtree_search.argtypes = [c_p, c_l, c_p, c_l, c_i, c_i, c_f, c_l, c_p, c_p, c_p]
+        L.ref_fpfh.restype = c_d
+        L.ref_fpfh.argtypes = [c_p, c_p, c_l, c_i, c_f, c_p]
         L.ref_estimate_normals.restype = c_d
         L.ref_estimate_normals.argtypes = [c_p, c_l, c_f, c_i, c_p]
     L.ref_set_quiet(1)
@@ -417,3 +420,23 @@ def downsample(points, colors, normals, grid_len):
     on = None if nrm is None else np.zeros_like(pts)
     n = lib("f32").ref_downsample(_ptr(pts), _ptr(col), _ptr(nrm), len(pts), grid_len, _ptr(op), _ptr(oc), _ptr(on))
     return op[:n].copy(), None if oc is None else oc[:n].copy(), None if on is None else on[:n].copy()
+
+
+def kdtree_search(points, queries, mode, k, radius=0.0):
+    """geometry::KDTree<3> searches of the compiled reference (mode 0 Knn, 1 Radius, 2 KnnRadius)"""
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    qs = np.ascontiguousarray(queries, np.float32).reshape(-1, 3)
+    idx = np.zeros((len(qs), k), np.int32)
+    dist = np.zeros((len(qs), k), np.float32)
+    cnt = np.zeros(len(qs), np.int32)
+    lib("f32").ref_kdtree_search(_ptr(pts), len(pts), _ptr(qs), len(qs), mode, k, radius, k, _ptr(idx), _ptr(dist), _ptr(cnt))
+    return idx, dist, cnt
+
+
+def fpfh(points, normals, knn=100, radius=0.1):
+    """registration::ComputeFPFHFeature of the compiled reference -> ([n,33], seconds)"""
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    nrm = np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+    out = np.zeros((len(pts), 33), np.float32)
+    dt = lib("f32").ref_fpfh(_ptr(pts), _ptr(nrm), len(pts), knn, radius, _ptr(out))
+    return out, dt
