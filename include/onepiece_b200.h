@@ -284,9 +284,38 @@ int opb_icp_point_to_point(opb_icp *c, const float *src_xyz, size_t ns, const fl
  * included) whose SQUARED distance does not exceed `radius` (the reference's KnnRadiusSearch compares dist^2 with radius,
  * KDTree.h:248-254), geometry::FitPlane on them (Geometry.cpp:172-199: float mean and covariance, Eigen JacobiSVD, third
  * column of U, normalised); fewer than 3 points -> the zero vector.  Bit-identical to the reference when no two neighbours of
- * a point are at exactly the same distance; exact ties are ordered by index here and by k-d tree traversal there.
+ * a point are at exactly the same distance; exact ties are ordered by index here and by k-d tree traversal there
+ * (opb_kdtree_estimate_normals below follows the reference's order and is what the drop-ins call).
  * xyz / normals: 3 floats per point, host or device pointers; knn <= 64. */
 int opb_icp_estimate_normals(opb_icp *c, const float *xyz, size_t n, float radius, int knn, float *normals);
+/* ---- geometry::KDTree<3> with the reference's visiting order, and what the reference builds on it ----
+ * The reference's searches go through its vendored, modified nanoflann (src/Geometry/KDTree.h:60-262).  Which neighbours come
+ * back and in which order depends on the tree, not only on the distances: equal distances are ordered by the traversal, the
+ * radius search stops after (size_t)(2.5 k) hits in traversal order and sorts them with std::sort (unstable).  The float sums
+ * downstream depend on that order, so the device builds the same tree (nanoflann.hpp:843-1010, leaf size 10) and walks it the
+ * same way (:1354-1417); results are identical to the reference's, ties and early stops included. */
+typedef struct opb_kdtree opb_kdtree;
+int opb_kdtree_create(int device, opb_kdtree **out);
+void opb_kdtree_destroy(opb_kdtree *t);
+/* KDTree::BuildTree (KDTree.h:84-92): xyz = 3 floats per point (finite), host or device pointer; copied. */
+int opb_kdtree_build(opb_kdtree *t, const float *xyz, size_t n);
+/* mode 0: KnnSearch (KDTree.h:176-195), k <= 64.  mode 1: RadiusSearch(radius, max_result = k) (:125-143; `radius` is compared
+ * with SQUARED distances), k <= 409.  mode 2: KnnRadiusSearch(k, radius) (:230-256), k <= 64.  queries: 3 floats each; outputs
+ * are nq rows of k entries, padded with -1 behind out_count[q] results; host or device pointers. */
+int opb_kdtree_search(opb_kdtree *t, const float *queries, size_t nq, int mode, int k, float radius, int32_t *out_index,
+                      float *out_dist, int32_t *out_count);
+/* PointCloud::EstimateNormals(radius, knn) (PointCloud.cpp:102-144) over the tree's points; knn <= 64.  Bit-identical to the
+ * reference on every cloud, tied distances included. */
+int opb_kdtree_estimate_normals(opb_kdtree *t, float radius, int knn, float *normals);
+/* registration::ComputeFPFHFeature(pcd, features, knn = 100, radius = 0.1) (src/Registration/3DFeature.cpp:83-131) over the
+ * tree's points with the given normals: 33 floats per point.  Points without neighbours get NaN rows like the reference's
+ * (0 * inf).  The descriptor angle goes through a double atan2 rounded to float as in the reference; the device's atan2 may
+ * differ from glibc's in the last place of the DOUBLE, which survives the float rounding about once in 1e8 pairs. knn <= 256. */
+int opb_kdtree_fpfh(opb_kdtree *t, const float *normals, int knn, float radius, float *features33);
+/* test hook: the built tree (vind: n ints; nodes in allocation order, root = 0: left, right, child1, child2 (-1 = leaf), divfeat;
+ * divlow, divhigh); all output pointers NULL -> only n_nodes */
+int opb_kdtree_dump(opb_kdtree *t, int32_t *vind, int32_t *node_ints5, float *node_floats2, float root_box[6], size_t *n_nodes);
+
 /* One registration over several GPUs (no counterpart in the reference).  The source points are split
  * across the ranks, every rank holds the whole target; each iteration every rank reduces its share to the 30-scalar packet
  * (21 J^T J + 6 J^T r + 2 error + count) and the packets are summed across ranks inside the reduction kernel's last CTA through

@@ -141,6 +141,13 @@ SIGNATURES = {
     "opb_icp_comm_detach": (C.c_int, [_p]),
     "opb_icp_last_search_count": (C.c_int, [_p, C.POINTER(C.c_uint64)]),
     "opb_icp_estimate_normals": (C.c_int, [_p, _p, _sz, C.c_float, C.c_int, _p]),
+    "opb_kdtree_create": (C.c_int, [C.c_int, _p]),
+    "opb_kdtree_destroy": (None, [_p]),
+    "opb_kdtree_build": (C.c_int, [_p, _p, _sz]),
+    "opb_kdtree_search": (C.c_int, [_p, _p, _sz, C.c_int, C.c_int, C.c_float, _p, _p, _p]),
+    "opb_kdtree_estimate_normals": (C.c_int, [_p, C.c_float, C.c_int, _p]),
+    "opb_kdtree_fpfh": (C.c_int, [_p, _p, C.c_int, C.c_float, _p]),
+    "opb_kdtree_dump": (C.c_int, [_p, _p, _p, _p, _p, _p]),
     "opb_icp_last_launch_count": (C.c_int, [_p, C.POINTER(C.c_int)]),
     "opb_icp_last_search_trace": (C.c_int, [_p, _p, C.c_int]),
     "opb_icp_last_nn": (C.c_int, [_p, _p, _sz]),

@@ -85,8 +85,8 @@ void TriangleMesh::ComputeNormals()
 
 void PointCloud::EstimateNormals(float radius, int knn)
 {
-    static opb_icp *ws = nullptr; // callers are single-threaded; one search workspace per process
-    if (!ws && opb_icp_create(0, nullptr, &ws) != OPB_OK)
+    static opb_kdtree *ws = nullptr; // callers are single-threaded; one search workspace per process
+    if (!ws && opb_kdtree_create(0, &ws) != OPB_OK)
     {
         Report("EstimateNormals");
         std::exit(1); // no device: there is no CPU path
@@ -94,7 +94,12 @@ void PointCloud::EstimateNormals(float radius, int knn)
     std::cout << BLUE << "[EstimateNormals]::[INFO]::RadiusSearch " << knn << " nearest points, radius: " << radius << RESET << std::endl;
     std::vector<float> p, n(points.size() * 3);
     Flatten(points, p);
-    if (opb_icp_estimate_normals(ws, p.data(), points.size(), radius, knn, n.data()) != OPB_OK) { Report("EstimateNormals"); return; }
+    // the reference's own k-d tree and visiting order on the device: identical neighbours, identical order
+    if (opb_kdtree_build(ws, p.data(), points.size()) != OPB_OK || opb_kdtree_estimate_normals(ws, radius, knn, n.data()) != OPB_OK)
+    {
+        Report("EstimateNormals");
+        return;
+    }
     Unflatten(n.data(), points.size(), normals);
 }
 

@@ -1,0 +1,1006 @@
+// geometry::KDTree<3> on the device, with the reference's exact visiting order, and what the reference builds on it:
+// PointCloud::EstimateNormals and registration::ComputeFPFHFeature.
+//
+// The reference searches through a (locally modified) nanoflann.  Which neighbours come back, and in which order, is not
+// a function of the distances alone: equal distances are ordered by the tree traversal, the radius search stops after
+// (size_t)(2.5 k) hits IN TRAVERSAL ORDER (with DenseSlam's own parameters that is the normal case, not a corner), and the
+// hits are then ordered by libstdc++'s unstable std::sort.  The float sums downstream (FitPlane's covariance, the FPFH
+// weighted histogram sum) depend on that order, so a bit-identical result needs the same tree and the same walk:
+//
+//   build     nanoflann.hpp:843-1010 (computeMinMax, divideTree, middleSplit_, planeSplit), leaf size 10 (KDTree.h:74)
+//             level-synchronous: one CTA per node, min/max by block reduction, the two Hoare partition passes of planeSplit
+//             reproduced exactly in parallel -- the k-th out-of-place element from the left always meets the k-th from the
+//             right, so ranks from a block scan give the same permutation as the sequential pointer walk
+//   search    nanoflann.hpp:1012-1028,1228-1295,1354-1417 (computeInitialDistances, searchLevel) as an explicit-stack walk,
+//             one thread per query; KNNResultSet (:150-204) in shared memory, RadiusResultSet with the reference's
+//             max_neighbors stop (:216-262) in a global scratch; std::sort restated (introsort, median of three, threshold
+//             16, heap-sort fallback at depth 2 log2 n, final insertion sort: bits/stl_algo.h, bits/stl_heap.h)
+//   users     KDTree.h:93-256 (KnnSearch, RadiusSearch, KnnRadiusSearch); PointCloud.cpp:102-144; 3DFeature.cpp:7-131
+//
+// All float arithmetic that decides a comparison uses the non-contracting intrinsics in the reference's operation order.
+#include <cfloat>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/onepiece_b200.h"
+#include "opb_common.cuh"
+#include "opb_fitplane.cuh"
+
+namespace opb
+{
+constexpr int kLeafMax = 10;
+constexpr int kBuildThreads = 256;
+constexpr int kBuildWarps = kBuildThreads / 32;
+constexpr int kMaxDepth = 64;
+constexpr int kQueryThreads = 128;
+constexpr int kKnnCap = 64;       // k of the shared-memory k-nearest list
+constexpr int kRadiusCapMax = 1024; // (int)(2.5 k) of the radius search
+constexpr int kQueryBatch = 32768;
+
+struct KdNode
+{
+    int left, right, child1, child2, divfeat;
+    float divlow, divhigh;
+    int level;
+};
+struct KdBuildCtl
+{
+    int n_nodes, queue_count[2], max_level;
+    float root_lo[3], root_hi[3];
+};
+struct KdView
+{
+    const float *pts;
+    const int *vind;
+    const KdNode *nodes;
+    float root_lo[3], root_hi[3];
+    int n;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// build
+// ---------------------------------------------------------------------------------------------------------
+template <class T, class Op>
+__device__ __forceinline__ T block_reduce(T v, Op op, T *sh)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    T r = sh[0];
+#pragma unroll
+    for (int w = 1; w < kBuildWarps; ++w) r = op(r, sh[w]);
+    return r;
+}
+__device__ __forceinline__ int block_exscan(int v, int *sh, int &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();
+    if (lane == 31) sh[warp] = incl;
+    __syncthreads();
+    int base = 0;
+    total = 0;
+#pragma unroll
+    for (int w = 0; w < kBuildWarps; ++w)
+    {
+        if (w < warp) base += sh[w];
+        total += sh[w];
+    }
+    return base + incl - v;
+}
+// One Hoare pass of planeSplit (nanoflann.hpp:978-991 / :996-1008) over [begin, end): afterwards every element with `pred`
+// sits below `boundary` (= begin + their count).  LE selects the second pass's predicate (<= cutval) over the first (<).
+template <bool LE>
+__device__ __forceinline__ void partition_pass(int *ind, float *key, int *pos, int begin, int end, int boundary, float cutval, int *sh)
+{
+    const int len = end - begin;
+    const int seg = (len + kBuildThreads - 1) / kBuildThreads;
+    const int a = min(begin + (int)threadIdx.x * seg, end), b = min(a + seg, end);
+    int cl = 0, cr = 0;
+    for (int i = a; i < b; ++i)
+    {
+        const bool p = LE ? key[i] <= cutval : key[i] < cutval;
+        cl += (i < boundary && !p);
+        cr += (i >= boundary && p);
+    }
+    int m, m2;
+    int bl = block_exscan(cl, sh, m);
+    int br = block_exscan(cr, sh, m2);
+    int *pos_l = pos + begin, *pos_r = pos + begin + (len + 1) / 2; // m <= len / 2: the two lists cannot overlap
+    for (int i = a; i < b; ++i)
+    {
+        const bool p = LE ? key[i] <= cutval : key[i] < cutval;
+        if (i < boundary && !p) pos_l[bl++] = i;
+        if (i >= boundary && p) pos_r[br++] = i;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < m; k += kBuildThreads)
+    {
+        const int i = pos_l[k], j = pos_r[m - 1 - k];
+        const int ti = ind[i]; ind[i] = ind[j]; ind[j] = ti;
+        const float tk = key[i]; key[i] = key[j]; key[j] = tk;
+    }
+    __syncthreads();
+}
+__global__ void kd_iota_kernel(int *vind, int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) vind[i] = i;
+}
+// divideTree (nanoflann.hpp:864-914) for one node per CTA; boxes = the LOOSE box handed down by the parent (it, not the tight
+// one, picks the cut dimension and the middle), 6 floats per node
+__global__ void __launch_bounds__(kBuildThreads) kd_split_kernel(const float *__restrict__ pts, int *vind, float *key, int *pos, KdNode *nodes,
+                                                                 float *boxes, const int *__restrict__ queue_in, int *queue_out, KdBuildCtl *ctl,
+                                                                 int out_slot)
+{
+    __shared__ float shf[kBuildWarps];
+    __shared__ int shi[kBuildWarps];
+    const int id = queue_in[blockIdx.x];
+    const int left = nodes[id].left, right = nodes[id].right, count = right - left, level = nodes[id].level;
+    int *ind = vind + left;
+    float *ky = key + left;
+    // computeMinMax of all three coordinates
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = threadIdx.x; i < count; i += kBuildThreads)
+    {
+        const int j = ind[i];
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+        {
+            const float v = pts[3 * j + d];
+            mn[d] = fminf(mn[d], v);
+            mx[d] = fmaxf(mx[d], v);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+    {
+        mn[d] = block_reduce(mn[d], [](float x, float y) { return fminf(x, y); }, shf);
+        mx[d] = block_reduce(mx[d], [](float x, float y) { return fmaxf(x, y); }, shf);
+    }
+    float lo[3], hi[3];
+    if (id == 0)
+    {
+        // computeBoundingBox (:1324-1350): the root's box is the tight one
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { lo[d] = mn[d]; hi[d] = mx[d]; }
+        if (threadIdx.x == 0)
+            for (int d = 0; d < 3; ++d) { ctl->root_lo[d] = mn[d]; ctl->root_hi[d] = mx[d]; }
+    }
+    else
+    {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { lo[d] = boxes[6 * id + d]; hi[d] = boxes[6 * id + 3 + d]; }
+    }
+    if (count <= kLeafMax) return; // only the root can arrive here as a leaf
+    // middleSplit_ (:916-963)
+    float max_span = fsub(hi[0], lo[0]);
+#pragma unroll
+    for (int d = 1; d < 3; ++d)
+    {
+        const float span = fsub(hi[d], lo[d]);
+        if (span > max_span) max_span = span;
+    }
+    const float thresh = fmul(fsub(1.0f, 0.00001f), max_span);
+    float max_spread = -1.0f;
+    int cutfeat = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+    {
+        const float span = fsub(hi[d], lo[d]);
+        if (span > thresh)
+        {
+            const float spread = fsub(mx[d], mn[d]);
+            if (spread > max_spread) { cutfeat = d; max_spread = spread; }
+        }
+    }
+    const float lo_c = cutfeat == 0 ? lo[0] : cutfeat == 1 ? lo[1] : lo[2];
+    const float hi_c = cutfeat == 0 ? hi[0] : cutfeat == 1 ? hi[1] : hi[2];
+    const float mn_c = cutfeat == 0 ? mn[0] : cutfeat == 1 ? mn[1] : mn[2];
+    const float mx_c = cutfeat == 0 ? mx[0] : cutfeat == 1 ? mx[1] : mx[2];
+    const float split_val = fdiv(fadd(lo_c, hi_c), 2.0f);
+    const float cutval = split_val < mn_c ? mn_c : split_val > mx_c ? mx_c : split_val;
+    // planeSplit (:974-1010): lim1 = #(< cutval), lim2 = lim1 + #(== cutval)
+    int cl = 0, ce = 0;
+    for (int i = threadIdx.x; i < count; i += kBuildThreads)
+    {
+        const float v = pts[3 * ind[i] + cutfeat];
+        ky[i] = v;
+        cl += v < cutval;
+        ce += v == cutval;
+    }
+    const int lim1 = block_reduce(cl, [](int x, int y) { return x + y; }, shi);
+    const int lim2 = lim1 + block_reduce(ce, [](int x, int y) { return x + y; }, shi);
+    partition_pass<false>(ind, ky, pos + left, 0, count, lim1, cutval, shi);
+    partition_pass<true>(ind, ky, pos + left, lim1, count, lim2, cutval, shi);
+    const int half = count / 2;
+    const int idx = lim1 > half ? lim1 : lim2 < half ? lim2 : half;
+    // the children's tight extent along the cut: divlow = left_bbox[cutfeat].high, divhigh = right_bbox[cutfeat].low (:904-905)
+    float dl = -FLT_MAX, dh = FLT_MAX;
+    for (int i = threadIdx.x; i < count; i += kBuildThreads)
+    {
+        const float v = ky[i];
+        if (i < idx) dl = fmaxf(dl, v);
+        else dh = fminf(dh, v);
+    }
+    dl = block_reduce(dl, [](float x, float y) { return fmaxf(x, y); }, shf);
+    dh = block_reduce(dh, [](float x, float y) { return fminf(x, y); }, shf);
+    if (threadIdx.x == 0)
+    {
+        const int c = atomicAdd(&ctl->n_nodes, 2);
+        KdNode a, b;
+        a.left = left; a.right = left + idx; a.child1 = a.child2 = -1; a.divfeat = -1; a.divlow = a.divhigh = 0.0f; a.level = level + 1;
+        b = a;
+        b.left = left + idx; b.right = right;
+        nodes[c] = a;
+        nodes[c + 1] = b;
+        for (int d = 0; d < 3; ++d)
+        {
+            boxes[6 * c + d] = lo[d]; boxes[6 * c + 3 + d] = d == cutfeat ? cutval : hi[d];
+            boxes[6 * (c + 1) + d] = d == cutfeat ? cutval : lo[d]; boxes[6 * (c + 1) + 3 + d] = hi[d];
+        }
+        nodes[id].child1 = c; nodes[id].child2 = c + 1; nodes[id].divfeat = cutfeat;
+        nodes[id].divlow = dl; nodes[id].divhigh = dh;
+        if (idx > kLeafMax) queue_out[atomicAdd(&ctl->queue_count[out_slot], 1)] = c;
+        if (count - idx > kLeafMax) queue_out[atomicAdd(&ctl->queue_count[out_slot], 1)] = c + 1;
+        atomicMax(&ctl->max_level, level + 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// search
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float pick3(const float *v, int i) { return i == 0 ? v[0] : i == 1 ? v[1] : v[2]; }
+__device__ __forceinline__ void put3(float *v, int i, float x)
+{
+    if (i == 0) v[0] = x;
+    else if (i == 1) v[1] = x;
+    else v[2] = x;
+}
+// L2_Simple_Adaptor::evalMetric (:438-446): result += diff * diff, dimension by dimension
+__device__ __forceinline__ float kd_dist2(const float *q, const float *__restrict__ pts, int j)
+{
+    const float dx = fsub(q[0], pts[3 * j]), dy = fsub(q[1], pts[3 * j + 1]), dz = fsub(q[2], pts[3 * j + 2]);
+    return fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+}
+// KNNResultSet (:150-204): a new point goes BEHIND the stored points of equal distance
+struct KnnSet
+{
+    float *d;
+    int *i;
+    int count, capacity;
+    __device__ __forceinline__ float &dist(int e) { return d[e * kQueryThreads]; }
+    __device__ __forceinline__ int &index(int e) { return i[e * kQueryThreads]; }
+    __device__ __forceinline__ void init(float *smem, int k)
+    {
+        d = smem + threadIdx.x;
+        i = reinterpret_cast<int *>(smem + k * kQueryThreads) + threadIdx.x;
+        count = 0;
+        capacity = k;
+        dist(k - 1) = FLT_MAX;
+    }
+    __device__ __forceinline__ float worst() { return dist(capacity - 1); }
+    __device__ __forceinline__ bool add(float dd, int idx)
+    {
+        int e;
+        for (e = count; e > 0; --e)
+        {
+            if (dist(e - 1) > dd)
+            {
+                if (e < capacity) { dist(e) = dist(e - 1); index(e) = index(e - 1); }
+            }
+            else break;
+        }
+        if (e < capacity) { dist(e) = dd; index(e) = idx; }
+        if (count < capacity) count++;
+        return true;
+    }
+};
+// RadiusResultSet with the reference's early stop (:216-262); entries live in a global scratch, entry e of query slot s at
+// [e * stride + s]
+struct RadiusSet
+{
+    float *d;
+    int *i;
+    int stride, count, capacity;
+    float radius;
+    __device__ __forceinline__ float &dist(int e) { return d[(size_t)e * stride]; }
+    __device__ __forceinline__ int &index(int e) { return i[(size_t)e * stride]; }
+    __device__ __forceinline__ float worst() { return radius; }
+    __device__ __forceinline__ bool add(float dd, int idx)
+    {
+        if (capacity > 0 && count >= capacity) return false;
+        if (dd < radius) { dist(count) = dd; index(count) = idx; ++count; }
+        return true;
+    }
+};
+struct KdFrame
+{
+    int node, other, idx_stage;
+    float mind, dst, cut;
+};
+// findNeighbors + searchLevel (:1228-1248, :1354-1417); false when the result set asked to stop
+template <class ResultSet>
+__device__ bool kd_find(const KdView &t, ResultSet &rs, const float *q, float eps_error)
+{
+    if (t.n == 0) return true;
+    float dists[3] = {0.0f, 0.0f, 0.0f};
+    float distsq = 0.0f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+    {
+        if (q[d] < t.root_lo[d]) { const float x = fsub(q[d], t.root_lo[d]); dists[d] = fmul(x, x); distsq = fadd(distsq, dists[d]); }
+        if (q[d] > t.root_hi[d]) { const float x = fsub(q[d], t.root_hi[d]); dists[d] = fmul(x, x); distsq = fadd(distsq, dists[d]); }
+    }
+    KdFrame st[kMaxDepth];
+    int sp = 0;
+    st[0].node = 0; st[0].idx_stage = 0; st[0].mind = distsq;
+    while (sp >= 0)
+    {
+        KdFrame &f = st[sp];
+        const int stage = f.idx_stage & 3, idx = f.idx_stage >> 2;
+        if (stage == 0)
+        {
+            const KdNode nd = t.nodes[f.node];
+            if (nd.child1 < 0)
+            {
+                const float worst = rs.worst();
+                for (int i = nd.left; i < nd.right; ++i)
+                {
+                    const int index = t.vind[i];
+                    const float d = kd_dist2(q, t.pts, index);
+                    if (d < worst)
+                        if (!rs.add(d, index)) return false;
+                }
+                --sp;
+                continue;
+            }
+            const int cf = nd.divfeat;
+            const float val = pick3(q, cf);
+            const float diff1 = fsub(val, nd.divlow), diff2 = fsub(val, nd.divhigh);
+            int best;
+            if (fadd(diff1, diff2) < 0.0f) { best = nd.child1; f.other = nd.child2; f.cut = fmul(diff2, diff2); }
+            else { best = nd.child2; f.other = nd.child1; f.cut = fmul(diff1, diff1); }
+            f.idx_stage = (cf << 2) | 1;
+            const float mind = f.mind;
+            if (sp + 1 >= kMaxDepth) return true; // the host refuses trees deeper than kMaxDepth - 2 before any search
+            ++sp;
+            st[sp].node = best; st[sp].idx_stage = 0; st[sp].mind = mind;
+        }
+        else if (stage == 1)
+        {
+            const float dst = pick3(dists, idx);
+            const float mind = fsub(fadd(f.mind, f.cut), dst);
+            put3(dists, idx, f.cut);
+            f.dst = dst;
+            if (fmul(mind, eps_error) <= rs.worst())
+            {
+                f.idx_stage = (idx << 2) | 2;
+                const int other = f.other;
+                ++sp;
+                st[sp].node = other; st[sp].idx_stage = 0; st[sp].mind = mind;
+            }
+            else
+            {
+                put3(dists, idx, dst);
+                --sp;
+            }
+        }
+        else
+        {
+            put3(dists, idx, f.dst);
+            --sp;
+        }
+    }
+    return true;
+}
+
+// libstdc++ std::sort over the radius hits, compared by distance only (IndexDist_Sorter, nanoflann.hpp:206-214)
+struct HitPair { float d; int i; };
+struct HitArray
+{
+    float *d;
+    int *i;
+    int stride;
+    __device__ __forceinline__ HitPair get(int e) const { HitPair p; p.d = d[(size_t)e * stride]; p.i = i[(size_t)e * stride]; return p; }
+    __device__ __forceinline__ float key(int e) const { return d[(size_t)e * stride]; }
+    __device__ __forceinline__ void set(int e, HitPair p) const { d[(size_t)e * stride] = p.d; i[(size_t)e * stride] = p.i; }
+    __device__ __forceinline__ void swap(int a, int b) const { const HitPair x = get(a), y = get(b); set(a, y); set(b, x); }
+};
+// __adjust_heap + __push_heap (bits/stl_heap.h) relative to `first`
+__device__ void hit_adjust_heap(const HitArray &A, int first, int hole, int len, HitPair value)
+{
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2)
+    {
+        child = 2 * (child + 1);
+        if (A.key(first + child) < A.key(first + child - 1)) child--;
+        A.set(first + hole, A.get(first + child));
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2)
+    {
+        child = 2 * (child + 1);
+        A.set(first + hole, A.get(first + child - 1));
+        hole = child - 1;
+    }
+    int parent = (hole - 1) / 2;
+    while (hole > top && A.key(first + parent) < value.d)
+    {
+        A.set(first + hole, A.get(first + parent));
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    A.set(first + hole, value);
+}
+__device__ void hit_heap_sort(const HitArray &A, int first, int last)
+{
+    const int len = last - first;
+    if (len >= 2)
+        for (int parent = (len - 2) / 2;; --parent)
+        {
+            hit_adjust_heap(A, first, parent, len, A.get(first + parent));
+            if (parent == 0) break;
+        }
+    while (last - first > 1)
+    {
+        --last;
+        const HitPair value = A.get(last);
+        A.set(last, A.get(first));
+        hit_adjust_heap(A, first, 0, last - first, value);
+    }
+}
+__device__ __forceinline__ void hit_unguarded_linear_insert(const HitArray &A, int last)
+{
+    const HitPair val = A.get(last);
+    int next = last - 1;
+    while (val.d < A.key(next))
+    {
+        A.set(last, A.get(next));
+        last = next;
+        --next;
+    }
+    A.set(last, val);
+}
+__device__ void hit_insertion_sort(const HitArray &A, int first, int last)
+{
+    if (first == last) return;
+    for (int i = first + 1; i != last; ++i)
+    {
+        if (A.key(i) < A.key(first))
+        {
+            const HitPair val = A.get(i);
+            for (int k = i; k > first; --k) A.set(k, A.get(k - 1)); // move_backward
+            A.set(first, val);
+        }
+        else hit_unguarded_linear_insert(A, i);
+    }
+}
+__device__ void hit_std_sort(const HitArray &A, int n)
+{
+    if (n == 0) return;
+    int lg = 0;
+    for (int m = n; m > 1; m >>= 1) ++lg;
+    // __introsort_loop: the two halves of a partition are independent, so a work stack visits them in any order; both
+    // inherit the decremented depth budget
+    int stk_first[48], stk_last[48], stk_depth[48];
+    int sp = 0;
+    stk_first[0] = 0; stk_last[0] = n; stk_depth[0] = 2 * lg;
+    while (sp >= 0)
+    {
+        int first = stk_first[sp], last = stk_last[sp], depth = stk_depth[sp];
+        --sp;
+        while (last - first > 16)
+        {
+            if (depth == 0) { hit_heap_sort(A, first, last); break; }
+            --depth;
+            // __move_median_to_first(first, first + 1, mid, last - 1)
+            const int a = first + 1, b = first + (last - first) / 2, c = last - 1;
+            const float ka = A.key(a), kb = A.key(b), kc = A.key(c);
+            if (ka < kb)
+            {
+                if (kb < kc) A.swap(first, b);
+                else if (ka < kc) A.swap(first, c);
+                else A.swap(first, a);
+            }
+            else if (ka < kc) A.swap(first, a);
+            else if (kb < kc) A.swap(first, c);
+            else A.swap(first, b);
+            // __unguarded_partition(first + 1, last, pivot = *first)
+            const float pivot = A.key(first);
+            int lo = first + 1, hi = last;
+            for (;;)
+            {
+                while (A.key(lo) < pivot) ++lo;
+                --hi;
+                while (pivot < A.key(hi)) --hi;
+                if (!(lo < hi)) break;
+                A.swap(lo, hi);
+                ++lo;
+            }
+            if (sp + 1 < 48) { ++sp; stk_first[sp] = lo; stk_last[sp] = last; stk_depth[sp] = depth; }
+            last = lo;
+        }
+    }
+    // __final_insertion_sort
+    if (n > 16)
+    {
+        hit_insertion_sort(A, 0, 16);
+        for (int i = 16; i != n; ++i) hit_unguarded_linear_insert(A, i);
+    }
+    else hit_insertion_sort(A, 0, n);
+}
+
+// KnnSearch (mode 0) / KnnRadiusSearch (mode 2), KDTree.h:176-195,230-256: rows of k entries, -1 padded
+__global__ void __launch_bounds__(kQueryThreads) kd_knn_kernel(KdView t, const float *__restrict__ queries, int nq, int mode, int k, float radius,
+                                                               int *__restrict__ out_index, float *__restrict__ out_dist, int *__restrict__ out_count)
+{
+    extern __shared__ float knn_smem[];
+    for (int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < nq; qi += gridDim.x * blockDim.x)
+    {
+        const float q[3] = {queries[3 * qi], queries[3 * qi + 1], queries[3 * qi + 2]};
+        KnnSet rs;
+        rs.init(knn_smem, k);
+        kd_find(t, rs, q, 1.0f);
+        int cnt = rs.count;
+        if (mode == 2)
+        {
+            int in_radius = 0;
+            for (; in_radius != cnt; ++in_radius)
+                if (rs.dist(in_radius) > radius) break;
+            cnt = in_radius;
+        }
+        out_count[qi] = cnt;
+        for (int e = 0; e < k; ++e)
+        {
+            out_index[(size_t)qi * k + e] = e < cnt ? rs.index(e) : -1;
+            out_dist[(size_t)qi * k + e] = e < cnt ? rs.dist(e) : -1.0f;
+        }
+    }
+}
+// RadiusSearch (KDTree.h:125-143): up to `cap` hits with dist^2 < radius in traversal order, std::sort, the first k kept.
+// Queries q0 .. q0 + nq of one batch; scratch holds cap x stride (distance, index) entries.
+__global__ void __launch_bounds__(kQueryThreads) kd_radius_kernel(KdView t, const float *__restrict__ queries, int q0, int nq, int k, int cap, float radius,
+                                                                  float *scratch_d, int *scratch_i, int stride, int *__restrict__ out_index,
+                                                                  float *__restrict__ out_dist, int *__restrict__ out_count)
+{
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nq; s += gridDim.x * blockDim.x)
+    {
+        const int qi = q0 + s;
+        const float q[3] = {queries[3 * qi], queries[3 * qi + 1], queries[3 * qi + 2]};
+        RadiusSet rs;
+        rs.d = scratch_d + s; rs.i = scratch_i + s; rs.stride = stride; rs.count = 0; rs.capacity = cap; rs.radius = radius;
+        kd_find(t, rs, q, 1.0f + 1e-8f); // SearchParameter's eps (KDTree.h:19): 1 + 1e-8 rounds to 1 in float, like the reference's
+        HitArray A;
+        A.d = rs.d; A.i = rs.i; A.stride = stride;
+        hit_std_sort(A, rs.count);
+        const int cnt = rs.count > k ? k : rs.count;
+        out_count[qi] = cnt;
+        for (int e = 0; e < k; ++e)
+        {
+            out_index[(size_t)qi * k + e] = e < cnt ? rs.index(e) : -1;
+            if (out_dist) out_dist[(size_t)qi * k + e] = e < cnt ? rs.dist(e) : -1.0f;
+        }
+    }
+}
+// PointCloud::EstimateNormals (PointCloud.cpp:102-144): KnnRadiusSearch(knn, radius) around every point of the tree, FitPlane
+__global__ void __launch_bounds__(kQueryThreads) kd_normals_kernel(KdView t, int k, float radius, float *__restrict__ normals)
+{
+    extern __shared__ float knn_smem[];
+    for (int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < t.n; qi += gridDim.x * blockDim.x)
+    {
+        const float q[3] = {t.pts[3 * qi], t.pts[3 * qi + 1], t.pts[3 * qi + 2]};
+        KnnSet rs;
+        rs.init(knn_smem, k);
+        kd_find(t, rs, q, 1.0f);
+        int in_radius = 0;
+        for (; in_radius != rs.count; ++in_radius)
+            if (rs.dist(in_radius) > radius) break;
+        float nrm[3];
+        fit_plane_normal(t.pts, in_radius, [&](int e) { return rs.index(e); }, nrm);
+        normals[3 * qi] = nrm[0]; normals[3 * qi + 1] = nrm[1]; normals[3 * qi + 2] = nrm[2];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// FPFH (3DFeature.cpp:7-131)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dot3e(const float *a, const float *b) { return fadd(fmul(a[0], b[0]), fadd(fmul(a[1], b[1]), fmul(a[2], b[2]))); } // Eigen: x + (y + z)
+__device__ __forceinline__ void cross3e(const float *a, const float *b, float *o)
+{
+    o[0] = fsub(fmul(a[1], b[2]), fmul(a[2], b[1]));
+    o[1] = fsub(fmul(a[2], b[0]), fmul(a[0], b[2]));
+    o[2] = fsub(fmul(a[0], b[1]), fmul(a[1], b[0]));
+}
+// ComputePairDescriptor (:7-25) reduced to the three histogram bins ComputeSPFH takes from it (:63-75)
+__device__ __forceinline__ void fpfh_pair_bins(const float *ps, const float *ns, const float *pt, const float *nt, int *bins)
+{
+    const float d[3] = {fsub(ps[0], pt[0]), fsub(ps[1], pt[1]), fsub(ps[2], pt[2])};
+    const float distance = __fsqrt_rn(dot3e(d, d));
+    const float diff[3] = {fsub(pt[0], ps[0]), fsub(pt[1], ps[1]), fsub(pt[2], ps[2])};
+    const float dir[3] = {fdiv(diff[0], distance), fdiv(diff[1], distance), fdiv(diff[2], distance)};
+    float v[3], w[3], desc[3] = {0.0f, 0.0f, 0.0f};
+    cross3e(ns, dir, v);
+    if (__fsqrt_rn(dot3e(v, v)) != 0.0f)
+    {
+        cross3e(ns, v, w);
+        desc[1] = dot3e(v, nt);
+        desc[2] = fdiv(dot3e(ns, diff), distance);
+        // the reference's unqualified atan2 is the double one; its float rounding is what reaches the histogram
+        desc[0] = (float)atan2((double)dot3e(w, nt), (double)dot3e(ns, nt));
+    }
+    const double kPi = 3.14159265358979323846;
+    bins[0] = (int)floor(11 * ((double)desc[0] + kPi) / (2.0 * kPi));
+    bins[1] = (int)floor((double)fmul(11.0f, fadd(desc[1], 1.0f)) / 2.0);
+    bins[2] = (int)floor((double)fmul(11.0f, fadd(desc[2], 1.0f)) / 2.0);
+#pragma unroll
+    for (int b = 0; b < 3; ++b) bins[b] = bins[b] > 10 ? 10 : bins[b] < 0 ? 0 : bins[b];
+}
+// ComputeSPFH (:28-81) after the radius search: nbr rows hold the search result (first hit = the point itself, skipped).
+// Every pair adds the same integer 100 / (points_num - 1) to one bin per third, so a bin is count x increment exactly.
+__global__ void __launch_bounds__(kQueryThreads) fpfh_spfh_kernel(const float *__restrict__ pts, const float *__restrict__ nrm, int n, int knn,
+                                                                  const int *__restrict__ nbr, const int *__restrict__ nbr_count,
+                                                                  float *__restrict__ spfh)
+{
+    __shared__ unsigned char hits[33 * kQueryThreads];
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x)
+    {
+        const int i = base + threadIdx.x;
+        for (int b = 0; b < 33; ++b) hits[b * kQueryThreads + threadIdx.x] = 0;
+        if (i < n)
+        {
+            int points_num = nbr_count[i];
+            float each = 0.0f;
+            if (points_num - 1 > 0)
+            {
+                if (points_num > knn) points_num = knn;
+                each = (float)(100 / (points_num - 1));
+                const float ps[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]}, ns[3] = {nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]};
+                for (int j = 1; j != points_num; ++j)
+                {
+                    const int t = nbr[(size_t)i * knn + j];
+                    const float pt[3] = {pts[3 * t], pts[3 * t + 1], pts[3 * t + 2]}, nt[3] = {nrm[3 * t], nrm[3 * t + 1], nrm[3 * t + 2]};
+                    int bins[3];
+                    fpfh_pair_bins(ps, ns, pt, nt, bins);
+                    hits[bins[0] * kQueryThreads + threadIdx.x]++;          // knn <= 256 neighbours: a byte holds the count
+                    hits[(bins[1] + 11) * kQueryThreads + threadIdx.x]++;
+                    hits[(bins[2] + 22) * kQueryThreads + threadIdx.x]++;
+                }
+            }
+            for (int b = 0; b < 33; ++b) spfh[(size_t)i * 33 + b] = fmul((float)hits[b * kQueryThreads + threadIdx.x], each);
+        }
+    }
+}
+// ComputeFPFHFeature's second loop (:104-130): one warp per point, lane e owns histogram element e (lane 0 also element 32)
+// and walks the neighbours in list order, so every element sees the reference's sequence of float additions
+__global__ void __launch_bounds__(kQueryThreads) fpfh_combine_kernel(const float *__restrict__ pts, int n, int knn, const int *__restrict__ nbr,
+                                                                     const int *__restrict__ nbr_count, const float *__restrict__ spfh,
+                                                                     float *__restrict__ fpfh)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps)
+    {
+        int points_num = nbr_count[i];
+        if (points_num > knn) points_num = knn;
+        const float p[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+        float f = 0.0f, f32 = 0.0f;
+        double sum[3] = {0.0, 0.0, 0.0};
+        for (int j = 1; j < points_num; ++j)
+        {
+            const int t = nbr[(size_t)i * knn + j];
+            const float d[3] = {fsub(p[0], pts[3 * t]), fsub(p[1], pts[3 * t + 1]), fsub(p[2], pts[3 * t + 2])};
+            const float dist = __fsqrt_rn(dot3e(d, d));
+            if (dist != 0.0f)
+            {
+                const float w_d = fdiv(1.0f, dist);
+                const float s = spfh[(size_t)t * 33 + lane];
+                f = fadd(f, fmul(w_d, s));
+                const float s32 = spfh[(size_t)t * 33 + 32];
+                f32 = fadd(f32, fmul(w_d, s32));
+                // block<11,1>.sum() of integer-valued bins: exact in any order
+                const float in0 = lane < 11 ? s : 0.0f, in1 = lane >= 11 && lane < 22 ? s : 0.0f, in2 = lane >= 22 ? s : 0.0f;
+                float b0 = in0, b1 = in1, b2 = in2;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                {
+                    b0 += __shfl_xor_sync(0xFFFFFFFFu, b0, o);
+                    b1 += __shfl_xor_sync(0xFFFFFFFFu, b1, o);
+                    b2 += __shfl_xor_sync(0xFFFFFFFFu, b2, o);
+                }
+                sum[0] += (double)b0; sum[1] += (double)b1; sum[2] += (double)(b2 + s32);
+            }
+        }
+        const float scale0 = (float)(100.0 / sum[0]), scale1 = (float)(100.0 / sum[1]), scale2 = (float)(100.0 / sum[2]);
+        const float scale = lane < 11 ? scale0 : lane < 22 ? scale1 : scale2;
+        f = fadd(fmul(f, scale), spfh[(size_t)i * 33 + lane]);
+        fpfh[(size_t)i * 33 + lane] = f;
+        if (lane == 0) fpfh[(size_t)i * 33 + 32] = fadd(fmul(f32, scale2), spfh[(size_t)i * 33 + 32]);
+    }
+}
+} // namespace opb
+
+using namespace opb;
+
+struct opb_kdtree
+{
+    int device = 0, sm_count = 148;
+    cudaStream_t stream = nullptr;
+    size_t cap_points = 0, n = 0;
+    float *d_pts = nullptr, *d_key = nullptr, *d_boxes = nullptr;
+    int *d_vind = nullptr, *d_pos = nullptr, *d_queue[2] = {nullptr, nullptr};
+    KdNode *d_nodes = nullptr;
+    KdBuildCtl *d_ctl = nullptr, *h_ctl = nullptr;
+    int n_nodes = 0, max_level = 0;
+    bool built = false;
+    // query scratch
+    void *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void *d_aux[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t aux_bytes[4] = {0, 0, 0, 0};
+};
+
+static int kd_reserve(void **p, size_t *have, size_t want)
+{
+    if (*have >= want && *p) return OPB_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    OPB_CUDA(cudaMalloc(p, want));
+    *have = want;
+    return OPB_OK;
+}
+static KdView kd_view(const opb_kdtree *t)
+{
+    KdView v;
+    v.pts = t->d_pts; v.vind = t->d_vind; v.nodes = t->d_nodes; v.n = (int)t->n;
+    for (int d = 0; d < 3; ++d) { v.root_lo[d] = t->h_ctl->root_lo[d]; v.root_hi[d] = t->h_ctl->root_hi[d]; }
+    return v;
+}
+static int kd_grid(const opb_kdtree *t, size_t work, int per_sm)
+{
+    const size_t blocks = (work + kQueryThreads - 1) / kQueryThreads;
+    const size_t cap = (size_t)t->sm_count * per_sm;
+    return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+int opb_kdtree_create(int device, opb_kdtree **out)
+{
+    if (!out) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+    {
+        set_error("no CUDA device %d (the library has no CPU path)", device);
+        return OPB_ERR_CUDA;
+    }
+    OPB_CUDA(cudaSetDevice(device));
+    opb_kdtree *t = new opb_kdtree();
+    t->device = device;
+    cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking) != cudaSuccess || cudaMalloc((void **)&t->d_ctl, sizeof(KdBuildCtl)) != cudaSuccess ||
+        cudaMallocHost((void **)&t->h_ctl, sizeof(KdBuildCtl)) != cudaSuccess)
+    {
+        set_error("kd-tree workspace allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete t;
+        return OPB_ERR_CUDA;
+    }
+    *out = t;
+    return OPB_OK;
+}
+void opb_kdtree_destroy(opb_kdtree *t)
+{
+    if (!t) return;
+    cudaSetDevice(t->device);
+    cudaFree(t->d_pts); cudaFree(t->d_key); cudaFree(t->d_boxes); cudaFree(t->d_vind); cudaFree(t->d_pos);
+    cudaFree(t->d_queue[0]); cudaFree(t->d_queue[1]); cudaFree(t->d_nodes); cudaFree(t->d_ctl); cudaFree(t->d_scratch);
+    for (int i = 0; i < 4; ++i) cudaFree(t->d_aux[i]);
+    if (t->h_ctl) cudaFreeHost(t->h_ctl);
+    if (t->stream) cudaStreamDestroy(t->stream);
+    delete t;
+}
+int opb_kdtree_build(opb_kdtree *t, const float *xyz, size_t n)
+{
+    if (!t || (!xyz && n)) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    if (n > 0x3FFFFFF0u) { set_error("clouds above 2^30 points are not supported"); return OPB_ERR_INVALID; }
+    OPB_CUDA(cudaSetDevice(t->device));
+    t->built = false;
+    t->n = n;
+    if (n > t->cap_points)
+    {
+        cudaFree(t->d_pts); cudaFree(t->d_key); cudaFree(t->d_boxes); cudaFree(t->d_vind); cudaFree(t->d_pos);
+        cudaFree(t->d_queue[0]); cudaFree(t->d_queue[1]); cudaFree(t->d_nodes);
+        t->d_pts = t->d_key = t->d_boxes = nullptr; t->d_vind = t->d_pos = t->d_queue[0] = t->d_queue[1] = nullptr; t->d_nodes = nullptr;
+        t->cap_points = 0;
+        const size_t cap = n + n / 8 + 1024, nodes = 2 * cap + 2;
+        OPB_CUDA(cudaMalloc((void **)&t->d_pts, cap * 3 * sizeof(float)));
+        OPB_CUDA(cudaMalloc((void **)&t->d_key, cap * sizeof(float)));
+        OPB_CUDA(cudaMalloc((void **)&t->d_vind, cap * sizeof(int)));
+        OPB_CUDA(cudaMalloc((void **)&t->d_pos, cap * sizeof(int)));
+        OPB_CUDA(cudaMalloc((void **)&t->d_queue[0], nodes * sizeof(int)));
+        OPB_CUDA(cudaMalloc((void **)&t->d_queue[1], nodes * sizeof(int)));
+        OPB_CUDA(cudaMalloc((void **)&t->d_nodes, nodes * sizeof(KdNode)));
+        OPB_CUDA(cudaMalloc((void **)&t->d_boxes, nodes * 6 * sizeof(float)));
+        t->cap_points = cap;
+    }
+    cudaStream_t s = t->stream;
+    memset(t->h_ctl, 0, sizeof(KdBuildCtl));
+    t->n_nodes = 0;
+    t->max_level = 0;
+    if (n == 0) { t->built = true; return OPB_OK; }
+    OPB_CUDA(cudaMemcpyAsync(t->d_pts, xyz, n * 3 * sizeof(float), cudaMemcpyDefault, s));
+    kd_iota_kernel<<<kd_grid(t, n, 8), kQueryThreads, 0, s>>>(t->d_vind, (int)n);
+    KdNode root;
+    root.left = 0; root.right = (int)n; root.child1 = root.child2 = -1; root.divfeat = -1; root.divlow = root.divhigh = 0.0f; root.level = 0;
+    const int zero = 0;
+    t->h_ctl->n_nodes = 1;
+    OPB_CUDA(cudaMemcpyAsync(t->d_nodes, &root, sizeof(KdNode), cudaMemcpyHostToDevice, s));
+    OPB_CUDA(cudaMemcpyAsync(t->d_queue[0], &zero, sizeof(int), cudaMemcpyHostToDevice, s));
+    OPB_CUDA(cudaMemcpyAsync(t->d_ctl, t->h_ctl, sizeof(KdBuildCtl), cudaMemcpyHostToDevice, s));
+    OPB_CUDA(cudaStreamSynchronize(s)); // root / zero are stack variables
+    int in_count = 1, slot = 0;
+    for (int level = 0; in_count > 0; ++level)
+    {
+        if (level > 4 * kMaxDepth) { set_error("kd-tree build did not terminate"); return OPB_ERR_UNSUPPORTED; }
+        const int out_slot = slot ^ 1;
+        OPB_CUDA(cudaMemsetAsync(&t->d_ctl->queue_count[out_slot], 0, sizeof(int), s));
+        kd_split_kernel<<<in_count, kBuildThreads, 0, s>>>(t->d_pts, t->d_vind, t->d_key, t->d_pos, t->d_nodes, t->d_boxes, t->d_queue[slot],
+                                                           t->d_queue[out_slot], t->d_ctl, out_slot);
+        OPB_CUDA(cudaGetLastError());
+        OPB_CUDA(cudaMemcpyAsync(t->h_ctl, t->d_ctl, sizeof(KdBuildCtl), cudaMemcpyDeviceToHost, s));
+        OPB_CUDA(cudaStreamSynchronize(s));
+        in_count = t->h_ctl->queue_count[out_slot];
+        slot = out_slot;
+    }
+    t->n_nodes = t->h_ctl->n_nodes;
+    t->max_level = t->h_ctl->max_level;
+    if (t->max_level + 2 > kMaxDepth)
+    {
+        set_error("kd-tree of depth %d exceeds the search stack (%d levels)", t->max_level, kMaxDepth - 2);
+        return OPB_ERR_UNSUPPORTED;
+    }
+    t->built = true;
+    return OPB_OK;
+}
+int opb_kdtree_dump(opb_kdtree *t, int32_t *vind, int32_t *node_ints, float *node_floats, float root_box[6], size_t *n_nodes)
+{
+    if (!t || !n_nodes) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    if (!t->built) { set_error("opb_kdtree_build has not succeeded"); return OPB_ERR_INVALID; }
+    *n_nodes = (size_t)t->n_nodes;
+    if (!vind && !node_ints && !node_floats) return OPB_OK;
+    OPB_CUDA(cudaSetDevice(t->device));
+    if (vind && t->n) OPB_CUDA(cudaMemcpy(vind, t->d_vind, t->n * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<KdNode> nodes((size_t)t->n_nodes);
+    if (t->n_nodes) OPB_CUDA(cudaMemcpy(nodes.data(), t->d_nodes, nodes.size() * sizeof(KdNode), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < t->n_nodes; ++i)
+    {
+        if (node_ints)
+        {
+            node_ints[5 * i] = nodes[i].left; node_ints[5 * i + 1] = nodes[i].right; node_ints[5 * i + 2] = nodes[i].child1;
+            node_ints[5 * i + 3] = nodes[i].child2; node_ints[5 * i + 4] = nodes[i].divfeat;
+        }
+        if (node_floats) { node_floats[2 * i] = nodes[i].divlow; node_floats[2 * i + 1] = nodes[i].divhigh; }
+    }
+    if (root_box)
+        for (int d = 0; d < 3; ++d) { root_box[d] = t->h_ctl->root_lo[d]; root_box[3 + d] = t->h_ctl->root_hi[d]; }
+    return OPB_OK;
+}
+// device-side radius search of the tree's own points or of `d_queries` into rows of k indices
+static int kd_radius_rows(opb_kdtree *t, const float *d_queries, size_t nq, int k, float radius, int *d_index, float *d_dist, int *d_count)
+{
+    const int cap = (int)(size_t)(k * 2.5);
+    const size_t batch = nq < (size_t)kQueryBatch ? nq : (size_t)kQueryBatch;
+    int rc = kd_reserve(&t->d_scratch, &t->scratch_bytes, batch * (size_t)cap * 8);
+    if (rc) return rc;
+    float *sd = (float *)t->d_scratch;
+    int *si = (int *)(sd + batch * (size_t)cap);
+    const KdView v = kd_view(t);
+    for (size_t q0 = 0; q0 < nq; q0 += batch)
+    {
+        const size_t m = nq - q0 < batch ? nq - q0 : batch;
+        kd_radius_kernel<<<kd_grid(t, m, 16), kQueryThreads, 0, t->stream>>>(v, d_queries, (int)q0, (int)m, k, cap, radius, sd, si, (int)batch, d_index,
+                                                                             d_dist, d_count);
+        OPB_CUDA(cudaGetLastError());
+    }
+    return OPB_OK;
+}
+int opb_kdtree_search(opb_kdtree *t, const float *queries, size_t nq, int mode, int k, float radius, int32_t *out_index, float *out_dist,
+                      int32_t *out_count)
+{
+    if (!t || (!queries && nq) || !out_index || !out_dist || !out_count) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    if (!t->built) { set_error("opb_kdtree_build has not succeeded"); return OPB_ERR_INVALID; }
+    if (mode < 0 || mode > 2) { set_error("mode must be 0 (knn), 1 (radius) or 2 (knn within radius)"); return OPB_ERR_INVALID; }
+    if (k < 1 || (mode != 1 && k > kKnnCap) || (mode == 1 && (int)(size_t)(k * 2.5) > kRadiusCapMax))
+    {
+        set_error("k must be 1..%d (knn) or 1..%d (radius)", kKnnCap, (int)(kRadiusCapMax / 2.5));
+        return OPB_ERR_INVALID;
+    }
+    if (nq == 0) return OPB_OK;
+    if (nq > 0x7FFFFFF0u / (size_t)k) { set_error("too many queries"); return OPB_ERR_INVALID; }
+    OPB_CUDA(cudaSetDevice(t->device));
+    int rc;
+    if ((rc = kd_reserve(&t->d_aux[0], &t->aux_bytes[0], nq * 3 * sizeof(float)))) return rc;
+    if ((rc = kd_reserve(&t->d_aux[1], &t->aux_bytes[1], nq * (size_t)k * sizeof(int)))) return rc;
+    if ((rc = kd_reserve(&t->d_aux[2], &t->aux_bytes[2], nq * (size_t)k * sizeof(float)))) return rc;
+    if ((rc = kd_reserve(&t->d_aux[3], &t->aux_bytes[3], nq * sizeof(int)))) return rc;
+    cudaStream_t s = t->stream;
+    float *dq = (float *)t->d_aux[0];
+    int *di = (int *)t->d_aux[1];
+    float *dd = (float *)t->d_aux[2];
+    int *dc = (int *)t->d_aux[3];
+    OPB_CUDA(cudaMemcpyAsync(dq, queries, nq * 3 * sizeof(float), cudaMemcpyDefault, s));
+    if (mode == 1)
+    {
+        if ((rc = kd_radius_rows(t, dq, nq, k, radius, di, dd, dc))) return rc;
+    }
+    else
+    {
+        const size_t smem = (size_t)k * kQueryThreads * 8;
+        OPB_CUDA(cudaFuncSetAttribute(kd_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKnnCap * kQueryThreads * 8));
+        kd_knn_kernel<<<kd_grid(t, nq, 4), kQueryThreads, smem, s>>>(kd_view(t), dq, (int)nq, mode, k, radius, di, dd, dc);
+        OPB_CUDA(cudaGetLastError());
+    }
+    OPB_CUDA(cudaMemcpyAsync(out_index, di, nq * (size_t)k * sizeof(int), cudaMemcpyDefault, s));
+    OPB_CUDA(cudaMemcpyAsync(out_dist, dd, nq * (size_t)k * sizeof(float), cudaMemcpyDefault, s));
+    OPB_CUDA(cudaMemcpyAsync(out_count, dc, nq * sizeof(int), cudaMemcpyDefault, s));
+    OPB_CUDA(cudaStreamSynchronize(s));
+    return OPB_OK;
+}
+int opb_kdtree_estimate_normals(opb_kdtree *t, float radius, int knn, float *normals)
+{
+    if (!t || !normals) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    if (!t->built) { set_error("opb_kdtree_build has not succeeded"); return OPB_ERR_INVALID; }
+    if (knn < 1 || knn > kKnnCap) { set_error("knn must be 1..%d", kKnnCap); return OPB_ERR_INVALID; }
+    if (t->n == 0) return OPB_OK;
+    OPB_CUDA(cudaSetDevice(t->device));
+    int rc;
+    if ((rc = kd_reserve(&t->d_aux[2], &t->aux_bytes[2], t->n * 3 * sizeof(float)))) return rc;
+    float *dn = (float *)t->d_aux[2];
+    const size_t smem = (size_t)knn * kQueryThreads * 8;
+    OPB_CUDA(cudaFuncSetAttribute(kd_normals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKnnCap * kQueryThreads * 8));
+    int per_sm = 0;
+    OPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kd_normals_kernel, kQueryThreads, smem));
+    kd_normals_kernel<<<kd_grid(t, t->n, (per_sm < 1 ? 1 : per_sm) * 2), kQueryThreads, smem, t->stream>>>(kd_view(t), knn, radius, dn);
+    OPB_CUDA(cudaGetLastError());
+    OPB_CUDA(cudaMemcpyAsync(normals, dn, t->n * 3 * sizeof(float), cudaMemcpyDefault, t->stream));
+    OPB_CUDA(cudaStreamSynchronize(t->stream));
+    return OPB_OK;
+}
+int opb_kdtree_fpfh(opb_kdtree *t, const float *normals, int knn, float radius, float *features)
+{
+    if (!t || !normals || !features) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    if (!t->built) { set_error("opb_kdtree_build has not succeeded"); return OPB_ERR_INVALID; }
+    if (knn < 1 || knn > 256 || (int)(size_t)(knn * 2.5) > kRadiusCapMax) { set_error("knn must be 1..256"); return OPB_ERR_INVALID; }
+    const size_t n = t->n;
+    if (n == 0) return OPB_OK;
+    if (n > 0x7FFFFFF0u / (size_t)(knn > 33 ? knn : 33)) { set_error("cloud too large for %d neighbours per point", knn); return OPB_ERR_INVALID; }
+    OPB_CUDA(cudaSetDevice(t->device));
+    int rc;
+    if ((rc = kd_reserve(&t->d_aux[0], &t->aux_bytes[0], n * 3 * sizeof(float)))) return rc;  // normals
+    if ((rc = kd_reserve(&t->d_aux[1], &t->aux_bytes[1], n * (size_t)knn * sizeof(int)))) return rc; // neighbour rows
+    if ((rc = kd_reserve(&t->d_aux[2], &t->aux_bytes[2], n * 66 * sizeof(float)))) return rc; // spfh, fpfh
+    if ((rc = kd_reserve(&t->d_aux[3], &t->aux_bytes[3], n * sizeof(int)))) return rc;
+    cudaStream_t s = t->stream;
+    float *dn = (float *)t->d_aux[0];
+    int *nbr = (int *)t->d_aux[1];
+    float *spfh = (float *)t->d_aux[2], *fpfh = spfh + n * 33;
+    int *cnt = (int *)t->d_aux[3];
+    OPB_CUDA(cudaMemcpyAsync(dn, normals, n * 3 * sizeof(float), cudaMemcpyDefault, s));
+    if ((rc = kd_radius_rows(t, t->d_pts, n, knn, radius, nbr, nullptr, cnt))) return rc;
+    fpfh_spfh_kernel<<<kd_grid(t, n, 8), kQueryThreads, 0, s>>>(t->d_pts, dn, (int)n, knn, nbr, cnt, spfh);
+    OPB_CUDA(cudaGetLastError());
+    fpfh_combine_kernel<<<kd_grid(t, n * 32, 8), kQueryThreads, 0, s>>>(t->d_pts, (int)n, knn, nbr, cnt, spfh, fpfh);
+    OPB_CUDA(cudaGetLastError());
+    OPB_CUDA(cudaMemcpyAsync(features, fpfh, n * 33 * sizeof(float), cudaMemcpyDefault, s));
+    OPB_CUDA(cudaStreamSynchronize(s));
+    return OPB_OK;
+}

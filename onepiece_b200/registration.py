@@ -3,6 +3,7 @@ names, argument meaning and result fields as the reference, computed on the GPU 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -40,10 +41,17 @@ class PointCloud:
         return self.normals is not None and len(self.normals) == len(self.points) and len(self.points) > 0
 
     def EstimateNormals(self, radius: float = 0.1, knn: int = 30, device: int = 0):
-        """PointCloud::EstimateNormals(radius, knn) (reference src/Geometry/PointCloud.cpp:102-144) on the GPU; fills self.normals"""
+        """PointCloud::EstimateNormals(radius, knn) (reference src/Geometry/PointCloud.cpp:102-144) on the GPU; fills self.normals.
+        Neighbours come from the reference's own k-d tree walk (KDTree below), so equal distances are ordered as there.
+        OPB_NORMALS_KNN=grid (developer knob) takes the uniform-grid search instead: same result unless distances tie."""
         self.normals = np.zeros_like(self.points)
-        capi.check(capi.lib.opb_icp_estimate_normals(_Workspace.get(device), _ptr(self.points), len(self.points), radius, knn,
-                                                     _ptr(self.normals)))
+        if os.environ.get("OPB_NORMALS_KNN", "tree") == "grid":
+            capi.check(capi.lib.opb_icp_estimate_normals(_Workspace.get(device), _ptr(self.points), len(self.points), radius, knn,
+                                                         _ptr(self.normals)))
+            return
+        tree = KDTree(device)
+        tree.BuildTree(self.points)
+        capi.check(capi.lib.opb_kdtree_estimate_normals(tree._h, radius, knn, _ptr(self.normals)))
 
     def DownSample(self, grid_len: float, colors=None, device: int = 0):
         """PointCloud::DownSample(grid_len) (reference src/Geometry/PointCloud.cpp:145-189) on the GPU -> new PointCloud
@@ -64,6 +72,68 @@ class PointCloud:
             return a
         out = PointCloud(take(op), take(on) if nrm is not None else None)
         return (out, take(oc)) if col is not None else out
+
+
+class KDTree:
+    """geometry::KDTree<3> (reference src/Geometry/KDTree.h:60-262) on the GPU: the same tree as the reference's nanoflann builds
+    and the same walk, so every search returns the reference's neighbours in the reference's order (ties, early stop and all).
+    One device workspace per (device) is shared by all instances; BuildTree replaces its contents."""
+    _by_device = {}
+
+    def __init__(self, device: int = 0):
+        if device not in KDTree._by_device:
+            h = C.c_void_p()
+            capi.check(capi.lib.opb_kdtree_create(device, C.byref(h)))
+            KDTree._by_device[device] = h
+        self._h = KDTree._by_device[device]
+        self.n = 0
+
+    def BuildTree(self, points):
+        pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        self.n = len(pts)
+        capi.check(capi.lib.opb_kdtree_build(self._h, _ptr(pts), len(pts)))
+
+    def _search(self, queries, mode, k, radius):
+        qs = np.ascontiguousarray(queries, np.float32).reshape(-1, 3)
+        idx = np.zeros((len(qs), k), np.int32)
+        dist = np.zeros((len(qs), k), np.float32)
+        cnt = np.zeros(len(qs), np.int32)
+        capi.check(capi.lib.opb_kdtree_search(self._h, _ptr(qs), len(qs), mode, k, radius, _ptr(idx), _ptr(dist), _ptr(cnt)))
+        return idx, dist, cnt
+
+    def KnnSearch(self, queries, k):
+        """-> (indices [nq,k] padded with -1, squared distances, result counts)"""
+        return self._search(queries, 0, k, 0.0)
+
+    def RadiusSearch(self, queries, radius, max_result):
+        """`radius` bounds the SQUARED distance, as in the reference (KDTree.h:131)"""
+        return self._search(queries, 1, max_result, radius)
+
+    def KnnRadiusSearch(self, queries, k, radius):
+        return self._search(queries, 2, k, radius)
+
+    def Dump(self):
+        """test hook: (vind, node ints [m,5], node floats [m,2], root box) in the device's allocation order, root = node 0"""
+        m = C.c_size_t(0)
+        capi.check(capi.lib.opb_kdtree_dump(self._h, None, None, None, None, C.byref(m)))
+        vind = np.zeros(self.n, np.int32)
+        ni = np.zeros((m.value, 5), np.int32)
+        nf = np.zeros((m.value, 2), np.float32)
+        box = np.zeros(6, np.float32)
+        capi.check(capi.lib.opb_kdtree_dump(self._h, _ptr(vind), _ptr(ni), _ptr(nf), _ptr(box), C.byref(m)))
+        return vind, ni, nf, box
+
+
+def ComputeFPFHFeature(pcd: "PointCloud", knn: int = 100, radius: float = 0.1, device: int = 0):
+    """registration::ComputeFPFHFeature(pcd, features, knn, radius) (reference src/Registration/3DFeature.cpp:83-131) on the GPU
+    -> [n, 33] float32.  The cloud needs normals (the reference reads pcd.normals unchecked)."""
+    if not pcd.HasNormals():
+        raise ValueError("ComputeFPFHFeature: the point cloud has no normals")
+    tree = KDTree(device)
+    tree.BuildTree(pcd.points)
+    out = np.zeros((len(pcd.points), 33), np.float32)
+    capi.check(capi.lib.opb_kdtree_fpfh(tree._h, _ptr(pcd.normals), knn, radius, _ptr(out)))
+    return out
 
 
 class _Workspace:

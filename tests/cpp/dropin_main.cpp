@@ -12,6 +12,7 @@
 #include "Geometry/RGBDFrame.h"
 #include "Integration/CubeHandler.h"
 #include "Odometry/Odometry.h"
+#include "Registration/3DFeature.h"
 #include "Registration/ICP.h"
 #include "Tool/ImageProcessing.h"
 
@@ -143,6 +144,20 @@ int main(int argc, char **argv)
         for (size_t i = 0; i < e_pcd.normals.size(); ++i)
             for (int k = 0; k < 3; ++k) en.push_back(e_pcd.normals[i](k));
         WriteAll(dir + "/estimated_normals.bin", en);
+        // the submap back end's descriptor step (example/DenseFusion/DenseSlam.cpp:76 -> DownSampleAndExtractFeature):
+        // down-sample, normals, FPFH with DenseSlam's parameters (DenseSlam.h:49-56)
+        auto down = e_pcd.DownSample(0.05);
+        down->EstimateNormals(0.1, 30);
+        registration::FeatureSet features;
+        registration::ComputeFPFHFeature(*down, features, 100, 0.25);
+        std::vector<float> ff, fp;
+        for (size_t i = 0; i < features.size(); ++i)
+        {
+            for (int k = 0; k < 33; ++k) ff.push_back(features[i](k));
+            for (int k = 0; k < 3; ++k) fp.push_back(down->points[i](k));
+        }
+        WriteAll(dir + "/fpfh.bin", ff);
+        WriteAll(dir + "/fpfh_points.bin", fp);
     }
     registration::ICPParameter icp_para;
     icp_para.threshold = 0.05;

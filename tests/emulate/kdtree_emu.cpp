@@ -1,0 +1,107 @@
+// TEST INFRASTRUCTURE ONLY.  Runs the DEVICE code of onepiece_b200/csrc/opb_kdtree.cu (everything inside namespace opb, cut out
+// by tests/test_kdtree_emulated.py into kdtree_device.inc) on the host emulator in cuda_emu.h, driven the way the library's host
+// code drives it, so the build / search / sort / FPFH kernels can be compared with the oracle without a GPU.
+#include "opb_common.cuh"
+namespace opb { float knn_smem[64 * 128 * 2]; }
+#include "kdtree_device.inc"
+
+using namespace opb;
+
+struct Tree
+{
+    std::vector<float> pts, key, boxes;
+    std::vector<int> vind, pos, queue[2];
+    std::vector<KdNode> nodes;
+    KdBuildCtl ctl;
+    int n = 0;
+    KdView view() const
+    {
+        KdView v;
+        v.pts = pts.data(); v.vind = vind.data(); v.nodes = nodes.data(); v.n = n;
+        for (int d = 0; d < 3; ++d) { v.root_lo[d] = ctl.root_lo[d]; v.root_hi[d] = ctl.root_hi[d]; }
+        return v;
+    }
+};
+static int grid_for(size_t work, int cap) { const size_t b = (work + kQueryThreads - 1) / kQueryThreads; return (int)(b < (size_t)cap ? (b ? b : 1) : cap); }
+
+extern "C"
+{
+void *emu_build(const float *xyz, long n)
+{
+    Tree *t = new Tree();
+    t->n = (int)n;
+    t->pts.assign(xyz, xyz + 3 * n);
+    t->key.resize(n + 1); t->vind.resize(n + 1); t->pos.resize(n + 1);
+    t->nodes.resize(2 * n + 2); t->boxes.resize(6 * (2 * n + 2));
+    t->queue[0].resize(2 * n + 2); t->queue[1].resize(2 * n + 2);
+    memset(&t->ctl, 0, sizeof t->ctl);
+    if (n == 0) return t;
+    emu::launch(grid_for(n, 4), kQueryThreads, [&] { kd_iota_kernel(t->vind.data(), (int)n); });
+    KdNode root;
+    root.left = 0; root.right = (int)n; root.child1 = root.child2 = -1; root.divfeat = -1; root.divlow = root.divhigh = 0.0f; root.level = 0;
+    t->nodes[0] = root;
+    t->queue[0][0] = 0;
+    t->ctl.n_nodes = 1;
+    int in_count = 1, slot = 0;
+    while (in_count > 0)
+    {
+        const int out_slot = slot ^ 1;
+        t->ctl.queue_count[out_slot] = 0;
+        emu::launch(in_count, kBuildThreads, [&] {
+            kd_split_kernel(t->pts.data(), t->vind.data(), t->key.data(), t->pos.data(), t->nodes.data(), t->boxes.data(), t->queue[slot].data(),
+                            t->queue[out_slot].data(), &t->ctl, out_slot);
+        });
+        in_count = t->ctl.queue_count[out_slot];
+        slot = out_slot;
+    }
+    return t;
+}
+void emu_destroy(void *p) { delete (Tree *)p; }
+long emu_dump(void *p, int32_t *vind, int32_t *ni, float *nf, float *box)
+{
+    Tree *t = (Tree *)p;
+    for (int i = 0; i < t->n; ++i) vind[i] = t->vind[i];
+    for (int i = 0; i < t->ctl.n_nodes; ++i)
+    {
+        const KdNode &nd = t->nodes[i];
+        ni[5 * i] = nd.left; ni[5 * i + 1] = nd.right; ni[5 * i + 2] = nd.child1; ni[5 * i + 3] = nd.child2; ni[5 * i + 4] = nd.divfeat;
+        nf[2 * i] = nd.divlow; nf[2 * i + 1] = nd.divhigh;
+    }
+    for (int d = 0; d < 3; ++d) { box[d] = t->ctl.root_lo[d]; box[3 + d] = t->ctl.root_hi[d]; }
+    return t->ctl.n_nodes * 1000L + t->ctl.max_level;
+}
+void emu_search(void *p, const float *queries, long nq, int mode, int k, float radius, int32_t *out_index, float *out_dist, int32_t *out_count)
+{
+    Tree *t = (Tree *)p;
+    const KdView v = t->view();
+    if (mode == 1)
+    {
+        const int cap = (int)(size_t)(k * 2.5);
+        std::vector<float> sd((size_t)nq * cap + 1);
+        std::vector<int> si((size_t)nq * cap + 1);
+        emu::launch(grid_for(nq, 4), kQueryThreads,
+                    [&] { kd_radius_kernel(v, queries, 0, (int)nq, k, cap, radius, sd.data(), si.data(), (int)nq, out_index, out_dist, out_count); });
+    }
+    else
+        emu::launch(grid_for(nq, 4), kQueryThreads, [&] { kd_knn_kernel(v, queries, (int)nq, mode, k, radius, out_index, out_dist, out_count); });
+}
+void emu_normals(void *p, float radius, int knn, float *normals)
+{
+    Tree *t = (Tree *)p;
+    const KdView v = t->view();
+    emu::launch(grid_for(t->n, 4), kQueryThreads, [&] { kd_normals_kernel(v, knn, radius, normals); });
+}
+void emu_fpfh(void *p, const float *normals, int knn, float radius, float *features)
+{
+    Tree *t = (Tree *)p;
+    const KdView v = t->view();
+    const long n = t->n;
+    const int cap = (int)(size_t)(knn * 2.5);
+    std::vector<float> sd((size_t)n * cap + 1), spfh((size_t)n * 33 + 1);
+    std::vector<int> si((size_t)n * cap + 1), nbr((size_t)n * knn + 1), cnt(n + 1);
+    emu::launch(grid_for(n, 4), kQueryThreads,
+                [&] { kd_radius_kernel(v, t->pts.data(), 0, (int)n, knn, cap, radius, sd.data(), si.data(), (int)n, nbr.data(), nullptr, cnt.data()); });
+    emu::launch(grid_for(n, 3), kQueryThreads, [&] { fpfh_spfh_kernel(t->pts.data(), normals, (int)n, knn, nbr.data(), cnt.data(), spfh.data()); });
+    emu::launch(grid_for(n * 32, 5), kQueryThreads, [&] { fpfh_combine_kernel(t->pts.data(), (int)n, knn, nbr.data(), cnt.data(), spfh.data(), features); });
+}
+}

@@ -71,6 +71,13 @@ def test_reference_caller_code_runs_on_the_gpu(tmp_path):
     # PointCloud::EstimateNormals through the drop-in (example/ICPTest.cpp:27-29)
     en = np.fromfile(tmp_path / "estimated_normals.bin", np.float32).reshape(-1, 3)
     assert_bit_equal(en, oracleapi.estimate_normals(tgt), "EstimateNormals through the drop-in")
+    # registration::ComputeFPFHFeature through the drop-in, called the way DenseSlam's submap back end calls it
+    fp = np.fromfile(tmp_path / "fpfh_points.bin", np.float32).reshape(-1, 3)
+    ff = np.fromfile(tmp_path / "fpfh.bin", np.float32).reshape(-1, 33)
+    down = oracleapi.downsample(tgt, None, None, 0.05)[0]
+    assert_bit_equal(fp, down, "DownSample through the drop-in")
+    of = oracleapi.fpfh(down, oracleapi.estimate_normals(down, 0.1, 30), 100, 0.25)
+    assert len(ff) == len(of) > 100 and ((ff.view(np.uint32) == of.view(np.uint32)) | (np.isnan(ff) & np.isnan(of))).all()
     # Odometry::DenseTracking through the drop-in: two chained calls on the same RGBDFrames, then the cv::Mat overload
     odo = np.fromfile(tmp_path / "odometry.bin", np.float64)
     S, T = oracleapi.OracleFrame(c1_bgr, d1), oracleapi.OracleFrame(c0_bgr, d0)

@@ -180,8 +180,9 @@ def test_certification_does_not_change_the_result(tmp_path):
 
 
 def test_estimate_normals_matches_the_oracle_bit_for_bit():
-    """PointCloud::EstimateNormals on the device: exact 30-nearest search on the grid + FitPlane + the JacobiSVD restatement.
-    Same neighbour order rule as the oracle (distance, then index), so even the tie-ridden raw cloud must agree bit for bit."""
+    """PointCloud::EstimateNormals on the device: the reference's own k-d tree walk (same tree, same visiting order) + FitPlane +
+    the JacobiSVD restatement, so even the tie-ridden raw cloud must agree bit for bit with the oracle (itself bit-identical to
+    the compiled reference there).  The uniform-grid search (developer knob) orders ties by index: identical on tie-free clouds."""
     from onepiece_b200 import capi
     c0 = scenes.Camera()
     cam = scenes.Camera(c0.fx / 4, c0.fy / 4, c0.cx / 4, c0.cy / 4, 160, 120, 1000.0)
@@ -194,6 +195,13 @@ def test_estimate_normals_matches_the_oracle_bit_for_bit():
         ref = oracleapi.estimate_normals(cloud)
         same = (pc.normals.view(np.uint32) == ref.view(np.uint32)).all(1)
         assert same.all(), f"{what}: {np.count_nonzero(~same)} of {len(cloud)} normals differ, first at {np.argmax(~same)}"
+    os.environ["OPB_NORMALS_KNN"] = "grid"
+    try:
+        pg = reg.PointCloud(jit)
+        pg.EstimateNormals()
+        assert np.array_equal(pg.normals.view(np.uint32), oracleapi.estimate_normals(jit).view(np.uint32)), "grid search, tie-free cloud"
+    finally:
+        del os.environ["OPB_NORMALS_KNN"]
     # the estimated normals are the surface normals up to sign (away from the room's edges)
     nt = n_true.reshape(-1, 3)[(d > 0).reshape(-1)]
     assert np.median(np.abs((pc.normals * nt).sum(1))) > 0.999

@@ -1,0 +1,105 @@
+"""The DEVICE code of onepiece_b200/csrc/opb_kdtree.cu (tree build with the parallel Hoare partition, the explicit-stack walk, the
+std::sort restatement, normals, FPFH) executed in the CPU container on the host-thread CUDA emulator in tests/emulate, and
+compared with the oracle bit for bit.  This is a check of the kernels' logic before they reach a GPU -- not a product path: the
+emulator lives under tests/ and the library itself still has no CPU route.  The -m gpu tests repeat the comparison on the device."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracleapi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+p = C.c_void_p
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("kdtree_emu"))
+    src = open(os.path.join(ROOT, "onepiece_b200", "csrc", "opb_kdtree.cu")).read()
+    a = src.index("namespace opb\n{")
+    b = src.index("} // namespace opb\n\nusing namespace opb;") + len("} // namespace opb\n")
+    dev = src[a:b].replace("extern __shared__ float knn_smem[];", "")
+    # 64 threads per building CTA keep the emulation fast (the -m gpu tests run the real 256)
+    dev = dev.replace("constexpr int kBuildThreads = 256;", "constexpr int kBuildThreads = 64;")
+    assert "kBuildThreads = 64" in dev
+    open(os.path.join(out, "kdtree_device.inc"), "w").write('#include "opb_fitplane.cuh"\n' + dev)
+    shutil.copy(os.path.join(ROOT, "onepiece_b200", "csrc", "opb_fitplane.cuh"), out)
+    for f in ("cuda_emu.h", "kdtree_emu.cpp", os.path.join("stubs", "opb_common.cuh")):
+        shutil.copy(os.path.join(ROOT, "tests", "emulate", f), out)
+    lib = os.path.join(out, "libkdtree_emu.so")
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-msse4.2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", out,
+                        "-o", lib, os.path.join(out, "kdtree_emu.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    L = C.CDLL(lib)
+    L.emu_build.restype = p
+    L.emu_build.argtypes = [p, C.c_long]
+    L.emu_destroy.argtypes = [p]
+    L.emu_dump.restype = C.c_long
+    L.emu_dump.argtypes = [p] * 5
+    L.emu_search.argtypes = [p, p, C.c_long, C.c_int, C.c_int, C.c_float, p, p, p]
+    L.emu_normals.argtypes = [p, C.c_float, C.c_int, p]
+    L.emu_fpfh.argtypes = [p, p, C.c_int, C.c_float, p]
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(p)
+
+
+def canonical_tree(ni, nf):
+    """nodes in pre-order as (left, right, divfeat, divlow, divhigh): independent of the order the nodes were allocated in"""
+    out, stack = [], [0]
+    while stack:
+        i = stack.pop()
+        out.append((int(ni[i, 0]), int(ni[i, 1]), int(ni[i, 4]), float(nf[i, 0]), float(nf[i, 1])))
+        if ni[i, 2] >= 0:
+            stack.extend((int(ni[i, 3]), int(ni[i, 2])))
+    return out
+
+
+def clouds():
+    rng = np.random.default_rng(3)
+    u = rng.uniform(-1, 1, (700, 2)).astype(np.float32)
+    z = (2.0 + 0.3 * np.sin(3 * u[:, 0]) * np.cos(2 * u[:, 1])).astype(np.float32)
+    yield "surface", (np.stack([u[:, 0], u[:, 1], z], 1) + rng.normal(0, 0.002, (700, 3))).astype(np.float32)
+    g = np.stack(np.meshgrid(np.arange(16), np.arange(16), np.arange(2), indexing="ij"), -1).reshape(-1, 3).astype(np.float32) * 0.02
+    yield "lattice", g[rng.permutation(len(g))]
+    d = rng.uniform(-1, 1, (300, 3)).astype(np.float32)
+    yield "duplicates", np.concatenate([d, d[:150], d[:50]])
+    yield "eleven", rng.uniform(-1, 1, (11, 3)).astype(np.float32)
+
+
+@pytest.mark.parametrize("name,pts", list(clouds()), ids=[c[0] for c in clouds()])
+def test_emulated_device_code_matches_the_oracle(emu, name, pts):
+    n = len(pts)
+    h = emu.emu_build(_ptr(pts), n)
+    try:
+        vind, ni, nf, box = np.zeros(n, np.int32), np.zeros((2 * n + 2, 5), np.int32), np.zeros((2 * n + 2, 2), np.float32), np.zeros(6, np.float32)
+        m = emu.emu_dump(h, _ptr(vind), _ptr(ni), _ptr(nf), _ptr(box)) // 1000
+        ov, oni, onf, obox = oracleapi.kdtree_dump(pts)
+        assert np.array_equal(vind, ov), "point permutation (planeSplit)"
+        assert m == len(oni) and canonical_tree(ni, nf) == canonical_tree(oni, onf) and np.array_equal(box, obox)
+        rng = np.random.default_rng(5)
+        qs = np.concatenate([pts[:200], rng.uniform(-1.5, 1.5, (40, 3)).astype(np.float32)])
+        for mode, k, radius in [(0, 1, 0.0), (0, 30, 0.0), (2, 30, 0.01), (1, 100, 0.1), (1, 20, 0.05), (1, 60, 0.25)]:
+            idx, dist, cnt = np.zeros((len(qs), k), np.int32), np.zeros((len(qs), k), np.float32), np.zeros(len(qs), np.int32)
+            emu.emu_search(h, _ptr(qs), len(qs), mode, k, radius, _ptr(idx), _ptr(dist), _ptr(cnt))
+            a = oracleapi.kdtree_search(pts, qs, mode, k, radius)
+            assert np.array_equal(cnt, a[2]) and np.array_equal(idx, a[0]), (name, mode, k, radius)
+            assert np.array_equal(dist.view(np.uint32), a[1].view(np.uint32))
+        nrm = np.zeros_like(pts)
+        emu.emu_normals(h, 0.1, 30, _ptr(nrm))
+        on = oracleapi.estimate_normals(pts, 0.1, 30)
+        assert np.array_equal(nrm.view(np.uint32), on.view(np.uint32))
+        on = np.nan_to_num(on)
+        for knn, radius in [(100, 0.1), (40, 0.25)]:
+            f = np.zeros((n, 33), np.float32)
+            emu.emu_fpfh(h, _ptr(on), knn, radius, _ptr(f))
+            of = oracleapi.fpfh(pts, on, knn, radius)
+            assert ((f.view(np.uint32) == of.view(np.uint32)) | (np.isnan(f) & np.isnan(of))).all(), (name, knn, radius)
+    finally:
+        emu.emu_destroy(h)

@@ -1,0 +1,132 @@
+"""geometry::KDTree<3>, PointCloud::EstimateNormals and registration::ComputeFPFHFeature on the device
+against the oracle, which is itself pinned bit for bit to the compiled reference (tests/test_oracle_kdtree.py): same tree, same
+neighbours in the same order, same descriptors."""
+import time
+
+import numpy as np
+import pytest
+
+from oracle import oracleapi
+from test_kdtree_emulated import canonical_tree
+
+pytestmark = pytest.mark.gpu
+
+
+def _reg():
+    from onepiece_b200 import registration as reg
+    return reg
+
+
+def _surface(n, seed=5, noise=0.002):
+    rng = np.random.default_rng(seed)
+    u = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+    z = (2.0 + 0.3 * np.sin(3 * u[:, 0]) * np.cos(2 * u[:, 1])).astype(np.float32)
+    return (np.stack([u[:, 0], u[:, 1], z], 1) + rng.normal(0, noise, (n, 3))).astype(np.float32)
+
+
+def _room_cloud(div):
+    from onepiece_b200 import scenes
+    c0 = scenes.Camera()
+    cam = scenes.Camera(c0.fx / div, c0.fy / div, c0.cx / div, c0.cy / div, 640 // div, 480 // div, 1000.0)
+    d, _, _ = scenes.room(cam, 0)
+    return scenes.backproject(d, cam)
+
+
+def _clouds():
+    rng = np.random.default_rng(3)
+    yield "random-100k", rng.uniform(-1, 1, (100000, 3)).astype(np.float32)
+    g = np.stack(np.meshgrid(np.arange(40), np.arange(40), np.arange(3), indexing="ij"), -1).reshape(-1, 3).astype(np.float32) * 0.02
+    yield "lattice", g[rng.permutation(len(g))]
+    d = rng.uniform(-1, 1, (2000, 3)).astype(np.float32)
+    yield "duplicates", np.concatenate([d, d[:500], d[:100]])
+    p = rng.uniform(-1, 1, (3000, 3)).astype(np.float32)
+    p[:, 2] = 0.5
+    yield "plane", p
+    yield "sensor-160x120", _room_cloud(4)
+    yield "tiny", rng.uniform(-1, 1, (7, 3)).astype(np.float32)
+    yield "eleven", rng.uniform(-1, 1, (11, 3)).astype(np.float32)
+
+
+@pytest.mark.parametrize("name,pts", list(_clouds()), ids=[c[0] for c in _clouds()])
+def test_device_tree_and_searches_are_the_references(name, pts):
+    reg = _reg()
+    tree = reg.KDTree()
+    tree.BuildTree(pts)
+    vind, ni, nf, box = tree.Dump()
+    ov, oni, onf, obox = oracleapi.kdtree_dump(pts)
+    assert np.array_equal(vind, ov), "point permutation (planeSplit)"
+    assert len(ni) == len(oni) and canonical_tree(ni, nf) == canonical_tree(oni, onf) and np.array_equal(box, obox)
+    rng = np.random.default_rng(11)
+    qs = np.concatenate([pts[:3000], rng.uniform(-1.5, 1.5, (300, 3)).astype(np.float32)])
+    for search, args, mode in [(tree.KnnSearch, (1,), 0), (tree.KnnSearch, (30,), 0), (tree.KnnSearch, (64,), 0),
+                               (tree.KnnRadiusSearch, (30, 0.01), 2), (tree.RadiusSearch, (0.1, 100), 1),
+                               (tree.RadiusSearch, (0.05, 20), 1), (tree.RadiusSearch, (0.25, 100), 1)]:
+        idx, dist, cnt = search(qs, *args)
+        k = args[0] if mode != 1 else args[1]
+        radius = 0.0 if mode == 0 else (args[1] if mode == 2 else args[0])
+        a = oracleapi.kdtree_search(pts, qs, mode, k, radius)
+        assert np.array_equal(cnt, a[2]) and np.array_equal(idx, a[0]), (name, mode, args, np.nonzero((idx != a[0]).any(1))[0][:5])
+        assert np.array_equal(dist.view(np.uint32), a[1].view(np.uint32))
+
+
+def test_kdtree_argument_errors():
+    from onepiece_b200 import capi
+    reg = _reg()
+    tree = reg.KDTree()
+    tree.BuildTree(np.zeros((0, 3), np.float32))
+    idx, dist, cnt = tree.KnnSearch(np.zeros((4, 3), np.float32), 3)
+    assert (cnt == 0).all() and (idx == -1).all()
+    tree.BuildTree(_surface(100))
+    with pytest.raises(capi.OpbError):
+        tree.KnnSearch(np.zeros((1, 3), np.float32), 65)
+    with pytest.raises(capi.OpbError):
+        tree.RadiusSearch(np.zeros((1, 3), np.float32), 0.1, 500)
+    with pytest.raises(capi.OpbError):
+        tree.KnnSearch(np.zeros((1, 3), np.float32), 0)
+    with pytest.raises(ValueError):
+        reg.ComputeFPFHFeature(reg.PointCloud(_surface(10)))
+
+
+@pytest.mark.parametrize("case", ["surface", "capped", "sparse", "lattice", "denseslam"])
+def test_fpfh_matches_the_oracle_bit_for_bit(case):
+    """ComputeFPFHFeature: below and above the radius search's 2.5 k early stop, isolated points (NaN rows), tied distances, and
+    the way DenseSlam calls it (DownSample(0.05) of a 640x480 frame, normals (0.1, 30), FPFH (100, 0.25): DenseSlam.h:49-56)."""
+    reg = _reg()
+    if case == "lattice":
+        g = np.stack(np.meshgrid(np.arange(50), np.arange(50), indexing="ij"), -1).reshape(-1, 2).astype(np.float32) * 0.04
+        pts, knn, radius = np.concatenate([g, np.full((len(g), 1), 2.0, np.float32)], 1), 50, 0.05
+    elif case == "denseslam":
+        pts, knn, radius = reg.PointCloud(_room_cloud(1)).DownSample(0.05).points, 100, 0.25
+    else:
+        pts, knn, radius = {"surface": (_surface(20000), 100, 0.1), "capped": (_surface(20000), 100, 0.25),
+                            "sparse": (_surface(300), 100, 0.01)}[case]
+    pc = reg.PointCloud(pts)
+    pc.EstimateNormals(0.1, 30)
+    on = oracleapi.estimate_normals(pts, 0.1, 30)
+    assert np.array_equal(pc.normals.view(np.uint32), on.view(np.uint32)), "normals"
+    pc.normals = np.nan_to_num(pc.normals)
+    t0 = time.perf_counter()
+    f = reg.ComputeFPFHFeature(pc, knn, radius)
+    dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    of = oracleapi.fpfh(pts, pc.normals, knn, radius)
+    dt_o = time.perf_counter() - t0
+    same = (f.view(np.uint32) == of.view(np.uint32)) | (np.isnan(f) & np.isnan(of))
+    print(f"fpfh[{case}]: {len(pts)} points, device {dt * 1e3:.1f} ms (tree build + search + features, host buffers), oracle {dt_o * 1e3:.0f} ms")
+    assert same.all(), f"{np.count_nonzero(~same.all(1))} of {len(pts)} descriptors differ, first at {np.argmax(~same.all(1))}"
+    assert np.isnan(f).any() == (case == "sparse")
+
+
+def test_estimate_normals_full_frame_matches_the_oracle():
+    """640x480 raw sensor-like cloud (quantised depth: many exactly equal neighbour distances): 307,200 normals, all bit-identical"""
+    reg = _reg()
+    pts = _room_cloud(1)
+    pc = reg.PointCloud(pts)
+    pc.EstimateNormals()
+    t0 = time.perf_counter()
+    pc.EstimateNormals()
+    dt = time.perf_counter() - t0
+    on = oracleapi.estimate_normals(pts)
+    same = (pc.normals.view(np.uint32) == on.view(np.uint32)).all(1)
+    print(f"EstimateNormals (k-d tree order): {len(pts)} points in {dt * 1e3:.1f} ms")
+    assert same.all(), f"{np.count_nonzero(~same)} of {len(pts)} normals differ"
