@@ -576,7 +576,8 @@ int opb_pointcloud_downsample(int device, const float *points, const float *colo
     while (cap < 2 * n) cap <<= 1;
     const int n_attr = 1 + (colors ? 1 : 0) + (normals ? 1 : 0);
     Arena A;
-    A.cap = cap * 12 + n * 4 * 10 + n * 12 * (size_t)(2 * n_attr + 1) + 64 * 256;
+    // inputs (n_attr x 12 n), cell_mean / cell_attr / d_out (3 x 12 n), eight index arrays (4 n each, big_list n / 16), the hash table
+    A.cap = cap * 12 + n * 4 * 10 + n * 12 * (size_t)(n_attr + 4) + 64 * 256;
     OPB_CUDA(cudaMalloc(&A.base, A.cap));
     ClusterDev d;
     float *d_in[3] = {A.take<float>(3 * n), colors ? A.take<float>(3 * n) : nullptr, normals ? A.take<float>(3 * n) : nullptr};
