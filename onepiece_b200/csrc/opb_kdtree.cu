@@ -30,8 +30,8 @@
 namespace opb
 {
 constexpr int kLeafMax = 10;
-constexpr int kBuildThreads = 256;
-constexpr int kBuildWarps = kBuildThreads / 32;
+constexpr int kBuildThreadsBig = 1024, kBuildThreadsMid = 256, kBuildThreadsSmall = 64; // CTA size by the level's largest node
+constexpr int kBuildBigNode = 8192, kBuildSmallNode = 256;
 constexpr int kMaxDepth = 64;
 constexpr int kQueryThreads = 128;
 constexpr int kKnnCap = 64;       // k of the shared-memory k-nearest list
@@ -46,12 +46,13 @@ struct KdNode
 };
 struct KdBuildCtl
 {
-    int n_nodes, queue_count[2], max_level;
+    int n_nodes, queue_count[2], queue_max[2], max_level; // queue_max: the largest node waiting in that queue
     float root_lo[3], root_hi[3];
 };
 struct KdView
 {
     const float *pts;
+    const float4 *sorted; // the points in vind order, w = the point's index: a leaf is one contiguous run
     const int *vind;
     const KdNode *nodes;
     float root_lo[3], root_hi[3];
@@ -61,9 +62,10 @@ struct KdView
 // ---------------------------------------------------------------------------------------------------------
 // build
 // ---------------------------------------------------------------------------------------------------------
-template <class T, class Op>
+template <int THREADS, class T, class Op>
 __device__ __forceinline__ T block_reduce(T v, Op op, T *sh)
 {
+    constexpr int kBuildWarps = THREADS / 32;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
     __syncthreads();
@@ -74,8 +76,10 @@ __device__ __forceinline__ T block_reduce(T v, Op op, T *sh)
     for (int w = 1; w < kBuildWarps; ++w) r = op(r, sh[w]);
     return r;
 }
+template <int THREADS>
 __device__ __forceinline__ int block_exscan(int v, int *sh, int &total)
 {
+    constexpr int kBuildWarps = THREADS / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int incl = v;
 #pragma unroll
@@ -99,11 +103,11 @@ __device__ __forceinline__ int block_exscan(int v, int *sh, int &total)
 }
 // One Hoare pass of planeSplit (nanoflann.hpp:978-991 / :996-1008) over [begin, end): afterwards every element with `pred`
 // sits below `boundary` (= begin + their count).  LE selects the second pass's predicate (<= cutval) over the first (<).
-template <bool LE>
+template <int THREADS, bool LE>
 __device__ __forceinline__ void partition_pass(int *ind, float *key, int *pos, int begin, int end, int boundary, float cutval, int *sh)
 {
     const int len = end - begin;
-    const int seg = (len + kBuildThreads - 1) / kBuildThreads;
+    const int seg = (len + THREADS - 1) / THREADS;
     const int a = min(begin + (int)threadIdx.x * seg, end), b = min(a + seg, end);
     int cl = 0, cr = 0;
     for (int i = a; i < b; ++i)
@@ -113,8 +117,8 @@ __device__ __forceinline__ void partition_pass(int *ind, float *key, int *pos, i
         cr += (i >= boundary && p);
     }
     int m, m2;
-    int bl = block_exscan(cl, sh, m);
-    int br = block_exscan(cr, sh, m2);
+    int bl = block_exscan<THREADS>(cl, sh, m);
+    int br = block_exscan<THREADS>(cr, sh, m2);
     int *pos_l = pos + begin, *pos_r = pos + begin + (len + 1) / 2; // m <= len / 2: the two lists cannot overlap
     for (int i = a; i < b; ++i)
     {
@@ -123,7 +127,7 @@ __device__ __forceinline__ void partition_pass(int *ind, float *key, int *pos, i
         if (i >= boundary && p) pos_r[br++] = i;
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < m; k += kBuildThreads)
+    for (int k = threadIdx.x; k < m; k += THREADS)
     {
         const int i = pos_l[k], j = pos_r[m - 1 - k];
         const int ti = ind[i]; ind[i] = ind[j]; ind[j] = ti;
@@ -137,19 +141,20 @@ __global__ void kd_iota_kernel(int *vind, int n)
 }
 // divideTree (nanoflann.hpp:864-914) for one node per CTA; boxes = the LOOSE box handed down by the parent (it, not the tight
 // one, picks the cut dimension and the middle), 6 floats per node
-__global__ void __launch_bounds__(kBuildThreads) kd_split_kernel(const float *__restrict__ pts, int *vind, float *key, int *pos, KdNode *nodes,
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) kd_split_kernel(const float *__restrict__ pts, int *vind, float *key, int *pos, KdNode *nodes,
                                                                  float *boxes, const int *__restrict__ queue_in, int *queue_out, KdBuildCtl *ctl,
                                                                  int out_slot)
 {
-    __shared__ float shf[kBuildWarps];
-    __shared__ int shi[kBuildWarps];
+    __shared__ float shf[THREADS / 32];
+    __shared__ int shi[THREADS / 32];
     const int id = queue_in[blockIdx.x];
     const int left = nodes[id].left, right = nodes[id].right, count = right - left, level = nodes[id].level;
     int *ind = vind + left;
     float *ky = key + left;
     // computeMinMax of all three coordinates
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for (int i = threadIdx.x; i < count; i += kBuildThreads)
+    for (int i = threadIdx.x; i < count; i += THREADS)
     {
         const int j = ind[i];
 #pragma unroll
@@ -163,8 +168,8 @@ __global__ void __launch_bounds__(kBuildThreads) kd_split_kernel(const float *__
 #pragma unroll
     for (int d = 0; d < 3; ++d)
     {
-        mn[d] = block_reduce(mn[d], [](float x, float y) { return fminf(x, y); }, shf);
-        mx[d] = block_reduce(mx[d], [](float x, float y) { return fmaxf(x, y); }, shf);
+        mn[d] = block_reduce<THREADS>(mn[d], [](float x, float y) { return fminf(x, y); }, shf);
+        mx[d] = block_reduce<THREADS>(mx[d], [](float x, float y) { return fmaxf(x, y); }, shf);
     }
     float lo[3], hi[3];
     if (id == 0)
@@ -210,29 +215,29 @@ __global__ void __launch_bounds__(kBuildThreads) kd_split_kernel(const float *__
     const float cutval = split_val < mn_c ? mn_c : split_val > mx_c ? mx_c : split_val;
     // planeSplit (:974-1010): lim1 = #(< cutval), lim2 = lim1 + #(== cutval)
     int cl = 0, ce = 0;
-    for (int i = threadIdx.x; i < count; i += kBuildThreads)
+    for (int i = threadIdx.x; i < count; i += THREADS)
     {
         const float v = pts[3 * ind[i] + cutfeat];
         ky[i] = v;
         cl += v < cutval;
         ce += v == cutval;
     }
-    const int lim1 = block_reduce(cl, [](int x, int y) { return x + y; }, shi);
-    const int lim2 = lim1 + block_reduce(ce, [](int x, int y) { return x + y; }, shi);
-    partition_pass<false>(ind, ky, pos + left, 0, count, lim1, cutval, shi);
-    partition_pass<true>(ind, ky, pos + left, lim1, count, lim2, cutval, shi);
+    const int lim1 = block_reduce<THREADS>(cl, [](int x, int y) { return x + y; }, shi);
+    const int lim2 = lim1 + block_reduce<THREADS>(ce, [](int x, int y) { return x + y; }, shi);
+    partition_pass<THREADS, false>(ind, ky, pos + left, 0, count, lim1, cutval, shi);
+    partition_pass<THREADS, true>(ind, ky, pos + left, lim1, count, lim2, cutval, shi);
     const int half = count / 2;
     const int idx = lim1 > half ? lim1 : lim2 < half ? lim2 : half;
     // the children's tight extent along the cut: divlow = left_bbox[cutfeat].high, divhigh = right_bbox[cutfeat].low (:904-905)
     float dl = -FLT_MAX, dh = FLT_MAX;
-    for (int i = threadIdx.x; i < count; i += kBuildThreads)
+    for (int i = threadIdx.x; i < count; i += THREADS)
     {
         const float v = ky[i];
         if (i < idx) dl = fmaxf(dl, v);
         else dh = fminf(dh, v);
     }
-    dl = block_reduce(dl, [](float x, float y) { return fmaxf(x, y); }, shf);
-    dh = block_reduce(dh, [](float x, float y) { return fminf(x, y); }, shf);
+    dl = block_reduce<THREADS>(dl, [](float x, float y) { return fmaxf(x, y); }, shf);
+    dh = block_reduce<THREADS>(dh, [](float x, float y) { return fminf(x, y); }, shf);
     if (threadIdx.x == 0)
     {
         const int c = atomicAdd(&ctl->n_nodes, 2);
@@ -251,7 +256,17 @@ __global__ void __launch_bounds__(kBuildThreads) kd_split_kernel(const float *__
         nodes[id].divlow = dl; nodes[id].divhigh = dh;
         if (idx > kLeafMax) queue_out[atomicAdd(&ctl->queue_count[out_slot], 1)] = c;
         if (count - idx > kLeafMax) queue_out[atomicAdd(&ctl->queue_count[out_slot], 1)] = c + 1;
+        atomicMax(&ctl->queue_max[out_slot], max(idx, count - idx));
         atomicMax(&ctl->max_level, level + 1);
+    }
+}
+
+__global__ void kd_reorder_kernel(const float *__restrict__ pts, const int *__restrict__ vind, int n, float4 *__restrict__ sorted)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const int v = vind[i];
+        sorted[i] = make_float4(pts[3 * v], pts[3 * v + 1], pts[3 * v + 2], __int_as_float(v));
     }
 }
 
@@ -266,9 +281,9 @@ __device__ __forceinline__ void put3(float *v, int i, float x)
     else v[2] = x;
 }
 // L2_Simple_Adaptor::evalMetric (:438-446): result += diff * diff, dimension by dimension
-__device__ __forceinline__ float kd_dist2(const float *q, const float *__restrict__ pts, int j)
+__device__ __forceinline__ float kd_dist2(const float *q, const float4 p)
 {
-    const float dx = fsub(q[0], pts[3 * j]), dy = fsub(q[1], pts[3 * j + 1]), dz = fsub(q[2], pts[3 * j + 2]);
+    const float dx = fsub(q[0], p.x), dy = fsub(q[1], p.y), dz = fsub(q[2], p.z);
     return fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
 }
 // KNNResultSet (:150-204): a new point goes BEHIND the stored points of equal distance
@@ -355,10 +370,10 @@ __device__ bool kd_find(const KdView &t, ResultSet &rs, const float *q, float ep
                 const float worst = rs.worst();
                 for (int i = nd.left; i < nd.right; ++i)
                 {
-                    const int index = t.vind[i];
-                    const float d = kd_dist2(q, t.pts, index);
+                    const float4 p = t.sorted[i];
+                    const float d = kd_dist2(q, p);
                     if (d < worst)
-                        if (!rs.add(d, index)) return false;
+                        if (!rs.add(d, __float_as_int(p.w))) return false;
                 }
                 --sp;
                 continue;
@@ -568,20 +583,26 @@ __global__ void __launch_bounds__(kQueryThreads) kd_knn_kernel(KdView t, const f
     }
 }
 // RadiusSearch (KDTree.h:125-143): up to `cap` hits with dist^2 < radius in traversal order, std::sort, the first k kept.
-// Queries q0 .. q0 + nq of one batch; scratch holds cap x stride (distance, index) entries.
-__global__ void __launch_bounds__(kQueryThreads) kd_radius_kernel(KdView t, const float *__restrict__ queries, int q0, int nq, int k, int cap, float radius,
-                                                                  float *scratch_d, int *scratch_i, int stride, int *__restrict__ out_index,
-                                                                  float *__restrict__ out_dist, int *__restrict__ out_count)
+// Queries q0 .. q0 + nq of one batch (taken in the tree's leaf order when they are the tree's own points: `order` = vind, so the
+// threads of a warp walk the same part of the tree).  The hits of a thread live in shared memory (cap x blockDim entries) when
+// scratch_d is NULL, else in a global scratch of cap x stride entries.
+__global__ void __launch_bounds__(kQueryThreads) kd_radius_kernel(KdView t, const float *__restrict__ queries, const int *__restrict__ order, int q0,
+                                                                  int nq, int k, int cap, float radius, float *scratch_d, int *scratch_i, int stride,
+                                                                  int *__restrict__ out_index, float *__restrict__ out_dist,
+                                                                  int *__restrict__ out_count)
 {
+    extern __shared__ float knn_smem[];
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nq; s += gridDim.x * blockDim.x)
     {
-        const int qi = q0 + s;
+        const int qi = order ? order[q0 + s] : q0 + s;
         const float q[3] = {queries[3 * qi], queries[3 * qi + 1], queries[3 * qi + 2]};
         RadiusSet rs;
-        rs.d = scratch_d + s; rs.i = scratch_i + s; rs.stride = stride; rs.count = 0; rs.capacity = cap; rs.radius = radius;
+        if (scratch_d) { rs.d = scratch_d + s; rs.i = scratch_i + s; rs.stride = stride; }
+        else { rs.d = knn_smem + threadIdx.x; rs.i = reinterpret_cast<int *>(knn_smem + cap * blockDim.x) + threadIdx.x; rs.stride = blockDim.x; }
+        rs.count = 0; rs.capacity = cap; rs.radius = radius;
         kd_find(t, rs, q, 1.0f + 1e-8f); // SearchParameter's eps (KDTree.h:19): 1 + 1e-8 rounds to 1 in float, like the reference's
         HitArray A;
-        A.d = rs.d; A.i = rs.i; A.stride = stride;
+        A.d = rs.d; A.i = rs.i; A.stride = rs.stride;
         hit_std_sort(A, rs.count);
         const int cnt = rs.count > k ? k : rs.count;
         out_count[qi] = cnt;
@@ -596,9 +617,12 @@ __global__ void __launch_bounds__(kQueryThreads) kd_radius_kernel(KdView t, cons
 __global__ void __launch_bounds__(kQueryThreads) kd_normals_kernel(KdView t, int k, float radius, float *__restrict__ normals)
 {
     extern __shared__ float knn_smem[];
-    for (int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < t.n; qi += gridDim.x * blockDim.x)
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < t.n; slot += gridDim.x * blockDim.x)
     {
-        const float q[3] = {t.pts[3 * qi], t.pts[3 * qi + 1], t.pts[3 * qi + 2]};
+        // queries in the tree's leaf order: the threads of a warp walk the same part of the tree
+        const float4 self = t.sorted[slot];
+        const int qi = __float_as_int(self.w);
+        const float q[3] = {self.x, self.y, self.z};
         KnnSet rs;
         rs.init(knn_smem, k);
         kd_find(t, rs, q, 1.0f);
@@ -737,6 +761,7 @@ struct opb_kdtree
     cudaStream_t stream = nullptr;
     size_t cap_points = 0, n = 0;
     float *d_pts = nullptr, *d_key = nullptr, *d_boxes = nullptr;
+    float4 *d_sorted = nullptr;
     int *d_vind = nullptr, *d_pos = nullptr, *d_queue[2] = {nullptr, nullptr};
     KdNode *d_nodes = nullptr;
     KdBuildCtl *d_ctl = nullptr, *h_ctl = nullptr;
@@ -762,7 +787,7 @@ static int kd_reserve(void **p, size_t *have, size_t want)
 static KdView kd_view(const opb_kdtree *t)
 {
     KdView v;
-    v.pts = t->d_pts; v.vind = t->d_vind; v.nodes = t->d_nodes; v.n = (int)t->n;
+    v.pts = t->d_pts; v.sorted = t->d_sorted; v.vind = t->d_vind; v.nodes = t->d_nodes; v.n = (int)t->n;
     for (int d = 0; d < 3; ++d) { v.root_lo[d] = t->h_ctl->root_lo[d]; v.root_hi[d] = t->h_ctl->root_hi[d]; }
     return v;
 }
@@ -801,7 +826,7 @@ void opb_kdtree_destroy(opb_kdtree *t)
 {
     if (!t) return;
     cudaSetDevice(t->device);
-    cudaFree(t->d_pts); cudaFree(t->d_key); cudaFree(t->d_boxes); cudaFree(t->d_vind); cudaFree(t->d_pos);
+    cudaFree(t->d_pts); cudaFree(t->d_key); cudaFree(t->d_boxes); cudaFree(t->d_vind); cudaFree(t->d_pos); cudaFree(t->d_sorted);
     cudaFree(t->d_queue[0]); cudaFree(t->d_queue[1]); cudaFree(t->d_nodes); cudaFree(t->d_ctl); cudaFree(t->d_scratch);
     for (int i = 0; i < 4; ++i) cudaFree(t->d_aux[i]);
     if (t->h_ctl) cudaFreeHost(t->h_ctl);
@@ -817,13 +842,15 @@ int opb_kdtree_build(opb_kdtree *t, const float *xyz, size_t n)
     t->n = n;
     if (n > t->cap_points)
     {
-        cudaFree(t->d_pts); cudaFree(t->d_key); cudaFree(t->d_boxes); cudaFree(t->d_vind); cudaFree(t->d_pos);
+        cudaFree(t->d_pts); cudaFree(t->d_key); cudaFree(t->d_boxes); cudaFree(t->d_vind); cudaFree(t->d_pos); cudaFree(t->d_sorted);
         cudaFree(t->d_queue[0]); cudaFree(t->d_queue[1]); cudaFree(t->d_nodes);
+        t->d_sorted = nullptr;
         t->d_pts = t->d_key = t->d_boxes = nullptr; t->d_vind = t->d_pos = t->d_queue[0] = t->d_queue[1] = nullptr; t->d_nodes = nullptr;
         t->cap_points = 0;
         const size_t cap = n + n / 8 + 1024, nodes = 2 * cap + 2;
         OPB_CUDA(cudaMalloc((void **)&t->d_pts, cap * 3 * sizeof(float)));
         OPB_CUDA(cudaMalloc((void **)&t->d_key, cap * sizeof(float)));
+        OPB_CUDA(cudaMalloc((void **)&t->d_sorted, cap * sizeof(float4)));
         OPB_CUDA(cudaMalloc((void **)&t->d_vind, cap * sizeof(int)));
         OPB_CUDA(cudaMalloc((void **)&t->d_pos, cap * sizeof(int)));
         OPB_CUDA(cudaMalloc((void **)&t->d_queue[0], nodes * sizeof(int)));
@@ -847,20 +874,30 @@ int opb_kdtree_build(opb_kdtree *t, const float *xyz, size_t n)
     OPB_CUDA(cudaMemcpyAsync(t->d_queue[0], &zero, sizeof(int), cudaMemcpyHostToDevice, s));
     OPB_CUDA(cudaMemcpyAsync(t->d_ctl, t->h_ctl, sizeof(KdBuildCtl), cudaMemcpyHostToDevice, s));
     OPB_CUDA(cudaStreamSynchronize(s)); // root / zero are stack variables
-    int in_count = 1, slot = 0;
+    int in_count = 1, slot = 0, largest = (int)n;
     for (int level = 0; in_count > 0; ++level)
     {
         if (level > 4 * kMaxDepth) { set_error("kd-tree build did not terminate"); return OPB_ERR_UNSUPPORTED; }
         const int out_slot = slot ^ 1;
         OPB_CUDA(cudaMemsetAsync(&t->d_ctl->queue_count[out_slot], 0, sizeof(int), s));
-        kd_split_kernel<<<in_count, kBuildThreads, 0, s>>>(t->d_pts, t->d_vind, t->d_key, t->d_pos, t->d_nodes, t->d_boxes, t->d_queue[slot],
-                                                           t->d_queue[out_slot], t->d_ctl, out_slot);
+        OPB_CUDA(cudaMemsetAsync(&t->d_ctl->queue_max[out_slot], 0, sizeof(int), s));
+        // one CTA per node, sized for the largest node of the level: the top of the tree is a few very long nodes
+#define OPB_KD_SPLIT(THREADS)                                                                                                                      \
+    kd_split_kernel<THREADS><<<in_count, THREADS, 0, s>>>(t->d_pts, t->d_vind, t->d_key, t->d_pos, t->d_nodes, t->d_boxes, t->d_queue[slot], \
+                                                          t->d_queue[out_slot], t->d_ctl, out_slot)
+        if (largest > kBuildBigNode) OPB_KD_SPLIT(kBuildThreadsBig);
+        else if (largest > kBuildSmallNode) OPB_KD_SPLIT(kBuildThreadsMid);
+        else OPB_KD_SPLIT(kBuildThreadsSmall);
+#undef OPB_KD_SPLIT
         OPB_CUDA(cudaGetLastError());
         OPB_CUDA(cudaMemcpyAsync(t->h_ctl, t->d_ctl, sizeof(KdBuildCtl), cudaMemcpyDeviceToHost, s));
         OPB_CUDA(cudaStreamSynchronize(s));
         in_count = t->h_ctl->queue_count[out_slot];
+        largest = t->h_ctl->queue_max[out_slot];
         slot = out_slot;
     }
+    kd_reorder_kernel<<<kd_grid(t, n, 8), kQueryThreads, 0, s>>>(t->d_pts, t->d_vind, (int)n, t->d_sorted);
+    OPB_CUDA(cudaGetLastError());
     t->n_nodes = t->h_ctl->n_nodes;
     t->max_level = t->h_ctl->max_level;
     if (t->max_level + 2 > kMaxDepth)
@@ -898,17 +935,30 @@ int opb_kdtree_dump(opb_kdtree *t, int32_t *vind, int32_t *node_ints, float *nod
 static int kd_radius_rows(opb_kdtree *t, const float *d_queries, size_t nq, int k, float radius, int *d_index, float *d_dist, int *d_count)
 {
     const int cap = (int)(size_t)(k * 2.5);
+    const KdView v = kd_view(t);
+    const int *order = d_queries == t->d_pts ? t->d_vind : nullptr; // the tree's own points are queried in leaf order
+    // one warp per CTA with the hits of its 32 threads in shared memory (8 B x cap x 32) when that fits -- the sort walks them
+    // thousands of times --, else a global scratch
+    const size_t smem = (size_t)cap * 32 * 8;
+    if (smem <= 96 * 1024)
+    {
+        OPB_CUDA(cudaFuncSetAttribute(kd_radius_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        const size_t blocks = (nq + 31) / 32, limit = (size_t)t->sm_count * 64;
+        kd_radius_kernel<<<(unsigned)(blocks < limit ? blocks : limit), 32, smem, t->stream>>>(v, d_queries, order, 0, (int)nq, k, cap, radius, nullptr,
+                                                                                               nullptr, 0, d_index, d_dist, d_count);
+        OPB_CUDA(cudaGetLastError());
+        return OPB_OK;
+    }
     const size_t batch = nq < (size_t)kQueryBatch ? nq : (size_t)kQueryBatch;
     int rc = kd_reserve(&t->d_scratch, &t->scratch_bytes, batch * (size_t)cap * 8);
     if (rc) return rc;
     float *sd = (float *)t->d_scratch;
     int *si = (int *)(sd + batch * (size_t)cap);
-    const KdView v = kd_view(t);
     for (size_t q0 = 0; q0 < nq; q0 += batch)
     {
         const size_t m = nq - q0 < batch ? nq - q0 : batch;
-        kd_radius_kernel<<<kd_grid(t, m, 16), kQueryThreads, 0, t->stream>>>(v, d_queries, (int)q0, (int)m, k, cap, radius, sd, si, (int)batch, d_index,
-                                                                             d_dist, d_count);
+        kd_radius_kernel<<<kd_grid(t, m, 16), kQueryThreads, 0, t->stream>>>(v, d_queries, order, (int)q0, (int)m, k, cap, radius, sd, si, (int)batch,
+                                                                             d_index, d_dist, d_count);
         OPB_CUDA(cudaGetLastError());
     }
     return OPB_OK;

@@ -2,7 +2,10 @@
 // by tests/test_kdtree_emulated.py into kdtree_device.inc) on the host emulator in cuda_emu.h, driven the way the library's host
 // code drives it, so the build / search / sort / FPFH kernels can be compared with the oracle without a GPU.
 #include "opb_common.cuh"
-namespace opb { float knn_smem[64 * 128 * 2]; }
+namespace opb { float knn_smem[1 << 17]; } // stands in for the kernels' dynamic shared memory
+#ifndef EMU_BUILD_THREADS
+#define EMU_BUILD_THREADS 64
+#endif
 #include "kdtree_device.inc"
 
 using namespace opb;
@@ -10,6 +13,7 @@ using namespace opb;
 struct Tree
 {
     std::vector<float> pts, key, boxes;
+    std::vector<float4> sorted;
     std::vector<int> vind, pos, queue[2];
     std::vector<KdNode> nodes;
     KdBuildCtl ctl;
@@ -17,7 +21,7 @@ struct Tree
     KdView view() const
     {
         KdView v;
-        v.pts = pts.data(); v.vind = vind.data(); v.nodes = nodes.data(); v.n = n;
+        v.pts = pts.data(); v.sorted = sorted.data(); v.vind = vind.data(); v.nodes = nodes.data(); v.n = n;
         for (int d = 0; d < 3; ++d) { v.root_lo[d] = ctl.root_lo[d]; v.root_hi[d] = ctl.root_hi[d]; }
         return v;
     }
@@ -31,7 +35,7 @@ void *emu_build(const float *xyz, long n)
     Tree *t = new Tree();
     t->n = (int)n;
     t->pts.assign(xyz, xyz + 3 * n);
-    t->key.resize(n + 1); t->vind.resize(n + 1); t->pos.resize(n + 1);
+    t->key.resize(n + 1); t->vind.resize(n + 1); t->pos.resize(n + 1); t->sorted.resize(n + 1);
     t->nodes.resize(2 * n + 2); t->boxes.resize(6 * (2 * n + 2));
     t->queue[0].resize(2 * n + 2); t->queue[1].resize(2 * n + 2);
     memset(&t->ctl, 0, sizeof t->ctl);
@@ -47,13 +51,15 @@ void *emu_build(const float *xyz, long n)
     {
         const int out_slot = slot ^ 1;
         t->ctl.queue_count[out_slot] = 0;
-        emu::launch(in_count, kBuildThreads, [&] {
-            kd_split_kernel(t->pts.data(), t->vind.data(), t->key.data(), t->pos.data(), t->nodes.data(), t->boxes.data(), t->queue[slot].data(),
+        t->ctl.queue_max[out_slot] = 0;
+        emu::launch(in_count, EMU_BUILD_THREADS, [&] {
+            kd_split_kernel<EMU_BUILD_THREADS>(t->pts.data(), t->vind.data(), t->key.data(), t->pos.data(), t->nodes.data(), t->boxes.data(), t->queue[slot].data(),
                             t->queue[out_slot].data(), &t->ctl, out_slot);
         });
         in_count = t->ctl.queue_count[out_slot];
         slot = out_slot;
     }
+    emu::launch(grid_for(n, 4), kQueryThreads, [&] { kd_reorder_kernel(t->pts.data(), t->vind.data(), (int)n, t->sorted.data()); });
     return t;
 }
 void emu_destroy(void *p) { delete (Tree *)p; }
@@ -79,8 +85,13 @@ void emu_search(void *p, const float *queries, long nq, int mode, int k, float r
         const int cap = (int)(size_t)(k * 2.5);
         std::vector<float> sd((size_t)nq * cap + 1);
         std::vector<int> si((size_t)nq * cap + 1);
-        emu::launch(grid_for(nq, 4), kQueryThreads,
-                    [&] { kd_radius_kernel(v, queries, 0, (int)nq, k, cap, radius, sd.data(), si.data(), (int)nq, out_index, out_dist, out_count); });
+        if ((size_t)cap * 32 * 2 <= sizeof(knn_smem) / sizeof(float) && k != 20) // the library's one-warp CTAs with the hits in shared memory
+            emu::launch((int)std::min<long>((nq + 31) / 32, 8), 32,
+                        [&] { kd_radius_kernel(v, queries, nullptr, 0, (int)nq, k, cap, radius, nullptr, nullptr, 0, out_index, out_dist, out_count); });
+        else
+            emu::launch(grid_for(nq, 4), kQueryThreads, [&] {
+                kd_radius_kernel(v, queries, nullptr, 0, (int)nq, k, cap, radius, sd.data(), si.data(), (int)nq, out_index, out_dist, out_count);
+            });
     }
     else
         emu::launch(grid_for(nq, 4), kQueryThreads, [&] { kd_knn_kernel(v, queries, (int)nq, mode, k, radius, out_index, out_dist, out_count); });
@@ -99,8 +110,10 @@ void emu_fpfh(void *p, const float *normals, int knn, float radius, float *featu
     const int cap = (int)(size_t)(knn * 2.5);
     std::vector<float> sd((size_t)n * cap + 1), spfh((size_t)n * 33 + 1);
     std::vector<int> si((size_t)n * cap + 1), nbr((size_t)n * knn + 1), cnt(n + 1);
-    emu::launch(grid_for(n, 4), kQueryThreads,
-                [&] { kd_radius_kernel(v, t->pts.data(), 0, (int)n, knn, cap, radius, sd.data(), si.data(), (int)n, nbr.data(), nullptr, cnt.data()); });
+    // the tree's own points, in leaf order, hits in shared memory: what opb_kdtree_fpfh launches
+    emu::launch((int)std::min<long>((n + 31) / 32, 8), 32, [&] {
+        kd_radius_kernel(v, t->pts.data(), t->vind.data(), 0, (int)n, knn, cap, radius, nullptr, nullptr, 0, nbr.data(), nullptr, cnt.data());
+    });
     emu::launch(grid_for(n, 3), kQueryThreads, [&] { fpfh_spfh_kernel(t->pts.data(), normals, (int)n, knn, nbr.data(), cnt.data(), spfh.data()); });
     emu::launch(grid_for(n * 32, 5), kQueryThreads, [&] { fpfh_combine_kernel(t->pts.data(), (int)n, knn, nbr.data(), cnt.data(), spfh.data(), features); });
 }

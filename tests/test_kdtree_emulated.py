@@ -23,9 +23,8 @@ def emu(tmp_path_factory):
     a = src.index("namespace opb\n{")
     b = src.index("} // namespace opb\n\nusing namespace opb;") + len("} // namespace opb\n")
     dev = src[a:b].replace("extern __shared__ float knn_smem[];", "")
-    # 64 threads per building CTA keep the emulation fast (the -m gpu tests run the real 256)
-    dev = dev.replace("constexpr int kBuildThreads = 256;", "constexpr int kBuildThreads = 64;")
-    assert "kBuildThreads = 64" in dev
+    # the harness instantiates the building kernel with 64 threads per CTA, which keeps the emulation fast (the -m gpu tests run
+    # all three CTA sizes the library picks from)
     open(os.path.join(out, "kdtree_device.inc"), "w").write('#include "opb_fitplane.cuh"\n' + dev)
     shutil.copy(os.path.join(ROOT, "onepiece_b200", "csrc", "opb_fitplane.cuh"), out)
     for f in ("cuda_emu.h", "kdtree_emu.cpp", os.path.join("stubs", "opb_common.cuh")):
@@ -63,10 +62,10 @@ def canonical_tree(ni, nf):
 
 def clouds():
     rng = np.random.default_rng(3)
-    u = rng.uniform(-1, 1, (700, 2)).astype(np.float32)
+    u = rng.uniform(-1, 1, (400, 2)).astype(np.float32)
     z = (2.0 + 0.3 * np.sin(3 * u[:, 0]) * np.cos(2 * u[:, 1])).astype(np.float32)
-    yield "surface", (np.stack([u[:, 0], u[:, 1], z], 1) + rng.normal(0, 0.002, (700, 3))).astype(np.float32)
-    g = np.stack(np.meshgrid(np.arange(16), np.arange(16), np.arange(2), indexing="ij"), -1).reshape(-1, 3).astype(np.float32) * 0.02
+    yield "surface", (np.stack([u[:, 0], u[:, 1], z], 1) + rng.normal(0, 0.002, (400, 3))).astype(np.float32)
+    g = np.stack(np.meshgrid(np.arange(12), np.arange(12), np.arange(2), indexing="ij"), -1).reshape(-1, 3).astype(np.float32) * 0.02
     yield "lattice", g[rng.permutation(len(g))]
     d = rng.uniform(-1, 1, (300, 3)).astype(np.float32)
     yield "duplicates", np.concatenate([d, d[:150], d[:50]])
@@ -96,7 +95,8 @@ def test_emulated_device_code_matches_the_oracle(emu, name, pts):
         on = oracleapi.estimate_normals(pts, 0.1, 30)
         assert np.array_equal(nrm.view(np.uint32), on.view(np.uint32))
         on = np.nan_to_num(on)
-        for knn, radius in [(100, 0.1), (40, 0.25)]:
+        # the warp-per-point FPFH kernel shuffles per neighbour, which the emulator pays with two barriers each: small cases only
+        for knn, radius in {"surface": [(40, 0.25)], "lattice": [(60, 0.1)], "eleven": [(100, 0.1), (40, 0.25)]}.get(name, []):
             f = np.zeros((n, 33), np.float32)
             emu.emu_fpfh(h, _ptr(on), knn, radius, _ptr(f))
             of = oracleapi.fpfh(pts, on, knn, radius)
