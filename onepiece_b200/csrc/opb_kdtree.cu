@@ -337,10 +337,13 @@ struct RadiusSet
         return true;
     }
 };
-struct KdFrame
+// one level of searchLevel's recursion, 16 bytes so that a frame moves as one vector access: `node` is the node to visit until
+// it has been expanded and the far child afterwards; `value` is the node's mindistsq until the near child returns and the saved
+// side distance afterwards
+struct __align__(16) KdFrame
 {
-    int node, other, idx_stage;
-    float mind, dst, cut;
+    int node, idx_stage;
+    float value, cut;
 };
 // findNeighbors + searchLevel (:1228-1248, :1354-1417); false when the result set asked to stop
 template <class ResultSet>
@@ -357,10 +360,10 @@ __device__ bool kd_find(const KdView &t, ResultSet &rs, const float *q, float ep
     }
     KdFrame st[kMaxDepth];
     int sp = 0;
-    st[0].node = 0; st[0].idx_stage = 0; st[0].mind = distsq;
+    st[0].node = 0; st[0].idx_stage = 0; st[0].value = distsq; st[0].cut = 0.0f;
     while (sp >= 0)
     {
-        KdFrame &f = st[sp];
+        KdFrame f = st[sp];
         const int stage = f.idx_stage & 3, idx = f.idx_stage >> 2;
         if (stage == 0)
         {
@@ -382,26 +385,26 @@ __device__ bool kd_find(const KdView &t, ResultSet &rs, const float *q, float ep
             const float val = pick3(q, cf);
             const float diff1 = fsub(val, nd.divlow), diff2 = fsub(val, nd.divhigh);
             int best;
-            if (fadd(diff1, diff2) < 0.0f) { best = nd.child1; f.other = nd.child2; f.cut = fmul(diff2, diff2); }
-            else { best = nd.child2; f.other = nd.child1; f.cut = fmul(diff1, diff1); }
+            if (fadd(diff1, diff2) < 0.0f) { best = nd.child1; f.node = nd.child2; f.cut = fmul(diff2, diff2); }
+            else { best = nd.child2; f.node = nd.child1; f.cut = fmul(diff1, diff1); }
             f.idx_stage = (cf << 2) | 1;
-            const float mind = f.mind;
+            st[sp] = f;
             if (sp + 1 >= kMaxDepth) return true; // the host refuses trees deeper than kMaxDepth - 2 before any search
             ++sp;
-            st[sp].node = best; st[sp].idx_stage = 0; st[sp].mind = mind;
+            st[sp].node = best; st[sp].idx_stage = 0; st[sp].value = f.value; st[sp].cut = 0.0f;
         }
         else if (stage == 1)
         {
             const float dst = pick3(dists, idx);
-            const float mind = fsub(fadd(f.mind, f.cut), dst);
+            const float mind = fsub(fadd(f.value, f.cut), dst);
             put3(dists, idx, f.cut);
-            f.dst = dst;
             if (fmul(mind, eps_error) <= rs.worst())
             {
                 f.idx_stage = (idx << 2) | 2;
-                const int other = f.other;
+                f.value = dst;
+                st[sp] = f;
                 ++sp;
-                st[sp].node = other; st[sp].idx_stage = 0; st[sp].mind = mind;
+                st[sp].node = f.node; st[sp].idx_stage = 0; st[sp].value = mind; st[sp].cut = 0.0f;
             }
             else
             {
@@ -411,7 +414,7 @@ __device__ bool kd_find(const KdView &t, ResultSet &rs, const float *q, float ep
         }
         else
         {
-            put3(dists, idx, f.dst);
+            put3(dists, idx, f.value);
             --sp;
         }
     }

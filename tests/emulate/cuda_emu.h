@@ -22,6 +22,7 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
+#define __align__(n) alignas(n)
 
 struct Dim3 { int x = 1, y = 1, z = 1; };
 inline thread_local Dim3 threadIdx, blockIdx;
