@@ -35,10 +35,12 @@
 
 namespace cv
 {
+class Mat;
 template <typename T, int N> struct Vec
 {
     T val[N];
     Vec() { for (int i = 0; i < N; ++i) val[i] = T(0); }
+    Vec(const Mat &) { for (int i = 0; i < N; ++i) val[i] = T(0); } // only GlobalRegistration.cpp's unused Eigen2OpenCV needs it to parse
     Vec(T a, T b) { static_assert(N >= 2, ""); val[0] = a; val[1] = b; for (int i = 2; i < N; ++i) val[i] = T(0); }
     Vec(T a, T b, T c) { static_assert(N >= 3, ""); val[0] = a; val[1] = b; val[2] = c; for (int i = 3; i < N; ++i) val[i] = T(0); }
     T &operator[](int i) { return val[i]; }

@@ -1783,6 +1783,7 @@ void orc_estimate_normals(const float *pts, long n, float radius, int knn, float
  * Everything here is what decides WHICH neighbours come back and IN WHAT ORDER when distances tie or when the radius
  * search stops early, which the float sums downstream (FitPlane, FPFH) depend on.
  * ------------------------------------------------------------------------------------------------------------------ */
+#define KD_MAX_DIM 33
 typedef struct { int left, right, child1, child2, divfeat; float divlow, divhigh; } kd_node;
 typedef struct
 {
@@ -1790,16 +1791,16 @@ typedef struct
     long n;
     int *vind;
     kd_node *nodes;
-    int n_nodes, leaf_max;
-    float root_lo[3], root_hi[3];
+    int n_nodes, leaf_max, dim; /* dim = 3 (points) or 33 (FPFH features, KDTree<33>) */
+    float root_lo[KD_MAX_DIM], root_hi[KD_MAX_DIM];
 } kd_tree;
 
 static void kd_minmax(const kd_tree *t, const int *ind, int count, int e, float *mn, float *mx)
 {
-    *mn = *mx = t->pts[3 * ind[0] + e];
+    *mn = *mx = t->pts[t->dim * ind[0] + e];
     for (int i = 1; i < count; ++i)
     {
-        const float v = t->pts[3 * ind[i] + e];
+        const float v = t->pts[t->dim * ind[i] + e];
         if (v < *mn) *mn = v;
         if (v > *mx) *mx = v;
     }
@@ -1810,8 +1811,8 @@ static void kd_plane_split(const kd_tree *t, int *ind, unsigned count, int cutfe
     unsigned left = 0, right = count - 1;
     for (;;)
     {
-        while (left <= right && t->pts[3 * ind[left] + cutfeat] < cutval) ++left;
-        while (right && left <= right && t->pts[3 * ind[right] + cutfeat] >= cutval) --right;
+        while (left <= right && t->pts[t->dim * ind[left] + cutfeat] < cutval) ++left;
+        while (right && left <= right && t->pts[t->dim * ind[right] + cutfeat] >= cutval) --right;
         if (left > right || !right) break;
         int tmp = ind[left]; ind[left] = ind[right]; ind[right] = tmp;
         ++left; --right;
@@ -1820,8 +1821,8 @@ static void kd_plane_split(const kd_tree *t, int *ind, unsigned count, int cutfe
     right = count - 1;
     for (;;)
     {
-        while (left <= right && t->pts[3 * ind[left] + cutfeat] <= cutval) ++left;
-        while (right && left <= right && t->pts[3 * ind[right] + cutfeat] > cutval) --right;
+        while (left <= right && t->pts[t->dim * ind[left] + cutfeat] <= cutval) ++left;
+        while (right && left <= right && t->pts[t->dim * ind[right] + cutfeat] > cutval) --right;
         if (left > right || !right) break;
         int tmp = ind[left]; ind[left] = ind[right]; ind[right] = tmp;
         ++left; --right;
@@ -1837,11 +1838,11 @@ static int kd_divide(kd_tree *t, int left, int right, float *lo, float *hi)
     if (right - left <= t->leaf_max)
     {
         node->child1 = node->child2 = -1; node->divfeat = -1; node->divlow = node->divhigh = 0.0f;
-        for (int i = 0; i < 3; ++i) lo[i] = hi[i] = t->pts[3 * t->vind[left] + i];
+        for (int i = 0; i < t->dim; ++i) lo[i] = hi[i] = t->pts[t->dim * t->vind[left] + i];
         for (int k = left + 1; k < right; ++k)
-            for (int i = 0; i < 3; ++i)
+            for (int i = 0; i < t->dim; ++i)
             {
-                const float v = t->pts[3 * t->vind[k] + i];
+                const float v = t->pts[t->dim * t->vind[k] + i];
                 if (lo[i] > v) lo[i] = v;
                 if (hi[i] < v) hi[i] = v;
             }
@@ -1852,10 +1853,10 @@ static int kd_divide(kd_tree *t, int left, int right, float *lo, float *hi)
     const unsigned count = (unsigned)(right - left);
     const float eps = 0.00001f;
     float max_span = hi[0] - lo[0];
-    for (int i = 1; i < 3; ++i) { const float span = hi[i] - lo[i]; if (span > max_span) max_span = span; }
+    for (int i = 1; i < t->dim; ++i) { const float span = hi[i] - lo[i]; if (span > max_span) max_span = span; }
     float max_spread = -1.0f;
     int cutfeat = 0;
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < t->dim; ++i)
     {
         const float span = hi[i] - lo[i];
         if (span > (1 - eps) * max_span)
@@ -1874,8 +1875,9 @@ static int kd_divide(kd_tree *t, int left, int right, float *lo, float *hi)
     kd_plane_split(t, ind, count, cutfeat, cutval, &lim1, &lim2);
     if (lim1 > count / 2) idx = lim1; else if (lim2 < count / 2) idx = lim2; else idx = count / 2;
 
-    float llo[3], lhi[3], rlo[3], rhi[3];
-    memcpy(llo, lo, sizeof llo); memcpy(lhi, hi, sizeof lhi); memcpy(rlo, lo, sizeof rlo); memcpy(rhi, hi, sizeof rhi);
+    float llo[KD_MAX_DIM], lhi[KD_MAX_DIM], rlo[KD_MAX_DIM], rhi[KD_MAX_DIM];
+    const size_t box_bytes = sizeof(float) * (size_t)t->dim;
+    memcpy(llo, lo, box_bytes); memcpy(lhi, hi, box_bytes); memcpy(rlo, lo, box_bytes); memcpy(rhi, hi, box_bytes);
     lhi[cutfeat] = cutval;
     const int c1 = kd_divide(t, left, left + (int)idx, llo, lhi);
     rlo[cutfeat] = cutval;
@@ -1883,28 +1885,29 @@ static int kd_divide(kd_tree *t, int left, int right, float *lo, float *hi)
     node = &t->nodes[id];
     node->child1 = c1; node->child2 = c2; node->divfeat = cutfeat;
     node->divlow = lhi[cutfeat]; node->divhigh = rlo[cutfeat];
-    for (int i = 0; i < 3; ++i) { lo[i] = llo[i] < rlo[i] ? llo[i] : rlo[i]; hi[i] = lhi[i] > rhi[i] ? lhi[i] : rhi[i]; }
+    for (int i = 0; i < t->dim; ++i) { lo[i] = rlo[i] < llo[i] ? rlo[i] : llo[i]; hi[i] = lhi[i] < rhi[i] ? rhi[i] : lhi[i]; } /* std::min / std::max: the first argument wins against NaN */
     return id;
 }
-static kd_tree *kd_build(const float *pts, long n, int leaf_max)
+static kd_tree *kd_build_dim(const float *pts, long n, int leaf_max, int dim)
 {
     kd_tree *t = (kd_tree *)calloc(1, sizeof *t);
-    t->pts = pts; t->n = n; t->leaf_max = leaf_max;
+    t->pts = pts; t->n = n; t->leaf_max = leaf_max; t->dim = dim;
     t->vind = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
     t->nodes = (kd_node *)malloc(sizeof(kd_node) * (size_t)(2 * n + 1));
     for (long i = 0; i < n; ++i) t->vind[i] = (int)i;
     if (n == 0) return t;
     /* computeBoundingBox :1324-1350 */
-    for (int i = 0; i < 3; ++i) t->root_lo[i] = t->root_hi[i] = pts[i];
+    for (int i = 0; i < t->dim; ++i) t->root_lo[i] = t->root_hi[i] = pts[i];
     for (long k = 1; k < n; ++k)
-        for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < t->dim; ++i)
         {
-            if (pts[3 * k + i] < t->root_lo[i]) t->root_lo[i] = pts[3 * k + i];
-            if (pts[3 * k + i] > t->root_hi[i]) t->root_hi[i] = pts[3 * k + i];
+            if (pts[t->dim * k + i] < t->root_lo[i]) t->root_lo[i] = pts[t->dim * k + i];
+            if (pts[t->dim * k + i] > t->root_hi[i]) t->root_hi[i] = pts[t->dim * k + i];
         }
     kd_divide(t, 0, (int)n, t->root_lo, t->root_hi);
     return t;
 }
+static kd_tree *kd_build(const float *pts, long n, int leaf_max) { return kd_build_dim(pts, n, leaf_max, 3); }
 static void kd_free(kd_tree *t) { free(t->vind); free(t->nodes); free(t); }
 
 /* result sets: mode 0 = KNNResultSet(capacity), mode 1 = RadiusResultSet(radius, max_neighbors) */
@@ -1947,7 +1950,7 @@ static int kd_search_level(const kd_tree *t, kd_result *r, const float *q, int n
         {
             const int index = t->vind[i];
             float d = 0.0f;
-            for (int k = 0; k < 3; ++k) { const float diff = q[k] - t->pts[3 * index + k]; d += diff * diff; }
+            for (int k = 0; k < t->dim; ++k) { const float diff = q[k] - t->pts[t->dim * index + k]; d += diff * diff; }
             if (d < worst)
                 if (!kd_add(r, d, index)) return 0;
         }
@@ -1973,8 +1976,8 @@ static void kd_find(const kd_tree *t, kd_result *r, const float *q, float eps)
 {
     if (t->n == 0) return;
     const float eps_error = 1 + eps;
-    float dists[3] = {0, 0, 0}, distsq = 0.0f;
-    for (int i = 0; i < 3; ++i)
+    float dists[KD_MAX_DIM] = {0}, distsq = 0.0f;
+    for (int i = 0; i < t->dim; ++i)
     {
         if (q[i] < t->root_lo[i]) { dists[i] = (q[i] - t->root_lo[i]) * (q[i] - t->root_lo[i]); distsq += dists[i]; }
         if (q[i] > t->root_hi[i]) { dists[i] = (q[i] - t->root_hi[i]) * (q[i] - t->root_hi[i]); distsq += dists[i]; }
@@ -2297,4 +2300,83 @@ void orc_estimate_normals(const float *pts, long n, float radius, int knn, float
         free(bd); free(bi);
     }
     kd_free(t);
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * registration::FeatureMatching3D (src/Registration/GlobalRegistration.cpp:29-73): KDTree<33> over the target features,
+ * KnnSearch(k = 1) per source feature; a source whose search returns nothing (NaN feature: no distance compares below
+ * the initial worst) is left out.  Same tree code as above with dim = 33, so ties and NaN rows behave as in nanoflann.
+ * ------------------------------------------------------------------------------------------------------------------ */
+long orc_feature_matching(const float *src_feat, long ns, const float *tgt_feat, long nt, int32_t *pairs)
+{
+    kd_tree *t = kd_build_dim(tgt_feat, nt, 10, 33);
+    int32_t *nn = (int32_t *)malloc(sizeof(int32_t) * (size_t)(ns + 1));
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long i = 0; i < ns; ++i)
+    {
+        int idx[2];
+        float dist[2];
+        kd_result r;
+        r.mode = 0; r.capacity = 1; r.count = 0; r.radius = 0.0f; r.index = idx; r.dist = dist;
+        dist[0] = FLT_MAX;
+        kd_find(t, &r, src_feat + 33 * i, 0.0f);
+        nn[i] = r.count ? idx[0] : -1;
+    }
+    long m = 0;
+    for (long i = 0; i < ns; ++i)
+        if (nn[i] >= 0) { pairs[2 * m] = (int32_t)i; pairs[2 * m + 1] = nn[i]; ++m; }
+    free(nn);
+    kd_free(t);
+    return m;
+}
+
+/* registration::RejectMatchesRanSaPC (GlobalRegistration.cpp:75-108), `rounds` calls sharing one default-constructed
+ * std::default_random_engine as in RansacRegistration (:168-172).  libstdc++: default_random_engine = minstd_rand0
+ * (x <- 16807 x mod 2^31-1, seed 1, range [1, 2^31-2]); uniform_int_distribution<int>(0, N-1) on it takes the
+ * "downscaling" branch of bits/uniform_int_dist.h: scaling = urange_of_engine / N, reject draws >= N * scaling, divide. */
+static uint32_t minstd_next(uint32_t *state)
+{
+    *state = (uint32_t)(((uint64_t)*state * 16807u) % 2147483647u);
+    return *state;
+}
+static int uniform_int_libstdcxx(uint32_t *state, int n_values)
+{
+    const uint32_t urngmin = 1u, urngrange = 2147483646u - 1u;
+    const uint32_t uerange = (uint32_t)n_values; /* urange + 1 */
+    if (urngrange > uerange - 1u)
+    {
+        const uint32_t scaling = urngrange / uerange, past = uerange * scaling;
+        uint32_t ret;
+        do ret = minstd_next(state) - urngmin; while (ret >= past);
+        return (int)(ret / scaling);
+    }
+    return -1; /* more matches than the engine's range: not reachable for int counts below 2^31 - 2 */
+}
+long orc_reject_matches(const float *src, const float *tgt, int32_t *pairs, long n, int rounds, int candidate_num, float difference)
+{
+    uint32_t state = 1u;
+    int32_t *kept = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)(n + 1));
+    for (int round = 0; round < rounds; ++round)
+    {
+        /* uniform_int_distribution<int> uniform(0, N - 1) with N = 0 would be (0, -1): the loop below never draws then */
+        long m = 0;
+        for (long i = 0; i < n; ++i)
+        {
+            const float *rp = src + 3 * pairs[2 * i], *np = tgt + 3 * pairs[2 * i + 1];
+            int keep = 0;
+            for (int j = 0; j < candidate_num; ++j)
+            {
+                const int c = uniform_int_libstdcxx(&state, (int)n);
+                const float *rq = src + 3 * pairs[2 * c], *nq = tgt + 3 * pairs[2 * c + 1];
+                float a[3] = {rq[0] - rp[0], rq[1] - rp[1], rq[2] - rp[2]}, b[3] = {nq[0] - np[0], nq[1] - np[1], nq[2] - np[2]};
+                const float d1 = sqrtf(dot3(a, a)), d2 = sqrtf(dot3(b, b));
+                if (fabs(d1 - d2) <= difference * d1) { keep = 1; break; } /* fabs: double of the float difference */
+            }
+            if (keep) { kept[2 * m] = pairs[2 * i]; kept[2 * m + 1] = pairs[2 * i + 1]; ++m; }
+        }
+        memcpy(pairs, kept, sizeof(int32_t) * 2 * (size_t)m);
+        n = m;
+    }
+    free(kept);
+    return n;
 }

@@ -134,6 +134,11 @@ long orc_kdtree_dump(const float *pts, long n, int32_t *vind, int32_t *node_ints
 /* registration::ComputeFPFHFeature (3DFeature.cpp:83-131): n x 33 floats; -1 if std::sort's heap fallback would be needed */
 int orc_fpfh(const float *pts, const float *normals, long n, int knn, float radius, float *features);
 
+/* registration::FeatureMatching3D (GlobalRegistration.cpp:29-73): (source, target) index pairs, returns their number */
+long orc_feature_matching(const float *src_feat, long ns, const float *tgt_feat, long nt, int32_t *pairs);
+/* registration::RejectMatchesRanSaPC (GlobalRegistration.cpp:75-108) applied `rounds` times with one default-seeded engine, in place */
+long orc_reject_matches(const float *src, const float *tgt, int32_t *pairs, long n, int rounds, int candidate_num, float difference);
+
 /* caller-side depth pre-filter: tool::ConvertDepthTo32F (ImageProcessing.cpp:68-91), tool::BilateralFilter (:64-67) */
 void orc_convert_depth_32f(const void *depth, int is_u16, long n, float depth_scale, float *out);
 void orc_bilateral_filter(const float *src, int w, int h, int d, double sigma_color, double sigma_space, float *dst);

@@ -82,6 +82,10 @@ def lib():
     L.orc_kdtree_dump.argtypes = [c_p, c_l, c_p, c_p, c_p, c_p]
     L.orc_fpfh.restype = c_i
     L.orc_fpfh.argtypes = [c_p, c_p, c_l, c_i, c_f, c_p]
+    L.orc_feature_matching.restype = c_l
+    L.orc_feature_matching.argtypes = [c_p, c_l, c_p, c_l, c_p]
+    L.orc_reject_matches.restype = c_l
+    L.orc_reject_matches.argtypes = [c_p, c_p, c_p, c_l, c_i, c_i, c_f]
     L.orc_downsample.restype = c_l
     L.orc_downsample.argtypes = [c_p, c_p, c_p, c_l, c_f, c_p, c_p, c_p]
     L.orc_volume_transform.restype = c_p
@@ -457,3 +461,21 @@ def fpfh(points, normals, knn=100, radius=0.1):
     if rc != 0:
         raise RuntimeError("orc_fpfh: std::sort heap fallback reached (not restated)")
     return out
+
+
+def feature_matching(src_feat, tgt_feat):
+    """registration::FeatureMatching3D -> [m,2] (source, target) indices"""
+    sf = np.ascontiguousarray(src_feat, np.float32).reshape(-1, 33)
+    tf = np.ascontiguousarray(tgt_feat, np.float32).reshape(-1, 33)
+    pairs = np.zeros((len(sf), 2), np.int32)
+    m = lib().orc_feature_matching(_ptr(sf), len(sf), _ptr(tf), len(tf), _ptr(pairs))
+    return pairs[:m].copy()
+
+
+def reject_matches(src_pts, tgt_pts, pairs, rounds=3, candidate_num=4, difference=0.1):
+    """registration::RejectMatchesRanSaPC x rounds on one default-seeded engine (GlobalRegistration.cpp:168-172) -> kept pairs"""
+    s = np.ascontiguousarray(src_pts, np.float32).reshape(-1, 3)
+    t = np.ascontiguousarray(tgt_pts, np.float32).reshape(-1, 3)
+    p = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2).copy()
+    m = lib().orc_reject_matches(_ptr(s), _ptr(t), _ptr(p), len(p), rounds, candidate_num, difference)
+    return p[:m].copy()

@@ -29,6 +29,8 @@
 #include "Registration/ICP.h"
 #ifndef USING_FLOAT64
 #include "Registration/3DFeature.h"
+#include "Registration/GlobalRegistration.h"
+#include "Geometry/Ransac.h"
 #endif
 
 using namespace one_piece;
@@ -572,6 +574,69 @@ double ref_fpfh(const float *xyz, const float *normals, long n, int knn, float r
     double dt = Now() - t0;
     for (long i = 0; i < n; ++i)
         for (int k = 0; k < 33; ++k) features[33 * i + k] = fs[i](k);
+    return dt;
+}
+// registration::FeatureMatching3D (GlobalRegistration.cpp:29-73): nearest target feature (33-D) of every source feature
+long ref_feature_matching(const float *src_feat, long ns, const float *tgt_feat, long nt, int32_t *pairs)
+{
+    registration::FeatureSet sf(ns), tf(nt);
+    for (long i = 0; i < ns; ++i) { sf[i].resize(33); for (int k = 0; k < 33; ++k) sf[i](k) = src_feat[33 * i + k]; }
+    for (long i = 0; i < nt; ++i) { tf[i].resize(33); for (int k = 0; k < 33; ++k) tf[i](k) = tgt_feat[33 * i + k]; }
+    geometry::FMatchSet m;
+    registration::FeatureMatching3D(sf, tf, m);
+    for (size_t i = 0; i < m.size(); ++i) { pairs[2 * i] = m[i].first; pairs[2 * i + 1] = m[i].second; }
+    return (long)m.size();
+}
+// registration::RejectMatchesRanSaPC (GlobalRegistration.cpp:75-108), `rounds` calls on one default-seeded engine as in
+// RansacRegistration (:168-172,236-240); matches in/out as (source, target) index pairs
+long ref_reject_matches(const float *src, long ns, const float *tgt, long nt, int32_t *pairs, long n, int rounds, int candidate_num,
+                        float difference)
+{
+    geometry::Point3List s, t;
+    ToList(src, ns, s);
+    ToList(tgt, nt, t);
+    geometry::FMatchSet m(n);
+    for (long i = 0; i < n; ++i) m[i] = std::make_pair(pairs[2 * i], pairs[2 * i + 1]);
+    std::default_random_engine engine;
+    for (int r = 0; r < rounds; ++r) registration::RejectMatchesRanSaPC(s, t, engine, m, candidate_num, difference);
+    for (size_t i = 0; i < m.size(); ++i) { pairs[2 * i] = m[i].first; pairs[2 * i + 1] = m[i].second; }
+    return (long)m.size();
+}
+// one RANSAC hypothesis of geometry::EstimateRigidTransformationRANSAC (Ransac.cpp:7-41): TransformationModel over the eight
+// sampled pairs (TransformationModel.hpp:54-75), Evaluate over all pairs in the given order (:77-94) -> inlier fraction, flags
+double ref_ransac_hypothesis(const float *a, const float *b, long n, const int32_t *sample8, double threshold, uint8_t *inlier)
+{
+    std::vector<std::shared_ptr<GRANSAC::AbstractParameter>> all, sample;
+    for (long i = 0; i < n; ++i)
+        all.push_back(std::make_shared<geometry::Point3fPair>(geometry::Point3(a[3 * i], a[3 * i + 1], a[3 * i + 2]),
+                                                              geometry::Point3(b[3 * i], b[3 * i + 1], b[3 * i + 2]), (int)i));
+    for (int k = 0; k < 8; ++k) sample.push_back(all[sample8[k]]);
+    geometry::TransformationModel model(sample);
+    auto eval = model.Evaluate(all, threshold);
+    for (long i = 0; i < n; ++i) inlier[i] = 0;
+    for (auto &p : eval.second) inlier[std::dynamic_pointer_cast<geometry::Point3fPair>(p)->id] = 1;
+    return eval.first;
+}
+// registration::RansacRegistration on precomputed features (GlobalRegistration.cpp:219-267); seeded from std::random_device
+// inside GRANSAC, so two runs differ: for statistics and timing only
+double ref_ransac_registration(const float *src, long ns, const float *tgt, long nt, const float *src_feat, const float *tgt_feat,
+                               int max_iteration, double threshold, double *T_cm, long *n_inliers, double *rmse)
+{
+    geometry::PointCloud sp, tp;
+    ToList(src, ns, sp.points);
+    ToList(tgt, nt, tp.points);
+    registration::FeatureSet sf(ns), tf(nt);
+    for (long i = 0; i < ns; ++i) { sf[i].resize(33); for (int k = 0; k < 33; ++k) sf[i](k) = src_feat[33 * i + k]; }
+    for (long i = 0; i < nt; ++i) { tf[i].resize(33); for (int k = 0; k < 33; ++k) tf[i](k) = tgt_feat[33 * i + k]; }
+    registration::RANSACParameter para;
+    para.max_iteration = max_iteration;
+    para.threshold = threshold;
+    double t0 = Now();
+    auto r = registration::RansacRegistration(sp, tp, sf, tf, para);
+    double dt = Now() - t0;
+    PoseToColMajor(r->T, T_cm);
+    *n_inliers = (long)r->correspondence_set.size();
+    *rmse = r->rmse;
     return dt;
 }
 #endif

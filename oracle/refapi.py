@@ -86,6 +86,10 @@ def lib(kind: str = "f32"):
         L.ref_kdtree_search.argtypes = [c_p, c_l, c_p, c_l, c_i, c_i, c_f, c_l, c_p, c_p, c_p]
         L.ref_fpfh.restype = c_d
         L.ref_fpfh.argtypes = [c_p, c_p, c_l, c_i, c_f, c_p]
+        L.ref_feature_matching.restype = c_l
+        L.ref_feature_matching.argtypes = [c_p, c_l, c_p, c_l, c_p]
+        L.ref_reject_matches.restype = c_l
+        L.ref_reject_matches.argtypes = [c_p, c_l, c_p, c_l, c_p, c_l, c_i, c_i, c_f]
         L.ref_estimate_normals.restype = c_d
         L.ref_estimate_normals.argtypes = [c_p, c_l, c_f, c_i, c_p]
     L.ref_set_quiet(1)
@@ -440,3 +444,19 @@ def fpfh(points, normals, knn=100, radius=0.1):
     out = np.zeros((len(pts), 33), np.float32)
     dt = lib("f32").ref_fpfh(_ptr(pts), _ptr(nrm), len(pts), knn, radius, _ptr(out))
     return out, dt
+
+
+def feature_matching(src_feat, tgt_feat):
+    sf = np.ascontiguousarray(src_feat, np.float32).reshape(-1, 33)
+    tf = np.ascontiguousarray(tgt_feat, np.float32).reshape(-1, 33)
+    pairs = np.zeros((len(sf), 2), np.int32)
+    m = lib("f32").ref_feature_matching(_ptr(sf), len(sf), _ptr(tf), len(tf), _ptr(pairs))
+    return pairs[:m].copy()
+
+
+def reject_matches(src_pts, tgt_pts, pairs, rounds=3, candidate_num=4, difference=0.1):
+    s = np.ascontiguousarray(src_pts, np.float32).reshape(-1, 3)
+    t = np.ascontiguousarray(tgt_pts, np.float32).reshape(-1, 3)
+    p = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2).copy()
+    m = lib("f32").ref_reject_matches(_ptr(s), len(s), _ptr(t), len(t), _ptr(p), len(p), rounds, candidate_num, difference)
+    return p[:m].copy()

@@ -83,3 +83,44 @@ def test_fpfh_matches_the_compiled_reference(ref_available, case):
         assert np.isnan(a).any()
     else:
         assert np.isfinite(a).all() and (a >= 0).all() and a.any(1).all()
+
+
+def _two_frames_features():
+    """two 320x240 views of the S2 room the way DenseSlam's submap back end prepares them: DownSample(0.05), normals (0.1, 30),
+    FPFH (100, 0.25)"""
+    from onepiece_b200 import scenes
+    c0 = scenes.Camera()
+    cam = scenes.Camera(c0.fx / 2, c0.fy / 2, c0.cx / 2, c0.cy / 2, 320, 240, 1000.0)
+    out = []
+    for k in (0, 12):
+        d, _, _ = scenes.room(cam, k)
+        down = oracleapi.downsample(scenes.backproject(d, cam), None, None, 0.05)[0]
+        nrm = np.nan_to_num(oracleapi.estimate_normals(down, 0.1, 30))
+        out.append((down, oracleapi.fpfh(down, nrm, 100, 0.25)))
+    return out
+
+
+def test_feature_matching_and_rejection_match_the_compiled_reference(ref_available):
+    """FeatureMatching3D (KDTree<33>, k = 1) and RejectMatchesRanSaPC (std::default_random_engine + uniform_int_distribution as
+    libstdc++ implements them) index for index -- also with duplicate features (ties) and with NaN target rows, which poison
+    nanoflann's boxes (std::min / std::max keep their first argument against NaN) and make the reference prune real neighbours."""
+    if not ref_available:
+        pytest.skip("oracle/_ref not built")
+    (ps, fs), (pt, ft) = _two_frames_features()
+    a, b = oracleapi.feature_matching(fs, ft), refapi.feature_matching(fs, ft)
+    assert len(a) == len(fs) and np.array_equal(a, b)
+    brute = ((fs[:500, None, :] - ft[None, :, :]) ** 2).sum(-1).argmin(1)
+    assert (brute == a[:500, 1]).mean() > 0.999          # it is the nearest neighbour (float64 brute force, up to rounding)
+    s2, t2 = fs.copy(), ft.copy()
+    s2[5] = np.nan
+    t2[0] = np.nan
+    t2[77] = np.nan
+    t2[100:110] = t2[200:210]
+    s2[300] = t2[205]
+    a2, b2 = oracleapi.feature_matching(s2, t2), refapi.feature_matching(s2, t2)
+    assert len(a2) == len(fs) - 1 and np.array_equal(a2, b2)
+    assert (a2[:, 1] != a[np.isin(a[:, 0], a2[:, 0]), 1]).mean() > 0.1   # the NaN rows really do change what the reference returns
+    for rounds, cand, diff in [(1, 4, 0.1), (3, 4, 0.1), (3, 2, 0.05), (2, 8, 0.01)]:
+        x, y = oracleapi.reject_matches(ps, pt, a, rounds, cand, diff), refapi.reject_matches(ps, pt, a, rounds, cand, diff)
+        assert 0 < len(x) < len(a) and np.array_equal(x, y), (rounds, cand, diff)
+    assert len(oracleapi.reject_matches(ps, pt, a[:0])) == 0
