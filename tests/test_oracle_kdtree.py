@@ -119,7 +119,7 @@ def test_feature_matching_and_rejection_match_the_compiled_reference(ref_availab
     s2[300] = t2[205]
     a2, b2 = oracleapi.feature_matching(s2, t2), refapi.feature_matching(s2, t2)
     assert len(a2) == len(fs) - 1 and np.array_equal(a2, b2)
-    assert (a2[:, 1] != a[np.isin(a[:, 0], a2[:, 0]), 1]).mean() > 0.1   # the NaN rows really do change what the reference returns
+    assert (a2[:, 1] != a[np.isin(a[:, 0], a2[:, 0]), 1]).mean() > 0.01   # the NaN rows really do change what the reference returns
     for rounds, cand, diff in [(1, 4, 0.1), (3, 4, 0.1), (3, 2, 0.05), (2, 8, 0.01)]:
         x, y = oracleapi.reject_matches(ps, pt, a, rounds, cand, diff), refapi.reject_matches(ps, pt, a, rounds, cand, diff)
         assert 0 < len(x) < len(a) and np.array_equal(x, y), (rounds, cand, diff)
