@@ -312,6 +312,21 @@ int opb_kdtree_estimate_normals(opb_kdtree *t, float radius, int knn, float *nor
  * (0 * inf).  The descriptor angle goes through a double atan2 rounded to float as in the reference; the device's atan2 may
  * differ from glibc's in the last place of the DOUBLE, which survives the float rounding about once in 1e8 pairs. knn <= 256. */
 int opb_kdtree_fpfh(opb_kdtree *t, const float *normals, int knn, float radius, float *features33);
+/* registration::FeatureMatching3D (src/Registration/GlobalRegistration.cpp:29-73): for every source feature (33 floats) the nearest
+ * target feature; pairs = (source index, target index), 2 * ns ints of room; a NaN source feature matches nothing and is left
+ * out, like the reference's empty KnnSearch result.  Exhaustive scan with nanoflann's metric.  Identical to the reference's
+ * KDTree<33> answer unless (a) two targets are at exactly the same distance (lowest index here, tree traversal order there) or
+ * (b) a TARGET feature is NaN: NaN rows poison nanoflann's bounding boxes and make it prune real neighbours (a few percent of
+ * the answers change); the device returns the true nearest finite neighbour.  `t` only lends its stream and buffers. */
+int opb_kdtree_feature_matching(opb_kdtree *t, const float *src_feat33, size_t ns, const float *tgt_feat33, size_t nt, int32_t *pairs,
+                                size_t *n_pairs);
+/* registration::RejectMatchesRanSaPC(source_points, target_points, engine, init_matches, candidate_num = 4, difference = 0.1)
+ * (GlobalRegistration.cpp:75-108), one call: keeps a match if one of candidate_num randomly drawn other matches preserves the
+ * distance to it within `difference`.  *engine_state is the std::default_random_engine (libstdc++: minstd_rand0) the reference
+ * threads through its three calls: 1 for a default-constructed engine, updated on return.  pairs / *n_pairs in place.  HOST
+ * code and host pointers: the draws form one sequential data-dependent chain; identical to the reference index for index. */
+int opb_reject_matches(const float *src_xyz, size_t ns, const float *tgt_xyz, size_t nt, int32_t *pairs, size_t *n_pairs,
+                       uint32_t *engine_state, int candidate_num, float difference);
 /* test hook: the built tree (vind: n ints; nodes in allocation order, root = 0: left, right, child1, child2 (-1 = leaf), divfeat;
  * divlow, divhigh); all output pointers NULL -> only n_nodes */
 int opb_kdtree_dump(opb_kdtree *t, int32_t *vind, int32_t *node_ints5, float *node_floats2, float root_box[6], size_t *n_nodes);

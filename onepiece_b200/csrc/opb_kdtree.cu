@@ -754,6 +754,45 @@ __global__ void __launch_bounds__(kQueryThreads) fpfh_combine_kernel(const float
         if (lane == 0) fpfh[(size_t)i * 33 + 32] = fadd(fmul(f32, scale2), spfh[(size_t)i * 33 + 32]);
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// registration::FeatureMatching3D (src/Registration/GlobalRegistration.cpp:29-73): nearest target feature of every source
+// feature in 33 dimensions.  The reference asks a KDTree<33> for k = 1; the nearest neighbour is what an exhaustive scan finds,
+// with nanoflann's metric (L2_Simple_Adaptor::evalMetric: result += diff * diff, dimension by dimension) and its acceptance rule
+// (dist < worst, worst starting at FLT_MAX: a NaN feature matches nothing).  One thread per source feature, the targets pass
+// through shared memory in tiles read as broadcasts.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kMatchThreads = 64, kMatchTile = 64, kFeatureDim = 33;
+__global__ void __launch_bounds__(kMatchThreads) fpfh_match_kernel(const float *__restrict__ src, int ns, const float *__restrict__ tgt, int nt,
+                                                                   int *__restrict__ nearest)
+{
+    __shared__ float tile[kMatchTile * kFeatureDim];
+    const int i = blockIdx.x * kMatchThreads + threadIdx.x;
+    float f[kFeatureDim];
+#pragma unroll
+    for (int e = 0; e < kFeatureDim; ++e) f[e] = i < ns ? src[(size_t)i * kFeatureDim + e] : 0.0f;
+    float best = FLT_MAX;
+    int best_j = -1;
+    for (int j0 = 0; j0 < nt; j0 += kMatchTile)
+    {
+        const int m = min(kMatchTile, nt - j0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < m * kFeatureDim; e += kMatchThreads) tile[e] = tgt[(size_t)j0 * kFeatureDim + e];
+        __syncthreads();
+        for (int j = 0; j < m; ++j)
+        {
+            float d = 0.0f;
+#pragma unroll
+            for (int e = 0; e < kFeatureDim; ++e)
+            {
+                const float diff = fsub(f[e], tile[j * kFeatureDim + e]);
+                d = fadd(d, fmul(diff, diff));
+            }
+            if (d < best) { best = d; best_j = j0 + j; }
+        }
+    }
+    if (i < ns) nearest[i] = best_j;
+}
 } // namespace opb
 
 using namespace opb;
@@ -1055,5 +1094,90 @@ int opb_kdtree_fpfh(opb_kdtree *t, const float *normals, int knn, float radius, 
     OPB_CUDA(cudaGetLastError());
     OPB_CUDA(cudaMemcpyAsync(features, fpfh, n * 33 * sizeof(float), cudaMemcpyDefault, s));
     OPB_CUDA(cudaStreamSynchronize(s));
+    return OPB_OK;
+}
+
+int opb_kdtree_feature_matching(opb_kdtree *t, const float *src_feat33, size_t ns, const float *tgt_feat33, size_t nt, int32_t *pairs, size_t *n_pairs)
+{
+    if (!t || !n_pairs || (ns && (!src_feat33 || !pairs)) || (nt && !tgt_feat33)) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    *n_pairs = 0;
+    if (ns == 0 || nt == 0) return OPB_OK; // an empty tree answers no query (nanoflann.hpp:1231-1232)
+    if (ns > 0x7FFFFFF0u / kFeatureDim || nt > 0x7FFFFFF0u / kFeatureDim) { set_error("feature set too large"); return OPB_ERR_INVALID; }
+    OPB_CUDA(cudaSetDevice(t->device));
+    int rc;
+    if ((rc = kd_reserve(&t->d_aux[0], &t->aux_bytes[0], ns * kFeatureDim * sizeof(float)))) return rc;
+    if ((rc = kd_reserve(&t->d_aux[2], &t->aux_bytes[2], nt * kFeatureDim * sizeof(float)))) return rc;
+    if ((rc = kd_reserve(&t->d_aux[3], &t->aux_bytes[3], ns * sizeof(int)))) return rc;
+    cudaStream_t s = t->stream;
+    OPB_CUDA(cudaMemcpyAsync(t->d_aux[0], src_feat33, ns * kFeatureDim * sizeof(float), cudaMemcpyDefault, s));
+    OPB_CUDA(cudaMemcpyAsync(t->d_aux[2], tgt_feat33, nt * kFeatureDim * sizeof(float), cudaMemcpyDefault, s));
+    fpfh_match_kernel<<<(unsigned)((ns + kMatchThreads - 1) / kMatchThreads), kMatchThreads, 0, s>>>((const float *)t->d_aux[0], (int)ns,
+                                                                                                  (const float *)t->d_aux[2], (int)nt, (int *)t->d_aux[3]);
+    OPB_CUDA(cudaGetLastError());
+    std::vector<int> nearest(ns);
+    OPB_CUDA(cudaMemcpyAsync(nearest.data(), t->d_aux[3], ns * sizeof(int), cudaMemcpyDeviceToHost, s));
+    OPB_CUDA(cudaStreamSynchronize(s));
+    size_t m = 0;
+    for (size_t i = 0; i < ns; ++i)
+        if (nearest[i] >= 0) { pairs[2 * m] = (int32_t)i; pairs[2 * m + 1] = nearest[i]; ++m; }
+    *n_pairs = m;
+    return OPB_OK;
+}
+
+// registration::RejectMatchesRanSaPC (GlobalRegistration.cpp:75-108).  Host code on purpose: every decision consumes a
+// data-dependent number of draws from ONE std::default_random_engine, so the reference's result is defined by a strictly
+// sequential walk over a few thousand matches (microseconds of work).  libstdc++'s default_random_engine is minstd_rand0
+// (x <- 16807 x mod 2^31 - 1, outputs in [1, 2^31 - 2]); uniform_int_distribution<int>(0, N - 1) on it scales down by integer
+// division and rejects the draws past N * scaling (bits/uniform_int_dist.h, the non-power-of-two branch).
+namespace
+{
+inline uint32_t minstd_rand0_next(uint32_t &x)
+{
+    x = (uint32_t)(((uint64_t)x * 16807u) % 2147483647u);
+    return x;
+}
+inline float norm3_eigen(const float *a, const float *b)
+{
+    const float x = a[0] - b[0], y = a[1] - b[1], z = a[2] - b[2];
+    return sqrtf(x * x + (y * y + z * z)); // Eigen's fixed-size reduction order; -ffp-contract=off keeps the products rounded
+}
+} // namespace
+int opb_reject_matches(const float *src_xyz, size_t ns, const float *tgt_xyz, size_t nt, int32_t *pairs, size_t *n_pairs, uint32_t *engine_state,
+                       int candidate_num, float difference)
+{
+    if (!n_pairs || !engine_state || (*n_pairs && (!src_xyz || !tgt_xyz || !pairs))) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    const size_t n = *n_pairs;
+    if (n > 0x7FFFFFF0u) { set_error("too many matches"); return OPB_ERR_INVALID; }
+    if (*engine_state == 0 || *engine_state >= 2147483647u) { set_error("engine state must be in [1, 2^31 - 2] (a default-constructed engine holds 1)"); return OPB_ERR_INVALID; }
+    for (size_t i = 0; i < n; ++i)
+        if (pairs[2 * i] < 0 || (size_t)pairs[2 * i] >= ns || pairs[2 * i + 1] < 0 || (size_t)pairs[2 * i + 1] >= nt)
+        {
+            set_error("match %zu names a point outside the clouds", i);
+            return OPB_ERR_INVALID;
+        }
+    if (n == 0) return OPB_OK;
+    const uint32_t urng_range = 2147483646u - 1u, ue_range = (uint32_t)n;
+    const uint32_t scaling = urng_range / ue_range, past = ue_range * scaling;
+    std::vector<int32_t> kept;
+    kept.reserve(2 * n);
+    uint32_t x = *engine_state;
+    for (size_t i = 0; i < n; ++i)
+    {
+        const float *ref_point = src_xyz + 3 * (size_t)pairs[2 * i], *new_point = tgt_xyz + 3 * (size_t)pairs[2 * i + 1];
+        bool keep = false;
+        for (int j = 0; j < candidate_num; ++j)
+        {
+            uint32_t r;
+            do r = minstd_rand0_next(x) - 1u; while (r >= past);
+            const size_t c = r / scaling;
+            const float d1 = norm3_eigen(src_xyz + 3 * (size_t)pairs[2 * c], ref_point);
+            const float d2 = norm3_eigen(tgt_xyz + 3 * (size_t)pairs[2 * c + 1], new_point);
+            if (fabs((double)(d1 - d2)) <= (double)(difference * d1)) { keep = true; break; }
+        }
+        if (keep) { kept.push_back(pairs[2 * i]); kept.push_back(pairs[2 * i + 1]); }
+    }
+    memcpy(pairs, kept.data(), kept.size() * sizeof(int32_t));
+    *n_pairs = kept.size() / 2;
+    *engine_state = x;
     return OPB_OK;
 }

@@ -136,6 +136,37 @@ def ComputeFPFHFeature(pcd: "PointCloud", knn: int = 100, radius: float = 0.1, d
     return out
 
 
+def FeatureMatching3D(source_feature, target_feature, device: int = 0):
+    """registration::FeatureMatching3D(source_feature, target_feature, matching_index) (reference
+    src/Registration/GlobalRegistration.cpp:29-73) on the GPU -> [m, 2] int32 (source index, target index)"""
+    sf = np.ascontiguousarray(source_feature, np.float32).reshape(-1, 33)
+    tf = np.ascontiguousarray(target_feature, np.float32).reshape(-1, 33)
+    pairs = np.zeros((len(sf), 2), np.int32)
+    m = C.c_size_t(0)
+    capi.check(capi.lib.opb_kdtree_feature_matching(KDTree(device)._h, _ptr(sf), len(sf), _ptr(tf), len(tf), _ptr(pairs), C.byref(m)))
+    return pairs[:m.value].copy()
+
+
+class DefaultRandomEngine:
+    """std::default_random_engine as libstdc++ defines it (minstd_rand0); default-constructed state 1"""
+
+    def __init__(self, seed: int = 1):
+        self.state = C.c_uint32(seed)
+
+
+def RejectMatchesRanSaPC(source_points, target_points, engine: DefaultRandomEngine, init_matches, candidate_num: int = 4,
+                         difference: float = 0.1):
+    """registration::RejectMatchesRanSaPC (reference src/Registration/GlobalRegistration.cpp:75-108) -> the kept matches; the
+    engine advances exactly as the reference's does, so three calls on one engine reproduce RansacRegistration's three."""
+    s = np.ascontiguousarray(source_points, np.float32).reshape(-1, 3)
+    t = np.ascontiguousarray(target_points, np.float32).reshape(-1, 3)
+    p = np.ascontiguousarray(init_matches, np.int32).reshape(-1, 2).copy()
+    m = C.c_size_t(len(p))
+    capi.check(capi.lib.opb_reject_matches(_ptr(s), len(s), _ptr(t), len(t), _ptr(p), C.byref(m), C.byref(engine.state), candidate_num,
+                                           difference))
+    return p[:m.value].copy()
+
+
 class _Workspace:
     _by_device = {}
 

@@ -13,6 +13,7 @@
 #include "Integration/CubeHandler.h"
 #include "Odometry/Odometry.h"
 #include "Registration/3DFeature.h"
+#include "Registration/GlobalRegistration.h"
 #include "Registration/ICP.h"
 #include "Tool/ImageProcessing.h"
 
@@ -158,6 +159,41 @@ int main(int argc, char **argv)
         }
         WriteAll(dir + "/fpfh.bin", ff);
         WriteAll(dir + "/fpfh_points.bin", fp);
+        // the rest of registration::RansacRegistration on precomputed features, statement for statement
+        // (GlobalRegistration.cpp:225-266): matching and the three rejection passes through the drop-ins, the estimator is the
+        // reference's own GRANSAC (randomly seeded: its T is checked against the true motion, not bit for bit)
+        geometry::PointCloud s_full;
+        s_full.points = s_pcd.points;
+        auto s_down = s_full.DownSample(0.05);
+        s_down->EstimateNormals(0.1, 30);
+        registration::FeatureSet s_features;
+        registration::ComputeFPFHFeature(*s_down, s_features, 100, 0.25);
+        geometry::FMatchSet matches;
+        registration::FeatureMatching3D(s_features, features, matches);
+        std::vector<int32_t> m0, m3;
+        for (size_t i = 0; i < matches.size(); ++i) { m0.push_back(matches[i].first); m0.push_back(matches[i].second); }
+        std::default_random_engine engine;
+        registration::RejectMatchesRanSaPC(s_down->points, down->points, engine, matches);
+        registration::RejectMatchesRanSaPC(s_down->points, down->points, engine, matches);
+        registration::RejectMatchesRanSaPC(s_down->points, down->points, engine, matches);
+        for (size_t i = 0; i < matches.size(); ++i) { m3.push_back(matches[i].first); m3.push_back(matches[i].second); }
+        geometry::PointCorrespondenceSet correspondence_set, inliers;
+        for (size_t i = 0; i != matches.size(); ++i)
+            correspondence_set.push_back(std::make_pair(s_down->points[matches[i].first], down->points[matches[i].second]));
+        std::vector<int> inlier_ids;
+        auto T = geometry::EstimateRigidTransformationRANSAC(correspondence_set, inliers, inlier_ids, 2000, 0.1);
+        std::vector<double> rr;
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) rr.push_back(T(r, c));
+        rr.push_back((double)inliers.size());
+        rr.push_back((double)correspondence_set.size());
+        std::vector<float> sp;
+        for (size_t i = 0; i < s_down->points.size(); ++i)
+            for (int k = 0; k < 3; ++k) sp.push_back(s_down->points[i](k));
+        WriteAll(dir + "/ransac.bin", rr);
+        WriteAll(dir + "/matches_initial.bin", m0);
+        WriteAll(dir + "/matches_kept.bin", m3);
+        WriteAll(dir + "/fpfh_source_points.bin", sp);
     }
     registration::ICPParameter icp_para;
     icp_para.threshold = 0.05;

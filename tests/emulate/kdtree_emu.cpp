@@ -117,4 +117,8 @@ void emu_fpfh(void *p, const float *normals, int knn, float radius, float *featu
     emu::launch(grid_for(n, 3), kQueryThreads, [&] { fpfh_spfh_kernel(t->pts.data(), normals, (int)n, knn, nbr.data(), cnt.data(), spfh.data()); });
     emu::launch(grid_for(n * 32, 5), kQueryThreads, [&] { fpfh_combine_kernel(t->pts.data(), (int)n, knn, nbr.data(), cnt.data(), spfh.data(), features); });
 }
+void emu_match(const float *src, long ns, const float *tgt, long nt, int32_t *nearest)
+{
+    emu::launch((int)((ns + kMatchThreads - 1) / kMatchThreads), kMatchThreads, [&] { fpfh_match_kernel(src, (int)ns, tgt, (int)nt, nearest); });
+}
 }

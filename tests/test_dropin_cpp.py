@@ -78,6 +78,20 @@ def test_reference_caller_code_runs_on_the_gpu(tmp_path):
     assert_bit_equal(fp, down, "DownSample through the drop-in")
     of = oracleapi.fpfh(down, oracleapi.estimate_normals(down, 0.1, 30), 100, 0.25)
     assert len(ff) == len(of) > 100 and ((ff.view(np.uint32) == of.view(np.uint32)) | (np.isnan(ff) & np.isnan(of))).all()
+    # the rest of RansacRegistration: matching + three rejection passes through the drop-ins are the oracle's index for index;
+    # the estimator is the reference's own randomly seeded GRANSAC, so its pose is only checked against the true camera motion
+    sdown = oracleapi.downsample(src, None, None, 0.05)[0]
+    assert_bit_equal(np.fromfile(tmp_path / "fpfh_source_points.bin", np.float32).reshape(-1, 3), sdown, "source DownSample")
+    sf = oracleapi.fpfh(sdown, oracleapi.estimate_normals(sdown, 0.1, 30), 100, 0.25)
+    m0 = oracleapi.feature_matching(sf, of)
+    assert np.array_equal(np.fromfile(tmp_path / "matches_initial.bin", np.int32).reshape(-1, 2), m0)
+    m3 = oracleapi.reject_matches(sdown, down, m0, 3)
+    assert np.array_equal(np.fromfile(tmp_path / "matches_kept.bin", np.int32).reshape(-1, 2), m3) and 8 < len(m3) < len(m0)
+    rr = np.fromfile(tmp_path / "ransac.bin", np.float64)
+    T_est, n_inl, n_corr = rr[:16].reshape(4, 4), int(rr[16]), int(rr[17])
+    T_true = np.linalg.inv(scenes.room_pose(0)) @ scenes.room_pose(3)
+    assert n_corr == len(m3) and n_inl > 0.3 * n_corr
+    assert np.linalg.norm(T_est[:3, 3] - T_true[:3, 3]) < 0.1 and np.abs(T_est[:3, :3] - T_true[:3, :3]).max() < 0.1
     # Odometry::DenseTracking through the drop-in: two chained calls on the same RGBDFrames, then the cv::Mat overload
     odo = np.fromfile(tmp_path / "odometry.bin", np.float64)
     S, T = oracleapi.OracleFrame(c1_bgr, d1), oracleapi.OracleFrame(c0_bgr, d0)

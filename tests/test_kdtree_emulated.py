@@ -42,6 +42,7 @@ def emu(tmp_path_factory):
     L.emu_search.argtypes = [p, p, C.c_long, C.c_int, C.c_int, C.c_float, p, p, p]
     L.emu_normals.argtypes = [p, C.c_float, C.c_int, p]
     L.emu_fpfh.argtypes = [p, p, C.c_int, C.c_float, p]
+    L.emu_match.argtypes = [p, C.c_long, p, C.c_long, p]
     return L
 
 
@@ -103,3 +104,16 @@ def test_emulated_device_code_matches_the_oracle(emu, name, pts):
             assert ((f.view(np.uint32) == of.view(np.uint32)) | (np.isnan(f) & np.isnan(of))).all(), (name, knn, radius)
     finally:
         emu.emu_destroy(h)
+
+
+def test_emulated_feature_matching_matches_the_oracle(emu):
+    """fpfh_match_kernel (exhaustive 33-D nearest neighbour) against the oracle's KDTree<33> restatement on real descriptors"""
+    from test_oracle_kdtree import _two_frames_features
+    (_, fs), (_, ft) = _two_frames_features()
+    fs, ft = np.ascontiguousarray(fs[:700]), np.ascontiguousarray(ft[:1500])
+    fs[7] = np.nan                                            # a NaN source feature matches nothing
+    nearest = np.zeros(len(fs), np.int32)
+    emu.emu_match(_ptr(fs), len(fs), _ptr(ft), len(ft), _ptr(nearest))
+    want = oracleapi.feature_matching(fs, ft)
+    got = np.stack([np.nonzero(nearest >= 0)[0], nearest[nearest >= 0]], 1).astype(np.int32)
+    assert nearest[7] == -1 and np.array_equal(got, want)

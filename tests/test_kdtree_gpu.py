@@ -130,3 +130,27 @@ def test_estimate_normals_full_frame_matches_the_oracle():
     same = (pc.normals.view(np.uint32) == on.view(np.uint32)).all(1)
     print(f"EstimateNormals (k-d tree order): {len(pts)} points in {dt * 1e3:.1f} ms")
     assert same.all(), f"{np.count_nonzero(~same)} of {len(pts)} normals differ"
+
+
+def test_feature_matching_and_rejection_match_the_oracle():
+    """FeatureMatching3D on the device and RejectMatchesRanSaPC in the library's host code, chained the way RansacRegistration
+    chains them (GlobalRegistration.cpp:232-240), index for index against the oracle (itself pinned to the compiled reference)."""
+    from test_oracle_kdtree import _two_frames_features
+    reg = _reg()
+    (ps, fs), (pt, ft) = _two_frames_features()
+    t0 = time.perf_counter()
+    m = reg.FeatureMatching3D(fs, ft)
+    dt = time.perf_counter() - t0
+    want = oracleapi.feature_matching(fs, ft)
+    print(f"FeatureMatching3D: {len(fs)} x {len(ft)} descriptors in {dt * 1e3:.2f} ms (host buffers)")
+    assert np.array_equal(m, want)
+    engine = reg.DefaultRandomEngine()
+    kept = m
+    for _ in range(3):
+        kept = reg.RejectMatchesRanSaPC(ps, pt, engine, kept)
+    assert np.array_equal(kept, oracleapi.reject_matches(ps, pt, want, 3)) and 0 < len(kept) < len(m)
+    fs2 = fs.copy()
+    fs2[5] = np.nan
+    m2 = reg.FeatureMatching3D(fs2, ft)
+    assert len(m2) == len(fs) - 1 and np.array_equal(m2, oracleapi.feature_matching(fs2, ft))
+    assert len(reg.FeatureMatching3D(fs[:0], ft)) == 0 and len(reg.FeatureMatching3D(fs, ft[:0])) == 0
