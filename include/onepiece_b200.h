@@ -314,10 +314,12 @@ int opb_kdtree_estimate_normals(opb_kdtree *t, float radius, int knn, float *nor
 int opb_kdtree_fpfh(opb_kdtree *t, const float *normals, int knn, float radius, float *features33);
 /* registration::FeatureMatching3D (src/Registration/GlobalRegistration.cpp:29-73): for every source feature (33 floats) the nearest
  * target feature; pairs = (source index, target index), 2 * ns ints of room; a NaN source feature matches nothing and is left
- * out, like the reference's empty KnnSearch result.  Exhaustive scan with nanoflann's metric.  Identical to the reference's
- * KDTree<33> answer unless (a) two targets are at exactly the same distance (lowest index here, tree traversal order there) or
- * (b) a TARGET feature is NaN: NaN rows poison nanoflann's bounding boxes and make it prune real neighbours (a few percent of
- * the answers change); the device returns the true nearest finite neighbour.  `t` only lends its stream and buffers. */
+ * out, like the reference's empty KnnSearch result.  Answered the reference's way: the device builds the KDTree<33> nanoflann
+ * would build over the targets and walks it per source, so exactly equidistant targets (duplicate descriptors on flat
+ * surfaces) come back in the reference's order -- identical index for index.  One exception: if a TARGET row is NaN or
+ * infinite (descriptor of an isolated point), nanoflann's bounding boxes are poisoned and the reference prunes real
+ * neighbours (a few percent of its answers change); such sets are scanned exhaustively here and every source gets its true
+ * nearest finite target (lowest index on exact ties).  `t` lends its stream and buffers; its own tree is untouched. */
 int opb_kdtree_feature_matching(opb_kdtree *t, const float *src_feat33, size_t ns, const float *tgt_feat33, size_t nt, int32_t *pairs,
                                 size_t *n_pairs);
 /* registration::RejectMatchesRanSaPC(source_points, target_points, engine, init_matches, candidate_num = 4, difference = 0.1)

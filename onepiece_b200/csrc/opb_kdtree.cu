@@ -33,6 +33,7 @@ constexpr int kLeafMax = 10;
 constexpr int kBuildThreadsBig = 1024, kBuildThreadsMid = 256, kBuildThreadsSmall = 64; // CTA size by the level's largest node
 constexpr int kBuildBigNode = 8192, kBuildSmallNode = 256;
 constexpr int kMaxDepth = 64;
+constexpr int kMaxDim = 33;       // 3 (points, KDTree<3>) or 33 (FPFH descriptors, KDTree<33>)
 constexpr int kQueryThreads = 128;
 constexpr int kKnnCap = 64;       // k of the shared-memory k-nearest list
 constexpr int kRadiusCapMax = 1024; // (int)(2.5 k) of the radius search
@@ -47,17 +48,35 @@ struct KdNode
 struct KdBuildCtl
 {
     int n_nodes, queue_count[2], queue_max[2], max_level; // queue_max: the largest node waiting in that queue
-    float root_lo[3], root_hi[3];
+    float root_lo[kMaxDim], root_hi[kMaxDim];
 };
 struct KdView
 {
     const float *pts;
-    const float4 *sorted; // the points in vind order, w = the point's index: a leaf is one contiguous run
+    const float4 *sorted;     // DIM 3: the points in vind order, w = the point's index: a leaf is one contiguous run
+    const float *sorted_rows; // DIM 33: the rows in vind order
     const int *vind;
     const KdNode *nodes;
-    float root_lo[3], root_hi[3];
+    float root_lo[kMaxDim], root_hi[kMaxDim];
     int n;
 };
+template <int DIM>
+__device__ __forceinline__ float pick(const float *v, int i)
+{
+    if (DIM == 3) return i == 0 ? v[0] : i == 1 ? v[1] : v[2];
+    return v[i];
+}
+template <int DIM>
+__device__ __forceinline__ void put(float *v, int i, float x)
+{
+    if (DIM == 3)
+    {
+        if (i == 0) v[0] = x;
+        else if (i == 1) v[1] = x;
+        else v[2] = x;
+    }
+    else v[i] = x;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // build
@@ -140,8 +159,8 @@ __global__ void kd_iota_kernel(int *vind, int n)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) vind[i] = i;
 }
 // divideTree (nanoflann.hpp:864-914) for one node per CTA; boxes = the LOOSE box handed down by the parent (it, not the tight
-// one, picks the cut dimension and the middle), 6 floats per node
-template <int THREADS>
+// one, picks the cut dimension and the middle), 2 DIM floats per node
+template <int THREADS, int DIM>
 __global__ void __launch_bounds__(THREADS) kd_split_kernel(const float *__restrict__ pts, int *vind, float *key, int *pos, KdNode *nodes,
                                                                  float *boxes, const int *__restrict__ queue_in, int *queue_out, KdBuildCtl *ctl,
                                                                  int out_slot)
@@ -152,44 +171,46 @@ __global__ void __launch_bounds__(THREADS) kd_split_kernel(const float *__restri
     const int left = nodes[id].left, right = nodes[id].right, count = right - left, level = nodes[id].level;
     int *ind = vind + left;
     float *ky = key + left;
-    // computeMinMax of all three coordinates
-    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    // computeMinMax of every coordinate
+    float mn[DIM], mx[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) { mn[d] = FLT_MAX; mx[d] = -FLT_MAX; }
     for (int i = threadIdx.x; i < count; i += THREADS)
     {
         const int j = ind[i];
 #pragma unroll
-        for (int d = 0; d < 3; ++d)
+        for (int d = 0; d < DIM; ++d)
         {
-            const float v = pts[3 * j + d];
+            const float v = pts[(size_t)DIM * j + d];
             mn[d] = fminf(mn[d], v);
             mx[d] = fmaxf(mx[d], v);
         }
     }
 #pragma unroll
-    for (int d = 0; d < 3; ++d)
+    for (int d = 0; d < DIM; ++d)
     {
         mn[d] = block_reduce<THREADS>(mn[d], [](float x, float y) { return fminf(x, y); }, shf);
         mx[d] = block_reduce<THREADS>(mx[d], [](float x, float y) { return fmaxf(x, y); }, shf);
     }
-    float lo[3], hi[3];
+    float lo[DIM], hi[DIM];
     if (id == 0)
     {
         // computeBoundingBox (:1324-1350): the root's box is the tight one
 #pragma unroll
-        for (int d = 0; d < 3; ++d) { lo[d] = mn[d]; hi[d] = mx[d]; }
+        for (int d = 0; d < DIM; ++d) { lo[d] = mn[d]; hi[d] = mx[d]; }
         if (threadIdx.x == 0)
-            for (int d = 0; d < 3; ++d) { ctl->root_lo[d] = mn[d]; ctl->root_hi[d] = mx[d]; }
+            for (int d = 0; d < DIM; ++d) { ctl->root_lo[d] = mn[d]; ctl->root_hi[d] = mx[d]; }
     }
     else
     {
 #pragma unroll
-        for (int d = 0; d < 3; ++d) { lo[d] = boxes[6 * id + d]; hi[d] = boxes[6 * id + 3 + d]; }
+        for (int d = 0; d < DIM; ++d) { lo[d] = boxes[(size_t)2 * DIM * id + d]; hi[d] = boxes[(size_t)2 * DIM * id + DIM + d]; }
     }
     if (count <= kLeafMax) return; // only the root can arrive here as a leaf
     // middleSplit_ (:916-963)
     float max_span = fsub(hi[0], lo[0]);
 #pragma unroll
-    for (int d = 1; d < 3; ++d)
+    for (int d = 1; d < DIM; ++d)
     {
         const float span = fsub(hi[d], lo[d]);
         if (span > max_span) max_span = span;
@@ -198,7 +219,7 @@ __global__ void __launch_bounds__(THREADS) kd_split_kernel(const float *__restri
     float max_spread = -1.0f;
     int cutfeat = 0;
 #pragma unroll
-    for (int d = 0; d < 3; ++d)
+    for (int d = 0; d < DIM; ++d)
     {
         const float span = fsub(hi[d], lo[d]);
         if (span > thresh)
@@ -207,17 +228,14 @@ __global__ void __launch_bounds__(THREADS) kd_split_kernel(const float *__restri
             if (spread > max_spread) { cutfeat = d; max_spread = spread; }
         }
     }
-    const float lo_c = cutfeat == 0 ? lo[0] : cutfeat == 1 ? lo[1] : lo[2];
-    const float hi_c = cutfeat == 0 ? hi[0] : cutfeat == 1 ? hi[1] : hi[2];
-    const float mn_c = cutfeat == 0 ? mn[0] : cutfeat == 1 ? mn[1] : mn[2];
-    const float mx_c = cutfeat == 0 ? mx[0] : cutfeat == 1 ? mx[1] : mx[2];
+    const float lo_c = pick<DIM>(lo, cutfeat), hi_c = pick<DIM>(hi, cutfeat), mn_c = pick<DIM>(mn, cutfeat), mx_c = pick<DIM>(mx, cutfeat);
     const float split_val = fdiv(fadd(lo_c, hi_c), 2.0f);
     const float cutval = split_val < mn_c ? mn_c : split_val > mx_c ? mx_c : split_val;
     // planeSplit (:974-1010): lim1 = #(< cutval), lim2 = lim1 + #(== cutval)
     int cl = 0, ce = 0;
     for (int i = threadIdx.x; i < count; i += THREADS)
     {
-        const float v = pts[3 * ind[i] + cutfeat];
+        const float v = pts[(size_t)DIM * ind[i] + cutfeat];
         ky[i] = v;
         cl += v < cutval;
         ce += v == cutval;
@@ -247,10 +265,11 @@ __global__ void __launch_bounds__(THREADS) kd_split_kernel(const float *__restri
         b.left = left + idx; b.right = right;
         nodes[c] = a;
         nodes[c + 1] = b;
-        for (int d = 0; d < 3; ++d)
+        float *box_a = boxes + (size_t)2 * DIM * c, *box_b = box_a + 2 * DIM;
+        for (int d = 0; d < DIM; ++d)
         {
-            boxes[6 * c + d] = lo[d]; boxes[6 * c + 3 + d] = d == cutfeat ? cutval : hi[d];
-            boxes[6 * (c + 1) + d] = d == cutfeat ? cutval : lo[d]; boxes[6 * (c + 1) + 3 + d] = hi[d];
+            box_a[d] = lo[d]; box_a[DIM + d] = d == cutfeat ? cutval : hi[d];
+            box_b[d] = d == cutfeat ? cutval : lo[d]; box_b[DIM + d] = hi[d];
         }
         nodes[id].child1 = c; nodes[id].child2 = c + 1; nodes[id].divfeat = cutfeat;
         nodes[id].divlow = dl; nodes[id].divhigh = dh;
@@ -261,6 +280,11 @@ __global__ void __launch_bounds__(THREADS) kd_split_kernel(const float *__restri
     }
 }
 
+__global__ void kd_reorder_rows_kernel(const float *__restrict__ pts, const int *__restrict__ vind, int n, int dim, float *__restrict__ rows)
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)n * dim; e += (size_t)gridDim.x * blockDim.x)
+        rows[e] = pts[(size_t)vind[e / dim] * dim + e % dim];
+}
 __global__ void kd_reorder_kernel(const float *__restrict__ pts, const int *__restrict__ vind, int n, float4 *__restrict__ sorted)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -273,13 +297,6 @@ __global__ void kd_reorder_kernel(const float *__restrict__ pts, const int *__re
 // ---------------------------------------------------------------------------------------------------------
 // search
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float pick3(const float *v, int i) { return i == 0 ? v[0] : i == 1 ? v[1] : v[2]; }
-__device__ __forceinline__ void put3(float *v, int i, float x)
-{
-    if (i == 0) v[0] = x;
-    else if (i == 1) v[1] = x;
-    else v[2] = x;
-}
 // L2_Simple_Adaptor::evalMetric (:438-446): result += diff * diff, dimension by dimension
 __device__ __forceinline__ float kd_dist2(const float *q, const float4 p)
 {
@@ -346,15 +363,16 @@ struct __align__(16) KdFrame
     float value, cut;
 };
 // findNeighbors + searchLevel (:1228-1248, :1354-1417); false when the result set asked to stop
-template <class ResultSet>
+template <int DIM, class ResultSet>
 __device__ bool kd_find(const KdView &t, ResultSet &rs, const float *q, float eps_error)
 {
     if (t.n == 0) return true;
-    float dists[3] = {0.0f, 0.0f, 0.0f};
+    float dists[DIM];
     float distsq = 0.0f;
 #pragma unroll
-    for (int d = 0; d < 3; ++d)
+    for (int d = 0; d < DIM; ++d)
     {
+        dists[d] = 0.0f;
         if (q[d] < t.root_lo[d]) { const float x = fsub(q[d], t.root_lo[d]); dists[d] = fmul(x, x); distsq = fadd(distsq, dists[d]); }
         if (q[d] > t.root_hi[d]) { const float x = fsub(q[d], t.root_hi[d]); dists[d] = fmul(x, x); distsq = fadd(distsq, dists[d]); }
     }
@@ -373,16 +391,32 @@ __device__ bool kd_find(const KdView &t, ResultSet &rs, const float *q, float ep
                 const float worst = rs.worst();
                 for (int i = nd.left; i < nd.right; ++i)
                 {
-                    const float4 p = t.sorted[i];
-                    const float d = kd_dist2(q, p);
-                    if (d < worst)
-                        if (!rs.add(d, __float_as_int(p.w))) return false;
+                    if (DIM == 3)
+                    {
+                        const float4 p = t.sorted[i];
+                        const float d = kd_dist2(q, p);
+                        if (d < worst)
+                            if (!rs.add(d, __float_as_int(p.w))) return false;
+                    }
+                    else
+                    {
+                        // L2_Simple_Adaptor::evalMetric (:438-446): result += diff * diff, dimension by dimension
+                        const float *row = t.sorted_rows + (size_t)i * DIM;
+                        float d = 0.0f;
+                        for (int e = 0; e < DIM; ++e)
+                        {
+                            const float diff = fsub(q[e], row[e]);
+                            d = fadd(d, fmul(diff, diff));
+                        }
+                        if (d < worst)
+                            if (!rs.add(d, t.vind[i])) return false;
+                    }
                 }
                 --sp;
                 continue;
             }
             const int cf = nd.divfeat;
-            const float val = pick3(q, cf);
+            const float val = pick<DIM>(q, cf);
             const float diff1 = fsub(val, nd.divlow), diff2 = fsub(val, nd.divhigh);
             int best;
             if (fadd(diff1, diff2) < 0.0f) { best = nd.child1; f.node = nd.child2; f.cut = fmul(diff2, diff2); }
@@ -395,9 +429,9 @@ __device__ bool kd_find(const KdView &t, ResultSet &rs, const float *q, float ep
         }
         else if (stage == 1)
         {
-            const float dst = pick3(dists, idx);
+            const float dst = pick<DIM>(dists, idx);
             const float mind = fsub(fadd(f.value, f.cut), dst);
-            put3(dists, idx, f.cut);
+            put<DIM>(dists, idx, f.cut);
             if (fmul(mind, eps_error) <= rs.worst())
             {
                 f.idx_stage = (idx << 2) | 2;
@@ -408,13 +442,13 @@ __device__ bool kd_find(const KdView &t, ResultSet &rs, const float *q, float ep
             }
             else
             {
-                put3(dists, idx, dst);
+                put<DIM>(dists, idx, dst);
                 --sp;
             }
         }
         else
         {
-            put3(dists, idx, f.value);
+            put<DIM>(dists, idx, f.value);
             --sp;
         }
     }
@@ -568,7 +602,7 @@ __global__ void __launch_bounds__(kQueryThreads) kd_knn_kernel(KdView t, const f
         const float q[3] = {queries[3 * qi], queries[3 * qi + 1], queries[3 * qi + 2]};
         KnnSet rs;
         rs.init(knn_smem, k);
-        kd_find(t, rs, q, 1.0f);
+        kd_find<3>(t, rs, q, 1.0f);
         int cnt = rs.count;
         if (mode == 2)
         {
@@ -603,7 +637,7 @@ __global__ void __launch_bounds__(kQueryThreads) kd_radius_kernel(KdView t, cons
         if (scratch_d) { rs.d = scratch_d + s; rs.i = scratch_i + s; rs.stride = stride; }
         else { rs.d = knn_smem + threadIdx.x; rs.i = reinterpret_cast<int *>(knn_smem + cap * blockDim.x) + threadIdx.x; rs.stride = blockDim.x; }
         rs.count = 0; rs.capacity = cap; rs.radius = radius;
-        kd_find(t, rs, q, 1.0f + 1e-8f); // SearchParameter's eps (KDTree.h:19): 1 + 1e-8 rounds to 1 in float, like the reference's
+        kd_find<3>(t, rs, q, 1.0f + 1e-8f); // SearchParameter's eps (KDTree.h:19): 1 + 1e-8 rounds to 1 in float, like the reference's
         HitArray A;
         A.d = rs.d; A.i = rs.i; A.stride = rs.stride;
         hit_std_sort(A, rs.count);
@@ -628,7 +662,7 @@ __global__ void __launch_bounds__(kQueryThreads) kd_normals_kernel(KdView t, int
         const float q[3] = {self.x, self.y, self.z};
         KnnSet rs;
         rs.init(knn_smem, k);
-        kd_find(t, rs, q, 1.0f);
+        kd_find<3>(t, rs, q, 1.0f);
         int in_radius = 0;
         for (; in_radius != rs.count; ++in_radius)
             if (rs.dist(in_radius) > radius) break;
@@ -793,17 +827,57 @@ __global__ void __launch_bounds__(kMatchThreads) fpfh_match_kernel(const float *
     }
     if (i < ns) nearest[i] = best_j;
 }
+// the same question asked the reference's way: a KDTree<33> over the (finite) target descriptors, walked per source descriptor
+// with a one-entry KNNResultSet -- so that exactly equidistant targets (duplicate descriptors on flat surfaces) come back in the
+// reference's order too
+struct Nearest1
+{
+    float best;
+    int index;
+    __device__ __forceinline__ float worst() { return best; }
+    // KNNResultSet::addPoint with capacity 1 (:175-199): only a strictly closer point replaces the entry -- the leaf loop's
+    // worst_dist is read once per leaf (:1361), so farther points of the same leaf do arrive here
+    __device__ __forceinline__ bool add(float d, int i)
+    {
+        if (best > d) { best = d; index = i; }
+        return true;
+    }
+};
+__global__ void __launch_bounds__(kMatchThreads) fpfh_match_tree_kernel(KdView t, const float *__restrict__ src, int ns, int *__restrict__ nearest)
+{
+    const int i = blockIdx.x * kMatchThreads + threadIdx.x;
+    if (i >= ns) return;
+    float q[kFeatureDim];
+    for (int e = 0; e < kFeatureDim; ++e) q[e] = src[(size_t)i * kFeatureDim + e];
+    Nearest1 rs;
+    rs.best = FLT_MAX;
+    rs.index = -1;
+    kd_find<kFeatureDim>(t, rs, q, 1.0f);
+    nearest[i] = rs.index;
+}
+// rows with a NaN or an infinity (isolated points' descriptors are 0 * inf): flags[0] = their number
+__global__ void count_nonfinite_rows_kernel(const float *__restrict__ rows, int n, int dim, int *flags)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        bool bad = false;
+        for (int e = 0; e < dim; ++e) bad |= !isfinite(rows[(size_t)i * dim + e]);
+        if (bad) atomicAdd(flags, 1);
+    }
+}
 } // namespace opb
 
 using namespace opb;
 
 struct opb_kdtree
 {
-    int device = 0, sm_count = 148;
+    int device = 0, sm_count = 148, dim = 3;
+    opb_kdtree *feature_tree = nullptr; // the KDTree<33> workspace of opb_kdtree_feature_matching, created on first use
     cudaStream_t stream = nullptr;
     size_t cap_points = 0, n = 0;
     float *d_pts = nullptr, *d_key = nullptr, *d_boxes = nullptr;
     float4 *d_sorted = nullptr;
+    float *d_sorted_rows = nullptr;
     int *d_vind = nullptr, *d_pos = nullptr, *d_queue[2] = {nullptr, nullptr};
     KdNode *d_nodes = nullptr;
     KdBuildCtl *d_ctl = nullptr, *h_ctl = nullptr;
@@ -829,8 +903,8 @@ static int kd_reserve(void **p, size_t *have, size_t want)
 static KdView kd_view(const opb_kdtree *t)
 {
     KdView v;
-    v.pts = t->d_pts; v.sorted = t->d_sorted; v.vind = t->d_vind; v.nodes = t->d_nodes; v.n = (int)t->n;
-    for (int d = 0; d < 3; ++d) { v.root_lo[d] = t->h_ctl->root_lo[d]; v.root_hi[d] = t->h_ctl->root_hi[d]; }
+    v.pts = t->d_pts; v.sorted = t->d_sorted; v.sorted_rows = t->d_sorted_rows; v.vind = t->d_vind; v.nodes = t->d_nodes; v.n = (int)t->n;
+    for (int d = 0; d < kMaxDim; ++d) { v.root_lo[d] = t->h_ctl->root_lo[d]; v.root_hi[d] = t->h_ctl->root_hi[d]; }
     return v;
 }
 static int kd_grid(const opb_kdtree *t, size_t work, int per_sm)
@@ -867,7 +941,9 @@ int opb_kdtree_create(int device, opb_kdtree **out)
 void opb_kdtree_destroy(opb_kdtree *t)
 {
     if (!t) return;
+    opb_kdtree_destroy(t->feature_tree);
     cudaSetDevice(t->device);
+    cudaFree(t->d_sorted_rows);
     cudaFree(t->d_pts); cudaFree(t->d_key); cudaFree(t->d_boxes); cudaFree(t->d_vind); cudaFree(t->d_pos); cudaFree(t->d_sorted);
     cudaFree(t->d_queue[0]); cudaFree(t->d_queue[1]); cudaFree(t->d_nodes); cudaFree(t->d_ctl); cudaFree(t->d_scratch);
     for (int i = 0; i < 4; ++i) cudaFree(t->d_aux[i]);
@@ -875,30 +951,33 @@ void opb_kdtree_destroy(opb_kdtree *t)
     if (t->stream) cudaStreamDestroy(t->stream);
     delete t;
 }
-int opb_kdtree_build(opb_kdtree *t, const float *xyz, size_t n)
+// builds the tree of t->dim-dimensional rows
+static int kd_build_rows(opb_kdtree *t, const float *xyz, size_t n)
 {
-    if (!t || (!xyz && n)) { set_error("NULL argument"); return OPB_ERR_INVALID; }
-    if (n > 0x3FFFFFF0u) { set_error("clouds above 2^30 points are not supported"); return OPB_ERR_INVALID; }
+    const size_t dim = (size_t)t->dim;
+    if (n > 0x3FFFFFF0u / dim) { set_error("clouds above 2^30 values are not supported"); return OPB_ERR_INVALID; }
     OPB_CUDA(cudaSetDevice(t->device));
     t->built = false;
     t->n = n;
     if (n > t->cap_points)
     {
         cudaFree(t->d_pts); cudaFree(t->d_key); cudaFree(t->d_boxes); cudaFree(t->d_vind); cudaFree(t->d_pos); cudaFree(t->d_sorted);
-        cudaFree(t->d_queue[0]); cudaFree(t->d_queue[1]); cudaFree(t->d_nodes);
+        cudaFree(t->d_queue[0]); cudaFree(t->d_queue[1]); cudaFree(t->d_nodes); cudaFree(t->d_sorted_rows);
         t->d_sorted = nullptr;
+        t->d_sorted_rows = nullptr;
         t->d_pts = t->d_key = t->d_boxes = nullptr; t->d_vind = t->d_pos = t->d_queue[0] = t->d_queue[1] = nullptr; t->d_nodes = nullptr;
         t->cap_points = 0;
         const size_t cap = n + n / 8 + 1024, nodes = 2 * cap + 2;
-        OPB_CUDA(cudaMalloc((void **)&t->d_pts, cap * 3 * sizeof(float)));
+        OPB_CUDA(cudaMalloc((void **)&t->d_pts, cap * dim * sizeof(float)));
         OPB_CUDA(cudaMalloc((void **)&t->d_key, cap * sizeof(float)));
-        OPB_CUDA(cudaMalloc((void **)&t->d_sorted, cap * sizeof(float4)));
+        if (dim == 3) OPB_CUDA(cudaMalloc((void **)&t->d_sorted, cap * sizeof(float4)));
+        else OPB_CUDA(cudaMalloc((void **)&t->d_sorted_rows, cap * dim * sizeof(float)));
         OPB_CUDA(cudaMalloc((void **)&t->d_vind, cap * sizeof(int)));
         OPB_CUDA(cudaMalloc((void **)&t->d_pos, cap * sizeof(int)));
         OPB_CUDA(cudaMalloc((void **)&t->d_queue[0], nodes * sizeof(int)));
         OPB_CUDA(cudaMalloc((void **)&t->d_queue[1], nodes * sizeof(int)));
         OPB_CUDA(cudaMalloc((void **)&t->d_nodes, nodes * sizeof(KdNode)));
-        OPB_CUDA(cudaMalloc((void **)&t->d_boxes, nodes * 6 * sizeof(float)));
+        OPB_CUDA(cudaMalloc((void **)&t->d_boxes, nodes * 2 * dim * sizeof(float)));
         t->cap_points = cap;
     }
     cudaStream_t s = t->stream;
@@ -906,7 +985,7 @@ int opb_kdtree_build(opb_kdtree *t, const float *xyz, size_t n)
     t->n_nodes = 0;
     t->max_level = 0;
     if (n == 0) { t->built = true; return OPB_OK; }
-    OPB_CUDA(cudaMemcpyAsync(t->d_pts, xyz, n * 3 * sizeof(float), cudaMemcpyDefault, s));
+    OPB_CUDA(cudaMemcpyAsync(t->d_pts, xyz, n * dim * sizeof(float), cudaMemcpyDefault, s));
     kd_iota_kernel<<<kd_grid(t, n, 8), kQueryThreads, 0, s>>>(t->d_vind, (int)n);
     KdNode root;
     root.left = 0; root.right = (int)n; root.child1 = root.child2 = -1; root.divfeat = -1; root.divlow = root.divhigh = 0.0f; root.level = 0;
@@ -924,12 +1003,17 @@ int opb_kdtree_build(opb_kdtree *t, const float *xyz, size_t n)
         OPB_CUDA(cudaMemsetAsync(&t->d_ctl->queue_count[out_slot], 0, sizeof(int), s));
         OPB_CUDA(cudaMemsetAsync(&t->d_ctl->queue_max[out_slot], 0, sizeof(int), s));
         // one CTA per node, sized for the largest node of the level: the top of the tree is a few very long nodes
-#define OPB_KD_SPLIT(THREADS)                                                                                                                      \
-    kd_split_kernel<THREADS><<<in_count, THREADS, 0, s>>>(t->d_pts, t->d_vind, t->d_key, t->d_pos, t->d_nodes, t->d_boxes, t->d_queue[slot], \
-                                                          t->d_queue[out_slot], t->d_ctl, out_slot)
-        if (largest > kBuildBigNode) OPB_KD_SPLIT(kBuildThreadsBig);
-        else if (largest > kBuildSmallNode) OPB_KD_SPLIT(kBuildThreadsMid);
-        else OPB_KD_SPLIT(kBuildThreadsSmall);
+#define OPB_KD_SPLIT(THREADS, DIM)                                                                                                                  \
+    kd_split_kernel<THREADS, DIM><<<in_count, THREADS, 0, s>>>(t->d_pts, t->d_vind, t->d_key, t->d_pos, t->d_nodes, t->d_boxes, t->d_queue[slot], \
+                                                               t->d_queue[out_slot], t->d_ctl, out_slot)
+        if (dim == 3)
+        {
+            if (largest > kBuildBigNode) OPB_KD_SPLIT(kBuildThreadsBig, 3);
+            else if (largest > kBuildSmallNode) OPB_KD_SPLIT(kBuildThreadsMid, 3);
+            else OPB_KD_SPLIT(kBuildThreadsSmall, 3);
+        }
+        else if (largest > kBuildSmallNode) OPB_KD_SPLIT(kBuildThreadsMid, kFeatureDim); // descriptor sets are a few thousand rows
+        else OPB_KD_SPLIT(kBuildThreadsSmall, kFeatureDim);
 #undef OPB_KD_SPLIT
         OPB_CUDA(cudaGetLastError());
         OPB_CUDA(cudaMemcpyAsync(t->h_ctl, t->d_ctl, sizeof(KdBuildCtl), cudaMemcpyDeviceToHost, s));
@@ -938,7 +1022,8 @@ int opb_kdtree_build(opb_kdtree *t, const float *xyz, size_t n)
         largest = t->h_ctl->queue_max[out_slot];
         slot = out_slot;
     }
-    kd_reorder_kernel<<<kd_grid(t, n, 8), kQueryThreads, 0, s>>>(t->d_pts, t->d_vind, (int)n, t->d_sorted);
+    if (dim == 3) kd_reorder_kernel<<<kd_grid(t, n, 8), kQueryThreads, 0, s>>>(t->d_pts, t->d_vind, (int)n, t->d_sorted);
+    else kd_reorder_rows_kernel<<<kd_grid(t, n * dim, 8), kQueryThreads, 0, s>>>(t->d_pts, t->d_vind, (int)n, (int)dim, t->d_sorted_rows);
     OPB_CUDA(cudaGetLastError());
     t->n_nodes = t->h_ctl->n_nodes;
     t->max_level = t->h_ctl->max_level;
@@ -949,6 +1034,11 @@ int opb_kdtree_build(opb_kdtree *t, const float *xyz, size_t n)
     }
     t->built = true;
     return OPB_OK;
+}
+int opb_kdtree_build(opb_kdtree *t, const float *xyz, size_t n)
+{
+    if (!t || (!xyz && n)) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    return kd_build_rows(t, xyz, n);
 }
 int opb_kdtree_dump(opb_kdtree *t, int32_t *vind, int32_t *node_ints, float *node_floats, float root_box[6], size_t *n_nodes)
 {
@@ -1111,9 +1201,33 @@ int opb_kdtree_feature_matching(opb_kdtree *t, const float *src_feat33, size_t n
     cudaStream_t s = t->stream;
     OPB_CUDA(cudaMemcpyAsync(t->d_aux[0], src_feat33, ns * kFeatureDim * sizeof(float), cudaMemcpyDefault, s));
     OPB_CUDA(cudaMemcpyAsync(t->d_aux[2], tgt_feat33, nt * kFeatureDim * sizeof(float), cudaMemcpyDefault, s));
-    fpfh_match_kernel<<<(unsigned)((ns + kMatchThreads - 1) / kMatchThreads), kMatchThreads, 0, s>>>((const float *)t->d_aux[0], (int)ns,
-                                                                                                  (const float *)t->d_aux[2], (int)nt, (int *)t->d_aux[3]);
-    OPB_CUDA(cudaGetLastError());
+    // a NaN / infinite TARGET row poisons nanoflann's boxes (the reference then prunes real neighbours); such sets take the
+    // exhaustive scan, which returns the true nearest finite row.  Everything else is answered by the reference's own tree.
+    int bad_rows = 0;
+    OPB_CUDA(cudaMemsetAsync(t->d_ctl, 0, sizeof(int), s));
+    count_nonfinite_rows_kernel<<<kd_grid(t, nt, 8), kQueryThreads, 0, s>>>((const float *)t->d_aux[2], (int)nt, kFeatureDim, (int *)t->d_ctl);
+    OPB_CUDA(cudaMemcpyAsync(&bad_rows, t->d_ctl, sizeof(int), cudaMemcpyDeviceToHost, s));
+    OPB_CUDA(cudaStreamSynchronize(s));
+    const unsigned blocks = (unsigned)((ns + kMatchThreads - 1) / kMatchThreads);
+    const char *forced = getenv("OPB_MATCH_EXHAUSTIVE"); // developer knob
+    if (bad_rows || (forced && atoi(forced)))
+    {
+        fpfh_match_kernel<<<blocks, kMatchThreads, 0, s>>>((const float *)t->d_aux[0], (int)ns, (const float *)t->d_aux[2], (int)nt, (int *)t->d_aux[3]);
+        OPB_CUDA(cudaGetLastError());
+    }
+    else
+    {
+        if (!t->feature_tree)
+        {
+            if ((rc = opb_kdtree_create(t->device, &t->feature_tree))) return rc;
+            t->feature_tree->dim = kFeatureDim;
+        }
+        opb_kdtree *ft = t->feature_tree;
+        if ((rc = kd_build_rows(ft, (const float *)t->d_aux[2], nt))) return rc;
+        OPB_CUDA(cudaStreamSynchronize(ft->stream));
+        fpfh_match_tree_kernel<<<blocks, kMatchThreads, 0, s>>>(kd_view(ft), (const float *)t->d_aux[0], (int)ns, (int *)t->d_aux[3]);
+        OPB_CUDA(cudaGetLastError());
+    }
     std::vector<int> nearest(ns);
     OPB_CUDA(cudaMemcpyAsync(nearest.data(), t->d_aux[3], ns * sizeof(int), cudaMemcpyDeviceToHost, s));
     OPB_CUDA(cudaStreamSynchronize(s));

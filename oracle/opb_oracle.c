@@ -2157,9 +2157,15 @@ void orc_kdtree_search(const float *pts, long n, const float *queries, long nq, 
 }
 /* the built tree, for checking a device build: vind (n ints) and the nodes in pre-order, 5 ints + 2 floats each
  * (left, right, child1, child2, divfeat; divlow, divhigh) with children renumbered in pre-order; returns node count */
+long orc_kdtree_dump_dim(const float *pts, long n, int dim, int32_t *vind, int32_t *node_ints, float *node_floats, float *root_box);
 long orc_kdtree_dump(const float *pts, long n, int32_t *vind, int32_t *node_ints, float *node_floats, float *root_box)
 {
-    kd_tree *t = kd_build(pts, n, 10);
+    return orc_kdtree_dump_dim(pts, n, 3, vind, node_ints, node_floats, root_box);
+}
+/* root_box: dim lows then dim highs */
+long orc_kdtree_dump_dim(const float *pts, long n, int dim, int32_t *vind, int32_t *node_ints, float *node_floats, float *root_box)
+{
+    kd_tree *t = kd_build_dim(pts, n, 10, dim);
     for (long i = 0; i < n; ++i) vind[i] = t->vind[i];
     for (int i = 0; i < t->n_nodes; ++i)
     {
@@ -2168,7 +2174,7 @@ long orc_kdtree_dump(const float *pts, long n, int32_t *vind, int32_t *node_ints
         node_ints[5 * i + 3] = nd->child2; node_ints[5 * i + 4] = nd->divfeat;
         node_floats[2 * i] = nd->divlow; node_floats[2 * i + 1] = nd->divhigh;
     }
-    for (int i = 0; i < 3; ++i) { root_box[i] = t->root_lo[i]; root_box[3 + i] = t->root_hi[i]; }
+    for (int i = 0; i < dim; ++i) { root_box[i] = t->root_lo[i]; root_box[dim + i] = t->root_hi[i]; }
     const long nn = t->n_nodes;
     kd_free(t);
     return nn;

@@ -89,5 +89,6 @@ struct float4 { float x, y, z, w; };
 inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+using std::isfinite;
 using std::max;
 using std::min;

@@ -16,27 +16,28 @@ struct Tree
     std::vector<float4> sorted;
     std::vector<int> vind, pos, queue[2];
     std::vector<KdNode> nodes;
+    std::vector<float> sorted_rows;
     KdBuildCtl ctl;
-    int n = 0;
+    int n = 0, dim = 3;
     KdView view() const
     {
         KdView v;
-        v.pts = pts.data(); v.sorted = sorted.data(); v.vind = vind.data(); v.nodes = nodes.data(); v.n = n;
-        for (int d = 0; d < 3; ++d) { v.root_lo[d] = ctl.root_lo[d]; v.root_hi[d] = ctl.root_hi[d]; }
+        v.pts = pts.data(); v.sorted = sorted.data(); v.sorted_rows = sorted_rows.data(); v.vind = vind.data(); v.nodes = nodes.data(); v.n = n;
+        for (int d = 0; d < kMaxDim; ++d) { v.root_lo[d] = ctl.root_lo[d]; v.root_hi[d] = ctl.root_hi[d]; }
         return v;
     }
 };
 static int grid_for(size_t work, int cap) { const size_t b = (work + kQueryThreads - 1) / kQueryThreads; return (int)(b < (size_t)cap ? (b ? b : 1) : cap); }
 
-extern "C"
-{
-void *emu_build(const float *xyz, long n)
+static Tree *build_rows(const float *xyz, long n, int dim)
 {
     Tree *t = new Tree();
     t->n = (int)n;
-    t->pts.assign(xyz, xyz + 3 * n);
+    t->dim = dim;
+    t->pts.assign(xyz, xyz + (size_t)dim * n);
+    t->sorted_rows.resize((size_t)dim * n + 1);
     t->key.resize(n + 1); t->vind.resize(n + 1); t->pos.resize(n + 1); t->sorted.resize(n + 1);
-    t->nodes.resize(2 * n + 2); t->boxes.resize(6 * (2 * n + 2));
+    t->nodes.resize(2 * n + 2); t->boxes.resize((size_t)2 * dim * (2 * n + 2));
     t->queue[0].resize(2 * n + 2); t->queue[1].resize(2 * n + 2);
     memset(&t->ctl, 0, sizeof t->ctl);
     if (n == 0) return t;
@@ -53,15 +54,38 @@ void *emu_build(const float *xyz, long n)
         t->ctl.queue_count[out_slot] = 0;
         t->ctl.queue_max[out_slot] = 0;
         emu::launch(in_count, EMU_BUILD_THREADS, [&] {
-            kd_split_kernel<EMU_BUILD_THREADS>(t->pts.data(), t->vind.data(), t->key.data(), t->pos.data(), t->nodes.data(), t->boxes.data(), t->queue[slot].data(),
-                            t->queue[out_slot].data(), &t->ctl, out_slot);
+            if (dim == 3)
+                kd_split_kernel<EMU_BUILD_THREADS, 3>(t->pts.data(), t->vind.data(), t->key.data(), t->pos.data(), t->nodes.data(), t->boxes.data(),
+                                                      t->queue[slot].data(), t->queue[out_slot].data(), &t->ctl, out_slot);
+            else
+                kd_split_kernel<EMU_BUILD_THREADS, kFeatureDim>(t->pts.data(), t->vind.data(), t->key.data(), t->pos.data(), t->nodes.data(),
+                                                                t->boxes.data(), t->queue[slot].data(), t->queue[out_slot].data(), &t->ctl, out_slot);
         });
         in_count = t->ctl.queue_count[out_slot];
         slot = out_slot;
     }
-    emu::launch(grid_for(n, 4), kQueryThreads, [&] { kd_reorder_kernel(t->pts.data(), t->vind.data(), (int)n, t->sorted.data()); });
+    if (dim == 3) emu::launch(grid_for(n, 4), kQueryThreads, [&] { kd_reorder_kernel(t->pts.data(), t->vind.data(), (int)n, t->sorted.data()); });
+    else emu::launch(grid_for(n, 4), kQueryThreads, [&] { kd_reorder_rows_kernel(t->pts.data(), t->vind.data(), (int)n, dim, t->sorted_rows.data()); });
     return t;
 }
+extern "C"
+{
+void *emu_build(const float *xyz, long n) { return build_rows(xyz, n, 3); }
+void *emu_build_rows(const float *rows, long n, int dim) { return build_rows(rows, n, dim); }
+// what opb_kdtree_feature_matching does for finite targets: a KDTree<33> over them, one walk per source descriptor
+void emu_match_tree(const float *src, long ns, const float *tgt, long nt, int32_t *nearest)
+{
+    int bad = 0;
+    emu::launch(grid_for(nt, 2), kQueryThreads, [&] { count_nonfinite_rows_kernel(tgt, (int)nt, kFeatureDim, &bad); });
+    if (bad) { for (long i = 0; i < ns; ++i) nearest[i] = -2; return; }
+    Tree *t = build_rows(tgt, nt, kFeatureDim);
+    const KdView v = t->view();
+    emu::launch((int)((ns + kMatchThreads - 1) / kMatchThreads), kMatchThreads, [&] { fpfh_match_tree_kernel(v, src, (int)ns, nearest); });
+    delete t;
+}
+}
+extern "C"
+{
 void emu_destroy(void *p) { delete (Tree *)p; }
 long emu_dump(void *p, int32_t *vind, int32_t *ni, float *nf, float *box)
 {
@@ -73,7 +97,7 @@ long emu_dump(void *p, int32_t *vind, int32_t *ni, float *nf, float *box)
         ni[5 * i] = nd.left; ni[5 * i + 1] = nd.right; ni[5 * i + 2] = nd.child1; ni[5 * i + 3] = nd.child2; ni[5 * i + 4] = nd.divfeat;
         nf[2 * i] = nd.divlow; nf[2 * i + 1] = nd.divhigh;
     }
-    for (int d = 0; d < 3; ++d) { box[d] = t->ctl.root_lo[d]; box[3 + d] = t->ctl.root_hi[d]; }
+    for (int d = 0; d < t->dim; ++d) { box[d] = t->ctl.root_lo[d]; box[t->dim + d] = t->ctl.root_hi[d]; }
     return t->ctl.n_nodes * 1000L + t->ctl.max_level;
 }
 void emu_search(void *p, const float *queries, long nq, int mode, int k, float radius, int32_t *out_index, float *out_dist, int32_t *out_count)

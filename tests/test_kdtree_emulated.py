@@ -43,6 +43,7 @@ def emu(tmp_path_factory):
     L.emu_normals.argtypes = [p, C.c_float, C.c_int, p]
     L.emu_fpfh.argtypes = [p, p, C.c_int, C.c_float, p]
     L.emu_match.argtypes = [p, C.c_long, p, C.c_long, p]
+    L.emu_match_tree.argtypes = [p, C.c_long, p, C.c_long, p]
     return L
 
 
@@ -110,10 +111,24 @@ def test_emulated_feature_matching_matches_the_oracle(emu):
     """fpfh_match_kernel (exhaustive 33-D nearest neighbour) against the oracle's KDTree<33> restatement on real descriptors"""
     from test_oracle_kdtree import _two_frames_features
     (_, fs), (_, ft) = _two_frames_features()
-    fs, ft = np.ascontiguousarray(fs[:700]), np.ascontiguousarray(ft[:1500])
+    fs, ft = np.ascontiguousarray(fs[:300]), np.ascontiguousarray(ft[:600])
     fs[7] = np.nan                                            # a NaN source feature matches nothing
     nearest = np.zeros(len(fs), np.int32)
     emu.emu_match(_ptr(fs), len(fs), _ptr(ft), len(ft), _ptr(nearest))
     want = oracleapi.feature_matching(fs, ft)
     got = np.stack([np.nonzero(nearest >= 0)[0], nearest[nearest >= 0]], 1).astype(np.int32)
     assert nearest[7] == -1 and np.array_equal(got, want)
+    # the reference's own way -- a KDTree<33> over the targets -- with duplicate descriptors, whose tie only the tree order settles
+    ft[40:60] = ft[300:320]
+    ft[61] = ft[62] = ft[63]
+    fs[100] = ft[305]
+    fs[101] = ft[63]
+    emu.emu_match_tree(_ptr(fs), len(fs), _ptr(ft), len(ft), _ptr(nearest))
+    want = oracleapi.feature_matching(fs, ft)
+    got = np.stack([np.nonzero(nearest >= 0)[0], nearest[nearest >= 0]], 1).astype(np.int32)
+    assert nearest[7] == -1 and np.array_equal(got, want)
+    emu.emu_match(_ptr(fs), len(fs), _ptr(ft), len(ft), _ptr(nearest))
+    assert (nearest[nearest >= 0] != want[:, 1]).any()        # the exhaustive scan orders those ties by index instead
+    ft[5] = np.nan
+    emu.emu_match_tree(_ptr(fs), len(fs), _ptr(ft), len(ft), _ptr(nearest))
+    assert (nearest == -2).all()                              # non-finite targets are detected (the library then scans exhaustively)

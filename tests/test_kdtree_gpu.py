@@ -149,8 +149,20 @@ def test_feature_matching_and_rejection_match_the_oracle():
     for _ in range(3):
         kept = reg.RejectMatchesRanSaPC(ps, pt, engine, kept)
     assert np.array_equal(kept, oracleapi.reject_matches(ps, pt, want, 3)) and 0 < len(kept) < len(m)
-    fs2 = fs.copy()
-    fs2[5] = np.nan
-    m2 = reg.FeatureMatching3D(fs2, ft)
-    assert len(m2) == len(fs) - 1 and np.array_equal(m2, oracleapi.feature_matching(fs2, ft))
+    fs2, ft2 = fs.copy(), ft.copy()
+    fs2[5] = np.nan                       # a NaN source matches nothing
+    ft2[100:140] = ft2[900:940]           # duplicate descriptors: exact ties, settled by the tree's visiting order
+    ft2[61] = ft2[62] = ft2[63]
+    fs2[300], fs2[301] = ft2[905], ft2[63]
+    m2 = reg.FeatureMatching3D(fs2, ft2)
+    assert len(m2) == len(fs) - 1 and np.array_equal(m2, oracleapi.feature_matching(fs2, ft2))
+    # a NaN target row: the reference's tree is poisoned and returns wrong neighbours; the device scans exhaustively instead
+    ft2[7] = np.nan
+    m3 = reg.FeatureMatching3D(fs2, ft2)
+    finite = np.ones(len(ft2), bool)
+    finite[7] = False
+    probe = m3[:400]
+    d = ((fs2[probe[:, 0], None, :].astype(np.float64) - ft2[None, finite, :]) ** 2).sum(-1)
+    best = ((fs2[probe[:, 0]].astype(np.float64) - ft2[probe[:, 1]]) ** 2).sum(-1)
+    assert len(m3) == len(fs) - 1 and (best <= d.min(1) * (1 + 1e-6)).all()
     assert len(reg.FeatureMatching3D(fs[:0], ft)) == 0 and len(reg.FeatureMatching3D(fs, ft[:0])) == 0
