@@ -32,7 +32,8 @@ namespace opb
 constexpr int kLeafMax = 10;
 constexpr int kBuildThreadsBig = 1024, kBuildThreadsMid = 256, kBuildThreadsSmall = 64; // CTA size by the level's largest node
 constexpr int kBuildBigNode = 8192, kBuildSmallNode = 256;
-constexpr int kMaxDepth = 64;
+constexpr int kMaxDepth = 64;      // search stack, 3-D trees (a 307,200-point frame is 23 levels deep)
+constexpr int kMaxDepthRows = 256; // descriptor trees: middle splits of skewed histograms run 70-80 levels deep at 5,000 rows
 constexpr int kMaxDim = 33;       // 3 (points, KDTree<3>) or 33 (FPFH descriptors, KDTree<33>)
 constexpr int kQueryThreads = 128;
 constexpr int kKnnCap = 64;       // k of the shared-memory k-nearest list
@@ -376,7 +377,8 @@ __device__ bool kd_find(const KdView &t, ResultSet &rs, const float *q, float ep
         if (q[d] < t.root_lo[d]) { const float x = fsub(q[d], t.root_lo[d]); dists[d] = fmul(x, x); distsq = fadd(distsq, dists[d]); }
         if (q[d] > t.root_hi[d]) { const float x = fsub(q[d], t.root_hi[d]); dists[d] = fmul(x, x); distsq = fadd(distsq, dists[d]); }
     }
-    KdFrame st[kMaxDepth];
+    constexpr int kStack = DIM == 3 ? kMaxDepth : kMaxDepthRows;
+    KdFrame st[kStack];
     int sp = 0;
     st[0].node = 0; st[0].idx_stage = 0; st[0].value = distsq; st[0].cut = 0.0f;
     while (sp >= 0)
@@ -423,7 +425,7 @@ __device__ bool kd_find(const KdView &t, ResultSet &rs, const float *q, float ep
             else { best = nd.child2; f.node = nd.child1; f.cut = fmul(diff1, diff1); }
             f.idx_stage = (cf << 2) | 1;
             st[sp] = f;
-            if (sp + 1 >= kMaxDepth) return true; // the host refuses trees deeper than kMaxDepth - 2 before any search
+            if (sp + 1 >= kStack) return true; // the host refuses trees deeper than the stack before any search
             ++sp;
             st[sp].node = best; st[sp].idx_stage = 0; st[sp].value = f.value; st[sp].cut = 0.0f;
         }
@@ -998,7 +1000,7 @@ static int kd_build_rows(opb_kdtree *t, const float *xyz, size_t n)
     int in_count = 1, slot = 0, largest = (int)n;
     for (int level = 0; in_count > 0; ++level)
     {
-        if (level > 4 * kMaxDepth) { set_error("kd-tree build did not terminate"); return OPB_ERR_UNSUPPORTED; }
+        if (level > 4 * kMaxDepthRows) { set_error("kd-tree build did not terminate"); return OPB_ERR_UNSUPPORTED; }
         const int out_slot = slot ^ 1;
         OPB_CUDA(cudaMemsetAsync(&t->d_ctl->queue_count[out_slot], 0, sizeof(int), s));
         OPB_CUDA(cudaMemsetAsync(&t->d_ctl->queue_max[out_slot], 0, sizeof(int), s));
@@ -1027,9 +1029,10 @@ static int kd_build_rows(opb_kdtree *t, const float *xyz, size_t n)
     OPB_CUDA(cudaGetLastError());
     t->n_nodes = t->h_ctl->n_nodes;
     t->max_level = t->h_ctl->max_level;
-    if (t->max_level + 2 > kMaxDepth)
+    const int stack_levels = dim == 3 ? kMaxDepth : kMaxDepthRows;
+    if (t->max_level + 2 > stack_levels)
     {
-        set_error("kd-tree of depth %d exceeds the search stack (%d levels)", t->max_level, kMaxDepth - 2);
+        set_error("kd-tree of depth %d exceeds the search stack (%d levels)", t->max_level, stack_levels - 2);
         return OPB_ERR_UNSUPPORTED;
     }
     t->built = true;
@@ -1210,12 +1213,8 @@ int opb_kdtree_feature_matching(opb_kdtree *t, const float *src_feat33, size_t n
     OPB_CUDA(cudaStreamSynchronize(s));
     const unsigned blocks = (unsigned)((ns + kMatchThreads - 1) / kMatchThreads);
     const char *forced = getenv("OPB_MATCH_EXHAUSTIVE"); // developer knob
-    if (bad_rows || (forced && atoi(forced)))
-    {
-        fpfh_match_kernel<<<blocks, kMatchThreads, 0, s>>>((const float *)t->d_aux[0], (int)ns, (const float *)t->d_aux[2], (int)nt, (int *)t->d_aux[3]);
-        OPB_CUDA(cudaGetLastError());
-    }
-    else
+    bool exhaustive = bad_rows || (forced && atoi(forced));
+    if (!exhaustive)
     {
         if (!t->feature_tree)
         {
@@ -1223,9 +1222,19 @@ int opb_kdtree_feature_matching(opb_kdtree *t, const float *src_feat33, size_t n
             t->feature_tree->dim = kFeatureDim;
         }
         opb_kdtree *ft = t->feature_tree;
-        if ((rc = kd_build_rows(ft, (const float *)t->d_aux[2], nt))) return rc;
-        OPB_CUDA(cudaStreamSynchronize(ft->stream));
-        fpfh_match_tree_kernel<<<blocks, kMatchThreads, 0, s>>>(kd_view(ft), (const float *)t->d_aux[0], (int)ns, (int *)t->d_aux[3]);
+        rc = kd_build_rows(ft, (const float *)t->d_aux[2], nt);
+        if (rc == OPB_ERR_UNSUPPORTED) exhaustive = true; // a tree deeper than the search stack (never seen: 5,000 descriptors are 70-80 levels)
+        else if (rc) return rc;
+        else
+        {
+            OPB_CUDA(cudaStreamSynchronize(ft->stream));
+            fpfh_match_tree_kernel<<<blocks, kMatchThreads, 0, s>>>(kd_view(ft), (const float *)t->d_aux[0], (int)ns, (int *)t->d_aux[3]);
+            OPB_CUDA(cudaGetLastError());
+        }
+    }
+    if (exhaustive)
+    {
+        fpfh_match_kernel<<<blocks, kMatchThreads, 0, s>>>((const float *)t->d_aux[0], (int)ns, (const float *)t->d_aux[2], (int)nt, (int *)t->d_aux[3]);
         OPB_CUDA(cudaGetLastError());
     }
     std::vector<int> nearest(ns);
