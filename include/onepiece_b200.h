@@ -329,6 +329,20 @@ int opb_kdtree_feature_matching(opb_kdtree *t, const float *src_feat33, size_t n
  * code and host pointers: the draws form one sequential data-dependent chain; identical to the reference index for index. */
 int opb_reject_matches(const float *src_xyz, size_t ns, const float *tgt_xyz, size_t nt, int32_t *pairs, size_t *n_pairs,
                        uint32_t *engine_state, int candidate_num, float difference);
+/* geometry::EstimateRigidTransformationRANSAC(correspondence_set, inliers, inlier_ids, max_iteration, threshold)
+ * (src/Geometry/Ransac.cpp:7-41 over 3rdparty/GRANSAC/GRANSAC.hpp:71-131 and TransformationModel.hpp:28-96), the last step of
+ * RansacRegistration (GlobalRegistration.cpp:252): max_iteration hypotheses, each the rigid motion of eight distinct pairs
+ * (EstimateRigidTransformation in float, operation for operation), scored by the number of pairs with |R a + t - b| < threshold;
+ * the first hypothesis with the strictly largest score wins; T = its eight-point motion (column-major), inlier_ids = the pairs
+ * it explains, ascending (the reference lists them in its shuffled order), room for n.  The reference draws its samples from
+ * engines seeded by std::random_device, so its own result differs from run to run; here hypothesis h takes its sample from a
+ * counter-based generator keyed by (seed, h), or from forced_samples (max_iteration x 8 pair indices) when that is not NULL --
+ * with the same samples the winner, its motion and its inliers are the reference's bit for bit.  n < 8: T = 0, no inliers
+ * (the reference's warning path); n == 8, or no hypothesis with an inlier: OPB_ERR_INVALID (the reference crashes).
+ * best_iteration / best_sample (8 ints) may be NULL.  `t` lends its stream and buffers. */
+int opb_ransac_rigid_transformation(opb_kdtree *t, const float *src_xyz, const float *tgt_xyz, size_t n, int max_iteration, double threshold,
+                                    uint64_t seed, const int32_t *forced_samples, float T_colmajor[16], int32_t *inlier_ids, size_t *n_inliers,
+                                    int32_t *best_iteration, int32_t best_sample[8]);
 /* test hook: the built tree (vind: n ints; nodes in allocation order, root = 0: left, right, child1, child2 (-1 = leaf), divfeat;
  * divlow, divhigh); all output pointers NULL -> only n_nodes */
 int opb_kdtree_dump(opb_kdtree *t, int32_t *vind, int32_t *node_ints5, float *node_floats2, float root_box[6], size_t *n_nodes);

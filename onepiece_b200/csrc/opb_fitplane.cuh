@@ -32,9 +32,11 @@ __device__ __forceinline__ void rot_apply(float &x, float &y, Rot j)
     y = fadd(fmul(-j.s, xi), fmul(j.c, yi));
 }
 // third column of U of JacobiSVD(W) after the descending sort; W row-major
-static __device__ void svd3_smallest_direction(const float *Win, float *normal)
+// JacobiSVD<MatrixXf>(W 3x3, ComputeThinU | ComputeThinV): U and (WITH_V) V, columns sorted by descending singular value
+template <bool WITH_V>
+static __device__ void jacobi_svd3(const float *Win, float (&U)[3][3], float (&V)[3][3])
 {
-    float W[3][3], U[3][3];
+    float W[3][3];
     float scale = 0.0f;
 #pragma unroll
     for (int i = 0; i < 9; ++i) scale = fmaxf(scale, fabsf(Win[i]));
@@ -42,7 +44,7 @@ static __device__ void svd3_smallest_direction(const float *Win, float *normal)
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { W[r][c] = fdiv(Win[r * 3 + c], scale); U[r][c] = r == c ? 1.0f : 0.0f; }
+        for (int c = 0; c < 3; ++c) { W[r][c] = fdiv(Win[r * 3 + c], scale); U[r][c] = r == c ? 1.0f : 0.0f; if (WITH_V) V[r][c] = U[r][c]; }
     const float precision = 2.0f * FLT_EPSILON;
     float max_diag = fmaxf(fabsf(W[0][0]), fmaxf(fabsf(W[1][1]), fabsf(W[2][2])));
     bool finished = false;
@@ -84,6 +86,9 @@ static __device__ void svd3_smallest_direction(const float *Win, float *normal)
                 {
 #pragma unroll
                     for (int r = 0; r < 3; ++r) rot_apply(W[r][p], W[r][q], jrt);    // columns p, q with j_right^T
+                    if (WITH_V)
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) rot_apply(V[r][p], V[r][q], jrt); // m_matrixV.applyOnTheRight(p, q, j_right)
                 }
                 max_diag = fmaxf(max_diag, fmaxf(fabsf(W[p][p]), fabsf(W[q][q])));
             }
@@ -111,9 +116,65 @@ static __device__ void svd3_smallest_direction(const float *Win, float *normal)
             const float tmp = sv[i]; sv[i] = sv[pos]; sv[pos] = tmp;
 #pragma unroll
             for (int r = 0; r < 3; ++r) { const float u = U[r][i]; U[r][i] = U[r][pos]; U[r][pos] = u; }
+            if (WITH_V)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { const float v = V[r][i]; V[r][i] = V[r][pos]; V[r][pos] = v; }
         }
     }
+}
+// third column of U of JacobiSVD(W) after the descending sort; W row-major
+static __device__ void svd3_smallest_direction(const float *Win, float *normal)
+{
+    float U[3][3], V[3][3];
+    jacobi_svd3<false>(Win, U, V);
     normal[0] = U[0][2]; normal[1] = U[1][2]; normal[2] = U[2][2];
+}
+// geometry::EstimateRigidTransformation (Geometry.cpp:107-151) over `count` pairs a(k) -> b(k), operation for operation: float
+// means, W += (a - ma)(b - mb)^T, JacobiSVD, R = V U^T (Eigen's coefficient-based product of dynamic matrices: sequential sum),
+// cofactor determinant, V's last column flipped when it is negative, t = mb - R ma (fixed-size product: x + (y + z)).
+// R row-major, t.  PairOf(k, a, b) fills the k-th pair.
+template <class PairOf>
+static __device__ void kabsch_f32(int count, PairOf pair_of, float *R, float *t)
+{
+    float ma[3] = {0.0f, 0.0f, 0.0f}, mb[3] = {0.0f, 0.0f, 0.0f};
+    for (int k = 0; k < count; ++k)
+    {
+        float a[3], b[3];
+        pair_of(k, a, b);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { ma[c] = fadd(ma[c], a[c]); mb[c] = fadd(mb[c], b[c]); }
+    }
+    const float cnt = (float)count;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { ma[c] = fdiv(ma[c], cnt); mb[c] = fdiv(mb[c], cnt); }
+    float W[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < count; ++k)
+    {
+        float a[3], b[3];
+        pair_of(k, a, b);
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) W[p * 3 + q] = fadd(W[p * 3 + q], fmul(fsub(a[p], ma[p]), fsub(b[q], mb[q])));
+    }
+    float U[3][3], V[3][3];
+    jacobi_svd3<true>(W, U, V);
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass)
+    {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) R[i * 3 + j] = fadd(fadd(fmul(V[i][0], U[j][0]), fmul(V[i][1], U[j][1])), fmul(V[i][2], U[j][2]));
+        const float c0 = fmul(R[0], fsub(fmul(R[4], R[8]), fmul(R[5], R[7])));
+        const float c1 = fmul(R[1], fsub(fmul(R[3], R[8]), fmul(R[5], R[6])));
+        const float c2 = fmul(R[2], fsub(fmul(R[3], R[7]), fmul(R[4], R[6])));
+        const float det = fadd(fsub(c0, c1), c2);
+        if (!(det < 0.0f) || pass) break;
+        V[0][2] = -V[0][2]; V[1][2] = -V[1][2]; V[2][2] = -V[2][2];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) t[i] = fsub(mb[i], fadd(fmul(R[i * 3], ma[0]), fadd(fmul(R[i * 3 + 1], ma[1]), fmul(R[i * 3 + 2], ma[2]))));
 }
 
 // FitPlane over the points pts[index(0..count)]: float mean, float covariance / count, smallest singular direction,

@@ -857,6 +857,93 @@ __global__ void __launch_bounds__(kMatchThreads) fpfh_match_tree_kernel(KdView t
     kd_find<kFeatureDim>(t, rs, q, 1.0f);
     nearest[i] = rs.index;
 }
+// ---------------------------------------------------------------------------------------------------------
+// geometry::EstimateRigidTransformationRANSAC (src/Geometry/Ransac.cpp:7-41) on 3rdparty/GRANSAC/GRANSAC.hpp:71-131 with
+// TransformationModel (src/Geometry/TransformationModel.hpp:28-96): every iteration takes eight distinct pairs, fits a rigid
+// motion to them (EstimateRigidTransformation, float) and scores it by the number of pairs with |R a + t - b| < threshold;
+// the FIRST iteration with the strictly largest score wins (GRANSAC.hpp:113-122) and its eight-point motion is the result.
+// The iterations are independent: one thread per hypothesis, all threads of a warp stream the same pair at the same time
+// (broadcast loads).  GRANSAC seeds its engines from std::random_device, so the reference's choice of samples is not
+// reproducible even by itself; here the samples come from a counter-based generator (or from the caller, which is how the
+// parity tests force the same hypotheses through the oracle).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kRansacSample = 8; // MIN_INLIER_SIZE_RANSAC_TRANSFORMATION, TransformationModel.hpp:5
+__device__ __forceinline__ unsigned int ransac_mix(unsigned long long x)
+{
+    x += 0x9E3779B97F4A7C15ull; // splitmix64
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return (unsigned int)((x ^ (x >> 31)) >> 32);
+}
+// eight distinct indices, each uniform over what is left: the distribution of the first eight entries of a uniform shuffle
+__device__ __forceinline__ void ransac_draw(unsigned long long seed, int iteration, int n, int *s8)
+{
+    for (int k = 0; k < kRansacSample; ++k)
+        for (unsigned int attempt = 0;; ++attempt)
+        {
+            const unsigned int r = ransac_mix(seed ^ ((unsigned long long)iteration << 24) ^ ((unsigned long long)k << 20) ^ attempt);
+            const int idx = (int)(((unsigned long long)r * (unsigned long long)n) >> 32);
+            bool seen = false;
+            for (int j = 0; j < k; ++j) seen |= s8[j] == idx;
+            if (!seen) { s8[k] = idx; break; }
+        }
+}
+__device__ __forceinline__ bool ransac_is_inlier(const float *R, const float *t, const float *__restrict__ a, const float *__restrict__ b, int i,
+                                                 double threshold)
+{
+    const float ax = a[3 * i], ay = a[3 * i + 1], az = a[3 * i + 2];
+    float e[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+        e[r] = fsub(fadd(fadd(fmul(R[r * 3], ax), fadd(fmul(R[r * 3 + 1], ay), fmul(R[r * 3 + 2], az))), t[r]), b[3 * i + r]);
+    const float err = __fsqrt_rn(fadd(fmul(e[0], e[0]), fadd(fmul(e[1], e[1]), fmul(e[2], e[2]))));
+    return (double)err < threshold; // ComputeDistanceMeasure returns the float norm as a double (TransformationModel.hpp:37-52,83)
+}
+__device__ __forceinline__ void ransac_model(const float *__restrict__ a, const float *__restrict__ b, const int *s8, float *R, float *t)
+{
+    kabsch_f32(kRansacSample, [&](int k, float *pa, float *pb) {
+        const int j = s8[k];
+        pa[0] = a[3 * j]; pa[1] = a[3 * j + 1]; pa[2] = a[3 * j + 2];
+        pb[0] = b[3 * j]; pb[1] = b[3 * j + 1]; pb[2] = b[3 * j + 2];
+    }, R, t);
+}
+// best: (score << 32) | ~iteration, so that atomicMax keeps the highest score and, among equals, the earliest iteration
+__global__ void __launch_bounds__(128) ransac_score_kernel(const float *__restrict__ a, const float *__restrict__ b, int n, int iterations,
+                                                           double threshold, unsigned long long seed, const int *__restrict__ forced,
+                                                           int *__restrict__ scores, unsigned long long *best)
+{
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= iterations) return;
+    int s8[kRansacSample];
+    if (forced)
+        for (int k = 0; k < kRansacSample; ++k) s8[k] = forced[(size_t)h * kRansacSample + k];
+    else ransac_draw(seed, h, n, s8);
+    float R[9], t[3];
+    ransac_model(a, b, s8, R, t);
+    int score = 0;
+    for (int i = 0; i < n; ++i) score += ransac_is_inlier(R, t, a, b, i, threshold);
+    scores[h] = score;
+    atomicMax(best, ((unsigned long long)(unsigned int)score << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)h));
+}
+// the winner again: its sample, its motion (12 floats: R row-major, t) and one inlier flag per pair
+__global__ void ransac_winner_kernel(const float *__restrict__ a, const float *__restrict__ b, int n, int winner, double threshold,
+                                     unsigned long long seed, const int *__restrict__ forced, unsigned char *__restrict__ inlier,
+                                     float *__restrict__ motion, int *__restrict__ sample)
+{
+    int s8[kRansacSample];
+    if (forced)
+        for (int k = 0; k < kRansacSample; ++k) s8[k] = forced[(size_t)winner * kRansacSample + k];
+    else ransac_draw(seed, winner, n, s8);
+    float R[9], t[3];
+    ransac_model(a, b, s8, R, t);
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        for (int k = 0; k < 9; ++k) motion[k] = R[k];
+        for (int k = 0; k < 3; ++k) motion[9 + k] = t[k];
+        for (int k = 0; k < kRansacSample; ++k) sample[k] = s8[k];
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) inlier[i] = ransac_is_inlier(R, t, a, b, i, threshold);
+}
 // rows with a NaN or an infinity (isolated points' descriptors are 0 * inf): flags[0] = their number
 __global__ void count_nonfinite_rows_kernel(const float *__restrict__ rows, int n, int dim, int *flags)
 {
@@ -1302,5 +1389,71 @@ int opb_reject_matches(const float *src_xyz, size_t ns, const float *tgt_xyz, si
     memcpy(pairs, kept.data(), kept.size() * sizeof(int32_t));
     *n_pairs = kept.size() / 2;
     *engine_state = x;
+    return OPB_OK;
+}
+
+int opb_ransac_rigid_transformation(opb_kdtree *t, const float *src_xyz, const float *tgt_xyz, size_t n, int max_iteration, double threshold,
+                                    uint64_t seed, const int32_t *forced_samples, float T_colmajor[16], int32_t *inlier_ids, size_t *n_inliers,
+                                    int32_t *best_iteration, int32_t best_sample[8])
+{
+    if (!t || !T_colmajor || !n_inliers || (n && (!src_xyz || !tgt_xyz || !inlier_ids))) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    *n_inliers = 0;
+    if (best_iteration) *best_iteration = -1;
+    for (int i = 0; i < 16; ++i) T_colmajor[i] = 0.0f;
+    if (n < (size_t)kRansacSample) return OPB_OK; // "Too few canidate point pair": the zero matrix (Ransac.cpp:10-14)
+    if (n == (size_t)kRansacSample) { set_error("RANSAC needs more than %d pairs (GRANSAC refuses and the reference then dereferences a null model)", kRansacSample); return OPB_ERR_INVALID; }
+    if (max_iteration < 1 || max_iteration > (1 << 24)) { set_error("max_iteration must be 1..2^24"); return OPB_ERR_INVALID; }
+    if (n > 0x7FFFFFF0u / 3) { set_error("too many pairs"); return OPB_ERR_INVALID; }
+    if (forced_samples)
+        for (size_t i = 0; i < (size_t)max_iteration * kRansacSample; ++i)
+            if (forced_samples[i] < 0 || (size_t)forced_samples[i] >= n) { set_error("sample %zu names a pair outside the set", i); return OPB_ERR_INVALID; }
+    OPB_CUDA(cudaSetDevice(t->device));
+    int rc;
+    const size_t pts_bytes = n * 3 * sizeof(float), iters = (size_t)max_iteration;
+    if ((rc = kd_reserve(&t->d_aux[0], &t->aux_bytes[0], 2 * pts_bytes))) return rc;                                   // a, b
+    if ((rc = kd_reserve(&t->d_aux[1], &t->aux_bytes[1], iters * (forced_samples ? kRansacSample + 1 : 1) * sizeof(int) + 64))) return rc; // scores, samples
+    if ((rc = kd_reserve(&t->d_aux[3], &t->aux_bytes[3], n + 256))) return rc;                                         // flags, motion, sample, best
+    cudaStream_t s = t->stream;
+    float *da = (float *)t->d_aux[0], *db = da + n * 3;
+    int *scores = (int *)t->d_aux[1], *forced = forced_samples ? scores + iters : nullptr;
+    unsigned char *flags = (unsigned char *)t->d_aux[3];
+    char *tail = (char *)t->d_aux[3] + ((n + 63) & ~(size_t)63);
+    unsigned long long *best = (unsigned long long *)tail;
+    float *motion = (float *)(tail + 16);
+    int *sample = (int *)(tail + 16 + 12 * sizeof(float));
+    OPB_CUDA(cudaMemcpyAsync(da, src_xyz, pts_bytes, cudaMemcpyDefault, s));
+    OPB_CUDA(cudaMemcpyAsync(db, tgt_xyz, pts_bytes, cudaMemcpyDefault, s));
+    if (forced) OPB_CUDA(cudaMemcpyAsync(forced, forced_samples, iters * kRansacSample * sizeof(int), cudaMemcpyDefault, s));
+    OPB_CUDA(cudaMemsetAsync(best, 0, sizeof(unsigned long long), s));
+    ransac_score_kernel<<<(unsigned)((iters + 127) / 128), 128, 0, s>>>(da, db, (int)n, max_iteration, threshold, seed, forced, scores, best);
+    OPB_CUDA(cudaGetLastError());
+    unsigned long long h_best = 0;
+    OPB_CUDA(cudaMemcpyAsync(&h_best, best, sizeof(h_best), cudaMemcpyDeviceToHost, s));
+    OPB_CUDA(cudaStreamSynchronize(s));
+    const unsigned int score = (unsigned int)(h_best >> 32);
+    if (score == 0) { set_error("no hypothesis has an inlier (the reference would dereference a null model)"); return OPB_ERR_INVALID; }
+    const int winner = (int)(0xFFFFFFFFu - (unsigned int)(h_best & 0xFFFFFFFFu));
+    ransac_winner_kernel<<<kd_grid(t, n, 8), kQueryThreads, 0, s>>>(da, db, (int)n, winner, threshold, seed, forced, flags, motion, sample);
+    OPB_CUDA(cudaGetLastError());
+    std::vector<unsigned char> h_flags(n);
+    float h_motion[12];
+    int h_sample[kRansacSample];
+    OPB_CUDA(cudaMemcpyAsync(h_flags.data(), flags, n, cudaMemcpyDeviceToHost, s));
+    OPB_CUDA(cudaMemcpyAsync(h_motion, motion, sizeof(h_motion), cudaMemcpyDeviceToHost, s));
+    OPB_CUDA(cudaMemcpyAsync(h_sample, sample, sizeof(h_sample), cudaMemcpyDeviceToHost, s));
+    OPB_CUDA(cudaStreamSynchronize(s));
+    size_t m = 0;
+    for (size_t i = 0; i < n; ++i)
+        if (h_flags[i]) inlier_ids[m++] = (int32_t)i;
+    *n_inliers = m;
+    for (int r = 0; r < 3; ++r)
+    {
+        for (int c = 0; c < 3; ++c) T_colmajor[c * 4 + r] = h_motion[r * 3 + c];
+        T_colmajor[12 + r] = h_motion[9 + r];
+    }
+    T_colmajor[15] = 1.0f;
+    if (best_iteration) *best_iteration = winner;
+    if (best_sample)
+        for (int k = 0; k < kRansacSample; ++k) best_sample[k] = h_sample[k];
     return OPB_OK;
 }

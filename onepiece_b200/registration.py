@@ -167,6 +167,65 @@ def RejectMatchesRanSaPC(source_points, target_points, engine: DefaultRandomEngi
     return p[:m.value].copy()
 
 
+def EstimateRigidTransformationRANSAC(source_points, target_points, max_iteration: int = 2000, threshold: float = 0.1, seed: int = 0,
+                                      samples=None, device: int = 0):
+    """geometry::EstimateRigidTransformationRANSAC(correspondence_set, inliers, inlier_ids, max_iteration, threshold) (reference
+    src/Geometry/Ransac.cpp:7-41) on the GPU over the pairs source_points[i] -> target_points[i]
+    -> (T 4x4 float32, inlier_ids int32 ascending, best_iteration, best_sample[8]).  `samples` ([max_iteration, 8] pair indices)
+    forces the hypotheses; otherwise hypothesis h draws from a generator keyed by (seed, h)."""
+    a = np.ascontiguousarray(source_points, np.float32).reshape(-1, 3)
+    b = np.ascontiguousarray(target_points, np.float32).reshape(-1, 3)
+    if len(a) != len(b):
+        raise ValueError("source_points and target_points must pair up")
+    forced = None
+    if samples is not None:
+        forced = np.ascontiguousarray(samples, np.int32).reshape(-1, 8)
+        max_iteration = len(forced)
+    T = np.zeros(16, np.float32)
+    ids = np.zeros(max(len(a), 1), np.int32)
+    m, it = C.c_size_t(0), C.c_int32(-1)
+    s8 = np.zeros(8, np.int32)
+    capi.check(capi.lib.opb_ransac_rigid_transformation(KDTree(device)._h, _ptr(a), _ptr(b), len(a), max_iteration, threshold, seed,
+                                                        _ptr(forced), _ptr(T), _ptr(ids), C.byref(m), C.byref(it), _ptr(s8)))
+    return T.reshape(4, 4).T.copy(), ids[:m.value].copy(), it.value, s8
+
+
+@dataclass
+class RANSACParameter:
+    """registration::RANSACParameter (reference src/Registration/GlobalRegistration.h:12-24)"""
+    max_iteration: int = 30
+    threshold: float = 0.2
+    scaling: float = 1.0
+    max_nn: int = 100
+    max_nn_normal: int = 30
+    search_radius_normal: float = 0.1
+    voxel_len: float = 0.1
+    search_radius: float = 0.25
+
+
+def RansacRegistration(source_feature_pcd: "PointCloud", target_feature_pcd: "PointCloud", source_features, target_features,
+                       r_para: RANSACParameter = RANSACParameter(), seed: int = 0, device: int = 0):
+    """registration::RansacRegistration(source_feature_pcd, target_feature_pcd, source_features, target_features, r_para)
+    (reference src/Registration/GlobalRegistration.cpp:219-267), every step on the library: descriptor matching, three rejection
+    passes on one default-seeded engine, RANSAC, ComputeRMSE -> RegistrationResult."""
+    matches = FeatureMatching3D(source_features, target_features, device)
+    engine = DefaultRandomEngine()
+    for _ in range(3):
+        matches = RejectMatchesRanSaPC(source_feature_pcd.points, target_feature_pcd.points, engine, matches)
+    a = source_feature_pcd.points[matches[:, 0]]
+    b = target_feature_pcd.points[matches[:, 1]]
+    T, ids, _, _ = EstimateRigidTransformationRANSAC(a, b, r_para.max_iteration, r_para.threshold, seed, None, device)
+    res = RegistrationResult(T=T, correspondence_set_index=matches[ids], correspondence_set=(a[ids], b[ids]), ok=len(ids) > 0)
+    if len(ids):
+        # ComputeRMSE (GlobalRegistration.cpp:7-15): float sum of squared norms in inlier order, sqrt(sum / count)
+        e = (a[ids] @ T[:3, :3].T + T[:3, 3] - b[ids]).astype(np.float32)
+        total = np.float32(0)
+        for v in (e * e).sum(1, dtype=np.float32):
+            total = np.float32(total + v)
+        res.rmse = float(np.sqrt(total / np.float32(len(ids))))
+    return res
+
+
 class _Workspace:
     _by_device = {}
 

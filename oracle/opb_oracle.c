@@ -1684,7 +1684,10 @@ static void rot_apply(float *x, int incx, float *y, int incy, int n, jrot_t j)
     }
 }
 /* JacobiSVD<MatrixXf>(W 3x3, ComputeThinU | ComputeThinV): U (row-major 3x3) and the singular values, sorted descending */
-static void jacobi_svd3(const float *Win, float *U, float *sv)
+static void jacobi_svd3_uv(const float *Win, float *U, float *V, float *sv);
+static void jacobi_svd3(const float *Win, float *U, float *sv) { jacobi_svd3_uv(Win, U, NULL, sv); }
+/* the same with V (row-major 3x3) when V != NULL: m_matrixV.applyOnTheRight(p, q, j_right), JacobiSVD.h:~730 */
+static void jacobi_svd3_uv(const float *Win, float *U, float *V, float *sv)
 {
     float W[9]; /* row-major work matrix */
     float scale = 0.0f;
@@ -1692,6 +1695,7 @@ static void jacobi_svd3(const float *Win, float *U, float *sv)
     if (scale == 0.0f) scale = 1.0f;
     for (int i = 0; i < 9; ++i) W[i] = Win[i] / scale;
     for (int i = 0; i < 9; ++i) U[i] = (i % 4 == 0) ? 1.0f : 0.0f;
+    if (V) for (int i = 0; i < 9; ++i) V[i] = (i % 4 == 0) ? 1.0f : 0.0f;
     const float precision = 2.0f * FLT_EPSILON, consider_zero = FLT_MIN;
     float max_diag = fmaxf(fabsf(W[0]), fmaxf(fabsf(W[4]), fabsf(W[8])));
     int finished = 0;
@@ -1725,6 +1729,7 @@ static void jacobi_svd3(const float *Win, float *U, float *sv)
                     rot_apply(&W[p * 3], 1, &W[q * 3], 1, 3, j_left);       /* workMatrix.applyOnTheLeft(p, q, j_left): rows */
                     rot_apply(&U[p], 3, &U[q], 3, 3, (jrot_t){jlt.c, -jlt.s}); /* U.applyOnTheRight(p, q, j_left^T): columns, with (j^T)^T */
                     rot_apply(&W[p], 3, &W[q], 3, 3, jrt);                  /* workMatrix.applyOnTheRight(p, q, j_right): columns, with j^T */
+                    if (V) rot_apply(&V[p], 3, &V[q], 3, 3, jrt);           /* m_matrixV.applyOnTheRight(p, q, j_right) */
                     max_diag = fmaxf(max_diag, fmaxf(fabsf(W[p * 3 + p]), fabsf(W[q * 3 + q])));
                 }
             }
@@ -1746,6 +1751,7 @@ static void jacobi_svd3(const float *Win, float *U, float *sv)
         {
             const float tmp = sv[i]; sv[i] = sv[pos]; sv[pos] = tmp;
             for (int r = 0; r < 3; ++r) { const float u = U[r * 3 + i]; U[r * 3 + i] = U[r * 3 + pos]; U[r * 3 + pos] = u; }
+            if (V) for (int r = 0; r < 3; ++r) { const float v = V[r * 3 + i]; V[r * 3 + i] = V[r * 3 + pos]; V[r * 3 + pos] = v; }
         }
     }
 }
@@ -2385,4 +2391,80 @@ long orc_reject_matches(const float *src, const float *tgt, int32_t *pairs, long
     }
     free(kept);
     return n;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * geometry::EstimateRigidTransformation (Geometry.cpp:107-151) in the float build, operation for operation: float means,
+ * W += (a - ma)(b - mb)^T, JacobiSVD<MatrixXf>(W, ThinU | ThinV), R = V U^T through Eigen's coefficient-based product of
+ * dynamic 3x3 matrices (sequential sum), determinant by cofactors (bruteforce_det3_helper), V's last column flipped if
+ * det < 0, t = mb - R ma (fixed-size product: x + (y + z)).  T row-major 4x4.  Used where the result decides something
+ * discrete: the RANSAC hypotheses of geometry::EstimateRigidTransformationRANSAC (Ransac.cpp:7-41).
+ * ------------------------------------------------------------------------------------------------------------------ */
+static void kabsch_f32(const float *a, const float *b, long n, float *T)
+{
+    float ma[3] = {0, 0, 0}, mb[3] = {0, 0, 0}, W[9] = {0};
+    for (long i = 0; i < n; ++i)
+        for (int c = 0; c < 3; ++c) { ma[c] += a[3 * i + c]; mb[c] += b[3 * i + c]; }
+    for (int c = 0; c < 3; ++c) { ma[c] /= (float)n; mb[c] /= (float)n; }
+    for (long i = 0; i < n; ++i)
+        for (int p = 0; p < 3; ++p)
+            for (int q = 0; q < 3; ++q) W[p * 3 + q] += (a[3 * i + p] - ma[p]) * (b[3 * i + q] - mb[q]);
+    float U[9], V[9], sv[3], R[9];
+    jacobi_svd3_uv(W, U, V, sv);
+    for (int pass = 0; pass < 2; ++pass)
+    {
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) R[i * 3 + j] = (V[i * 3] * U[j * 3] + V[i * 3 + 1] * U[j * 3 + 1]) + V[i * 3 + 2] * U[j * 3 + 2];
+        const float det = (R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6])) + R[2] * (R[3] * R[7] - R[4] * R[6]);
+        if (!(det < 0) || pass) break;
+        V[2] = -V[2]; V[5] = -V[5]; V[8] = -V[8];
+    }
+    for (int i = 0; i < 16; ++i) T[i] = 0.0f;
+    for (int i = 0; i < 3; ++i)
+    {
+        for (int j = 0; j < 3; ++j) T[i * 4 + j] = R[i * 3 + j];
+        T[i * 4 + 3] = mb[i] - (R[i * 3] * ma[0] + (R[i * 3 + 1] * ma[1] + R[i * 3 + 2] * ma[2]));
+    }
+    T[15] = 1.0f;
+}
+void orc_kabsch_f32(const float *a, const float *b, long n, float *T_rowmajor) { kabsch_f32(a, b, n, T_rowmajor); }
+/* one RANSAC hypothesis: TransformationModel over the eight sampled pairs (TransformationModel.hpp:54-75), Evaluate over all
+ * pairs (:77-94): inlier if |R a + t - b| < threshold (float norm against the double threshold) -> inlier count */
+long orc_ransac_hypothesis(const float *a, const float *b, long n, const int32_t *sample8, double threshold, float *T_rowmajor, uint8_t *inlier)
+{
+    float sa[24], sb[24], T[16];
+    for (int k = 0; k < 8; ++k)
+        for (int c = 0; c < 3; ++c) { sa[3 * k + c] = a[3 * (long)sample8[k] + c]; sb[3 * k + c] = b[3 * (long)sample8[k] + c]; }
+    kabsch_f32(sa, sb, 8, T);
+    long cnt = 0;
+    for (long i = 0; i < n; ++i)
+    {
+        float e[3];
+        for (int r = 0; r < 3; ++r)
+            e[r] = ((T[r * 4] * a[3 * i] + (T[r * 4 + 1] * a[3 * i + 1] + T[r * 4 + 2] * a[3 * i + 2])) + T[r * 4 + 3]) - b[3 * i + r];
+        const float err = sqrtf(e[0] * e[0] + (e[1] * e[1] + e[2] * e[2]));
+        const int in = (double)err < threshold;
+        if (inlier) inlier[i] = (uint8_t)in;
+        cnt += in;
+    }
+    if (T_rowmajor) memcpy(T_rowmajor, T, sizeof T);
+    return cnt;
+}
+
+/* geometry::EstimateRigidTransformationRANSAC with the samples given (iterations x 8 pair indices): the first iteration with
+ * the strictly largest inlier fraction wins (GRANSAC.hpp:113-122); returns its index (-1 if none has an inlier), its motion
+ * (row-major 4x4) and its inlier flags */
+long orc_ransac_select(const float *a, const float *b, long n, const int32_t *samples, long iterations, double threshold, float *T_rowmajor,
+                       uint8_t *inlier, long *best_count)
+{
+    long best = -1, best_cnt = 0;
+    long *cnt = (long *)malloc(sizeof(long) * (size_t)(iterations + 1));
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long h = 0; h < iterations; ++h) cnt[h] = orc_ransac_hypothesis(a, b, n, samples + 8 * h, threshold, NULL, NULL);
+    for (long h = 0; h < iterations; ++h)
+        if ((double)cnt[h] / (double)n > (double)best_cnt / (double)n) { best_cnt = cnt[h]; best = h; }
+    free(cnt);
+    if (best >= 0) orc_ransac_hypothesis(a, b, n, samples + 8 * best, threshold, T_rowmajor, inlier);
+    if (best_count) *best_count = best_cnt;
+    return best;
 }

@@ -139,6 +139,13 @@ long orc_feature_matching(const float *src_feat, long ns, const float *tgt_feat,
 /* registration::RejectMatchesRanSaPC (GlobalRegistration.cpp:75-108) applied `rounds` times with one default-seeded engine, in place */
 long orc_reject_matches(const float *src, const float *tgt, int32_t *pairs, long n, int rounds, int candidate_num, float difference);
 
+/* geometry::EstimateRigidTransformation in the float build, bit for bit (Geometry.cpp:107-151); T row-major 4x4 */
+void orc_kabsch_f32(const float *a, const float *b, long n, float *T_rowmajor);
+/* one hypothesis / the whole selection of geometry::EstimateRigidTransformationRANSAC with given samples (Ransac.cpp:7-41) */
+long orc_ransac_hypothesis(const float *a, const float *b, long n, const int32_t *sample8, double threshold, float *T_rowmajor, uint8_t *inlier);
+long orc_ransac_select(const float *a, const float *b, long n, const int32_t *samples, long iterations, double threshold, float *T_rowmajor,
+                       uint8_t *inlier, long *best_count);
+
 /* caller-side depth pre-filter: tool::ConvertDepthTo32F (ImageProcessing.cpp:68-91), tool::BilateralFilter (:64-67) */
 void orc_convert_depth_32f(const void *depth, int is_u16, long n, float depth_scale, float *out);
 void orc_bilateral_filter(const float *src, int w, int h, int d, double sigma_color, double sigma_space, float *dst);

@@ -86,6 +86,11 @@ def lib():
     L.orc_feature_matching.argtypes = [c_p, c_l, c_p, c_l, c_p]
     L.orc_reject_matches.restype = c_l
     L.orc_reject_matches.argtypes = [c_p, c_p, c_p, c_l, c_i, c_i, c_f]
+    L.orc_kabsch_f32.argtypes = [c_p, c_p, c_l, c_p]
+    L.orc_ransac_hypothesis.restype = c_l
+    L.orc_ransac_hypothesis.argtypes = [c_p, c_p, c_l, c_p, c_d, c_p, c_p]
+    L.orc_ransac_select.restype = c_l
+    L.orc_ransac_select.argtypes = [c_p, c_p, c_l, c_p, c_l, c_d, c_p, c_p, c_p]
     L.orc_downsample.restype = c_l
     L.orc_downsample.argtypes = [c_p, c_p, c_p, c_l, c_f, c_p, c_p, c_p]
     L.orc_volume_transform.restype = c_p
@@ -479,3 +484,34 @@ def reject_matches(src_pts, tgt_pts, pairs, rounds=3, candidate_num=4, differenc
     p = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2).copy()
     m = lib().orc_reject_matches(_ptr(s), _ptr(t), _ptr(p), len(p), rounds, candidate_num, difference)
     return p[:m].copy()
+
+
+def kabsch_f32(a, b):
+    """geometry::EstimateRigidTransformation, float build, bit for bit -> T 4x4 float32"""
+    a = np.ascontiguousarray(a, np.float32).reshape(-1, 3)
+    b = np.ascontiguousarray(b, np.float32).reshape(-1, 3)
+    T = np.zeros(16, np.float32)
+    lib().orc_kabsch_f32(_ptr(a), _ptr(b), len(a), _ptr(T))
+    return T.reshape(4, 4)
+
+
+def ransac_hypothesis(a, b, sample8, threshold):
+    """one GRANSAC iteration with the given eight pairs -> (T 4x4 float32, inlier flags uint8)"""
+    a = np.ascontiguousarray(a, np.float32).reshape(-1, 3)
+    b = np.ascontiguousarray(b, np.float32).reshape(-1, 3)
+    s8 = np.ascontiguousarray(sample8, np.int32)
+    T = np.zeros(16, np.float32)
+    flags = np.zeros(len(a), np.uint8)
+    lib().orc_ransac_hypothesis(_ptr(a), _ptr(b), len(a), _ptr(s8), threshold, _ptr(T), _ptr(flags))
+    return T.reshape(4, 4), flags
+
+
+def ransac_select(a, b, samples, threshold):
+    """geometry::EstimateRigidTransformationRANSAC with forced samples [iterations, 8] -> (winner, T 4x4 float32, inlier ids)"""
+    a = np.ascontiguousarray(a, np.float32).reshape(-1, 3)
+    b = np.ascontiguousarray(b, np.float32).reshape(-1, 3)
+    s = np.ascontiguousarray(samples, np.int32).reshape(-1, 8)
+    T = np.zeros(16, np.float32)
+    flags = np.zeros(len(a), np.uint8)
+    w = lib().orc_ransac_select(_ptr(a), _ptr(b), len(a), _ptr(s), len(s), threshold, _ptr(T), _ptr(flags), None)
+    return int(w), T.reshape(4, 4), np.nonzero(flags)[0].astype(np.int32)

@@ -90,6 +90,10 @@ def lib(kind: str = "f32"):
         L.ref_feature_matching.argtypes = [c_p, c_l, c_p, c_l, c_p]
         L.ref_reject_matches.restype = c_l
         L.ref_reject_matches.argtypes = [c_p, c_l, c_p, c_l, c_p, c_l, c_i, c_i, c_f]
+        L.ref_ransac_hypothesis.restype = c_d
+        L.ref_ransac_hypothesis.argtypes = [c_p, c_p, c_l, c_p, c_d, c_p]
+        L.ref_ransac_registration.restype = c_d
+        L.ref_ransac_registration.argtypes = [c_p, c_l, c_p, c_l, c_p, c_p, c_i, c_d, c_p, c_p, c_p]
         L.ref_estimate_normals.restype = c_d
         L.ref_estimate_normals.argtypes = [c_p, c_l, c_f, c_i, c_p]
     L.ref_set_quiet(1)
@@ -460,3 +464,26 @@ def reject_matches(src_pts, tgt_pts, pairs, rounds=3, candidate_num=4, differenc
     p = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2).copy()
     m = lib("f32").ref_reject_matches(_ptr(s), len(s), _ptr(t), len(t), _ptr(p), len(p), rounds, candidate_num, difference)
     return p[:m].copy()
+
+
+def ransac_hypothesis(a, b, sample8, threshold):
+    """TransformationModel over the eight pairs + Evaluate over all -> (inlier fraction, flags)"""
+    a = np.ascontiguousarray(a, np.float32).reshape(-1, 3)
+    b = np.ascontiguousarray(b, np.float32).reshape(-1, 3)
+    s8 = np.ascontiguousarray(sample8, np.int32)
+    flags = np.zeros(len(a), np.uint8)
+    frac = lib("f32").ref_ransac_hypothesis(_ptr(a), _ptr(b), len(a), _ptr(s8), threshold, _ptr(flags))
+    return frac, flags
+
+
+def ransac_registration(src_pts, tgt_pts, src_feat, tgt_feat, max_iteration, threshold):
+    """registration::RansacRegistration on precomputed features (randomly seeded inside GRANSAC) -> (T, n_inliers, rmse, seconds)"""
+    s = np.ascontiguousarray(src_pts, np.float32).reshape(-1, 3)
+    t = np.ascontiguousarray(tgt_pts, np.float32).reshape(-1, 3)
+    sf = np.ascontiguousarray(src_feat, np.float32).reshape(-1, 33)
+    tf = np.ascontiguousarray(tgt_feat, np.float32).reshape(-1, 33)
+    T = np.zeros(16, np.float64)
+    n_in, rmse = C.c_long(0), C.c_double(0)
+    dt = lib("f32").ref_ransac_registration(_ptr(s), len(s), _ptr(t), len(t), _ptr(sf), _ptr(tf), max_iteration, threshold, _ptr(T),
+                                            C.byref(n_in), C.byref(rmse))
+    return T.reshape(4, 4).T.copy(), n_in.value, rmse.value, dt

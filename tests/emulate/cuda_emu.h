@@ -80,6 +80,7 @@ template <class T> T __shfl_xor_sync(unsigned, T v, int o) { return emu::exchang
 template <class T> T __shfl_up_sync(unsigned, T v, int o) { const int lane = threadIdx.x & 31; return emu::exchange(v, lane >= o ? lane - o : lane); }
 inline int atomicAdd(int *p, int v) { std::lock_guard<std::mutex> g(emu::atomic_mutex); const int old = *p; *p = old + v; return old; }
 inline int atomicMax(int *p, int v) { std::lock_guard<std::mutex> g(emu::atomic_mutex); const int old = *p; if (v > old) *p = v; return old; }
+inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) { std::lock_guard<std::mutex> g(emu::atomic_mutex); const unsigned long long old = *p; if (v > old) *p = v; return old; }
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __fsub_rn(float a, float b) { return a - b; }

@@ -145,4 +145,16 @@ void emu_match(const float *src, long ns, const float *tgt, long nt, int32_t *ne
 {
     emu::launch((int)((ns + kMatchThreads - 1) / kMatchThreads), kMatchThreads, [&] { fpfh_match_kernel(src, (int)ns, tgt, (int)nt, nearest); });
 }
+// opb_ransac_rigid_transformation's two launches; returns the winner (-1: no hypothesis with an inlier)
+int emu_ransac(const float *a, const float *b, long n, int iterations, double threshold, unsigned long long seed, const int32_t *forced,
+               float *motion12, unsigned char *inlier, int32_t *sample8)
+{
+    std::vector<int> scores(iterations + 1);
+    unsigned long long best = 0;
+    emu::launch((iterations + 127) / 128, 128, [&] { ransac_score_kernel(a, b, (int)n, iterations, threshold, seed, forced, scores.data(), &best); });
+    if ((best >> 32) == 0) return -1;
+    const int winner = (int)(0xFFFFFFFFu - (unsigned int)(best & 0xFFFFFFFFu));
+    emu::launch(grid_for(n, 4), kQueryThreads, [&] { ransac_winner_kernel(a, b, (int)n, winner, threshold, seed, forced, inlier, motion12, sample8); });
+    return winner;
+}
 }

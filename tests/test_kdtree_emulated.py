@@ -44,6 +44,7 @@ def emu(tmp_path_factory):
     L.emu_fpfh.argtypes = [p, p, C.c_int, C.c_float, p]
     L.emu_match.argtypes = [p, C.c_long, p, C.c_long, p]
     L.emu_match_tree.argtypes = [p, C.c_long, p, C.c_long, p]
+    L.emu_ransac.argtypes = [p, p, C.c_long, C.c_int, C.c_double, C.c_uint64, p, p, p, p]
     return L
 
 
@@ -132,3 +133,37 @@ def test_emulated_feature_matching_matches_the_oracle(emu):
     ft[5] = np.nan
     emu.emu_match_tree(_ptr(fs), len(fs), _ptr(ft), len(ft), _ptr(nearest))
     assert (nearest == -2).all()                              # non-finite targets are detected (the library then scans exhaustively)
+
+
+def ransac_case(n=600, outliers=0.5, seed=4):
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(-2, 2, (n, 3)).astype(np.float32)
+    R = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+    R *= np.sign(np.linalg.det(R))
+    b = (a @ R.T + 0.3 + rng.normal(0, 0.02, (n, 3))).astype(np.float32)
+    bad = rng.random(n) < outliers
+    b[bad] = rng.uniform(-2, 2, (int(bad.sum()), 3)).astype(np.float32)
+    T = np.eye(4)
+    T[:3, :3], T[:3, 3] = R, 0.3
+    return a, b, T, rng
+
+
+def test_emulated_ransac_matches_the_oracle(emu):
+    """ransac_score_kernel / ransac_winner_kernel with forced samples: winner, motion and inliers are the oracle's (which is
+    pinned hypothesis by hypothesis to the compiled reference); with drawn samples the eight indices are distinct and in range"""
+    a, b, T_true, rng = ransac_case()
+    samples = np.stack([rng.choice(len(a), 8, replace=False) for _ in range(300)]).astype(np.int32)
+    samples[17] = samples[3]                                  # a duplicate hypothesis: the earlier one must win a tie
+    for thr in (0.1, 0.03):
+        motion, flags, s8 = np.zeros(12, np.float32), np.zeros(len(a), np.uint8), np.zeros(8, np.int32)
+        w = emu.emu_ransac(_ptr(a), _ptr(b), len(a), len(samples), thr, 0, _ptr(samples), _ptr(motion), _ptr(flags), _ptr(s8))
+        ow, oT, oids = oracleapi.ransac_select(a, b, samples, thr)
+        assert w == ow and np.array_equal(s8, samples[w]) and np.array_equal(np.nonzero(flags)[0], oids)
+        assert np.array_equal(motion[:9].reshape(3, 3).view(np.uint32), oT[:3, :3].view(np.uint32))
+        assert np.array_equal(motion[9:].view(np.uint32), oT[:3, 3].view(np.uint32))
+    motion, flags, s8 = np.zeros(12, np.float32), np.zeros(len(a), np.uint8), np.zeros(8, np.int32)
+    w = emu.emu_ransac(_ptr(a), _ptr(b), len(a), 400, 0.1, 12345, None, _ptr(motion), _ptr(flags), _ptr(s8))
+    assert 0 <= w < 400 and len(set(s8.tolist())) == 8 and s8.min() >= 0 and s8.max() < len(a)
+    oT, oflags = oracleapi.ransac_hypothesis(a, b, s8, 0.1)
+    assert np.array_equal(flags, oflags) and np.array_equal(motion[:9].reshape(3, 3).view(np.uint32), oT[:3, :3].view(np.uint32))
+    assert flags.sum() > 0.4 * len(a) and np.abs(motion[:9].reshape(3, 3) - T_true[:3, :3]).max() < 0.05   # it found the motion

@@ -166,3 +166,44 @@ def test_feature_matching_and_rejection_match_the_oracle():
     best = ((fs2[probe[:, 0]].astype(np.float64) - ft2[probe[:, 1]]) ** 2).sum(-1)
     assert len(m3) == len(fs) - 1 and (best <= d.min(1) * (1 + 1e-6)).all()
     assert len(reg.FeatureMatching3D(fs[:0], ft)) == 0 and len(reg.FeatureMatching3D(fs, ft[:0])) == 0
+
+
+def test_ransac_with_forced_samples_is_the_oracles_and_registration_recovers_the_motion():
+    """EstimateRigidTransformationRANSAC on the device: with the hypotheses forced, the winner, its motion and its inliers are the
+    oracle's bit for bit (the oracle is pinned hypothesis by hypothesis to the compiled reference); with its own sampler the whole
+    RansacRegistration chain recovers the true camera motion between two views."""
+    from test_kdtree_emulated import ransac_case
+    from test_oracle_kdtree import _two_frames_features
+    from onepiece_b200 import capi, scenes
+    reg = _reg()
+    a, b, T_true, rng = ransac_case(3000)
+    samples = np.stack([rng.choice(len(a), 8, replace=False) for _ in range(4000)]).astype(np.int32)
+    samples[170] = samples[30]
+    for thr in (0.1, 0.03):
+        T, ids, w, s8 = reg.EstimateRigidTransformationRANSAC(a, b, threshold=thr, samples=samples)
+        ow, oT, oids = oracleapi.ransac_select(a, b, samples, thr)
+        assert w == ow and np.array_equal(s8, samples[w]) and np.array_equal(ids, oids)
+        assert np.array_equal(T.view(np.uint32), oT.view(np.uint32))
+    t0 = time.perf_counter()
+    T, ids, w, s8 = reg.EstimateRigidTransformationRANSAC(a, b, 40000, 0.1, seed=7)
+    dt = time.perf_counter() - t0
+    print(f"EstimateRigidTransformationRANSAC: 40,000 hypotheses x {len(a)} pairs in {dt * 1e3:.1f} ms (host buffers)")
+    oT, oflags = oracleapi.ransac_hypothesis(a, b, s8, 0.1)
+    assert len(set(s8.tolist())) == 8 and np.array_equal(T.view(np.uint32), oT.view(np.uint32)) and np.array_equal(ids, np.nonzero(oflags)[0])
+    assert len(ids) > 0.45 * len(a) and np.abs(T - T_true).max() < 0.05
+    T2, ids2, w2, _ = reg.EstimateRigidTransformationRANSAC(a, b, 40000, 0.1, seed=7)
+    assert w2 == w and np.array_equal(T2, T)                      # same seed, same answer
+    # the reference's corner cases
+    T0, ids0, _, _ = reg.EstimateRigidTransformationRANSAC(a[:5], b[:5], 10, 0.1)
+    assert not T0.any() and len(ids0) == 0                        # fewer than eight pairs: the zero matrix
+    with pytest.raises(capi.OpbError):
+        reg.EstimateRigidTransformationRANSAC(a[:8], b[:8], 10, 0.1)
+    # the whole chain on two views of the room (DenseSlam's parameters)
+    (ps, fs), (pt, ft) = _two_frames_features()
+    para = reg.RANSACParameter(max_iteration=40000, threshold=0.1)
+    t0 = time.perf_counter()
+    res = reg.RansacRegistration(reg.PointCloud(ps), reg.PointCloud(pt), fs, ft, para, seed=1)
+    dt = time.perf_counter() - t0
+    T_true = np.linalg.inv(scenes.room_pose(12)) @ scenes.room_pose(0)     # source = frame 0, target = frame 12
+    print(f"RansacRegistration: {len(ps)} / {len(pt)} points, {len(res.correspondence_set_index)} inliers, rmse {res.rmse:.4f}, {dt * 1e3:.1f} ms")
+    assert np.linalg.norm(res.T[:3, 3] - T_true[:3, 3]) < 0.1 and np.abs(res.T[:3, :3] - T_true[:3, :3]).max() < 0.1
