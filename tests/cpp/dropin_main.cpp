@@ -160,8 +160,8 @@ int main(int argc, char **argv)
         WriteAll(dir + "/fpfh.bin", ff);
         WriteAll(dir + "/fpfh_points.bin", fp);
         // the rest of registration::RansacRegistration on precomputed features, statement for statement
-        // (GlobalRegistration.cpp:225-266): matching and the three rejection passes through the drop-ins, the estimator is the
-        // reference's own GRANSAC (randomly seeded: its T is checked against the true motion, not bit for bit)
+        // (GlobalRegistration.cpp:225-266): matching, the three rejection passes and the RANSAC estimator all through the drop-ins
+        // (the estimator draws fresh samples per call like the reference's: its T is checked against the true motion)
         geometry::PointCloud s_full;
         s_full.points = s_pcd.points;
         auto s_down = s_full.DownSample(0.05);
@@ -187,6 +187,7 @@ int main(int argc, char **argv)
             for (int c = 0; c < 4; ++c) rr.push_back(T(r, c));
         rr.push_back((double)inliers.size());
         rr.push_back((double)correspondence_set.size());
+        for (size_t i = 0; i < inlier_ids.size(); ++i) rr.push_back((double)inlier_ids[i]);
         std::vector<float> sp;
         for (size_t i = 0; i < s_down->points.size(); ++i)
             for (int k = 0; k < 3; ++k) sp.push_back(s_down->points[i](k));

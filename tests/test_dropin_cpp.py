@@ -79,7 +79,8 @@ def test_reference_caller_code_runs_on_the_gpu(tmp_path):
     of = oracleapi.fpfh(down, oracleapi.estimate_normals(down, 0.1, 30), 100, 0.25)
     assert len(ff) == len(of) > 100 and ((ff.view(np.uint32) == of.view(np.uint32)) | (np.isnan(ff) & np.isnan(of))).all()
     # the rest of RansacRegistration: matching + three rejection passes through the drop-ins are the oracle's index for index;
-    # the estimator is the reference's own randomly seeded GRANSAC, so its pose is only checked against the true camera motion
+    # the estimator (drop-in too) draws fresh samples on every call like the reference's GRANSAC, so its pose is checked against
+    # the true camera motion, and its inlier list against the oracle's evaluation of the pose it returned
     sdown = oracleapi.downsample(src, None, None, 0.05)[0]
     assert_bit_equal(np.fromfile(tmp_path / "fpfh_source_points.bin", np.float32).reshape(-1, 3), sdown, "source DownSample")
     sf = oracleapi.fpfh(sdown, oracleapi.estimate_normals(sdown, 0.1, 30), 100, 0.25)
@@ -91,6 +92,10 @@ def test_reference_caller_code_runs_on_the_gpu(tmp_path):
     T_est, n_inl, n_corr = rr[:16].reshape(4, 4), int(rr[16]), int(rr[17])
     T_true = np.linalg.inv(scenes.room_pose(0)) @ scenes.room_pose(3)
     assert n_corr == len(m3) and n_inl > 0.3 * n_corr
+    ids = rr[18:18 + n_inl].astype(np.int64)
+    a3, b3 = sdown[m3[:, 0]], down[m3[:, 1]]
+    err = np.linalg.norm(a3 @ T_est[:3, :3].T + T_est[:3, 3] - b3, axis=1)
+    assert (np.diff(ids) > 0).all() and (err[ids] < 0.1 + 1e-5).all() and (np.delete(err, ids) > 0.1 - 1e-5).all()
     assert np.linalg.norm(T_est[:3, 3] - T_true[:3, 3]) < 0.1 and np.abs(T_est[:3, :3] - T_true[:3, :3]).max() < 0.1
     # Odometry::DenseTracking through the drop-in: two chained calls on the same RGBDFrames, then the cv::Mat overload
     odo = np.fromfile(tmp_path / "odometry.bin", np.float64)
