@@ -1,4 +1,5 @@
-"""One full-frame EstimateNormals and one DenseSlam-style FPFH extraction (for ncu launch lists and wall-clock timing)."""
+"""One full-frame EstimateNormals, one DenseSlam-style FPFH extraction and one RansacRegistration against a second view (for ncu
+launch lists and wall-clock timing)."""
 import os
 import sys
 import time
@@ -23,5 +24,18 @@ for _ in range(reps):
     t3 = time.perf_counter()
     f = reg.ComputeFPFHFeature(down, 100, 0.25)
     t4 = time.perf_counter()
+# the rest of the submap registration chain (GlobalRegistration.cpp:219-267) against a second view
+d1, _, _ = scenes.room(cam, 12)
+pc1 = reg.PointCloud(scenes.backproject(d1, cam)).DownSample(0.05)
+pc1.EstimateNormals(0.1, 30)
+f1 = reg.ComputeFPFHFeature(pc1, 100, 0.25)
+for _ in range(reps):
+    t5 = time.perf_counter()
+    m = reg.FeatureMatching3D(f, f1)
+    t6 = time.perf_counter()
+    res = reg.RansacRegistration(down, pc1, f, f1, reg.RANSACParameter(max_iteration=40000, threshold=0.1), seed=1)
+    t7 = time.perf_counter()
+print(f"FeatureMatching3D {len(f)} x {len(f1)} {1e3 * (t6 - t5):.2f} ms | RansacRegistration (matching + 3 rejections + 40,000 hypotheses) "
+      f"{1e3 * (t7 - t6):.2f} ms, {len(res.correspondence_set_index)} inliers")
 print(f"EstimateNormals {len(cloud)} pts {1e3 * (t1 - t0):.2f} ms | DownSample -> {len(down.points)} pts {1e3 * (t2 - t1):.2f} ms | "
       f"EstimateNormals {1e3 * (t3 - t2):.2f} ms | ComputeFPFHFeature {1e3 * (t4 - t3):.2f} ms | finite rows {int(np.isfinite(f).all(1).sum())}")
