@@ -2468,3 +2468,138 @@ long orc_ransac_select(const float *a, const float *b, long n, const int32_t *sa
     if (best_count) *best_count = best_cnt;
     return best;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * optimization::SimpleBA = Optimizer::FastBA (src/Optimization/SimpleBA.cpp:18-157): pose-graph refinement over frame pairs
+ * linked by 3-D point pairs.  Per pair and point: r = (R1 p1 + t1) - (R2 p2 + t2), J_s = [I | -skew(R1 p1 + t1)],
+ * J_t = [-I | skew(R2 p2 + t2)]; the 6x6 blocks J^T J and -J^T r are summed per frame pair, assembled into the sparse
+ * normal equations over poses 1 .. n-1 (pose 0 is fixed), solved (Eigen SimplicialLDLT there, a dense LDL^T here) and every
+ * pose is updated as Se3ToSE3(delta_i) * pose_i.  Sums are kept in float like the reference's; the solve is in double, so
+ * the restatement is pinned by tolerance (blocks 1e-5 relative, poses 1e-5), not bit for bit.
+ * out of orc_ba_blocks: JTJ_ss, JTJ_tt, JTJ_st, JTJ_ts (row-major 6x6), JTr_s, JTr_t: 156 floats.  Poses row-major here.
+ * ------------------------------------------------------------------------------------------------------------------ */
+static void ba_blocks_rm(const float *Ps, const float *Pt, const float *a, const float *b, long n, float *out)
+{
+    for (int i = 0; i < 156; ++i) out[i] = 0.0f;
+    float *ss = out, *tt = out + 36, *st = out + 72, *ts = out + 108, *rs = out + 144, *rt = out + 150;
+    for (long k = 0; k < n; ++k)
+    {
+        float q1[3], q2[3], r[3];
+        for (int i = 0; i < 3; ++i)
+        {
+            q1[i] = (Ps[4 * i] * a[3 * k] + (Ps[4 * i + 1] * a[3 * k + 1] + Ps[4 * i + 2] * a[3 * k + 2])) + Ps[4 * i + 3];
+            q2[i] = (Pt[4 * i] * b[3 * k] + (Pt[4 * i + 1] * b[3 * k + 1] + Pt[4 * i + 2] * b[3 * k + 2])) + Pt[4 * i + 3];
+        }
+        for (int i = 0; i < 3; ++i) r[i] = q1[i] - q2[i];
+        float Js[18] = {1, 0, 0, 0, q1[2], -q1[1], 0, 1, 0, -q1[2], 0, q1[0], 0, 0, 1, q1[1], -q1[0], 0};   /* [I | -skew(q1)] */
+        float Jt[18] = {-1, 0, 0, 0, -q2[2], q2[1], 0, -1, 0, q2[2], 0, -q2[0], 0, 0, -1, -q2[1], q2[0], 0}; /* [-I | skew(q2)] */
+        for (int i = 0; i < 6; ++i)
+        {
+            for (int j = 0; j < 6; ++j)
+            {
+                float s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+                for (int m = 0; m < 3; ++m)
+                {
+                    s1 += Js[6 * m + i] * Js[6 * m + j]; s2 += Jt[6 * m + i] * Jt[6 * m + j];
+                    s3 += Js[6 * m + i] * Jt[6 * m + j]; s4 += Jt[6 * m + i] * Js[6 * m + j];
+                }
+                ss[6 * i + j] += s1; tt[6 * i + j] += s2; st[6 * i + j] += s3; ts[6 * i + j] += s4;
+            }
+            float g1 = 0, g2 = 0;
+            for (int m = 0; m < 3; ++m) { g1 += Js[6 * m + i] * r[m]; g2 += Jt[6 * m + i] * r[m]; }
+            rs[i] -= g1; rt[i] -= g2;
+        }
+    }
+}
+void orc_ba_blocks(const float *pose_s_cm, const float *pose_t_cm, const float *a, const float *b, long n, float *out)
+{
+    float Ps[16], Pt[16];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) { Ps[4 * r + c] = pose_s_cm[4 * c + r]; Pt[4 * r + c] = pose_t_cm[4 * c + r]; }
+    ba_blocks_rm(Ps, Pt, a, b, n, out);
+}
+/* dense LDL^T solve of a symmetric positive definite system, in place (A n x n row-major, b -> x); 0 on success */
+static int ldlt_solve(double *A, double *b, int n)
+{
+    for (int j = 0; j < n; ++j)
+    {
+        double d = A[j * n + j];
+        for (int k = 0; k < j; ++k) d -= A[j * n + k] * A[j * n + k] * A[k * n + k];
+        if (!(fabs(d) > 0)) return -1;
+        A[j * n + j] = d;
+        for (int i = j + 1; i < n; ++i)
+        {
+            double v = A[i * n + j];
+            for (int k = 0; k < j; ++k) v -= A[i * n + k] * A[j * n + k] * A[k * n + k];
+            A[i * n + j] = v / d;
+        }
+    }
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < i; ++k) b[i] -= A[i * n + k] * b[k];
+    for (int i = 0; i < n; ++i) b[i] /= A[i * n + i];
+    for (int i = n - 1; i >= 0; --i)
+        for (int k = i + 1; k < n; ++k) b[i] -= A[k * n + i] * b[k];
+    return 0;
+}
+int orc_simple_ba(int n_poses, float *poses_cm, int n_corr, const int32_t *src_id, const int32_t *tgt_id, const int64_t *offset,
+                  const float *a, const float *b, int max_iteration)
+{
+    if (n_poses < 3) return 0;              /* "Too few optimization variables" (:84-88) */
+    if (n_corr < n_poses - 1) return -1;    /* "There are unconnected components" (:89-93) */
+    const int nv = 6 * (n_poses - 1);
+    double *A = (double *)malloc(sizeof(double) * (size_t)nv * nv), *g = (double *)malloc(sizeof(double) * (size_t)nv);
+    float *P = (float *)malloc(sizeof(float) * 16 * (size_t)n_poses); /* row-major */
+    for (int i = 0; i < n_poses; ++i)
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) P[16 * i + 4 * r + c] = poses_cm[16 * i + 4 * c + r];
+    int rc = 0;
+    for (int iter = 0; iter < max_iteration && !rc; ++iter)
+    {
+        float *gf = (float *)calloc((size_t)nv, sizeof(float)); /* JTr is a float vector in the reference */
+        memset(A, 0, sizeof(double) * (size_t)nv * nv);
+        for (int k = 0; k < n_corr; ++k)
+        {
+            float blk[156];
+            const int s = src_id[k], t = tgt_id[k];
+            ba_blocks_rm(P + 16 * s, P + 16 * t, a + 3 * offset[k], b + 3 * offset[k], (long)(offset[k + 1] - offset[k]), blk);
+            for (int i = 0; i < 6; ++i)
+            {
+                for (int j = 0; j < 6; ++j)
+                {
+                    if (s != 0)
+                    {
+                        A[(size_t)((s - 1) * 6 + i) * nv + (s - 1) * 6 + j] += blk[6 * i + j];
+                        A[(size_t)((s - 1) * 6 + i) * nv + (t - 1) * 6 + j] += blk[72 + 6 * i + j];
+                        A[(size_t)((t - 1) * 6 + i) * nv + (s - 1) * 6 + j] += blk[108 + 6 * i + j];
+                    }
+                    A[(size_t)((t - 1) * 6 + i) * nv + (t - 1) * 6 + j] += blk[36 + 6 * i + j];
+                }
+                if (s != 0) gf[(s - 1) * 6 + i] += blk[144 + i];
+                gf[(t - 1) * 6 + i] += blk[150 + i];
+            }
+        }
+        for (int i = 0; i < nv; ++i) g[i] = gf[i];
+        free(gf);
+        if (ldlt_solve(A, g, nv)) { rc = -2; break; }
+        for (int i = 1; i < n_poses; ++i)
+        {
+            double x[6], D[16];
+            for (int e = 0; e < 6; ++e) x[e] = (float)g[(i - 1) * 6 + e];
+            se3_exp_rm(x, D);
+            float N[16];
+            for (int r = 0; r < 4; ++r)
+                for (int c = 0; c < 4; ++c)
+                {
+                    double v = 0;
+                    for (int m = 0; m < 4; ++m) v += D[4 * r + m] * P[16 * i + 4 * m + c];
+                    N[4 * r + c] = (float)v;
+                }
+            memcpy(P + 16 * i, N, sizeof N);
+        }
+    }
+    for (int i = 0; i < n_poses; ++i)
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) poses_cm[16 * i + 4 * c + r] = P[16 * i + 4 * r + c];
+    free(A); free(g); free(P);
+    return rc;
+}

@@ -146,6 +146,12 @@ long orc_ransac_hypothesis(const float *a, const float *b, long n, const int32_t
 long orc_ransac_select(const float *a, const float *b, long n, const int32_t *samples, long iterations, double threshold, float *T_rowmajor,
                        uint8_t *inlier, long *best_count);
 
+/* optimization::SimpleBA = Optimizer::FastBA (SimpleBA.cpp:18-157): per-pair blocks (156 floats) and the whole refinement; poses
+ * column-major 4x4 in place; pinned by tolerance (the solve is dense double here, SimplicialLDLT<float> there) */
+void orc_ba_blocks(const float *pose_s_cm, const float *pose_t_cm, const float *a, const float *b, long n, float *out156);
+int orc_simple_ba(int n_poses, float *poses_cm, int n_corr, const int32_t *src_id, const int32_t *tgt_id, const int64_t *offset,
+                  const float *a, const float *b, int max_iteration);
+
 /* caller-side depth pre-filter: tool::ConvertDepthTo32F (ImageProcessing.cpp:68-91), tool::BilateralFilter (:64-67) */
 void orc_convert_depth_32f(const void *depth, int is_u16, long n, float depth_scale, float *out);
 void orc_bilateral_filter(const float *src, int w, int h, int d, double sigma_color, double sigma_space, float *dst);

@@ -31,6 +31,7 @@
 #include "Registration/3DFeature.h"
 #include "Registration/GlobalRegistration.h"
 #include "Geometry/Ransac.h"
+#include "Optimization/SimpleBA.h"
 #endif
 
 using namespace one_piece;
@@ -638,6 +639,51 @@ double ref_ransac_registration(const float *src, long ns, const float *tgt, long
     *n_inliers = (long)r->correspondence_set.size();
     *rmse = r->rmse;
     return dt;
+}
+// optimization::SimpleBA (= Optimizer::FastBA, src/Optimization/SimpleBA.cpp:80-157): correspondence k links frames
+// src_id[k] -> tgt_id[k] through the point pairs [offset[k], offset[k+1]) of a / b; poses column-major 4x4 floats, in place
+double ref_simple_ba(int n_poses, float *poses_cm, int n_corr, const int32_t *src_id, const int32_t *tgt_id, const int64_t *offset,
+                     const float *a, const float *b, int max_iteration)
+{
+    geometry::SE3List poses(n_poses);
+    for (int i = 0; i < n_poses; ++i)
+        for (int c = 0; c < 4; ++c)
+            for (int r = 0; r < 4; ++r) poses[i](r, c) = poses_cm[16 * i + 4 * c + r];
+    std::vector<optimization::Correspondence> cs;
+    for (int k = 0; k < n_corr; ++k)
+    {
+        geometry::PointCorrespondenceSet set;
+        for (int64_t j = offset[k]; j < offset[k + 1]; ++j)
+            set.push_back(std::make_pair(geometry::Point3(a[3 * j], a[3 * j + 1], a[3 * j + 2]), geometry::Point3(b[3 * j], b[3 * j + 1], b[3 * j + 2])));
+        cs.push_back(optimization::Correspondence(src_id[k], tgt_id[k], set));
+    }
+    double t0 = Now();
+    optimization::SimpleBA(cs, poses, max_iteration);
+    double dt = Now() - t0;
+    for (int i = 0; i < n_poses; ++i)
+        for (int c = 0; c < 4; ++c)
+            for (int r = 0; r < 4; ++r) poses_cm[16 * i + 4 * c + r] = (float)poses[i](r, c);
+    return dt;
+}
+// optimization::ComputeJTJAndJTr (SimpleBA.cpp:18-78) for one correspondence: out = JTJ_ss, JTJ_tt, JTJ_st, JTJ_ts (row-major 6x6
+// each), JTr_s, JTr_t (6 each) = 156 floats
+void ref_ba_blocks(const float *pose_s_cm, const float *pose_t_cm, const float *a, const float *b, long n, float *out)
+{
+    geometry::SE3List poses(2);
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 4; ++r) { poses[0](r, c) = pose_s_cm[4 * c + r]; poses[1](r, c) = pose_t_cm[4 * c + r]; }
+    geometry::PointCorrespondenceSet set;
+    for (long j = 0; j < n; ++j)
+        set.push_back(std::make_pair(geometry::Point3(a[3 * j], a[3 * j + 1], a[3 * j + 2]), geometry::Point3(b[3 * j], b[3 * j + 1], b[3 * j + 2])));
+    optimization::Correspondence corr(0, 1, set);
+    geometry::Matrix6 ss, tt, st, ts;
+    geometry::Se3 rs, rt;
+    std::tie(ss, tt, st, ts, rs, rt) = optimization::ComputeJTJAndJTr(corr, poses);
+    const geometry::Matrix6 *m[4] = {&ss, &tt, &st, &ts};
+    for (int k = 0; k < 4; ++k)
+        for (int r = 0; r < 6; ++r)
+            for (int c = 0; c < 6; ++c) out[36 * k + 6 * r + c] = (float)(*m[k])(r, c);
+    for (int r = 0; r < 6; ++r) { out[144 + r] = (float)rs(r); out[150 + r] = (float)rt(r); }
 }
 #endif
 } // extern "C"
