@@ -343,6 +343,20 @@ int opb_reject_matches(const float *src_xyz, size_t ns, const float *tgt_xyz, si
 int opb_ransac_rigid_transformation(opb_kdtree *t, const float *src_xyz, const float *tgt_xyz, size_t n, int max_iteration, double threshold,
                                     uint64_t seed, const int32_t *forced_samples, float T_colmajor[16], int32_t *inlier_ids, size_t *n_inliers,
                                     int32_t *best_iteration, int32_t best_sample[8]);
+/* optimization::SimpleBA(correspondences, poses, max_iteration = 5) = Optimizer::FastBA (src/Optimization/SimpleBA.cpp:80-157,
+ * Optimizer.h:22-25), the pose-graph refinement over submaps: frame pair k links poses src_id[k] -> tgt_id[k] (tgt_id >= 1: the
+ * reference indexes block tgt_id - 1) through the point pairs [offset[k], offset[k+1]) of a_xyz / b_xyz (points in the two
+ * frames' own coordinates); poses are camera-to-world 4x4 column-major floats, refined in place, pose 0 fixed.  The per-pair
+ * normal-equation blocks are reduced on the device (28 sums per pair, float products, double accumulation), the 6 (n_poses - 1)
+ * unknowns are solved on the host (dense LDL^T in double; the reference: float sums, SimplicialLDLT<float>), so poses agree
+ * with the reference to ~1e-4, not bit for bit.  n_poses < 3: nothing to do (OPB_OK); n_corr < n_poses - 1: OPB_ERR_INVALID
+ * (the reference prints "unconnected components" and returns).  NOTE: not yet exercised on a GPU (see csrc/opb_ba.cu). */
+int opb_simple_ba(int device, int n_poses, float *poses_colmajor, int n_corr, const int32_t *src_id, const int32_t *tgt_id,
+                  const int64_t *offset, const float *a_xyz, const float *b_xyz, int max_iteration);
+/* test hook, host only: one iteration's assembly + solve + pose update from per-pair sums (28 doubles each: N, sum q1, sum q2,
+ * upper triangles of sum q1 q1^T and sum q2 q2^T, sum q1 q2^T row-major; q = pose applied to the point) */
+int opb_simple_ba_from_sums(int n_poses, float *poses_colmajor, int n_corr, const int32_t *src_id, const int32_t *tgt_id,
+                            const double *sums28);
 /* test hook: the built tree (vind: n ints; nodes in allocation order, root = 0: left, right, child1, child2 (-1 = leaf), divfeat;
  * divlow, divhigh); all output pointers NULL -> only n_nodes */
 int opb_kdtree_dump(opb_kdtree *t, int32_t *vind, int32_t *node_ints5, float *node_floats2, float root_box[6], size_t *n_nodes);

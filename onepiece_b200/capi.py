@@ -150,6 +150,8 @@ SIGNATURES = {
     "opb_kdtree_dump": (C.c_int, [_p, _p, _p, _p, _p, _p]),
     "opb_kdtree_feature_matching": (C.c_int, [_p, _p, _sz, _p, _sz, _p, _p]),
     "opb_ransac_rigid_transformation": (C.c_int, [_p, _p, _p, _sz, C.c_int, C.c_double, C.c_uint64, _p, _p, _p, _p, _p, _p]),
+    "opb_simple_ba": (C.c_int, [C.c_int, C.c_int, _p, C.c_int, _p, _p, _p, _p, _p, C.c_int]),
+    "opb_simple_ba_from_sums": (C.c_int, [C.c_int, _p, C.c_int, _p, _p, _p]),
     "opb_reject_matches": (C.c_int, [_p, _sz, _p, _sz, _p, _p, _p, C.c_int, C.c_float]),
     "opb_icp_last_launch_count": (C.c_int, [_p, C.POINTER(C.c_int)]),
     "opb_icp_last_search_trace": (C.c_int, [_p, _p, C.c_int]),

@@ -58,19 +58,20 @@ void launch(int grid, int block, F f)
     pthread_barrier_destroy(&block_bar);
     for (int w = 0; w < warps; ++w) pthread_barrier_destroy(&warp_bar[w]);
 }
+inline uint64_t warp_slot64[32][32];
 template <class T>
 T exchange(T v, int src_lane)
 {
-    static_assert(sizeof(T) == 4, "32-bit shuffles only");
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "32- and 64-bit shuffles only");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t bits;
-    memcpy(&bits, &v, 4);
-    warp_slot[warp][lane] = bits;
+    uint64_t bits = 0;
+    memcpy(&bits, &v, sizeof(T));
+    warp_slot64[warp][lane] = bits;
     pthread_barrier_wait(&warp_bar[warp]);
-    uint32_t r = src_lane >= 0 && src_lane < 32 ? warp_slot[warp][src_lane] : bits;
+    uint64_t r = src_lane >= 0 && src_lane < 32 ? warp_slot64[warp][src_lane] : bits;
     pthread_barrier_wait(&warp_bar[warp]);
     T out;
-    memcpy(&out, &r, 4);
+    memcpy(&out, &r, sizeof(T));
     return out;
 }
 } // namespace emu
