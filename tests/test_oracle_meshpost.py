@@ -146,6 +146,10 @@ def test_estimate_normals_matches_the_compiled_reference(ref_available):
     assert np.abs(np.linalg.norm(a, axis=1) - 1).max() < 1e-5
     a, (b, _) = oracleapi.estimate_normals(pts), refapi.estimate_normals(pts)
     assert_bit_equal(a, b, "normals of the raw cloud (equal distances ordered by the tree traversal)")
+    # and the full 640x480 frame (307,200 points), the size the device path is checked at against this oracle
+    full = scenes.backproject(scenes.room(scenes.Camera(), 0)[0], scenes.Camera())
+    a, (b, _) = oracleapi.estimate_normals(full), refapi.estimate_normals(full)
+    assert_bit_equal(a, b, "normals of the full raw frame")
     # fewer than three points in range: FitPlane's warning path returns the zero vector
     far = np.array([[0, 0, 0], [10, 0, 0], [0, 10, 0], [10, 10, 0]], np.float32)
     assert not oracleapi.estimate_normals(far, 0.1, 30).any()
