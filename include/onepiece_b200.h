@@ -379,9 +379,12 @@ int opb_ipc_open(int device, const unsigned char ipc_handle[OPB_IPC_HANDLE_BYTES
 int opb_ipc_close(int device, void *d_ptr);
 int opb_icp_comm_attach(opb_icp *c, int rank, int world, void *const *buffers);
 int opb_icp_comm_detach(opb_icp *c);
-/* nearest-neighbour index per source point from the last search of the previous call (-1: none within the
- * threshold), for parity tests against KDTree::KnnSearch */
+/* nearest-neighbour index per source point from the last search of the previous call -- the search of the LAST ITERATION, under
+ * the pose before its update; -1: none that could pass the closing inlier test -- for parity tests against KDTree::KnnSearch */
 int opb_icp_last_nn(opb_icp *c, int32_t *nn, size_t n);
+/* the pose those neighbours were searched under: start_T BEFORE the last iteration's update (column-major).  The reference's
+ * closing CountInliers re-tests exactly these neighbours with the final pose and runs no search of its own (ICP.cpp:90,206) */
+int opb_icp_last_prev_pose(opb_icp *c, float T_colmajor[16]);
 /* how many exact grid searches the last call performed, of n_source * (max_iteration + 1) queries: the others kept the
  * certified nearest neighbour of an earlier pass (see csrc/opb_icp.cu, icp_certify_kernel) */
 int opb_icp_last_search_count(opb_icp *c, uint64_t *full_searches);

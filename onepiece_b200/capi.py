@@ -156,6 +156,7 @@ SIGNATURES = {
     "opb_icp_last_launch_count": (C.c_int, [_p, C.POINTER(C.c_int)]),
     "opb_icp_last_search_trace": (C.c_int, [_p, _p, C.c_int]),
     "opb_icp_last_nn": (C.c_int, [_p, _p, _sz]),
+    "opb_icp_last_prev_pose": (C.c_int, [_p, _p]),
     "opb_icp_set_profiling": (C.c_int, [_p, C.c_int]),
     "opb_icp_last_timing": (C.c_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "opb_odometry_desc_default": (None, [C.POINTER(OdometryDesc)]),

@@ -46,6 +46,7 @@ struct IcpGrid
 struct IcpState // device-resident solver state
 {
     float T[16];        // current source->target transform, column-major float (start_T)
+    float T_prev[16];   // the pose the last solving pass searched under (the closing CountInliers re-tests ITS neighbours)
     double packet[kPacket];
     int iteration;
     IcpGrid grid;
@@ -405,6 +406,9 @@ struct IcpArgs
     float search_radius;
     double sq_threshold;
     int final_pass;         // 1: only CountInliers (rmse + pairs), no solve
+    int keep_far;           // 1 in the last solving pass: nn keeps the true nearest neighbour even beyond the inlier radius (or -2 =
+                            // "none within the search radius, true nearest unknown"), because the closing CountInliers re-tests
+                            // exactly these neighbours under the NEXT pose (ICP.cpp:90,206)
     int *pairs;             // final pass: inlier flags are turned into pairs by the compaction kernel
     unsigned char *inlier;  // ns flags
     IcpComm comm;           // world <= 1: single GPU
@@ -635,8 +639,9 @@ __global__ void __launch_bounds__(kIcpThreads) icp_certify_kernel(IcpArgs a)
                 if (j >= 0)
                 {
                     const float d = dist2_nanoflann(px, py, pz, __ldg(&a.tgt[3 * j]), __ldg(&a.tgt[3 * j + 1]), __ldg(&a.tgt[3 * j + 2]));
-                    if (!(d > r2cap)) nn = j;
+                    if (!(d > r2cap) || a.keep_far) nn = j;
                 }
+                else if (a.keep_far) nn = -2;
                 a.nn[i] = nn;
             }
             else if (moved < a.budget2[i])
@@ -645,7 +650,7 @@ __global__ void __launch_bounds__(kIcpThreads) icp_certify_kernel(IcpArgs a)
                 const float da = dist2_nanoflann(px, py, pz, __ldg(&a.tgt[3 * jj.x]), __ldg(&a.tgt[3 * jj.x + 1]), __ldg(&a.tgt[3 * jj.x + 2]));
                 const float db = dist2_nanoflann(px, py, pz, __ldg(&a.tgt[3 * jj.y]), __ldg(&a.tgt[3 * jj.y + 1]), __ldg(&a.tgt[3 * jj.y + 2]));
                 const bool first = da < db || (da == db && jj.x < jj.y);
-                if (!((first ? da : db) > r2cap)) nn = first ? jj.x : jj.y;
+                if (!((first ? da : db) > r2cap) || a.keep_far) nn = first ? jj.x : jj.y;
                 a.nn[i] = nn;
             }
             else
@@ -677,11 +682,43 @@ __global__ void __launch_bounds__(kIcpThreads) icp_search_kernel(IcpArgs a)
         float px, py, pz;
         transform_point(sT, a.src[3 * i], a.src[3 * i + 1], a.src[3 * i + 2], px, py, pz);
         const NnResult r = grid_nearest(g, a.cell_start, a.sorted, px, py, pz, a.search_radius, a.certify ? a.guard * g.h : 0.0f);
-        a.nn[i] = r.index;
+        a.nn[i] = r.index < 0 && a.keep_far ? -2 : r.index;
         a.nn_ref[i] = make_int2(r.index, r.index2);
         a.qref[i] = make_float4(px, py, pz, a.certify ? r.budget : -1.0f);
         a.budget2[i] = a.certify ? r.budget2 : -1.0f;
     }
+}
+
+// The closing CountInliers (ICP.cpp:90,206) runs no search: it re-tests corresponding_index of the last loop iteration -- the
+// nearest neighbours under the PREVIOUS pose, at whatever distance -- with the final pose.  The last solving pass therefore
+// leaves in nn the true nearest neighbour where it knows it (keep_far) and -2 where all it knows is "nothing within the search
+// radius".  Such a point can only become an inlier if the pose update moved it by more than its clearance: the new position
+// is within m of the old one, so a neighbour that passes the test now was within threshold + m then.  Points whose clearance
+// (the "none" budget of their last full search) covers the move have no candidate; the others get an exact search of that
+// radius around their PREVIOUS position.  Kept out of line: it is the rare path of one pass.
+__device__ __noinline__ int final_resolve_far(const IcpArgs &a, const IcpGrid &g, const float *T_prev, const float *T, int i)
+{
+    const float sx = a.src[3 * i], sy = a.src[3 * i + 1], sz = a.src[3 * i + 2];
+    float ox, oy, oz, px, py, pz;
+    transform_point(T_prev, sx, sy, sz, ox, oy, oz);
+    transform_point(T, sx, sy, sz, px, py, pz);
+    const float4 q = a.qref[i];
+    const float ax = ox - q.x, ay = oy - q.y, az = oz - q.z, bx = px - ox, by = py - oy, bz = pz - oz;
+    const float moved = sqrtf(ax * ax + ay * ay + az * az) * (1.0f + 1e-6f);
+    const float m = sqrtf(bx * bx + by * by + bz * bz) * (1.0f + 1e-6f);
+    if (moved + m < q.w) return -1; // also false for NaN
+    if (!(m == m) || !(fabsf(m) < 1e30f)) return -1;
+    return grid_nearest(g, a.cell_start, a.sorted, ox, oy, oz, a.search_radius + m * (1.0f + 1e-3f) + 1e-6f, 0.0f).index;
+}
+__global__ void __launch_bounds__(kIcpThreads) icp_final_resolve_kernel(IcpArgs a)
+{
+    __shared__ float sT[32];
+    if (threadIdx.x < 16) sT[threadIdx.x] = a.st->T[threadIdx.x];
+    else if (threadIdx.x < 32) sT[threadIdx.x] = a.st->T_prev[threadIdx.x - 16];
+    __syncthreads();
+    const IcpGrid g = a.st->grid;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.ns; i += gridDim.x * blockDim.x)
+        if (a.nn[i] == -2) a.nn[i] = final_resolve_far(a, g, sT + 16, sT, i);
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -705,6 +742,7 @@ __device__ void icp_solve_and_update(const IcpArgs &a, IcpState *st)
     st->n_inliers = (unsigned long long)(st->packet[29] + 0.5);
     if (a.final_pass) return;
     st->iteration += 1;
+    for (int e = 0; e < 16; ++e) st->T_prev[e] = st->T[e];
     double dT[16];
     if (a.nrm)
     {
@@ -741,6 +779,7 @@ struct IcpShared
 {
     double part[kIcpThreads / 32][kPacket];
     float T[16];
+    float T_prev[16];
     bool last;
 };
 // returns true in every thread of the CTA that finished last (the one that summed the partials, solved and updated the pose)
@@ -760,7 +799,7 @@ __device__ __forceinline__ bool accumulate_pass(const IcpArgs &a, IcpShared &sh)
 #pragma unroll
     for (int k = 0; k < NA; ++k) acc[k] = 0.0;
     const bool sums = !a.final_pass;
-    const int *__restrict__ nn = a.nn;
+    const int *nn = a.nn;
     const float *__restrict__ src = a.src;
     const float *__restrict__ tgt = a.tgt;
     const float *__restrict__ nrm = a.nrm;
@@ -768,7 +807,7 @@ __device__ __forceinline__ bool accumulate_pass(const IcpArgs &a, IcpShared &sh)
 #pragma unroll 2
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.ns; i += gridDim.x * blockDim.x)
     {
-        const int j = __ldg(&nn[i]);
+        const int j = __ldcg(&nn[i]); // written by this very thread earlier in the pass (or the pass before): not the read-only path
         bool inl = false;
         if (j >= 0)
         {
@@ -914,10 +953,19 @@ __global__ void __launch_bounds__(kIcpThreads, 2) icp_loop_kernel(IcpArgs a, int
     for (int pass = 0; pass < n_pass; ++pass)
     {
         a.final_pass = pass == n_pass - 1;
+        a.keep_far = pass == n_pass - 2;
         __syncthreads();
         if (threadIdx.x < 16) sh.T[threadIdx.x] = a.st->T[threadIdx.x];
+        else if (threadIdx.x < 32 && a.final_pass) sh.T_prev[threadIdx.x - 16] = a.st->T_prev[threadIdx.x - 16];
         __syncthreads();
         unsigned int searched = 0;
+        if (a.final_pass)
+        {
+            // no search: the neighbours of the last solving pass, re-tested under the final pose by accumulate_pass
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.ns; i += gridDim.x * blockDim.x)
+                if (a.nn[i] == -2) { a.nn[i] = final_resolve_far(a, g, sh.T_prev, sh.T, i); ++searched; }
+        }
+        else
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.ns; i += gridDim.x * blockDim.x)
         {
             float px, py, pz;
@@ -932,8 +980,9 @@ __global__ void __launch_bounds__(kIcpThreads, 2) icp_loop_kernel(IcpArgs a, int
                 if (j >= 0)
                 {
                     const float d = dist2_nanoflann(px, py, pz, __ldg(&a.tgt[3 * j]), __ldg(&a.tgt[3 * j + 1]), __ldg(&a.tgt[3 * j + 2]));
-                    if (!(d > r2cap)) nn = j;
+                    if (!(d > r2cap) || a.keep_far) nn = j;
                 }
+                else if (a.keep_far) nn = -2;
             }
             else if (moved < a.budget2[i])
             {
@@ -941,12 +990,12 @@ __global__ void __launch_bounds__(kIcpThreads, 2) icp_loop_kernel(IcpArgs a, int
                 const float da = dist2_nanoflann(px, py, pz, __ldg(&a.tgt[3 * jj.x]), __ldg(&a.tgt[3 * jj.x + 1]), __ldg(&a.tgt[3 * jj.x + 2]));
                 const float db = dist2_nanoflann(px, py, pz, __ldg(&a.tgt[3 * jj.y]), __ldg(&a.tgt[3 * jj.y + 1]), __ldg(&a.tgt[3 * jj.y + 2]));
                 const bool first = da < db || (da == db && jj.x < jj.y);
-                if (!((first ? da : db) > r2cap)) nn = first ? jj.x : jj.y;
+                if (!((first ? da : db) > r2cap) || a.keep_far) nn = first ? jj.x : jj.y;
             }
             else
             {
                 const NnResult r = grid_nearest(g, a.cell_start, a.sorted, px, py, pz, a.search_radius, guard);
-                nn = r.index;
+                nn = r.index < 0 && a.keep_far ? -2 : r.index;
                 a.nn_ref[i] = make_int2(r.index, r.index2);
                 a.qref[i] = make_float4(px, py, pz, a.certify ? r.budget : -1.0f);
                 a.budget2[i] = a.certify ? r.budget2 : -1.0f;
@@ -1489,7 +1538,7 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     a.ns = (int)ns;
     a.search_radius = (float)(par->threshold * (1.0 + 1e-3)) + 1e-6f;
     a.sq_threshold = par->threshold * par->threshold;
-    a.final_pass = 0; a.pairs = c->d_pairs; a.inlier = c->d_inlier;
+    a.final_pass = 0; a.keep_far = 0; a.pairs = c->d_pairs; a.inlier = c->d_inlier;
     a.comm = c->comm;
     // nearest-neighbour certificates: a NaN budget marks "never searched"
     a.qref = c->d_qref; a.nn_ref = c->d_nn_ref; a.worklist = c->d_worklist; a.budget2 = c->d_budget2;
@@ -1497,6 +1546,7 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     static const int k_certify = getenv("OPB_ICP_CERTIFY") ? atoi(getenv("OPB_ICP_CERTIFY")) : 1;
     a.guard = k_guard; a.certify = k_certify;
     if (ns) OPB_CUDA(cudaMemsetAsync(c->d_qref, 0xFF, ns * sizeof(float4), s));
+    if (ns) OPB_CUDA(cudaMemsetAsync(c->d_nn, 0xFF, ns * sizeof(int), s)); // corresponding_index(n, -1) (ICP.cpp:58,174)
     const int nb_need = ns ? (int)((ns + kIcpThreads - 1) / kIcpThreads) : 1; // an empty share still takes part in the exchange
     // developer knobs for grid-size sweeps (CTAs per SM); the defaults are the measured optimum on B200
     static const int k_search = getenv("OPB_ICP_SEARCH_CTAS") ? atoi(getenv("OPB_ICP_SEARCH_CTAS")) : 8;
@@ -1526,9 +1576,15 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     {
         // the last pass is the final CountInliers with the final T (ICP.cpp:90-91,206-207)
         a.final_pass = it == par->max_iteration;
+        a.keep_far = it == par->max_iteration - 1;
         if (it == 0) OPB_CUDA(cudaStreamWaitEvent(s, c->ev_copy[1], 0)); // source points uploaded
-        icp_certify_kernel<<<nb_c, kIcpThreads, 0, s>>>(a);
-        icp_search_kernel<<<nb_s, kIcpThreads, 0, s>>>(a);
+        if (a.final_pass)
+            icp_final_resolve_kernel<<<nb_c, kIcpThreads, 0, s>>>(a); // no search: last pass's neighbours under the final pose
+        else
+        {
+            icp_certify_kernel<<<nb_c, kIcpThreads, 0, s>>>(a);
+            icp_search_kernel<<<nb_s, kIcpThreads, 0, s>>>(a);
+        }
         if (it == 0) OPB_CUDA(cudaStreamWaitEvent(s, c->ev_copy[2], 0)); // target normals uploaded
         if (point_to_plane) icp_accumulate_kernel<true><<<nb_a, kIcpThreads, 0, s>>>(a);
         else icp_accumulate_kernel<false><<<nb_a, kIcpThreads, 0, s>>>(a);
@@ -1725,7 +1781,13 @@ int opb_icp_comm_detach(opb_icp *c)
     c->peers_share_device = false;
     return OPB_OK;
 }
-// nearest-neighbour indices of the LAST search (final CountInliers pass), for tests
+int opb_icp_last_prev_pose(opb_icp *c, float T[16])
+{
+    if (!c || !T) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    memcpy(T, c->h_state->T_prev, 16 * sizeof(float));
+    return OPB_OK;
+}
+// nearest-neighbour indices of the LAST search (the last iteration's, which the closing CountInliers re-tests), for tests
 int opb_icp_last_nn(opb_icp *c, int32_t *nn, size_t n)
 {
     if (!c || !nn) { set_error("NULL argument"); return OPB_ERR_INVALID; }

@@ -287,3 +287,10 @@ def last_nn(n, device=0):
     nn = np.zeros(n, np.int32)
     capi.check(capi.lib.opb_icp_last_nn(_Workspace.get(device), _ptr(nn), n))
     return nn
+
+
+def last_prev_pose(device=0):
+    """the pose the neighbours of last_nn were searched under (start_T before the last iteration's update), 4x4"""
+    T = np.zeros(16, np.float32)
+    capi.check(capi.lib.opb_icp_last_prev_pose(_Workspace.get(device), _ptr(T)))
+    return T.reshape(4, 4).T.copy()

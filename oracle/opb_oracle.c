@@ -860,8 +860,16 @@ long orc_icp(const float *src_in, long ns, const float *tgt_in, const float *nrm
     float *tp = (float *)malloc(sizeof(float) * 3 * ns);
     int32_t *nn = (int32_t *)malloc(sizeof(int32_t) * ns);
     long n_in = 0;
+    for (long i = 0; i < ns; ++i) nn[i] = -1; /* corresponding_index(source.points.size(), -1) (ICP.cpp:58,174) */
     for (int it = 0; it <= max_it; ++it)
     {
+        if (it == max_it)
+        {
+            /* The closing CountInliers (ICP.cpp:90,206) re-tests the corresponding_index of the LAST loop iteration -- the
+             * neighbours found under the previous pose, whatever their distance -- with the final pose; no new search. */
+            n_in = count_inliers(src, tgt, nn, ns, T, thr, pairs, rmse);
+            break;
+        }
         /* geometry::TransformPoints (Geometry.cpp:19-27) */
         for (long i = 0; i < ns; ++i)
         {
@@ -871,7 +879,6 @@ long orc_icp(const float *src_in, long ns, const float *tgt_in, const float *nrm
         }
         orc_nearest(tp, ns, tgt, nt, nn);
         n_in = count_inliers(src, tgt, nn, ns, T, thr, pairs, rmse);
-        if (it == max_it) break; /* final CountInliers with the final T (ICP.cpp:90,206) */
         double dT[16];
         if (nrm)
         {   /* EstimateRigidTransformationPointToPlane (ICP.cpp:108-144) */

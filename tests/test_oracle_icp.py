@@ -68,3 +68,24 @@ def test_oracle_icp_vs_compiled_reference(g, mode):
     assert np.array_equal(o["pairs"], r["pairs"])
     x = np.array([0.01, -0.02, 0.03, 0.1, -0.2, 0.05])
     assert np.abs(oracleapi.se3_exp(x) - refapi.se3_exp(x, "f64")).max() < 1e-14
+
+
+@pytest.mark.skipif(not refapi.available("f64"), reason="oracle/_ref not built")
+@pytest.mark.parametrize("mode", ["plane", "point"])
+@pytest.mark.parametrize("max_iter", [0, 1, 2, 3])
+def test_oracle_icp_unconverged_vs_compiled_reference(g, mode, max_iter):
+    """Few iterations from a large offset: the closing CountInliers (ICP.cpp:90,206) reuses the neighbours found under the
+    previous pose -- whatever their distance -- and only re-tests them with the final pose.  DenseSlam calls PointToPoint with
+    max_iteration = 1 (example/DenseFusion/DenseSlam.cpp:72-90), so this is a caller-visible case."""
+    nrm = g["nrm"] if mode == "plane" else None
+    T0 = np.eye(4)
+    T0[:3, 3] = [0.03, -0.01, 0.015]
+    o = oracleapi.icp(g["src"], g["tgt"], nrm, T0, max_iter, 0.04)
+    r = refapi.icp(g["src"], g["tgt"], nrm, T0, max_iter, 0.04, "f64")
+    assert np.array_equal(o["pairs"], r["pairs"])
+    if max_iter == 0:
+        assert len(r["pairs"]) == 0 and np.isnan(o["rmse"]) and np.isnan(r["rmse"])
+        return
+    dt, dr = pose_delta(o["T"], r["T"])
+    assert dt < 1e-6 and dr < 1e-6, (dt, dr)
+    assert abs(o["rmse"] - r["rmse"]) < 1e-7
