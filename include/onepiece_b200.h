@@ -100,7 +100,8 @@ typedef struct
     int32_t candidate_cubes; /* cubes tested in [min-1,max+1]^3   (CubeHandler.cpp:165-171) */
     int32_t frame_cubes;     /* cubes listed for this frame        (:181-191)               */
     int32_t total_cubes;     /* cubes allocated in the volume                                */
-    int32_t overflow;        /* !=0 if the pool or table was full and cubes were dropped     */
+    int32_t overflow;        /* how many times the block pool has grown so far (the synchronous calls grow it instead
+                                of dropping cubes; asynchronous ones return OPB_ERR_CAPACITY at the next synchronisation) */
     int64_t updated_voxels;  /* voxels whose |sdf| < truncation this frame (Integrator.cpp:74) */
     float bbox_min[3], bbox_max[3]; /* CubeHandler::ComputeBounding result (CubeHandler.cpp:116-145) */
     float select_ms;         /* device time of cube selection, when profiling is on */
@@ -138,6 +139,13 @@ int opb_volume_frame_stats(opb_volume *v, opb_frame_stats *out); /* synchronizes
  * list (ids: 3 x int32 per cube, unordered).  *n_cubes in: capacity, out: count. */
 int opb_volume_prepare_cubes(opb_volume *v, const void *depth, int depth_type, const float pose_colmajor[16],
                              int32_t *cube_ids, size_t *n_cubes);
+/* CubeHandler::ComputeBounding(depth, pose, max_pos, min_pos) (CubeHandler.cpp:116-145) by itself: read-only like the
+ * reference's -- nothing is selected or allocated.  Host depth image, synchronous. */
+int opb_volume_compute_bounding(opb_volume *v, const void *depth, int depth_type, const float pose_colmajor[16],
+                                float bbox_min[3], float bbox_max[3]);
+/* the cube ids the last frame listed (PrepareCubes' cube_id_list); *n_cubes in: capacity of cube_ids (3 int32 each), out: count;
+ * cube_ids may be NULL to ask for the count */
+int opb_volume_last_frame_cubes(opb_volume *v, int32_t *cube_ids, size_t *n_cubes);
 
 int opb_volume_num_cubes(opb_volume *v, size_t *n);
 /* CubeHandler::GetCubeMap (CubeHandler.h:339): cube_ids 3 x int32 per cube; voxels 512 x 5 float per cube in

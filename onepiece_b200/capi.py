@@ -106,6 +106,8 @@ SIGNATURES = {
     "opb_volume_synchronize": (C.c_int, [_p]),
     "opb_volume_frame_stats": (C.c_int, [_p, C.POINTER(FrameStats)]),
     "opb_volume_prepare_cubes": (C.c_int, [_p, _p, C.c_int, _p, _p, C.POINTER(_sz)]),
+    "opb_volume_compute_bounding": (C.c_int, [_p, _p, C.c_int, _p, _p, _p]),
+    "opb_volume_last_frame_cubes": (C.c_int, [_p, _p, C.POINTER(_sz)]),
     "opb_volume_num_cubes": (C.c_int, [_p, C.POINTER(_sz)]),
     "opb_volume_download": (C.c_int, [_p, _p, _p, C.POINTER(_sz)]),
     "opb_volume_upload": (C.c_int, [_p, _p, _p, _sz]),

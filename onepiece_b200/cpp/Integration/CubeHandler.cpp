@@ -14,7 +14,7 @@ namespace integration
 {
 namespace
 {
-void Check(int rc, const char *what)
+bool Check(int rc, const char *what)
 {
     if (rc != OPB_OK)
     {
@@ -22,6 +22,7 @@ void Check(int rc, const char *what)
         std::cout << RED << "[ERROR]::[" << what << "]::" << opb_last_error() << RESET << std::endl;
         if (rc == OPB_ERR_CUDA) std::exit(1); // no device, no result: there is no CPU path to fall back to
     }
+    return rc == OPB_OK;
 }
 int DepthType(const cv::Mat &depth)
 {
@@ -101,22 +102,23 @@ void CubeHandler::PrepareCubes(const cv::Mat &depth, const geometry::Transformat
     EnsureVolume();
     float p[16];
     PoseToArray(pose, p);
-    std::vector<int32_t> ids((size_t)max_cubes * 3);
-    size_t n = (size_t)max_cubes;
-    Check(opb_volume_prepare_cubes(volume, depth.data, DepthType(depth), p, ids.data(), &n), "PrepareCubes");
+    size_t n = 0;
+    if (!Check(opb_volume_prepare_cubes(volume, depth.data, DepthType(depth), p, nullptr, &n), "PrepareCubes")) { cube_id_list.clear(); return; }
+    std::vector<int32_t> ids(n * 3 + 3);
+    Check(opb_volume_last_frame_cubes(volume, ids.data(), &n), "PrepareCubes");
     cube_id_list.clear();
-    for (size_t i = 0; i < n && i < (size_t)max_cubes; ++i) cube_id_list.push_back(CubeID(ids[3 * i], ids[3 * i + 1], ids[3 * i + 2]));
+    for (size_t i = 0; i < n; ++i) cube_id_list.push_back(CubeID(ids[3 * i], ids[3 * i + 1], ids[3 * i + 2]));
 }
-// CubeHandler.cpp:116-145
+// CubeHandler.cpp:116-145 (read-only, like the reference's: nothing is selected or allocated)
 void CubeHandler::ComputeBounding(const cv::Mat &depth, const geometry::TransformationMatrix &pose, geometry::Point3 &max_pos,
                                   geometry::Point3 &min_pos)
 {
-    std::vector<CubeID> unused;
-    PrepareCubes(depth, pose, unused);
-    opb_frame_stats st;
-    Check(opb_volume_frame_stats(volume, &st), "ComputeBounding");
-    max_pos = geometry::Point3(st.bbox_max[0], st.bbox_max[1], st.bbox_max[2]);
-    min_pos = geometry::Point3(st.bbox_min[0], st.bbox_min[1], st.bbox_min[2]);
+    EnsureVolume();
+    float p[16], mn[3], mx[3];
+    PoseToArray(pose, p);
+    if (!Check(opb_volume_compute_bounding(volume, depth.data, DepthType(depth), p, mn, mx), "ComputeBounding")) return;
+    max_pos = geometry::Point3(mx[0], mx[1], mx[2]);
+    min_pos = geometry::Point3(mn[0], mn[1], mn[2]);
 }
 // CubeHandler.cpp:9-44 + TriangleMesh::LoadFromMeshes (TriangleMesh.cpp:73-94)
 void CubeHandler::ExtractTriangleMesh(geometry::TriangleMesh &mesh)

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) resample_alloc_kernel(VolumeDev src, int 
             const int ci = (n0[0] + (i & 1)) >> 3, cj = (n0[1] + ((i >> 1) & 1)) >> 3, ck = (n0[2] + (i >> 2)) >> 3; // floor(v / 8)
             unsigned long long key = kEmptyKey;
             const bool ok = live && pack_id(ci, cj, ck, key);
-            if (live && !ok) dst.fc->overflow = 1;
+            if (live && !ok) raise_overflow(dst, kOverflowRange);
             // one lane per distinct cube of the warp performs the insert
             const unsigned int peers = __match_any_sync(0xffffffffu, ok ? key : kEmptyKey);
             if (ok && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) table_find_or_insert(dst, ci, cj, ck);
@@ -306,16 +306,20 @@ int opb_volume_merge(opb_volume *dst, opb_volume *other)
     cudaFree(d_new);
     if (e != cudaSuccess) { set_error("volume merge failed: %s", cudaGetErrorString(e)); return OPB_ERR_CUDA; }
     if (n_dst + (size_t)n_new > (size_t)dst->dev.max_cubes)
-    {
-        set_error("merge needs %zu cubes, max_cubes=%d", n_dst + (size_t)n_new, dst->dev.max_cubes);
-        return OPB_ERR_CAPACITY;
+    {   // the reference's map is unbounded (CubeHandler.h:145-177): make room
+        rc = volume_grow(dst, (long long)(n_dst + (size_t)n_new));
+        if (rc) return rc;
     }
     merge_kernel<<<(unsigned int)n_other, kCubeVoxels, 0, s>>>(dst->dev, other->dev, (int)n_other);
     OPB_CUDA(cudaGetLastError());
     int t_other = 0;
     OPB_CUDA(cudaMemcpyAsync(&t_other, other->dev.tainted, sizeof(int), cudaMemcpyDeviceToHost, s));
     OPB_CUDA(cudaStreamSynchronize(s));
-    if (t_other) OPB_CUDA(cudaMemcpy(dst->dev.tainted, &t_other, sizeof(int), cudaMemcpyHostToDevice));
+    if (t_other)
+    {
+        OPB_CUDA(cudaMemcpyAsync(dst->dev.tainted, &t_other, sizeof(int), cudaMemcpyHostToDevice, s));
+        OPB_CUDA(cudaStreamSynchronize(s));
+    }
     return OPB_OK;
 }
 } // extern "C"

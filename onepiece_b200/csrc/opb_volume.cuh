@@ -26,7 +26,7 @@ struct FrameCounters
     unsigned int bbox_max[3];
     int candidate_cubes;
     int frame_cubes;
-    int overflow;
+    int overflow;   // kOverflowPool: pool or table full, cubes were skipped; kOverflowRange: cube ids beyond 21 bits per axis
     int wild_frame; // a depth value outside [1e-6, 1e6] m was seen: the update kernel takes its IEEE-division path
     unsigned long long updated_voxels;
 };
@@ -42,6 +42,7 @@ struct VolumeDev
     int *tainted;             // != 0 after an upload of values outside the range the fast quotient is exact for
     float2 *texels;           // per-frame W*H texels {depth in metres (f32), b | g<<8 | r<<16 as raw bits}
     FrameCounters *fc;        // counters of the frame in flight
+    volatile int *host_flags; // mapped pinned host memory, sticky until the host clears it: [0] pool full, [1] ids out of range
     int max_cubes;
     unsigned int table_mask;
 };
@@ -64,7 +65,14 @@ struct FrameParams
     double width_d, height_d;
     int shard_rank, shard_world, shard_axis, shard_slab;
     int exact_division; // host decision: pose / intrinsics outside the tame range -> IEEE-division path
+    int min_new_slot;   // > 0: list only cubes allocated by this very pass (slot >= min_new_slot) -- the re-run after the pool grew
 };
+constexpr int kOverflowPool = 1, kOverflowRange = 2;
+__device__ __forceinline__ void raise_overflow(const VolumeDev &v, int bit)
+{
+    atomicOr(&v.fc->overflow, bit);
+    if (v.host_flags) v.host_flags[bit == kOverflowPool ? 0 : 1] = 1;
+}
 
 __host__ __device__ __forceinline__ bool pack_id(int i, int j, int k, unsigned long long &key)
 {
@@ -101,7 +109,7 @@ __device__ __forceinline__ int table_find(const VolumeDev &v, int i, int j, int 
 __device__ __forceinline__ int table_find_or_insert(const VolumeDev &v, int i, int j, int k)
 {
     unsigned long long key;
-    if (!pack_id(i, j, k, key)) { v.fc->overflow = 1; return -1; }
+    if (!pack_id(i, j, k, key)) { raise_overflow(v, kOverflowRange); return -1; }
     unsigned int h = hash_key(key) & v.table_mask;
     for (unsigned int probe = 0; probe <= v.table_mask; ++probe)
     {
@@ -111,7 +119,7 @@ __device__ __forceinline__ int table_find_or_insert(const VolumeDev &v, int i, i
             const int slot = atomicAdd(v.n_alloc, 1);
             if (slot >= v.max_cubes)
             {
-                v.fc->overflow = 1;
+                raise_overflow(v, kOverflowPool);
                 v.vals[h] = -1;
                 return -1;
             }
@@ -124,7 +132,7 @@ __device__ __forceinline__ int table_find_or_insert(const VolumeDev &v, int i, i
         if (prev == key) return v.vals[h]; // inserted by an earlier frame (a cube is tested once per frame)
         h = (h + 1) & v.table_mask;
     }
-    v.fc->overflow = 1;
+    raise_overflow(v, kOverflowPool);
     return -1;
 }
 

@@ -45,6 +45,15 @@ struct opb_volume
     void *halo_scratch = nullptr;
     size_t halo_scratch_bytes = 0;
 
+    // pool exhaustion (the reference's unordered_map is unbounded, CubeHandler.cpp:181-191): the kernels raise sticky flags in
+    // mapped host memory; the synchronous calls grow the pool and re-run the frame for the cubes that found no slot, the
+    // asynchronous ones report OPB_ERR_CAPACITY at the next synchronisation
+    int *h_flags = nullptr;
+    long long frames_with_lost_cubes = 0;
+    int grow_count = 0;
+    int carry_frame_cubes = 0;                 // counters of a frame's first pass when the pool grew under it
+    unsigned long long carry_updated = 0;
+
     int profile_acquire(opb::ProfileSlot **out);
     int profile_drain();
 };
@@ -55,6 +64,8 @@ void build_frame_params(const opb_volume *v, const float *pose_cm, int depth_typ
 // enqueue on the volume's stream: slots [first, first+n) back to the TSDFVoxel defaults; hash table rebuilt from slots [0, n_alloc)
 int volume_reinit_slots(opb_volume *v, size_t first, size_t n);
 int volume_rebuild_table(opb_volume *v, int n_alloc);
+// doubles the block pool (at least min_cubes slots), keeps the cubes, rebuilds the table; OPB_ERR_CAPACITY when memory is short
+int volume_grow(opb_volume *v, long long min_cubes);
 int halo_drop_ghosts(opb_volume *v); // opb_halo.cu
 // opb_meshpost.cu: TriangleMesh::ClusteringSimplify on device-resident arrays (outputs are cudaMalloc'ed), and the download
 // of such a result into malloc'ed host buffers (frees the device copies)

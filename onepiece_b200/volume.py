@@ -110,13 +110,23 @@ class CubeHandler:
         capi.check(capi.lib.opb_volume_synchronize(self._h))
 
     def PrepareCubes(self, depth, pose):
+        """CubeHandler::PrepareCubes(depth, pose, cube_id_list) (CubeHandler.cpp:147-196) -> [n, 3] int32 cube ids"""
         depth = np.ascontiguousarray(depth)
         p = pose_colmajor(pose)
-        cap = int(self.desc.max_cubes)
-        ids = np.zeros((cap, 3), np.int32)
-        n = C.c_size_t(cap)
-        capi.check(capi.lib.opb_volume_prepare_cubes(self._h, _ptr(depth), depth_type_of(depth), _ptr(p), _ptr(ids), C.byref(n)))
+        n = C.c_size_t(0)
+        capi.check(capi.lib.opb_volume_prepare_cubes(self._h, _ptr(depth), depth_type_of(depth), _ptr(p), None, C.byref(n)))
+        ids = np.zeros((max(n.value, 1), 3), np.int32)
+        n = C.c_size_t(len(ids))
+        capi.check(capi.lib.opb_volume_last_frame_cubes(self._h, _ptr(ids), C.byref(n)))
         return ids[: n.value].copy()
+
+    def ComputeBounding(self, depth, pose):
+        """CubeHandler::ComputeBounding(depth, pose, max_pos, min_pos) (CubeHandler.cpp:116-145) -> (max_pos, min_pos); read-only"""
+        depth = np.ascontiguousarray(depth)
+        p = pose_colmajor(pose)
+        mn, mx = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        capi.check(capi.lib.opb_volume_compute_bounding(self._h, _ptr(depth), depth_type_of(depth), _ptr(p), _ptr(mn), _ptr(mx)))
+        return mx, mn
 
     def FrameStats(self) -> capi.FrameStats:
         s = capi.FrameStats()

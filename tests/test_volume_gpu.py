@@ -209,16 +209,78 @@ def test_setters_take_effect():
     compare_volumes(gpu, ov)
 
 
+def test_a_full_pool_grows_instead_of_dropping_cubes():
+    """The reference's cube map is unbounded (CubeHandler.cpp:181-191).  A pool that is far too small grows under the
+    synchronous calls and the frame is completed for the cubes that found no slot: same volume as with a roomy pool."""
+    cam = small_camera()
+    rng = np.random.default_rng(5)
+    small = CubeHandler(cam, 0.02, max_cubes=64)  # ~1000 cubes needed
+    roomy = CubeHandler(cam, 0.02, max_cubes=8192)
+    ov = oracleapi.OracleVolume(cam, 0.02)
+    for k in range(3):
+        d, c = scenes.wavy_wall(cam, k)
+        T = random_pose(rng, 0.1 if k else 0.0)
+        small.IntegrateImage(d, c, T)
+        roomy.IntegrateImage(d, c, T)
+        n = ov.integrate(d, c, T)
+        st = small.FrameStats()
+        assert st.frame_cubes == n == roomy.FrameStats().frame_cubes
+        assert st.updated_voxels == roomy.FrameStats().updated_voxels
+    assert small.FrameStats().overflow >= 4 and roomy.FrameStats().overflow == 0   # 64 -> 128 -> ... -> 1024+
+    a, b = small.GetCubeMap(), roomy.GetCubeMap()
+    oa, ob = np.lexsort(a[0].T[::-1]), np.lexsort(b[0].T[::-1])
+    assert np.array_equal(a[0][oa], b[0][ob])
+    assert_bit_equal(a[1][oa], b[1][ob], "voxels of the grown volume")
+    oi, ovx = ov.download()
+    oo = np.lexsort(oi.T[::-1])
+    assert np.array_equal(a[0][oa], oi[oo])
+    assert_bit_equal(a[1][oa], ovx[oo], "grown volume vs oracle")
+    # PrepareCubes and SetCubeMap grow as well
+    tiny = CubeHandler(cam, 0.02, max_cubes=16)
+    d, c = scenes.wavy_wall(cam, 0)
+    ids = tiny.PrepareCubes(d, np.eye(4))
+    assert len(ids) == len(roomy.PrepareCubes(d, np.eye(4))) and len(ids) > 16
+    tiny2 = CubeHandler(cam, 0.02, max_cubes=16)
+    tiny2.SetCubeMap(*b)
+    c2 = tiny2.GetCubeMap()
+    assert np.array_equal(c2[0], b[0]) and np.array_equal(c2[1].view(np.uint32), b[1].view(np.uint32))
+
+
+def test_compute_bounding_is_read_only():
+    cam = small_camera()
+    d, c = scenes.wavy_wall(cam, 0)
+    T = scenes.se3_exp([0.05, -0.02, 0.03, 0.02, -0.03, 0.01]).astype(np.float32)
+    gpu = CubeHandler(cam, 0.02, max_cubes=4096)
+    ov = oracleapi.OracleVolume(cam, 0.02)
+    mx, mn = gpu.ComputeBounding(d, T)
+    omx, omn = ov.bounding(d, T)
+    assert_bit_equal(mx, omx, "bbox max")
+    assert_bit_equal(mn, omn, "bbox min")
+    assert gpu.NumCubes() == 0        # the reference's ComputeBounding allocates nothing (CubeHandler.cpp:116-145)
+    gpu.IntegrateImage(d, c, T)
+    n = gpu.NumCubes()
+    gpu.ComputeBounding(d, np.eye(4))
+    assert gpu.NumCubes() == n
+
+
 def test_errors_are_loud():
     cam = small_camera()
     d, c = scenes.wavy_wall(cam, 0)
-    gpu = CubeHandler(cam, 0.02, max_cubes=64)  # far too small: ~1000 cubes needed
-    gpu.IntegrateImage(d, c, np.eye(4))
-    st = gpu.FrameStats()
-    assert st.overflow != 0 and st.total_cubes == 64
+    gpu = CubeHandler(cam, 0.02, max_cubes=64)
+    # asynchronous frames cannot be re-run once their inputs are gone: a full pool is an error at the next synchronisation
+    import torch
+    pd, pc = torch.from_numpy(d).pin_memory(), torch.from_numpy(c).pin_memory()
+    I = np.ascontiguousarray(np.eye(4, dtype=np.float32)).reshape(16)
+    gpu.IntegrateImageAsync(pd.numpy(), capi.OPB_DEPTH_F32, pc.numpy(), I)
     with pytest.raises(capi.OpbError) as e:
-        gpu.PrepareCubes(d, np.eye(4))
+        gpu.Synchronize()
     assert e.value.code == capi.OPB_ERR_CAPACITY
+    gpu.Synchronize()                                 # reported once; the volume stays usable
+    assert gpu.NumCubes() == 64
+    gpu.IntegrateImage(d, c, np.eye(4))               # ... and the synchronous call completes it
+    big = CubeHandler(cam, 0.02, max_cubes=4096)
+    big.IntegrateImage(d, c, np.eye(4))
+    assert gpu.NumCubes() == big.NumCubes()
     # unknown depth type: the reference exit(1)s (ImageProcessing.cpp:86-90); the C-ABI returns an error
     with pytest.raises(capi.OpbError) as e:
         gpu.IntegrateImage(d.astype(np.float64), c, np.eye(4))
