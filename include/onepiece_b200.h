@@ -287,6 +287,38 @@ int opb_icp_point_to_plane(opb_icp *c, const float *src_xyz, size_t ns, const fl
 int opb_icp_point_to_point(opb_icp *c, const float *src_xyz, size_t ns, const float *tgt_xyz, size_t nt,
                            const float init_T_colmajor[16], const opb_icp_params *params, opb_icp_result *result,
                            int32_t *pairs, size_t pairs_cap);
+/* ---- geometry::PointCloud resident on the device (src/Geometry/PointCloud.h:52-54) ----
+ * The reference's callers back-project every frame on the host (PointCloud::LoadFromDepth, src/Geometry/PointCloud.cpp:72-100)
+ * and hand the cloud to ICP, which copies it again (ICP.cpp:150-151); a frame is the source of one registration and the target
+ * of the next, and is then integrated.  An opb_cloud uploads the depth (and colour) image once, builds the cloud on the device
+ * with the reference's arithmetic (bit-identical points, raster order, z > 0 only) and keeps images, points and normals in
+ * HBM for all three uses.  Calls that take images or arrays only ENQUEUE on the cloud's own stream: host buffers must stay
+ * valid until opb_cloud_size (or any call that consumes the cloud) has returned; pinned host memory makes the copies truly
+ * asynchronous, so the next frame can be loaded while the current one is being registered. */
+typedef struct opb_cloud opb_cloud;
+int opb_cloud_create(int device, void *stream /* cudaStream_t or NULL: own stream */, opb_cloud **out);
+void opb_cloud_destroy(opb_cloud *c);
+/* PointCloud::LoadFromDepth(depth, camera); bgr (optional, W*H*3) is kept with the depth image for opb_volume_integrate_cloud.
+ * depth / bgr: host or device pointers. */
+int opb_cloud_load_from_depth(opb_cloud *c, const void *depth, int depth_type, const uint8_t *bgr, float fx, float fy, float cx,
+                              float cy, int width, int height, float depth_scale);
+/* an arbitrary cloud / its normals from arrays (3 floats per point, host or device) */
+int opb_cloud_set_points(opb_cloud *c, const float *xyz, size_t n);
+int opb_cloud_set_normals(opb_cloud *c, const float *normals, size_t n);
+/* waits for everything enqueued on the cloud; number of points */
+int opb_cloud_size(opb_cloud *c, size_t *n);
+/* points / normals back to the host (either may be NULL) */
+int opb_cloud_download(opb_cloud *c, float *xyz, float *normals);
+/* PointToPlane / PointToPoint on device-resident clouds: the buffers are used where they lie, nothing is copied (PointToPoint
+ * with scaling != 1 works on scaled copies like the reference).  Everything else as opb_icp_point_to_plane / _point. */
+int opb_icp_point_to_plane_clouds(opb_icp *c, opb_cloud *source, opb_cloud *target, const float init_T_colmajor[16],
+                                  const opb_icp_params *params, opb_icp_result *result, int32_t *pairs, size_t pairs_cap);
+int opb_icp_point_to_point_clouds(opb_icp *c, opb_cloud *source, opb_cloud *target, const float init_T_colmajor[16],
+                                  const opb_icp_params *params, opb_icp_result *result, int32_t *pairs, size_t pairs_cap);
+/* CubeHandler::IntegrateImage(depth, rgb, pose) with the images the cloud was loaded from (already in HBM); synchronous, grows
+ * the pool like opb_volume_integrate */
+int opb_volume_integrate_cloud(opb_volume *v, opb_cloud *frame, const float pose_colmajor[16]);
+
 /* PointCloud::EstimateNormals(radius = 0.1, knn = 30) (src/Geometry/PointCloud.cpp:102-144), the step in front of PointToPlane
  * when the clouds come without normals (example/ICPTest.cpp:27-33): per point the knn nearest points (the point itself
  * included) whose SQUARED distance does not exceed `radius` (the reference's KnnRadiusSearch compares dist^2 with radius,
@@ -403,6 +435,10 @@ int opb_icp_last_search_trace(opb_icp *c, uint32_t *per_pass, int cap);
 /* CUDA-event timing of the last call when enabled: grid construction and the iteration loop */
 int opb_icp_set_profiling(opb_icp *c, int on);
 int opb_icp_last_timing(opb_icp *c, float *grid_build_ms, float *iterations_ms);
+/* per-pass time stamps of the persistent loop kernel of the last call (globaltimer ns), 8 per pass for the first min(passes, 48)
+ * passes.  CTA 0: [0] pass start, [1] own points certified / searched, [2] accumulated + partial published, [3] released into
+ * the next pass; the CTA that finished last: [4] knows it is last, [5] partials summed, [6] solved + pose updated; [7] unused */
+int opb_icp_last_stamps(opb_icp *c, uint64_t *stamps, int passes);
 
 
 /* ------------------------------------------------------------------------------------------------------

@@ -159,6 +159,17 @@ SIGNATURES = {
     "opb_icp_last_search_trace": (C.c_int, [_p, _p, C.c_int]),
     "opb_icp_last_nn": (C.c_int, [_p, _p, _sz]),
     "opb_icp_last_prev_pose": (C.c_int, [_p, _p]),
+    "opb_icp_last_stamps": (C.c_int, [_p, _p, C.c_int]),
+    "opb_cloud_create": (C.c_int, [C.c_int, _p, C.POINTER(_p)]),
+    "opb_cloud_destroy": (None, [_p]),
+    "opb_cloud_load_from_depth": (C.c_int, [_p, _p, C.c_int, _p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_float]),
+    "opb_cloud_set_points": (C.c_int, [_p, _p, _sz]),
+    "opb_cloud_set_normals": (C.c_int, [_p, _p, _sz]),
+    "opb_cloud_size": (C.c_int, [_p, C.POINTER(_sz)]),
+    "opb_cloud_download": (C.c_int, [_p, _p, _p]),
+    "opb_icp_point_to_plane_clouds": (C.c_int, [_p, _p, _p, _p, C.POINTER(IcpParams), C.POINTER(IcpResult), _p, _sz]),
+    "opb_icp_point_to_point_clouds": (C.c_int, [_p, _p, _p, _p, C.POINTER(IcpParams), C.POINTER(IcpResult), _p, _sz]),
+    "opb_volume_integrate_cloud": (C.c_int, [_p, _p, _p]),
     "opb_icp_set_profiling": (C.c_int, [_p, C.c_int]),
     "opb_icp_last_timing": (C.c_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "opb_odometry_desc_default": (None, [C.POINTER(OdometryDesc)]),

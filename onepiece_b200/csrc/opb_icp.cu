@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "../../include/onepiece_b200.h"
+#include "opb_cloud_host.h"
 #include "opb_common.cuh"
 #include "opb_fitplane.cuh"
 #include "opb_linalg.h"
@@ -42,6 +43,13 @@ struct IcpGrid
     float h, inv_h;
     int dim[3];
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 struct IcpState // device-resident solver state
 {
@@ -60,7 +68,16 @@ struct IcpState // device-resident solver state
     unsigned long long searched_total;  // full searches done over the whole call (profiling)
     unsigned int searched_per_pass[64]; // ... and per pass (the first 64)
     unsigned int pass;
+    // per-pass time stamps of the persistent loop (globaltimer ns), the first kStampPasses passes.  CTA 0: [0] pass start, [1] own
+    // points certified / searched, [2] own points accumulated and partial published, [3] released into the next pass.  The CTA
+    // that finished last: [4] knows it is last, [5] partials summed (+ exchanged), [6] solved and pose updated.
+    unsigned long long stamps[48][8];
 };
+constexpr int kStampPasses = 48;
+__device__ __forceinline__ void icp_stamp(IcpState *st, unsigned int pass, int slot)
+{
+    if (pass < (unsigned int)kStampPasses) st->stamps[pass][slot] = global_timer_ns();
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // cross-GPU exchange of the reduction packet: when the source points of one registration are split
@@ -84,12 +101,6 @@ struct IcpComm
     int rank, world;
 };
 
-__device__ __forceinline__ unsigned long long global_timer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 
 // Sum of packet[0..n) over all ranks, in rank order; called by every thread of ONE CTA (>= 32 threads) on every rank the same
 // number of times.  Two mailbox halves alternate: a rank can be at most one exchange ahead of a peer, because finishing an
@@ -735,22 +746,19 @@ __device__ __forceinline__ void warp_accumulate(double (*s_part)[kPacket], int w
     if (lane == 0) s_part[warp][k] += v;
 }
 
-// the pose update of one iteration (ICP.cpp:78-86, 137-143, 198), run by one thread of the last CTA
-__device__ void icp_solve_and_update(const IcpArgs &a, IcpState *st)
+// the pose update of one iteration (ICP.cpp:78-86, 137-143, 198) from the 30-scalar packet: T <- dT * T, T_prev <- T.  One thread.
+// Returns false when nothing was updated (point-to-point without inliers: the reference would produce NaNs there).
+__device__ bool icp_solve_core(const double *pk, bool plane, float *T, float *T_prev)
 {
-    st->sum_error = st->packet[28];
-    st->n_inliers = (unsigned long long)(st->packet[29] + 0.5);
-    if (a.final_pass) return;
-    st->iteration += 1;
-    for (int e = 0; e < 16; ++e) st->T_prev[e] = st->T[e];
+    for (int e = 0; e < 16; ++e) T_prev[e] = T[e];
     double dT[16];
-    if (a.nrm)
+    if (plane)
     {
         double JTJ[36], nJTr[6], x[6];
         int k = 0;
         for (int p = 0; p < 6; ++p)
-            for (int q = p; q < 6; ++q) { JTJ[p * 6 + q] = st->packet[k]; JTJ[q * 6 + p] = st->packet[k]; ++k; }
-        for (int p = 0; p < 6; ++p) nJTr[p] = -st->packet[21 + p];
+            for (int q = p; q < 6; ++q) { JTJ[p * 6 + q] = pk[k]; JTJ[q * 6 + p] = pk[k]; ++k; }
+        for (int p = 0; p < 6; ++p) nJTr[p] = -pk[21 + p];
         linalg::solve_normal_equations6(JTJ, nJTr, x);
         // the reference's x is float32
         for (int p = 0; p < 6; ++p) x[p] = (double)(float)x[p];
@@ -758,8 +766,8 @@ __device__ void icp_solve_and_update(const IcpArgs &a, IcpState *st)
     }
     else
     {
-        if (st->packet[29] < 0.5) return; // no inliers: leave T unchanged (the reference would produce NaNs here)
-        linalg::kabsch_from_sums(st->packet[29], &st->packet[0], &st->packet[3], &st->packet[6], dT);
+        if (pk[29] < 0.5) return false; // no inliers: leave T unchanged
+        linalg::kabsch_from_sums(pk[29], &pk[0], &pk[3], &pk[6], dT);
     }
     // start_T = tmp_T * start_T in float (ICP.cpp:86,198)
     float dTf[16], Tn[16];
@@ -767,9 +775,24 @@ __device__ void icp_solve_and_update(const IcpArgs &a, IcpState *st)
         for (int c = 0; c < 4; ++c) dTf[c * 4 + r] = (float)dT[r * 4 + c];
     for (int c = 0; c < 4; ++c)
         for (int r = 0; r < 4; ++r)
-            Tn[c * 4 + r] = fadd(fadd(fadd(fmul(dTf[r], st->T[c * 4]), fmul(dTf[4 + r], st->T[c * 4 + 1])), fmul(dTf[8 + r], st->T[c * 4 + 2])),
-                                 fmul(dTf[12 + r], st->T[c * 4 + 3]));
-    for (int e = 0; e < 16; ++e) st->T[e] = Tn[e];
+            Tn[c * 4 + r] = fadd(fadd(fadd(fmul(dTf[r], T[c * 4]), fmul(dTf[4 + r], T[c * 4 + 1])), fmul(dTf[8 + r], T[c * 4 + 2])),
+                                 fmul(dTf[12 + r], T[c * 4 + 3]));
+    for (int e = 0; e < 16; ++e) T[e] = Tn[e];
+    return true;
+}
+// ... on the device-resident state, run by one thread of the last CTA (separate-launch form and first persistent form)
+__device__ void icp_solve_and_update(const IcpArgs &a, IcpState *st)
+{
+    st->sum_error = st->packet[28];
+    st->n_inliers = (unsigned long long)(st->packet[29] + 0.5);
+    if (a.final_pass) return;
+    st->iteration += 1;
+    float T[16], Tp[16];
+    for (int e = 0; e < 16; ++e) T[e] = st->T[e];
+    const bool moved = icp_solve_core(st->packet, a.nrm != nullptr, T, Tp);
+    for (int e = 0; e < 16; ++e) st->T_prev[e] = Tp[e];
+    if (moved)
+        for (int e = 0; e < 16; ++e) st->T[e] = T[e];
 }
 
 // K8: CountInliers test, Jacobian row and the 30-scalar packet over the pairs (i, nn[i]).  Per-thread double accumulators
@@ -883,6 +906,7 @@ __device__ __forceinline__ bool accumulate_pass(const IcpArgs &a, IcpShared &sh)
     __syncthreads();
     if (!s_last) return false;
     __threadfence();
+    if (threadIdx.x == 0) icp_stamp(a.st, a.st->pass, 4);
     {
         // 8 interleaved chains per component, then the chains in order: deterministic
         const int k = threadIdx.x & 31, chain = threadIdx.x >> 5;
@@ -923,11 +947,13 @@ __device__ __forceinline__ bool accumulate_pass(const IcpArgs &a, IcpShared &sh)
     if (threadIdx.x == 0) a.st->n_inliers_local = (unsigned long long)(a.st->packet[29] + 0.5);
     comm_allreduce(a.comm, a.st->packet, 30);
     if (threadIdx.x != 0) return true;
+    icp_stamp(a.st, a.st->pass, 5);
     a.st->blocks_done = 0;
     a.st->searched_total += a.st->wl_count;
     if (a.st->pass < 64) a.st->searched_per_pass[a.st->pass] = a.st->wl_count;
     a.st->wl_count = 0; // the next pass builds its own work list
     icp_solve_and_update(a, a.st);
+    icp_stamp(a.st, a.st->pass, 6);
     return true;
 }
 template <bool PLANE>
@@ -954,6 +980,7 @@ __global__ void __launch_bounds__(kIcpThreads, 2) icp_loop_kernel(IcpArgs a, int
     {
         a.final_pass = pass == n_pass - 1;
         a.keep_far = pass == n_pass - 2;
+        if (blockIdx.x == 0 && threadIdx.x == 0) icp_stamp(a.st, pass, 0);
         __syncthreads();
         if (threadIdx.x < 16) sh.T[threadIdx.x] = a.st->T[threadIdx.x];
         else if (threadIdx.x < 32 && a.final_pass) sh.T_prev[threadIdx.x - 16] = a.st->T_prev[threadIdx.x - 16];
@@ -1006,8 +1033,10 @@ __global__ void __launch_bounds__(kIcpThreads, 2) icp_loop_kernel(IcpArgs a, int
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) searched += __shfl_xor_sync(0xffffffffu, searched, o);
         if ((threadIdx.x & 31) == 0 && searched) atomicAdd(&a.st->wl_count, searched);
+        if (blockIdx.x == 0 && threadIdx.x == 0) icp_stamp(a.st, pass, 1);
         // every thread reads back only the nn entries it wrote itself: no grid-wide ordering is needed before this
         const bool last = accumulate_pass<PLANE>(a, sh);
+        if (blockIdx.x == 0 && threadIdx.x == 0) icp_stamp(a.st, pass, 2);
         if (pass == n_pass - 1) break;
         if (threadIdx.x == 0)
         {
@@ -1019,8 +1048,348 @@ __global__ void __launch_bounds__(kIcpThreads, 2) icp_loop_kernel(IcpArgs a, int
             else
                 while (*(volatile unsigned int *)&a.st->pass <= (unsigned int)pass) { }
             __threadfence();
+            if (blockIdx.x == 0) icp_stamp(a.st, pass, 3);
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The pass loop, second persistent form (the default).  What the first form spends its time on, measured per converged pass
+// (27 us, profiles/r02_icp_phases_before.json): 5 us certifying, 8 us accumulating 29 double sums per thread and folding them with
+// 435 shuffle instructions per warp, then 14 us in which 295 CTAs wait for one to sum 296 partials (7 us), solve (3 us) and
+// release them.  This form removes the serial owner and the per-thread sums:
+//   * one CTA of 1024 threads per SM, one point per lane and trip; certified points go straight from the certificate to their
+//     Jacobian row (one loop, the neighbour index never leaves the registers), the others are searched on the spot by an
+//     out-of-line call that keeps the exact grid walk's registers out of the loop;
+//   * the sums are an 8x8 outer-product accumulation: every point contributes c c^T with c = (n, s' x n, r, 1) for point-to-plane
+//     (J^T J, J^T r and the count are entries of that matrix), c = (s', 1, t, 0) for point-to-point (the Kabsch sums), c = (err, 1)
+//     for the closing CountInliers.  A warp stages its 32 vectors in shared memory and folds them with eight DMMA.8x8x4
+//     instructions -- the FP64 tensor-core op used as a reduction primitive, exact products of floats, double accumulation --
+//     into a fragment of two doubles per lane that lives in registers for the whole pass: no per-thread accumulators, no shuffles;
+//   * every CTA publishes its 8x8 partial, announces it on one counter, waits until all have, and then EVERY CTA sums all
+//     partials in the same fixed order and solves the same 6x6 system redundantly: nobody waits for an owner, the pose never
+//     travels through global memory, and the result is deterministic and identical on all CTAs.
+// When the source is split across ranks the exchange needs an owner again: CTA 0 sums, exchanges the packet with the peers
+// (comm_allreduce) and publishes the combined packet; the others wait for it.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kLoop2Threads = 1024;
+constexpr int kLoop2Warps = kLoop2Threads / 32;
+constexpr int kLoop2Chunks = kLoop2Threads / 64; // groups that each sum every 16th partial
+
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// entry (row * 8 + col) of the 8x8 sum matrix that feeds component k of the 30-scalar packet, -1: none.
+// mode 0 point-to-plane, 1 point-to-point, 2 closing CountInliers
+__host__ __device__ constexpr int packet_source(int mode, int k)
+{
+    if (mode == 0)
+    {
+        if (k < 21)
+        {   // upper triangle of J^T J, row by row
+            int p = 0, first = 0;
+            while (k >= first + (6 - p)) { first += 6 - p; ++p; }
+            return p * 8 + p + (k - first);
+        }
+        if (k < 27) return (k - 21) * 8 + 6; // J^T r
+        return k == 29 ? 63 : -1;            // count
+    }
+    if (mode == 1)
+    {
+        if (k < 3) return k * 8 + 3;               // sum s'
+        if (k < 6) return 3 * 8 + 4 + (k - 3);     // sum t
+        if (k < 15) return ((k - 6) / 3) * 8 + 4 + (k - 6) % 3; // sum s' t^T
+        return k == 29 ? 3 * 8 + 3 : -1;
+    }
+    return k == 28 ? 1 : (k == 29 ? 9 : -1);       // sum err, count
+}
+__host__ __device__ constexpr unsigned long long packet_need_mask(int mode)
+{
+    unsigned long long m = 0;
+    for (int k = 0; k < 30; ++k)
+        if (packet_source(mode, k) >= 0) m |= 1ull << packet_source(mode, k);
+    return m;
+}
+
+struct Loop2Shared
+{
+    union
+    {
+        float stage[kLoop2Warps][32 * 8]; // during the trips: per warp, 32 points x 8 components
+        double wsum[kLoop2Warps][64];     // after the trips: per-warp 8x8 sums
+        double chunk[kLoop2Chunks][64];   // partial sums of the cross-CTA reduction
+    } u;
+    double sum64[64];   // the 8x8 sums over all CTAs
+    double packet[32];  // ... as the 30-scalar packet
+    float T[16], T_prev[16];
+    IcpGrid grid;
+};
+
+// the exact search of one query, out of line (its registers stay out of the streaming loop); updates the certificate
+__device__ __noinline__ int loop2_search(const IcpArgs &a, const IcpGrid *g, float guard, int i, float px, float py, float pz, int keep_far)
+{
+    const NnResult r = grid_nearest(*g, a.cell_start, a.sorted, px, py, pz, a.search_radius, guard);
+    a.nn_ref[i] = make_int2(r.index, r.index2);
+    a.qref[i] = make_float4(px, py, pz, a.certify ? r.budget : -1.0f);
+    a.budget2[i] = a.certify ? r.budget2 : -1.0f;
+    return r.index < 0 && keep_far ? -2 : r.index;
+}
+// geometry::TransformPoints for a rigid pose: w = ((0*x + 0*y) + 0*z) + 1 == 1 exactly, and x / 1 == x, so the three divisions
+// are skipped whenever w is exactly one (any other w takes them)
+__device__ __forceinline__ void transform_point_w1(const float *T, float sx, float sy, float sz, float &px, float &py, float &pz)
+{
+    const float w = row_xyz1(T[3], T[7], T[11], T[15], sx, sy, sz);
+    px = row_xyz1(T[0], T[4], T[8], T[12], sx, sy, sz);
+    py = row_xyz1(T[1], T[5], T[9], T[13], sx, sy, sz);
+    pz = row_xyz1(T[2], T[6], T[10], T[14], sx, sy, sz);
+    if (w != 1.0f) { px = fdiv(px, w); py = fdiv(py, w); pz = fdiv(pz, w); }
+}
+
+template <bool PLANE>
+__global__ void __launch_bounds__(kLoop2Threads, 1) icp_loop2_kernel(const __grid_constant__ IcpArgs a, int n_pass, double *partials, unsigned int *sync)
+{
+    __shared__ Loop2Shared sh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_cta = gridDim.x;
+    if (threadIdx.x < 16) sh.T[threadIdx.x] = a.st->T[threadIdx.x];
+    if (threadIdx.x == 32) sh.grid = a.st->grid;
+    __syncthreads();
+    const float guard = a.certify ? a.guard * sh.grid.h : 0.0f;
+    const int n_trips = (a.ns + 31) >> 5;
+    for (int pass = 0; pass < n_pass; ++pass)
+    {
+        const bool final_pass = pass == n_pass - 1;
+        const int keep_far = pass == n_pass - 2;
+        if (blockIdx.x == 0 && threadIdx.x == 0) icp_stamp(a.st, pass, 0);
+        float T[12]; // rows 0..2 of the pose: T[4 * c + r]
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) T[3 * c + r] = sh.T[4 * c + r];
+        const bool rigid = sh.T[3] == 0.0f && sh.T[7] == 0.0f && sh.T[11] == 0.0f && sh.T[15] == 1.0f;
+        double c0 = 0.0, c1 = 0.0;
+        unsigned int searched = 0;
+        float *stage = sh.u.stage[warp];
+        for (int trip = blockIdx.x * kLoop2Warps + warp; trip < n_trips; trip += n_cta * kLoop2Warps)
+        {
+            const int i = trip * 32 + lane;
+            float comp[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+            if (i < a.ns)
+            {
+                const float sx = __ldg(&a.src[3 * i]), sy = __ldg(&a.src[3 * i + 1]), sz = __ldg(&a.src[3 * i + 2]);
+                int nn = -1;
+                float px = 0.0f, py = 0.0f, pz = 0.0f;
+                if (!final_pass)
+                {
+                    if (rigid)
+                    {   // the products with the zero row still decide whether w is 1 or NaN (non-finite source points)
+                        px = row_xyz1(T[0], T[3], T[6], T[9], sx, sy, sz);
+                        py = row_xyz1(T[1], T[4], T[7], T[10], sx, sy, sz);
+                        pz = row_xyz1(T[2], T[5], T[8], T[11], sx, sy, sz);
+                        const float w = row_xyz1(0.0f, 0.0f, 0.0f, 1.0f, sx, sy, sz);
+                        if (w != 1.0f) { px = fdiv(px, w); py = fdiv(py, w); pz = fdiv(pz, w); }
+                    }
+                    else
+                        transform_point(sh.T, sx, sy, sz, px, py, pz);
+                    const float4 q = a.qref[i];
+                    const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
+                    const float moved = sqrtf(dx * dx + dy * dy + dz * dz) * (1.0f + 1e-6f);
+                    if (moved < q.w)
+                    {   // the certified strictly nearest neighbour (beyond the inlier radius the inlier test below rejects it)
+                        nn = a.nn_ref[i].x;
+                        if (nn < 0 && keep_far) nn = -2;
+                    }
+                    else if (moved < a.budget2[i])
+                    {
+                        const int2 jj = a.nn_ref[i];
+                        const float da = dist2_nanoflann(px, py, pz, __ldg(&a.tgt[3 * jj.x]), __ldg(&a.tgt[3 * jj.x + 1]), __ldg(&a.tgt[3 * jj.x + 2]));
+                        const float db = dist2_nanoflann(px, py, pz, __ldg(&a.tgt[3 * jj.y]), __ldg(&a.tgt[3 * jj.y + 1]), __ldg(&a.tgt[3 * jj.y + 2]));
+                        nn = (da < db || (da == db && jj.x < jj.y)) ? jj.x : jj.y;
+                    }
+                    else
+                    {
+                        nn = loop2_search(a, &sh.grid, guard, i, px, py, pz, keep_far);
+                        ++searched;
+                    }
+                    if (keep_far) a.nn[i] = nn; // the closing CountInliers re-tests exactly these (ICP.cpp:90,206)
+                }
+                else
+                {
+                    nn = a.nn[i];
+                    if (nn == -2) { nn = final_resolve_far(a, sh.grid, sh.T_prev, sh.T, i); a.nn[i] = nn; ++searched; }
+                }
+                bool inl = false;
+                if (nn >= 0)
+                {
+                    const float tx = __ldg(&a.tgt[3 * nn]), ty = __ldg(&a.tgt[3 * nn + 1]), tz = __ldg(&a.tgt[3 * nn + 2]);
+                    // CountInliers (ICP.cpp:19-21): (R*s + t - target).squaredNorm() in float, compared as double
+                    const float ex = fsub(fadd(fadd(fmul(T[0], sx), fadd(fmul(T[3], sy), fmul(T[6], sz))), T[9]), tx);
+                    const float ey = fsub(fadd(fadd(fmul(T[1], sx), fadd(fmul(T[4], sy), fmul(T[7], sz))), T[10]), ty);
+                    const float ez = fsub(fadd(fadd(fmul(T[2], sx), fadd(fmul(T[5], sy), fmul(T[8], sz))), T[11]), tz);
+                    const float err = fadd(fmul(ex, ex), fadd(fmul(ey, ey), fmul(ez, ez)));
+                    inl = (double)err < a.sq_threshold;
+                    if (inl)
+                    {
+                        if (final_pass) { comp[0] = err; comp[1] = 1.0f; }
+                        else if (PLANE)
+                        {
+                            // EstimateRigidTransformationPointToPlane (ICP.cpp:121-136): row = [n ; s' x n], r = n.s' - n.t, in float
+                            const float nx = __ldg(&a.nrm[3 * nn]), ny = __ldg(&a.nrm[3 * nn + 1]), nz = __ldg(&a.nrm[3 * nn + 2]);
+                            comp[0] = nx; comp[1] = ny; comp[2] = nz;
+                            comp[3] = fsub(fmul(py, nz), fmul(pz, ny));
+                            comp[4] = fsub(fmul(pz, nx), fmul(px, nz));
+                            comp[5] = fsub(fmul(px, ny), fmul(py, nx));
+                            comp[6] = fsub(dot3(nx, ny, nz, px, py, pz), dot3(nx, ny, nz, tx, ty, tz));
+                            comp[7] = 1.0f;
+                        }
+                        else
+                        {   // PointToPoint (ICP.cpp:78-84): Kabsch sums over (transformed source, target)
+                            comp[0] = px; comp[1] = py; comp[2] = pz; comp[3] = 1.0f;
+                            comp[4] = tx; comp[5] = ty; comp[6] = tz;
+                        }
+                    }
+                }
+                if (final_pass) a.inlier[i] = inl;
+            }
+            // the warp's 32 vectors -> shared memory -> eight 8x8x4 outer-product accumulations (A = B^T = 8 components x 4 points)
+            *reinterpret_cast<float4 *>(stage + lane * 8) = make_float4(comp[0], comp[1], comp[2], comp[3]);
+            *reinterpret_cast<float4 *>(stage + lane * 8 + 4) = make_float4(comp[4], comp[5], comp[6], comp[7]);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+            {
+                const double v = (double)stage[(4 * j + (lane & 3)) * 8 + (lane >> 2)];
+                dmma_8x8x4(c0, c1, v, v);
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) searched += __shfl_xor_sync(0xffffffffu, searched, o);
+        if (lane == 0 && searched)
+        {
+            atomicAdd(&a.st->searched_total, (unsigned long long)searched);
+            if (pass < 64) atomicAdd(&a.st->searched_per_pass[pass], searched);
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) icp_stamp(a.st, pass, 1);
+        // ---- CTA partial: lane L of a warp holds entries 2L, 2L+1 of the row-major 8x8 matrix ----
+        __syncthreads(); // every warp is done with its staging area (aliased below)
+        *reinterpret_cast<double2 *>(&sh.u.wsum[warp][2 * lane]) = make_double2(c0, c1);
+        __syncthreads();
+        const unsigned long long need = final_pass ? packet_need_mask(2) : packet_need_mask(PLANE ? 0 : 1);
+        const int e = threadIdx.x & 63, grp = threadIdx.x >> 6;
+        const bool needed = (need >> e) & 1ull;
+        double v = 0.0;
+        if (needed && grp < 8)
+            v = (sh.u.wsum[4 * grp][e] + sh.u.wsum[4 * grp + 1][e]) + (sh.u.wsum[4 * grp + 2][e] + sh.u.wsum[4 * grp + 3][e]);
+        __syncthreads();
+        if (grp < 8) sh.u.chunk[grp][e] = v;
+        __syncthreads();
+        double *mine = partials + ((size_t)(pass & 1) * n_cta + blockIdx.x) * 64;
+        if (threadIdx.x < 64 && needed)
+        {
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t += sh.u.chunk[k][e];
+            __stcg(&mine[e], t);
+        }
+        __threadfence();
+        __syncthreads();
+        if (blockIdx.x == 0 && threadIdx.x == 0) icp_stamp(a.st, pass, 2);
+        // ---- arrive, wait for everybody ----
+        if (threadIdx.x == 0)
+        {
+            atomicAdd(sync, 1u);
+            const unsigned int want = (unsigned int)(pass + 1) * (unsigned int)n_cta;
+            while (*(volatile unsigned int *)sync < want) { }
+            __threadfence();
+        }
+        __syncthreads();
+        if (blockIdx.x == 0 && threadIdx.x == 0) icp_stamp(a.st, pass, 4);
+        // ---- all partials -> the 8x8 sums, in one fixed order (every CTA, or CTA 0 alone when ranks exchange packets) ----
+        const bool owner_mode = a.comm.world > 1;
+        if (!owner_mode || blockIdx.x == 0)
+        {
+            const double *all = partials + (size_t)(pass & 1) * n_cta * 64;
+            double t = 0.0;
+            if (needed)
+            {
+                if (n_cta <= kLoop2Chunks * 10)
+                {
+                    double ld[10];
+#pragma unroll
+                    for (int u = 0; u < 10; ++u)
+                    {
+                        const int b = grp + u * kLoop2Chunks;
+                        ld[u] = b < n_cta ? __ldcg(&all[(size_t)b * 64 + e]) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 10; ++u) t += ld[u];
+                }
+                else
+                    for (int b = grp; b < n_cta; b += kLoop2Chunks) t += __ldcg(&all[(size_t)b * 64 + e]);
+            }
+            sh.u.chunk[grp][e] = t;
+            __syncthreads();
+            if (threadIdx.x < 64)
+            {
+                double tot = 0.0;
+                if (needed)
+#pragma unroll
+                    for (int k = 0; k < kLoop2Chunks; ++k) tot += sh.u.chunk[k][e];
+                sh.sum64[e] = tot;
+            }
+            __syncthreads();
+            if (threadIdx.x < 32)
+            {
+                const int mode = final_pass ? 2 : (PLANE ? 0 : 1);
+                int src = -1;
+                if (threadIdx.x < 30) src = mode == 0 ? packet_source(0, threadIdx.x) : (mode == 1 ? packet_source(1, threadIdx.x) : packet_source(2, threadIdx.x));
+                sh.packet[threadIdx.x] = src >= 0 ? sh.sum64[src] : 0.0;
+            }
+            __syncthreads();
+        }
+        if (owner_mode)
+        {
+            if (blockIdx.x == 0)
+            {
+                if (threadIdx.x == 0) a.st->n_inliers_local = (unsigned long long)(sh.packet[29] + 0.5);
+                comm_allreduce(a.comm, sh.packet, 30);
+                if (threadIdx.x < 30) __stcg(&a.st->packet[threadIdx.x], sh.packet[threadIdx.x]);
+                __threadfence();
+                __syncthreads();
+                if (threadIdx.x == 0) atomicExch(&a.st->pass, (unsigned int)(pass + 1));
+            }
+            else
+            {
+                if (threadIdx.x == 0)
+                {
+                    while (*(volatile unsigned int *)&a.st->pass <= (unsigned int)pass) { }
+                    __threadfence();
+                }
+                __syncthreads();
+                if (threadIdx.x < 30) sh.packet[threadIdx.x] = __ldcg(&a.st->packet[threadIdx.x]);
+                __syncthreads();
+            }
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) icp_stamp(a.st, pass, 5);
+        // ---- the same solve on every CTA ----
+        if (threadIdx.x == 0 && !final_pass)
+            icp_solve_core(sh.packet, PLANE, sh.T, sh.T_prev);
+        if (blockIdx.x == 0 && threadIdx.x == 0) { icp_stamp(a.st, pass, 6); icp_stamp(a.st, pass, 3); }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        IcpState *st = a.st;
+        st->sum_error = sh.packet[28];
+        st->n_inliers = (unsigned long long)(sh.packet[29] + 0.5);
+        if (a.comm.world <= 1) st->n_inliers_local = st->n_inliers;
+        st->iteration = (int)(n_pass - 1);
+        for (int k = 0; k < 16; ++k) { st->T[k] = sh.T[k]; st->T_prev[k] = sh.T_prev[k]; }
+        for (int k = 0; k < 30; ++k) st->packet[k] = sh.packet[k];
+        st->pass = (unsigned int)n_pass;
     }
 }
 
@@ -1306,6 +1675,9 @@ struct opb_icp
     bool profiling = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     int coop_ctas_per_sm = 0; // resident CTAs per SM of the persistent loop kernel; 0: cooperative launch unavailable
+    bool loop2_ok = false;    // the second persistent form (one CTA of 1024 threads per SM) can be launched cooperatively
+    double *d_partials2 = nullptr; // 2 (pass parity) x SMs x 64: per-CTA 8x8 sums of icp_loop2_kernel
+    unsigned int *d_loop_sync = nullptr;
     int grid_ctas_per_sm = 0; // the same for the fused grid construction
     unsigned int *d_grid_sync = nullptr;
     bool peers_share_device = false; // a peer rank runs on this very GPU: two persistent grids could not be resident together
@@ -1359,7 +1731,7 @@ static int icp_reserve(opb_icp *c, size_t ns, size_t nt)
 }
 
 // uniform grid over the nt points in c->d_tgt (bounding box in c->d_state already reset): cell_start + cell-sorted points
-static int icp_build_grid(opb_icp *c, size_t nt)
+static int icp_build_grid(opb_icp *c, const float *d_tgt, size_t nt)
 {
     cudaStream_t s = c->stream;
     // Cap on the number of grid cells: the construction streams over all of them (clear, count, scan) while only a few
@@ -1375,7 +1747,7 @@ static int icp_build_grid(opb_icp *c, size_t nt)
         // one cooperative launch, grid-wide barriers between the phases (not when a peer rank shares this GPU: its kernels may
         // be spinning on our packet while ours waits for the whole device to be free)
         OPB_CUDA(cudaMemsetAsync(c->d_grid_sync, 0, sizeof(unsigned int), s));
-        const float *pts = c->d_tgt;
+        const float *pts = d_tgt;
         int n = (int)nt;
         float min_cell = 0.0f;
         unsigned int mc = (unsigned int)max_cells;
@@ -1385,14 +1757,14 @@ static int icp_build_grid(opb_icp *c, size_t nt)
         return OPB_OK;
     }
     const int nb_t = (int)((nt + 255) / 256) < c->sm_count * 8 ? (int)((nt + 255) / 256) : c->sm_count * 8;
-    icp_bbox_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)nt, c->d_state);
+    icp_bbox_kernel<<<nb_t, 256, 0, s>>>(d_tgt, (int)nt, c->d_state);
     icp_grid_setup_kernel<<<1, 1, 0, s>>>(c->d_state, (int)nt, 0.0f, (unsigned int)max_cells);
     icp_clear_kernel<<<c->sm_count * 8, 256, 0, s>>>(c->d_state, c->d_cell_count);
-    icp_count_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)nt, c->d_state, c->d_cell_count, c->d_point_cell);
+    icp_count_kernel<<<nb_t, 256, 0, s>>>(d_tgt, (int)nt, c->d_state, c->d_cell_count, c->d_point_cell);
     icp_tile_sums_kernel<<<c->sm_count * 2, 1024, 0, s>>>(c->d_state, c->d_cell_count, c->d_tile_sums);
     icp_scan_tiles_kernel<<<1, 1024, 0, s>>>(c->d_state, c->d_tile_sums);
     icp_scan_apply_kernel<<<c->sm_count * 2, 1024, 0, s>>>(c->d_state, c->d_cell_count, c->d_tile_sums, c->d_cell_start);
-    icp_scatter_kernel<<<nb_t, 256, 0, s>>>(c->d_tgt, (int)nt, c->d_point_cell, c->d_cell_start, c->d_cell_count, c->d_sorted);
+    icp_scatter_kernel<<<nb_t, 256, 0, s>>>(d_tgt, (int)nt, c->d_point_cell, c->d_cell_start, c->d_cell_count, c->d_sorted);
     OPB_CUDA(cudaGetLastError());
     return OPB_OK;
 }
@@ -1429,11 +1801,36 @@ int opb_icp_create(int device, void *stream, opb_icp **out)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess)
     {
+        // Load every kernel of the pass loop now.  With CUDA's lazy module loading the FIRST launch of a kernel takes a context-wide
+        // lock and may wait for the device to drain; when two workspaces of one process exchange packets (a kernel of one spins
+        // until the other's has run), a first launch in the middle of a call would stall the other thread's launches behind that
+        // lock and the exchange would never complete.
+        cudaFuncAttributes fa;
+        const void *fns[] = {(const void *)icp_certify_kernel, (const void *)icp_search_kernel, (const void *)icp_final_resolve_kernel,
+                             (const void *)icp_accumulate_kernel<true>, (const void *)icp_accumulate_kernel<false>,
+                             (const void *)icp_final_sums_kernel, (const void *)icp_final_reduce_kernel, (const void *)icp_pair_count_kernel,
+                             (const void *)icp_pair_scan_kernel, (const void *)icp_pair_write_kernel, (const void *)icp_scale_kernel,
+                             (const void *)icp_bbox_kernel, (const void *)icp_grid_setup_kernel, (const void *)icp_clear_kernel,
+                             (const void *)icp_count_kernel, (const void *)icp_tile_sums_kernel, (const void *)icp_scan_tiles_kernel,
+                             (const void *)icp_scan_apply_kernel, (const void *)icp_scatter_kernel, (const void *)icp_grid_build_kernel,
+                             (const void *)icp_loop_kernel<true>, (const void *)icp_loop_kernel<false>,
+                             (const void *)icp_loop2_kernel<true>, (const void *)icp_loop2_kernel<false>};
+        for (const void *fn : fns)
+            if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, fn);
+    }
+    if (e == cudaSuccess)
+    {
         int coop = 0, occ_plane = 0, occ_point = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
         if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_plane, icp_loop_kernel<true>, kIcpThreads, 0) == cudaSuccess &&
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_point, icp_loop_kernel<false>, kIcpThreads, 0) == cudaSuccess)
             c->coop_ctas_per_sm = occ_plane < occ_point ? occ_plane : occ_point;
+        int occ2a = 0, occ2b = 0;
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2a, icp_loop2_kernel<true>, kLoop2Threads, 0) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2b, icp_loop2_kernel<false>, kLoop2Threads, 0) == cudaSuccess && occ2a >= 1 && occ2b >= 1 &&
+            cudaMalloc(&c->d_partials2, (size_t)2 * c->sm_count * 64 * sizeof(double)) == cudaSuccess &&
+            cudaMalloc(&c->d_loop_sync, sizeof(unsigned int)) == cudaSuccess)
+            c->loop2_ok = true;
         int occ_grid = 0;
         if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_grid, icp_grid_build_kernel, 1024, 0) == cudaSuccess &&
             cudaMalloc(&c->d_grid_sync, sizeof(unsigned int)) == cudaSuccess)
@@ -1459,7 +1856,7 @@ void opb_icp_destroy(opb_icp *c)
     cudaFree(c->d_cell_count); cudaFree(c->d_tile_sums); cudaFree(c->d_cell_start); cudaFree(c->d_nn); cudaFree(c->d_pairs);
     cudaFree(c->d_inlier); cudaFree(c->d_partials); cudaFree(c->d_state); cudaFree(c->d_mailbox);
     cudaFree(c->d_qref); cudaFree(c->d_nn_ref); cudaFree(c->d_worklist); cudaFree(c->d_budget2); cudaFree(c->d_pair_tiles);
-    cudaFree(c->d_grid_sync);
+    cudaFree(c->d_grid_sync); cudaFree(c->d_partials2); cudaFree(c->d_loop_sync);
     if (c->h_state) cudaFreeHost(c->h_state);
     for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 3; ++i) if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
@@ -1483,9 +1880,12 @@ int opb_icp_last_timing(opb_icp *c, float *grid_build_ms, float *iterations_ms)
     return OPB_OK;
 }
 
-// src/tgt/nrm may be host or device pointers (cudaMemcpyDefault)
+// src/tgt/nrm may be host or device pointers (cudaMemcpyDefault).  borrow: they are device arrays that stay valid and unchanged
+// for the whole (synchronous) call -- opb_cloud buffers -- and are used where they lie (no copy); ready_a / ready_b: events the
+// work stream has to wait for before it reads them.
 static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, const float *nrm, size_t nt, const float *init_T,
-                   const opb_icp_params *par, opb_icp_result *res, int32_t *pairs, size_t pairs_cap, bool point_to_plane)
+                   const opb_icp_params *par, opb_icp_result *res, int32_t *pairs, size_t pairs_cap, bool point_to_plane,
+                   bool borrow = false, cudaEvent_t ready_a = nullptr, cudaEvent_t ready_b = nullptr)
 {
     if (!c || !src || !tgt || !init_T || !par || !res) { set_error("NULL argument"); return OPB_ERR_INVALID; }
     memset(res, 0, sizeof(*res));
@@ -1500,18 +1900,22 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     }
     if (nt == 0 || (ns == 0 && c->comm.world <= 1)) { set_error("empty point cloud"); res->status = OPB_ERR_INVALID; return OPB_ERR_INVALID; }
     OPB_CUDA(cudaSetDevice(c->device));
-    int rc = icp_reserve(c, ns, nt);
+    if (borrow && par->scaling != 1.0) borrow = false; // PointToPoint scales its own copies of both clouds (ICP.cpp:33-42)
+    int rc = icp_reserve(c, ns, nt); // (borrowed clouds leave the workspace's own copies unused: 12 bytes per point)
     if (rc) return rc;
     cudaStream_t s = c->stream;
+    const float *d_src = borrow ? src : c->d_src, *d_tgt = borrow ? tgt : c->d_tgt, *d_nrm = borrow ? nrm : c->d_nrm;
+    if (ready_a) OPB_CUDA(cudaStreamWaitEvent(s, ready_a, 0));
+    if (ready_b) OPB_CUDA(cudaStreamWaitEvent(s, ready_b, 0));
     // The target goes first on the work stream (the grid is built from it); the source and the normals follow on the copy
     // stream and arrive under the grid construction: the first certify pass waits for the source, the first accumulation
     // for the normals.  (Calls are synchronous, so nothing of an earlier call can still be reading these buffers.)
-    OPB_CUDA(cudaMemcpyAsync(c->d_tgt, tgt, nt * 3 * sizeof(float), cudaMemcpyDefault, s));
+    if (!borrow) OPB_CUDA(cudaMemcpyAsync(c->d_tgt, tgt, nt * 3 * sizeof(float), cudaMemcpyDefault, s));
     OPB_CUDA(cudaEventRecord(c->ev_copy[0], s));
     OPB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_copy[0], 0)); // keep the link for the target alone first
-    if (ns) OPB_CUDA(cudaMemcpyAsync(c->d_src, src, ns * 3 * sizeof(float), cudaMemcpyDefault, c->copy_stream));
+    if (ns && !borrow) OPB_CUDA(cudaMemcpyAsync(c->d_src, src, ns * 3 * sizeof(float), cudaMemcpyDefault, c->copy_stream));
     OPB_CUDA(cudaEventRecord(c->ev_copy[1], c->copy_stream));
-    if (point_to_plane) OPB_CUDA(cudaMemcpyAsync(c->d_nrm, nrm, nt * 3 * sizeof(float), cudaMemcpyDefault, c->copy_stream));
+    if (point_to_plane && !borrow) OPB_CUDA(cudaMemcpyAsync(c->d_nrm, nrm, nt * 3 * sizeof(float), cudaMemcpyDefault, c->copy_stream));
     OPB_CUDA(cudaEventRecord(c->ev_copy[2], c->copy_stream));
     const float scaling = (float)par->scaling;
     if (par->scaling != 1.0)
@@ -1528,12 +1932,12 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     OPB_CUDA(cudaMemcpyAsync(c->d_state, h, sizeof(IcpState), cudaMemcpyHostToDevice, s));
     if (c->profiling) OPB_CUDA(cudaEventRecord(c->ev[0], s));
     // grid over the target (opb_icp_estimate_normals builds the same grid over its cloud)
-    rc = icp_build_grid(c, nt);
+    rc = icp_build_grid(c, d_tgt, nt);
     if (rc) return rc;
     if (c->profiling) OPB_CUDA(cudaEventRecord(c->ev[1], s));
     // iterations
     IcpArgs a;
-    a.src = c->d_src; a.tgt = c->d_tgt; a.nrm = point_to_plane ? c->d_nrm : nullptr;
+    a.src = d_src; a.tgt = d_tgt; a.nrm = point_to_plane ? d_nrm : nullptr;
     a.cell_start = c->d_cell_start; a.sorted = c->d_sorted; a.nn = c->d_nn; a.partials = c->d_partials; a.st = c->d_state;
     a.ns = (int)ns;
     a.search_radius = (float)(par->threshold * (1.0 + 1e-3)) + 1e-6f;
@@ -1558,7 +1962,22 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     static const int k_persistent = getenv("OPB_ICP_PERSISTENT") ? atoi(getenv("OPB_ICP_PERSISTENT")) : 1;
     bool looped = false;
     c->last_launches = 8 + 3 * (par->max_iteration + 1) + 2 + (pairs && pairs_cap && ns ? 3 : 0) + (par->scaling != 1.0 ? 2 : 0);
-    if (k_persistent && c->coop_ctas_per_sm > 0 && !c->peers_share_device)
+    if (k_persistent == 1 && c->loop2_ok && !c->peers_share_device)
+    {
+        // second persistent form: one CTA of 1024 threads per SM, all passes in one cooperative launch
+        const int nb_trips = ns ? (int)((ns + 31) / 32 + kLoop2Warps - 1) / kLoop2Warps : 1;
+        const int nb_l = nb_trips < c->sm_count ? nb_trips : c->sm_count;
+        int n_pass = par->max_iteration + 1;
+        OPB_CUDA(cudaStreamWaitEvent(s, c->ev_copy[1], 0)); // source points uploaded
+        OPB_CUDA(cudaStreamWaitEvent(s, c->ev_copy[2], 0)); // target normals uploaded
+        OPB_CUDA(cudaMemsetAsync(c->d_loop_sync, 0, sizeof(unsigned int), s));
+        void *kargs[] = {(void *)&a, (void *)&n_pass, (void *)&c->d_partials2, (void *)&c->d_loop_sync};
+        const void *fn = point_to_plane ? (const void *)icp_loop2_kernel<true> : (const void *)icp_loop2_kernel<false>;
+        OPB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(nb_l), dim3(kLoop2Threads), kargs, 0, s));
+        looped = true;
+        c->last_launches = (c->grid_ctas_per_sm > 0 && !c->peers_share_device ? 1 : 8) + 1 + 2 + (pairs && pairs_cap && ns ? 3 : 0) + (par->scaling != 1.0 ? 2 : 0);
+    }
+    else if (k_persistent && c->coop_ctas_per_sm > 0 && !c->peers_share_device)
     {
         // one cooperative launch for all passes; grid = the accumulate grid (2 CTAs per SM), which fixes the order of the sums
         const int per_sm = c->coop_ctas_per_sm < k_accum ? c->coop_ctas_per_sm : k_accum;
@@ -1590,7 +2009,7 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
         else icp_accumulate_kernel<false><<<nb_a, kIcpThreads, 0, s>>>(a);
     }
     OPB_CUDA(cudaMemcpyAsync(h, c->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
-    icp_final_sums_kernel<<<nb_a, kIcpThreads, 0, s>>>(c->d_src, c->d_tgt, c->d_nn, c->d_inlier, (int)ns, scaling, c->d_partials);
+    icp_final_sums_kernel<<<nb_a, kIcpThreads, 0, s>>>(d_src, d_tgt, c->d_nn, c->d_inlier, (int)ns, scaling, c->d_partials);
     icp_final_reduce_kernel<<<1, kIcpThreads, 0, s>>>(c->d_partials, nb_a, c->d_state, c->comm);
     if (pairs && pairs_cap && ns)
     {
@@ -1665,6 +2084,28 @@ int opb_icp_point_to_point(opb_icp *c, const float *src_xyz, size_t ns, const fl
 {
     return icp_run(c, src_xyz, ns, tgt_xyz, nullptr, nt, init_T, params, result, pairs, pairs_cap, false);
 }
+static int icp_run_clouds(opb_icp *c, opb_cloud *source, opb_cloud *target, const float *init_T, const opb_icp_params *par,
+                          opb_icp_result *res, int32_t *pairs, size_t pairs_cap, bool plane)
+{
+    if (!c || !source || !target) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    if (source->device != c->device || target->device != c->device) { set_error("clouds and workspace live on different devices"); return OPB_ERR_INVALID; }
+    size_t ns = 0, nt = 0;
+    int rc = cloud_wait(source, &ns);
+    if (rc == OPB_OK) rc = cloud_wait(target, &nt);
+    if (rc) return rc;
+    return icp_run(c, source->d_xyz, ns, target->d_xyz, plane && target->has_normals ? target->d_nrm : nullptr, nt, init_T, par, res, pairs,
+                   pairs_cap, plane, true);
+}
+int opb_icp_point_to_plane_clouds(opb_icp *c, opb_cloud *source, opb_cloud *target, const float init_T[16], const opb_icp_params *params,
+                                  opb_icp_result *result, int32_t *pairs, size_t pairs_cap)
+{
+    return icp_run_clouds(c, source, target, init_T, params, result, pairs, pairs_cap, true);
+}
+int opb_icp_point_to_point_clouds(opb_icp *c, opb_cloud *source, opb_cloud *target, const float init_T[16], const opb_icp_params *params,
+                                  opb_icp_result *result, int32_t *pairs, size_t pairs_cap)
+{
+    return icp_run_clouds(c, source, target, init_T, params, result, pairs, pairs_cap, false);
+}
 int opb_icp_last_search_count(opb_icp *c, uint64_t *full_searches)
 {
     if (!c || !full_searches) { set_error("NULL argument"); return OPB_ERR_INVALID; }
@@ -1687,7 +2128,7 @@ int opb_icp_estimate_normals(opb_icp *c, const float *xyz, size_t n, float radiu
     memset(h, 0, sizeof(IcpState));
     for (int a = 0; a < 3; ++a) { h->bbox_enc[a] = 0xFFFFFFFFu; h->bbox_enc[3 + a] = 0u; }
     OPB_CUDA(cudaMemcpyAsync(c->d_state, h, sizeof(IcpState), cudaMemcpyHostToDevice, s));
-    rc = icp_build_grid(c, n);
+    rc = icp_build_grid(c, c->d_tgt, n);
     if (rc) return rc;
     // the normals land in the workspace's normal buffer, then go to wherever the caller's pointer lives
     const size_t knn_smem = (size_t)knn * kKnnThreads * (sizeof(float) + sizeof(int));
@@ -1779,6 +2220,13 @@ int opb_icp_comm_detach(opb_icp *c)
     OPB_CUDA(cudaStreamSynchronize(c->stream));
     c->comm = IcpComm{};
     c->peers_share_device = false;
+    return OPB_OK;
+}
+int opb_icp_last_stamps(opb_icp *c, uint64_t *stamps, int passes)
+{
+    if (!c || !stamps) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    for (int p = 0; p < passes && p < kStampPasses; ++p)
+        for (int k = 0; k < 8; ++k) stamps[p * 8 + k] = c->h_state->stamps[p][k];
     return OPB_OK;
 }
 int opb_icp_last_prev_pose(opb_icp *c, float T[16])

@@ -273,6 +273,94 @@ def _run(source: PointCloud, target: PointCloud, init_T, icp_para: ICPParameter,
     return out
 
 
+class DeviceCloud:
+    """geometry::PointCloud kept in HBM (opb_cloud): built on the device from a depth image with PointCloud::LoadFromDepth's
+    arithmetic (reference src/Geometry/PointCloud.cpp:72-100), reused as source of one registration, target of the next and as
+    the frame CubeHandler.IntegrateCloud integrates.  Loads only enqueue; `size` waits."""
+
+    def __init__(self, device: int = 0, stream=None):
+        self._h = C.c_void_p()
+        self.device = device
+        capi.check(capi.lib.opb_cloud_create(device, C.c_void_p(stream) if stream else None, C.byref(self._h)))
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            capi.lib.opb_cloud_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        self.close()
+
+    def LoadFromDepth(self, depth, camera, bgr=None):
+        """depth [H, W] float32 metres or uint16 raw; bgr [H, W, 3] uint8 optional (kept for IntegrateCloud).  Arrays must stay
+        alive until `size` (or a call that uses the cloud) has returned: they are held here."""
+        depth = np.ascontiguousarray(depth)
+        dt = capi.OPB_DEPTH_F32 if depth.dtype == np.float32 else (capi.OPB_DEPTH_U16 if depth.dtype == np.uint16 else -1)
+        bgr = None if bgr is None else np.ascontiguousarray(bgr, np.uint8)
+        self._keep = [depth, bgr]
+        capi.check(capi.lib.opb_cloud_load_from_depth(self._h, _ptr(depth), dt, _ptr(bgr), camera.fx, camera.fy, camera.cx, camera.cy,
+                                                      camera.width, camera.height, camera.depth_scale))
+        return self
+
+    def SetPoints(self, points):
+        pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        self._keep = [pts]
+        capi.check(capi.lib.opb_cloud_set_points(self._h, _ptr(pts), len(pts)))
+        return self
+
+    def SetNormals(self, normals):
+        n = np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+        self._keep.append(n)
+        capi.check(capi.lib.opb_cloud_set_normals(self._h, _ptr(n), len(n)))
+        return self
+
+    @property
+    def size(self) -> int:
+        n = C.c_size_t(0)
+        capi.check(capi.lib.opb_cloud_size(self._h, C.byref(n)))
+        self._keep = []
+        return n.value
+
+    def Download(self, normals: bool = False):
+        n = self.size
+        pts = np.zeros((n, 3), np.float32)
+        nrm = np.zeros((n, 3), np.float32) if normals else None
+        capi.check(capi.lib.opb_cloud_download(self._h, _ptr(pts), _ptr(nrm)))
+        return (pts, nrm) if normals else pts
+
+
+def _run_clouds(source: DeviceCloud, target: DeviceCloud, init_T, icp_para: ICPParameter, plane: bool, workspace=None, want_pairs: bool = True):
+    ws = workspace if workspace is not None else _Workspace.get(source.device)
+    par = capi.IcpParams(icp_para.max_iteration, icp_para.threshold, icp_para.scaling)
+    res = capi.IcpResult()
+    T0 = np.ascontiguousarray(np.asarray(init_T, np.float32).reshape(4, 4).T).reshape(16)
+    ns = source.size
+    pairs = np.zeros((max(ns, 1), 2), np.int32) if want_pairs else None
+    fn = capi.lib.opb_icp_point_to_plane_clouds if plane else capi.lib.opb_icp_point_to_point_clouds
+    rc = fn(ws, source._h, target._h, _ptr(T0), C.byref(par), C.byref(res), _ptr(pairs), ns if want_pairs else 0)
+    if rc == capi.OPB_ERR_INVALID and res.status == capi.OPB_ERR_INVALID:
+        print(capi.lib.opb_last_error().decode())
+        return RegistrationResult(ok=False)
+    capi.check(rc)
+    out = RegistrationResult()
+    out.T = np.array(res.T[:], np.float32).reshape(4, 4).T.copy()
+    out.T_iterated = np.array(res.T_iterated[:], np.float32).reshape(4, 4).T.copy()
+    out.correspondence_set_index = pairs[: res.n_local_pairs].copy() if want_pairs else np.zeros((0, 2), np.int32)
+    out.rmse = res.rmse
+    return out
+
+
+def PointToPlaneClouds(source: DeviceCloud, target: DeviceCloud, init_T=np.eye(4), icp_para=ICPParameter(), **kw):
+    """registration::PointToPlane (ICP.cpp:146-224) on device-resident clouds (the target carries its normals)"""
+    return _run_clouds(source, target, init_T, icp_para, True, **kw)
+
+
+def PointToPointClouds(source: DeviceCloud, target: DeviceCloud, init_T=np.eye(4), icp_para=ICPParameter(), **kw):
+    """registration::PointToPoint (ICP.cpp:31-107) on device-resident clouds"""
+    return _run_clouds(source, target, init_T, icp_para, False, **kw)
+
+
 def PointToPlane(source, target, init_T=np.eye(4), icp_para=ICPParameter(), **kw):
     """registration::PointToPlane (ICP.cpp:146-224)"""
     return _run(source, target, init_T, icp_para, True, **kw)

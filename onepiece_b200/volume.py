@@ -100,6 +100,12 @@ class CubeHandler:
         p = pose_colmajor(pose)
         capi.check(capi.lib.opb_volume_integrate(self._h, _ptr(depth), depth_type_of(depth), _ptr(rgb), _ptr(p)))
 
+    def IntegrateCloud(self, cloud, pose):
+        """CubeHandler::IntegrateImage with the depth + colour images a registration.DeviceCloud was loaded from (already in
+        HBM); synchronous."""
+        p = pose_colmajor(pose)
+        capi.check(capi.lib.opb_volume_integrate_cloud(self._h, cloud._h, _ptr(p)))
+
     def IntegrateImageAsync(self, depth_ptr, depth_type, bgr_ptr, pose_cm):
         capi.check(capi.lib.opb_volume_integrate_async(self._h, _ptr(depth_ptr), depth_type, _ptr(bgr_ptr), _ptr(pose_cm)))
 

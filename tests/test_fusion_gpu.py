@@ -167,7 +167,9 @@ def test_split_icp_workspaces_on_one_device(world, plane):
     assert np.array_equal(np.concatenate(pairs), whole.correspondence_set_index)
     assert np.abs(out[0][1].T_iterated - whole.T_iterated).max() < 1e-6
     assert np.abs(out[0][1].T - whole.T).max() < 1e-6
-    assert abs(out[0][1].rmse - whole.rmse) < 1e-9
+    # (the whole call sums exact products in the persistent loop's 8x8 accumulation, the split one float-rounded products:
+    # the iterated pose may differ in its last float bit, the rmse with it)
+    assert abs(out[0][1].rmse - whole.rmse) < 1e-7 * whole.rmse + 1e-12
     # a collective call that a peer never makes fails after the time limit instead of hanging
     if world == 2 and plane:
         with pytest.raises(capi.OpbError) as e:
