@@ -755,12 +755,21 @@ __device__ bool icp_solve_core(const double *pk, bool plane, float *T, float *T_
     if (plane)
     {
         double JTJ[36], nJTr[6], x[6];
-        int k = 0;
+        // (fully unrolled: every index is a compile-time constant, the system stays in registers on the common path)
+#pragma unroll
         for (int p = 0; p < 6; ++p)
-            for (int q = p; q < 6; ++q) { JTJ[p * 6 + q] = pk[k]; JTJ[q * 6 + p] = pk[k]; ++k; }
+#pragma unroll
+            for (int q = p; q < 6; ++q)
+            {
+                const double v = pk[p * 6 - (p * (p - 1)) / 2 + (q - p)]; // position of (p, q) in the row-wise upper triangle
+                JTJ[p * 6 + q] = v;
+                JTJ[q * 6 + p] = v;
+            }
+#pragma unroll
         for (int p = 0; p < 6; ++p) nJTr[p] = -pk[21 + p];
         linalg::solve_normal_equations6(JTJ, nJTr, x);
         // the reference's x is float32
+#pragma unroll
         for (int p = 0; p < 6; ++p) x[p] = (double)(float)x[p];
         linalg::se3_exp(x, dT);
     }
@@ -771,12 +780,17 @@ __device__ bool icp_solve_core(const double *pk, bool plane, float *T, float *T_
     }
     // start_T = tmp_T * start_T in float (ICP.cpp:86,198)
     float dTf[16], Tn[16];
+#pragma unroll
     for (int r = 0; r < 4; ++r)
+#pragma unroll
         for (int c = 0; c < 4; ++c) dTf[c * 4 + r] = (float)dT[r * 4 + c];
+#pragma unroll
     for (int c = 0; c < 4; ++c)
+#pragma unroll
         for (int r = 0; r < 4; ++r)
             Tn[c * 4 + r] = fadd(fadd(fadd(fmul(dTf[r], T[c * 4]), fmul(dTf[4 + r], T[c * 4 + 1])), fmul(dTf[8 + r], T[c * 4 + 2])),
                                  fmul(dTf[12 + r], T[c * 4 + 3]));
+#pragma unroll
     for (int e = 0; e < 16; ++e) T[e] = Tn[e];
     return true;
 }
@@ -1147,6 +1161,74 @@ __device__ __forceinline__ void transform_point_w1(const float *T, float sx, flo
     if (w != 1.0f) { px = fdiv(px, w); py = fdiv(py, w); pz = fdiv(pz, w); }
 }
 
+// the inlier test and the point's 8 components (zeros unless it is an inlier); T = rows 0..2 of the pose, T[3 * col + row]
+template <bool PLANE>
+__device__ __forceinline__ bool loop2_components(const IcpArgs &a, const float *T, bool final_pass, int nn, float sx, float sy, float sz, float px,
+                                                 float py, float pz, float *comp)
+{
+#pragma unroll
+    for (int k = 0; k < 8; ++k) comp[k] = 0.0f;
+    if (nn < 0) return false;
+    const float tx = __ldg(&a.tgt[3 * nn]), ty = __ldg(&a.tgt[3 * nn + 1]), tz = __ldg(&a.tgt[3 * nn + 2]);
+    // CountInliers (ICP.cpp:19-21): (R*s + t - target).squaredNorm() in float, compared as double
+    const float ex = fsub(fadd(fadd(fmul(T[0], sx), fadd(fmul(T[3], sy), fmul(T[6], sz))), T[9]), tx);
+    const float ey = fsub(fadd(fadd(fmul(T[1], sx), fadd(fmul(T[4], sy), fmul(T[7], sz))), T[10]), ty);
+    const float ez = fsub(fadd(fadd(fmul(T[2], sx), fadd(fmul(T[5], sy), fmul(T[8], sz))), T[11]), tz);
+    const float err = fadd(fmul(ex, ex), fadd(fmul(ey, ey), fmul(ez, ez)));
+    if (!((double)err < a.sq_threshold)) return false;
+    if (final_pass) { comp[0] = err; comp[1] = 1.0f; }
+    else if (PLANE)
+    {
+        // EstimateRigidTransformationPointToPlane (ICP.cpp:121-136): row = [n ; s' x n], r = n.s' - n.t, in float
+        const float nx = __ldg(&a.nrm[3 * nn]), ny = __ldg(&a.nrm[3 * nn + 1]), nz = __ldg(&a.nrm[3 * nn + 2]);
+        comp[0] = nx; comp[1] = ny; comp[2] = nz;
+        comp[3] = fsub(fmul(py, nz), fmul(pz, ny));
+        comp[4] = fsub(fmul(pz, nx), fmul(px, nz));
+        comp[5] = fsub(fmul(px, ny), fmul(py, nx));
+        comp[6] = fsub(dot3(nx, ny, nz, px, py, pz), dot3(nx, ny, nz, tx, ty, tz));
+        comp[7] = 1.0f;
+    }
+    else
+    {   // PointToPoint (ICP.cpp:78-84): Kabsch sums over (transformed source, target)
+        comp[0] = px; comp[1] = py; comp[2] = pz; comp[3] = 1.0f;
+        comp[4] = tx; comp[5] = ty; comp[6] = tz;
+    }
+    return true;
+}
+// the warp's 32 vectors -> shared memory -> eight 8x8x4 outer-product accumulations (A = B^T = 8 components x 4 points).  The
+// eight products go to four independent accumulators (a dependent DMMA chain costs ~140 cycles per link, independent ones issue
+// every 16: scripts/micro/dmma_rate.cu) and are folded with plain additions.
+__device__ __forceinline__ void loop2_fold(float *stage, int lane, const float *comp, double &c0, double &c1)
+{
+    *reinterpret_cast<float4 *>(stage + lane * 8) = make_float4(comp[0], comp[1], comp[2], comp[3]);
+    *reinterpret_cast<float4 *>(stage + lane * 8 + 4) = make_float4(comp[4], comp[5], comp[6], comp[7]);
+    __syncwarp();
+    double t0[4] = {0.0, 0.0, 0.0, 0.0}, t1[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+    {
+        const double v = (double)stage[(4 * j + (lane & 3)) * 8 + (lane >> 2)];
+        dmma_8x8x4(t0[j & 3], t1[j & 3], v, v);
+    }
+    __syncwarp();
+    c0 += (t0[0] + t0[1]) + (t0[2] + t0[3]);
+    c1 += (t1[0] + t1[1]) + (t1[2] + t1[3]);
+}
+__device__ __forceinline__ void loop2_transform(const float *T, bool rigid, const float *T_full, float sx, float sy, float sz, float &px, float &py,
+                                                float &pz)
+{
+    if (rigid)
+    {   // the products with the zero row still decide whether w is 1 or NaN (non-finite source points)
+        px = row_xyz1(T[0], T[3], T[6], T[9], sx, sy, sz);
+        py = row_xyz1(T[1], T[4], T[7], T[10], sx, sy, sz);
+        pz = row_xyz1(T[2], T[5], T[8], T[11], sx, sy, sz);
+        const float w = row_xyz1(0.0f, 0.0f, 0.0f, 1.0f, sx, sy, sz);
+        if (w != 1.0f) { px = fdiv(px, w); py = fdiv(py, w); pz = fdiv(pz, w); }
+    }
+    else
+        transform_point(T_full, sx, sy, sz, px, py, pz);
+}
+
 template <bool PLANE>
 __global__ void __launch_bounds__(kLoop2Threads, 1) icp_loop2_kernel(const __grid_constant__ IcpArgs a, int n_pass, double *partials, unsigned int *sync)
 {
@@ -1158,21 +1240,26 @@ __global__ void __launch_bounds__(kLoop2Threads, 1) icp_loop2_kernel(const __gri
     __syncthreads();
     const float guard = a.certify ? a.guard * sh.grid.h : 0.0f;
     const int n_trips = (a.ns + 31) >> 5;
+    // trips of this warp: first, first + step, ...  Consecutive trips go to different CTAs, so that a cluster of points that need
+    // a full search (they come in spatial clusters) is spread over the grid instead of holding up one CTA.
+    const int first_trip = warp * n_cta + blockIdx.x, trip_step = kLoop2Warps * n_cta;
     for (int pass = 0; pass < n_pass; ++pass)
     {
         const bool final_pass = pass == n_pass - 1;
         const int keep_far = pass == n_pass - 2;
         if (blockIdx.x == 0 && threadIdx.x == 0) icp_stamp(a.st, pass, 0);
-        float T[12]; // rows 0..2 of the pose: T[4 * c + r]
+        float T[12]; // rows 0..2 of the pose: T[3 * c + r]
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
             for (int r = 0; r < 3; ++r) T[3 * c + r] = sh.T[4 * c + r];
         const bool rigid = sh.T[3] == 0.0f && sh.T[7] == 0.0f && sh.T[11] == 0.0f && sh.T[15] == 1.0f;
         double c0 = 0.0, c1 = 0.0;
-        unsigned int searched = 0;
         float *stage = sh.u.stage[warp];
-        for (int trip = blockIdx.x * kLoop2Warps + warp; trip < n_trips; trip += n_cta * kLoop2Warps)
+        // ---- streaming loop: certified points go from the certificate straight to their row; the others are noted ----
+        unsigned int todo = 0; // bit k: the point of this lane in the warp's k-th trip needs the out-of-line path
+        int k = 0;
+        for (int trip = first_trip; trip < n_trips; trip += trip_step, ++k)
         {
             const int i = trip * 32 + lane;
             float comp[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
@@ -1180,91 +1267,81 @@ __global__ void __launch_bounds__(kLoop2Threads, 1) icp_loop2_kernel(const __gri
             {
                 const float sx = __ldg(&a.src[3 * i]), sy = __ldg(&a.src[3 * i + 1]), sz = __ldg(&a.src[3 * i + 2]);
                 int nn = -1;
+                bool later = false;
                 float px = 0.0f, py = 0.0f, pz = 0.0f;
                 if (!final_pass)
                 {
-                    if (rigid)
-                    {   // the products with the zero row still decide whether w is 1 or NaN (non-finite source points)
-                        px = row_xyz1(T[0], T[3], T[6], T[9], sx, sy, sz);
-                        py = row_xyz1(T[1], T[4], T[7], T[10], sx, sy, sz);
-                        pz = row_xyz1(T[2], T[5], T[8], T[11], sx, sy, sz);
-                        const float w = row_xyz1(0.0f, 0.0f, 0.0f, 1.0f, sx, sy, sz);
-                        if (w != 1.0f) { px = fdiv(px, w); py = fdiv(py, w); pz = fdiv(pz, w); }
-                    }
-                    else
-                        transform_point(sh.T, sx, sy, sz, px, py, pz);
+                    loop2_transform(T, rigid, sh.T, sx, sy, sz, px, py, pz);
                     const float4 q = a.qref[i];
                     const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
-                    const float moved = sqrtf(dx * dx + dy * dy + dz * dz) * (1.0f + 1e-6f);
-                    if (moved < q.w)
-                    {   // the certified strictly nearest neighbour (beyond the inlier radius the inlier test below rejects it)
+                    const float moved2 = (dx * dx + dy * dy + dz * dz) * (1.0f + 4e-6f);
+                    if (q.w > 0.0f && moved2 < q.w * q.w)
+                    {   // the certified strictly nearest neighbour (beyond the inlier radius the inlier test rejects it)
                         nn = a.nn_ref[i].x;
                         if (nn < 0 && keep_far) nn = -2;
                     }
-                    else if (moved < a.budget2[i])
-                    {
-                        const int2 jj = a.nn_ref[i];
-                        const float da = dist2_nanoflann(px, py, pz, __ldg(&a.tgt[3 * jj.x]), __ldg(&a.tgt[3 * jj.x + 1]), __ldg(&a.tgt[3 * jj.x + 2]));
-                        const float db = dist2_nanoflann(px, py, pz, __ldg(&a.tgt[3 * jj.y]), __ldg(&a.tgt[3 * jj.y + 1]), __ldg(&a.tgt[3 * jj.y + 2]));
-                        nn = (da < db || (da == db && jj.x < jj.y)) ? jj.x : jj.y;
-                    }
                     else
                     {
-                        nn = loop2_search(a, &sh.grid, guard, i, px, py, pz, keep_far);
-                        ++searched;
+                        const float b2 = a.budget2[i];
+                        if (b2 > 0.0f && moved2 < b2 * b2)
+                        {
+                            const int2 jj = a.nn_ref[i];
+                            const float da = dist2_nanoflann(px, py, pz, __ldg(&a.tgt[3 * jj.x]), __ldg(&a.tgt[3 * jj.x + 1]), __ldg(&a.tgt[3 * jj.x + 2]));
+                            const float db = dist2_nanoflann(px, py, pz, __ldg(&a.tgt[3 * jj.y]), __ldg(&a.tgt[3 * jj.y + 1]), __ldg(&a.tgt[3 * jj.y + 2]));
+                            nn = (da < db || (da == db && jj.x < jj.y)) ? jj.x : jj.y;
+                        }
+                        else
+                            later = true;
                     }
-                    if (keep_far) a.nn[i] = nn; // the closing CountInliers re-tests exactly these (ICP.cpp:90,206)
+                    if (keep_far && !later) a.nn[i] = nn; // the closing CountInliers re-tests exactly these (ICP.cpp:90,206)
                 }
                 else
                 {
                     nn = a.nn[i];
-                    if (nn == -2) { nn = final_resolve_far(a, sh.grid, sh.T_prev, sh.T, i); a.nn[i] = nn; ++searched; }
+                    later = nn == -2;
                 }
-                bool inl = false;
-                if (nn >= 0)
+                if (later) todo |= 1u << (k & 31);
+                else
                 {
-                    const float tx = __ldg(&a.tgt[3 * nn]), ty = __ldg(&a.tgt[3 * nn + 1]), tz = __ldg(&a.tgt[3 * nn + 2]);
-                    // CountInliers (ICP.cpp:19-21): (R*s + t - target).squaredNorm() in float, compared as double
-                    const float ex = fsub(fadd(fadd(fmul(T[0], sx), fadd(fmul(T[3], sy), fmul(T[6], sz))), T[9]), tx);
-                    const float ey = fsub(fadd(fadd(fmul(T[1], sx), fadd(fmul(T[4], sy), fmul(T[7], sz))), T[10]), ty);
-                    const float ez = fsub(fadd(fadd(fmul(T[2], sx), fadd(fmul(T[5], sy), fmul(T[8], sz))), T[11]), tz);
-                    const float err = fadd(fmul(ex, ex), fadd(fmul(ey, ey), fmul(ez, ez)));
-                    inl = (double)err < a.sq_threshold;
-                    if (inl)
-                    {
-                        if (final_pass) { comp[0] = err; comp[1] = 1.0f; }
-                        else if (PLANE)
-                        {
-                            // EstimateRigidTransformationPointToPlane (ICP.cpp:121-136): row = [n ; s' x n], r = n.s' - n.t, in float
-                            const float nx = __ldg(&a.nrm[3 * nn]), ny = __ldg(&a.nrm[3 * nn + 1]), nz = __ldg(&a.nrm[3 * nn + 2]);
-                            comp[0] = nx; comp[1] = ny; comp[2] = nz;
-                            comp[3] = fsub(fmul(py, nz), fmul(pz, ny));
-                            comp[4] = fsub(fmul(pz, nx), fmul(px, nz));
-                            comp[5] = fsub(fmul(px, ny), fmul(py, nx));
-                            comp[6] = fsub(dot3(nx, ny, nz, px, py, pz), dot3(nx, ny, nz, tx, ty, tz));
-                            comp[7] = 1.0f;
-                        }
-                        else
-                        {   // PointToPoint (ICP.cpp:78-84): Kabsch sums over (transformed source, target)
-                            comp[0] = px; comp[1] = py; comp[2] = pz; comp[3] = 1.0f;
-                            comp[4] = tx; comp[5] = ty; comp[6] = tz;
-                        }
-                    }
+                    const bool inl = loop2_components<PLANE>(a, T, final_pass, nn, sx, sy, sz, px, py, pz, comp);
+                    if (final_pass) a.inlier[i] = inl;
                 }
+            }
+            loop2_fold(stage, lane, comp, c0, c1);
+        }
+        // ---- the noted points: exact search (or, in the closing pass, the wider re-search), then the same fold ----
+        unsigned int searched = 0;
+        double d0 = 0.0, d1 = 0.0; // own accumulators: these live across the out-of-line calls, the streaming loop's must not
+        while (__any_sync(0xffffffffu, todo != 0u))
+        {
+            float comp[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+            if (todo)
+            {
+                const int kk = __ffs(todo) - 1;
+                todo &= todo - 1u;
+                const int i = (first_trip + kk * trip_step) * 32 + lane;
+                const float sx = __ldg(&a.src[3 * i]), sy = __ldg(&a.src[3 * i + 1]), sz = __ldg(&a.src[3 * i + 2]);
+                float px = 0.0f, py = 0.0f, pz = 0.0f;
+                int nn;
+                if (!final_pass)
+                {
+                    loop2_transform(T, rigid, sh.T, sx, sy, sz, px, py, pz);
+                    nn = loop2_search(a, &sh.grid, guard, i, px, py, pz, keep_far);
+                    if (keep_far) a.nn[i] = nn;
+                }
+                else
+                {
+                    nn = final_resolve_far(a, sh.grid, sh.T_prev, sh.T, i);
+                    a.nn[i] = nn;
+                }
+                ++searched;
+                const bool inl = loop2_components<PLANE>(a, T, final_pass, nn, sx, sy, sz, px, py, pz, comp);
                 if (final_pass) a.inlier[i] = inl;
             }
-            // the warp's 32 vectors -> shared memory -> eight 8x8x4 outer-product accumulations (A = B^T = 8 components x 4 points)
-            *reinterpret_cast<float4 *>(stage + lane * 8) = make_float4(comp[0], comp[1], comp[2], comp[3]);
-            *reinterpret_cast<float4 *>(stage + lane * 8 + 4) = make_float4(comp[4], comp[5], comp[6], comp[7]);
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-            {
-                const double v = (double)stage[(4 * j + (lane & 3)) * 8 + (lane >> 2)];
-                dmma_8x8x4(c0, c1, v, v);
-            }
-            __syncwarp();
+            loop2_fold(stage, lane, comp, d0, d1);
         }
+        c0 += d0;
+        c1 += d1;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) searched += __shfl_xor_sync(0xffffffffu, searched, o);
         if (lane == 0 && searched)
@@ -1962,7 +2039,7 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     static const int k_persistent = getenv("OPB_ICP_PERSISTENT") ? atoi(getenv("OPB_ICP_PERSISTENT")) : 1;
     bool looped = false;
     c->last_launches = 8 + 3 * (par->max_iteration + 1) + 2 + (pairs && pairs_cap && ns ? 3 : 0) + (par->scaling != 1.0 ? 2 : 0);
-    if (k_persistent == 1 && c->loop2_ok && !c->peers_share_device)
+    if (k_persistent == 1 && c->loop2_ok && !c->peers_share_device && (ns + 31) / 32 <= (size_t)32 * kLoop2Warps * c->sm_count)
     {
         // second persistent form: one CTA of 1024 threads per SM, all passes in one cooperative launch
         const int nb_trips = ns ? (int)((ns + 31) / 32 + kLoop2Warps - 1) / kLoop2Warps : 1;

@@ -24,9 +24,23 @@ def test_reference_arm_prints_the_contract_line():
                 "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
-    assert "workload" in d["config"] and d["value"] > 0 and d["steps"] == 1
+    assert "workload" in d["config"] and d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 0
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.config_of(1)     # the reference arm prints exactly the config object of the other arm
+    import re
+    m = re.search(r"on (\d+) threads", d["cpu_baseline"]["sample"])
+    assert m and int(m.group(1)) == d["cpu_baseline"]["cores"]
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_uses_all_host_threads_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; rank 0's reference run must not inherit that"""
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "0"], env={"OMP_NUM_THREADS": "1", "RANK": "0", "WORLD_SIZE": "1"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
 
 
 def test_reference_arm_is_silent_on_other_ranks():

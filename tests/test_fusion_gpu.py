@@ -169,7 +169,7 @@ def test_split_icp_workspaces_on_one_device(world, plane):
     assert np.abs(out[0][1].T - whole.T).max() < 1e-6
     # (the whole call sums exact products in the persistent loop's 8x8 accumulation, the split one float-rounded products:
     # the iterated pose may differ in its last float bit, the rmse with it)
-    assert abs(out[0][1].rmse - whole.rmse) < 1e-7 * whole.rmse + 1e-12
+    assert abs(out[0][1].rmse - whole.rmse) < 2e-6 * whole.rmse
     # a collective call that a peer never makes fails after the time limit instead of hanging
     if world == 2 and plane:
         with pytest.raises(capi.OpbError) as e:
