@@ -410,6 +410,67 @@ def bench_config4(local, rank, world, steps, warmup, reference_on_rank0: bool):
     return res
 
 
+# ----------------------------------------------------------------------------------------------------------
+# BASELINE.json config 5 at the bench's image size: the DenseFusion loop over ALL ranks -- per frame a point-to-plane ICP whose
+# source points are split across the ranks (the 6x6 packet all-reduced over peer memory inside the persistent solver kernel),
+# then the frame integrated into the volume partitioned by cube ownership; at the end boundary-cube exchange + Marching Cubes.
+# Host buffers, wall clock between barriers.  The solvers are latency-bound at 640x480 (SURVEY.md 8e expected little or
+# negative gain from splitting them): this number says what the collectives cost, it is not the scaling headline.
+# ----------------------------------------------------------------------------------------------------------
+def bench_config5(cam, local, rank, world, steps):
+    import torch
+    import torch.distributed as dist
+
+    from onepiece_b200 import fusion, registration as reg
+    frames = make_stream(cam, 0)   # every rank looks at the SAME stream here
+    sp = fusion.SplitICP(local)
+    sh = fusion.ShardedCubeHandler(cam, VOXEL, max_cubes=1 << 16, axis=0, slab=8, device_index=local)
+    par = reg.ICPParameter(ICP_ITERS, ICP_THRESHOLD, 1.0)
+
+    def pinned(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+
+    clouds = []
+    for f in frames:
+        pc = reg.PointCloud(f["cloud"], f["normals"])
+        pc.points, pc.normals = pinned(pc.points), pinned(pc.normals)
+        f["depth"], f["bgr"] = pinned(f["depth"]), pinned(f["bgr"])
+        clouds.append(pc)
+
+    def step(s):
+        k = s % (N_TRAJ - 1)
+        r = sp.PointToPlane(clouds[k + 1], clouds[k], np.eye(4), par, gather_pairs=False)
+        pose = (frames[k]["pose"] @ r.T.astype(np.float64)).astype(np.float32)
+        sh.IntegrateImage(frames[k + 1]["depth"], frames[k + 1]["bgr"], pose)
+        return r
+
+    for s in range(3):
+        step(s)
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for s in range(steps):
+        r = step(3 + s)
+    torch.cuda.synchronize(); dist.barrier()
+    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    n_ghost = fusion.exchange_halo(sh.volume, rank, world, sh.device)
+    torch.cuda.synchronize(); dist.barrier()
+    t2 = time.perf_counter()
+    nv, nt = sh.volume.CountMesh()
+    tot = torch.tensor([sh.volume.NumCubes(), n_ghost, nv], device="cuda", dtype=torch.int64)
+    dist.all_reduce(tot)
+    Ts = [None] * world
+    dist.all_gather_object(Ts, r.T.tobytes())
+    sp.close()
+    return {"what": "config5 at 640x480: one stream fused by all ranks, split point-to-plane ICP (peer-memory packet exchange inside "
+                    "the persistent solver kernel) + partitioned integration per frame, host buffers; then halo exchange + Marching Cubes "
+                    "count.  Dense odometry is not split across ranks (its correspondence pass is order-dependent; at 1 ms per frame pair "
+                    "a split cannot pay for the exchange), so a DenseTracking-based pipeline scales only in its integration leg",
+            "frames_per_s": steps / dt, "ms_per_frame": 1e3 * dt / steps, "frames": steps, "cubes_total": int(tot[0]),
+            "boundary_cubes_exchanged": int(tot[1]), "halo_exchange_ms": 1e3 * (t2 - t1), "mesh_vertices_total": int(tot[2]),
+            "pose_identical_on_all_ranks": bool(all(t == Ts[0] for t in Ts))}
+
+
 def config4_line(c4, world, steps, peak_gbs):
     """the numbers of bench_config4 as reported in the JSON line"""
     p = c4["partitioned"]
@@ -693,6 +754,13 @@ def run_ours(args):
     e2e_nopairs_ms, _ = timed(lambda s: e2e_step(s, False), K, W, e2e_prime)
     hostsig_ms, _ = timed(hostsig_step, K, W)
 
+    c5 = None
+    if world > 1 and not args.no_partitioned:
+        vol.close()  # make room: the partitioned volume is a second pool on the same GPU
+        try:
+            c5 = bench_config5(cam, local, rank, world, min(25 * K, 500))
+        except Exception as exc:  # noqa: BLE001  -- a secondary measurement must never cost the headline line
+            c5 = {"error": f"{type(exc).__name__}: {exc}"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -759,6 +827,8 @@ def run_ours(args):
                        "d2h_bytes_per_step": 0, "clock": line4["e2e_note"]},
                "gpu_launches": 3 * K * world, "clocks": clocks4,
                "replicas": dict(replicas, details=details, roofline=roofline, e2e_detail=e2e, clocks=clocks)}
+        if c5 is not None:
+            out["dense_fusion_pipeline"] = dict(c5, single_gpu_frames_per_s=replicas["e2e"] / world)
     if not args.no_cpu_baseline and world == 1:
         cb, _, _, cpu_T = cpu_reference_fps(30, 1, budget_s=20.0)
         out["cpu_baseline"] = cb

@@ -430,6 +430,7 @@ struct IcpArgs
     unsigned int *worklist; // ns
     float guard;            // extra radius every full search covers beyond its nearest neighbour, in grid cells
     int certify;            // 0: every pass searches every point (reference behaviour of the search, for A/B tests)
+    float unscale;          // ICPParameter::scaling: the closing pass divides the (scaled) coordinates by it again
 };
 
 // geometry::TransformPoints: T * (x,y,z,1) then divide by w (Geometry.cpp:19-27)
@@ -1117,7 +1118,12 @@ __host__ __device__ constexpr int packet_source(int mode, int k)
         if (k < 15) return ((k - 6) / 3) * 8 + 4 + (k - 6) % 3; // sum s' t^T
         return k == 29 ? 3 * 8 + 3 : -1;
     }
-    return k == 28 ? 1 : (k == 29 ? 9 : -1);       // sum err, count
+    // closing pass, c = (s, 1, t, err) with the ORIGINAL clouds: the Kabsch sums of result.T (ICP.cpp:93-105,208-221), sum err, count
+    if (k < 3) return k * 8 + 3;               // sum s
+    if (k < 6) return 3 * 8 + 4 + (k - 3);     // sum t
+    if (k < 15) return ((k - 6) / 3) * 8 + 4 + (k - 6) % 3; // sum s t^T
+    if (k == 15) return 3 * 8 + 3;             // count (where kabsch_from_sums' caller expects it)
+    return k == 28 ? 3 * 8 + 7 : (k == 29 ? 3 * 8 + 3 : -1); // sum err, count
 }
 __host__ __device__ constexpr unsigned long long packet_need_mask(int mode)
 {
@@ -1170,17 +1176,28 @@ __device__ __forceinline__ bool loop2_components(const IcpArgs &a, const float *
     for (int k = 0; k < 8; ++k) comp[k] = 0.0f;
     if (nn < 0) return false;
     const float tx = __ldg(&a.tgt[3 * nn]), ty = __ldg(&a.tgt[3 * nn + 1]), tz = __ldg(&a.tgt[3 * nn + 2]);
+    // the normal travels with the target point, not after the inlier test: one round trip to L2 instead of two
+    float nx = 0.0f, ny = 0.0f, nz = 0.0f;
+    if (PLANE && !final_pass) { nx = __ldg(&a.nrm[3 * nn]); ny = __ldg(&a.nrm[3 * nn + 1]); nz = __ldg(&a.nrm[3 * nn + 2]); }
     // CountInliers (ICP.cpp:19-21): (R*s + t - target).squaredNorm() in float, compared as double
     const float ex = fsub(fadd(fadd(fmul(T[0], sx), fadd(fmul(T[3], sy), fmul(T[6], sz))), T[9]), tx);
     const float ey = fsub(fadd(fadd(fmul(T[1], sx), fadd(fmul(T[4], sy), fmul(T[7], sz))), T[10]), ty);
     const float ez = fsub(fadd(fadd(fmul(T[2], sx), fadd(fmul(T[5], sy), fmul(T[8], sz))), T[11]), tz);
     const float err = fadd(fmul(ex, ex), fadd(fmul(ey, ey), fmul(ez, ez)));
     if (!((double)err < a.sq_threshold)) return false;
-    if (final_pass) { comp[0] = err; comp[1] = 1.0f; }
+    if (final_pass)
+    {   // un-scaled originals (ICP.cpp:93-99,208-214 divide the scaled copies again)
+        comp[0] = sx; comp[1] = sy; comp[2] = sz; comp[3] = 1.0f;
+        comp[4] = tx; comp[5] = ty; comp[6] = tz; comp[7] = err;
+        if (a.unscale != 1.0f)
+        {
+            comp[0] = fdiv(sx, a.unscale); comp[1] = fdiv(sy, a.unscale); comp[2] = fdiv(sz, a.unscale);
+            comp[4] = fdiv(tx, a.unscale); comp[5] = fdiv(ty, a.unscale); comp[6] = fdiv(tz, a.unscale);
+        }
+    }
     else if (PLANE)
     {
         // EstimateRigidTransformationPointToPlane (ICP.cpp:121-136): row = [n ; s' x n], r = n.s' - n.t, in float
-        const float nx = __ldg(&a.nrm[3 * nn]), ny = __ldg(&a.nrm[3 * nn + 1]), nz = __ldg(&a.nrm[3 * nn + 2]);
         comp[0] = nx; comp[1] = ny; comp[2] = nz;
         comp[3] = fsub(fmul(py, nz), fmul(pz, ny));
         comp[4] = fsub(fmul(pz, nx), fmul(px, nz));
@@ -1271,13 +1288,14 @@ __global__ void __launch_bounds__(kLoop2Threads, 1) icp_loop2_kernel(const __gri
                 float px = 0.0f, py = 0.0f, pz = 0.0f;
                 if (!final_pass)
                 {
-                    loop2_transform(T, rigid, sh.T, sx, sy, sz, px, py, pz);
                     const float4 q = a.qref[i];
+                    const int2 jj = a.nn_ref[i]; // with the certificate, not after it: the gathers below start one round trip earlier
+                    loop2_transform(T, rigid, sh.T, sx, sy, sz, px, py, pz);
                     const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
                     const float moved2 = (dx * dx + dy * dy + dz * dz) * (1.0f + 4e-6f);
                     if (q.w > 0.0f && moved2 < q.w * q.w)
                     {   // the certified strictly nearest neighbour (beyond the inlier radius the inlier test rejects it)
-                        nn = a.nn_ref[i].x;
+                        nn = jj.x;
                         if (nn < 0 && keep_far) nn = -2;
                     }
                     else
@@ -1285,7 +1303,6 @@ __global__ void __launch_bounds__(kLoop2Threads, 1) icp_loop2_kernel(const __gri
                         const float b2 = a.budget2[i];
                         if (b2 > 0.0f && moved2 < b2 * b2)
                         {
-                            const int2 jj = a.nn_ref[i];
                             const float da = dist2_nanoflann(px, py, pz, __ldg(&a.tgt[3 * jj.x]), __ldg(&a.tgt[3 * jj.x + 1]), __ldg(&a.tgt[3 * jj.x + 2]));
                             const float db = dist2_nanoflann(px, py, pz, __ldg(&a.tgt[3 * jj.y]), __ldg(&a.tgt[3 * jj.y + 1]), __ldg(&a.tgt[3 * jj.y + 2]));
                             nn = (da < db || (da == db && jj.x < jj.y)) ? jj.x : jj.y;
@@ -1745,6 +1762,7 @@ struct opb_icp
     size_t cap_partials = 0;
     IcpState *d_state = nullptr;
     IcpState *h_state = nullptr; // pinned
+    double *h_sums = nullptr;    // pinned: the 16 Kabsch sums of result.T (separate-launch finaliser)
     // cross-GPU exchange (opb_icp_comm_*)
     IcpMailbox *d_mailbox = nullptr;
     IcpComm comm = {};
@@ -1870,6 +1888,7 @@ int opb_icp_create(int device, void *stream, opb_icp **out)
     else { OPB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     cudaError_t e = cudaMalloc(&c->d_state, sizeof(IcpState));
     if (e == cudaSuccess) e = cudaHostAlloc(&c->h_state, sizeof(IcpState), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc(&c->h_sums, 16 * sizeof(double), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_cell_count, ((size_t)kMaxCells + 1) * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_tile_sums, ((size_t)kMaxTiles + 1) * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_cell_start, ((size_t)kMaxCells + 2) * sizeof(unsigned int));
@@ -1935,6 +1954,7 @@ void opb_icp_destroy(opb_icp *c)
     cudaFree(c->d_qref); cudaFree(c->d_nn_ref); cudaFree(c->d_worklist); cudaFree(c->d_budget2); cudaFree(c->d_pair_tiles);
     cudaFree(c->d_grid_sync); cudaFree(c->d_partials2); cudaFree(c->d_loop_sync);
     if (c->h_state) cudaFreeHost(c->h_state);
+    if (c->h_sums) cudaFreeHost(c->h_sums);
     for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 3; ++i) if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
@@ -2025,7 +2045,7 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     a.qref = c->d_qref; a.nn_ref = c->d_nn_ref; a.worklist = c->d_worklist; a.budget2 = c->d_budget2;
     static const float k_guard = getenv("OPB_ICP_GUARD") ? (float)atof(getenv("OPB_ICP_GUARD")) : 0.125f;
     static const int k_certify = getenv("OPB_ICP_CERTIFY") ? atoi(getenv("OPB_ICP_CERTIFY")) : 1;
-    a.guard = k_guard; a.certify = k_certify;
+    a.guard = k_guard; a.certify = k_certify; a.unscale = scaling;
     if (ns) OPB_CUDA(cudaMemsetAsync(c->d_qref, 0xFF, ns * sizeof(float4), s));
     if (ns) OPB_CUDA(cudaMemsetAsync(c->d_nn, 0xFF, ns * sizeof(int), s)); // corresponding_index(n, -1) (ICP.cpp:58,174)
     const int nb_need = ns ? (int)((ns + kIcpThreads - 1) / kIcpThreads) : 1; // an empty share still takes part in the exchange
@@ -2037,7 +2057,7 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     static const int k_cert = getenv("OPB_ICP_CERTIFY_CTAS") ? atoi(getenv("OPB_ICP_CERTIFY_CTAS")) : 8;
     const int nb_c = nb_need < c->sm_count * k_cert ? nb_need : c->sm_count * k_cert;
     static const int k_persistent = getenv("OPB_ICP_PERSISTENT") ? atoi(getenv("OPB_ICP_PERSISTENT")) : 1;
-    bool looped = false;
+    bool looped = false, looped2 = false;
     c->last_launches = 8 + 3 * (par->max_iteration + 1) + 2 + (pairs && pairs_cap && ns ? 3 : 0) + (par->scaling != 1.0 ? 2 : 0);
     if (k_persistent == 1 && c->loop2_ok && !c->peers_share_device && (ns + 31) / 32 <= (size_t)32 * kLoop2Warps * c->sm_count)
     {
@@ -2051,8 +2071,8 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
         void *kargs[] = {(void *)&a, (void *)&n_pass, (void *)&c->d_partials2, (void *)&c->d_loop_sync};
         const void *fn = point_to_plane ? (const void *)icp_loop2_kernel<true> : (const void *)icp_loop2_kernel<false>;
         OPB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(nb_l), dim3(kLoop2Threads), kargs, 0, s));
-        looped = true;
-        c->last_launches = (c->grid_ctas_per_sm > 0 && !c->peers_share_device ? 1 : 8) + 1 + 2 + (pairs && pairs_cap && ns ? 3 : 0) + (par->scaling != 1.0 ? 2 : 0);
+        looped = looped2 = true; // (its closing pass also forms the Kabsch sums of result.T: no finaliser kernels)
+        c->last_launches = (c->grid_ctas_per_sm > 0 && !c->peers_share_device ? 1 : 8) + 1 + (pairs && pairs_cap && ns ? 3 : 0) + (par->scaling != 1.0 ? 2 : 0);
     }
     else if (k_persistent && c->coop_ctas_per_sm > 0 && !c->peers_share_device)
     {
@@ -2086,14 +2106,22 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
         else icp_accumulate_kernel<false><<<nb_a, kIcpThreads, 0, s>>>(a);
     }
     OPB_CUDA(cudaMemcpyAsync(h, c->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
-    icp_final_sums_kernel<<<nb_a, kIcpThreads, 0, s>>>(d_src, d_tgt, c->d_nn, c->d_inlier, (int)ns, scaling, c->d_partials);
-    icp_final_reduce_kernel<<<1, kIcpThreads, 0, s>>>(c->d_partials, nb_a, c->d_state, c->comm);
-    if (pairs && pairs_cap && ns)
+    if (!looped2)
+    {
+        icp_final_sums_kernel<<<nb_a, kIcpThreads, 0, s>>>(d_src, d_tgt, c->d_nn, c->d_inlier, (int)ns, scaling, c->d_partials);
+        icp_final_reduce_kernel<<<1, kIcpThreads, 0, s>>>(c->d_partials, nb_a, c->d_state, c->comm);
+        OPB_CUDA(cudaMemcpyAsync(c->h_sums, (const char *)c->d_state + offsetof(IcpState, packet), 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    const size_t n_copy = pairs && pairs_cap && ns ? (pairs_cap < ns ? pairs_cap : ns) : 0;
+    if (n_copy)
     {
         const int n_tiles = (int)((ns + kPairTile - 1) / kPairTile);
         icp_pair_count_kernel<<<n_tiles, kPairTile, 0, s>>>(c->d_inlier, (int)ns, c->d_pair_tiles);
         icp_pair_scan_kernel<<<1, 1024, 0, s>>>(c->d_pair_tiles, n_tiles);
         icp_pair_write_kernel<<<n_tiles, kPairTile, 0, s>>>(c->d_nn, c->d_inlier, (int)ns, c->d_pair_tiles, c->d_pairs, (unsigned long long)pairs_cap);
+        // the pairs follow on the same stream (one synchronisation for the whole call): the first n_local_pairs entries are the
+        // result, the rest of the caller's buffer up to min(pairs_cap, ns) is scratch
+        OPB_CUDA(cudaMemcpyAsync(pairs, c->d_pairs, n_copy * 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
     }
     if (c->profiling) OPB_CUDA(cudaEventRecord(c->ev[2], s));
     OPB_CUDA(cudaGetLastError());
@@ -2122,8 +2150,7 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     res->iterations = h->iteration;
     memcpy(res->T_iterated, h->T, 16 * sizeof(float));
     // result.T = Kabsch over the final inlier pairs of the original clouds (ICP.cpp:103-105,221)
-    double sums[16];
-    OPB_CUDA(cudaMemcpy(sums, (const char *)c->d_state + offsetof(IcpState, packet), sizeof(sums), cudaMemcpyDeviceToHost));
+    const double *sums = looped2 ? h->packet : c->h_sums;
     if (sums[15] >= 0.5)
     {
         double Tk[16];
@@ -2133,11 +2160,6 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     }
     else
         for (int e = 0; e < 16; ++e) res->T[e] = nanf(""); // the reference divides by zero pairs here
-    if (pairs && pairs_cap)
-    {
-        const size_t n = res->n_local_pairs < pairs_cap ? res->n_local_pairs : pairs_cap;
-        OPB_CUDA(cudaMemcpy(pairs, c->d_pairs, n * 2 * sizeof(int), cudaMemcpyDeviceToHost));
-    }
     res->status = OPB_OK;
     return OPB_OK;
 }

@@ -4,6 +4,11 @@ import sys
 import numpy as np
 import pytest
 
+# Several ICP workspaces of ONE process exchange packets in tests/test_fusion_gpu.py (a kernel of one spins until another's has
+# run): every stream needs its own hardware queue, or a kernel can be queued behind the very kernel that waits for it.  Real
+# deployments run one process per GPU.  (Read by the CUDA driver when the context is created, i.e. after this line.)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
