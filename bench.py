@@ -381,13 +381,26 @@ def bench_config4(local, rank, world, steps, warmup, reference_on_rank0: bool):
         out = {"ms_per_frame": ms_dev / steps, "e2e_ms_per_frame": ms_e2e / steps, "cubes": vol.NumCubes(), "frame_cubes": st.frame_cubes,
                "updated_voxels_per_frame": upd / max(n_prof, 1), "select_ms": sel_ms / max(nprof, 1), "integrate_ms": int_ms / max(nprof, 1),
                "pool_grew": st.overflow}
-        # mesh: boundary cubes from the owner of the next slab, then Marching Cubes (count only)
-        t0 = time.perf_counter()
-        n_ghost = fusion.exchange_halo(vol, rank, world, torch.device("cuda", local)) if (collective and world > 1) else 0
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
+        # mesh: boundary cubes from the owner of the next slab, then Marching Cubes (count only).  The exchange is two kernel
+        # launches per rank over peer memory (export into the neighbour's box, import from one's own); timed with CUDA events
+        # on the volume's stream between barriers, the second of two exchanges (the first maps the peer pages)
+        n_ghost, halo_ms = 0, 0.0
+        if collective and world > 1:
+            maps = fusion.attach_halo_peers(vol, rank, world, max(vol.NumCubes(), 1024), local)
+            for rep in range(2):
+                vol.HaloClear()
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                vol.HaloExchangeBegin()
+                e1.record(stream)
+                n_sent, n_ghost = vol.HaloExchangeEnd()
+                halo_ms = e0.elapsed_time(e1)
+            barrier()
         nv, nt = vol.CountMesh()
-        out.update(halo_exchange_ms=1e3 * (t1 - t0), boundary_cubes_imported=int(n_ghost), mesh_vertices=int(nv))
+        out.update(halo_exchange_ms=halo_ms, boundary_cubes_imported=int(n_ghost), mesh_vertices=int(nv))
+        if collective and world > 1:
+            fusion.detach_halo_peers(vol, maps, local)
         vol.close()
         return out
 
@@ -462,6 +475,7 @@ def bench_config5(cam, local, rank, world, steps):
     Ts = [None] * world
     dist.all_gather_object(Ts, r.T.tobytes())
     sp.close()
+    sh.close()
     return {"what": "config5 at 640x480: one stream fused by all ranks, split point-to-plane ICP (peer-memory packet exchange inside "
                     "the persistent solver kernel) + partitioned integration per frame, host buffers; then halo exchange + Marching Cubes "
                     "count.  Dense odometry is not split across ranks (its correspondence pass is order-dependent; at 1 ms per frame pair "
@@ -469,6 +483,57 @@ def bench_config5(cam, local, rank, world, steps):
             "frames_per_s": steps / dt, "ms_per_frame": 1e3 * dt / steps, "frames": steps, "cubes_total": int(tot[0]),
             "boundary_cubes_exchanged": int(tot[1]), "halo_exchange_ms": 1e3 * (t2 - t1), "mesh_vertices_total": int(tot[2]),
             "pose_identical_on_all_ranks": bool(all(t == Ts[0] for t in Ts))}
+
+
+def bench_packed16(cam, frames, local, steps, peak_gbs):
+    """The voxel update on OPB_STORAGE_PACKED16 volumes (8-byte voxels: half sdf, half weight, rgb8 -- north_star's "fp16 voxel
+    writes") over the same frames with their true poses, next to the float kernel's roofline and with its deviation from the
+    float volume.  A secondary: the packed mode is outside the parity contract, the headline stays on 20-byte float voxels."""
+    import torch
+
+    from onepiece_b200 import capi
+    from onepiece_b200.volume import CubeHandler
+    vols = {name: CubeHandler(cam, VOXEL, max_cubes=1 << 17, device=local, storage=st)
+            for name, st in (("f32", capi.OPB_STORAGE_F32), ("packed16", capi.OPB_STORAGE_PACKED16))}
+    D = [(torch.from_numpy(f["depth"]).cuda(), torch.from_numpy(f["bgr"]).cuda(),
+          np.ascontiguousarray(f["pose"].astype(np.float32).T).reshape(16)) for f in frames]
+    out = {}
+    for name, vol in vols.items():
+        for d, c, pose in D:   # first pass: allocation
+            vol.IntegrateImageDevice(d.data_ptr(), capi.OPB_DEPTH_U16, c.data_ptr(), pose)
+        vol.Synchronize()
+        vol.SetProfiling(True)
+        vol.ProfileRead(reset=True)
+        upd = 0
+        for s in range(steps):
+            d, c, pose = D[s % len(D)]
+            vol.IntegrateImageDevice(d.data_ptr(), capi.OPB_DEPTH_U16, c.data_ptr(), pose)
+            upd += vol.FrameStats().updated_voxels
+        sel_ms, int_ms, n = vol.ProfileRead(reset=True)
+        vol.SetProfiling(False)
+        bytes_per_voxel = 20 if name == "f32" else 8
+        alg = upd / steps * 2 * bytes_per_voxel + cam.width * cam.height * 5
+        k_ms = int_ms / max(n, 1)
+        out[name] = {"bytes_per_voxel": bytes_per_voxel, "kernel_ms": k_ms, "updated_voxels_per_frame": int(upd / steps),
+                     "algorithmic_bytes_per_launch": int(alg), "achieved_gbs": alg / (k_ms * 1e-3) / 1e9,
+                     "frac_of_hbm_peak": alg / (k_ms * 1e-3) / 1e9 / peak_gbs}
+    fi, fv = vols["f32"].GetCubeMap()
+    pi, pv = vols["packed16"].GetCubeMap()
+    same = bool(np.array_equal(fi, pi))
+    err = {"cube_set_identical": same}
+    if same:
+        seen = fv[..., 1] > 0
+        err.update(max_abs_sdf_error_m=float(np.abs(fv[..., 0] - pv[..., 0])[seen].max()),
+                   max_abs_colour_error=float(np.abs(fv[..., 2:] - pv[..., 2:])[seen].max()),
+                   weights_identical=bool(np.array_equal(fv[..., 1], pv[..., 1])))
+    nv_f, nv_p = vols["f32"].CountMesh()[0], vols["packed16"].CountMesh()[0]
+    err.update(mesh_vertices_f32=int(nv_f), mesh_vertices_packed16=int(nv_p), frames_integrated=len(D) + steps)
+    for v in vols.values():
+        v.close()
+    return {"what": "voxel update alone, frames and poses of the bench stream, 5 mm: 20-byte float voxels (the parity path, kernel "
+                    "integrate_pipelined_kernel) against 8-byte packed voxels (integrate_packed_kernel); gate of the packed mode in "
+                    "tests/test_packed_gpu.py",
+            "kernel_speedup": out["f32"]["kernel_ms"] / out["packed16"]["kernel_ms"], **out, "deviation_from_f32": err}
 
 
 def config4_line(c4, world, steps, peak_gbs):
@@ -843,6 +908,11 @@ def run_ours(args):
             out["partitioned_fusion"] = config4_line(bench_config4(local, 0, 1, min(K, 50), W, False), 1, min(K, 50), pk["hbm_gbs"])
         except Exception as exc:  # noqa: BLE001  -- a secondary measurement must never cost the headline line
             out["partitioned_fusion"] = {"error": f"{type(exc).__name__}: {exc}"}
+    if world == 1 and not args.no_partitioned:
+        try:
+            out["packed16_voxels"] = bench_packed16(cam, frames, local, min(K, 50), pk["hbm_gbs"])
+        except Exception as exc:  # noqa: BLE001
+            out["packed16_voxels"] = {"error": f"{type(exc).__name__}: {exc}"}
     if not args.no_odometry and world == 1:
         out["dense_odometry"] = bench_dense_odometry(frames, cam, local, min(K, 100), not args.no_cpu_baseline)
     print(json.dumps(out), flush=True)

@@ -27,6 +27,8 @@
 extern "C" {
 #endif
 
+#define OPB_IPC_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t): handles of device buffers that peer ranks map (opb_ipc_open) */
+
 typedef enum
 {
     OPB_OK = 0,
@@ -222,6 +224,26 @@ int opb_volume_halo_export(opb_volume *v, int32_t *ids, float *layers, size_t ca
 int opb_volume_halo_import(opb_volume *v, const int32_t *ids, const float *layers, size_t n);
 int opb_volume_halo_clear(opb_volume *v);
 int opb_volume_num_ghost_cubes(opb_volume *v, size_t *n);
+/* The same exchange with the transport inside the kernels (steps 1-3 as two launches, no host program in between):
+ *   opb_volume_halo_peer_buffer    this volume's receive box for up to cap_cubes boundary cubes (device memory; created once)
+ *                                  and its cudaIpc handle, which the host program hands to the neighbouring ranks
+ *                                  (opb_ipc_open maps it there);
+ *   opb_volume_halo_peer_attach    dst_buffer = the mapped box of rank-1 (this rank exports into it; dst_cap_cubes = its
+ *                                  capacity), src_buffer = the mapped box of rank+1 (this rank acknowledges there).  With two
+ *                                  ranks both are the same box.  NULL, 0, NULL detaches;
+ *   opb_volume_halo_exchange_peer  collective over the ranks: the export kernel stores ids and layers straight into the
+ *                                  destination's box over NVLink and raises a flag there; the import kernel, queued behind it,
+ *                                  waits for the flag of rank+1 in its own box, registers the ghosts and acknowledges.  Returns
+ *                                  the cubes sent and the ghosts imported.  A peer that never makes the call ends the wait
+ *                                  after 4 s with OPB_ERR_CUDA; OPB_ERR_CAPACITY when a box or the block pool is too small.
+ *   opb_volume_halo_exchange_begin / _end   the same call in two halves (enqueue / synchronise and read the counters) for a
+ *                                  host thread that drives several ranks' volumes itself.
+ * No counterpart in the single-process reference (CubeHandler.cpp:83-99 reads the neighbour cubes from its own map). */
+int opb_volume_halo_peer_buffer(opb_volume *v, size_t cap_cubes, void **d_buffer, unsigned char ipc_handle[OPB_IPC_HANDLE_BYTES]);
+int opb_volume_halo_peer_attach(opb_volume *v, void *dst_buffer, size_t dst_cap_cubes, void *src_buffer);
+int opb_volume_halo_exchange_peer(opb_volume *v, size_t *n_sent, size_t *n_imported);
+int opb_volume_halo_exchange_begin(opb_volume *v);
+int opb_volume_halo_exchange_end(opb_volume *v, size_t *n_sent, size_t *n_imported);
 
 /* ------------------------------------------------------------------------------------------------------
  * Depth pre-filter  (replaces one_piece::tool::ConvertDepthTo32F and tool::BilateralFilter,
@@ -413,7 +435,6 @@ int opb_kdtree_dump(opb_kdtree *t, int32_t *vind, int32_t *node_ints5, float *no
  * Afterwards opb_icp_point_to_plane / opb_icp_point_to_point are COLLECTIVE calls: every rank must make them in the same
  * order with its share of the source and identical target, init_T and params (a missing peer makes the call fail with
  * OPB_ERR_CUDA after 4 s instead of hanging).  A rank's share may be empty. */
-#define OPB_IPC_HANDLE_BYTES 64
 int opb_icp_comm_buffer(opb_icp *c, void **d_buffer, unsigned char ipc_handle[OPB_IPC_HANDLE_BYTES]);
 int opb_ipc_open(int device, const unsigned char ipc_handle[OPB_IPC_HANDLE_BYTES], void **d_ptr);
 int opb_ipc_close(int device, void *d_ptr);

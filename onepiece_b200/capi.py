@@ -125,6 +125,11 @@ SIGNATURES = {
     "opb_volume_halo_import": (C.c_int, [_p, _p, _p, _sz]),
     "opb_volume_halo_clear": (C.c_int, [_p]),
     "opb_volume_num_ghost_cubes": (C.c_int, [_p, C.POINTER(_sz)]),
+    "opb_volume_halo_peer_buffer": (C.c_int, [_p, _sz, C.POINTER(_p), _p]),
+    "opb_volume_halo_peer_attach": (C.c_int, [_p, _p, _sz, _p]),
+    "opb_volume_halo_exchange_peer": (C.c_int, [_p, C.POINTER(_sz), C.POINTER(_sz)]),
+    "opb_volume_halo_exchange_begin": (C.c_int, [_p]),
+    "opb_volume_halo_exchange_end": (C.c_int, [_p, C.POINTER(_sz), C.POINTER(_sz)]),
     "opb_prefilter_create": (C.c_int, [C.c_int, _p, C.c_int, C.c_int, C.POINTER(_p)]),
     "opb_prefilter_destroy": (None, [_p]),
     "opb_prefilter_run": (C.c_int, [_p, _p, C.c_int, C.c_float, C.c_int, C.c_double, C.c_double, _p, _p]),

@@ -100,6 +100,13 @@ __host__ __device__ __forceinline__ float ordered_to_float(unsigned int u)
 #endif
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // floor division / modulo of ints by a positive int
 __host__ __device__ __forceinline__ int floor_div(int a, int b)
 {
@@ -107,5 +114,34 @@ __host__ __device__ __forceinline__ int floor_div(int a, int b)
     return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
 }
 __host__ __device__ __forceinline__ int floor_mod(int a, int b) { return a - floor_div(a, b) * b; }
+
+// ---------------------------------------------------------------------------------------------------------
+// FP64 tensor-core op as a reduction primitive (the persistent solver loops of opb_icp.cu and opb_odometry.cu): a warp folds the
+// outer products c c^T of its 32 eight-component float vectors into an 8x8 double matrix held as two doubles per lane (lane L:
+// entries 2L, 2L+1 of the row-major matrix).  Products of floats are exact in double; accumulation is double.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// the warp's 32 vectors -> shared memory -> eight 8x8x4 outer-product accumulations (A = B^T = 8 components x 4 points).  The
+// eight products go to four independent accumulators (a dependent DMMA chain costs ~140 cycles per link, independent ones issue
+// every 16: scripts/micro/dmma_rate.cu) and are folded with plain additions.
+__device__ __forceinline__ void warp_fold_outer8(float *stage, int lane, const float *comp, double &c0, double &c1)
+{
+    *reinterpret_cast<float4 *>(stage + lane * 8) = make_float4(comp[0], comp[1], comp[2], comp[3]);
+    *reinterpret_cast<float4 *>(stage + lane * 8 + 4) = make_float4(comp[4], comp[5], comp[6], comp[7]);
+    __syncwarp();
+    double t0[4] = {0.0, 0.0, 0.0, 0.0}, t1[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+    {
+        const double v = (double)stage[(4 * j + (lane & 3)) * 8 + (lane >> 2)];
+        dmma_8x8x4(t0[j & 3], t1[j & 3], v, v);
+    }
+    __syncwarp();
+    c0 += (t0[0] + t0[1]) + (t0[2] + t0[3]);
+    c1 += (t1[0] + t1[1]) + (t1[2] + t1[3]);
+}
 
 } // namespace opb

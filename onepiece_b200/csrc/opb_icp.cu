@@ -44,12 +44,6 @@ struct IcpGrid
     int dim[3];
 };
 
-__device__ __forceinline__ unsigned long long global_timer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 
 struct IcpState // device-resident solver state
 {
@@ -1092,10 +1086,6 @@ constexpr int kLoop2Threads = 1024;
 constexpr int kLoop2Warps = kLoop2Threads / 32;
 constexpr int kLoop2Chunks = kLoop2Threads / 64; // groups that each sum every 16th partial
 
-__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b)
-{
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
 // entry (row * 8 + col) of the 8x8 sum matrix that feeds component k of the 30-scalar packet, -1: none.
 // mode 0 point-to-plane, 1 point-to-point, 2 closing CountInliers
 __host__ __device__ constexpr int packet_source(int mode, int k)
@@ -1212,25 +1202,6 @@ __device__ __forceinline__ bool loop2_components(const IcpArgs &a, const float *
     }
     return true;
 }
-// the warp's 32 vectors -> shared memory -> eight 8x8x4 outer-product accumulations (A = B^T = 8 components x 4 points).  The
-// eight products go to four independent accumulators (a dependent DMMA chain costs ~140 cycles per link, independent ones issue
-// every 16: scripts/micro/dmma_rate.cu) and are folded with plain additions.
-__device__ __forceinline__ void loop2_fold(float *stage, int lane, const float *comp, double &c0, double &c1)
-{
-    *reinterpret_cast<float4 *>(stage + lane * 8) = make_float4(comp[0], comp[1], comp[2], comp[3]);
-    *reinterpret_cast<float4 *>(stage + lane * 8 + 4) = make_float4(comp[4], comp[5], comp[6], comp[7]);
-    __syncwarp();
-    double t0[4] = {0.0, 0.0, 0.0, 0.0}, t1[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-    {
-        const double v = (double)stage[(4 * j + (lane & 3)) * 8 + (lane >> 2)];
-        dmma_8x8x4(t0[j & 3], t1[j & 3], v, v);
-    }
-    __syncwarp();
-    c0 += (t0[0] + t0[1]) + (t0[2] + t0[3]);
-    c1 += (t1[0] + t1[1]) + (t1[2] + t1[3]);
-}
 __device__ __forceinline__ void loop2_transform(const float *T, bool rigid, const float *T_full, float sx, float sy, float sz, float &px, float &py,
                                                 float &pz)
 {
@@ -1324,7 +1295,7 @@ __global__ void __launch_bounds__(kLoop2Threads, 1) icp_loop2_kernel(const __gri
                     if (final_pass) a.inlier[i] = inl;
                 }
             }
-            loop2_fold(stage, lane, comp, c0, c1);
+            warp_fold_outer8(stage, lane, comp, c0, c1);
         }
         // ---- the noted points: exact search (or, in the closing pass, the wider re-search), then the same fold ----
         unsigned int searched = 0;
@@ -1355,7 +1326,7 @@ __global__ void __launch_bounds__(kLoop2Threads, 1) icp_loop2_kernel(const __gri
                 const bool inl = loop2_components<PLANE>(a, T, final_pass, nn, sx, sy, sz, px, py, pz, comp);
                 if (final_pass) a.inlier[i] = inl;
             }
-            loop2_fold(stage, lane, comp, d0, d1);
+            warp_fold_outer8(stage, lane, comp, d0, d1);
         }
         c0 += d0;
         c1 += d1;
@@ -2113,15 +2084,22 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
         OPB_CUDA(cudaMemcpyAsync(c->h_sums, (const char *)c->d_state + offsetof(IcpState, packet), 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
     const size_t n_copy = pairs && pairs_cap && ns ? (pairs_cap < ns ? pairs_cap : ns) : 0;
+    bool pairs_direct = false;
     if (n_copy)
     {
         const int n_tiles = (int)((ns + kPairTile - 1) / kPairTile);
         icp_pair_count_kernel<<<n_tiles, kPairTile, 0, s>>>(c->d_inlier, (int)ns, c->d_pair_tiles);
         icp_pair_scan_kernel<<<1, 1024, 0, s>>>(c->d_pair_tiles, n_tiles);
         icp_pair_write_kernel<<<n_tiles, kPairTile, 0, s>>>(c->d_nn, c->d_inlier, (int)ns, c->d_pair_tiles, c->d_pairs, (unsigned long long)pairs_cap);
-        // the pairs follow on the same stream (one synchronisation for the whole call): the first n_local_pairs entries are the
-        // result, the rest of the caller's buffer up to min(pairs_cap, ns) is scratch
-        OPB_CUDA(cudaMemcpyAsync(pairs, c->d_pairs, n_copy * 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        // Into page-locked (or device) memory the pairs follow on the same stream (one synchronisation for the whole call): the
+        // first n_local_pairs entries are the result, the rest of the caller's buffer up to min(pairs_cap, ns) is scratch.
+        // Into pageable memory the runtime would stage the copy and keep this thread inside the driver until the stream
+        // has drained -- with a peer workspace of the same process still to launch the kernels ours waits for, that is a
+        // deadlock (until the exchange times out); such buffers get exactly n_local_pairs entries after the synchronisation.
+        cudaPointerAttributes attr;
+        pairs_direct = cudaPointerGetAttributes(&attr, pairs) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered;
+        cudaGetLastError();
+        if (pairs_direct) OPB_CUDA(cudaMemcpyAsync(pairs, c->d_pairs, n_copy * 2 * sizeof(int), cudaMemcpyDefault, s));
     }
     if (c->profiling) OPB_CUDA(cudaEventRecord(c->ev[2], s));
     OPB_CUDA(cudaGetLastError());
@@ -2160,6 +2138,11 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     }
     else
         for (int e = 0; e < 16; ++e) res->T[e] = nanf(""); // the reference divides by zero pairs here
+    if (n_copy && !pairs_direct)
+    {
+        const size_t n = res->n_local_pairs < pairs_cap ? res->n_local_pairs : pairs_cap;
+        OPB_CUDA(cudaMemcpy(pairs, c->d_pairs, n * 2 * sizeof(int), cudaMemcpyDeviceToHost));
+    }
     res->status = OPB_OK;
     return OPB_OK;
 }

@@ -227,6 +227,8 @@ static int mesh_count(opb_volume *v, int *n_slots_out, unsigned int **d_counts_o
     *n_tris = 0;
     *d_counts_out = nullptr;
     if (n == 0) return OPB_OK;
+    rc = volume_materialize(v); // packed volumes are meshed from their float mirror
+    if (rc) return rc;
     const size_t need = n * sizeof(unsigned int) + 16;
     if (v->mesh_scratch_bytes < need)
     {

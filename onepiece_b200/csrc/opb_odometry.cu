@@ -211,6 +211,31 @@ struct OdoArgs
     const float *T_override; // identity for the NormalizeIntensity correspondences, else nullptr (= st->T)
 };
 
+// the candidate of source pixel s (its target pixel and transformed depth, or -1): a pure function of the pixel and the pose
+__device__ __forceinline__ int2 candidate_of(const float *__restrict__ sd, const float *__restrict__ td, const float *sM, int w, int h, int s)
+{
+    const int i = s / w, j = s - i * w;
+    const float d_s = sd[s];
+    int2 c = make_int2(-1, 0);
+    if (d_s == d_s)
+    {
+        float uv[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            uv[r] = fadd(fadd(fmul(fmul(d_s, sM[r * 3]), (float)j), fadd(fmul(fmul(d_s, sM[r * 3 + 1]), (float)i), fmul(d_s, sM[r * 3 + 2]))),
+                         sM[9 + r]);
+        const float tds = uv[2];
+        // (int)(x / z + 0.5): float division, double add, truncation (x86 semantics)
+        const int u_t = cvtt_x86(__dadd_rn((double)fdiv(uv[0], tds), 0.5));
+        const int v_t = cvtt_x86(__dadd_rn((double)fdiv(uv[1], tds), 0.5));
+        if (u_t >= 0 && u_t < w && v_t >= 0 && v_t < h)
+        {
+            const float d_t = td[v_t * w + u_t];
+            if (d_t == d_t && (double)fabsf(fsub(d_t, tds)) < 0.05) c = make_int2(v_t * w + u_t, __float_as_int(tds));
+        }
+    }
+    return c;
+}
 __device__ __forceinline__ void candidates_phase(const OdoArgs &a, float *sM)
 {
     __syncthreads(); // the previous user of the shared block is done
@@ -219,30 +244,7 @@ __device__ __forceinline__ void candidates_phase(const OdoArgs &a, float *sM)
     const int w = a.cam.w, h = a.cam.h, n = w * h;
     const float *__restrict__ sd = a.src.img[1][a.level];
     const float *__restrict__ td = a.tgt.img[1][a.level];
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x)
-    {
-        const int i = s / w, j = s - i * w;
-        const float d_s = sd[s];
-        int2 c = make_int2(-1, 0);
-        if (d_s == d_s)
-        {
-            float uv[3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-                uv[r] = fadd(fadd(fmul(fmul(d_s, sM[r * 3]), (float)j), fadd(fmul(fmul(d_s, sM[r * 3 + 1]), (float)i), fmul(d_s, sM[r * 3 + 2]))),
-                             sM[9 + r]);
-            const float tds = uv[2];
-            // (int)(x / z + 0.5): float division, double add, truncation (x86 semantics)
-            const int u_t = cvtt_x86(__dadd_rn((double)fdiv(uv[0], tds), 0.5));
-            const int v_t = cvtt_x86(__dadd_rn((double)fdiv(uv[1], tds), 0.5));
-            if (u_t >= 0 && u_t < w && v_t >= 0 && v_t < h)
-            {
-                const float d_t = td[v_t * w + u_t];
-                if (d_t == d_t && (double)fabsf(fsub(d_t, tds)) < 0.05) c = make_int2(v_t * w + u_t, __float_as_int(tds));
-            }
-        }
-        a.cand[s] = c;
-    }
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) a.cand[s] = candidate_of(sd, td, sM, w, h, s);
 }
 __global__ void __launch_bounds__(kOdoThreads) odo_candidates_kernel(OdoArgs a)
 {
@@ -285,19 +287,35 @@ __device__ __forceinline__ double warp_sum_d(double v)
 
 // One Jacobian row pair of a correspondence, float arithmetic in the reference's order (DenseOdometryFunction.cpp:146-296);
 // adds its products to the per-thread double accumulators acc[0..20] (upper triangle of J^T J), acc[21..26] (J^T r), acc[27] (r^2)
-template <int TERM>
-__device__ __forceinline__ void accumulate_rows(const OdoArgs &a, const float *T, int s, int t, double *acc)
+struct RowCtx // what compute_rows reads of one pyramid level
 {
-    const int l = a.level, w = a.cam.w;
+    const float *sgray, *sdepth, *tgray, *tdepth, *tgx, *tgy, *tdx, *tdy;
+    float fx, fy, cx, cy;
+    int w;
+};
+__device__ __forceinline__ RowCtx row_ctx(const OdoArgs &a)
+{
+    const int l = a.level;
+    RowCtx c;
+    c.sgray = a.src.img[0][l]; c.sdepth = a.src.img[1][l];
+    c.tgray = a.tgt.img[0][l]; c.tdepth = a.tgt.img[1][l];
+    c.tgx = a.tgt.img[2][l]; c.tgy = a.tgt.img[3][l]; c.tdx = a.tgt.img[4][l]; c.tdy = a.tgt.img[5][l];
+    c.fx = a.cam.fx; c.fy = a.cam.fy; c.cx = a.cam.cx; c.cy = a.cam.cy; c.w = a.cam.w;
+    return c;
+}
+template <int TERM>
+__device__ __forceinline__ int compute_rows(const RowCtx &a, const float *T, int s, int t, float (*J)[6], float *res)
+{
+    const int w = a.w;
     const int v_s = s / w, u_s = s - v_s * w;
-    const float fx = a.cam.fx, fy = a.cam.fy;
+    const float fx = a.fx, fy = a.fy;
     // source_XYZ[v_s][u_s] (TransformToMatXYZ, Geometry.cpp:72-106)
-    const float z = a.src.img[1][l][s];
+    const float z = a.sdepth[s];
     float p0 = -1.0f, p1 = -1.0f, p2 = -1.0f;
     if (z > 0)
     {
-        p0 = fdiv(fmul(fsub((float)u_s, a.cam.cx), z), fx);
-        p1 = fdiv(fmul(fsub((float)v_s, a.cam.cy), z), fy);
+        p0 = fdiv(fmul(fsub((float)u_s, a.cx), z), fx);
+        p1 = fdiv(fmul(fsub((float)v_s, a.cy), z), fy);
         p2 = z;
     }
     // R * p + t: Eigen's fixed-size order m0 + (m1 + m2), then + t
@@ -306,12 +324,11 @@ __device__ __forceinline__ void accumulate_rows(const OdoArgs &a, const float *T
     const float q2 = fadd(fadd(fmul(T[2], p0), fadd(fmul(T[6], p1), fmul(T[10], p2))), T[14]);
     const float invz = (float)(1.0 / (double)q2);
     const float sq = 0.70710678118654752440f; // (float)sqrt(0.5) == (float)sqrt(1 - 0.5)
-    float J[2][6], res[2];
     int rows = 0;
     if (TERM == 0 || TERM == 1)
     {
-        const float diff = fsub(a.tgt.img[0][l][t], a.src.img[0][l][s]);
-        const float gx = fmul(0.125f, a.tgt.img[2][l][t]), gy = fmul(0.125f, a.tgt.img[3][l][t]);
+        const float diff = fsub(a.tgray[t], a.sgray[s]);
+        const float gx = fmul(0.125f, a.tgx[t]), gy = fmul(0.125f, a.tgy[t]);
         const float c0 = fmul(fmul(gx, fx), invz), c1 = fmul(fmul(gy, fy), invz);
         const float c2 = fmul(-fadd(fmul(c0, q0), fmul(c1, q1)), invz);
         float *j = J[rows];
@@ -330,10 +347,10 @@ __device__ __forceinline__ void accumulate_rows(const OdoArgs &a, const float *T
     }
     if (TERM == 0 || TERM == 2)
     {
-        float gx = fmul(0.125f, a.tgt.img[4][l][t]), gy = fmul(0.125f, a.tgt.img[5][l][t]);
+        float gx = fmul(0.125f, a.tdx[t]), gy = fmul(0.125f, a.tdy[t]);
         if (gx != gx) gx = 0.0f;
         if (gy != gy) gy = 0.0f;
-        const float diff = fsub(a.tgt.img[1][l][t], q2);
+        const float diff = fsub(a.tdepth[t], q2);
         const float d0 = fmul(fmul(gx, fx), invz), d1 = fmul(fmul(gy, fy), invz);
         const float d2 = fmul(-fadd(fmul(d0, q0), fmul(d1, q1)), invz);
         float *j = J[rows];
@@ -350,6 +367,14 @@ __device__ __forceinline__ void accumulate_rows(const OdoArgs &a, const float *T
         else res[rows] = diff;
         ++rows;
     }
+    return rows;
+}
+template <int TERM>
+__device__ __forceinline__ void accumulate_rows(const OdoArgs &a, const float *T, int s, int t, double *acc)
+{
+    float J[2][6], res[2];
+    const RowCtx ctx = row_ctx(a);
+    const int rows = compute_rows<TERM>(ctx, T, s, t, J, res);
 #pragma unroll
     for (int r = 0; r < 2; ++r)
     {
@@ -365,26 +390,47 @@ __device__ __forceinline__ void accumulate_rows(const OdoArgs &a, const float *T
     }
 }
 
-// the pose update of DoSingleIteration (DenseOdometryFunction.cpp:402-411), run by one thread of the last CTA
+// the pose update of DoSingleIteration (DenseOdometryFunction.cpp:402-411) from the 29-scalar packet: T <- exp(delta) * T.  One thread.
+__device__ __noinline__ void odo_solve_core(const double *P, float *T)
+{
+    double JTJ[36], nJTr[6], x[6], dT[16];
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int q = p; q < 6; ++q)
+        {
+            const double v = P[p * 6 - (p * (p - 1)) / 2 + (q - p)]; // position of (p, q) in the row-wise upper triangle
+            JTJ[p * 6 + q] = v;
+            JTJ[q * 6 + p] = v;
+        }
+#pragma unroll
+    for (int p = 0; p < 6; ++p) nJTr[p] = -P[21 + p];
+    linalg::solve_normal_equations6(JTJ, nJTr, x);
+#pragma unroll
+    for (int p = 0; p < 6; ++p) x[p] = (double)(float)x[p]; // the reference's delta is float32
+    linalg::se3_exp(x, dT);
+    float dTf[16], Tn[16];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dTf[c * 4 + r] = (float)dT[r * 4 + c];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            Tn[c * 4 + r] = fadd(fadd(fadd(fmul(dTf[r], T[c * 4]), fmul(dTf[4 + r], T[c * 4 + 1])), fmul(dTf[8 + r], T[c * 4 + 2])),
+                                 fmul(dTf[12 + r], T[c * 4 + 3]));
+#pragma unroll
+    for (int e = 0; e < 16; ++e) T[e] = Tn[e];
+}
+// ... on the device-resident state, run by one thread of the last CTA (separate-launch form and first persistent form)
 __device__ void solve_and_update(const OdoArgs &a, OdoState *st)
 {
     const double *P = st->packet;
     const int n = (int)(P[28] + 0.5);
-    double JTJ[36], nJTr[6], x[6], dT[16];
-    int k = 0;
-    for (int p = 0; p < 6; ++p)
-        for (int q = p; q < 6; ++q) { JTJ[p * 6 + q] = P[k]; JTJ[q * 6 + p] = P[k]; ++k; }
-    for (int p = 0; p < 6; ++p) nJTr[p] = -P[21 + p];
-    linalg::solve_normal_equations6(JTJ, nJTr, x);
-    for (int p = 0; p < 6; ++p) x[p] = (double)(float)x[p]; // the reference's delta is float32
-    linalg::se3_exp(x, dT);
-    float dTf[16], Tn[16];
-    for (int r = 0; r < 4; ++r)
-        for (int c = 0; c < 4; ++c) dTf[c * 4 + r] = (float)dT[r * 4 + c];
-    for (int c = 0; c < 4; ++c)
-        for (int r = 0; r < 4; ++r)
-            Tn[c * 4 + r] = fadd(fadd(fadd(fmul(dTf[r], st->T[c * 4]), fmul(dTf[4 + r], st->T[c * 4 + 1])), fmul(dTf[8 + r], st->T[c * 4 + 2])),
-                                 fmul(dTf[12 + r], st->T[c * 4 + 3]));
+    float Tn[16];
+    for (int e = 0; e < 16; ++e) Tn[e] = st->T[e];
+    odo_solve_core(P, Tn);
     for (int e = 0; e < 16; ++e) st->T[e] = Tn[e];
     const int it = st->iteration;
     if (it < kMaxTrace)
@@ -556,6 +602,273 @@ __global__ void __launch_bounds__(kOdoThreads, 2) odo_loop_kernel(OdoLoopArgs L)
                 a.st->phase_ns[0] += t1 - t0; a.st->phase_ns[1] += t2 - t1; a.st->phase_ns[2] += t3 - t2; a.st->phase_ns[3] += t4 - t3;
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// MultiScaleComputing, second persistent form (the default).  Where the first form's 19 us per iteration go, measured
+// (profiles/r02_odo_loop_kernel_ncu_full_before.md, opb_odometry_last_phases): 1.4 us candidates, 1.5 us grid barrier, 6 us in which
+// every thread keeps 29 double sums and a warp folds them with 290 shuffles, 10 us in which 295 CTAs wait for one CTA to sum 296
+// partials and for one of its threads to solve.  This form removes the first barrier, the per-thread sums and the serial owner:
+//   * the candidate of a pixel is a pure function of the pixel and the pose (candidate_of), so the acceptance chain of pixel s
+//     recomputes the candidates of the pixels it visits instead of reading a list other CTAs wrote: one phase, no barrier between
+//     candidates and acceptance (the chain is 0 or 1 steps long for almost every pixel);
+//   * the sums are an 8x8 outer-product accumulation on the FP64 tensor-core op (warp_fold_outer8): a Jacobian row contributes
+//     c c^T with c = (J0..J5, r, 1) -- J^T J, J^T r, r^2 and the count are entries of that matrix; the hybrid term's second row
+//     goes in with c = (J0..J5, r, 0).  Products of floats are exact in double (the separate-launch kernels round them to float
+//     first, as the oracle does: the two forms agree to ~1e-8 relative in the sums, far inside the 1e-6 pose gate);
+//   * one CTA of 1024 threads per SM publishes its 8x8 partial, announces it on one counter, waits until all have, and then EVERY
+//     CTA sums all partials in the same fixed order and solves the same 6x6 system: nobody waits for an owner, the pose lives
+//     in shared memory, the result is deterministic and identical on all CTAs (CTA 0 records the trace).
+// The candidate / accept lists that the ordered compaction after the loop reads are written by the iterations of `list_level`.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kOdo2Threads = 1024;
+constexpr int kOdo2Warps = kOdo2Threads / 32;
+constexpr int kOdo2Chunks = kOdo2Threads / 64; // groups that each sum every 16th partial
+
+// entries of the row-major 8x8 sum matrix that feed the 29-scalar packet: upper triangle of the leading 6x6, column 6 down to
+// (6,6), and (7,7)
+__host__ __device__ constexpr unsigned long long odo2_need_mask()
+{
+    unsigned long long m = 0;
+    for (int p = 0; p < 6; ++p)
+        for (int q = p; q < 7; ++q) m |= 1ull << (p * 8 + q);
+    m |= 1ull << (6 * 8 + 6);
+    m |= 1ull << (7 * 8 + 7);
+    return m;
+}
+// ... and where component k of the packet comes from
+__host__ __device__ constexpr int odo2_packet_source(int k)
+{
+    if (k < 21)
+    {
+        int p = 0, first = 0;
+        while (k >= first + (6 - p)) { first += 6 - p; ++p; }
+        return p * 8 + p + (k - first);
+    }
+    if (k < 27) return (k - 21) * 8 + 6;
+    return k == 27 ? 6 * 8 + 6 : (k == 28 ? 7 * 8 + 7 : -1);
+}
+struct Odo2Shared
+{
+    union
+    {
+        float stage[kOdo2Warps][32 * 8]; // during the trips: per warp, 32 rows x 8 components
+        double wsum[kOdo2Warps][64];     // after the trips: per-warp 8x8 sums
+        double chunk[kOdo2Chunks][64];   // partial sums of the cross-CTA reduction
+    } u;
+    double sum64[64];
+    double packet[kOdoPacket];
+    float T[16];
+    float M[12];
+    RowCtx ctx;
+    int break_level, iteration, last_count;
+    unsigned long long t[5], ph[4]; // profiling stamps of CTA 0
+};
+struct OdoLoop2Args
+{
+    OdoArgs base;
+    OdoCam cams[kMaxLevels];
+    int iterations[kMaxLevels];
+    int levels;
+    int list_level;       // iterations of this level write a.cand / a.accepted (the compaction after the loop reads them)
+    double *partials;     // [2][gridDim.x][64]
+    unsigned int *sync;   // arrivals, monotonic over the launch
+};
+template <int TERM>
+__global__ void __launch_bounds__(kOdo2Threads, 1) odo_loop2_kernel(const __grid_constant__ OdoLoop2Args L)
+{
+    __shared__ Odo2Shared sh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_cta = gridDim.x;
+    const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
+    OdoState *st = L.base.st;
+    if (threadIdx.x < 16) sh.T[threadIdx.x] = st->T[threadIdx.x];
+    if (threadIdx.x == 32) { sh.break_level = -1; sh.iteration = 0; sh.last_count = 0; }
+    if (threadIdx.x < 4) sh.ph[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned int n_sync = 0; // barriers passed so far, identical in every thread of the grid
+    for (int l = L.levels - 1; l >= 0; --l)
+    {
+        const OdoCam cam = L.cams[l];
+        const int w = cam.w, h = cam.h, n = w * h;
+        const int n_trips = (n + 31) >> 5;
+        // consecutive trips go to different CTAs: the coarse levels keep every SM's load pipes busy instead of a few CTAs'
+        const int first_trip = warp * n_cta + blockIdx.x, trip_step = kOdo2Warps * n_cta;
+        const float *__restrict__ sd = L.base.src.img[1][l];
+        const float *__restrict__ td = L.base.tgt.img[1][l];
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            RowCtx c;
+            c.sgray = L.base.src.img[0][l]; c.sdepth = L.base.src.img[1][l];
+            c.tgray = L.base.tgt.img[0][l]; c.tdepth = L.base.tgt.img[1][l];
+            c.tgx = L.base.tgt.img[2][l]; c.tgy = L.base.tgt.img[3][l]; c.tdx = L.base.tgt.img[4][l]; c.tdy = L.base.tgt.img[5][l];
+            c.fx = cam.fx; c.fy = cam.fy; c.cx = cam.cx; c.cy = cam.cy; c.w = cam.w;
+            sh.ctx = c;
+        }
+        const bool lists = l == L.list_level;
+        for (int j = 0; j < L.iterations[l]; ++j)
+        {
+            if (sh.break_level == l) break; // every CTA computed the same value
+            if (stamp) sh.t[0] = timer_ns();
+            if (threadIdx.x == 0) warp_matrices(cam, sh.T, sh.M, sh.M + 9);
+            __syncthreads();
+            double c0 = 0.0, c1 = 0.0;
+            float *stage = sh.u.stage[warp];
+            for (int trip = first_trip; trip < n_trips; trip += trip_step)
+            {
+                const int s = trip * 32 + lane;
+                float J[2][6], res[2];
+                int rows = 0;
+                bool ok = false;
+                if (s < n)
+                {
+                    int2 c = candidate_of(sd, td, sh.M, w, h, s);
+                    const int t_first = c.x;
+                    if (lists) L.base.cand[s] = c;
+                    // AddElementToCorrespondenceMap resolved as in resolve_accept, the visited candidates recomputed
+                    if (c.x >= 0)
+                    {
+                        ok = true;
+                        int cur = s;
+                        for (;;)
+                        {
+                            const int t = c.x;
+                            if (t >= cur) break;
+                            const int2 ct = candidate_of(sd, td, sh.M, w, h, t);
+                            if (ct.x < 0) break;
+                            if (__int_as_float(ct.y) > __int_as_float(c.y)) break;
+                            ok = !ok;
+                            cur = t;
+                            c = ct;
+                        }
+                    }
+                    if (lists) L.base.accepted[s] = ok;
+                    if (ok) rows = compute_rows<TERM>(sh.ctx, sh.T, s, t_first, J, res);
+                }
+                float comp[8];
+#pragma unroll
+                for (int e = 0; e < 6; ++e) comp[e] = rows > 0 ? J[0][e] : 0.0f;
+                comp[6] = rows > 0 ? res[0] : 0.0f;
+                comp[7] = ok ? 1.0f : 0.0f;
+                warp_fold_outer8(stage, lane, comp, c0, c1);
+                if (TERM == 0)
+                {
+#pragma unroll
+                    for (int e = 0; e < 6; ++e) comp[e] = rows > 1 ? J[1][e] : 0.0f;
+                    comp[6] = rows > 1 ? res[1] : 0.0f;
+                    comp[7] = 0.0f;
+                    warp_fold_outer8(stage, lane, comp, c0, c1);
+                }
+            }
+            if (stamp) sh.t[1] = timer_ns();
+            // ---- CTA partial ----
+            __syncthreads(); // every warp is done with its staging area (aliased below)
+            *reinterpret_cast<double2 *>(&sh.u.wsum[warp][2 * lane]) = make_double2(c0, c1);
+            __syncthreads();
+            constexpr unsigned long long need = odo2_need_mask();
+            const int e = threadIdx.x & 63, grp = threadIdx.x >> 6;
+            const bool needed = (need >> e) & 1ull;
+            double v = 0.0;
+            if (needed && grp < 8)
+                v = (sh.u.wsum[4 * grp][e] + sh.u.wsum[4 * grp + 1][e]) + (sh.u.wsum[4 * grp + 2][e] + sh.u.wsum[4 * grp + 3][e]);
+            __syncthreads();
+            if (grp < 8) sh.u.chunk[grp][e] = v;
+            __syncthreads();
+            double *mine = L.partials + ((size_t)(n_sync & 1u) * n_cta + blockIdx.x) * 64;
+            if (threadIdx.x < 64 && needed)
+            {
+                double t = 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) t += sh.u.chunk[k][e];
+                __stcg(&mine[e], t);
+            }
+            __threadfence();
+            __syncthreads();
+            // ---- arrive, wait for everybody ----
+            const double *all = L.partials + (size_t)(n_sync & 1u) * n_cta * 64;
+            ++n_sync;
+            if (threadIdx.x == 0)
+            {
+                atomicAdd(L.sync, 1u);
+                const unsigned int want = n_sync * (unsigned int)n_cta;
+                while (*(volatile unsigned int *)L.sync < want) { }
+                __threadfence();
+            }
+            __syncthreads();
+            if (stamp) sh.t[2] = timer_ns();
+            // ---- all partials -> the 8x8 sums, in one fixed order, on every CTA ----
+            {
+                double t = 0.0;
+                if (needed)
+                {
+                    if (n_cta <= kOdo2Chunks * 10)
+                    {
+                        double ld[10];
+#pragma unroll
+                        for (int u = 0; u < 10; ++u)
+                        {
+                            const int b = grp + u * kOdo2Chunks;
+                            ld[u] = b < n_cta ? __ldcg(&all[(size_t)b * 64 + e]) : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 10; ++u) t += ld[u];
+                    }
+                    else
+                        for (int b = grp; b < n_cta; b += kOdo2Chunks) t += __ldcg(&all[(size_t)b * 64 + e]);
+                }
+                sh.u.chunk[grp][e] = t;
+                __syncthreads();
+                if (threadIdx.x < 64)
+                {
+                    double tot = 0.0;
+                    if (needed)
+#pragma unroll
+                        for (int k = 0; k < kOdo2Chunks; ++k) tot += sh.u.chunk[k][e];
+                    sh.sum64[e] = tot;
+                }
+                __syncthreads();
+                if (threadIdx.x < kOdoPacket)
+                {
+                    const int src = odo2_packet_source(threadIdx.x);
+                    sh.packet[threadIdx.x] = src >= 0 ? sh.sum64[src] : 0.0;
+                }
+                __syncthreads();
+            }
+            if (stamp) sh.t[3] = timer_ns();
+            // ---- the same solve on every CTA (DoSingleIteration's tail, MultiScaleComputing's early exit) ----
+            if (threadIdx.x == 0)
+            {
+                const int cnt = (int)(sh.packet[28] + 0.5);
+                odo_solve_core(sh.packet, sh.T);
+                const int it = sh.iteration;
+                if (blockIdx.x == 0 && it < kMaxTrace)
+                {
+                    st->trace_count[it] = cnt;
+                    for (int k = 0; k < 16; ++k) st->trace_T[it][k] = sh.T[k];
+                }
+                sh.iteration = it + 1;
+                sh.last_count = cnt;
+                if ((double)fdiv((float)cnt, (float)L.base.full_pixels) > 0.9) sh.break_level = l;
+            }
+            __syncthreads();
+            if (stamp)
+            {
+                sh.t[4] = timer_ns();
+                for (int k = 0; k < 4; ++k) sh.ph[k] += sh.t[k + 1] - sh.t[k];
+            }
+        }
+    }
+    if (stamp)
+    {
+        for (int k = 0; k < 16; ++k) st->T[k] = sh.T[k];
+        for (int k = 0; k < kOdoPacket; ++k) st->packet[k] = sh.packet[k];
+        st->iteration = sh.iteration;
+        st->last_count = sh.last_count;
+        st->break_level = sh.break_level;
+        for (int k = 0; k < 4; ++k) st->phase_ns[k] += sh.ph[k];
+        st->tail_ns += sh.ph[2] + sh.ph[3];
     }
 }
 
@@ -930,6 +1243,8 @@ struct opb_odometry
     int *d_mean_totals = nullptr;   // ... and their step totals per binade
     unsigned int *d_sync = nullptr; // barrier words of the persistent loop kernel
     int coop_ctas_per_sm = 0;       // resident CTAs per SM of odo_loop_kernel; 0: cooperative launch unavailable
+    bool loop2_ok = false;          // odo_loop2_kernel (one CTA of 1024 threads per SM) can be launched cooperatively
+    double *d_partials2 = nullptr;  // its per-CTA 8x8 partials, two generations
     bool profiling = false;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     float last_ms = 0;
@@ -995,7 +1310,7 @@ void opb_odometry_destroy(opb_odometry *o)
     cudaSetDevice(o->device);
     if (o->stream) cudaStreamSynchronize(o->stream);
     cudaFree(o->d_cand); cudaFree(o->d_accepted); cudaFree(o->d_partials); cudaFree(o->d_tiles); cudaFree(o->d_pairs);
-    cudaFree(o->d_corr_xyz); cudaFree(o->d_identity); cudaFree(o->d_tmp); cudaFree(o->d_state); cudaFree(o->d_sync); cudaFree(o->d_vals); cudaFree(o->d_mean_totals);
+    cudaFree(o->d_corr_xyz); cudaFree(o->d_identity); cudaFree(o->d_tmp); cudaFree(o->d_state); cudaFree(o->d_sync); cudaFree(o->d_partials2); cudaFree(o->d_vals); cudaFree(o->d_mean_totals);
     if (o->h_state) cudaFreeHost(o->h_state);
     for (int i = 0; i < 2; ++i) if (o->ev[i]) cudaEventDestroy(o->ev[i]);
     if (o->own_stream && o->stream) cudaStreamDestroy(o->stream);
@@ -1055,6 +1370,13 @@ int opb_odometry_create(const opb_odometry_desc *desc, opb_odometry **out)
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], odo_loop_kernel<1>, kOdoThreads, 0) == cudaSuccess &&
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], odo_loop_kernel<2>, kOdoThreads, 0) == cudaSuccess)
             o->coop_ctas_per_sm = occ[0] < occ[1] ? (occ[0] < occ[2] ? occ[0] : occ[2]) : (occ[1] < occ[2] ? occ[1] : occ[2]);
+        cudaGetLastError();
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], odo_loop2_kernel<0>, kOdo2Threads, 0) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], odo_loop2_kernel<1>, kOdo2Threads, 0) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], odo_loop2_kernel<2>, kOdo2Threads, 0) == cudaSuccess &&
+            occ[0] > 0 && occ[1] > 0 && occ[2] > 0 &&
+            cudaMalloc(&o->d_partials2, (size_t)2 * o->sm_count * 64 * sizeof(double)) == cudaSuccess)
+            o->loop2_ok = true;
         cudaGetLastError();
     }
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&o->ev[i]);
@@ -1276,7 +1598,25 @@ static int run_tracking(opb_odometry *o, opb_frame *S, opb_frame *T, int term, o
 {
     cudaStream_t s = o->stream;
     static const int k_persistent = getenv("OPB_ODO_PERSISTENT") ? atoi(getenv("OPB_ODO_PERSISTENT")) : 1;
-    if (k_persistent && o->coop_ctas_per_sm > 0)
+    int last_level = -1;
+    for (int l = 0; l < o->desc.levels && last_level < 0; ++l)
+        if (o->desc.iterations[l] > 0) last_level = l;
+    if (k_persistent == 1 && o->loop2_ok)
+    {
+        // second persistent form: one CTA of 1024 threads per SM, one grid barrier per iteration, every CTA sums and solves
+        OdoLoop2Args L;
+        L.base = make_args(o, S, T, 0, term);
+        for (int l = 0; l < kMaxLevels; ++l) { L.cams[l] = o->cams[l]; L.iterations[l] = l < o->desc.levels ? o->desc.iterations[l] : 0; }
+        L.levels = o->desc.levels;
+        L.list_level = last_level;
+        L.partials = o->d_partials2;
+        L.sync = o->d_sync;
+        OPB_CUDA(cudaMemsetAsync(o->d_sync, 0, 4 * sizeof(unsigned int), s));
+        void *kargs[] = {(void *)&L};
+        const void *fn = term == 0 ? (const void *)odo_loop2_kernel<0> : (term == 1 ? (const void *)odo_loop2_kernel<1> : (const void *)odo_loop2_kernel<2>);
+        OPB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(o->sm_count), dim3(kOdo2Threads), kargs, 0, s));
+    }
+    else if (k_persistent && o->coop_ctas_per_sm > 0)
     {
         OdoLoopArgs L;
         L.base = make_args(o, S, T, 0, term);
@@ -1299,9 +1639,6 @@ static int run_tracking(opb_odometry *o, opb_frame *S, opb_frame *T, int term, o
         }
     // the correspondences of the last executed iteration, in raster order (level 0 unless its iteration count is 0;
     // the reference then indexes the level-0 XYZ images with the coarser level's pixel coordinates, and so does this)
-    int last_level = -1;
-    for (int l = 0; l < o->desc.levels && last_level < 0; ++l)
-        if (o->desc.iterations[l] > 0) last_level = l;
     if (last_level >= 0) launch_compaction(o, last_level);
     const int n0 = (int)level_pixels(o, 0);
     odo_rmse_kernel<<<grid_for(o, n0), kOdoThreads, 0, s>>>(o->d_pairs, o->d_state, S->im.img[1][0], T->im.img[1][0], o->cams[0],

@@ -221,7 +221,8 @@ int opb_volume_transform(opb_volume *src, const float trans_cm[16], int nearest,
     *out = nullptr;
     OPB_CUDA(cudaSetDevice(src->desc.device));
     size_t n_src = 0;
-    int rc = opb_volume_num_cubes(src, &n_src); // synchronizes
+    int rc = volume_require_float(src, "opb_volume_transform");
+    if (rc == OPB_OK) rc = opb_volume_num_cubes(src, &n_src); // synchronizes
     if (rc) return rc;
     ResampleParams p;
     memcpy(p.fwd, trans_cm, sizeof(p.fwd));
@@ -292,7 +293,10 @@ int opb_volume_merge(opb_volume *dst, opb_volume *other)
     }
     OPB_CUDA(cudaSetDevice(dst->desc.device));
     size_t n_dst = 0, n_other = 0;
-    int rc = opb_volume_num_cubes(dst, &n_dst);
+    int rc = volume_require_float(dst, "opb_volume_merge");
+    if (rc == OPB_OK) rc = volume_require_float(other, "opb_volume_merge");
+    if (rc) return rc;
+    rc = opb_volume_num_cubes(dst, &n_dst);
     if (rc == OPB_OK) rc = opb_volume_num_cubes(other, &n_other);
     if (rc || n_other == 0) return rc;
     if (dst->n_ghost) { rc = halo_drop_ghosts(dst); if (rc) return rc; }

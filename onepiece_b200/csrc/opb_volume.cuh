@@ -33,7 +33,8 @@ struct FrameCounters
 
 struct VolumeDev
 {
-    float *pool;              // max_cubes * kSlotFloats
+    float *pool;              // max_cubes * kSlotFloats (OPB_STORAGE_PACKED16: the float mirror, materialised on demand, else NULL)
+    uint2 *pool16;            // OPB_STORAGE_PACKED16: max_cubes * 512 voxels of 8 bytes {half sdf | half weight << 16, b | g<<8 | r<<16}
     int *slot_ids;            // max_cubes * 3
     unsigned long long *keys; // table_cap
     int *vals;                // table_cap

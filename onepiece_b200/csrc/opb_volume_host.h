@@ -25,6 +25,8 @@ struct opb_volume
     int sm_count = 0;
     int integrate_grid = 0;
     int integrate_pipe_grid = 0; // grid of integrate_pipelined_kernel
+    int integrate_packed_grid = 0; // grid of integrate_packed_kernel
+    int integrate_bulk_grid = 0;   // grid of integrate_bulk_kernel
     // double-buffered device staging for host frames
     void *stage_depth[2] = {nullptr, nullptr};
     unsigned char *stage_bgr[2] = {nullptr, nullptr};
@@ -44,6 +46,12 @@ struct opb_volume
     int n_ghost = 0;
     void *halo_scratch = nullptr;
     size_t halo_scratch_bytes = 0;
+    // peer-memory exchange (opb_volume_halo_peer_*): this volume's receive box, the mapped boxes of the rank it exports to
+    // (dst) and of the rank it imports from (src), the device words of an exchange, the number of exchanges started
+    void *halo_box = nullptr, *halo_local = nullptr, *halo_dst = nullptr, *halo_src = nullptr;
+    size_t halo_box_cap = 0, halo_dst_cap = 0;
+    unsigned long long halo_epoch = 0;
+    bool halo_pending = false;
 
     // pool exhaustion (the reference's unordered_map is unbounded, CubeHandler.cpp:181-191): the kernels raise sticky flags in
     // mapped host memory; the synchronous calls grow the pool and re-run the frame for the cubes that found no slot, the
@@ -67,6 +75,8 @@ int volume_rebuild_table(opb_volume *v, int n_alloc);
 // doubles the block pool (at least min_cubes slots), keeps the cubes, rebuilds the table; OPB_ERR_CAPACITY when memory is short
 int volume_grow(opb_volume *v, long long min_cubes);
 int halo_drop_ghosts(opb_volume *v); // opb_halo.cu
+int volume_materialize(opb_volume *v);                          // packed volumes: float mirror up to date (enqueued on the stream)
+int volume_require_float(const opb_volume *v, const char *what); // OPB_ERR_UNSUPPORTED for packed volumes
 // opb_meshpost.cu: TriangleMesh::ClusteringSimplify on device-resident arrays (outputs are cudaMalloc'ed), and the download
 // of such a result into malloc'ed host buffers (frees the device copies)
 int clustering_simplify_device(int sm_count, cudaStream_t s, const float *d_points, const float *d_colors, size_t nv, const unsigned int *d_tri,

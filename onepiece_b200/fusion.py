@@ -38,11 +38,48 @@ def shard_range(n: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def attach_halo_peers(volume, rank: int, world: int, cap_cubes: int, device_index: int, group=None):
+    """Collective, once per volume: every rank creates its receive box for `cap_cubes` boundary cubes, the cudaIpc handles go
+    round the group, and each rank maps the boxes of rank-1 (it exports into it) and rank+1 (it acknowledges there).  After
+    this `exchange_halo` runs entirely on the device.  Returns the mapped pointers (hand them to `detach_halo_peers`)."""
+    import ctypes as C
+
+    from . import capi
+    if world <= 1:
+        return []
+    own, handle = volume.HaloPeerBuffer(cap_cubes)
+    handles = [None] * world
+    dist.all_gather_object(handles, (handle, cap_cubes), group=group)
+    dst, src = halo_peers(rank, world)
+    mapped, opened = {}, []
+    for r in {dst, src}:
+        p = C.c_void_p()
+        capi.check(capi.lib.opb_ipc_open(device_index, (C.c_ubyte * 64).from_buffer_copy(handles[r][0]), C.byref(p)))
+        mapped[r] = p.value
+        opened.append(p)
+    volume.HaloPeerAttach(mapped[dst], handles[dst][1], mapped[src])
+    dist.barrier(group=group)  # nobody exports before every box is mapped
+    return opened
+
+
+def detach_halo_peers(volume, opened, device_index: int, group=None):
+    from . import capi
+    if not opened:
+        return
+    volume.HaloPeerAttach(None, 0, None)
+    dist.barrier(group=group)  # peers may still be writing into this rank's box until they detached too
+    for p in opened:
+        capi.lib.opb_ipc_close(device_index, p)
+
+
 def exchange_halo(volume, rank: int, world: int, device="cpu", group=None) -> int:
     """Boundary-cube exchange before Marching Cubes.  Returns the number of ghost cubes imported.  Collective: every rank
-    of the group must call it."""
+    of the group must call it.  A volume with attached peer boxes (`attach_halo_peers`) does it in two kernel launches over
+    peer memory; otherwise the buffers travel through torch.distributed send / recv (the path the gloo tests exercise)."""
     if world <= 1:
         return 0
+    if getattr(volume, "HaloPeersAttached", None) and volume.HaloPeersAttached():
+        return volume.HaloExchangePeer()[1]
     dst, src = halo_peers(rank, world)
     n_send = volume.HaloCount()
     counts = torch.zeros(world, dtype=torch.int64, device=device)
@@ -105,14 +142,27 @@ class ShardedCubeHandler:
     (src/Integration/CubeHandler.h) for the calls the fusion mains make."""
 
     def __init__(self, camera, voxel_resolution=0.01, truncation=0.1, max_cubes=1 << 17, axis=0, slab=4, device_index=0,
-                 group=None, **kw):
+                 group=None, halo_cubes=None, **kw):
+        """halo_cubes: capacity of this rank's receive box for boundary cubes (default max_cubes / 4; 0: no peer boxes, the
+        exchange then goes through torch.distributed send / recv).  Collective when the group has more than one rank."""
         from .volume import CubeHandler
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.group = group
         self.device = torch.device("cuda", device_index)
+        self.device_index = device_index
         self.volume = CubeHandler(camera, voxel_resolution, truncation, max_cubes=max_cubes, device=device_index,
                                   shard=(self.rank, self.world, axis, slab), **kw)
+        cap = max(1024, max_cubes // 4) if halo_cubes is None else int(halo_cubes)
+        self._halo_maps = attach_halo_peers(self.volume, self.rank, self.world, cap, device_index, group) if cap > 0 else []
+
+    def close(self):
+        """Collective: unmaps the neighbours' boxes, then releases the volume."""
+        if self.volume is not None:
+            detach_halo_peers(self.volume, self._halo_maps, self.device_index, self.group)
+            self._halo_maps = []
+            self.volume.close()
+            self.volume = None
 
     def IntegrateImage(self, depth, rgb, pose):
         """Every rank is given the same frame and pose (the host program broadcasts or loads it per rank)."""

@@ -225,6 +225,35 @@ class CubeHandler:
     def HaloClear(self):
         capi.check(capi.lib.opb_volume_halo_clear(self._h))
 
+    # ... with the transport inside the kernels (peer memory over NVLink): see fusion.attach_halo_peers
+    def HaloPeerBuffer(self, cap_cubes: int):
+        """-> (device address of this volume's receive box, its 64-byte cudaIpc handle)"""
+        buf = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        capi.check(capi.lib.opb_volume_halo_peer_buffer(self._h, cap_cubes, C.byref(buf), handle))
+        return buf.value, bytes(handle)
+
+    def HaloPeerAttach(self, dst_buffer, dst_cap_cubes: int, src_buffer):
+        capi.check(capi.lib.opb_volume_halo_peer_attach(self._h, C.c_void_p(dst_buffer), dst_cap_cubes, C.c_void_p(src_buffer)))
+        self._halo_peers = bool(dst_buffer)
+
+    def HaloPeersAttached(self) -> bool:
+        return getattr(self, "_halo_peers", False)
+
+    def HaloExchangePeer(self):
+        """collective: -> (boundary cubes sent to rank-1, ghost cubes imported from rank+1)"""
+        ns, ni = C.c_size_t(0), C.c_size_t(0)
+        capi.check(capi.lib.opb_volume_halo_exchange_peer(self._h, C.byref(ns), C.byref(ni)))
+        return ns.value, ni.value
+
+    def HaloExchangeBegin(self):
+        capi.check(capi.lib.opb_volume_halo_exchange_begin(self._h))
+
+    def HaloExchangeEnd(self):
+        ns, ni = C.c_size_t(0), C.c_size_t(0)
+        capi.check(capi.lib.opb_volume_halo_exchange_end(self._h, C.byref(ns), C.byref(ni)))
+        return ns.value, ni.value
+
     def NumGhostCubes(self) -> int:
         n = C.c_size_t(0)
         capi.check(capi.lib.opb_volume_num_ghost_cubes(self._h, C.byref(n)))

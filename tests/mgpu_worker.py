@@ -34,6 +34,15 @@ def main():
         assert int(owned.item()) == len(ids), (int(owned.item()), len(ids))
         assert np.array_equal(canon_triangles(P, Cc), canon_triangles(opts, ocol)), "sharded mesh differs from the oracle mesh"
         assert len(tri) * 3 == len(P)
+    assert sh.volume.HaloPeersAttached()   # the exchange above went through the peer boxes, not through send / recv
+    # ... and the same exchange through torch.distributed send / recv imports the same number of ghosts
+    n_peer = fusion.exchange_halo(sh.volume, rank, world, sh.device)
+    sh.volume.HaloClear()
+    maps, sh._halo_maps = sh._halo_maps, []
+    fusion.detach_halo_peers(sh.volume, maps, local)
+    n_nccl = fusion.exchange_halo(sh.volume, rank, world, sh.device)
+    assert n_peer == n_nccl > 0, (n_peer, n_nccl)
+    sh.close()
     # 2. split ICP over peer memory vs the single-GPU call on this rank's device
     src, tgt, nrm = _icp_inputs(quarter=False)
     par = reg.ICPParameter(10, 0.05, 1.0)
@@ -82,6 +91,7 @@ def main():
         assert full_sum == whole.CountMesh()[0] > bare_sum, (full_sum, whole.CountMesh()[0], bare_sum)
         print(f"config 4 slice: {cubes} cubes over {world} ranks, {ghosts} boundary cubes exchanged "
               f"({ghosts * 1292 / 1e6:.1f} MB instead of {ghosts * 10240 / 1e6:.1f} MB), {full_sum} mesh vertices = unsharded")
+    sh4.close()
     dist.barrier()
     # 4. BASELINE.json config 5 in miniature: a DenseFusion-style loop -- per frame one ICP split over the ranks (6x6 packet
     #    exchanged over peer memory), the pose chained, the frame integrated into the partitioned volume -- then halo exchange
@@ -128,6 +138,7 @@ def main():
         print(f"config 5 slice: 5 frames tracked with split ICP (drift {1e3 * err:.2f} mm vs ground truth), {len(wi)} cubes, "
               f"{len(wp)} mesh vertices identical to the single-GPU pipeline")
     sp5.close()
+    sh5.close()
     dist.barrier()
     if rank == 0:
         print("MGPU OK")

@@ -71,6 +71,52 @@ def test_halo_exchange_between_shards_on_one_device(world, axis, slab):
     assert sum(s.CountMesh()[0] for s in shards) < full.CountMesh()[0]
 
 
+@pytest.mark.parametrize("world,axis,slab", [(2, 0, 2), (3, 1, 1)])
+def test_halo_exchange_through_peer_boxes_on_one_device(world, axis, slab):
+    """The exchange with the transport inside the kernels: every shard exports straight into the receive box of the previous
+    shard and imports from its own (plain device pointers here, cudaIpc mappings between processes).  Same mesh as the
+    unsharded volume, twice in a row (the acknowledgement lets the second export overwrite the box)."""
+    from onepiece_b200 import capi
+    from onepiece_b200.volume import CubeHandler
+    cam, res, frames, ids, vox, (opts, ocol) = small_scene()
+    full = CubeHandler(cam, res, max_cubes=4096)
+    shards = [CubeHandler(cam, res, max_cubes=4096, shard=(r, world, axis, slab)) for r in range(world)]
+    boxes = [s.HaloPeerBuffer(2048)[0] for s in shards]
+    for r, s in enumerate(shards):
+        s.HaloPeerAttach(boxes[(r - 1) % world], 2048, boxes[(r + 1) % world])
+        assert s.HaloPeersAttached()
+    for rounds in range(2):
+        d, c, pose = frames[rounds] if rounds < len(frames) else frames[-1]
+        full.IntegrateImage(d, c, pose)
+        for s in shards:
+            s.IntegrateImage(d, c, pose)
+            assert s.NumGhostCubes() == 0
+        expect = [s.HaloCount() for s in shards]
+        for s in shards:
+            s.HaloExchangeBegin()          # one host thread drives all ranks: enqueue everywhere, then collect
+        got = [s.HaloExchangeEnd() for s in shards]
+        for r in range(world):
+            assert got[r][0] == expect[r]
+            assert got[r][1] == expect[(r + 1) % world] == shards[r].NumGhostCubes()
+        fpts, fcol, _ = full.ExtractTriangleMesh()
+        parts = [s.ExtractTriangleMesh() for s in shards]
+        P = np.concatenate([p[0] for p in parts])
+        Cc = np.concatenate([p[1] for p in parts])
+        assert np.array_equal(canon_triangles(P, Cc), canon_triangles(fpts, fcol))
+    # a box that is too small is an error, not a truncated mesh
+    small = [CubeHandler(cam, res, max_cubes=4096, shard=(r, 2, 0, 1)) for r in range(2)]
+    sb = [s.HaloPeerBuffer(4)[0] for s in small]
+    for r, s in enumerate(small):
+        s.HaloPeerAttach(sb[1 - r], 4, sb[1 - r])
+        s.IntegrateImage(*frames[0])
+    for s in small:
+        s.HaloExchangeBegin()
+    for s in small:
+        with pytest.raises(capi.OpbError) as e:
+            s.HaloExchangeEnd()
+        assert e.value.code == capi.OPB_ERR_CAPACITY
+
+
 def test_halo_capacity_and_unsharded_volume():
     from onepiece_b200 import capi
     from onepiece_b200.volume import CubeHandler
