@@ -503,6 +503,12 @@ void opb_odometry_desc_default(opb_odometry_desc *desc);
 int opb_odometry_create(const opb_odometry_desc *desc, opb_odometry **out);
 void opb_odometry_destroy(opb_odometry *o);
 int opb_odometry_set_profiling(opb_odometry *o, int on);
+/* How MultiScaleComputing (Odometry.cpp:621-685) is launched: 1 (default) the second persistent form -- one cooperative launch for all
+ * levels and iterations, the 29 sums as 8x8 outer-product accumulations with EXACT float x float products; 2 the first persistent
+ * form and 0 one launch pair per iteration -- both round every product to float before the double accumulation, as the oracle
+ * does, so their sums equal the oracle's to the last bit.  The forms agree to ~1e-8 relative in the sums (far inside the 1e-6 pose
+ * gate); discrete per-iteration correspondence counts can differ by a few pixels on a 640x480 run.  -1 restores the default. */
+int opb_odometry_set_loop_form(opb_odometry *o, int form);
 /* CUDA-event time of the last tracking call (pre-processing of new frames included) and the mean time per solver
  * iteration that the last CTA spent on the fixed-order partial sum + 6x6 solve + pose update (%globaltimer) */
 int opb_odometry_last_timing(opb_odometry *o, float *tracking_ms, float *solve_tail_us);

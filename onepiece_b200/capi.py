@@ -181,6 +181,7 @@ SIGNATURES = {
     "opb_odometry_create": (C.c_int, [C.POINTER(OdometryDesc), C.POINTER(_p)]),
     "opb_odometry_destroy": (None, [_p]),
     "opb_odometry_set_profiling": (C.c_int, [_p, C.c_int]),
+    "opb_odometry_set_loop_form": (C.c_int, [_p, C.c_int]),
     "opb_odometry_last_phases": (C.c_int, [_p, _p]),
     "opb_odometry_last_timing": (C.c_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "opb_frame_create": (C.c_int, [_p, _p, _p, C.c_int, C.POINTER(_p)]),

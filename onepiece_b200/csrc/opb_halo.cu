@@ -116,7 +116,10 @@ __device__ __forceinline__ bool halo_wait(volatile unsigned long long *word, uns
 {
     const unsigned long long t0 = global_timer_ns();
     while (*word < want)
-        if (*(volatile int *)error || global_timer_ns() - t0 > 4000000000ull) { *error = 1; return false; }
+    {
+        if (*(volatile int *)error) return false; // the exchange already failed (time limit or capacity): keep the first reason
+        if (global_timer_ns() - t0 > 4000000000ull) { atomicCAS(error, 0, 1); return false; }
+    }
     return true;
 }
 
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(kHaloThreads) halo_export_peer_kernel(VolumeDe
     {
         __threadfence();
         const unsigned int n = *(volatile unsigned int *)&loc->n_sent;
-        if (n > dst_cap) loc->error = 3;
+        if (n > dst_cap) atomicCAS(&loc->error, 0, 3);
         *(volatile unsigned int *)&dst->count = n;
         __threadfence_system();
         *(volatile unsigned long long *)&dst->flag = epoch;
@@ -192,8 +195,8 @@ __global__ void __launch_bounds__(kHaloThreads) halo_import_peer_kernel(VolumeDe
             n = (int)*(volatile unsigned int *)&own->count;
             int n_alloc = *v.n_alloc;
             if (n_alloc > v.max_cubes) n_alloc = v.max_cubes;
-            if ((unsigned int)n > own_cap) { loc->error = 3; n = -1; }
-            else if ((long long)n_alloc + n_ghost + n > (long long)v.max_cubes) { loc->error = 2; n = -1; }
+            if ((unsigned int)n > own_cap) { atomicCAS(&loc->error, 0, 3); n = -1; }
+            else if ((long long)n_alloc + n_ghost + n > (long long)v.max_cubes) { atomicCAS(&loc->error, 0, 2); n = -1; }
         }
         s_n = n;
     }

@@ -259,7 +259,9 @@ __global__ void __launch_bounds__(kOdoThreads) odo_candidates_kernel(OdoArgs a)
 //   t >= s, t not a valid candidate, or d(t) > d(s)  ->  accept(s) = true
 //   otherwise                                         ->  accept(s) = !accept(t)
 // and t < s strictly along such a chain, so walking it terminates at an unconditional "true".
-__device__ __forceinline__ bool resolve_accept(const int2 *__restrict__ cand, int s, int2 c)
+// (no __restrict__ on the list: the persistent kernels write it in an earlier phase of the same launch, so its loads must stay
+// ordinary coherent loads -- a restrict-qualified const pointer lets the compiler use the non-coherent path)
+__device__ __forceinline__ bool resolve_accept(const int2 *cand, int s, int2 c)
 {
     if (c.x < 0) return false;
     bool acc = true;
@@ -609,10 +611,10 @@ __global__ void __launch_bounds__(kOdoThreads, 2) odo_loop_kernel(OdoLoopArgs L)
 // MultiScaleComputing, second persistent form (the default).  Where the first form's 19 us per iteration go, measured
 // (profiles/r02_odo_loop_kernel_ncu_full_before.md, opb_odometry_last_phases): 1.4 us candidates, 1.5 us grid barrier, 6 us in which
 // every thread keeps 29 double sums and a warp folds them with 290 shuffles, 10 us in which 295 CTAs wait for one CTA to sum 296
-// partials and for one of its threads to solve.  This form removes the first barrier, the per-thread sums and the serial owner:
-//   * the candidate of a pixel is a pure function of the pixel and the pose (candidate_of), so the acceptance chain of pixel s
-//     recomputes the candidates of the pixels it visits instead of reading a list other CTAs wrote: one phase, no barrier between
-//     candidates and acceptance (the chain is 0 or 1 steps long for almost every pixel);
+// partials and for one of its threads to solve.  This form removes the per-thread sums and the serial owner:
+//   * (measured and dropped: recomputing the candidates of the pixels an acceptance chain visits instead of reading the list,
+//     which would remove the mid-iteration barrier -- the chains are long, 35 pixels on average and up to 150 on the bench
+//     frames, and two dependent loads plus the projection per step cost more than the barrier: 0.58 ms per call against 0.55);
 //   * the sums are an 8x8 outer-product accumulation on the FP64 tensor-core op (warp_fold_outer8): a Jacobian row contributes
 //     c c^T with c = (J0..J5, r, 1) -- J^T J, J^T r, r^2 and the count are entries of that matrix; the hybrid term's second row
 //     goes in with c = (J0..J5, r, 0).  Products of floats are exact in double (the separate-launch kernels round them to float
@@ -663,7 +665,7 @@ struct Odo2Shared
     float M[12];
     RowCtx ctx;
     int break_level, iteration, last_count;
-    unsigned long long t[5], ph[4]; // profiling stamps of CTA 0
+    unsigned long long t[6], ph[4]; // profiling stamps of CTA 0
 };
 struct OdoLoop2Args
 {
@@ -708,12 +710,32 @@ __global__ void __launch_bounds__(kOdo2Threads, 1) odo_loop2_kernel(const __grid
             sh.ctx = c;
         }
         const bool lists = l == L.list_level;
+        int2 *cand = L.base.cand;
         for (int j = 0; j < L.iterations[l]; ++j)
         {
             if (sh.break_level == l) break; // every CTA computed the same value
             if (stamp) sh.t[0] = timer_ns();
             if (threadIdx.x == 0) warp_matrices(cam, sh.T, sh.M, sh.M + 9);
             __syncthreads();
+            // ---- candidates of every pixel (a pure function of the pixel and the pose), then a grid barrier: the acceptance chain
+            //      of a pixel reads the candidates of the pixels it visits ----
+            for (int trip = first_trip; trip < n_trips; trip += trip_step)
+            {
+                const int s = trip * 32 + lane;
+                if (s < n) cand[s] = candidate_of(sd, td, sh.M, w, h, s);
+            }
+            __threadfence();
+            __syncthreads();
+            ++n_sync;
+            if (threadIdx.x == 0)
+            {
+                atomicAdd(L.sync, 1u);
+                const unsigned int want = n_sync * (unsigned int)n_cta;
+                while (*(volatile unsigned int *)L.sync < want) { }
+                __threadfence();
+            }
+            __syncthreads();
+            if (stamp) sh.t[1] = timer_ns();
             double c0 = 0.0, c1 = 0.0;
             float *stage = sh.u.stage[warp];
             for (int trip = first_trip; trip < n_trips; trip += trip_step)
@@ -724,28 +746,10 @@ __global__ void __launch_bounds__(kOdo2Threads, 1) odo_loop2_kernel(const __grid
                 bool ok = false;
                 if (s < n)
                 {
-                    int2 c = candidate_of(sd, td, sh.M, w, h, s);
-                    const int t_first = c.x;
-                    if (lists) L.base.cand[s] = c;
-                    // AddElementToCorrespondenceMap resolved as in resolve_accept, the visited candidates recomputed
-                    if (c.x >= 0)
-                    {
-                        ok = true;
-                        int cur = s;
-                        for (;;)
-                        {
-                            const int t = c.x;
-                            if (t >= cur) break;
-                            const int2 ct = candidate_of(sd, td, sh.M, w, h, t);
-                            if (ct.x < 0) break;
-                            if (__int_as_float(ct.y) > __int_as_float(c.y)) break;
-                            ok = !ok;
-                            cur = t;
-                            c = ct;
-                        }
-                    }
+                    const int2 c = cand[s];
+                    ok = resolve_accept(cand, s, c); // AddElementToCorrespondenceMap, resolved along the chain
                     if (lists) L.base.accepted[s] = ok;
-                    if (ok) rows = compute_rows<TERM>(sh.ctx, sh.T, s, t_first, J, res);
+                    if (ok) rows = compute_rows<TERM>(sh.ctx, sh.T, s, c.x, J, res);
                 }
                 float comp[8];
 #pragma unroll
@@ -762,7 +766,7 @@ __global__ void __launch_bounds__(kOdo2Threads, 1) odo_loop2_kernel(const __grid
                     warp_fold_outer8(stage, lane, comp, c0, c1);
                 }
             }
-            if (stamp) sh.t[1] = timer_ns();
+            if (stamp) sh.t[2] = timer_ns();
             // ---- CTA partial ----
             __syncthreads(); // every warp is done with its staging area (aliased below)
             *reinterpret_cast<double2 *>(&sh.u.wsum[warp][2 * lane]) = make_double2(c0, c1);
@@ -776,7 +780,7 @@ __global__ void __launch_bounds__(kOdo2Threads, 1) odo_loop2_kernel(const __grid
             __syncthreads();
             if (grp < 8) sh.u.chunk[grp][e] = v;
             __syncthreads();
-            double *mine = L.partials + ((size_t)(n_sync & 1u) * n_cta + blockIdx.x) * 64;
+            double *mine = L.partials + ((size_t)(sh.iteration & 1) * n_cta + blockIdx.x) * 64;
             if (threadIdx.x < 64 && needed)
             {
                 double t = 0.0;
@@ -787,7 +791,7 @@ __global__ void __launch_bounds__(kOdo2Threads, 1) odo_loop2_kernel(const __grid
             __threadfence();
             __syncthreads();
             // ---- arrive, wait for everybody ----
-            const double *all = L.partials + (size_t)(n_sync & 1u) * n_cta * 64;
+            const double *all = L.partials + (size_t)(sh.iteration & 1) * n_cta * 64;
             ++n_sync;
             if (threadIdx.x == 0)
             {
@@ -797,7 +801,7 @@ __global__ void __launch_bounds__(kOdo2Threads, 1) odo_loop2_kernel(const __grid
                 __threadfence();
             }
             __syncthreads();
-            if (stamp) sh.t[2] = timer_ns();
+            if (stamp) sh.t[3] = timer_ns();
             // ---- all partials -> the 8x8 sums, in one fixed order, on every CTA ----
             {
                 double t = 0.0;
@@ -836,7 +840,7 @@ __global__ void __launch_bounds__(kOdo2Threads, 1) odo_loop2_kernel(const __grid
                 }
                 __syncthreads();
             }
-            if (stamp) sh.t[3] = timer_ns();
+            if (stamp) sh.t[4] = timer_ns();
             // ---- the same solve on every CTA (DoSingleIteration's tail, MultiScaleComputing's early exit) ----
             if (threadIdx.x == 0)
             {
@@ -855,8 +859,9 @@ __global__ void __launch_bounds__(kOdo2Threads, 1) odo_loop2_kernel(const __grid
             __syncthreads();
             if (stamp)
             {
-                sh.t[4] = timer_ns();
-                for (int k = 0; k < 4; ++k) sh.ph[k] += sh.t[k + 1] - sh.t[k];
+                sh.t[5] = timer_ns();
+                // candidates + barrier | acceptance + rows | publish + barrier + sum of partials | solve
+                sh.ph[0] += sh.t[1] - sh.t[0]; sh.ph[1] += sh.t[2] - sh.t[1]; sh.ph[2] += sh.t[4] - sh.t[2]; sh.ph[3] += sh.t[5] - sh.t[4];
             }
         }
     }
@@ -868,7 +873,7 @@ __global__ void __launch_bounds__(kOdo2Threads, 1) odo_loop2_kernel(const __grid
         st->last_count = sh.last_count;
         st->break_level = sh.break_level;
         for (int k = 0; k < 4; ++k) st->phase_ns[k] += sh.ph[k];
-        st->tail_ns += sh.ph[2] + sh.ph[3];
+        st->tail_ns += sh.t[5] - sh.t[3];
     }
 }
 
@@ -1243,6 +1248,7 @@ struct opb_odometry
     int *d_mean_totals = nullptr;   // ... and their step totals per binade
     unsigned int *d_sync = nullptr; // barrier words of the persistent loop kernel
     int coop_ctas_per_sm = 0;       // resident CTAs per SM of odo_loop_kernel; 0: cooperative launch unavailable
+    int loop_form = -1;             // opb_odometry_set_loop_form: -1 default (OPB_ODO_PERSISTENT, else 1)
     bool loop2_ok = false;          // odo_loop2_kernel (one CTA of 1024 threads per SM) can be launched cooperatively
     double *d_partials2 = nullptr;  // its per-CTA 8x8 partials, two generations
     bool profiling = false;
@@ -1394,6 +1400,13 @@ int opb_odometry_set_profiling(opb_odometry *o, int on)
 {
     if (!o) { set_error("odometry is NULL"); return OPB_ERR_INVALID; }
     o->profiling = on != 0;
+    return OPB_OK;
+}
+int opb_odometry_set_loop_form(opb_odometry *o, int form)
+{
+    if (!o) { set_error("odometry is NULL"); return OPB_ERR_INVALID; }
+    if (form < -1 || form > 2) { set_error("loop form %d: -1 default, 0 separate launches, 1 second persistent form, 2 first persistent form", form); return OPB_ERR_INVALID; }
+    o->loop_form = form;
     return OPB_OK;
 }
 int opb_odometry_last_phases(opb_odometry *o, uint64_t phase_ns[4])
@@ -1597,7 +1610,8 @@ static int run_tracking(opb_odometry *o, opb_frame *S, opb_frame *T, int term, o
                         size_t pairs_cap, float *corr_xyz)
 {
     cudaStream_t s = o->stream;
-    static const int k_persistent = getenv("OPB_ODO_PERSISTENT") ? atoi(getenv("OPB_ODO_PERSISTENT")) : 1;
+    static const int k_env = getenv("OPB_ODO_PERSISTENT") ? atoi(getenv("OPB_ODO_PERSISTENT")) : 1;
+    const int k_persistent = o->loop_form >= 0 ? o->loop_form : k_env;
     int last_level = -1;
     for (int l = 0; l < o->desc.levels && last_level < 0; ++l)
         if (o->desc.iterations[l] > 0) last_level = l;

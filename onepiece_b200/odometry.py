@@ -109,6 +109,11 @@ class Odometry:
     def set_profiling(self, on=True):
         capi.check(capi.lib.opb_odometry_set_profiling(self.handle, int(on)))
 
+    def SetLoopForm(self, form: int):
+        """1 (default): second persistent solver loop (exact products in the sums); 2 / 0: the forms that round every product to
+        float like the oracle (include/onepiece_b200.h, opb_odometry_set_loop_form)"""
+        capi.check(capi.lib.opb_odometry_set_loop_form(self.handle, int(form)))
+
     def last_tracking_ms(self):
         ms, tail = C.c_float(0), C.c_float(0)
         capi.check(capi.lib.opb_odometry_last_timing(self.handle, C.byref(ms), C.byref(tail)))

@@ -18,7 +18,8 @@ template <typename T> struct Ptr
 };
 struct ORB
 {
-    static Ptr<ORB> create() { return Ptr<ORB>(); }
+    static Ptr<ORB> create() { Ptr<ORB> p; p.p = std::make_shared<ORB>(); return p; }
+    void setMaxFeatures(int) {}
     template <typename... A> void detectAndCompute(A &&...) const {}
     template <typename... A> void detect(A &&...) const {}
     template <typename... A> void compute(A &&...) const {}
@@ -30,5 +31,14 @@ struct BFMatcher
     template <typename... A> void match(A &&...) const {}
 };
 template <typename... A> Mat findHomography(A &&...) { return Mat(); }
+// window / drawing calls of the sparse path's debug output (Odometry.cpp:125-131,154-157, ...): never reached by the dense path
+struct NoArray {};
+inline NoArray noArray() { return NoArray(); }
+struct DrawMatchesFlags { enum { DEFAULT = 0 }; };
+template <typename... A> void drawKeypoints(A &&...) {}
+template <typename... A> void drawMatches(A &&...) {}
+template <typename... A> void imshow(A &&...) {}
+template <typename... A> void destroyWindow(A &&...) {}
+inline int waitKey(int = 0) { return -1; }
 } // namespace cv
 #endif

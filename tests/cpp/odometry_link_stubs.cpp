@@ -5,4 +5,11 @@ namespace MILD
 {
 SparseMatcher::SparseMatcher(int, int, int, float) {}
 SparseMatcher::~SparseMatcher() {}
+// referenced by the reference's src/Odometry/SparseMatcher.cpp (linked into the reference-side build of the example mains)
+void SparseMatcher::train(cv::Mat) {}
+void SparseMatcher::search_8(cv::Mat, std::vector<cv::DMatch> &, int) {}
+void SparseMatcher::search_8_with_range(cv::Mat, std::vector<cv::DMatch> &, const std::vector<cv::KeyPoint> &, const std::vector<cv::KeyPoint> &, float,
+                                        int)
+{
+}
 } // namespace MILD

@@ -1,0 +1,146 @@
+"""The reference's example mains compiled UNMODIFIED (tests/cpp/Makefile, target `mains`) twice -- against the drop-in C++
+classes over libonepiece_b200.so and against the reference's own translation units -- run on the same synthetic dataset;
+the meshes they write must be the same mesh (see `same_mesh`).  Only test stand-ins are added: a headless Visualizer, cv::imread
+for raw image containers, the associate.txt / trajectory.txt readers (tests/cpp/mains/headless)."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from onepiece_b200 import scenes
+
+MAINS = os.path.join(ROOT, "tests", "cpp", "mains")
+CV_8UC3, CV_16UC1 = 16, 2
+
+
+def write_image(path, arr, cv_type):
+    arr = np.ascontiguousarray(arr)
+    with open(path, "wb") as f:
+        f.write(b"OPBIMG\0\0" + struct.pack("<iii", arr.shape[0], arr.shape[1], cv_type))
+        f.write(arr.tobytes())
+
+
+def make_dataset(root, n_frames, every):
+    """TUM-style directory: associate.txt, trajectory.txt, rgb/ and depth/ containers of the S2 room sequence (640x480, u16 mm)."""
+    cam = scenes.Camera()
+    os.makedirs(os.path.join(root, "rgb")); os.makedirs(os.path.join(root, "depth"))
+    with open(os.path.join(root, "associate.txt"), "w") as fa, open(os.path.join(root, "trajectory.txt"), "w") as ft:
+        for k in range(n_frames):
+            fa.write(f"{k / 30:.6f} rgb/{k}.png {k / 30:.6f} depth/{k}.png\n")
+            T = scenes.room_pose(k).astype(np.float32)
+            ft.write(" ".join(repr(float(x)) for x in T.reshape(-1)) + "\n")
+            if k % every == 0:
+                d, c, _ = scenes.room(cam, k)
+                write_image(os.path.join(root, "rgb", f"{k}.png"), c, CV_8UC3)
+                write_image(os.path.join(root, "depth", f"{k}.png"), d, CV_16UC1)
+
+
+def run_main(binary, args, cwd, timeout=900):
+    env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
+    r = subprocess.run([binary, *args], cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout, env=env)
+    assert r.returncode in (0, 1), r.stdout[-3000:]   # DenseFusion.cpp ends with `return 1`
+    return r.stdout
+
+
+def _have(*names):
+    return all(os.path.exists(os.path.join(MAINS, n)) for n in names)
+
+
+def read_ply(path):
+    """binary_little_endian PLY as tool::WritePLY lays it out (src/Tool/PLYManager.cpp:188-276): xyz float + rgb uchar, uchar-counted uint faces"""
+    raw = open(path, "rb").read()
+    end = raw.index(b"end_header\n") + len(b"end_header\n")
+    head = raw[:end].decode().split("\n")
+    nv = int([l for l in head if l.startswith("element vertex")][0].split()[-1])
+    nf = int([l for l in head if l.startswith("element face")][0].split()[-1])
+    has_color = any("red" in l for l in head)
+    vdt = np.dtype([("p", "<f4", 3)] + ([("c", "u1", 3)] if has_color else []))
+    v = np.frombuffer(raw, vdt, nv, end)
+    f = np.frombuffer(raw, np.dtype([("n", "u1"), ("i", "<u4", 3)]), nf, end + nv * vdt.itemsize)
+    assert (f["n"] == 3).all() and end + nv * vdt.itemsize + nf * 13 == len(raw)
+    return head, v["p"].copy(), (v["c"].copy() if has_color else None), f["i"].astype(np.int64)
+
+
+def same_mesh(a_path, b_path, tol):
+    """The two PLY files hold the same mesh: same header, one-to-one vertex match within `tol` metres (colours within one level),
+    identical triangle set under that match (orientation kept).  Byte equality is not attainable: the reference emits the cubes'
+    triangles in the iteration order of its std::unordered_map, the device in block-pool order, and ClusteringSimplify averages the
+    vertices of a grid cell in arrival order (MeshSimplification.cpp:579-657), so the cluster centres round differently in the
+    last bit.  Returns (vertices, triangles, largest vertex distance)."""
+    from scipy.spatial import cKDTree
+    ha, pa, ca, fa = read_ply(a_path)
+    hb, pb, cb, fb = read_ply(b_path)
+    assert ha == hb, "PLY headers differ (element counts, properties)"
+    dist, idx = cKDTree(pb).query(pa)
+    assert dist.max() <= tol, f"largest vertex distance {dist.max():.3e} m"
+    assert len(np.unique(idx)) == len(pa), "the vertex match is not one-to-one"
+    if ca is not None:
+        assert np.abs(ca.astype(int) - cb[idx].astype(int)).max() <= 1
+
+    def canon(f):
+        r = np.argmin(f, 1)
+        g = np.stack([np.take_along_axis(f, ((r + k) % 3)[:, None], 1)[:, 0] for k in range(3)], 1)
+        return g[np.lexsort((g[:, 2], g[:, 1], g[:, 0]))]
+    assert np.array_equal(canon(idx[fa]), canon(fb)), "triangle sets differ"
+    return len(pa), len(fa), float(dist.max())
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not _have("image_sequence_integration_dropin.bin", "image_sequence_integration_ref.bin"),
+                    reason="tests/cpp/mains/*.bin not built (needs the reference tree: make -C tests/cpp mains)")
+def test_image_sequence_integration_main_writes_the_reference_mesh(tmp_path):
+    """example/ImageSequenceIntegration.cpp:20-53: every 10th frame pre-filtered (ConvertDepthTo32F + BilateralFilter) and
+    integrated at 6.25 mm, the volume resampled with TransformNearest(poses[n/2]), Marching Cubes, ClusteringSimplify, PLY."""
+    data = tmp_path / "data"
+    make_dataset(str(data), 21, 10)
+    for kind in ("ref", "dropin"):
+        cwd = tmp_path / kind
+        cwd.mkdir()
+        log = run_main(os.path.join(MAINS, f"image_sequence_integration_{kind}.bin"), [str(data)], str(cwd))
+        assert log.count("Processing on") == 3, log[-2000:]
+        assert "Finish image integration" in log
+    nv, nf, d = same_mesh(tmp_path / "dropin" / "image_integration.ply", tmp_path / "ref" / "image_integration.ply", 2e-6)
+    print(f"ImageSequenceIntegration main: {nv} vertices, {nf} triangles, largest vertex distance to the reference build's {d:.2e} m")
+    assert nv > 100000
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not _have("dense_fusion_dropin.bin", "dense_fusion_ref.bin"),
+                    reason="tests/cpp/mains/*.bin not built (needs the reference tree: make -C tests/cpp mains)")
+def test_dense_fusion_main_tracks_registers_and_fuses_like_the_reference(tmp_path):
+    """example/DenseFusion/DenseFusion.cpp:36-104 + DenseSlam.cpp: DenseTracking per frame, a submap every 50 frames
+    (RegisterSubmap: down-sampling, normals, FPFH, PointToPoint against the previous submap) and Optimizer::FastBA (= SimpleBA),
+    then every 8th frame integrated with the optimised poses, Marching Cubes, ClusteringSimplify, PLY + trajectory.txt.  The two
+    builds' poses differ by what float32-sequential and double accumulation of the 6x6 systems differ by, and GRANSAC seeds itself
+    from std::random_device (the reference's own result changes from run to run), so the gate is a tolerance: trajectories within
+    2 cm / 1e-2, drift against the ground truth no worse than twice the reference build's, mesh size within 2 %."""
+    n_frames = 112  # three submaps (50 + 50 + 12 frames): RansacRegistration of the third against the first, FastBA over three poses
+    logs, traj = {}, {}
+    for kind in ("ref", "dropin"):
+        data = tmp_path / f"data_{kind}"      # the main writes trajectory.txt into the dataset directory
+        make_dataset(str(data), n_frames, 1)
+        os.remove(data / "trajectory.txt")
+        cwd = tmp_path / kind
+        cwd.mkdir()
+        logs[kind] = run_main(os.path.join(MAINS, f"dense_fusion_{kind}.bin"), [str(data), "0.01"], str(cwd), timeout=1500)
+        traj[kind] = np.loadtxt(data / "trajectory.txt").reshape(-1, 4, 4)
+    for kind in ("ref", "dropin"):
+        assert logs[kind].count("tracking successful!") == n_frames, logs[kind][-3000:]
+        assert logs[kind].count("Processing on") == (n_frames - 1) // 8   # frame 0 is never marked tracking_success
+        assert "Too few optimization variables" not in logs[kind].split("Matching 1 ...")[-1], "FastBA must have run over the three submap poses"
+        assert "Match 0 successfully!" in logs[kind], "RansacRegistration of the third submap against the first"
+    assert traj["ref"].shape == traj["dropin"].shape == (n_frames - 1, 4, 4)   # frame 0 is skipped before the write, too
+    dt = np.linalg.norm(traj["ref"][:, :3, 3] - traj["dropin"][:, :3, 3], axis=1).max()
+    dR = np.abs(traj["ref"][:, :3, :3] - traj["dropin"][:, :3, :3]).max()
+    true = np.stack([scenes.room_pose(k) for k in range(n_frames)])
+    drift = {k: np.linalg.norm(traj[k][:, :3, 3] - (np.linalg.inv(true[0]) @ true)[1:, :3, 3], axis=1).max() for k in traj}
+    _, pa, _, fa = read_ply(tmp_path / "dropin" / "densefusion_generated_mesh.ply")
+    _, pb, _, fb = read_ply(tmp_path / "ref" / "densefusion_generated_mesh.ply")
+    print(f"DenseFusion main, {n_frames} frames: trajectories differ by {1e3 * dt:.3f} mm / {dR:.2e}; drift vs ground truth "
+          f"{1e3 * drift['dropin']:.2f} mm (drop-in) {1e3 * drift['ref']:.2f} mm (reference build); mesh {len(pa)} / {len(pb)} vertices")
+    assert dt < 2e-2 and dR < 1e-2
+    assert drift["dropin"] < max(2 * drift["ref"], 2e-2)
+    assert abs(len(pa) - len(pb)) <= 0.02 * len(pb) and abs(len(fa) - len(fb)) <= 0.02 * len(fb)
