@@ -339,19 +339,28 @@ def bench_config4(local, rank, world, steps, warmup, reference_on_rank0: bool):
         for d, c in frames:
             vol.IntegrateImage(d, c, I4)
 
-        def timed(host: bool):
+        banded = collective and n_world > 1
+        ring_maps = fusion.attach_frame_ring(vol, rank, n_world, local) if banded else None
+        lo, hi = fusion.shard_range(cam.height, rank, n_world) if banded else (0, cam.height)
+
+        def timed(host: bool, bands: bool = False):
             B = H if host else D
-            for s in range(warmup):
+
+            def one(s):
                 d, c = B[s % len(B)]
-                (vol.IntegrateImageAsync if host else vol.IntegrateImageDevice)(d.data_ptr(), capi.OPB_DEPTH_F32, c.data_ptr(), I16)
+                if bands:   # this rank uploads rows [lo, hi) only; the bands meet in every rank's frame ring over NVLink
+                    vol.IntegrateRowsAsync(d.data_ptr() + lo * cam.width * 4, capi.OPB_DEPTH_F32, c.data_ptr() + lo * cam.width * 3, lo, hi - lo, I16)
+                else:
+                    (vol.IntegrateImageAsync if host else vol.IntegrateImageDevice)(d.data_ptr(), capi.OPB_DEPTH_F32, c.data_ptr(), I16)
+            for s in range(warmup):
+                one(s)
             vol.Synchronize()
             if collective:
                 barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             for s in range(steps):
-                d, c = B[(warmup + s) % len(B)]
-                (vol.IntegrateImageAsync if host else vol.IntegrateImageDevice)(d.data_ptr(), capi.OPB_DEPTH_F32, c.data_ptr(), I16)
+                one(warmup + s)
             e1.record(stream)
             vol.Synchronize()
             if collective:
@@ -364,7 +373,10 @@ def bench_config4(local, rank, world, steps, warmup, reference_on_rank0: bool):
             return ms
 
         ms_dev = timed(False)
-        ms_e2e = timed(True)
+        ms_whole = timed(True)
+        ms_e2e = timed(True, True) if banded else timed(True)   # (the same number of frames either way: the meshes are compared)
+        if banded:
+            vol.FrameRingStatus()
         # per-kernel times of this rank's share
         vol.SetProfiling(True)
         vol.ProfileRead(reset=True)
@@ -378,7 +390,8 @@ def bench_config4(local, rank, world, steps, warmup, reference_on_rank0: bool):
         sel_ms, int_ms, nprof = vol.ProfileRead(reset=True)
         vol.SetProfiling(False)
         st = vol.FrameStats()
-        out = {"ms_per_frame": ms_dev / steps, "e2e_ms_per_frame": ms_e2e / steps, "cubes": vol.NumCubes(), "frame_cubes": st.frame_cubes,
+        out = {"ms_per_frame": ms_dev / steps, "e2e_ms_per_frame": ms_e2e / steps, "e2e_whole_frame_per_rank_ms": ms_whole / steps,
+               "cubes": vol.NumCubes(), "frame_cubes": st.frame_cubes,
                "updated_voxels_per_frame": upd / max(n_prof, 1), "select_ms": sel_ms / max(nprof, 1), "integrate_ms": int_ms / max(nprof, 1),
                "pool_grew": st.overflow}
         # mesh: boundary cubes from the owner of the next slab, then Marching Cubes (count only).  The exchange is two kernel
@@ -401,6 +414,8 @@ def bench_config4(local, rank, world, steps, warmup, reference_on_rank0: bool):
         out.update(halo_exchange_ms=halo_ms, boundary_cubes_imported=int(n_ghost), mesh_vertices=int(nv))
         if collective and world > 1:
             fusion.detach_halo_peers(vol, maps, local)
+        if ring_maps is not None:
+            fusion.detach_frame_ring(vol, ring_maps, local)
         vol.close()
         return out
 
@@ -543,8 +558,10 @@ def config4_line(c4, world, steps, peak_gbs):
     upd = c4.get("updated_voxels_per_frame_total", int(p["updated_voxels_per_frame"]))
     out = {"what": WORKLOAD4, "n_gpus": world, "frames_per_s": 1e3 / p["ms_per_frame"], "ms_per_frame": p["ms_per_frame"],
            "e2e_frames_per_s": 1e3 / p["e2e_ms_per_frame"],
-           "e2e_note": "every rank uploads every frame from its own pinned host copy (6.1 MB per frame and rank over its own PCIe link, "
-                       "double-buffered against the kernels)",
+           "e2e_note": ("every rank uploads only its band of rows of the frame from pinned host memory (8.6 MB per frame in total over N PCIe links); a "
+                        "scatter kernel stores the band into every peer's frame ring over NVLink, the frame is integrated when all bands have "
+                        "landed (opb_volume_integrate_rows_async)") if world > 1 else "the frame is uploaded from pinned host memory, double-buffered against the kernels",
+           "e2e_whole_frame_per_rank_frames_per_s": 1e3 / p["e2e_whole_frame_per_rank_ms"],
            "cubes_total": c4.get("cubes_total", p["cubes"]), "mesh_vertices_total": c4.get("mesh_vertices_total", p["mesh_vertices"]),
            "boundary_cubes_exchanged": c4.get("boundary_cubes_exchanged", 0),
            "halo_exchange_ms": c4.get("halo_exchange_ms_max_over_ranks", p["halo_exchange_ms"]),
@@ -888,7 +905,7 @@ def run_ours(args):
                "data": "synthetic", "config": config_of(world), "partitioned_fusion": line4,
                "roofline": dict(line4.get("roofline_per_gpu", {}), kernel="integrate_pipelined_kernel on the slowest rank's share of the frame",
                                 traffic=None),
-               "e2e": {"value": line4["e2e_frames_per_s"], "unit": UNIT, "h2d_bytes_per_step": world * 1280 * 960 * 7,
+               "e2e": {"value": line4["e2e_frames_per_s"], "unit": UNIT, "h2d_bytes_per_step": 1280 * 960 * 7,
                        "d2h_bytes_per_step": 0, "clock": line4["e2e_note"]},
                "gpu_launches": 3 * K * world, "clocks": clocks4,
                "replicas": dict(replicas, details=details, roofline=roofline, e2e_detail=e2e, clocks=clocks)}

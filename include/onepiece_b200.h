@@ -244,6 +244,22 @@ int opb_volume_halo_peer_attach(opb_volume *v, void *dst_buffer, size_t dst_cap_
 int opb_volume_halo_exchange_peer(opb_volume *v, size_t *n_sent, size_t *n_imported);
 int opb_volume_halo_exchange_begin(opb_volume *v);
 int opb_volume_halo_exchange_end(opb_volume *v, size_t *n_sent, size_t *n_imported);
+/* One frame uploaded in row bands by the ranks that fuse a stream into a partitioned volume (every rank needs the whole frame
+ * to update its own cubes; handing each rank the whole frame from host memory makes N ranks pull N copies through the host):
+ *   opb_volume_frame_ring_buffer     this volume's frame ring (two frame slots + flags, device memory) and its cudaIpc handle;
+ *   opb_volume_frame_ring_attach     buffers[r] = rank r's ring as mapped here (buffers[rank] = the own ring); NULL detaches;
+ *   opb_volume_integrate_rows_async  collective, asynchronous: this rank uploads rows [row0, row0 + n_rows) of the frame (depth_rows /
+ *                                    bgr_rows point at the first of those rows in host memory, pinned for overlap), a kernel stores the
+ *                                    band into every peer's ring over NVLink and raises a flag there; the frame is integrated (as
+ *                                    opb_volume_integrate_async does) once the bands of all ranks have landed.  The bands of the
+ *                                    ranks must tile the image.  opb_volume_synchronize waits for the frame;
+ *   opb_volume_frame_ring_status     synchronises and reports OPB_ERR_CUDA if a wait on a peer ran into the 4 s limit.
+ * No counterpart in the single-process reference (IntegrateImage is handed the frame, CubeHandler.cpp:198-227). */
+int opb_volume_frame_ring_buffer(opb_volume *v, void **d_buffer, unsigned char ipc_handle[OPB_IPC_HANDLE_BYTES]);
+int opb_volume_frame_ring_attach(opb_volume *v, int rank, int world, void *const *buffers);
+int opb_volume_integrate_rows_async(opb_volume *v, const void *depth_rows, int depth_type, const uint8_t *bgr_rows, int row0, int n_rows,
+                                    const float pose_cm[16]);
+int opb_volume_frame_ring_status(opb_volume *v);
 
 /* ------------------------------------------------------------------------------------------------------
  * Depth pre-filter  (replaces one_piece::tool::ConvertDepthTo32F and tool::BilateralFilter,
@@ -435,6 +451,10 @@ int opb_kdtree_dump(opb_kdtree *t, int32_t *vind, int32_t *node_ints5, float *no
  * Afterwards opb_icp_point_to_plane / opb_icp_point_to_point are COLLECTIVE calls: every rank must make them in the same
  * order with its share of the source and identical target, init_T and params (a missing peer makes the call fail with
  * OPB_ERR_CUDA after 4 s instead of hanging).  A rank's share may be empty. */
+/* Sizes the workspace for clouds of up to n_source / n_target points now instead of inside the first registration.  Device
+ * allocation can wait for running kernels; a workspace that takes part in a split registration with a peer on the SAME device (a
+ * peer's kernel spins until this workspace has launched its own) must not allocate in the middle of a collective call. */
+int opb_icp_reserve(opb_icp *c, size_t n_source, size_t n_target);
 int opb_icp_comm_buffer(opb_icp *c, void **d_buffer, unsigned char ipc_handle[OPB_IPC_HANDLE_BYTES]);
 int opb_ipc_open(int device, const unsigned char ipc_handle[OPB_IPC_HANDLE_BYTES], void **d_ptr);
 int opb_ipc_close(int device, void *d_ptr);
@@ -504,10 +524,9 @@ int opb_odometry_create(const opb_odometry_desc *desc, opb_odometry **out);
 void opb_odometry_destroy(opb_odometry *o);
 int opb_odometry_set_profiling(opb_odometry *o, int on);
 /* How MultiScaleComputing (Odometry.cpp:621-685) is launched: 1 (default) the second persistent form -- one cooperative launch for all
- * levels and iterations, the 29 sums as 8x8 outer-product accumulations with EXACT float x float products; 2 the first persistent
- * form and 0 one launch pair per iteration -- both round every product to float before the double accumulation, as the oracle
- * does, so their sums equal the oracle's to the last bit.  The forms agree to ~1e-8 relative in the sums (far inside the 1e-6 pose
- * gate); discrete per-iteration correspondence counts can differ by a few pixels on a 640x480 run.  -1 restores the default. */
+ * levels and iterations, the 29 sums as 8x8 outer-product accumulations on the FP64 tensor-core op; 2 the first persistent form; 0 one
+ * launch pair per iteration.  All forms sum exact (double) products of the float Jacobian rows in double; they differ only in the
+ * order of the additions (~1e-16 relative).  -1 restores the default.  For A/B runs and tests. */
 int opb_odometry_set_loop_form(opb_odometry *o, int form);
 /* CUDA-event time of the last tracking call (pre-processing of new frames included) and the mean time per solver
  * iteration that the last CTA spent on the fixed-order partial sum + 6x6 solve + pose update (%globaltimer) */

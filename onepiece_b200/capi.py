@@ -130,6 +130,10 @@ SIGNATURES = {
     "opb_volume_halo_exchange_peer": (C.c_int, [_p, C.POINTER(_sz), C.POINTER(_sz)]),
     "opb_volume_halo_exchange_begin": (C.c_int, [_p]),
     "opb_volume_halo_exchange_end": (C.c_int, [_p, C.POINTER(_sz), C.POINTER(_sz)]),
+    "opb_volume_frame_ring_buffer": (C.c_int, [_p, C.POINTER(_p), _p]),
+    "opb_volume_frame_ring_attach": (C.c_int, [_p, C.c_int, C.c_int, _p]),
+    "opb_volume_integrate_rows_async": (C.c_int, [_p, _p, C.c_int, _p, C.c_int, C.c_int, _p]),
+    "opb_volume_frame_ring_status": (C.c_int, [_p]),
     "opb_prefilter_create": (C.c_int, [C.c_int, _p, C.c_int, C.c_int, C.POINTER(_p)]),
     "opb_prefilter_destroy": (None, [_p]),
     "opb_prefilter_run": (C.c_int, [_p, _p, C.c_int, C.c_float, C.c_int, C.c_double, C.c_double, _p, _p]),
@@ -176,6 +180,7 @@ SIGNATURES = {
     "opb_icp_point_to_point_clouds": (C.c_int, [_p, _p, _p, _p, C.POINTER(IcpParams), C.POINTER(IcpResult), _p, _sz]),
     "opb_volume_integrate_cloud": (C.c_int, [_p, _p, _p]),
     "opb_icp_set_profiling": (C.c_int, [_p, C.c_int]),
+    "opb_icp_reserve": (C.c_int, [_p, _sz, _sz]),
     "opb_icp_last_timing": (C.c_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "opb_odometry_desc_default": (None, [C.POINTER(OdometryDesc)]),
     "opb_odometry_create": (C.c_int, [C.POINTER(OdometryDesc), C.POINTER(_p)]),

@@ -397,6 +397,9 @@ int opb_volume_halo_peer_buffer(opb_volume *v, size_t cap_cubes, void **d_buffer
         OPB_CUDA(cudaMalloc(&v->halo_local, sizeof(HaloLocal)));
         OPB_CUDA(cudaMemset(v->halo_local, 0, sizeof(HaloLocal)));
         v->halo_box_cap = cap_cubes;
+        cudaFuncAttributes fa; // load both kernels now (a first launch may wait for the device to drain: see opb_icp_create)
+        OPB_CUDA(cudaFuncGetAttributes(&fa, halo_export_peer_kernel));
+        OPB_CUDA(cudaFuncGetAttributes(&fa, halo_import_peer_kernel));
     }
     *d_buffer = v->halo_box;
     if (ipc_handle)

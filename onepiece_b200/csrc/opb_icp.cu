@@ -421,6 +421,7 @@ struct IcpArgs
     float4 *qref;           // ns: query position at the point's last full search; w = displacement budget (NaN: none yet)
     int2 *nn_ref;           // ns: nearest neighbour found by that search (-1 = none within the inlier radius) and the runner-up
     float *budget2;         // ns: displacement budget of the two-candidate certificate
+    float4 *rec;            // 2 x ns (second persistent form): the nearest neighbour's point and normal {tx,ty,tz,nx},{ny,nz,-,-}; tx = NaN: none
     unsigned int *worklist; // ns
     float guard;            // extra radius every full search covers beyond its nearest neighbour, in grid cells
     int certify;            // 0: every pass searches every point (reference behaviour of the search, for A/B tests)
@@ -1144,6 +1145,16 @@ __device__ __noinline__ int loop2_search(const IcpArgs &a, const IcpGrid *g, flo
     a.nn_ref[i] = make_int2(r.index, r.index2);
     a.qref[i] = make_float4(px, py, pz, a.certify ? r.budget : -1.0f);
     a.budget2[i] = a.certify ? r.budget2 : -1.0f;
+    // the neighbour's point and normal travel with the certificate: a certified pass then streams 60 contiguous bytes per point
+    // (source, certificate, record) instead of gathering two 32-byte sectors per point from the target arrays
+    float4 r0 = make_float4(__int_as_float(0x7fc00000), 0.0f, 0.0f, 0.0f), r1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (r.index >= 0)
+    {
+        r0.x = __ldg(&a.tgt[3 * r.index]); r0.y = __ldg(&a.tgt[3 * r.index + 1]); r0.z = __ldg(&a.tgt[3 * r.index + 2]);
+        if (a.nrm) { r0.w = __ldg(&a.nrm[3 * r.index]); r1.x = __ldg(&a.nrm[3 * r.index + 1]); r1.y = __ldg(&a.nrm[3 * r.index + 2]); }
+    }
+    a.rec[2 * i] = r0;
+    a.rec[2 * i + 1] = r1;
     return r.index < 0 && keep_far ? -2 : r.index;
 }
 // geometry::TransformPoints for a rigid pose: w = ((0*x + 0*y) + 0*z) + 1 == 1 exactly, and x / 1 == x, so the three divisions
@@ -1159,6 +1170,9 @@ __device__ __forceinline__ void transform_point_w1(const float *T, float sx, flo
 
 // the inlier test and the point's 8 components (zeros unless it is an inlier); T = rows 0..2 of the pose, T[3 * col + row]
 template <bool PLANE>
+__device__ __forceinline__ bool loop2_components_of(const IcpArgs &a, const float *T, bool final_pass, float tx, float ty, float tz, float nx, float ny,
+                                                    float nz, float sx, float sy, float sz, float px, float py, float pz, float *comp);
+template <bool PLANE>
 __device__ __forceinline__ bool loop2_components(const IcpArgs &a, const float *T, bool final_pass, int nn, float sx, float sy, float sz, float px,
                                                  float py, float pz, float *comp)
 {
@@ -1169,6 +1183,13 @@ __device__ __forceinline__ bool loop2_components(const IcpArgs &a, const float *
     // the normal travels with the target point, not after the inlier test: one round trip to L2 instead of two
     float nx = 0.0f, ny = 0.0f, nz = 0.0f;
     if (PLANE && !final_pass) { nx = __ldg(&a.nrm[3 * nn]); ny = __ldg(&a.nrm[3 * nn + 1]); nz = __ldg(&a.nrm[3 * nn + 2]); }
+    return loop2_components_of<PLANE>(a, T, final_pass, tx, ty, tz, nx, ny, nz, sx, sy, sz, px, py, pz, comp);
+}
+// ... given the neighbour's point (and normal): comp must be zero on entry
+template <bool PLANE>
+__device__ __forceinline__ bool loop2_components_of(const IcpArgs &a, const float *T, bool final_pass, float tx, float ty, float tz, float nx, float ny,
+                                                    float nz, float sx, float sy, float sz, float px, float py, float pz, float *comp)
+{
     // CountInliers (ICP.cpp:19-21): (R*s + t - target).squaredNorm() in float, compared as double
     const float ex = fsub(fadd(fadd(fmul(T[0], sx), fadd(fmul(T[3], sy), fmul(T[6], sz))), T[9]), tx);
     const float ey = fsub(fadd(fadd(fmul(T[1], sx), fadd(fmul(T[4], sy), fmul(T[7], sz))), T[10]), ty);
@@ -1257,20 +1278,28 @@ __global__ void __launch_bounds__(kLoop2Threads, 1) icp_loop2_kernel(const __gri
                 int nn = -1;
                 bool later = false;
                 float px = 0.0f, py = 0.0f, pz = 0.0f;
+                bool by_record = false;
+                float4 r0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), r1 = r0;
                 if (!final_pass)
                 {
                     const float4 q = a.qref[i];
-                    const int2 jj = a.nn_ref[i]; // with the certificate, not after it: the gathers below start one round trip earlier
+                    r0 = a.rec[2 * i];     // with the certificate, not after it: nothing in the certified path depends on a loaded index
+                    r1 = a.rec[2 * i + 1];
                     loop2_transform(T, rigid, sh.T, sx, sy, sz, px, py, pz);
                     const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
                     const float moved2 = (dx * dx + dy * dy + dz * dz) * (1.0f + 4e-6f);
                     if (q.w > 0.0f && moved2 < q.w * q.w)
                     {   // the certified strictly nearest neighbour (beyond the inlier radius the inlier test rejects it)
-                        nn = jj.x;
-                        if (nn < 0 && keep_far) nn = -2;
+                        by_record = true;
+                        if (keep_far)
+                        {
+                            nn = a.nn_ref[i].x;
+                            if (nn < 0) nn = -2;
+                        }
                     }
                     else
                     {
+                        const int2 jj = a.nn_ref[i];
                         const float b2 = a.budget2[i];
                         if (b2 > 0.0f && moved2 < b2 * b2)
                         {
@@ -1289,6 +1318,10 @@ __global__ void __launch_bounds__(kLoop2Threads, 1) icp_loop2_kernel(const __gri
                     later = nn == -2;
                 }
                 if (later) todo |= 1u << (k & 31);
+                else if (by_record)
+                {
+                    if (r0.x == r0.x) loop2_components_of<PLANE>(a, T, false, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, sx, sy, sz, px, py, pz, comp);
+                }
                 else
                 {
                     const bool inl = loop2_components<PLANE>(a, T, final_pass, nn, sx, sy, sz, px, py, pz, comp);
@@ -1724,6 +1757,7 @@ struct opb_icp
     float4 *d_qref = nullptr;          // nearest-neighbour certificates (icp_certify_kernel)
     int2 *d_nn_ref = nullptr;
     float *d_budget2 = nullptr;
+    float4 *d_rec = nullptr;
     unsigned int *d_pair_tiles = nullptr; // inlier count / offset per tile of 1024 source points
     unsigned int *d_worklist = nullptr;
     unsigned long long last_searched = 0; // full searches of the last call (of ns * (max_iteration + 1) queries)
@@ -1758,13 +1792,14 @@ static int icp_reserve(opb_icp *c, size_t ns, size_t nt)
     if (ns > c->cap_src)
     {
         cudaFree(c->d_src); cudaFree(c->d_nn); cudaFree(c->d_pairs); cudaFree(c->d_inlier);
-        cudaFree(c->d_qref); cudaFree(c->d_nn_ref); cudaFree(c->d_worklist); cudaFree(c->d_budget2);
-        c->d_budget2 = nullptr;
+        cudaFree(c->d_qref); cudaFree(c->d_nn_ref); cudaFree(c->d_worklist); cudaFree(c->d_budget2); cudaFree(c->d_rec);
+        c->d_budget2 = nullptr; c->d_rec = nullptr;
         c->d_src = nullptr; c->d_nn = nullptr; c->d_pairs = nullptr; c->d_inlier = nullptr; c->cap_src = 0;
         c->d_qref = nullptr; c->d_nn_ref = nullptr; c->d_worklist = nullptr;
         OPB_CUDA(cudaMalloc(&c->d_qref, ns * sizeof(float4)));
         OPB_CUDA(cudaMalloc(&c->d_nn_ref, ns * sizeof(int2)));
         OPB_CUDA(cudaMalloc(&c->d_budget2, ns * sizeof(float)));
+        OPB_CUDA(cudaMalloc(&c->d_rec, ns * 2 * sizeof(float4)));
         cudaFree(c->d_pair_tiles);
         c->d_pair_tiles = nullptr;
         OPB_CUDA(cudaMalloc(&c->d_pair_tiles, (ns / kPairTile + 2) * sizeof(unsigned int)));
@@ -1922,7 +1957,7 @@ void opb_icp_destroy(opb_icp *c)
     cudaFree(c->d_src); cudaFree(c->d_tgt); cudaFree(c->d_nrm); cudaFree(c->d_sorted); cudaFree(c->d_point_cell);
     cudaFree(c->d_cell_count); cudaFree(c->d_tile_sums); cudaFree(c->d_cell_start); cudaFree(c->d_nn); cudaFree(c->d_pairs);
     cudaFree(c->d_inlier); cudaFree(c->d_partials); cudaFree(c->d_state); cudaFree(c->d_mailbox);
-    cudaFree(c->d_qref); cudaFree(c->d_nn_ref); cudaFree(c->d_worklist); cudaFree(c->d_budget2); cudaFree(c->d_pair_tiles);
+    cudaFree(c->d_qref); cudaFree(c->d_nn_ref); cudaFree(c->d_worklist); cudaFree(c->d_budget2); cudaFree(c->d_rec); cudaFree(c->d_pair_tiles);
     cudaFree(c->d_grid_sync); cudaFree(c->d_partials2); cudaFree(c->d_loop_sync);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_sums) cudaFreeHost(c->h_sums);
@@ -2013,7 +2048,7 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     a.final_pass = 0; a.keep_far = 0; a.pairs = c->d_pairs; a.inlier = c->d_inlier;
     a.comm = c->comm;
     // nearest-neighbour certificates: a NaN budget marks "never searched"
-    a.qref = c->d_qref; a.nn_ref = c->d_nn_ref; a.worklist = c->d_worklist; a.budget2 = c->d_budget2;
+    a.qref = c->d_qref; a.nn_ref = c->d_nn_ref; a.worklist = c->d_worklist; a.budget2 = c->d_budget2; a.rec = c->d_rec;
     static const float k_guard = getenv("OPB_ICP_GUARD") ? (float)atof(getenv("OPB_ICP_GUARD")) : 0.125f;
     static const int k_certify = getenv("OPB_ICP_CERTIFY") ? atoi(getenv("OPB_ICP_CERTIFY")) : 1;
     a.guard = k_guard; a.certify = k_certify; a.unscale = scaling;
@@ -2145,6 +2180,14 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     }
     res->status = OPB_OK;
     return OPB_OK;
+}
+
+int opb_icp_reserve(opb_icp *c, size_t n_source, size_t n_target)
+{
+    if (!c) { set_error("icp is NULL"); return OPB_ERR_INVALID; }
+    OPB_CUDA(cudaSetDevice(c->device));
+    OPB_CUDA(cudaStreamSynchronize(c->stream));
+    return icp_reserve(c, n_source, n_target);
 }
 
 void opb_icp_params_default(opb_icp_params *p)

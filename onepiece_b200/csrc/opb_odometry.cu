@@ -288,7 +288,7 @@ __device__ __forceinline__ double warp_sum_d(double v)
 }
 
 // One Jacobian row pair of a correspondence, float arithmetic in the reference's order (DenseOdometryFunction.cpp:146-296);
-// adds its products to the per-thread double accumulators acc[0..20] (upper triangle of J^T J), acc[21..26] (J^T r), acc[27] (r^2)
+// adds its (exact, double) products to the per-thread double accumulators acc[0..20] (upper triangle of J^T J), acc[21..26] (J^T r), acc[27] (r^2)
 struct RowCtx // what compute_rows reads of one pyramid level
 {
     const float *sgray, *sdepth, *tgray, *tdepth, *tgx, *tgy, *tdx, *tdy;
@@ -385,10 +385,10 @@ __device__ __forceinline__ void accumulate_rows(const OdoArgs &a, const float *T
 #pragma unroll
         for (int p = 0; p < 6; ++p)
 #pragma unroll
-            for (int q = p; q < 6; ++q) acc[k++] += (double)fmul(J[r][p], J[r][q]);
+            for (int q = p; q < 6; ++q) acc[k++] += (double)J[r][p] * (double)J[r][q]; // exact product of two floats, double sum
 #pragma unroll
-        for (int p = 0; p < 6; ++p) acc[21 + p] += (double)fmul(J[r][p], res[r]);
-        acc[27] += (double)fmul(res[r], res[r]);
+        for (int p = 0; p < 6; ++p) acc[21 + p] += (double)J[r][p] * (double)res[r];
+        acc[27] += (double)res[r] * (double)res[r];
     }
 }
 
@@ -617,8 +617,8 @@ __global__ void __launch_bounds__(kOdoThreads, 2) odo_loop_kernel(OdoLoopArgs L)
 //     frames, and two dependent loads plus the projection per step cost more than the barrier: 0.58 ms per call against 0.55);
 //   * the sums are an 8x8 outer-product accumulation on the FP64 tensor-core op (warp_fold_outer8): a Jacobian row contributes
 //     c c^T with c = (J0..J5, r, 1) -- J^T J, J^T r, r^2 and the count are entries of that matrix; the hybrid term's second row
-//     goes in with c = (J0..J5, r, 0).  Products of floats are exact in double (the separate-launch kernels round them to float
-//     first, as the oracle does: the two forms agree to ~1e-8 relative in the sums, far inside the 1e-6 pose gate);
+//     goes in with c = (J0..J5, r, 0).  Products of floats are exact in double, which is also what the separate-launch kernels and
+//     the oracle sum: the forms differ only in the order of the double additions (~1e-16 relative);
 //   * one CTA of 1024 threads per SM publishes its 8x8 partial, announces it on one counter, waits until all have, and then EVERY
 //     CTA sums all partials in the same fixed order and solves the same 6x6 system: nobody waits for an owner, the pose lives
 //     in shared memory, the result is deterministic and identical on all CTAs (CTA 0 records the trace).

@@ -52,6 +52,12 @@ struct opb_volume
     size_t halo_box_cap = 0, halo_dst_cap = 0;
     unsigned long long halo_epoch = 0;
     bool halo_pending = false;
+    // frame ring (opb_volume_frame_ring_*): one frame uploaded in row bands by the ranks of a partitioned volume
+    void *frame_ring = nullptr, *frame_ring_tickets = nullptr;
+    void *frame_ring_peers[16] = {};
+    int frame_ring_rank = 0, frame_ring_world = 0;
+    unsigned long long frame_ring_count = 0;
+    cudaEvent_t frame_ring_consumed[2] = {nullptr, nullptr};
 
     // pool exhaustion (the reference's unordered_map is unbounded, CubeHandler.cpp:181-191): the kernels raise sticky flags in
     // mapped host memory; the synchronous calls grow the pool and re-run the frame for the cubes that found no slot, the

@@ -72,6 +72,42 @@ def detach_halo_peers(volume, opened, device_index: int, group=None):
         capi.lib.opb_ipc_close(device_index, p)
 
 
+def attach_frame_ring(volume, rank: int, world: int, device_index: int, group=None):
+    """Collective, once per volume: every rank creates its frame ring, the cudaIpc handles go round the group and every rank maps
+    all of them.  After this `volume.IntegrateRowsAsync` uploads only this rank's band of a frame and the bands meet over NVLink.
+    Returns the mapped pointers (hand them to `detach_frame_ring`)."""
+    import ctypes as C
+
+    from . import capi
+    own, handle = volume.FrameRingBuffer()
+    if world <= 1:
+        volume.FrameRingAttach(0, 1, [own])
+        return []
+    handles = [None] * world
+    dist.all_gather_object(handles, handle, group=group)
+    bufs, opened = [], []
+    for r in range(world):
+        if r == rank:
+            bufs.append(own)
+            continue
+        p = C.c_void_p()
+        capi.check(capi.lib.opb_ipc_open(device_index, (C.c_ubyte * 64).from_buffer_copy(handles[r]), C.byref(p)))
+        opened.append(p)
+        bufs.append(p.value)
+    volume.FrameRingAttach(rank, world, bufs)
+    dist.barrier(group=group)  # nobody scatters before every ring is mapped (and zeroed) everywhere
+    return opened
+
+
+def detach_frame_ring(volume, opened, device_index: int, group=None):
+    from . import capi
+    volume.FrameRingAttach(0, 0, None)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.barrier(group=group)  # peers may still be writing into this rank's ring until they detached too
+    for p in opened:
+        capi.lib.opb_ipc_close(device_index, p)
+
+
 def exchange_halo(volume, rank: int, world: int, device="cpu", group=None) -> int:
     """Boundary-cube exchange before Marching Cubes.  Returns the number of ghost cubes imported.  Collective: every rank
     of the group must call it.  A volume with attached peer boxes (`attach_halo_peers`) does it in two kernel launches over
@@ -159,6 +195,9 @@ class ShardedCubeHandler:
     def close(self):
         """Collective: unmaps the neighbours' boxes, then releases the volume."""
         if self.volume is not None:
+            if hasattr(self, "_ring_maps"):
+                detach_frame_ring(self.volume, self._ring_maps, self.device_index, self.group)
+                del self._ring_maps
             detach_halo_peers(self.volume, self._halo_maps, self.device_index, self.group)
             self._halo_maps = []
             self.volume.close()
@@ -167,6 +206,18 @@ class ShardedCubeHandler:
     def IntegrateImage(self, depth, rgb, pose):
         """Every rank is given the same frame and pose (the host program broadcasts or loads it per rank)."""
         self.volume.IntegrateImage(depth, rgb, pose)
+
+    def IntegrateImageRows(self, depth, rgb, pose):
+        """Every rank holds the frame in host memory but uploads only its band of rows; the bands are exchanged over NVLink
+        (opb_volume_integrate_rows_async).  Collective and asynchronous: `self.volume.Synchronize()` waits for the frame.  The
+        host arrays must stay alive (and should be pinned) until then."""
+        from .volume import depth_type_of, pose_colmajor
+        if not hasattr(self, "_ring_maps"):
+            self._ring_maps = attach_frame_ring(self.volume, self.rank, self.world, self.device_index, self.group)
+        depth = np.ascontiguousarray(depth)
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        lo, hi = shard_range(depth.shape[0], self.rank, self.world)
+        self.volume.IntegrateRowsAsync(depth[lo:hi].ctypes.data, depth_type_of(depth), rgb[lo:hi].ctypes.data, lo, hi - lo, pose_colmajor(pose))
 
     def IntegrateImageBroadcast(self, depth, rgb, pose, src: int = 0):
         """The frame lives on rank `src` only (the others pass None): depth, colour and pose are broadcast over NCCL into

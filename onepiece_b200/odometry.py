@@ -110,8 +110,8 @@ class Odometry:
         capi.check(capi.lib.opb_odometry_set_profiling(self.handle, int(on)))
 
     def SetLoopForm(self, form: int):
-        """1 (default): second persistent solver loop (exact products in the sums); 2 / 0: the forms that round every product to
-        float like the oracle (include/onepiece_b200.h, opb_odometry_set_loop_form)"""
+        """1 (default): second persistent solver loop; 2: first persistent form; 0: one launch pair per iteration
+        (include/onepiece_b200.h, opb_odometry_set_loop_form)"""
         capi.check(capi.lib.opb_odometry_set_loop_form(self.handle, int(form)))
 
     def last_tracking_ms(self):

@@ -254,6 +254,30 @@ class CubeHandler:
         capi.check(capi.lib.opb_volume_halo_exchange_end(self._h, C.byref(ns), C.byref(ni)))
         return ns.value, ni.value
 
+    # -- one frame uploaded in row bands by the ranks of a partitioned volume (opb_volume_frame_ring_*): fusion.attach_frame_ring
+    def FrameRingBuffer(self):
+        """-> (device address of this volume's frame ring, its 64-byte cudaIpc handle)"""
+        buf = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        capi.check(capi.lib.opb_volume_frame_ring_buffer(self._h, C.byref(buf), handle))
+        return buf.value, bytes(handle)
+
+    def FrameRingAttach(self, rank: int, world: int, buffers):
+        """buffers: the `world` ring addresses as mapped in this process (own ring at [rank]); None detaches"""
+        if buffers is None:
+            capi.check(capi.lib.opb_volume_frame_ring_attach(self._h, 0, 0, None))
+            return
+        arr = (C.c_void_p * world)(*[C.c_void_p(b) for b in buffers])
+        capi.check(capi.lib.opb_volume_frame_ring_attach(self._h, rank, world, arr))
+
+    def IntegrateRowsAsync(self, depth_rows_ptr, depth_type, bgr_rows_ptr, row0: int, n_rows: int, pose_cm):
+        """collective, asynchronous: this rank's band of the frame from (pinned) host memory; see include/onepiece_b200.h"""
+        capi.check(capi.lib.opb_volume_integrate_rows_async(self._h, C.c_void_p(depth_rows_ptr), depth_type, C.c_void_p(bgr_rows_ptr), row0,
+                                                            n_rows, _ptr(pose_cm)))
+
+    def FrameRingStatus(self):
+        capi.check(capi.lib.opb_volume_frame_ring_status(self._h))
+
     def NumGhostCubes(self) -> int:
         n = C.c_size_t(0)
         capi.check(capi.lib.opb_volume_num_ghost_cubes(self._h, C.byref(n)))

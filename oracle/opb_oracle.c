@@ -1234,10 +1234,12 @@ static long odo_iteration(orc_frame *S, orc_frame *Tg, int l, float fx, float fy
         for (int r = 0; r < rows; ++r)
             for (int a = 0; a < 6; ++a)
             {
-                for (int b = 0; b < 6; ++b) JTJ[a * 6 + b] += (double)(J[r][a] * J[r][b]);
-                nJTr[a] -= (double)(J[r][a] * res[r]);
+                /* float rows, products and sums in double (the product of two floats is exact in double): the reference's float64
+                 * build does the same with double rows, its float32 build sums float products sequentially in float */
+                for (int b = 0; b < 6; ++b) JTJ[a * 6 + b] += (double)J[r][a] * (double)J[r][b];
+                nJTr[a] -= (double)J[r][a] * (double)res[r];
             }
-        for (int r = 0; r < rows; ++r) r2 += (double)(res[r] * res[r]);
+        for (int r = 0; r < rows; ++r) r2 += (double)res[r] * (double)res[r];
     }
     if (sums_out)
     {

@@ -113,8 +113,12 @@ def main():
             pose = pose @ r5.T_iterated.astype(np.float64)
         prev = (cloud, nrm5)
         p32 = pose.astype(np.float32)
-        if k % 2:
+        if k % 3 == 1:
             sh5.IntegrateImage(d, c, p32)               # every rank loaded the frame itself
+        elif k % 3 == 2:
+            sh5.IntegrateImageRows(d, c, p32)           # every rank uploads its band of rows, the bands meet over NVLink
+            sh5.volume.Synchronize()
+            sh5.volume.FrameRingStatus()
         else:
             sh5.IntegrateImageBroadcast(d if rank == 0 else None, c if rank == 0 else None, p32 if rank == 0 else None, src=0)
         if whole5 is not None:

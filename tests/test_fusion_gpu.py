@@ -117,6 +117,44 @@ def test_halo_exchange_through_peer_boxes_on_one_device(world, axis, slab):
         assert e.value.code == capi.OPB_ERR_CAPACITY
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_frame_uploaded_in_row_bands_and_gathered_over_peer_memory(world):
+    """opb_volume_integrate_rows_async: every shard uploads only its band of rows, the bands meet in every shard's frame ring
+    (plain device pointers here, cudaIpc mappings between processes).  The union of the shards equals the unsharded volume bit for
+    bit, over more frames than the ring has slots (the consumed flags gate the reuse of a slot)."""
+    from onepiece_b200 import capi
+    from onepiece_b200.fusion import shard_range
+    from onepiece_b200.volume import CubeHandler, depth_type_of, pose_colmajor
+    cam, res, frames, ids, vox, _ = small_scene(5)
+    full = CubeHandler(cam, res, max_cubes=4096)
+    shards = [CubeHandler(cam, res, max_cubes=4096, shard=(r, world, 0, 2)) for r in range(world)]
+    rings = [s.FrameRingBuffer()[0] for s in shards]
+    for r, s in enumerate(shards):
+        s.FrameRingAttach(r, world, rings)
+    for d, c, pose in frames:
+        full.IntegrateImage(d, c, pose)
+        d = np.ascontiguousarray(d); c = np.ascontiguousarray(c, np.uint8)
+        for r, s in enumerate(shards):      # one host thread drives all ranks: every call only enqueues
+            lo, hi = shard_range(d.shape[0], r, world)
+            s.IntegrateRowsAsync(d[lo:hi].ctypes.data, depth_type_of(d), c[lo:hi].ctypes.data, lo, hi - lo, pose_colmajor(pose))
+        for s in shards:
+            s.Synchronize()                 # (the host arrays of this frame are released after this)
+    for s in shards:
+        s.FrameRingStatus()
+    gi = np.concatenate([s.GetCubeMap()[0] for s in shards])
+    gv = np.concatenate([s.GetCubeMap()[1] for s in shards])
+    order = np.lexsort((gi[:, 2], gi[:, 1], gi[:, 0]))
+    fi, fv = full.GetCubeMap()
+    assert np.array_equal(gi[order], fi)
+    assert_bit_equal(gv[order], fv, "shards fed by row bands")
+    # a band that does not fit the image is refused before anything is enqueued
+    with pytest.raises(capi.OpbError) as e:
+        shards[0].IntegrateRowsAsync(d.ctypes.data, depth_type_of(d), c.ctypes.data, d.shape[0] - 1, 2, pose_colmajor(pose))
+    assert e.value.code == capi.OPB_ERR_INVALID
+    for s in shards:
+        s.FrameRingAttach(0, 0, None)
+
+
 def test_halo_capacity_and_unsharded_volume():
     from onepiece_b200 import capi
     from onepiece_b200.volume import CubeHandler
@@ -185,6 +223,7 @@ def test_split_icp_workspaces_on_one_device(world, plane):
         h, b = C.c_void_p(), C.c_void_p()
         capi.check(capi.lib.opb_icp_create(0, None, C.byref(h)))
         capi.check(capi.lib.opb_icp_comm_buffer(h, C.byref(b), None))
+        capi.check(capi.lib.opb_icp_reserve(h, len(src), len(tgt)))  # no allocation inside the collective calls (ranks share the device)
         ws.append(h)
         bufs[r] = b.value
     for r in range(world):

@@ -270,3 +270,34 @@ def test_estimate_normals_matches_the_oracle_bit_for_bit():
     assert not far.normals.any()                   # fewer than three points in range: FitPlane returns the zero vector
     with pytest.raises(capi.OpbError):
         pc.EstimateNormals(0.1, 65)
+
+
+def test_exactly_equidistant_targets_resolve_to_a_nearest_neighbour_documented_tie_rule():
+    """Tie rule (documented deviation): among EXACTLY equidistant targets the device search keeps the lowest
+    target index, nanoflann keeps the first one its depth-first walk meets (KDTree.h:177-196, KNNResultSet::addPoint), which depends
+    on the tree and on the side of each cut the query lies on.  On a lattice built to tie everywhere -- targets on a 0.25 m grid,
+    sources at the cell centres: eight exactly equidistant targets per query -- both must return A nearest neighbour (the same
+    distance bit for bit, every query an inlier), and the device's choice must be the lowest index among the ties."""
+    from oracle import refapi
+    g = np.arange(6, dtype=np.float32) * np.float32(0.25)
+    tgt = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    c = (np.arange(5, dtype=np.float32) * np.float32(0.25) + np.float32(0.125)).astype(np.float32)
+    src = np.stack(np.meshgrid(c, c, c, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    rng = np.random.default_rng(3)
+    tgt = tgt[rng.permutation(len(tgt))]            # index order unrelated to position
+    par = reg.ICPParameter(1, 0.5, 1.0)
+    r = reg.PointToPoint(reg.PointCloud(src), reg.PointCloud(tgt), np.eye(4), par)
+    pairs = r.correspondence_set_index
+    assert len(pairs) == len(src) and np.array_equal(pairs[:, 0], np.arange(len(src)))
+    d_all = ((src[:, None, :] - tgt[None, :, :]) ** 2).sum(-1)     # exact in float32: every term is a multiple of 2^-6
+    d_min = d_all.min(1)
+    assert (np.isclose(d_all, d_min[:, None], rtol=0, atol=0).sum(1) == 8).all(), "the lattice must tie eight ways"
+    mine = d_all[np.arange(len(src)), pairs[:, 1]]
+    assert np.array_equal(mine, d_min), "not a nearest neighbour"
+    assert np.array_equal(pairs[:, 1], np.argmax(d_all == d_min[:, None], 1)), "the device keeps the lowest index among exact ties"
+    if refapi.available("f32"):
+        ref = refapi.icp(src, tgt, None, np.eye(4), 1, 0.5, "f32")["pairs"]
+        assert len(ref) == len(src)
+        assert np.array_equal(d_all[np.arange(len(src)), ref[:, 1]], d_min), "the reference's choice is a nearest neighbour too"
+        differ = int((ref[:, 1] != pairs[:, 1]).sum())
+        print(f"exact 8-way ties: the reference's walk order and the lowest-index rule pick different (equidistant) targets for {differ} of {len(src)} queries")

@@ -148,31 +148,14 @@ def test_full_resolution_run_and_initial_pose():
     T0 = scenes.se3_exp([1e-3, 0, -1e-3, 0, 1e-3, 0]).astype(np.float32)
     odo = Odometry(cam)
     o = oracleapi.dense_tracking_frames(oracleapi.OracleFrame(c1, d1), oracleapi.OracleFrame(c0, d0), cam, T0, 0)
-    # the forms that round every product to float before summing (as the oracle does): identical counts and pair lists
-    for form in (2, 0):
+    # every way of launching the solver loop sums the same exact products in double (only the order differs): same counts, same
+    # pair lists, poses within 1e-6 at every iteration
+    for form in (1, 2, 0):
         odo.SetLoopForm(form)
         r = odo.DenseTracking(odo.Frame(c1, d1), odo.Frame(c0, d0), T0, 0)
         _compare_runs(r, o, f"640x480, loop form {form}")
-    assert r.tracking_success and len(r.pixel_correspondence_set) > 0.3 * 640 * 480
-    # the default form sums exact products (8x8 outer products on the FP64 tensor-core op): poses inside the same 1e-6 gate at
-    # every iteration; a pose that differs in the 9th digit can move a borderline pixel across the 0.05 m / rounding tests, so the
-    # discrete counts may differ by a few pixels out of ~250,000
-    odo.SetLoopForm(1)
-    d = odo.DenseTracking(odo.Frame(c1, d1), odo.Frame(c0, d0), T0, 0)
-    assert d.iterations == r.iterations
-    n = min(d.iterations, 64)
-    for i in range(n):
-        dt, dr = pose_delta(d.T_per_iteration[i], o["T_per_iteration"][i])
-        assert dt < 1e-6 and dr < 1e-6, ("default form, iteration", i, dt, dr)
-        assert abs(int(d.corr_per_iteration[i]) - int(o["corr_per_iteration"][i])) <= 1e-4 * o["corr_per_iteration"][i], i
-    dt, dr = pose_delta(d.T, o["T"])
-    assert dt < 1e-6 and dr < 1e-6, (dt, dr)
-    a = {tuple(p) for p in np.asarray(d.pixel_correspondence_set).reshape(len(d.pixel_correspondence_set), -1).tolist()}
-    b = {tuple(p) for p in np.asarray(o["pairs"]).reshape(len(o["pairs"]), -1).tolist()}
-    print(f"default loop form vs oracle at 640x480: {len(a ^ b)} of {len(b)} final pairs differ, final pose delta {dt:.2e} m / {dr:.2e} rad")
-    assert len(a ^ b) <= 1e-4 * len(b)
-    assert d.tracking_success == o["success"] and abs(d.rmse - o["rmse"]) <= 1e-5 * max(1.0, o["rmse"])
     odo.SetLoopForm(-1)
+    assert r.tracking_success and len(r.pixel_correspondence_set) > 0.3 * 640 * 480
 
 
 def test_set_multi_scale_and_early_exit():

