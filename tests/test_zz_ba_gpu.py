@@ -1,7 +1,6 @@
 """optimization::SimpleBA / Optimizer::FastBA through the library on the device, against the oracle (pinned to the compiled
 reference by tests/test_oracle_ba.py).  Tolerance 1e-4 on the poses: the device accumulates the per-pair sums in double, the
-reference in float.  (Named to run last: this path was written after the round's GPU budget was spent, so the driver's
-round-end run is its first time on a B200 -- the kernel and the host half are covered on the CPU by tests/test_ba_cpu.py.)"""
+reference in float.  (The kernel and the host half are also covered on the CPU by tests/test_ba_cpu.py.)"""
 import time
 
 import numpy as np
