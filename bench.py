@@ -117,7 +117,7 @@ WORKLOAD = ("config2: S2 room stream 640x480 (u16 depth, 307,200 points/frame), 
             "(frame k+1 -> frame k, analytic target normals, 30 iterations, threshold 0.05 m) then TSDF integration "
             "of the frame at 5 mm voxels with the ICP pose")
 WORKLOAD4 = ("config4: ONE S1 stream 1280x960 (f32 depth) fused by all ranks into a 2 mm volume partitioned by cube ownership "
-             "(slabs of 8 cubes along x, round-robin over the ranks; identity poses, truncation 0.1 m); every rank sees every "
+             "(slabs of 4 cubes along x, round-robin over the ranks; identity poses, truncation 0.1 m); every rank sees every "
              "frame and updates the cubes it owns, no data-path collective per frame; boundary-cube exchange + Marching Cubes "
              "at the end")
 
@@ -309,7 +309,7 @@ def bench_dense_odometry(frames, cam, device, steps, with_cpu):
 # up to the unpartitioned volume's.  world == 1 runs the same stream unpartitioned (the strong-scaling reference).
 # ----------------------------------------------------------------------------------------------------------
 VOXEL4 = 0.002
-SLAB4 = 8
+SLAB4 = 4   # cubes per slab: 8xB200 measured 6,015 / 6,648 / 6,600 frames/s with slabs of 8 / 4 / 2 (load balance against halo size)
 
 
 def bench_config4(local, rank, world, steps, warmup, reference_on_rank0: bool):
@@ -399,7 +399,7 @@ def bench_config4(local, rank, world, steps, warmup, reference_on_rank0: bool):
         # on the volume's stream between barriers, the second of two exchanges (the first maps the peer pages)
         n_ghost, halo_ms = 0, 0.0
         if collective and world > 1:
-            maps = fusion.attach_halo_peers(vol, rank, world, max(vol.NumCubes(), 1024), local)
+            maps = fusion.attach_halo_peers(vol, rank, world, max(2 * vol.NumCubes(), 1024), local)
             for rep in range(2):
                 vol.HaloClear()
                 barrier()

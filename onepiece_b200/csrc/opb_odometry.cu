@@ -280,6 +280,42 @@ __device__ __forceinline__ bool resolve_accept(const int2 *cand, int s, int2 c)
     return acc;
 }
 
+// The same resolution by asynchronous pointer jumping (second persistent loop form).  accept(s) is the parity of the length of the
+// chain s -> parent(s) -> ... -> root, where parent(s) = t(s) when the loop above would step to it.  Every pixel publishes a word
+// {ancestor << 1 | parity of the path to that ancestor} (its parent first) and then repeatedly replaces it by its ancestor's word
+// composed with its own.  Any word ever stored for a pixel is a true statement about one of its ancestors, words are single 32-bit
+// stores written only by their owner, and an ancestor's index is smaller than its descendant's, so readers may see any mixture of
+// old and new words: the answer is the same, only the number of steps differs (logarithmic in the chain length when the
+// pixels of a chain advance together, instead of the 35-pixel average / 147-pixel maximum walks of the bench frames).
+constexpr unsigned int kJumpUnset = 0xFFFFFFFFu;
+__device__ __forceinline__ unsigned int chain_word(const int2 *cand, int s, int2 c)
+{
+    const int t = c.x;
+    if (t >= s) return (unsigned int)s << 1;
+    const int2 ct = cand[t];
+    if (ct.x < 0 || __int_as_float(ct.y) > __int_as_float(c.y)) return (unsigned int)s << 1;
+    return ((unsigned int)t << 1) | 1u;
+}
+__device__ __forceinline__ bool resolve_accept_jumping(const int2 *cand, unsigned int *jump, int s, int2 c)
+{
+    if (c.x < 0) return false;
+    unsigned int w = chain_word(cand, s, c);
+    __stcg(&jump[s], w);
+    unsigned int a = w >> 1, p = w & 1u;
+    if (a == (unsigned int)s) return true;
+    for (;;)
+    {
+        unsigned int wa = __ldcg(&jump[a]);
+        if (wa == kJumpUnset) wa = chain_word(cand, (int)a, cand[a]); // its owner has not got there yet
+        const unsigned int a2 = wa >> 1;
+        if (a2 == a) break; // a is a root
+        p ^= wa & 1u;
+        a = a2;
+        __stcg(&jump[s], (a << 1) | p);
+    }
+    return p == 0u;
+}
+
 __device__ __forceinline__ double warp_sum_d(double v)
 {
 #pragma unroll
@@ -675,6 +711,7 @@ struct OdoLoop2Args
     int levels;
     int list_level;       // iterations of this level write a.cand / a.accepted (the compaction after the loop reads them)
     double *partials;     // [2][gridDim.x][64]
+    unsigned int *jump;   // per pixel: chain word of resolve_accept_jumping
     unsigned int *sync;   // arrivals, monotonic over the launch
 };
 template <int TERM>
@@ -722,7 +759,11 @@ __global__ void __launch_bounds__(kOdo2Threads, 1) odo_loop2_kernel(const __grid
             for (int trip = first_trip; trip < n_trips; trip += trip_step)
             {
                 const int s = trip * 32 + lane;
-                if (s < n) cand[s] = candidate_of(sd, td, sh.M, w, h, s);
+                if (s < n)
+                {
+                    cand[s] = candidate_of(sd, td, sh.M, w, h, s);
+                    __stcg(&L.jump[s], kJumpUnset);
+                }
             }
             __threadfence();
             __syncthreads();
@@ -747,7 +788,7 @@ __global__ void __launch_bounds__(kOdo2Threads, 1) odo_loop2_kernel(const __grid
                 if (s < n)
                 {
                     const int2 c = cand[s];
-                    ok = resolve_accept(cand, s, c); // AddElementToCorrespondenceMap, resolved along the chain
+                    ok = resolve_accept_jumping(cand, L.jump, s, c); // AddElementToCorrespondenceMap, resolved along the chain
                     if (lists) L.base.accepted[s] = ok;
                     if (ok) rows = compute_rows<TERM>(sh.ctx, sh.T, s, c.x, J, res);
                 }
@@ -1251,6 +1292,7 @@ struct opb_odometry
     int loop_form = -1;             // opb_odometry_set_loop_form: -1 default (OPB_ODO_PERSISTENT, else 1)
     bool loop2_ok = false;          // odo_loop2_kernel (one CTA of 1024 threads per SM) can be launched cooperatively
     double *d_partials2 = nullptr;  // its per-CTA 8x8 partials, two generations
+    unsigned int *d_jump = nullptr; // ... and its per-pixel chain words
     bool profiling = false;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     float last_ms = 0;
@@ -1316,7 +1358,7 @@ void opb_odometry_destroy(opb_odometry *o)
     cudaSetDevice(o->device);
     if (o->stream) cudaStreamSynchronize(o->stream);
     cudaFree(o->d_cand); cudaFree(o->d_accepted); cudaFree(o->d_partials); cudaFree(o->d_tiles); cudaFree(o->d_pairs);
-    cudaFree(o->d_corr_xyz); cudaFree(o->d_identity); cudaFree(o->d_tmp); cudaFree(o->d_state); cudaFree(o->d_sync); cudaFree(o->d_partials2); cudaFree(o->d_vals); cudaFree(o->d_mean_totals);
+    cudaFree(o->d_corr_xyz); cudaFree(o->d_identity); cudaFree(o->d_tmp); cudaFree(o->d_state); cudaFree(o->d_sync); cudaFree(o->d_partials2); cudaFree(o->d_jump); cudaFree(o->d_vals); cudaFree(o->d_mean_totals);
     if (o->h_state) cudaFreeHost(o->h_state);
     for (int i = 0; i < 2; ++i) if (o->ev[i]) cudaEventDestroy(o->ev[i]);
     if (o->own_stream && o->stream) cudaStreamDestroy(o->stream);
@@ -1381,7 +1423,8 @@ int opb_odometry_create(const opb_odometry_desc *desc, opb_odometry **out)
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], odo_loop2_kernel<1>, kOdo2Threads, 0) == cudaSuccess &&
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], odo_loop2_kernel<2>, kOdo2Threads, 0) == cudaSuccess &&
             occ[0] > 0 && occ[1] > 0 && occ[2] > 0 &&
-            cudaMalloc(&o->d_partials2, (size_t)2 * o->sm_count * 64 * sizeof(double)) == cudaSuccess)
+            cudaMalloc(&o->d_partials2, (size_t)2 * o->sm_count * 64 * sizeof(double)) == cudaSuccess &&
+            cudaMalloc(&o->d_jump, n * sizeof(unsigned int)) == cudaSuccess)
             o->loop2_ok = true;
         cudaGetLastError();
     }
@@ -1624,6 +1667,7 @@ static int run_tracking(opb_odometry *o, opb_frame *S, opb_frame *T, int term, o
         L.levels = o->desc.levels;
         L.list_level = last_level;
         L.partials = o->d_partials2;
+        L.jump = o->d_jump;
         L.sync = o->d_sync;
         OPB_CUDA(cudaMemsetAsync(o->d_sync, 0, 4 * sizeof(unsigned int), s));
         void *kargs[] = {(void *)&L};
