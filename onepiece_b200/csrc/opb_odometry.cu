@@ -316,6 +316,43 @@ __device__ __forceinline__ bool resolve_accept_jumping(const int2 *cand, unsigne
     return p == 0u;
 }
 
+// ... without a candidate list at all: a pixel's candidate is a pure function of the pixel and the pose (candidate_of), so the
+// first link of a pixel, and the word of an ancestor whose owner has not published yet, are computed on the spot.  Nothing a
+// pixel reads then depends on another thread having got anywhere: no grid barrier between candidates and acceptance.
+struct CandFn
+{
+    const float *sd, *td, *M;
+    int w, h;
+    __device__ __forceinline__ int2 operator()(int s) const { return candidate_of(sd, td, M, w, h, s); }
+};
+__device__ __forceinline__ unsigned int chain_word_lazy(const CandFn &f, int s, int2 c)
+{
+    const int t = c.x;
+    if (t >= s) return (unsigned int)s << 1;
+    const int2 ct = f(t);
+    if (ct.x < 0 || __int_as_float(ct.y) > __int_as_float(c.y)) return (unsigned int)s << 1;
+    return ((unsigned int)t << 1) | 1u;
+}
+__device__ __forceinline__ bool resolve_accept_lazy(const CandFn &f, unsigned int *jump, int s, int2 c)
+{
+    if (c.x < 0) return false;
+    unsigned int w = chain_word_lazy(f, s, c);
+    __stcg(&jump[s], w);
+    unsigned int a = w >> 1, p = w & 1u;
+    if (a == (unsigned int)s) return true;
+    for (;;)
+    {
+        unsigned int wa = __ldcg(&jump[a]);
+        if (wa == kJumpUnset) wa = chain_word_lazy(f, (int)a, f((int)a)); // its owner has not got there yet
+        const unsigned int a2 = wa >> 1;
+        if (a2 == a) break; // a is a root
+        p ^= wa & 1u;
+        a = a2;
+        __stcg(&jump[s], (a << 1) | p);
+    }
+    return p == 0u;
+}
+
 __device__ __forceinline__ double warp_sum_d(double v)
 {
 #pragma unroll
@@ -648,13 +685,15 @@ __global__ void __launch_bounds__(kOdoThreads, 2) odo_loop_kernel(OdoLoopArgs L)
 // (profiles/r02_odo_loop_kernel_ncu_full_before.md, opb_odometry_last_phases): 1.4 us candidates, 1.5 us grid barrier, 6 us in which
 // every thread keeps 29 double sums and a warp folds them with 290 shuffles, 10 us in which 295 CTAs wait for one CTA to sum 296
 // partials and for one of its threads to solve.  This form removes the per-thread sums and the serial owner:
-//   * (measured and dropped: recomputing the candidates of the pixels an acceptance chain visits instead of reading the list,
-//     which would remove the mid-iteration barrier -- the chains are long, 35 pixels on average and up to 150 on the bench
-//     frames, and two dependent loads plus the projection per step cost more than the barrier: 0.58 ms per call against 0.55);
+//   * (measured and dropped on the way: WALKING the chains over recomputed candidates instead of the list -- the chains are 35
+//     pixels long on average and up to 150 on the bench frames, and two dependent loads plus the projection per step cost more
+//     than the barrier that goes away: 0.58 ms per call against 0.55; pointer jumping needs the recomputation only for first links);
 //   * the sums are an 8x8 outer-product accumulation on the FP64 tensor-core op (warp_fold_outer8): a Jacobian row contributes
 //     c c^T with c = (J0..J5, r, 1) -- J^T J, J^T r, r^2 and the count are entries of that matrix; the hybrid term's second row
 //     goes in with c = (J0..J5, r, 0).  Products of floats are exact in double, which is also what the separate-launch kernels and
 //     the oracle sum: the forms differ only in the order of the double additions (~1e-16 relative);
+//   * candidates are not listed at all: a pixel's candidate is recomputed where a chain needs it, and the chains are resolved by
+//     asynchronous pointer jumping (resolve_accept_lazy), so the grid barrier between candidates and acceptance is gone;
 //   * one CTA of 1024 threads per SM publishes its 8x8 partial, announces it on one counter, waits until all have, and then EVERY
 //     CTA sums all partials in the same fixed order and solves the same 6x6 system: nobody waits for an owner, the pose lives
 //     in shared memory, the result is deterministic and identical on all CTAs (CTA 0 records the trace).
@@ -711,7 +750,8 @@ struct OdoLoop2Args
     int levels;
     int list_level;       // iterations of this level write a.cand / a.accepted (the compaction after the loop reads them)
     double *partials;     // [2][gridDim.x][64]
-    unsigned int *jump;   // per pixel: chain word of resolve_accept_jumping
+    unsigned int *jump;   // [2][jump_stride]: per pixel chain words of resolve_accept_lazy, two generations (this iteration's, the next one's)
+    unsigned int jump_stride;
     unsigned int *sync;   // arrivals, monotonic over the launch
 };
 template <int TERM>
@@ -754,29 +794,9 @@ __global__ void __launch_bounds__(kOdo2Threads, 1) odo_loop2_kernel(const __grid
             if (stamp) sh.t[0] = timer_ns();
             if (threadIdx.x == 0) warp_matrices(cam, sh.T, sh.M, sh.M + 9);
             __syncthreads();
-            // ---- candidates of every pixel (a pure function of the pixel and the pose), then a grid barrier: the acceptance chain
-            //      of a pixel reads the candidates of the pixels it visits ----
-            for (int trip = first_trip; trip < n_trips; trip += trip_step)
-            {
-                const int s = trip * 32 + lane;
-                if (s < n)
-                {
-                    cand[s] = candidate_of(sd, td, sh.M, w, h, s);
-                    __stcg(&L.jump[s], kJumpUnset);
-                }
-            }
-            __threadfence();
-            __syncthreads();
-            ++n_sync;
-            if (threadIdx.x == 0)
-            {
-                atomicAdd(L.sync, 1u);
-                const unsigned int want = n_sync * (unsigned int)n_cta;
-                while (*(volatile unsigned int *)L.sync < want) { }
-                __threadfence();
-            }
-            __syncthreads();
-            if (stamp) sh.t[1] = timer_ns();
+            // ---- one phase: candidate, acceptance (pointer jumping over lazily computed chains), Jacobian rows, fold ----
+            unsigned int *jump = L.jump + (size_t)(sh.iteration & 1) * L.jump_stride;
+            const CandFn candfn = {sd, td, sh.M, w, h};
             double c0 = 0.0, c1 = 0.0;
             float *stage = sh.u.stage[warp];
             for (int trip = first_trip; trip < n_trips; trip += trip_step)
@@ -787,8 +807,9 @@ __global__ void __launch_bounds__(kOdo2Threads, 1) odo_loop2_kernel(const __grid
                 bool ok = false;
                 if (s < n)
                 {
-                    const int2 c = cand[s];
-                    ok = resolve_accept_jumping(cand, L.jump, s, c); // AddElementToCorrespondenceMap, resolved along the chain
+                    const int2 c = candfn(s);
+                    if (lists) cand[s] = c;
+                    ok = resolve_accept_lazy(candfn, jump, s, c); // AddElementToCorrespondenceMap, resolved along the chain
                     if (lists) L.base.accepted[s] = ok;
                     if (ok) rows = compute_rows<TERM>(sh.ctx, sh.T, s, c.x, J, res);
                 }
@@ -807,7 +828,12 @@ __global__ void __launch_bounds__(kOdo2Threads, 1) odo_loop2_kernel(const __grid
                     warp_fold_outer8(stage, lane, comp, c0, c1);
                 }
             }
-            if (stamp) sh.t[2] = timer_ns();
+            {   // the words of the NEXT iteration start out unset (its level may have four times the pixels: clear the whole buffer)
+                unsigned int *jump_next = L.jump + (size_t)((sh.iteration + 1) & 1) * L.jump_stride;
+                for (unsigned int i = blockIdx.x * kOdo2Threads + threadIdx.x; i < L.jump_stride; i += gridDim.x * kOdo2Threads)
+                    __stcg(&jump_next[i], kJumpUnset);
+            }
+            if (stamp) sh.t[1] = sh.t[2] = timer_ns();
             // ---- CTA partial ----
             __syncthreads(); // every warp is done with its staging area (aliased below)
             *reinterpret_cast<double2 *>(&sh.u.wsum[warp][2 * lane]) = make_double2(c0, c1);
@@ -901,7 +927,7 @@ __global__ void __launch_bounds__(kOdo2Threads, 1) odo_loop2_kernel(const __grid
             if (stamp)
             {
                 sh.t[5] = timer_ns();
-                // candidates + barrier | acceptance + rows | publish + barrier + sum of partials | solve
+                // candidates, acceptance, rows | (unused) | publish + barrier + sum of partials | solve
                 sh.ph[0] += sh.t[1] - sh.t[0]; sh.ph[1] += sh.t[2] - sh.t[1]; sh.ph[2] += sh.t[4] - sh.t[2]; sh.ph[3] += sh.t[5] - sh.t[4];
             }
         }
@@ -1424,7 +1450,7 @@ int opb_odometry_create(const opb_odometry_desc *desc, opb_odometry **out)
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], odo_loop2_kernel<2>, kOdo2Threads, 0) == cudaSuccess &&
             occ[0] > 0 && occ[1] > 0 && occ[2] > 0 &&
             cudaMalloc(&o->d_partials2, (size_t)2 * o->sm_count * 64 * sizeof(double)) == cudaSuccess &&
-            cudaMalloc(&o->d_jump, n * sizeof(unsigned int)) == cudaSuccess)
+            cudaMalloc(&o->d_jump, 2 * n * sizeof(unsigned int)) == cudaSuccess)
             o->loop2_ok = true;
         cudaGetLastError();
     }
@@ -1668,6 +1694,8 @@ static int run_tracking(opb_odometry *o, opb_frame *S, opb_frame *T, int term, o
         L.list_level = last_level;
         L.partials = o->d_partials2;
         L.jump = o->d_jump;
+        L.jump_stride = (unsigned int)level_pixels(o, 0);
+        OPB_CUDA(cudaMemsetAsync(o->d_jump, 0xFF, (size_t)L.jump_stride * sizeof(unsigned int), s)); // generation 0 starts out unset
         L.sync = o->d_sync;
         OPB_CUDA(cudaMemsetAsync(o->d_sync, 0, 4 * sizeof(unsigned int), s));
         void *kargs[] = {(void *)&L};

@@ -21,7 +21,7 @@ from onepiece_b200 import capi
 ph = (C.c_uint64 * 4)()
 capi.check(capi.lib.opb_odometry_last_phases(odo.handle, ph))
 if os.environ.get("OPB_ODO_PERSISTENT", "1") == "1":
-    print("phases us (%d iterations): candidates+rows %.1f  publish+grid barrier %.1f  sum of partials %.1f  solve %.1f" % ((r.iterations,) + tuple(x / 1e3 for x in ph)))
+    print("phases us (%d iterations): candidates+acceptance+rows %.1f  (unused %.1f)  publish+barrier+sum %.1f  solve %.1f" % ((r.iterations,) + tuple(x / 1e3 for x in ph)))
 else:
     print("phases us (%d iterations): candidates %.1f  barrier %.1f  reduce %.1f  release-wait %.1f" % ((r.iterations,) + tuple(x / 1e3 for x in ph)))
 ms, tail = C.c_float(0), C.c_float(0)
