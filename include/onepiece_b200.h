@@ -451,6 +451,14 @@ int opb_kdtree_dump(opb_kdtree *t, int32_t *vind, int32_t *node_ints5, float *no
  * Afterwards opb_icp_point_to_plane / opb_icp_point_to_point are COLLECTIVE calls: every rank must make them in the same
  * order with its share of the source and identical target, init_T and params (a missing peer makes the call fail with
  * OPB_ERR_CUDA after 4 s instead of hanging).  A rank's share may be empty. */
+/* Pair list off the critical path.  A fusion loop needs the pose of a registration before it can integrate the frame, the inlier
+ * pairs (8 bytes per source point) only afterwards.  With async pairs on, a registration whose `pairs` buffer is page-locked host
+ * memory returns as soon as pose, rmse and counters are on the host; the list follows on the workspace's copy stream, under
+ * whatever the caller enqueues next, and is complete after opb_icp_wait_pairs (also implied by the next registration on the
+ * workspace).  The first n_local_pairs entries are the result, as in the synchronous call.  Off by default; ignored for pageable
+ * buffers and for workspaces that exchange packets with peer ranks. */
+int opb_icp_set_async_pairs(opb_icp *c, int on);
+int opb_icp_wait_pairs(opb_icp *c);
 /* Sizes the workspace for clouds of up to n_source / n_target points now instead of inside the first registration.  Device
  * allocation can wait for running kernels; a workspace that takes part in a split registration with a peer on the SAME device (a
  * peer's kernel spins until this workspace has launched its own) must not allocate in the middle of a collective call. */

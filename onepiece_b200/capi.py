@@ -181,6 +181,8 @@ SIGNATURES = {
     "opb_volume_integrate_cloud": (C.c_int, [_p, _p, _p]),
     "opb_icp_set_profiling": (C.c_int, [_p, C.c_int]),
     "opb_icp_reserve": (C.c_int, [_p, _sz, _sz]),
+    "opb_icp_set_async_pairs": (C.c_int, [_p, C.c_int]),
+    "opb_icp_wait_pairs": (C.c_int, [_p]),
     "opb_icp_last_timing": (C.c_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "opb_odometry_desc_default": (None, [C.POINTER(OdometryDesc)]),
     "opb_odometry_create": (C.c_int, [C.POINTER(OdometryDesc), C.POINTER(_p)]),

@@ -1784,6 +1784,9 @@ struct opb_icp
     // uploads that overlap the grid construction
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[3] = {nullptr, nullptr, nullptr};
+    // opb_icp_set_async_pairs: the call returns when pose and counters are on the host; the pair list follows on the copy stream
+    bool async_pairs = false, pairs_pending = false;
+    cudaEvent_t ev_pose = nullptr, ev_pairs_ready = nullptr, ev_pairs_done = nullptr;
     float last_build_ms = 0, last_iter_ms = 0;
 };
 
@@ -1900,6 +1903,9 @@ int opb_icp_create(int device, void *stream, opb_icp **out)
     if (e == cudaSuccess) e = cudaMalloc(&c->d_cell_start, ((size_t)kMaxCells + 2) * sizeof(unsigned int));
     for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
     for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_pose, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_pairs_ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_pairs_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess)
     {
@@ -1963,6 +1969,9 @@ void opb_icp_destroy(opb_icp *c)
     if (c->h_sums) cudaFreeHost(c->h_sums);
     for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 3; ++i) if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
+    if (c->ev_pose) cudaEventDestroy(c->ev_pose);
+    if (c->ev_pairs_ready) cudaEventDestroy(c->ev_pairs_ready);
+    if (c->ev_pairs_done) cudaEventDestroy(c->ev_pairs_done);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     cudaGetLastError();
@@ -2008,6 +2017,7 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     if (rc) return rc;
     cudaStream_t s = c->stream;
     const float *d_src = borrow ? src : c->d_src, *d_tgt = borrow ? tgt : c->d_tgt, *d_nrm = borrow ? nrm : c->d_nrm;
+    if (c->pairs_pending) { OPB_CUDA(cudaStreamWaitEvent(s, c->ev_pairs_done, 0)); c->pairs_pending = false; } // d_pairs is still being copied out
     if (ready_a) OPB_CUDA(cudaStreamWaitEvent(s, ready_a, 0));
     if (ready_b) OPB_CUDA(cudaStreamWaitEvent(s, ready_b, 0));
     // The target goes first on the work stream (the grid is built from it); the source and the normals follow on the copy
@@ -2118,6 +2128,7 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
         icp_final_reduce_kernel<<<1, kIcpThreads, 0, s>>>(c->d_partials, nb_a, c->d_state, c->comm);
         OPB_CUDA(cudaMemcpyAsync(c->h_sums, (const char *)c->d_state + offsetof(IcpState, packet), 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
+    OPB_CUDA(cudaEventRecord(c->ev_pose, s));
     const size_t n_copy = pairs && pairs_cap && ns ? (pairs_cap < ns ? pairs_cap : ns) : 0;
     bool pairs_direct = false;
     if (n_copy)
@@ -2134,13 +2145,24 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
         cudaPointerAttributes attr;
         pairs_direct = cudaPointerGetAttributes(&attr, pairs) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered;
         cudaGetLastError();
-        if (pairs_direct) OPB_CUDA(cudaMemcpyAsync(pairs, c->d_pairs, n_copy * 2 * sizeof(int), cudaMemcpyDefault, s));
+        const bool detached = pairs_direct && c->async_pairs && c->comm.world <= 1;
+        if (detached)
+        {   // the list leaves on the copy stream while the caller already works with the pose (opb_icp_wait_pairs collects it)
+            OPB_CUDA(cudaEventRecord(c->ev_pairs_ready, s));
+            OPB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_pairs_ready, 0));
+            OPB_CUDA(cudaMemcpyAsync(pairs, c->d_pairs, n_copy * 2 * sizeof(int), cudaMemcpyDefault, c->copy_stream));
+            OPB_CUDA(cudaEventRecord(c->ev_pairs_done, c->copy_stream));
+            c->pairs_pending = true;
+        }
+        else if (pairs_direct) OPB_CUDA(cudaMemcpyAsync(pairs, c->d_pairs, n_copy * 2 * sizeof(int), cudaMemcpyDefault, s));
     }
     if (c->profiling) OPB_CUDA(cudaEventRecord(c->ev[2], s));
     OPB_CUDA(cudaGetLastError());
-    OPB_CUDA(cudaStreamSynchronize(s));
+    if (c->pairs_pending) OPB_CUDA(cudaEventSynchronize(c->ev_pose)); // pose, counters and Kabsch sums are on the host
+    else OPB_CUDA(cudaStreamSynchronize(s));
     if (c->profiling)
     {
+        if (c->pairs_pending) cudaEventSynchronize(c->ev[2]);
         cudaEventElapsedTime(&c->last_build_ms, c->ev[0], c->ev[1]);
         cudaEventElapsedTime(&c->last_iter_ms, c->ev[1], c->ev[2]);
     }
@@ -2182,6 +2204,21 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     return OPB_OK;
 }
 
+int opb_icp_set_async_pairs(opb_icp *c, int on)
+{
+    if (!c) { set_error("icp is NULL"); return OPB_ERR_INVALID; }
+    c->async_pairs = on != 0;
+    return OPB_OK;
+}
+int opb_icp_wait_pairs(opb_icp *c)
+{
+    if (!c) { set_error("icp is NULL"); return OPB_ERR_INVALID; }
+    if (!c->pairs_pending) return OPB_OK;
+    OPB_CUDA(cudaSetDevice(c->device));
+    OPB_CUDA(cudaEventSynchronize(c->ev_pairs_done));
+    c->pairs_pending = false;
+    return OPB_OK;
+}
 int opb_icp_reserve(opb_icp *c, size_t n_source, size_t n_target)
 {
     if (!c) { set_error("icp is NULL"); return OPB_ERR_INVALID; }

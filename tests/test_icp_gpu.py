@@ -301,3 +301,41 @@ def test_exactly_equidistant_targets_resolve_to_a_nearest_neighbour_documented_t
         assert np.array_equal(d_all[np.arange(len(src)), ref[:, 1]], d_min), "the reference's choice is a nearest neighbour too"
         differ = int((ref[:, 1] != pairs[:, 1]).sum())
         print(f"exact 8-way ties: the reference's walk order and the lowest-index rule pick different (equidistant) targets for {differ} of {len(src)} queries")
+
+
+def test_pair_list_off_the_critical_path(g):
+    """opb_icp_set_async_pairs: the registration returns with pose and counters, the pair list lands in the caller's page-locked
+    buffer behind it and is complete after opb_icp_wait_pairs -- the same list, the same result, as the synchronous call; a
+    pageable buffer is filled inside the call as before."""
+    import ctypes as C
+
+    from onepiece_b200 import capi
+    src, tgt, nrm = np.ascontiguousarray(g["src"], np.float32), np.ascontiguousarray(g["tgt"], np.float32), np.ascontiguousarray(g["nrm"], np.float32)
+    want = reg.PointToPlane(reg.PointCloud(src), reg.PointCloud(tgt, nrm), np.eye(4), reg.ICPParameter(6, 0.04, 1.0))
+    ws = C.c_void_p()
+    capi.check(capi.lib.opb_icp_create(0, None, C.byref(ws)))
+    capi.check(capi.lib.opb_icp_set_async_pairs(ws, 1))
+    pinned = C.c_void_p()
+    capi.check(capi.lib.opb_host_alloc(C.byref(pinned), len(src) * 8))
+    try:
+        par, res = capi.IcpParams(6, 0.04, 1.0), capi.IcpResult()
+        T0 = np.ascontiguousarray(np.eye(4, dtype=np.float32)).reshape(16)
+        view = np.ctypeslib.as_array(C.cast(pinned, C.POINTER(C.c_int32)), shape=(len(src), 2))
+        for rep in range(3):  # back-to-back calls: the next registration waits for the previous list to have left the device buffer
+            view[:] = -7
+            capi.check(capi.lib.opb_icp_point_to_plane(ws, src.ctypes.data, len(src), tgt.ctypes.data, nrm.ctypes.data, len(tgt), T0.ctypes.data,
+                                                       C.byref(par), C.byref(res), pinned, len(src)))
+            assert np.array_equal(np.array(res.T[:], np.float32).reshape(4, 4).T, want.T) and res.rmse == want.rmse
+            assert res.n_local_pairs == len(want.correspondence_set_index)
+            if rep < 2:
+                capi.check(capi.lib.opb_icp_wait_pairs(ws))
+                assert np.array_equal(view[: res.n_local_pairs], want.correspondence_set_index)
+        capi.check(capi.lib.opb_icp_wait_pairs(ws))
+        assert np.array_equal(view[: res.n_local_pairs], want.correspondence_set_index)
+        pageable = np.full((len(src), 2), -7, np.int32)
+        capi.check(capi.lib.opb_icp_point_to_plane(ws, src.ctypes.data, len(src), tgt.ctypes.data, nrm.ctypes.data, len(tgt), T0.ctypes.data,
+                                                   C.byref(par), C.byref(res), pageable.ctypes.data, len(src)))
+        assert np.array_equal(pageable[: res.n_local_pairs], want.correspondence_set_index)  # complete on return
+    finally:
+        capi.lib.opb_host_free(pinned)
+        capi.lib.opb_icp_destroy(ws)
