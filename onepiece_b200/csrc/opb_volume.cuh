@@ -42,8 +42,6 @@ struct VolumeDev
     int *n_alloc;             // cubes allocated so far
     int *tainted;             // != 0 after an upload of values outside the range the fast quotient is exact for
     float2 *texels;           // per-frame W*H texels {depth in metres (f32), b | g<<8 | r<<16 as raw bits}
-    unsigned int *blk_lo, *blk_hi; // per 32x32-pixel block of the frame: min (stored complemented) / max valid depth as ordered uints, 0 = none
-    int blk_w, blk_h;
     FrameCounters *fc;        // counters of the frame in flight
     volatile int *host_flags; // mapped pinned host memory, sticky until the host clears it: [0] pool full, [1] ids out of range
     int max_cubes;
@@ -68,7 +66,6 @@ struct FrameParams
     double width_d, height_d;
     int shard_rank, shard_world, shard_axis, shard_slab;
     int exact_division; // host decision: pose / intrinsics outside the tame range -> IEEE-division path
-    int prune;          // host decision: the pose is rigid, so whole candidate cubes may be discarded by the block depth ranges
     int min_new_slot;   // > 0: list only cubes allocated by this very pass (slot >= min_new_slot) -- the re-run after the pool grew
 };
 constexpr int kOverflowPool = 1, kOverflowRange = 2;
