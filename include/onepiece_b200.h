@@ -205,6 +205,22 @@ int opb_volume_transform(opb_volume *src, const float trans_colmajor[16], int ne
  * reference prints "[Warning]::[MergeVoxelHash]::Voxel resolution is not identical." and returns).  Merge(another, trans)
  * (:168-177) is opb_volume_transform(another, trans, 0, ...) followed by this call.  Both volumes on one device. */
 int opb_volume_merge(opb_volume *dst, opb_volume *another);
+/* The reference's ORDER, for callers whose output depends on it.  The reference keeps its cubes in a std::unordered_map, emits the
+ * mesh cube by cube in that map's iteration order (CubeHandler.cpp:27-40) and creates the cubes of a resampled volume at their first
+ * touch while walking the source in that order (CubeHandler.h:198-241); TriangleMesh::ClusteringSimplify then averages vertices in
+ * arrival order, so the bytes of a written PLY depend on the sequence.  The block pool has no such order, so the caller supplies it:
+ *   opb_volume_extract_mesh_ordered  the mesh with the cubes taken in the given sequence (every cube of the volume exactly once; ids
+ *                                    as 3 x int32), cells inside a cube in GenerateMeshByCube's x / y / z nesting;
+ *   opb_volume_transform_ordered     opb_volume_transform plus, in *result_ids_in_order (malloc'ed, opb_free), the result's cubes in
+ *                                    the order the reference would have inserted them, given the source's cubes in the source map's
+ *                                    iteration order.
+ * onepiece_b200/cpp/Integration/CubeHandler.cpp keeps a mirror map of ids with the reference's insertion history to produce these
+ * sequences. */
+int opb_volume_extract_mesh_ordered(opb_volume *v, const int32_t *cube_ids, size_t n_ids, float **xyz, float **rgb, uint32_t **tri, size_t *nv,
+                                    size_t *nt);
+int opb_volume_transform_ordered(opb_volume *src, const float trans_colmajor[16], int nearest, float result_voxel_resolution,
+                                 int32_t result_max_cubes, const int32_t *src_ids_in_order, size_t n_src_ids, opb_volume **out,
+                                 int32_t **result_ids_in_order, size_t *n_result);
 /* the descriptor a volume currently runs with (e.g. of a transform result) */
 int opb_volume_get_desc(opb_volume *v, opb_volume_desc *out);
 

@@ -120,6 +120,8 @@ SIGNATURES = {
     "opb_volume_extract_mesh_clustered": (C.c_int, [_p, C.c_float, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_sz), C.POINTER(_sz)]),
     "opb_volume_transform": (C.c_int, [_p, _p, C.c_int, C.c_float, C.c_int32, C.POINTER(_p)]),
     "opb_volume_merge": (C.c_int, [_p, _p]),
+    "opb_volume_extract_mesh_ordered": (C.c_int, [_p, _p, _sz, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_sz), C.POINTER(_sz)]),
+    "opb_volume_transform_ordered": (C.c_int, [_p, _p, C.c_int, C.c_float, C.c_int32, _p, _sz, C.POINTER(_p), C.POINTER(_p), C.POINTER(_sz)]),
     "opb_volume_get_desc": (C.c_int, [_p, C.POINTER(VolumeDesc)]),
     "opb_volume_halo_export": (C.c_int, [_p, _p, _p, _sz, C.POINTER(_sz)]),
     "opb_volume_halo_import": (C.c_int, [_p, _p, _p, _sz]),

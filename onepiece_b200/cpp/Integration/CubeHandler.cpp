@@ -2,6 +2,7 @@
 // src/Integration/CubeHandler.{h,cpp}).
 #include "Integration/CubeHandler.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <fstream>
@@ -66,6 +67,55 @@ void CubeHandler::PushParams()
     FillDesc(d, camera, c_para, truncation, near, far, max_cubes, device);
     Check(opb_volume_set_params(volume, &d), "CubeHandler");
 }
+// ---- the mirror of the reference's cube map (see CubeHandler.h) ----
+void CubeHandler::NoteFrame()
+{
+    size_t n = 0;
+    if (volume && opb_volume_num_cubes(volume, &n) == OPB_OK && (frame_ends_.empty() ? n > ordered_cubes_ : n > frame_ends_.back())) frame_ends_.push_back(n);
+}
+void CubeHandler::SyncOrder() const
+{
+    EnsureVolume();
+    size_t n = 0;
+    if (opb_volume_num_cubes(volume, &n) != OPB_OK || n <= ordered_cubes_) { frame_ends_.clear(); return; }
+    std::vector<int32_t> ids(n * 3);
+    size_t cap = n;
+    if (!Check(opb_volume_download(volume, ids.data(), nullptr, &cap), "CubeHandler")) return;
+    if (frame_ends_.empty() || frame_ends_.back() < n) frame_ends_.push_back(n); // cubes of unknown history: treated as one frame
+    size_t from = ordered_cubes_;
+    for (size_t end : frame_ends_)
+    {
+        if (end <= from) continue;
+        // the cubes a frame creates enter the reference's map in PrepareCubes' loop nesting: i outermost, k innermost
+        std::vector<size_t> idx(end - from);
+        for (size_t q = 0; q < idx.size(); ++q) idx[q] = from + q;
+        std::sort(idx.begin(), idx.end(), [&](size_t a, size_t b) {
+            for (int c = 0; c < 3; ++c)
+                if (ids[3 * a + c] != ids[3 * b + c]) return ids[3 * a + c] < ids[3 * b + c];
+            return false;
+        });
+        for (size_t q : idx) order_[CubeID(ids[3 * q], ids[3 * q + 1], ids[3 * q + 2])] = 0;
+        from = end;
+    }
+    ordered_cubes_ = n;
+    frame_ends_.clear();
+}
+std::vector<int32_t> CubeHandler::IterationIds() const
+{
+    SyncOrder();
+    std::vector<int32_t> out;
+    out.reserve(order_.size() * 3);
+    for (auto it = order_.begin(); it != order_.end(); ++it)
+        for (int c = 0; c < 3; ++c) out.push_back(it->first(c));
+    return out;
+}
+void CubeHandler::AdoptOrder(const int32_t *ids, size_t n)
+{
+    order_.clear();
+    for (size_t q = 0; q < n; ++q) order_[CubeID(ids[3 * q], ids[3 * q + 1], ids[3 * q + 2])] = 0;
+    ordered_cubes_ = n;
+    frame_ends_.clear();
+}
 void CubeHandler::SetMaxCubes(int n) { max_cubes = n; }
 void CubeHandler::SetDevice(int dev) { device = dev; }
 // CubeHandler.h:36 (prints through CubePara::SetVoxelResolution like the reference)
@@ -74,7 +124,13 @@ void CubeHandler::SetTruncation(float trunc) { truncation = trunc; PushParams();
 void CubeHandler::SetCamera(const camera::PinholeCamera &_camera) { camera = _camera; PushParams(); } // :137
 void CubeHandler::SetFarPlane(float _far) { far = _far; PushParams(); }                            // :349
 void CubeHandler::SetNearPlane(float _near) { near = _near; PushParams(); }                        // :353
-void CubeHandler::Clear() { if (volume) Check(opb_volume_clear(volume), "Clear"); }                // :133
+void CubeHandler::Clear()                                                                        // :133
+{
+    if (volume) Check(opb_volume_clear(volume), "Clear");
+    order_.clear(); // (keeps its buckets, like cube_map.clear())
+    ordered_cubes_ = 0;
+    frame_ends_.clear();
+}
 
 // CubeHandler.cpp:197-210
 void CubeHandler::IntegrateImage(const cv::Mat &depth, const cv::Mat &rgb, const geometry::TransformationMatrix &pose)
@@ -84,6 +140,7 @@ void CubeHandler::IntegrateImage(const cv::Mat &depth, const cv::Mat &rgb, const
     PoseToArray(pose, p);
     int rc = opb_volume_integrate(volume, depth.data, DepthType(depth), rgb.data, p);
     Check(rc, "IntegrateImage");
+    NoteFrame();
 #if DEBUG_MODE
     opb_frame_stats st;
     if (opb_volume_frame_stats(volume, &st) == OPB_OK)
@@ -104,6 +161,7 @@ void CubeHandler::PrepareCubes(const cv::Mat &depth, const geometry::Transformat
     PoseToArray(pose, p);
     size_t n = 0;
     if (!Check(opb_volume_prepare_cubes(volume, depth.data, DepthType(depth), p, nullptr, &n), "PrepareCubes")) { cube_id_list.clear(); return; }
+    NoteFrame();
     std::vector<int32_t> ids(n * 3 + 3);
     Check(opb_volume_last_frame_cubes(volume, ids.data(), &n), "PrepareCubes");
     cube_id_list.clear();
@@ -127,7 +185,9 @@ void CubeHandler::ExtractTriangleMesh(geometry::TriangleMesh &mesh)
     float *xyz = nullptr, *rgb = nullptr;
     uint32_t *tri = nullptr;
     size_t nv = 0, nt = 0;
-    Check(opb_volume_extract_mesh(volume, &xyz, &rgb, &tri, &nv, &nt), "ExtractTriangleMesh");
+    // cube by cube in the iteration order of the reference's map (CubeHandler.cpp:27-40), cells in GenerateMeshByCube's nesting
+    const std::vector<int32_t> order = IterationIds();
+    Check(opb_volume_extract_mesh_ordered(volume, order.data(), order.size() / 3, &xyz, &rgb, &tri, &nv, &nt), "ExtractTriangleMesh");
     mesh.Reset();
     mesh.points.resize(nv);
     mesh.colors.resize(nv);
@@ -164,12 +224,20 @@ CubeMap CubeHandler::GetCubeMap()
     std::vector<int32_t> ids;
     std::vector<float> vox;
     Download(ids, vox);
+    // The copy iterates like the reference's map: same bucket count, keys inserted in REVERSE iteration order (a node goes to the
+    // front of its bucket, or of the whole list when the bucket is empty, so this rebuilds the list back to front).
+    SyncOrder();
+    std::unordered_map<CubeID, size_t, CubeHasher> slot_of;
+    for (size_t c = 0; c < ids.size() / 3; ++c) slot_of[CubeID(ids[3 * c], ids[3 * c + 1], ids[3 * c + 2])] = c;
+    std::vector<CubeID> seq;
+    for (auto it = order_.begin(); it != order_.end(); ++it) seq.push_back(it->first);
     CubeMap m;
-    for (size_t c = 0; c < ids.size() / 3; ++c)
+    m.rehash(order_.bucket_count());
+    for (size_t q = seq.size(); q-- > 0;)
     {
-        CubeID id(ids[3 * c], ids[3 * c + 1], ids[3 * c + 2]);
+        const CubeID &id = seq[q];
         VoxelCube cube(id);
-        const float *src = &vox[c * 512 * 5];
+        const float *src = &vox[slot_of[id] * 512 * 5];
         for (int j = 0; j < 512; ++j)
         {
             cube.voxels[j].sdf = src[5 * j];
@@ -200,6 +268,12 @@ void CubeHandler::SetCubeMap(const CubeMap &_cube_map)
         }
     }
     Check(opb_volume_upload(volume, ids.data(), vox.data(), _cube_map.size()), "SetCubeMap");
+    // cube_map = _cube_map: the copy iterates like the original (same buckets, same list)
+    order_.clear();
+    order_.rehash(_cube_map.bucket_count());
+    for (size_t q = ids.size() / 3; q-- > 0;) order_[CubeID(ids[3 * q], ids[3 * q + 1], ids[3 * q + 2])] = 0;
+    ordered_cubes_ = _cube_map.size();
+    frame_ends_.clear();
 }
 // CubeHandler.h:129-132
 bool CubeHandler::HasCube(const CubeID &cube_id) const
@@ -223,7 +297,12 @@ std::shared_ptr<geometry::PointCloud> CubeHandler::GetPointCloud() const
     Download(ids, vox);
     geometry::PointCloud pcd;
     const float cube_resolution = CUBE_SIZE * c_para.VoxelResolution;
-    for (size_t c = 0; c < ids.size() / 3; ++c)
+    SyncOrder();
+    std::unordered_map<CubeID, size_t, CubeHasher> slot_of;
+    for (size_t c = 0; c < ids.size() / 3; ++c) slot_of[CubeID(ids[3 * c], ids[3 * c + 1], ids[3 * c + 2])] = c;
+    for (auto it = order_.begin(); it != order_.end(); ++it) // the reference walks its map (CubeHandler.cpp:48)
+    {
+        const size_t c = slot_of[it->first];
         for (size_t x = 0; x != CUBE_SIZE; ++x)
             for (size_t y = 0; y != CUBE_SIZE; ++y)
                 for (size_t z = 0; z != CUBE_SIZE; ++z)
@@ -238,6 +317,7 @@ std::shared_ptr<geometry::PointCloud> CubeHandler::GetPointCloud() const
                         pcd.colors.push_back(geometry::Point3(f, f, f));
                     }
                 }
+    }
     return std::make_shared<geometry::PointCloud>(pcd);
 }
 // CubeHandler.h:242-298 (trilinear) and :299-338 (nearest).  Like the reference, Transform copies c_para into the result and
@@ -251,7 +331,13 @@ std::shared_ptr<CubeHandler> CubeHandler::Transform(const geometry::Transformati
     after_trans->c_para = c_para;
     float t[16];
     PoseToArray(trans, t);
-    Check(opb_volume_transform(volume, t, 0, after_trans->c_para.VoxelResolution, 0, &after_trans->volume), "Transform");
+    const std::vector<int32_t> order = IterationIds();
+    int32_t *created = nullptr;
+    size_t n_created = 0;
+    if (Check(opb_volume_transform_ordered(volume, t, 0, after_trans->c_para.VoxelResolution, 0, order.data(), order.size() / 3, &after_trans->volume,
+                                           &created, &n_created), "Transform"))
+        after_trans->AdoptOrder(created, n_created);
+    opb_free(created);
     opb_volume_desc d;
     if (after_trans->volume && opb_volume_get_desc(after_trans->volume, &d) == OPB_OK) after_trans->max_cubes = d.max_cubes;
     return after_trans;
@@ -263,7 +349,13 @@ std::shared_ptr<CubeHandler> CubeHandler::TransformNearest(const geometry::Trans
     after_trans->far = far; after_trans->near = near; after_trans->truncation = truncation; after_trans->device = device;
     float t[16];
     PoseToArray(trans, t);
-    Check(opb_volume_transform(volume, t, 1, after_trans->c_para.VoxelResolution, 0, &after_trans->volume), "TransformNearest");
+    const std::vector<int32_t> order = IterationIds();
+    int32_t *created = nullptr;
+    size_t n_created = 0;
+    if (Check(opb_volume_transform_ordered(volume, t, 1, after_trans->c_para.VoxelResolution, 0, order.data(), order.size() / 3, &after_trans->volume,
+                                           &created, &n_created), "TransformNearest"))
+        after_trans->AdoptOrder(created, n_created);
+    opb_free(created);
     opb_volume_desc d;
     if (after_trans->volume && opb_volume_get_desc(after_trans->volume, &d) == OPB_OK) after_trans->max_cubes = d.max_cubes;
     return after_trans;
@@ -278,7 +370,18 @@ void CubeHandler::Merge(const CubeHandler &another)
     }
     EnsureVolume();
     another.EnsureVolume();
-    Check(opb_volume_merge(volume, another.volume), "Merge");
+    SyncOrder();
+    const std::vector<int32_t> theirs = another.IterationIds();
+    if (!Check(opb_volume_merge(volume, another.volume), "Merge")) return;
+    // cubes this map did not have are inserted while walking the other map (CubeHandler.h:152-158)
+    for (size_t q = 0; q < theirs.size() / 3; ++q)
+    {
+        const CubeID id(theirs[3 * q], theirs[3 * q + 1], theirs[3 * q + 2]);
+        if (order_.find(id) == order_.end()) order_[id] = 0;
+    }
+    size_t n = 0;
+    if (opb_volume_num_cubes(volume, &n) == OPB_OK) ordered_cubes_ = n;
+    frame_ends_.clear();
 }
 // CubeHandler.h:168-177
 void CubeHandler::Merge(const CubeHandler &another, const geometry::TransformationMatrix &trans)

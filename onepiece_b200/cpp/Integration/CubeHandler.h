@@ -79,6 +79,20 @@ class CubeHandler
     void PushParams();
     void Download(std::vector<int32_t> &ids, std::vector<float> &voxels) const;
 
+    // The reference's ORDER.  Its cube_map is a std::unordered_map whose iteration order -- a function of the insertion history --
+    // decides the sequence of the extracted mesh, of the cubes a resampled volume creates, of the .cubes stream.  The block pool
+    // has no such order, so the class keeps a mirror of the KEYS with the same key type, hasher and insertion history (new cubes
+    // of a frame in PrepareCubes' i / j / k nesting, CubeHandler.cpp:163-191; resampled cubes at their first touch; merged cubes in
+    // the other map's order) and hands its iteration order to the library wherever the reference iterates its map.
+    typedef std::unordered_map<CubeID, int, CubeHasher> OrderMap;
+    void NoteFrame();                                   // the cubes created since the last note came from one PrepareCubes pass
+    void SyncOrder() const;                             // bring order_ up to date with the block pool
+    std::vector<int32_t> IterationIds() const;          // cube ids (3 ints each) in the reference's iteration order
+    void AdoptOrder(const int32_t *ids, size_t n);      // a fresh handler whose cubes were inserted in this sequence
+    mutable OrderMap order_;
+    mutable size_t ordered_cubes_ = 0;                  // pool cubes [0, ordered_cubes_) are in order_
+    mutable std::vector<size_t> frame_ends_;            // pool cube count after every frame since then
+
     camera::PinholeCamera camera;
     CubePara c_para;
     float truncation = 0.1f;

@@ -1897,7 +1897,7 @@ int opb_icp_create(int device, void *stream, opb_icp **out)
     else { OPB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     cudaError_t e = cudaMalloc(&c->d_state, sizeof(IcpState));
     if (e == cudaSuccess) e = cudaHostAlloc(&c->h_state, sizeof(IcpState), cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaHostAlloc(&c->h_sums, 16 * sizeof(double), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc(&c->h_sums, 17 * sizeof(double), cudaHostAllocDefault); // 16 sums + the mailbox error word
     if (e == cudaSuccess) e = cudaMalloc(&c->d_cell_count, ((size_t)kMaxCells + 1) * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_tile_sums, ((size_t)kMaxTiles + 1) * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_cell_start, ((size_t)kMaxCells + 2) * sizeof(unsigned int));
@@ -2168,8 +2168,12 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     }
     if (c->comm.world > 1)
     {
-        int err = 0;
-        OPB_CUDA(cudaMemcpy(&err, &c->d_mailbox->error, sizeof(int), cudaMemcpyDeviceToHost));
+        // (on the workspace's own stream, not the legacy stream: a command to the NULL stream is an implicit synchronisation point,
+        // and a peer workspace of the same process may have a kernel spinning on this workspace's next packet)
+        int *err_slot = (int *)(c->h_sums + 16);
+        OPB_CUDA(cudaMemcpyAsync(err_slot, &c->d_mailbox->error, sizeof(int), cudaMemcpyDeviceToHost, s));
+        OPB_CUDA(cudaStreamSynchronize(s));
+        const int err = *err_slot;
         if (err)
         {
             set_error("ICP packet exchange timed out: a peer rank did not make the matching call");
@@ -2198,7 +2202,8 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     if (n_copy && !pairs_direct)
     {
         const size_t n = res->n_local_pairs < pairs_cap ? res->n_local_pairs : pairs_cap;
-        OPB_CUDA(cudaMemcpy(pairs, c->d_pairs, n * 2 * sizeof(int), cudaMemcpyDeviceToHost));
+        OPB_CUDA(cudaMemcpyAsync(pairs, c->d_pairs, n * 2 * sizeof(int), cudaMemcpyDeviceToHost, s)); // the stream is idle: returns when copied
+        OPB_CUDA(cudaStreamSynchronize(s));
     }
     res->status = OPB_OK;
     return OPB_OK;

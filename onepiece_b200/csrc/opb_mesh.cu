@@ -109,18 +109,22 @@ __device__ __forceinline__ int block_scan_512(int v, McShared &sm, int *total)
     return base + inc - v;
 }
 
-__global__ void __launch_bounds__(512) mc_count_kernel(VolumeDev vol, int n_slots, unsigned int *cube_tris)
+// Emission order.  CTA b handles the cube order[b] (slot b without an order): the triangles of the mesh come cube by cube in that
+// sequence, and inside a cube cell by cell with x outermost and z innermost -- the nesting of GenerateMeshByCube's loops
+// (CubeHandler.cpp:75-79) -- so that a caller who supplies the iteration order of the reference's cube map gets the reference's mesh
+// triangle for triangle (opb_volume_extract_mesh_ordered).
+__global__ void __launch_bounds__(512) mc_count_kernel(VolumeDev vol, int n_slots, const int *order, unsigned int *cube_tris)
 {
     __shared__ McShared sm;
-    const int slot = blockIdx.x;
-    if (slot >= n_slots) return;
+    if ((int)blockIdx.x >= n_slots) return;
+    const int slot = order ? order[blockIdx.x] : (int)blockIdx.x;
     mc_stage(vol, slot, sm);
     const int t = threadIdx.x;
-    const int cs = mc_case(sm, t & 7, (t >> 3) & 7, t >> 6);
+    const int cs = mc_case(sm, t >> 6, (t >> 3) & 7, t & 7);
     const int ntri = cs < 0 ? 0 : kMcTriCount[cs];
     int total;
     block_scan_512(ntri, sm, &total);
-    if (t == 0) cube_tris[slot] = (unsigned int)total;
+    if (t == 0) cube_tris[blockIdx.x] = (unsigned int)total;
 }
 
 // in-place exclusive scan of n counts by one CTA of 1024 threads; writes the grand total to *total
@@ -166,21 +170,21 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(unsigned int *counts,
     if (threadIdx.x == 0) *total = carry;
 }
 
-__global__ void __launch_bounds__(512) mc_emit_kernel(VolumeDev vol, int n_slots, const unsigned int *cube_offsets, float res,
+__global__ void __launch_bounds__(512) mc_emit_kernel(VolumeDev vol, int n_slots, const int *order, const unsigned int *cube_offsets, float res,
                                                       float cube_res, float half_res, float *xyz, float *rgb)
 {
     __shared__ McShared sm;
-    const int slot = blockIdx.x;
-    if (slot >= n_slots) return;
+    if ((int)blockIdx.x >= n_slots) return;
+    const int slot = order ? order[blockIdx.x] : (int)blockIdx.x;
     mc_stage(vol, slot, sm);
     const int t = threadIdx.x;
-    const int x = t & 7, y = (t >> 3) & 7, z = t >> 6;
+    const int x = t >> 6, y = (t >> 3) & 7, z = t & 7;
     const int cs = mc_case(sm, x, y, z);
     const int ntri = cs < 0 ? 0 : kMcTriCount[cs];
     int total;
     const int off = block_scan_512(ntri, sm, &total);
     if (ntri == 0) return;
-    size_t out = ((size_t)cube_offsets[slot] + off) * 9; // floats: 3 vertices x 3
+    size_t out = ((size_t)cube_offsets[blockIdx.x] + off) * 9; // floats: 3 vertices x 3
     const unsigned long long row = kMcCases[cs];
     for (int k = 0; k < 3 * ntri; ++k)
     {
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(512) mc_emit_kernel(VolumeDev vol, int n_slots
     }
 }
 
-static int mesh_count(opb_volume *v, int *n_slots_out, unsigned int **d_counts_out, unsigned long long *n_tris)
+static int mesh_count(opb_volume *v, int *n_slots_out, unsigned int **d_counts_out, unsigned long long *n_tris, const int *d_order = nullptr)
 {
     size_t n = 0;
     int rc = opb_volume_num_cubes(v, &n);
@@ -240,7 +244,7 @@ static int mesh_count(opb_volume *v, int *n_slots_out, unsigned int **d_counts_o
     }
     unsigned long long *d_total = (unsigned long long *)v->mesh_scratch;
     unsigned int *d_counts = (unsigned int *)((char *)v->mesh_scratch + 16);
-    mc_count_kernel<<<(unsigned int)n, 512, 0, v->stream>>>(v->dev, (int)n, d_counts);
+    mc_count_kernel<<<(unsigned int)n, 512, 0, v->stream>>>(v->dev, (int)n, d_order, d_counts);
     scan_counts_kernel<<<1, 1024, 0, v->stream>>>(d_counts, (int)n, d_total);
     OPB_CUDA(cudaGetLastError());
     OPB_CUDA(cudaMemcpyAsync(n_tris, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, v->stream));
@@ -285,7 +289,7 @@ int opb_volume_extract_mesh_clustered(opb_volume *v, float grid_len, float **xyz
         return OPB_ERR_CUDA;
     }
     const float res = v->desc.voxel_resolution;
-    mc_emit_kernel<<<n_slots, 512, 0, v->stream>>>(v->dev, n_slots, d_counts, res, (float)kCube * res, res / 2, d_xyz, d_rgb);
+    mc_emit_kernel<<<n_slots, 512, 0, v->stream>>>(v->dev, n_slots, nullptr, d_counts, res, (float)kCube * res, res / 2, d_xyz, d_rgb);
     iota_kernel<<<v->sm_count * 8, 256, 0, v->stream>>>(d_tri, (size_t)tris * 3); // three fresh vertices per triangle
     float *r_p = nullptr, *r_c = nullptr;
     unsigned int *r_t = nullptr;
@@ -316,7 +320,7 @@ int opb_volume_count_mesh(opb_volume *v, size_t *nv, size_t *nt)
     return OPB_OK;
 }
 
-int opb_volume_extract_mesh(opb_volume *v, float **xyz, float **rgb, uint32_t **tri, size_t *nv, size_t *nt)
+static int extract_mesh_impl(opb_volume *v, const int *d_order, float **xyz, float **rgb, uint32_t **tri, size_t *nv, size_t *nt)
 {
     if (!v || !xyz || !rgb || !tri || !nv || !nt) { set_error("NULL argument"); return OPB_ERR_INVALID; }
     *xyz = *rgb = nullptr; *tri = nullptr; *nv = *nt = 0;
@@ -324,7 +328,7 @@ int opb_volume_extract_mesh(opb_volume *v, float **xyz, float **rgb, uint32_t **
     int n_slots;
     unsigned int *d_counts;
     unsigned long long tris;
-    int rc = mesh_count(v, &n_slots, &d_counts, &tris);
+    int rc = mesh_count(v, &n_slots, &d_counts, &tris, d_order);
     if (rc) return rc;
     if (tris == 0) return OPB_OK;
     if (tris > 0xFFFFFFFFull / 3) { set_error("mesh of %llu triangles exceeds 32-bit vertex indices", tris); return OPB_ERR_CAPACITY; }
@@ -338,7 +342,7 @@ int opb_volume_extract_mesh(opb_volume *v, float **xyz, float **rgb, uint32_t **
         return OPB_ERR_CUDA;
     }
     const float res = v->desc.voxel_resolution;
-    mc_emit_kernel<<<n_slots, 512, 0, v->stream>>>(v->dev, n_slots, d_counts, res, (float)kCube * res, res / 2, d_xyz, d_rgb);
+    mc_emit_kernel<<<n_slots, 512, 0, v->stream>>>(v->dev, n_slots, d_order, d_counts, res, (float)kCube * res, res / 2, d_xyz, d_rgb);
     float *h_xyz = (float *)malloc(nfl * sizeof(float)), *h_rgb = (float *)malloc(nfl * sizeof(float));
     uint32_t *h_tri = (uint32_t *)malloc((size_t)tris * 3 * sizeof(uint32_t));
     cudaError_t e = cudaGetLastError();
@@ -362,5 +366,55 @@ int opb_volume_extract_mesh(opb_volume *v, float **xyz, float **rgb, uint32_t **
     *nt = (size_t)tris;
     *nv = (size_t)tris * 3;
     return OPB_OK;
+}
+int opb_volume_extract_mesh(opb_volume *v, float **xyz, float **rgb, uint32_t **tri, size_t *nv, size_t *nt)
+{
+    return extract_mesh_impl(v, nullptr, xyz, rgb, tri, nv, nt);
+}
+
+// the cubes of the volume in the caller's sequence -> their slots (-1: no such cube)
+__global__ void ids_to_slots_kernel(VolumeDev vol, const int *ids, int n, int *slots, int *missing)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const int s = opb::table_find(vol, ids[3 * i], ids[3 * i + 1], ids[3 * i + 2]);
+        slots[i] = s;
+        if (s < 0 || s >= *vol.n_alloc) atomicAdd(missing, 1);
+    }
+}
+
+int opb_volume_extract_mesh_ordered(opb_volume *v, const int32_t *cube_ids, size_t n_ids, float **xyz, float **rgb, uint32_t **tri, size_t *nv,
+                                    size_t *nt)
+{
+    if (!v || !xyz || !rgb || !tri || !nv || !nt || (n_ids && !cube_ids)) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    *xyz = *rgb = nullptr; *tri = nullptr; *nv = *nt = 0;
+    OPB_CUDA(cudaSetDevice(v->desc.device));
+    size_t n = 0;
+    int rc = opb_volume_num_cubes(v, &n);
+    if (rc) return rc;
+    if (n_ids != n) { set_error("the cube sequence has %zu entries, the volume %zu cubes", n_ids, n); return OPB_ERR_INVALID; }
+    if (n == 0) return OPB_OK;
+    int *d_ids = nullptr;
+    OPB_CUDA(cudaMalloc(&d_ids, (n * 4 + 1) * sizeof(int))); // ids (3n), slots (n), missing (1)
+    int *d_slots = d_ids + 3 * n, *d_missing = d_slots + n;
+    cudaError_t e = cudaMemcpyAsync(d_ids, cube_ids, n * 3 * sizeof(int), cudaMemcpyHostToDevice, v->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_missing, 0, sizeof(int), v->stream);
+    int missing = 0;
+    if (e == cudaSuccess)
+    {
+        ids_to_slots_kernel<<<v->sm_count * 4, 256, 0, v->stream>>>(v->dev, d_ids, (int)n, d_slots, d_missing);
+        e = cudaMemcpyAsync(&missing, d_missing, sizeof(int), cudaMemcpyDeviceToHost, v->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(v->stream);
+    if (e != cudaSuccess || missing)
+    {
+        cudaFree(d_ids);
+        if (e != cudaSuccess) { set_error("mesh extraction failed: %s", cudaGetErrorString(e)); return OPB_ERR_CUDA; }
+        set_error("%d cubes of the sequence are not in the volume", missing);
+        return OPB_ERR_INVALID;
+    }
+    rc = extract_mesh_impl(v, d_slots, xyz, rgb, tri, nv, nt);
+    cudaFree(d_ids);
+    return rc;
 }
 } // extern "C"

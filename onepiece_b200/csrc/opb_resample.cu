@@ -19,7 +19,9 @@
 // on the result handler) uses CubePara's default VoxelResolution 0.01 whatever the source resolution is, while the sampling
 // pass (a member of the source handler) uses the source resolution.  The C-ABI takes the result resolution as an argument;
 // the drop-in class passes what the reference would use.
+#include <algorithm>
 #include <cstring>
+#include <vector>
 
 #include "../../include/onepiece_b200.h"
 #include "opb_host_math.h"
@@ -131,6 +133,49 @@ __global__ void __launch_bounds__(256) resample_alloc_kernel(VolumeDev src, int 
             // one lane per distinct cube of the warp performs the insert
             const unsigned int peers = __match_any_sync(0xffffffffu, ok ? key : kEmptyKey);
             if (ok && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) table_find_or_insert(dst, ci, cj, ck);
+        }
+    }
+}
+
+// The order in which the reference would have CREATED the cubes of the result (AddTransformedCube / AddTransformedCubeNearest,
+// CubeHandler.h:198-241: source cubes in the iteration order of the source's map, voxels 0..511, the eight neighbours 0..7, a cube is
+// inserted at its first touch).  rank[slot] = position of a source cube in that iteration; first_touch[result slot] = smallest
+// ((rank * 512 + voxel) * 8 + neighbour) that maps into the cube.
+__global__ void slot_ranks_kernel(VolumeDev src, const int *ids_in_order, int n, unsigned int *rank, int *missing)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const int s = table_find(src, ids_in_order[3 * i], ids_in_order[3 * i + 1], ids_in_order[3 * i + 2]);
+        if (s < 0 || s >= n) atomicAdd(missing, 1);
+        else rank[s] = (unsigned int)i;
+    }
+}
+__global__ void __launch_bounds__(256) resample_first_touch_kernel(VolumeDev src, int n_src, const unsigned int *rank, VolumeDev dst,
+                                                                   const __grid_constant__ ResampleParams p, unsigned long long *first_touch)
+{
+    const long long total = (long long)n_src * kCubeVoxels;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x)
+    {
+        const int slot = (int)(t >> 9), n = (int)(t & 511);
+        float gx, gy, gz, px, py, pz;
+        global_point(&src.slot_ids[3 * slot], n, p.alloc_res, gx, gy, gz);
+        transform_h(p.fwd, gx, gy, gz, px, py, pz);
+        if (!p.nearest)
+        {
+            const float half = fdiv(p.alloc_res, 2.0f);
+            px = fsub(px, half); py = fsub(py, half); pz = fsub(pz, half);
+        }
+        const int n0[3] = {voxel_coord(px, p.alloc_res), voxel_coord(py, p.alloc_res), voxel_coord(pz, p.alloc_res)};
+        const unsigned long long base_key = ((unsigned long long)rank[slot] * kCubeVoxels + (unsigned long long)n) * 8ull;
+        const int corners = p.nearest ? 1 : 8;
+        int last = -1;
+        for (int i = 0; i < corners; ++i)
+        {
+            const int ci = (n0[0] + (i & 1)) >> 3, cj = (n0[1] + ((i >> 1) & 1)) >> 3, ck = (n0[2] + (i >> 2)) >> 3;
+            const int d = table_find(dst, ci, cj, ck);
+            if (d < 0 || d == last) continue; // (the same cube as the neighbour before: its key is already smaller)
+            last = d;
+            if (base_key + i < first_touch[d]) atomicMin(&first_touch[d], base_key + (unsigned long long)i);
         }
     }
 }
@@ -278,6 +323,73 @@ int opb_volume_transform(opb_volume *src, const float trans_cm[16], int nearest,
         *out = r;
         return OPB_OK;
     }
+}
+
+int opb_volume_transform_ordered(opb_volume *src, const float trans_cm[16], int nearest, float result_voxel_resolution, int32_t result_max_cubes,
+                                 const int32_t *src_ids_in_order, size_t n_src_ids, opb_volume **out, int32_t **result_ids_in_order,
+                                 size_t *n_result)
+{
+    if (!src || !out || !result_ids_in_order || !n_result || (n_src_ids && !src_ids_in_order)) { set_error("NULL argument"); return OPB_ERR_INVALID; }
+    *result_ids_in_order = nullptr;
+    *n_result = 0;
+    size_t n_src = 0;
+    int rc = opb_volume_num_cubes(src, &n_src);
+    if (rc) return rc;
+    if (n_src_ids != n_src) { set_error("the cube sequence has %zu entries, the source volume %zu cubes", n_src_ids, n_src); return OPB_ERR_INVALID; }
+    rc = opb_volume_transform(src, trans_cm, nearest, result_voxel_resolution, result_max_cubes, out);
+    if (rc) return rc;
+    opb_volume *r = *out;
+    size_t n_dst = 0;
+    rc = opb_volume_num_cubes(r, &n_dst);
+    if (rc == OPB_OK && n_dst == 0) return OPB_OK;
+    auto fail = [&](int code) { opb_volume_destroy(r); *out = nullptr; return code; };
+    if (rc) return fail(rc);
+    ResampleParams p;
+    memcpy(p.fwd, trans_cm, sizeof(p.fwd));
+    hostmath::mat4_inverse_colmajor(trans_cm, p.inv);
+    p.res = src->desc.voxel_resolution;
+    p.alloc_res = r->desc.voxel_resolution;
+    p.nearest = nearest ? 1 : 0;
+    cudaStream_t s = r->stream;
+    int *d_ids = nullptr;
+    unsigned int *d_rank = nullptr;
+    unsigned long long *d_touch = nullptr;
+    int *d_missing = nullptr;
+    cudaError_t e = cudaMalloc(&d_ids, n_src * 3 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&d_rank, n_src * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&d_touch, n_dst * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&d_missing, sizeof(int));
+    std::vector<unsigned long long> touch(n_dst);
+    std::vector<int> ids(n_dst * 3);
+    int missing = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_ids, src_ids_in_order, n_src * 3 * sizeof(int), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_missing, 0, sizeof(int), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_touch, 0xFF, n_dst * sizeof(unsigned long long), s);
+    if (e == cudaSuccess)
+    {
+        slot_ranks_kernel<<<r->sm_count * 4, 256, 0, s>>>(src->dev, d_ids, (int)n_src, d_rank, d_missing);
+        const long long total = (long long)n_src * kCubeVoxels;
+        const int blocks = (int)((total + 255) / 256 < (long long)r->sm_count * 16 ? (total + 255) / 256 : (long long)r->sm_count * 16);
+        resample_first_touch_kernel<<<blocks, 256, 0, s>>>(src->dev, (int)n_src, d_rank, r->dev, p, d_touch);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&missing, d_missing, sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(touch.data(), d_touch, n_dst * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ids.data(), r->dev.slot_ids, n_dst * 3 * sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d_ids); cudaFree(d_rank); cudaFree(d_touch); cudaFree(d_missing);
+    if (e != cudaSuccess) { set_error("ordered transform failed: %s", cudaGetErrorString(e)); return fail(OPB_ERR_CUDA); }
+    if (missing) { set_error("%d cubes of the sequence are not in the source volume", missing); return fail(OPB_ERR_INVALID); }
+    std::vector<size_t> perm(n_dst);
+    for (size_t i = 0; i < n_dst; ++i) perm[i] = i;
+    std::sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return touch[a] < touch[b]; });
+    int32_t *o = (int32_t *)malloc(n_dst * 3 * sizeof(int32_t));
+    if (!o) { set_error("host allocation failed"); return fail(OPB_ERR_CAPACITY); }
+    for (size_t i = 0; i < n_dst; ++i)
+        for (int a = 0; a < 3; ++a) o[3 * i + a] = ids[3 * perm[i] + a];
+    *result_ids_in_order = o;
+    *n_result = n_dst;
+    return OPB_OK;
 }
 
 int opb_volume_merge(opb_volume *dst, opb_volume *other)

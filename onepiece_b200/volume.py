@@ -284,11 +284,18 @@ class CubeHandler:
         return n.value
 
     # -- Marching Cubes ---------------------------------------------------------------------------------
-    def ExtractTriangleMesh(self):
-        """CubeHandler::ExtractTriangleMesh -> (points [nv,3] f32, colors [nv,3] f32, triangles [nt,3] u32)."""
+    def ExtractTriangleMesh(self, cube_order=None):
+        """CubeHandler::ExtractTriangleMesh -> (points [nv,3] f32, colors [nv,3] f32, triangles [nt,3] u32).  cube_order (int32 [n,3],
+        every cube once): emit the cubes in that sequence -- e.g. the iteration order of the reference's cube map -- instead of
+        block-pool order (opb_volume_extract_mesh_ordered)."""
         xyz, rgb, tri = C.c_void_p(), C.c_void_p(), C.c_void_p()
         nv, nt = C.c_size_t(0), C.c_size_t(0)
-        capi.check(capi.lib.opb_volume_extract_mesh(self._h, C.byref(xyz), C.byref(rgb), C.byref(tri), C.byref(nv), C.byref(nt)))
+        if cube_order is None:
+            capi.check(capi.lib.opb_volume_extract_mesh(self._h, C.byref(xyz), C.byref(rgb), C.byref(tri), C.byref(nv), C.byref(nt)))
+        else:
+            order = np.ascontiguousarray(cube_order, np.int32).reshape(-1, 3)
+            capi.check(capi.lib.opb_volume_extract_mesh_ordered(self._h, _ptr(order), len(order), C.byref(xyz), C.byref(rgb), C.byref(tri),
+                                                                C.byref(nv), C.byref(nt)))
         n = nv.value
         if n == 0:
             return np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32)
