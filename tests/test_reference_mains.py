@@ -1,6 +1,6 @@
 """The reference's example mains compiled UNMODIFIED (tests/cpp/Makefile, target `mains`) twice -- against the drop-in C++
 classes over libonepiece_b200.so and against the reference's own translation units -- run on the same synthetic dataset;
-the meshes they write must be the same mesh (see `same_mesh`).  Only test stand-ins are added: a headless Visualizer, cv::imread
+ImageSequenceIntegration must write the same PLY byte for byte, DenseFusion the same mesh to a tolerance (see `same_mesh`).  Only test stand-ins are added: a headless Visualizer, cv::imread
 for raw image containers, the associate.txt / trajectory.txt readers (tests/cpp/mains/headless)."""
 import os
 import struct
