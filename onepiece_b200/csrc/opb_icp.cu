@@ -425,6 +425,7 @@ struct IcpArgs
     unsigned int *worklist; // ns
     float guard;            // extra radius every full search covers beyond its nearest neighbour, in grid cells
     int certify;            // 0: every pass searches every point (reference behaviour of the search, for A/B tests)
+    int seed_walks;         // 1: a full search starts from the previous pass's neighbour as its bound (same result, shorter walk)
     float unscale;          // ICPParameter::scaling: the closing pass divides the (scaled) coordinates by it again
 };
 
@@ -520,8 +521,11 @@ __device__ __forceinline__ float search_bound(float bd, float guard, float cap_g
 // settles the queries that sit on the bisector of two target points.  A query with no neighbour within the inlier radius has
 // none as long as it moved by less than (nearest distance seen or C) - inlier radius.  All budgets are shrunk by 1e-4
 // relative and 1 um absolute, orders of magnitude above the float rounding of the distance arithmetic they stand in for.
+// `seed_d2`: squared distance from the query to ANY point of this target cloud (the neighbour of the previous pass), +inf if none is
+// known.  It only tightens the radius the walk starts with -- the nearest point is at most that far, so everything within
+// sqrt(d1) + guard is still covered and the result, certificate included, is the one of the unseeded walk.
 __device__ NnResult grid_nearest(const IcpGrid &g, const unsigned int *__restrict__ cell_start, const float4 *__restrict__ sorted, float qx,
-                                 float qy, float qz, float radius, float guard)
+                                 float qy, float qz, float radius, float guard, float seed_d2 = HUGE_VALF)
 {
     NnResult out;
     out.index = out.index2 = -1;
@@ -544,7 +548,7 @@ __device__ NnResult grid_nearest(const IcpGrid &g, const unsigned int *__restric
     int xlo, xhi;
     scan_cells(g, cell_start, sorted, hx, hx, hy, hz, qx, qy, qz, nb);
     // ring 0: the rest of the home row
-    if (pr.interval(0, 0, search_bound(nb.d1, guard, cap_g2), xlo, xhi))
+    if (pr.interval(0, 0, search_bound(fminf(nb.d1, seed_d2), guard, cap_g2), xlo, xhi))
     {
         if (xlo < hx) scan_cells(g, cell_start, sorted, xlo, hx - 1, hy, hz, qx, qy, qz, nb);
         if (xhi > hx) scan_cells(g, cell_start, sorted, hx + 1, xhi, hy, hz, qx, qy, qz, nb);
@@ -556,7 +560,7 @@ __device__ NnResult grid_nearest(const IcpGrid &g, const unsigned int *__restric
     {
         // everything within `covered` cells has been seen once ring r-1 is complete
         const float covered = (float)(r - 1) + m_yz - pr.slack;
-        float eb = search_bound(nb.d1, guard, cap_g2);
+        float eb = search_bound(fminf(nb.d1, seed_d2), guard, cap_g2);
         if (covered > 0.0f && nb.i1 >= 0 && eb * pr.inv_h2 <= covered * covered) break;
         if (covered > radius_cells) break;
         if (r == 1)
@@ -580,7 +584,7 @@ __device__ NnResult grid_nearest(const IcpGrid &g, const unsigned int *__restric
                 if (pr.interval(dy, dz, eb, xlo, xhi))
                 {
                     scan_cells(g, cell_start, sorted, xlo, xhi, hy + dy, hz + dz, qx, qy, qz, nb);
-                    eb = search_bound(nb.d1, guard, cap_g2);
+                    eb = search_bound(fminf(nb.d1, seed_d2), guard, cap_g2);
                 }
             }
         }
@@ -591,7 +595,7 @@ __device__ NnResult grid_nearest(const IcpGrid &g, const unsigned int *__restric
                     if (pr.interval(dy, dz, eb, xlo, xhi))
                     {
                         scan_cells(g, cell_start, sorted, xlo, xhi, hy + dy, hz + dz, qx, qy, qz, nb);
-                        eb = search_bound(nb.d1, guard, cap_g2);
+                        eb = search_bound(fminf(nb.d1, seed_d2), guard, cap_g2);
                     }
         }
     }
@@ -1139,9 +1143,17 @@ struct Loop2Shared
 };
 
 // the exact search of one query, out of line (its registers stay out of the streaming loop); updates the certificate
-__device__ __noinline__ int loop2_search(const IcpArgs &a, const IcpGrid *g, float guard, int i, float px, float py, float pz, int keep_far)
+__device__ __noinline__ int loop2_search(const IcpArgs &a, const IcpGrid *g, float guard, int i, float px, float py, float pz, int keep_far, bool seeded)
 {
-    const NnResult r = grid_nearest(*g, a.cell_start, a.sorted, px, py, pz, a.search_radius, guard);
+    // from the second pass on the point's record holds the neighbour the previous search of THIS call found (pass 0 searches every
+    // point: the certificates start out invalid); its distance from where the query stands now bounds the walk from the start
+    float seed = __int_as_float(0x7f800000);
+    if (seeded)
+    {
+        const float4 p0 = a.rec[2 * i];
+        if (p0.x == p0.x) seed = dist2_nanoflann(px, py, pz, p0.x, p0.y, p0.z);
+    }
+    const NnResult r = grid_nearest(*g, a.cell_start, a.sorted, px, py, pz, a.search_radius, guard, seed);
     a.nn_ref[i] = make_int2(r.index, r.index2);
     a.qref[i] = make_float4(px, py, pz, a.certify ? r.budget : -1.0f);
     a.budget2[i] = a.certify ? r.budget2 : -1.0f;
@@ -1347,7 +1359,7 @@ __global__ void __launch_bounds__(kLoop2Threads, 1) icp_loop2_kernel(const __gri
                 if (!final_pass)
                 {
                     loop2_transform(T, rigid, sh.T, sx, sy, sz, px, py, pz);
-                    nn = loop2_search(a, &sh.grid, guard, i, px, py, pz, keep_far);
+                    nn = loop2_search(a, &sh.grid, guard, i, px, py, pz, keep_far, pass > 0 && a.seed_walks);
                     if (keep_far) a.nn[i] = nn;
                 }
                 else
@@ -2061,7 +2073,8 @@ static int icp_run(opb_icp *c, const float *src, size_t ns, const float *tgt, co
     a.qref = c->d_qref; a.nn_ref = c->d_nn_ref; a.worklist = c->d_worklist; a.budget2 = c->d_budget2; a.rec = c->d_rec;
     static const float k_guard = getenv("OPB_ICP_GUARD") ? (float)atof(getenv("OPB_ICP_GUARD")) : 0.125f;
     static const int k_certify = getenv("OPB_ICP_CERTIFY") ? atoi(getenv("OPB_ICP_CERTIFY")) : 1;
-    a.guard = k_guard; a.certify = k_certify; a.unscale = scaling;
+    static const int k_seed = getenv("OPB_ICP_SEED") ? atoi(getenv("OPB_ICP_SEED")) : 1;
+    a.guard = k_guard; a.certify = k_certify; a.seed_walks = k_seed; a.unscale = scaling;
     if (ns) OPB_CUDA(cudaMemsetAsync(c->d_qref, 0xFF, ns * sizeof(float4), s));
     if (ns) OPB_CUDA(cudaMemsetAsync(c->d_nn, 0xFF, ns * sizeof(int), s)); // corresponding_index(n, -1) (ICP.cpp:58,174)
     const int nb_need = ns ? (int)((ns + kIcpThreads - 1) / kIcpThreads) : 1; // an empty share still takes part in the exchange
