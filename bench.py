@@ -61,17 +61,62 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread every 2 ms (the driver times
+    as few as 20 steps, 16 ms -- too short for an nvidia-smi process to answer once); nvidia-smi -lms as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index: int):
         self.index = index
         self.proc = None
         self.lines = []
+        self.nvml = None          # (module, handle) when NVML answers
+        self.samples = []         # (sm MHz, reasons bitmask)
+        self.max_mhz = None
+        self.halt = threading.Event()
+        self.thread = None
+
+    def _nvml_handle(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(self.index).uuid)
+            try:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except TypeError:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            phys = int(ids[self.index]) if self.index < len(ids) and ids[self.index].isdigit() else self.index
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+
+    def _poll(self):
+        nv, h = self.nvml
+        while not self.halt.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    why = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    why = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((float(mhz), int(why)))
+            except Exception:
+                break
+            self.halt.wait(0.002)
 
     def start(self):
+        try:
+            self.nvml = self._nvml_handle()
+            self.max_mhz = float(self.nvml[0].nvmlDeviceGetMaxClockInfo(self.nvml[1], self.nvml[0].NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -86,8 +131,17 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml:
+            self.halt.set()
+            self.thread.join(timeout=2)
+            sm = [m for m, _ in self.samples]
+            bits = 0
+            for _, w in self.samples:
+                bits |= w
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                    "reasons": sorted(n for b, n in self.REASONS if bits & b), "source": "NVML, every 2 ms inside the timed region"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["neither NVML nor nvidia-smi available"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -107,7 +161,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 N_TRAJ = 9  # frames 0..8 of the S2 trajectory; step s registers frame k+1 against frame k, k = s mod 8
