@@ -55,3 +55,30 @@ def test_roofline_traffic_comes_from_a_committed_capture():
     assert source and os.path.exists(os.path.join(ROOT, source)) and source.startswith("profiles/")
     assert 4e8 < traffic < 7e8          # read + write of the bench frame's updated voxels
     assert bench.measured_traffic("no_such_kernel") == (None, None)
+
+
+def test_clock_sampler_says_why_when_no_gpu_answers():
+    """NVML first (fast enough for a 16 ms timed region), nvidia-smi second; with neither the line carries the reason, not a crash"""
+    sys.path.insert(0, ROOT)
+    import bench
+    s = bench.ClockSampler(0)
+    s.start()
+    c = s.stop()
+    assert set(c) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    if c["sm_mhz"] is None:
+        assert c.get("samples", 0) == 0
+    else:
+        assert c["samples"] >= 1 and c["sm_mhz"] <= c["sm_max_mhz"] + 1
+
+
+def test_committed_bench_line_carries_the_contract_keys():
+    """profiles/r02_bench_ours.json is the line the final tree printed on the B200"""
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_ours.json")))
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in d, key
+    assert d["roofline"]["bound"] == "hbm" and 0 < d["roofline"]["frac"] < 1 and d["roofline"]["traffic"]
+    assert abs(d["roofline"]["achieved"] / d["roofline"]["peak"] - d["roofline"]["frac"]) < 1e-9
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] < d["value"]
+    assert d["clocks"]["samples"] >= 1 and d["clocks"]["reasons"] == [] and d["gpu_launches"] > 0
+    assert d["parity_check"]["ok"] is True
