@@ -61,7 +61,7 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread every 2 ms (the driver times
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread, every 2 ms at first (the driver times
     as few as 20 steps, 16 ms -- too short for an nvidia-smi process to answer once); nvidia-smi -lms as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -106,7 +106,7 @@ class ClockSampler:
                 self.samples.append((float(mhz), int(why)))
             except Exception:
                 break
-            self.halt.wait(0.002)
+            self.halt.wait(0.002 if len(self.samples) < 25 else 0.02)  # dense over a short region, sparse over a long one
 
     def start(self):
         try:
@@ -139,7 +139,7 @@ class ClockSampler:
             for _, w in self.samples:
                 bits |= w
             return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
-                    "reasons": sorted(n for b, n in self.REASONS if bits & b), "source": "NVML, every 2 ms inside the timed region"}
+                    "reasons": sorted(n for b, n in self.REASONS if bits & b), "source": "NVML polled inside the timed region (every 2 ms for the first 25 samples, then every 20 ms)"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["neither NVML nor nvidia-smi available"]}
         self.proc.terminate()
